@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- reads aligned/s and GCUPS of the TREAT alignment hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (NewFragment + NewAlignment for every read: 48-byte records
++ 2-bit traceback ops) over one batch of synthetic RPS12-shaped reads per GPU (SURVEY.md 8d,
+BASELINE.json configs[2]; weak scaling: every rank aligns its own --reads reads, no data-path
+collective, one all-reduce of the summary counters per step).
+
+One JSON line on rank 0:
+  value      whole-job reads/s with the raw reads already resident in HBM (device-timed, max over ranks)
+  e2e        the same through treat_b200_align_batch with pinned HOST buffers (H2D + kernels + D2H)
+  roofline   k_align (the dominant kernel) against the INT32 ALU peak measured live on this GPU;
+             roofline_hbm gives the same launch against the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (a C port of the Go path; the Go reference cannot be built here)
+
+--impl reference times that CPU port with all host threads on bounded samples of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads_aligned_per_sec"
+UNIT = "reads/s"
+INT_OPS_PER_CELL = 8  # 1 compare/select, 3 adds, 2 max, 2 equality predicates
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--workload", default="rps12", choices=["rps12", "long"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_template(workload):
+    from treat_b200 import synth
+    if workload == "rps12":
+        return synth.rps12_template(), 0.0, synth.SEED_BASE + 3
+    return synth.long_template(300, 8), 0.2, synth.SEED_BASE + 5
+
+
+def workload_name(args, t):
+    return "synthetic-%s m=%d K=%d reads/gpu=%d (NewFragment+NewAlignment: records + traceback ops)" % (
+        args.workload, t.m, t.K, args.reads)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port) -- the only place outside tests/ and smoke() that executes oracle/
+# ---------------------------------------------------------------------------------------------
+def oracle_template(t):
+    from oracle import oracle as O
+    d = tempfile.mkdtemp(prefix="treat_bench_")
+    path = t.write_fasta(os.path.join(d, "tmpl.fa"))
+    return O, O.NewTemplateFromFasta(path, O.FORWARD, t.edit_base)
+
+
+def cpu_sample_rate(t, p_trunc, seed, n_reads, threads, repeats=1, first=0):
+    """reads/s of the CPU port (lean mode: one DP per read, record + ops) on n_reads reads."""
+    from treat_b200 import synth
+    O, om = oracle_template(t)
+    seqs, off, rc = synth.reads(t, n_reads, seed=seed, first=first, p_trunc=p_trunc)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        rec, _, _ = O.align_batch(om, seqs, off, rc, nthreads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    cells = float((rec["n_bases"].astype(np.int64) * t.m).sum())
+    return n_reads / best, cells / best / 1e9, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t, p_trunc, seed = make_template(args.workload)
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample or 4096 * threads
+    times, cells = [], 0.0
+    from treat_b200 import synth
+    O, om = oracle_template(t)
+    for s in range(args.warmup + args.steps):
+        seqs, off, rc = synth.reads(t, sample, seed=seed, first=s * sample, p_trunc=p_trunc)
+        t0 = time.perf_counter()
+        rec, _, _ = O.align_batch(om, seqs, off, rc, nthreads=threads)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+            cells += float((rec["n_bases"].astype(np.int64) * t.m).sum())
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "gcups": cells / total / 1e9,
+        "config": {"workload": workload_name(args, t), "sample_reads_per_step": sample,
+                   "note": "CPU port of the Go path (oracle/treat_oracle.c, full int64 score matrix + byte pointer "
+                           "matrix per read like nwalgo); the Go reference itself cannot be built here (no Go toolchain)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d reads per step x %d steps, lean mode (one DP per read, record + ops)" % (sample, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def pinned_array(nbytes):
+    from treat_b200 import cabi
+    p = C.c_void_p()
+    cabi.check(cabi.lib().treat_b200_host_alloc(C.byref(p), max(nbytes, 1)))
+    arr = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(p.value))
+    return arr, p
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import treat_b200 as T
+    from treat_b200 import cabi, parallel, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; treat_b200 has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    t, p_trunc, seed = make_template(args.workload)
+    with tempfile.TemporaryDirectory() as d:
+        tm = T.NewTemplateFromFasta(t.write_fasta(os.path.join(d, "tmpl.fa")), T.FORWARD, t.edit_base)
+    eng = T.Aligner(local)
+    eng.SetTemplate(tm)
+
+    N = args.reads
+    t0 = time.perf_counter()
+    hold = []
+
+    def alloc(nbytes):
+        arr, p = pinned_array(nbytes)
+        hold.append(p)
+        return arr
+    seqs, off, rc = synth.reads(t, N, seed=seed, first=rank * N, p_trunc=p_trunc, pinned_alloc=alloc)
+    lens = np.diff(off.astype(np.int64))
+    max_len = int(lens.max())
+    stride = eng.ops_stride(max_len)
+    h_rec_raw = alloc(N * 48)
+    h_ops_raw = alloc(N * stride)
+    h_rec = h_rec_raw.view(cabi.RECORD_DTYPE)
+    h_ops = h_ops_raw.reshape(N, stride)
+    h_off, h_rc = alloc((N + 1) * 8).view(np.uint64), alloc(N * 4).view(np.uint32)
+    h_off[:] = off
+    h_rc[:] = rc
+    log("[rank %d] generated %d reads (%.1f MB raw, max_len %d) in %.1fs" % (rank, N, len(seqs) / 1e6, max_len, time.perf_counter() - t0))
+
+    int_peak, _ = eng.measure_int32_peak()
+
+    # ---- device-resident inputs --------------------------------------------------------------
+    d_seqs = torch.from_numpy(np.ascontiguousarray(seqs)).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_rc = torch.from_numpy(rc.astype(np.int32)).to(dev)
+    d_rec = torch.empty(N * 48, dtype=torch.uint8, device=dev)
+    d_ops = torch.empty(N * stride, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sraw = stream.cuda_stream
+    flags = cabi.WANT_OPS
+    summ = parallel.summary_tensor(eng)
+
+    def step_device():
+        eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, flags,
+                               d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw)
+        red = summ.clone()
+        parallel.allreduce_summary(red)  # the only collective on the path: ~4 KB of uint64 counters
+        return red
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            tt = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return x
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+    rec_dev = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
+    cells_per_step = float((rec_dev["n_bases"].astype(np.int64) * t.m).sum())
+    value = world * N * args.steps / (dev_ms * 1e-3)
+
+    # ---- the dominant kernel alone (k_align on already-packed reads), CUDA events ----------------
+    pk = cabi.Packed()
+    cabi.check(cabi.lib().treat_b200_packed_layout(eng._ctx, N, max_len, 0, C.byref(pk)), eng._ctx)
+    d_n = torch.empty(N, dtype=torch.int16, device=dev)
+    d_fl = torch.empty(N, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(N * pk.bases_stride, dtype=torch.uint8, device=dev)
+    d_c = torch.empty(N * pk.counts_stride, dtype=torch.uint8, device=dev)
+    d_rl = torch.empty(N, dtype=torch.int32, device=dev)
+    pk.d_n, pk.d_flags, pk.d_bases, pk.d_counts, pk.d_raw_len = (d_n.data_ptr(), d_fl.data_ptr(), d_b.data_ptr(),
+                                                                 d_c.data_ptr(), d_rl.data_ptr())
+    cabi.check(cabi.lib().treat_b200_pack_device(eng._ctx, d_seqs.data_ptr(), d_off.data_ptr(), C.byref(pk), sraw), eng._ctx)
+    torch.cuda.synchronize()
+    max_n = int(d_n.max().item())
+    pk.max_len = max_n  # size the align launch for the longest stripped read, as the batch entry point does
+
+    def kernel_ms(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    pk_full = cabi.Packed()
+    C.memmove(C.byref(pk_full), C.byref(pk), C.sizeof(pk))
+    pk_full.max_len = max_len
+    align_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_align_packed_device(
+        eng._ctx, C.byref(pk), d_rc.data_ptr(), flags, d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw), eng._ctx), args.steps)
+    pack_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_pack_device(
+        eng._ctx, d_seqs.data_ptr(), d_off.data_ptr(), C.byref(pk_full), sraw), eng._ctx), args.steps)
+    n_arr = d_n.cpu().numpy().astype(np.int64) & 0xffff
+    # algorithmic HBM bytes of one k_align launch: packed bases + counts + n/flags/raw_len/read_count in, record + ops out
+    alg_bytes = float(((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4 + 4) + N * 48 + ((t.m + n_arr + 3) // 4).sum())
+    int_ops = cells_per_step * INT_OPS_PER_CELL
+    roofline = {"bound": "int32", "kernel": "k_align", "achieved": int_ops / (align_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                "unit": "Tiop/s", "frac": int_ops / (align_ms * 1e-3) / int_peak,
+                "peak_source": "measured live: k_int32_peak (dependent-free add+max, all SMs)",
+                "ops_per_cell": INT_OPS_PER_CELL, "cells_per_launch": cells_per_step, "ms_per_launch": align_ms,
+                "gcups": cells_per_step / (align_ms * 1e-3) / 1e9, "traffic": None}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    roofline_hbm = {"bound": "hbm", "kernel": "k_align", "achieved": alg_bytes / (align_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": alg_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "bytes_per_launch": alg_bytes, "traffic": None}
+    del d_b, d_c, d_n, d_fl, d_rl
+
+    # ---- end to end through the host-buffer C ABI call -------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def step_host():
+            eng.align_batch(seqs, h_off, h_rc, flags, rec=h_rec, ops=h_ops)
+            red = summ.clone()
+            parallel.allreduce_summary(red)
+            return int(red[0].item())  # device->host read of the step's reduced summary
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * N * args.steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(len(seqs) + (N + 1) * 8 + N * 4),
+               "d2h_bytes_per_step": int(N * 48 + N * stride + 8),
+               "ms_per_step": 1e3 * e2e_s / args.steps, "api": "treat_b200_align_batch (pinned host buffers)"}
+        assert np.array_equal(h_rec, rec_dev), "host-buffer and device-buffer paths disagree"
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = args.cpu_sample or min(N, 6144 * threads)
+        v, g, secs = cpu_sample_rate(t, p_trunc, seed, sample, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "gcups": g,
+               "sample": "first %d reads of the workload, %d threads, %.1f s; CPU port of the Go path (oracle/treat_oracle.c), "
+                         "lean mode: one DP per read, record + ops" % (sample, threads, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "gcups": world * cells_per_step * args.steps / (dev_ms * 1e-3) / 1e9,
+            "config": {"workload": workload_name(args, t), "l2": "inputs larger than L2 (%.0f MB raw reads per GPU per step)" % (len(seqs) / 1e6),
+                       "parallelism": "reads sharded over %d GPU(s), summary all-reduce only" % world,
+                       "outputs": "48-byte record + %d-byte 2-bit ops per read" % stride},
+            "kernels_ms": {"k_pack": pack_ms, "k_align": align_ms},
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    args = parse_args()
+    import __graft_entry__ as g
+    lib = os.path.join(ROOT, "treat_b200", "libtreat_b200.so")
+    if not os.path.exists(lib) or int(os.environ.get("LOCAL_RANK", "0")) == 0 and os.environ.get("TREAT_B200_REBUILD"):
+        g.build()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,246 @@
+/*
+ * treat_b200.h -- C ABI of libtreat_b200.so: the B200 (sm_100a) implementation of
+ * ubccr/treat's read-versus-template alignment hot path.
+ *
+ * The reference has no FFI; the path sits behind the Go package API of package `treat`
+ * (SURVEY.md 8b).  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference repository).  A cgo / ctypes caller binds exactly
+ * these symbols (INTEGRATION.md shows both stubs).
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns
+ * TREAT_B200_OK (0) or a negative TREAT_B200_ERR_* code and never throws; the callee does
+ * not retain caller pointers after return (cgo pointer rule); one context = one GPU =
+ * one caller thread at a time.  There is NO CPU fallback: without a usable CUDA device
+ * treat_b200_create fails with TREAT_B200_ERR_NO_DEVICE.
+ */
+#ifndef TREAT_B200_H
+#define TREAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TREAT_B200_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------- */
+#define TREAT_B200_OK 0
+#define TREAT_B200_ERR_INVALID (-1)     /* bad argument */
+#define TREAT_B200_ERR_CUDA (-2)        /* CUDA runtime error, see treat_b200_last_error */
+#define TREAT_B200_ERR_NOMEM (-3)
+#define TREAT_B200_ERR_TOO_LONG (-4)    /* template or read exceeds the kernel's shared-memory geometry */
+#define TREAT_B200_ERR_NO_TEMPLATE (-5) /* align called before set_template */
+#define TREAT_B200_ERR_NO_DEVICE (-6)   /* no CUDA device / not sm_100: there is no CPU path */
+#define TREAT_B200_ERR_TEMPLATE (-7)    /* template validation failed (template.go:97-113) */
+#define TREAT_B200_ERR_IO (-8)
+
+/* const.go:20-23 */
+#define TREAT_B200_FORWARD 1
+#define TREAT_B200_REVERSE (-1)
+
+/* ---- flags of the align calls ------------------------------------------------------- */
+#define TREAT_B200_EXCLUDE_SNPS 0x1u /* NewAlignment(..., excludeSnps=true), storage.go:756 */
+#define TREAT_B200_WANT_OPS 0x2u     /* also return the traceback (gapped strings in 2-bit form) */
+#define TREAT_B200_NO_SUMMARY 0x4u   /* do not accumulate the per-context summary histograms */
+
+/* ---- per-read status bits ----------------------------------------------------------- */
+#define TREAT_B200_ST_REF_PANIC 0x1u  /* reference indexes frag.EditSite out of range here (align.go:250-257) */
+#define TREAT_B200_ST_WIDE_BASE 0x2u  /* read holds a base outside the 3-letter packed alphabet */
+#define TREAT_B200_ST_SATURATED 0x4u  /* an edit-base run >= 255: batch was re-run on the wide path */
+
+/* ---- traceback ops: 2 bits per alignment column, 4 columns per byte, low bits first -- */
+#define TREAT_B200_OP_MATCH 0u /* template base over read base       (nwalgo pointer NW)   */
+#define TREAT_B200_OP_DEL 1u   /* template base over '-'   ("Up",   consumes template)     */
+#define TREAT_B200_OP_INS 2u   /* '-' over read base       ("Left", consumes read)         */
+
+/*
+ * Per-read result.  Bytes 0..23 are the fields of Alignment.MarshalBinary
+ * (align.go:316-335) in the same order, host endianness; Norm is always 0 on this path
+ * (fragment.go:120 leaves Fragment.Norm zero).  JuncSeq is returned as a window into the
+ * upper-cased raw read: JuncSeq == upper(seq[junc_seq_off : junc_seq_off + junc_seq_len]).
+ * EditStop/JuncStart/JuncEnd already include Template.EditOffset (align.go:274-276).
+ */
+typedef struct treat_b200_record {
+    int32_t edit_stop;
+    int32_t junc_start;
+    int32_t junc_end;
+    int32_t junc_len;
+    uint32_t read_count;
+    uint8_t has_mutation;
+    uint8_t alt_editing;
+    uint8_t mismatches;
+    uint8_t indel;
+    int32_t score;         /* nwalgo.Align's third return value */
+    uint32_t junc_seq_off;
+    uint32_t junc_seq_len;
+    uint16_t aln_len;      /* alignment columns = len(aln1) */
+    uint16_t n_bases;      /* len(Fragment.Bases) */
+    uint8_t status;        /* TREAT_B200_ST_* */
+    uint8_t reserved[3];
+    uint32_t raw_len;      /* len(seq) */
+} treat_b200_record; /* 48 bytes */
+
+/*
+ * Summary counters accumulated on the device over every align call since the last reset
+ * (the only data that crosses GPUs: SURVEY.md 8e).  Layout of the uint64 array returned by
+ * treat_b200_get_summary, with B = treat_b200_summary_bins(ctx) = Template.Len() + 2:
+ *   [0..6]   Total, Std, NonStd, Indels, Snps, SingleMismatch, DoubleMismatch weighted by
+ *            ReadCount (cmd/treat/stats.go:140-187, COUNT_FRAG)
+ *   [7..13]  the same seven counters counting each read once (COUNT_UNIQUE)
+ *   [14]     reads aligned, [15] DP cells (sum of m*n)
+ *   [16 .. 16+B)        histogram of EditStop  (bin = EditStop - EditOffset + 2)
+ *   [16+B .. 16+2B)     histogram of JuncLen   (bin = JuncLen)
+ *   [16+2B .. 16+3B)    histogram of JuncEnd   (bin = JuncEnd - EditOffset + 2)
+ * Histograms are weighted by ReadCount and skip reads with EditStop == Template.EditStop
+ * && JuncLen == 0, as cmd/treat/handlers.go:203-215 does.
+ */
+#define TREAT_B200_SUMMARY_HEADER 16
+
+typedef struct treat_b200_ctx treat_b200_ctx;
+typedef struct treat_b200_template treat_b200_template;
+
+/* ---- context ---------------------------------------------------------------------- */
+int treat_b200_abi_version(void);
+const char *treat_b200_strerror(int code);
+const char *treat_b200_last_error(const treat_b200_ctx *ctx);
+/* device = CUDA ordinal (one process per GPU: pass LOCAL_RANK) */
+int treat_b200_create(int device, treat_b200_ctx **out);
+void treat_b200_destroy(treat_b200_ctx *ctx);
+/* pinned host memory for the batch buffers (any host pointer works; pinned is faster) */
+int treat_b200_host_alloc(void **out, size_t bytes);
+void treat_b200_host_free(void *p);
+
+/* ---- template: replaces treat.NewTemplate / Template.SetOffset state (template.go:96-161) ----
+ * bases: m non-edit bases (upper case); edit_site: K rows of m+1 counts, row 0 = FE,
+ * row 1 = PE, rows 2.. = alternative templates; alt_start/alt_end: n_alt = K-2 regions
+ * AFTER SetOffset (template.go:157-160); tmpl_edit_stop: Template.EditStop after SetOffset.
+ * Validation of the FASTA-level invariants stays with the caller's NewTemplate. */
+int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m, const uint32_t *edit_site,
+                            int32_t K, const int32_t *alt_start, const int32_t *alt_end, int32_t n_alt,
+                            uint32_t edit_offset, int32_t tmpl_edit_stop, uint8_t edit_base);
+int treat_b200_use_template(treat_b200_ctx *ctx, const treat_b200_template *tmpl);
+
+/* ---- the hot path: replaces the per-read loop
+ *        frag := treat.NewFragment(rec.Id, rec.Seq, FORWARD, base)   (fragment.go:91)
+ *        aln  := treat.NewAlignment(frag, tmpl, excludeSnps)         (align.go:237)
+ *      of cmd/treat/align.go:114-120 and cmd/treat/storage.go:738-785 for a whole batch.
+ * seqs/seq_off: concatenated raw reads (any case), read i = seqs[seq_off[i] .. seq_off[i+1]);
+ * read_count: Fragment.ReadCount per read (treat_b200_parse_merge_count) or NULL for 1;
+ * rec: N records, caller owned; ops (may be NULL): ops_stride bytes per read, see
+ * treat_b200_ops_stride; results are in input order. */
+int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off,
+                           const uint32_t *read_count, uint64_t N, uint32_t flags, treat_b200_record *rec,
+                           uint8_t *ops, uint32_t ops_stride);
+/* same with every buffer already resident in device memory of ctx's GPU; max_len =
+ * max_i len(read i); runs asynchronously on `stream` (a cudaStream_t, NULL = ctx stream). */
+int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
+                                  const uint32_t *d_read_count, uint64_t N, uint32_t max_len, uint32_t flags,
+                                  treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, void *stream);
+/* bytes per read needed for the ops of reads up to max_len against the current template */
+uint32_t treat_b200_ops_stride(const treat_b200_ctx *ctx, uint32_t max_len);
+int treat_b200_synchronize(treat_b200_ctx *ctx);
+
+/* ---- stage-level entry points (device buffers): K1 = NewFragment for a batch, K2 = align --- */
+typedef struct treat_b200_packed {
+    uint64_t N;
+    uint32_t max_len;        /* longest raw read */
+    uint32_t wide;           /* 0: 2-bit bases + u8 counts, 1: u8 bases + u32 counts */
+    uint32_t bases_stride;   /* bytes per read, multiple of 16 */
+    uint32_t counts_stride;  /* bytes per read, multiple of 16 */
+    uint16_t *d_n;           /* [N] len(Fragment.Bases) */
+    uint8_t *d_flags;        /* [N] TREAT_B200_ST_WIDE_BASE | TREAT_B200_ST_SATURATED */
+    uint8_t *d_bases;        /* [N][bases_stride] */
+    uint8_t *d_counts;       /* [N][counts_stride]  Fragment.EditSite, n+1 entries */
+    uint32_t *d_raw_len;     /* [N] */
+} treat_b200_packed;
+/* sizes the strides for (N, max_len); the caller allocates the five arrays */
+int treat_b200_packed_layout(const treat_b200_ctx *ctx, uint64_t N, uint32_t max_len, uint32_t wide,
+                             treat_b200_packed *out);
+int treat_b200_pack_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
+                           const treat_b200_packed *dst, void *stream);
+int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed *src,
+                                   const uint32_t *d_read_count, uint32_t flags, treat_b200_record *d_rec,
+                                   uint8_t *d_ops, uint32_t ops_stride, void *stream);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx);
+
+/* ---- summaries: device-resident uint64 counters --------------------- */
+uint32_t treat_b200_summary_bins(const treat_b200_ctx *ctx);
+uint64_t treat_b200_summary_len(const treat_b200_ctx *ctx); /* TREAT_B200_SUMMARY_HEADER + 3*bins */
+int treat_b200_get_summary(treat_b200_ctx *ctx, uint64_t *out, uint64_t len);
+int treat_b200_reset_summary(treat_b200_ctx *ctx);
+/* device pointer of the counters, for an NCCL all-reduce issued by the caller */
+int treat_b200_summary_device_ptr(treat_b200_ctx *ctx, uint64_t **d_ptr);
+
+/* ---- roofline helper: dependent-free INT32 add/max throughput of this GPU ---------- */
+int treat_b200_measure_int32_peak(treat_b200_ctx *ctx, double *lane_ops_per_s, double *sm_mhz_effective);
+
+/* =====================================================================================
+ * Host-side mirror of the reference's Go API (no GPU work).  Implemented in C++ under
+ * treat_b200/csrc/host and exported here so ctypes/cgo callers can use it.
+ * ===================================================================================== */
+
+/* fragment.go:75-89 parseMergeCount */
+uint32_t treat_b200_parse_merge_count(const char *id, size_t len);
+/* fragment.go:91-121 NewFragment on the host (templates, SimpleAlign).  bases_out needs
+ * len bytes, edit_site_out len+1 entries. */
+int treat_b200_new_fragment(const uint8_t *seq, size_t len, int orientation, uint8_t base, uint8_t *bases_out,
+                            uint32_t *edit_site_out, size_t *n_out);
+
+/* template.go:51-94 NewTemplateFromFasta (+ SetOffset, template.go:153-161 when offset != 0) */
+int treat_b200_template_from_fasta(const char *path, int orientation, uint8_t base, int32_t offset,
+                                   treat_b200_template **out, char *err, size_t errlen);
+/* template.go:96-151 NewTemplate from raw template sequences (seqs[0]=FE, seqs[1]=PE, rest alt) */
+int treat_b200_template_new(const char *const *seqs, int32_t n_seqs, const int32_t *alt_start,
+                            const int32_t *alt_end, int32_t n_regions, int orientation, uint8_t base,
+                            treat_b200_template **out, char *err, size_t errlen);
+void treat_b200_template_set_offset(treat_b200_template *t, int32_t offset); /* template.go:153-161 */
+void treat_b200_template_free(treat_b200_template *t);
+int32_t treat_b200_template_size(const treat_b200_template *t);      /* Size()  template.go:163 */
+int32_t treat_b200_template_len(const treat_b200_template *t);       /* Len()   template.go:167 */
+int32_t treat_b200_template_edit_stop(const treat_b200_template *t);
+uint32_t treat_b200_template_edit_offset(const treat_b200_template *t);
+uint8_t treat_b200_template_edit_base(const treat_b200_template *t);
+const uint8_t *treat_b200_template_bases(const treat_b200_template *t);
+const uint32_t *treat_b200_template_edit_site(const treat_b200_template *t, int32_t k);
+const uint32_t *treat_b200_template_base_index(const treat_b200_template *t);
+int32_t treat_b200_template_n_alt(const treat_b200_template *t);
+int32_t treat_b200_template_alt_start(const treat_b200_template *t, int32_t i);
+int32_t treat_b200_template_alt_end(const treat_b200_template *t, int32_t i);
+uint32_t treat_b200_template_max(const treat_b200_template *t, int32_t i); /* Max(i) template.go:186 */
+
+/* FASTA reader with gofasta.SimpleParser's record semantics (cmd/treat/align.go:114) */
+typedef struct treat_b200_fasta treat_b200_fasta;
+int treat_b200_fasta_read(const char *path, treat_b200_fasta **out);
+void treat_b200_fasta_free(treat_b200_fasta *f);
+uint64_t treat_b200_fasta_count(const treat_b200_fasta *f);
+const char *treat_b200_fasta_id(const treat_b200_fasta *f, uint64_t i);
+const uint8_t *treat_b200_fasta_seqs(const treat_b200_fasta *f);     /* concatenated */
+const uint64_t *treat_b200_fasta_offsets(const treat_b200_fasta *f); /* count+1 */
+const uint32_t *treat_b200_fasta_read_counts(const treat_b200_fasta *f);
+
+/* align.go:388-520 Alignment.WriteTo from a device result: text for one read.  Returns the
+ * number of bytes needed; writes at most cap bytes to out (call twice or size generously). */
+int64_t treat_b200_format_alignment(const treat_b200_template *t, const treat_b200_record *rec,
+                                    const uint8_t *ops, const char *name, const uint8_t *seq, size_t seq_len,
+                                    int32_t tw, char *out, size_t cap);
+/* align.go:337-386 Alignment.SimpleAlign: runs f2 against f1 on the GPU (f1 as a one-row
+ * template) and assembles the two gapped strings.  out1/out2 need cap bytes each. */
+int64_t treat_b200_simple_align(treat_b200_ctx *ctx, const uint8_t *s1, size_t l1, const uint8_t *s2, size_t l2,
+                                uint8_t base, char *out1, char *out2, size_t cap);
+/* align.go:316-335 Alignment.MarshalBinary: 36-byte big-endian header + JuncSeq */
+int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *seq, size_t seq_len, uint8_t *out,
+                                  size_t cap);
+/* cmd/treat/align.go:59-122 `treat align`: writes the exact stdout text to a malloc'ed
+ * buffer (*out, release with treat_b200_free) */
+int treat_b200_cli_align(treat_b200_ctx *ctx, const char *template_path, const char *fragment_path,
+                         const char *s1, const char *s2, uint8_t base, int32_t offset, char **out,
+                         size_t *out_len, char *err, size_t errlen);
+void treat_b200_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREAT_B200_H */

@@ -1,0 +1,322 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact records, traceback
+ops and `treat align` text.  Run on the B200 box with -m gpu."""
+import random
+
+import numpy as np
+import pytest
+
+import treat_b200 as T
+from treat_b200 import cabi, synth
+from oracle import oracle as O
+from oracle import pyref as P
+from helpers import compare_records, summary_from_records
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = T.Aligner(0)
+    yield e
+    e.close()
+
+
+def _oracle_template(t: synth.TemplateArrays, tmp_path, offset=0):
+    path = t.write_fasta(str(tmp_path / "tmpl.fa"))
+    om = O.NewTemplateFromFasta(path, O.FORWARD, t.edit_base)
+    om.SetOffset(offset)
+    tm = T.NewTemplateFromFasta(path, T.FORWARD, t.edit_base)
+    tm.SetOffset(offset)
+    return om, tm
+
+
+def _check_attrs(a, attr, rid):
+    # align_test.go:86-133
+    assert a.EditStop == attr["ess"], rid
+    assert a.JuncStart == attr["jss"], rid
+    assert a.JuncEnd == attr["jes"], rid
+    assert a.JuncLen == attr["jes"] - attr["ess"], rid
+    assert a.AltEditing == attr["alt"], rid
+    assert a.HasMutation == attr["has_mutation"], rid
+    assert a.Mismatches == attr["mismatches"], rid
+    assert a.Indel == attr["indel"], rid
+
+
+def test_align_fragments(eng, fx, examples):
+    """TestAlignFragments (align_test.go:68-137) on the GPU, read by read as the reference does."""
+    ts = fx["test_sample"]
+    tmpl = T.NewTemplateFromFasta(examples[ts["templates"]], T.FORWARD, ts["base"])
+    assert tmpl.Size() == ts["size"]
+    for r in ts["reads"]:
+        frag = T.NewFragment(r["id"], r["seq"], T.FORWARD, ts["base"])
+        aln = eng.NewAlignment(frag, tmpl, False)
+        _check_attrs(aln, r["attr"], r["id"])
+
+
+def test_align_smoke(eng, fx):
+    """TestAlign (align_test.go:32-52): must not fail; text equals the oracle's."""
+    s = fx["align_smoke"]
+    a, b, c = (T.NewFragment(n, s[k], T.FORWARD, s["base"]) for n, k in (("a", "fe"), ("b", "pe"), ("c", "read")))
+    tmpl = T.NewTemplate(a, b, None, None)
+    aln = eng.NewAlignment(c, tmpl, False)
+    oa, ob, oc = (O.NewFragment(n, s[k], O.FORWARD, s["base"]) for n, k in (("a", "fe"), ("b", "pe"), ("c", "read")))
+    ot = O.NewTemplate(oa, ob)
+    assert aln.WriteTo(c, tmpl, 80) == O.NewAlignment(oc, ot).WriteTo(oc, ot, 80)
+
+
+def test_readme_goldens(eng, fx, examples):
+    rb = fx["readme_block"]
+    assert eng.cli_align(template=examples[rb["templates"]], fragment=examples[rb["reads"]], base=rb["base"]) == rb["stdout"]
+    rp = fx["readme_pairwise"]
+    assert eng.cli_align(s1=rp["s1"], s2=rp["s2"], base=rp["base"]) == rp["stdout"]
+    rc = fx["readme_csv"]
+    tmpl = T.NewTemplateFromFasta(examples[rc["templates"]], T.FORWARD, "T")
+    reads = T.read_fasta(examples[rc["reads"]])
+    alns = {rid: a for rid, a in zip(reads.ids, eng.NewAlignments(reads, tmpl, False))}
+    for row in rc["rows"]:
+        a = alns[row["id"]].fields()
+        for k in ("read_count", "alt_editing", "has_mutation", "edit_stop", "junc_end", "junc_len", "junc_seq"):
+            assert a[k] == row[k], (row["id"], k)
+
+
+def test_derived_fixtures(eng, fx, examples):
+    """Every frozen example set: fields, gapped strings, WriteTo text and MarshalBinary bytes."""
+    for s in fx["derived"]["sets"]:
+        tmpl = T.NewTemplateFromFasta(examples[s["templates"]], T.FORWARD, s["base"])
+        tmpl.SetOffset(s["offset"])
+        reads = T.read_fasta(examples[s["reads"]])
+        alns = eng.NewAlignments(reads, tmpl, s["exclude_snps"])
+        assert len(alns) == len(s["results"])
+        for i, (a, want) in enumerate(zip(alns, s["results"])):
+            assert reads.ids[i] == want["id"]
+            assert a.fields() == want["fields"], want["id"]
+            frag = T.NewFragment(reads.ids[i], reads.seq(i), T.FORWARD, s["base"])
+            assert a.gapped(tmpl.Bases, frag.Bases) == (want["aln1"], want["aln2"]), want["id"]
+            assert a.WriteTo(frag, tmpl, 80) == want["text"], want["id"]
+            assert a.MarshalBinary().hex() == want["marshal_hex"], want["id"]
+
+
+def test_cli_matches_oracle(eng, examples):
+    for t, f, base, off in (("templates.fa", "clones.fa", "T", 0), ("templates.fa", "sample-1.fa", "T", 10),
+                            ("test-templates.fa", "test-sample.fa", "t", 0)):
+        assert eng.cli_align(template=examples[t], fragment=examples[f], base=base, offset=off) == \
+            O.cli_align(template=examples[t], fragment=examples[f], base=base, offset=off)
+    # two-record file mode (cmd/treat/align.go:95-111)
+    assert eng.cli_align(fragment=examples["sample-1.fa"], base="T") == O.cli_align(fragment=examples["sample-1.fa"], base="T")
+
+
+def _mutate(rng, s):
+    s = list(s.upper())
+    for _ in range(rng.randint(0, 5)):
+        k = rng.randint(0, 5)
+        pos = rng.randrange(len(s) + 1)
+        if k == 0 and s:
+            del s[min(pos, len(s) - 1)]
+        elif k == 1:
+            s.insert(pos, rng.choice("ACGTTTN"))
+        elif k == 2 and s:
+            s[min(pos, len(s) - 1)] = rng.choice("ACGTTNRY")
+        elif k == 3:
+            s[pos:pos] = "T" * rng.randint(1, 9)
+        elif k == 4:
+            lo = rng.randrange(len(s) + 1)
+            del s[lo:lo + rng.randint(0, 30)]
+        else:
+            s[pos:pos] = [rng.choice("ACG") for _ in range(rng.randint(1, 12))]
+    return "".join(s)
+
+
+@pytest.mark.parametrize("tname,base", [("templates.fa", "T"), ("test-templates.fa", "t"), ("simple-templates.fa", "T")])
+def test_fuzz_vs_oracle(eng, examples, tname, base):
+    """Differential fuzz: mutated template strings (indels, substitutions, N/IUPAC, long edit-base
+    runs, truncations), both excludeSnps settings; records, ops and text must equal the oracle's."""
+    rng = random.Random(hash(tname) & 0xffff)
+    srcs = [s for _, s in P.read_fasta(examples[tname])]
+    recs = [("f-%d" % (i + 1), _mutate(rng, rng.choice(srcs))) for i in range(400)]
+    recs += [("empty-1", ""), ("allT-2", "TTTTTTT"), ("one-3", "A"), ("lower-4", srcs[0].lower())]
+    fb = T.FastaBatch.from_records(recs)
+    tm = T.NewTemplateFromFasta(examples[tname], T.FORWARD, base)
+    om = O.NewTemplateFromFasta(examples[tname], O.FORWARD, base)
+    for ex in (False, True):
+        alns = eng.NewAlignments(fb, tm, ex)
+        orec, oops, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, exclude_snps=ex)
+        grec = np.concatenate([a._rec for a in alns])
+        assert compare_records(grec, orec) == []
+        for i, a in enumerate(alns):
+            n = int(orec[i]["aln_len"])
+            assert a.ops() == [(int(oops[i, c >> 2]) >> (2 * (c & 3))) & 3 for c in range(n)], recs[i]
+        for i in range(0, len(recs), 23):
+            of = O.NewFragment(recs[i][0], recs[i][1], O.FORWARD, base)
+            tf = T.NewFragment(recs[i][0], recs[i][1], T.FORWARD, base)
+            oa = O.NewAlignment(of, om, ex)
+            assert alns[i].WriteTo(tf, tm, 80) == oa.WriteTo(of, om, 80)
+            assert alns[i].JuncSeq == oa.JuncSeq
+            assert alns[i].MarshalBinary() == oa.MarshalBinary()
+
+
+def _batch_vs_oracle(eng, t, tmp_path, N, seed, p_trunc=0.0, offset=0, exclude=False, nthreads=8):
+    om, tm = _oracle_template(t, tmp_path, offset)
+    eng.SetTemplate(tm)
+    seqs, off, rc = synth.reads(t, N, seed=seed, p_trunc=p_trunc)
+    flags = cabi.WANT_OPS | (cabi.EXCLUDE_SNPS if exclude else 0)
+    eng.reset_summary()
+    grec, gops = eng.align_batch(seqs, off, rc, flags)
+    orec, oops, _ = O.align_batch(om, seqs, off, rc, exclude_snps=exclude, nthreads=nthreads, ops_stride=gops.shape[1])
+    assert compare_records(grec, orec) == []
+    assert np.array_equal(gops, oops)
+    lens = np.diff(off.astype(np.int64))
+    assert np.array_equal(grec["raw_len"], lens)
+    want = summary_from_records(orec, t.m, offset, om.EditStop)
+    assert np.array_equal(eng.summary(), want)
+    return grec, orec, seqs, off
+
+
+def test_synthetic_rps12_vs_oracle(eng, tmp_path):
+    """Config 3 shape (RPS12, K=5) at a size the oracle finishes in seconds: all records + all ops."""
+    grec, orec, seqs, off = _batch_vs_oracle(eng, synth.rps12_template(), tmp_path, 20000, synth.SEED_BASE + 3)
+    # JuncSeq is a window of the upper-cased raw read
+    for i in np.nonzero(orec["junc_seq_len"] > 0)[0][:200]:
+        s = seqs[int(off[i]):int(off[i + 1])].tobytes().upper()
+        lo = int(grec[i]["junc_seq_off"])
+        assert len(s[lo:lo + int(grec[i]["junc_seq_len"])]) == int(orec[i]["junc_seq_len"])
+
+
+def test_synthetic_rps12_offset_exclude(eng, tmp_path):
+    _batch_vs_oracle(eng, synth.rps12_template(), tmp_path, 4000, synth.SEED_BASE + 31, offset=10, exclude=True)
+
+
+def test_synthetic_long_template_vs_oracle(eng, tmp_path):
+    """Config 5 shape: ~600-nt gene (m=300, K=10), variable-length reads with 5'/3' truncation."""
+    _batch_vs_oracle(eng, synth.long_template(300, 8), tmp_path, 3000, synth.SEED_BASE + 5, p_trunc=0.2)
+
+
+def test_other_template_sizes(eng, tmp_path):
+    """Exercise every columns-per-lane instantiation (m = 20 .. 500)."""
+    for m in (20, 40, 100, 150, 230, 330, 500):
+        _batch_vs_oracle(eng, synth.long_template(m, 2, seed=99 + m), tmp_path, 300, 1000 + m, p_trunc=0.3)
+
+
+def test_wide_paths(eng, tmp_path):
+    """Template with a non-ACG base, and a read with an edit-base run >= 255: both must take the
+    wide kernels and stay exact."""
+    fe, pe = "ACNGTTAGC" + "AG" * 20, "ACNGAGC" + "AG" * 20
+    p = tmp_path / "wide.fa"
+    p.write_text(">fe\n%s\n>pe\n%s\n" % (fe, pe))
+    tm = T.NewTemplateFromFasta(str(p), T.FORWARD, "T")
+    om = O.NewTemplateFromFasta(str(p), O.FORWARD, "T")
+    recs = [("a-1", fe), ("b-2", pe), ("c-3", fe.replace("N", "R")), ("d-4", "ACNG" + "T" * 300 + "AGC" + "AG" * 20),
+            ("e-5", "ACNGTTAGC" + "AG" * 19 + "A" + "T" * 700 + "G"), ("f-6", "N" * 30)]
+    fb = T.FastaBatch.from_records(recs)
+    alns = eng.NewAlignments(fb, tm, False)
+    orec, oops, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts)
+    assert compare_records(np.concatenate([a._rec for a in alns]), orec) == []
+    for i, a in enumerate(alns):
+        of, tf = O.NewFragment(*recs[i]), T.NewFragment(*recs[i])
+        oa = O.NewAlignment(of, om)
+        assert a.JuncSeq == oa.JuncSeq
+        assert a.WriteTo(tf, tm, 80) == oa.WriteTo(of, om, 80)
+    # canonical template, saturated read -> automatic re-run on the wide path
+    t = synth.rps12_template()
+    om2, tm2 = _oracle_template(t, tmp_path)
+    raw = t.raw_sequences()[0]
+    recs = [("x-1", raw), ("y-2", raw[:100] + "T" * 400 + raw[100:]), ("z-3", "T" * 260 + raw)]
+    fb = T.FastaBatch.from_records(recs)
+    alns = eng.NewAlignments(fb, tm2, False)
+    orec, _, _ = O.align_batch(om2, fb.seqs, fb.offsets, fb.read_counts)
+    assert compare_records(np.concatenate([a._rec for a in alns]), orec) == []
+    assert all(a.Status & cabi.ST_SATURATED for a in alns[1:])
+    for i, a in enumerate(alns):
+        assert a.JuncSeq == O.NewAlignment(O.NewFragment(*recs[i]), om2).JuncSeq
+
+
+def test_edge_cases(eng, tmp_path):
+    """Reference panic case, uint8 mismatch wrap, empty batch, argument errors."""
+    tm = T.NewTemplate(T.NewFragment("fe", "AT"), T.NewFragment("pe", "A"), None, None)
+    a = eng.NewAlignment(T.NewFragment("r-1", "TA"), tm, False)
+    ot = O.NewTemplate(O.NewFragment("fe", "AT"), O.NewFragment("pe", "A"))
+    oa = O.NewAlignment(O.NewFragment("r-1", "TA"), ot)
+    assert a.WouldPanic and oa.WouldPanic and a.fields() == oa.fields()
+    tm = T.NewTemplate(T.NewFragment("fe", "A" * 300), T.NewFragment("pe", "A" * 300), None, None)
+    a = eng.NewAlignment(T.NewFragment("x-1", "G" * 300), tm, False)
+    assert (a.Mismatches, a.HasMutation, a.Indel) == (300 % 256, 1, 0)
+    rec, ops = eng.align_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(rec) == 0
+    with pytest.raises(T.TreatError):
+        T.Aligner(0).align_batch(np.zeros(4, np.uint8), np.array([0, 4], np.uint64))  # no template
+    big = T.NewFragment("fe", "AC" * 300)
+    with pytest.raises(T.TreatError):
+        eng.SetTemplate(T.NewTemplate(big, big, None, None))  # 600 bases > 512
+    with pytest.raises(T.TreatError):
+        tm = T.NewTemplate(T.NewFragment("fe", "ACG"), T.NewFragment("pe", "ACG"), None, None)
+        eng.NewAlignment(T.NewFragment("long-1", "A" * 20000), tm, False)
+
+
+def test_device_resident_entry_point(eng, tmp_path):
+    """treat_b200_align_batch_device with torch-owned buffers on a torch stream == host-buffer call."""
+    import torch
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 5000
+    seqs, off, rc = synth.reads(t, N, seed=77)
+    hrec, hops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+    d_seqs = torch.from_numpy(seqs.copy()).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_rc = torch.from_numpy(rc.astype(np.int32)).cuda()
+    stride = hops.shape[1]
+    d_rec = torch.zeros(N * 48, dtype=torch.uint8, device="cuda")
+    d_ops = torch.zeros(N * stride, dtype=torch.uint8, device="cuda")
+    max_len = int(np.diff(off.astype(np.int64)).max())
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, cabi.WANT_OPS,
+                               d_rec.data_ptr(), d_ops.data_ptr(), stride, st.cuda_stream)
+    st.synchronize()
+    drec = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
+    assert np.array_equal(drec, hrec)
+    assert np.array_equal(d_ops.cpu().numpy().reshape(N, stride), hops)
+
+
+def test_full_size_properties(eng, tmp_path):
+    """Config 3 at full size (1M RPS12 reads): size-independent properties on every read, oracle
+    parity on a stride sample, determinism across two runs and across batch splits."""
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 1_000_000
+    seqs, off, rc = synth.reads(t, N, seed=synth.SEED_BASE + 3)
+    eng.reset_summary()
+    rec, ops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+    summ = eng.summary()
+    # (1) ops consume exactly m template bases and n read bases, and re-scoring them gives `score`
+    alen = rec["aln_len"].astype(np.int64)
+    cols = np.arange(ops.shape[1] * 4)
+    o = (ops[:, cols >> 2] >> (2 * (cols & 3)).astype(np.uint8)) & 3
+    valid = cols[None, :] < alen[:, None]
+    n_ins = ((o == 2) & valid).sum(1)
+    n_del = ((o == 1) & valid).sum(1)
+    n_mat = ((o == 0) & valid).sum(1)
+    assert np.array_equal(n_mat + n_del, np.full(N, t.m))
+    assert np.array_equal(n_mat + n_ins, rec["n_bases"].astype(np.int64))
+    assert np.array_equal((n_ins + n_del > 0).astype(np.uint8), rec["indel"])
+    # score = matches - mismatches - gaps, and mismatches (mod 256) is what the record holds
+    mism = (n_mat - rec["score"] - n_ins - n_del) // 2
+    assert np.array_equal((mism & 0xff).astype(np.uint8), rec["mismatches"])
+    assert np.all((o == 0)[~valid])  # padding is zero
+    # (2) summary == reference definition applied to the records
+    assert np.array_equal(summ, summary_from_records(rec, t.m, 0, om.EditStop))
+    # (3) oracle parity on a 1/64 stride sample
+    idx = np.arange(0, N, 64)
+    sub_off = np.zeros(len(idx) + 1, dtype=np.uint64)
+    lens = (off[idx + 1] - off[idx]).astype(np.uint64)
+    sub_off[1:] = np.cumsum(lens)
+    sub = np.concatenate([seqs[int(off[i]):int(off[i + 1])] for i in idx])
+    orec, oops, _ = O.align_batch(om, sub, sub_off, rc[idx], nthreads=8, ops_stride=ops.shape[1])
+    assert compare_records(rec[idx], orec) == []
+    assert np.array_equal(ops[idx], oops)
+    # (4) idempotence / independence of batch boundaries
+    rec2, ops2 = eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+    assert np.array_equal(rec, rec2) and np.array_equal(ops, ops2)
+    lo, hi = 300_000, 300_000 + 70_001
+    rec3, ops3 = eng.align_batch(seqs[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo], rc[lo:hi], cabi.WANT_OPS)
+    assert np.array_equal(rec3, rec[lo:hi]) and np.array_equal(ops3[:, :ops.shape[1]], ops[lo:hi, :ops3.shape[1]])

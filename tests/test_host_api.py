@@ -1,0 +1,142 @@
+"""Host-side mirror of the Go API (treat_b200/csrc/host) on CPU: the reference's own unit tests
+(fragment_test.go, template_test.go) plus differential checks against the oracle."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import treat_b200 as T
+from treat_b200 import cabi
+from oracle import oracle as O
+from oracle import pyref as P
+
+
+def test_fragment(fx):
+    """TestFragment, fragment_test.go:25-50."""
+    for s in fx["fragment_test"]["seqs"]:
+        frag = T.NewFragment("id", s, T.FORWARD, "t")
+        assert frag.String() == s.upper()
+        assert frag.ReadCount == 1
+        frag = T.NewFragment("1-143", s, T.REVERSE, "t")
+        assert frag.String() == s[::-1].upper()
+        assert frag.ReadCount == 143
+
+
+def test_parse_read_counts(fx):
+    """TestParseReadCounts, fragment_test.go:52-76."""
+    for rid, count in fx["parse_read_counts"]["table"].items():
+        frag = T.NewFragment(rid, "CTGCTG", T.FORWARD, "t")
+        assert frag.ReadCount == count, rid
+    for rid in ("a-99999999999999999999", "a-4294967297", "x_y-12", "-", "a-", "a--3", "a b-4", "  a_7  z-9"):
+        assert T.parseMergeCount(rid) == O.parseMergeCount(rid), rid
+
+
+def test_template(fx, examples):
+    """TestTemplate, template_test.go:26-70."""
+    tt = fx["template_test"]
+    tmpl = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "t")
+    assert tmpl.Size() == tt["rps12_size"]
+    full = T.NewFragment("full", tt["bad"]["full"], T.FORWARD, "t")
+    pre = T.NewFragment("pre", tt["bad"]["pre"], T.FORWARD, "t")
+    with pytest.raises(ValueError, match="Full and Pre templates must have the same non-edit bases"):
+        T.NewTemplate(full, pre, None, None)
+    full = T.NewFragment("full", tt["good"]["full"], T.FORWARD, "t")
+    pre = T.NewFragment("pre", tt["good"]["pre"], T.FORWARD, "t")
+    tmpl = T.NewTemplate(full, pre, None, None)
+    rebuilt = "".join(tmpl.EditBase * b + (tmpl.Bases[i] if i < len(tmpl.Bases) else "")
+                      for i, b in enumerate(tmpl.EditSite[1]))
+    assert rebuilt == pre.String()
+    with pytest.raises(ValueError, match="Please specify the alt regions"):
+        T.NewTemplate(full, pre, None, [None, None])
+
+
+def test_template_matches_oracle(examples):
+    for name, base in (("templates.fa", "T"), ("test-templates.fa", "t"), ("simple-templates.fa", "T")):
+        for offset in (0, 10):
+            a = T.NewTemplateFromFasta(examples[name], T.FORWARD, base)
+            b = O.NewTemplateFromFasta(examples[name], O.FORWARD, base)
+            a.SetOffset(offset)
+            b.SetOffset(offset)
+            assert (a.Size(), a.Len(), a.EditStop, a.EditOffset, a.EditBase) == (b.Size(), b.Len(), b.EditStop, b.EditOffset, b.EditBase)
+            assert a.Bases == b.Bases and a.EditSite == b.EditSite and a.BaseIndex == b.BaseIndex
+            assert a.AltRegion == b.AltRegion
+            assert [a.Max(i) for i in range(a.Len())] == [b.Max(i) for i in range(b.Len())]
+
+
+def test_template_errors(tmp_path):
+    p = tmp_path / "one.fa"
+    p.write_text(">only\nACGT\n")
+    with pytest.raises(ValueError, match="Must provide at least 2 templates"):
+        T.NewTemplateFromFasta(str(p), T.FORWARD, "T")
+    with pytest.raises(ValueError, match="Invalid FASTA file"):
+        T.NewTemplateFromFasta(str(tmp_path / "missing.fa"), T.FORWARD, "T")
+    p3 = tmp_path / "noalt.fa"
+    p3.write_text(">fe\nATTC\n>pe\nAC\n>alt without region\nATC\n")
+    with pytest.raises(ValueError, match="Please specify the alt regions"):
+        T.NewTemplateFromFasta(str(p3), T.FORWARD, "T")
+
+
+def test_fragment_fuzz_vs_oracle():
+    rng = random.Random(7)
+    for _ in range(300):
+        s = "".join(rng.choice("ACGTTTacgtNn-x") for _ in range(rng.randint(0, 60)))
+        base = rng.choice("TtAc")
+        o = rng.choice((T.FORWARD, T.REVERSE))
+        a, b = T.NewFragment("r_%d" % rng.randint(0, 99), s, o, base), None
+        b = O.NewFragment(a.Name, s, o, base)
+        assert (a.Bases, a.EditSite, a.EditBase, a.ReadCount, a.String()) == (b.Bases, b.EditSite, b.EditBase, b.ReadCount, b.String())
+
+
+def test_fasta_reader(examples, tmp_path):
+    for name in ("clones.fa", "templates.fa", "test-sample.fa"):
+        fb = T.read_fasta(examples[name])
+        want = P.read_fasta(examples[name])
+        assert fb.ids == [i for i, _ in want]
+        assert [fb.seq(i).decode() for i in range(len(fb))] == [s for _, s in want]
+        assert fb.read_counts.tolist() == [O.parseMergeCount(i) for i, _ in want]
+    p = tmp_path / "crlf.fa"
+    p.write_bytes(b"junk\n>a-3 x \r\nAC\r\nGT\r\n>b\nTT")
+    fb = T.read_fasta(str(p))
+    assert fb.ids == ["a-3 x", "b"] and [fb.seq(i) for i in range(2)] == [b"ACGT", b"TT"]
+    assert fb.read_counts.tolist() == [3, 1]
+
+
+def _oracle_record_as_product(orec):
+    rec = np.zeros(len(orec), dtype=cabi.RECORD_DTYPE)
+    for f in orec.dtype.names:
+        if f in rec.dtype.names and f not in ("pad",):
+            rec[f] = orec[f]
+    return rec
+
+
+def test_format_and_marshal_vs_oracle(examples):
+    """WriteTo / MarshalBinary text assembly on the host, fed with the oracle's record + ops
+    (so this host logic is covered without a GPU)."""
+    for tname, rname, base, offset in (("templates.fa", "clones.fa", "T", 0), ("test-templates.fa", "test-sample.fa", "t", 0),
+                                       ("templates.fa", "sample-1.fa", "T", 10)):
+        tm = T.NewTemplateFromFasta(examples[tname], T.FORWARD, base)
+        tm.SetOffset(offset)
+        om = O.NewTemplateFromFasta(examples[tname], O.FORWARD, base)
+        om.SetOffset(offset)
+        fb = T.read_fasta(examples[rname])
+        orec, oops, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts)
+        rec = _oracle_record_as_product(orec)
+        for i in range(len(fb)):
+            seq = fb.seq(i)
+            name = fb.ids[i].encode()
+            need = cabi.lib().treat_b200_format_alignment(tm._h, rec[i:i + 1].ctypes.data, oops[i].ctypes.data, name, seq, len(seq), 80, None, 0)
+            buf = C.create_string_buffer(int(need))
+            cabi.lib().treat_b200_format_alignment(tm._h, rec[i:i + 1].ctypes.data, oops[i].ctypes.data, name, seq, len(seq), 80, buf, need)
+            of = O.NewFragment(fb.ids[i], seq, O.FORWARD, base)
+            oa = O.NewAlignment(of, om, False)
+            assert buf.raw[:need].decode("latin-1") == oa.WriteTo(of, om, 80), fb.ids[i]
+            need = cabi.lib().treat_b200_marshal_record(rec[i:i + 1].ctypes.data, seq, len(seq), None, 0)
+            mb = (C.c_uint8 * int(need))()
+            cabi.lib().treat_b200_marshal_record(rec[i:i + 1].ctypes.data, seq, len(seq), mb, need)
+            assert bytes(mb) == oa.MarshalBinary(), fb.ids[i]
+
+
+def test_print_alignment():
+    a, b = "A" * 170, "C" * 170
+    assert T.PrintAlignment(a, b, 80) == P.PrintAlignment(a, b, 80)

@@ -1,0 +1,75 @@
+"""In-tree build of libtreat_b200.so (sm_100a only) and the treat_align CLI.
+
+nvcc cross-compiles without a GPU; the built library travels to the GPU box with the repo
+snapshot (it is git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "_build")
+LIB = os.path.join(PKG, "libtreat_b200.so")
+CLI = os.path.join(PKG, "bin", "treat_align")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
+]
+CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra"]
+
+CUDA_SOURCES = ["kernels.cu", "capi.cu"]
+CXX_SOURCES = ["host/treat_host.cpp", "host/capi_host.cpp"]
+HEADERS = ["device_format.h", "host/treat_host.hpp", "../../include/treat_b200.h"]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libtreat_b200.so cannot be built (there is no CPU fallback)")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    for src in CUDA_SOURCES + CXX_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace("/", "_") + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            if src.endswith(".cu"):
+                _run([_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o], verbose)
+            else:
+                _run([os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-c", s, "-o", o], verbose)
+    if force or _stale(LIB, objs):
+        _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+             + ["-cudart", "static", "-Xlinker", "--no-undefined"], verbose)
+    cli_src = os.path.join(CSRC, "cli", "treat_align.cpp")
+    if force or _stale(CLI, [cli_src, LIB] + hdrs):
+        _run([os.environ.get("CXX", "g++")] + CXX_FLAGS + [cli_src, "-o", CLI, "-L" + PKG, "-ltreat_b200",
+                                                           "-Wl,-rpath,$ORIGIN/.."], verbose)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

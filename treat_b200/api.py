@@ -1,0 +1,426 @@
+"""Python mirror of the reference's Go package API over the C ABI (include/treat_b200.h).
+
+Names, argument meaning and error behaviour follow package `treat`
+(fragment.go / template.go / align.go) so tests read like the reference's own tests:
+
+    tmpl = NewTemplateFromFasta("templates.fa", FORWARD, "t"); tmpl.SetOffset(0)
+    eng = Aligner(device=0)
+    frag = NewFragment(rec_id, rec_seq, FORWARD, "t")
+    aln = eng.NewAlignment(frag, tmpl, False)      # one read
+    alns = eng.NewAlignments(reads, tmpl, False)   # the reference's per-read loop as one batch
+    text = aln.WriteTo(frag, tmpl, 80)
+
+All alignment work happens in libtreat_b200.so on the GPU; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import cabi
+from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, RECORD_DTYPE, REVERSE, WANT_OPS, TreatError, check, lib)
+
+__all__ = [
+    "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
+    "NewTemplate", "NewTemplateFromFasta", "parseMergeCount", "PrintAlignment", "read_fasta", "TreatError",
+]
+
+
+def _b(s) -> bytes:
+    return s if isinstance(s, (bytes, bytearray)) else str(s).encode("latin-1")
+
+
+def parseMergeCount(rec_id) -> int:
+    """fragment.go:75-89"""
+    b = _b(rec_id)
+    return lib().treat_b200_parse_merge_count(b, len(b))
+
+
+class Fragment:
+    """fragment.go:57-64"""
+
+    def __init__(self, name: str, seq, orientation: int, base: str):
+        raw = _b(seq)
+        self.Name = name
+        self.Seq = raw  # the raw record; the device re-derives Bases/EditSite from it
+        self.Orientation = orientation
+        bases = np.zeros(max(1, len(raw)), dtype=np.uint8)
+        sites = np.zeros(len(raw) + 1, dtype=np.uint32)
+        n = C.c_size_t()
+        check(lib().treat_b200_new_fragment(raw, len(raw), orientation, ord(_b(base).upper()), bases.ctypes.data,
+                                            sites.ctypes.data, C.byref(n)))
+        self.Bases = bases[: n.value].tobytes().decode("latin-1")
+        self.EditSite = sites[: n.value + 1].tolist()
+        self.EditBase = _b(base).upper().decode("latin-1")
+        self.ReadCount = parseMergeCount(name)
+        self.Norm = 0.0
+
+    def Len(self) -> int:
+        return len(self.EditSite)
+
+    def String(self) -> str:
+        """fragment.go:136-147"""
+        out = []
+        for i, c in enumerate(self.EditSite):
+            out.append(self.EditBase * c)
+            if i < len(self.Bases):
+                out.append(self.Bases[i])
+        return "".join(out)
+
+    def ToFasta(self) -> str:
+        return ">" + self.Name + "\n" + self.String()
+
+    def forward_seq(self) -> bytes:
+        """The record in 5'->3' orientation, as NewFragment sees it after the optional reversal."""
+        return self.Seq[::-1] if self.Orientation == REVERSE else self.Seq
+
+
+def NewFragment(name, seq, orientation: int = FORWARD, base: str = "T") -> Fragment:
+    """fragment.go:91-121"""
+    return Fragment(name, seq, orientation, base)
+
+
+class Template:
+    """template.go:41-49 (handle to the C++ treat::Template)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().treat_b200_template_free(self._h)
+            self._h = None
+
+    def SetOffset(self, offset: int) -> None:
+        lib().treat_b200_template_set_offset(self._h, offset)
+
+    def Size(self) -> int:
+        return lib().treat_b200_template_size(self._h)
+
+    def Len(self) -> int:
+        return lib().treat_b200_template_len(self._h)
+
+    def Max(self, i: int) -> int:
+        return lib().treat_b200_template_max(self._h, i)
+
+    def IndexLabel(self, i: int) -> int:
+        return i + self.EditOffset
+
+    @property
+    def EditStop(self) -> int:
+        return lib().treat_b200_template_edit_stop(self._h)
+
+    @property
+    def EditOffset(self) -> int:
+        return lib().treat_b200_template_edit_offset(self._h)
+
+    @property
+    def EditBase(self) -> str:
+        return chr(lib().treat_b200_template_edit_base(self._h))
+
+    @property
+    def Bases(self) -> str:
+        return C.string_at(lib().treat_b200_template_bases(self._h), self.Len() - 1).decode("latin-1")
+
+    @property
+    def EditSite(self) -> List[List[int]]:
+        n = self.Len()
+        return [list((C.c_uint32 * n).from_address(lib().treat_b200_template_edit_site(self._h, k)))
+                for k in range(self.Size())]
+
+    @property
+    def BaseIndex(self) -> List[int]:
+        return list((C.c_uint32 * self.Len()).from_address(lib().treat_b200_template_base_index(self._h)))
+
+    @property
+    def AltRegion(self) -> List[Tuple[int, int]]:
+        L = lib()
+        return [(L.treat_b200_template_alt_start(self._h, i), L.treat_b200_template_alt_end(self._h, i))
+                for i in range(L.treat_b200_template_n_alt(self._h))]
+
+    def String(self) -> str:
+        es, b = self.EditSite[0], self.Bases
+        return "".join(self.EditBase * c + (b[i] if i < len(b) else "") for i, c in enumerate(es))
+
+
+def NewTemplateFromFasta(path: str, orientation: int = FORWARD, base: str = "T") -> Template:
+    """template.go:51-94; raises ValueError with the reference's message on its error paths."""
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib().treat_b200_template_from_fasta(_b(path), orientation, ord(_b(base)), 0, C.byref(h), err, 512)
+    if rc != cabi.OK:
+        raise ValueError(err.value.decode() or lib().treat_b200_strerror(rc).decode())
+    return Template(h)
+
+
+def NewTemplate(full: Fragment, pre: Fragment, alt: Optional[Sequence[Fragment]] = None,
+                altRegion: Optional[Sequence] = None) -> Template:
+    """template.go:96-151"""
+    alt = list(alt or [])
+    altRegion = list(altRegion or [])
+    frs = [full, pre] + alt
+    if any(f.EditBase != full.EditBase for f in frs):
+        raise ValueError("Invalid template sequences. Full and Pre templates must have the same non-edit bases")
+    arr = (C.c_char_p * len(frs))(*[f.forward_seq() for f in frs])
+    st = np.array([r[0] if r else 0 for r in altRegion] or [0], dtype=np.int32)
+    en = np.array([r[1] if r else 0 for r in altRegion] or [0], dtype=np.int32)
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib().treat_b200_template_new(arr, len(frs), st.ctypes.data, en.ctypes.data, len(altRegion), FORWARD,
+                                       ord(_b(full.EditBase)), C.byref(h), err, 512)
+    if rc != cabi.OK:
+        raise ValueError(err.value.decode() or lib().treat_b200_strerror(rc).decode())
+    return Template(h)
+
+
+class FastaBatch:
+    """Concatenated reads + offsets + ReadCounts: the batch layout of treat_b200_align_batch."""
+
+    def __init__(self, ids: List[str], seqs: np.ndarray, offsets: np.ndarray, read_counts: np.ndarray):
+        self.ids, self.seqs, self.offsets, self.read_counts = ids, seqs, offsets, read_counts
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def seq(self, i: int) -> bytes:
+        return self.seqs[int(self.offsets[i]): int(self.offsets[i + 1])].tobytes()
+
+    @staticmethod
+    def from_records(records: Iterable[Tuple[str, object]]) -> "FastaBatch":
+        ids, chunks = [], []
+        for rid, seq in records:
+            ids.append(rid)
+            chunks.append(_b(seq))
+        off = np.zeros(len(ids) + 1, dtype=np.uint64)
+        if ids:
+            off[1:] = np.cumsum([len(c) for c in chunks], dtype=np.uint64)
+        seqs = np.frombuffer(b"".join(chunks), dtype=np.uint8).copy() if ids else np.zeros(0, np.uint8)
+        rc = np.array([parseMergeCount(i) for i in ids], dtype=np.uint32)
+        return FastaBatch(ids, seqs, off, rc)
+
+
+def read_fasta(path: str) -> FastaBatch:
+    """gofasta.SimpleParser record semantics (cmd/treat/align.go:114), whole file as one batch."""
+    h = C.c_void_p()
+    check(lib().treat_b200_fasta_read(_b(path), C.byref(h)))
+    try:
+        L = lib()
+        n = L.treat_b200_fasta_count(h)
+        ids = [L.treat_b200_fasta_id(h, i).decode("latin-1") for i in range(n)]
+        off = np.array((C.c_uint64 * (n + 1)).from_address(L.treat_b200_fasta_offsets(h)), dtype=np.uint64) if n else np.zeros(1, np.uint64)
+        total = int(off[-1])
+        seqs = np.array((C.c_uint8 * total).from_address(L.treat_b200_fasta_seqs(h)), dtype=np.uint8) if total else np.zeros(0, np.uint8)
+        rc = np.array((C.c_uint32 * n).from_address(L.treat_b200_fasta_read_counts(h)), dtype=np.uint32) if n else np.zeros(0, np.uint32)
+        return FastaBatch(ids, seqs, off, rc)
+    finally:
+        lib().treat_b200_fasta_free(h)
+
+
+def PrintAlignment(a1: str, a2: str, tw: int = 80) -> str:
+    """cmd/treat/align.go:39-57"""
+    out = []
+    for r in range(0, len(a1), tw):
+        out += [a1[r:r + tw], "\n", a2[r:r + tw], "\n", "\n"]
+    return "".join(out)
+
+
+class Alignment:
+    """align.go:41-55, filled from one treat_b200_record."""
+
+    def __init__(self, rec: np.void, ops: Optional[np.ndarray], seq: bytes, engine: "Aligner"):
+        self._rec = np.array([rec], dtype=RECORD_DTYPE)
+        self._ops = None if ops is None else np.ascontiguousarray(ops, dtype=np.uint8)
+        self._seq = seq
+        self._eng = engine
+        r = self._rec[0]
+        self.EditStop, self.JuncStart, self.JuncEnd, self.JuncLen = (int(r["edit_stop"]), int(r["junc_start"]),
+                                                                    int(r["junc_end"]), int(r["junc_len"]))
+        self.ReadCount, self.Norm = int(r["read_count"]), 0.0
+        self.HasMutation, self.Mismatches, self.Indel, self.AltEditing = (int(r["has_mutation"]), int(r["mismatches"]),
+                                                                          int(r["indel"]), int(r["alt_editing"]))
+        self.Score, self.Status = int(r["score"]), int(r["status"])
+        o, n = int(r["junc_seq_off"]), int(r["junc_seq_len"])
+        self.JuncSeq = seq[o:o + n].decode("latin-1").upper()
+        self.WouldPanic = bool(self.Status & cabi.ST_REF_PANIC)
+
+    def fields(self) -> dict:
+        return dict(
+            edit_stop=self.EditStop, junc_start=self.JuncStart, junc_end=self.JuncEnd, junc_len=self.JuncLen,
+            read_count=self.ReadCount, has_mutation=self.HasMutation, mismatches=self.Mismatches,
+            indel=self.Indel, alt_editing=self.AltEditing, junc_seq=self.JuncSeq, score=self.Score,
+            would_panic=self.WouldPanic,
+        )
+
+    def ops(self) -> List[int]:
+        n = int(self._rec[0]["aln_len"])
+        return [(int(self._ops[c >> 2]) >> (2 * (c & 3))) & 3 for c in range(n)]
+
+    def gapped(self, tmpl_bases: str, frag_bases: str) -> Tuple[str, str]:
+        """nwalgo.Align's two strings rebuilt from the device ops."""
+        a, b, i, j = [], [], 0, 0
+        for op in self.ops():
+            if op == cabi.OP_INS:
+                a.append("-"); b.append(frag_bases[j]); j += 1
+            elif op == cabi.OP_DEL:
+                a.append(tmpl_bases[i]); b.append("-"); i += 1
+            else:
+                a.append(tmpl_bases[i]); b.append(frag_bases[j]); i += 1; j += 1
+        return "".join(a), "".join(b)
+
+    def WriteTo(self, frag: Fragment, tmpl: Template, tw: int = 80) -> str:
+        """align.go:388-520 (text assembled on the host from the device's record + ops)."""
+        if self._ops is None:
+            raise ValueError("alignment was computed without ops")
+        seq = frag.forward_seq()
+        name = _b(frag.Name)
+        need = lib().treat_b200_format_alignment(tmpl._h, self._rec.ctypes.data, self._ops.ctypes.data, name, seq,
+                                                 len(seq), tw, None, 0)
+        if need < 0:
+            raise TreatError(int(need))
+        buf = C.create_string_buffer(int(need) + 1)
+        lib().treat_b200_format_alignment(tmpl._h, self._rec.ctypes.data, self._ops.ctypes.data, name, seq, len(seq),
+                                          tw, buf, int(need))
+        return buf.raw[: int(need)].decode("latin-1")
+
+    def MarshalBinary(self) -> bytes:
+        """align.go:316-335"""
+        need = lib().treat_b200_marshal_record(self._rec.ctypes.data, self._seq, len(self._seq), None, 0)
+        buf = (C.c_uint8 * int(need))()
+        lib().treat_b200_marshal_record(self._rec.ctypes.data, self._seq, len(self._seq), buf, int(need))
+        return bytes(buf)
+
+    def SimpleAlign(self, f1: Fragment, f2: Fragment) -> Tuple[str, str]:
+        return self._eng.SimpleAlign(f1, f2)
+
+
+class Aligner:
+    """One GPU context (one process per GPU).  Wraps treat_b200_create / set_template / align_batch."""
+
+    def __init__(self, device: int = 0):
+        self._ctx = C.c_void_p()
+        check(lib().treat_b200_create(device, C.byref(self._ctx)))
+        self.device = device
+        self._tmpl = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib().treat_b200_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- template --------------------------------------------------------------------------
+    def SetTemplate(self, tmpl: Template) -> None:
+        check(lib().treat_b200_use_template(self._ctx, tmpl._h), self._ctx)
+        # the context keeps a device copy; remember the identity + offset state it was made from
+        self._tmpl = (tmpl, tmpl.EditOffset)
+
+    def _ensure_template(self, tmpl: Template) -> None:
+        if self._tmpl is None or self._tmpl[0] is not tmpl or self._tmpl[1] != tmpl.EditOffset:
+            self.SetTemplate(tmpl)
+
+    # ---- raw batch entry points ---------------------------------------------------------------
+    def ops_stride(self, max_len: int) -> int:
+        return lib().treat_b200_ops_stride(self._ctx, max_len)
+
+    def align_batch(self, seqs: np.ndarray, seq_off: np.ndarray, read_count: Optional[np.ndarray] = None,
+                    flags: int = WANT_OPS, rec: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None):
+        """treat_b200_align_batch on host buffers; returns (records, ops or None)."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        N = len(seq_off) - 1
+        if rec is None:
+            rec = np.zeros(N, dtype=RECORD_DTYPE)
+        stride = 0
+        if flags & WANT_OPS:
+            max_len = int(np.diff(seq_off.astype(np.int64)).max()) if N else 0
+            stride = self.ops_stride(max_len)
+            if ops is None:
+                ops = np.zeros((N, stride), dtype=np.uint8)
+            else:
+                stride = ops.shape[1]
+        rc = None if read_count is None else np.ascontiguousarray(read_count, dtype=np.uint32)
+        dummy = np.zeros(1, np.uint8)
+        check(lib().treat_b200_align_batch(
+            self._ctx, seqs.ctypes.data if seqs.size else dummy.ctypes.data, seq_off.ctypes.data,
+            rc.ctypes.data if rc is not None else None, N, flags, rec.ctypes.data,
+            ops.ctypes.data if (flags & WANT_OPS) else None, stride), self._ctx)
+        return rec, (ops if flags & WANT_OPS else None)
+
+    def align_batch_device(self, d_seqs: int, d_seq_off: int, d_read_count: int, N: int, max_len: int, flags: int,
+                           d_rec: int, d_ops: int, ops_stride: int, stream: int = 0) -> None:
+        """treat_b200_align_batch_device on raw device pointers (e.g. torch tensors' data_ptr())."""
+        check(lib().treat_b200_align_batch_device(self._ctx, d_seqs, d_seq_off, d_read_count or None, N, max_len, flags,
+                                                  d_rec, d_ops or None, ops_stride, stream or None), self._ctx)
+
+    def synchronize(self) -> None:
+        check(lib().treat_b200_synchronize(self._ctx), self._ctx)
+
+    def launch_count(self) -> int:
+        return lib().treat_b200_launch_count(self._ctx)
+
+    # ---- summaries -------------------------------------------------------------------------------
+    def summary(self) -> np.ndarray:
+        n = lib().treat_b200_summary_len(self._ctx)
+        out = np.zeros(n, dtype=np.uint64)
+        check(lib().treat_b200_get_summary(self._ctx, out.ctypes.data, n), self._ctx)
+        return out
+
+    def reset_summary(self) -> None:
+        check(lib().treat_b200_reset_summary(self._ctx), self._ctx)
+
+    def summary_device_ptr(self) -> Tuple[int, int]:
+        p = C.c_void_p()
+        check(lib().treat_b200_summary_device_ptr(self._ctx, C.byref(p)), self._ctx)
+        return p.value, lib().treat_b200_summary_len(self._ctx)
+
+    def measure_int32_peak(self) -> Tuple[float, float]:
+        a, b = C.c_double(), C.c_double()
+        check(lib().treat_b200_measure_int32_peak(self._ctx, C.byref(a), C.byref(b)), self._ctx)
+        return a.value, b.value
+
+    # ---- Go-shaped API -----------------------------------------------------------------------------
+    def NewAlignments(self, reads, tmpl: Template, excludeSnps: bool = False, want_ops: bool = True) -> List[Alignment]:
+        """The reference's per-read loop (cmd/treat/align.go:114-120, storage.go:738-785) as one batch.
+        `reads` is a FastaBatch or an iterable of (id, seq)."""
+        batch = reads if isinstance(reads, FastaBatch) else FastaBatch.from_records(reads)
+        self._ensure_template(tmpl)
+        flags = (EXCLUDE_SNPS if excludeSnps else 0) | (WANT_OPS if want_ops else 0)
+        rec, ops = self.align_batch(batch.seqs, batch.offsets, batch.read_counts, flags)
+        return [Alignment(rec[i], None if ops is None else ops[i], batch.seq(i), self) for i in range(len(batch))]
+
+    def NewAlignment(self, frag: Fragment, tmpl: Template, excludeSnps: bool = False) -> Alignment:
+        """align.go:237-279 for one fragment (a batch of one)."""
+        batch = FastaBatch.from_records([(frag.Name, frag.forward_seq())])
+        batch.read_counts[0] = frag.ReadCount
+        return self.NewAlignments(batch, tmpl, excludeSnps)[0]
+
+    def SimpleAlign(self, f1: Fragment, f2: Fragment) -> Tuple[str, str]:
+        """align.go:337-386"""
+        s1, s2 = f1.forward_seq(), f2.forward_seq()
+        cap = 2 * (len(s1) + len(s2)) + 64
+        o1, o2 = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        n = lib().treat_b200_simple_align(self._ctx, s1, len(s1), s2, len(s2), ord(_b(f1.EditBase)), o1, o2, cap)
+        self._tmpl = None  # SimpleAlign installs f1 as the context's template
+        if n < 0:
+            raise TreatError(int(n), lib().treat_b200_last_error(self._ctx).decode())
+        return o1.raw[: int(n)].decode("latin-1"), o2.raw[: int(n)].decode("latin-1")
+
+    def cli_align(self, template: Optional[str] = None, fragment: Optional[str] = None, s1: Optional[str] = None,
+                  s2: Optional[str] = None, base: str = "T", offset: int = 0) -> str:
+        """`treat align` stdout (cmd/treat/align.go:59-122)."""
+        out, n = C.c_void_p(), C.c_size_t()
+        err = C.create_string_buffer(512)
+        rc = lib().treat_b200_cli_align(self._ctx, _b(template) if template else None, _b(fragment) if fragment else None,
+                                        _b(s1) if s1 else None, _b(s2) if s2 else None, ord(_b(base)), offset,
+                                        C.byref(out), C.byref(n), err, 512)
+        self._tmpl = None
+        if rc != cabi.OK:
+            raise ValueError(err.value.decode() or lib().treat_b200_last_error(self._ctx).decode())
+        try:
+            return C.string_at(out.value, n.value).decode("latin-1")
+        finally:
+            lib().treat_b200_free(out)

@@ -1,0 +1,138 @@
+"""ctypes binding of libtreat_b200.so: one Python function per symbol of include/treat_b200.h.
+
+This is the same binding a cgo caller would write; nothing here computes.
+Loading fails loudly when the library is missing -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libtreat_b200.so")
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TOO_LONG, ERR_NO_TEMPLATE, ERR_NO_DEVICE, ERR_TEMPLATE, ERR_IO = range(-1, -9, -1)
+FORWARD, REVERSE = 1, -1
+EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY = 0x1, 0x2, 0x4
+ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
+OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
+SUMMARY_HEADER = 16
+
+RECORD_DTYPE = np.dtype(
+    [
+        ("edit_stop", "<i4"), ("junc_start", "<i4"), ("junc_end", "<i4"), ("junc_len", "<i4"),
+        ("read_count", "<u4"),
+        ("has_mutation", "u1"), ("alt_editing", "u1"), ("mismatches", "u1"), ("indel", "u1"),
+        ("score", "<i4"), ("junc_seq_off", "<u4"), ("junc_seq_len", "<u4"),
+        ("aln_len", "<u2"), ("n_bases", "<u2"),
+        ("status", "u1"), ("reserved", "u1", (3,)),
+        ("raw_len", "<u4"),
+    ]
+)
+assert RECORD_DTYPE.itemsize == 48
+
+
+class Packed(C.Structure):
+    """treat_b200_packed"""
+    _fields_ = [
+        ("N", C.c_uint64), ("max_len", C.c_uint32), ("wide", C.c_uint32),
+        ("bases_stride", C.c_uint32), ("counts_stride", C.c_uint32),
+        ("d_n", C.c_void_p), ("d_flags", C.c_void_p), ("d_bases", C.c_void_p), ("d_counts", C.c_void_p),
+        ("d_raw_len", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every function include/treat_b200.h declares
+_P, _U8P, _SZ = C.c_void_p, C.c_void_p, C.c_size_t
+SIGNATURES = {
+    "treat_b200_abi_version": (C.c_int, []),
+    "treat_b200_strerror": (C.c_char_p, [C.c_int]),
+    "treat_b200_last_error": (C.c_char_p, [_P]),
+    "treat_b200_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "treat_b200_destroy": (None, [_P]),
+    "treat_b200_host_alloc": (C.c_int, [C.POINTER(_P), _SZ]),
+    "treat_b200_host_free": (None, [_P]),
+    "treat_b200_set_template": (C.c_int, [_P, _U8P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, C.c_uint32, C.c_int32, C.c_uint8]),
+    "treat_b200_use_template": (C.c_int, [_P, _P]),
+    "treat_b200_align_batch": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, _P, _U8P, C.c_uint32]),
+    "treat_b200_align_batch_device": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
+    "treat_b200_ops_stride": (C.c_uint32, [_P, C.c_uint32]),
+    "treat_b200_synchronize": (C.c_int, [_P]),
+    "treat_b200_packed_layout": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(Packed)]),
+    "treat_b200_pack_device": (C.c_int, [_P, _U8P, _P, C.POINTER(Packed), _P]),
+    "treat_b200_align_packed_device": (C.c_int, [_P, C.POINTER(Packed), _P, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
+    "treat_b200_launch_count": (C.c_uint64, [_P]),
+    "treat_b200_summary_bins": (C.c_uint32, [_P]),
+    "treat_b200_summary_len": (C.c_uint64, [_P]),
+    "treat_b200_get_summary": (C.c_int, [_P, _P, C.c_uint64]),
+    "treat_b200_reset_summary": (C.c_int, [_P]),
+    "treat_b200_summary_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
+    "treat_b200_measure_int32_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "treat_b200_parse_merge_count": (C.c_uint32, [C.c_char_p, _SZ]),
+    "treat_b200_new_fragment": (C.c_int, [_U8P, _SZ, C.c_int, C.c_uint8, _U8P, _P, C.POINTER(_SZ)]),
+    "treat_b200_template_from_fasta": (C.c_int, [C.c_char_p, C.c_int, C.c_uint8, C.c_int32, C.POINTER(_P), C.c_char_p, _SZ]),
+    "treat_b200_template_new": (C.c_int, [C.POINTER(C.c_char_p), C.c_int32, _P, _P, C.c_int32, C.c_int, C.c_uint8, C.POINTER(_P), C.c_char_p, _SZ]),
+    "treat_b200_template_set_offset": (None, [_P, C.c_int32]),
+    "treat_b200_template_free": (None, [_P]),
+    "treat_b200_template_size": (C.c_int32, [_P]),
+    "treat_b200_template_len": (C.c_int32, [_P]),
+    "treat_b200_template_edit_stop": (C.c_int32, [_P]),
+    "treat_b200_template_edit_offset": (C.c_uint32, [_P]),
+    "treat_b200_template_edit_base": (C.c_uint8, [_P]),
+    "treat_b200_template_bases": (_P, [_P]),
+    "treat_b200_template_edit_site": (_P, [_P, C.c_int32]),
+    "treat_b200_template_base_index": (_P, [_P]),
+    "treat_b200_template_n_alt": (C.c_int32, [_P]),
+    "treat_b200_template_alt_start": (C.c_int32, [_P, C.c_int32]),
+    "treat_b200_template_alt_end": (C.c_int32, [_P, C.c_int32]),
+    "treat_b200_template_max": (C.c_uint32, [_P, C.c_int32]),
+    "treat_b200_fasta_read": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "treat_b200_fasta_free": (None, [_P]),
+    "treat_b200_fasta_count": (C.c_uint64, [_P]),
+    "treat_b200_fasta_id": (C.c_char_p, [_P, C.c_uint64]),
+    "treat_b200_fasta_seqs": (_P, [_P]),
+    "treat_b200_fasta_offsets": (_P, [_P]),
+    "treat_b200_fasta_read_counts": (_P, [_P]),
+    "treat_b200_format_alignment": (C.c_int64, [_P, _P, _U8P, C.c_char_p, _U8P, _SZ, C.c_int32, _P, _SZ]),
+    "treat_b200_simple_align": (C.c_int64, [_P, _U8P, _SZ, _U8P, _SZ, C.c_uint8, _P, _P, _SZ]),
+    "treat_b200_marshal_record": (C.c_int64, [_P, _U8P, _SZ, _U8P, _SZ]),
+    "treat_b200_cli_align": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint8, C.c_int32,
+                                       C.POINTER(_P), C.POINTER(_SZ), C.c_char_p, _SZ]),
+    "treat_b200_free": (None, [_P]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libtreat_b200.so (built in-tree by treat_b200._build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "treat_b200 has no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class TreatError(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        msg = lib().treat_b200_strerror(code).decode()
+        super().__init__(f"treat_b200 error {code}: {msg}" + (f" ({detail})" if detail else ""))
+
+
+def check(code: int, ctx=None):
+    if code != OK:
+        detail = lib().treat_b200_last_error(ctx).decode() if ctx else ""
+        raise TreatError(code, detail)

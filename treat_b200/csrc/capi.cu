@@ -1,0 +1,590 @@
+// capi.cu -- device side of the C ABI declared in include/treat_b200.h: the context, the
+// template upload, the batch entry points (host buffers and device buffers) and summaries.
+// There is no CPU path: every align call ends in launch_pack / launch_align.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_format.h"
+#include "host/treat_host.hpp"
+
+using namespace treat_b200;
+
+namespace {
+
+constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
+constexpr uint64_t kChunkReads = 1u << 18;  // reads per pipelined chunk of treat_b200_align_batch
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// device buffers of one in-flight chunk
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops;
+    uint32_t *scalars = nullptr;  // device [2]
+    uint32_t *h_scalars = nullptr;  // pinned [2]
+    void release()
+    {
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops}) b->release();
+        if (scalars) cudaFree(scalars);
+        if (h_scalars) cudaFreeHost(h_scalars);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+struct treat_b200_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int max_smem = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // template
+    bool have_template = false;
+    bool tmpl_wide = false;  // template needs the wide path (non-alphabet base or count >= 255)
+    TemplateDev td{};
+    DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut;
+    std::vector<uint8_t> lut;
+    uint64_t *d_summary = nullptr;
+    uint32_t bins = 0;
+    Slot slot[2];
+    // scratch for the device-resident entry point
+    Slot dev_slot;
+};
+
+#define CK(ctx, expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);            \
+            return TREAT_B200_ERR_CUDA;                                                 \
+        }                                                                               \
+    } while (0)
+
+static int fail(treat_b200_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+extern "C" {
+
+int treat_b200_abi_version(void) { return TREAT_B200_ABI_VERSION; }
+
+const char *treat_b200_strerror(int code)
+{
+    switch (code) {
+    case TREAT_B200_OK: return "ok";
+    case TREAT_B200_ERR_INVALID: return "invalid argument";
+    case TREAT_B200_ERR_CUDA: return "CUDA error";
+    case TREAT_B200_ERR_NOMEM: return "out of memory";
+    case TREAT_B200_ERR_TOO_LONG: return "template or read too long for the kernel geometry";
+    case TREAT_B200_ERR_NO_TEMPLATE: return "no template set";
+    case TREAT_B200_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU path)";
+    case TREAT_B200_ERR_TEMPLATE: return "invalid template";
+    case TREAT_B200_ERR_IO: return "I/O error";
+    default: return "unknown error";
+    }
+}
+
+const char *treat_b200_last_error(const treat_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int treat_b200_create(int device, treat_b200_ctx **out)
+{
+    if (!out) return TREAT_B200_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return TREAT_B200_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TREAT_B200_ERR_NO_DEVICE;
+    if (prop.major != 10) return TREAT_B200_ERR_NO_DEVICE;  // the fatbin holds sm_100a code only
+    if (cudaSetDevice(device) != cudaSuccess) return TREAT_B200_ERR_NO_DEVICE;
+    treat_b200_ctx *ctx = new treat_b200_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return TREAT_B200_ERR_CUDA;
+    }
+    int e = configure_kernels(ctx->max_smem);
+    if (e) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return TREAT_B200_ERR_CUDA;
+    }
+    *out = ctx;
+    return TREAT_B200_OK;
+}
+
+void treat_b200_destroy(treat_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut}) b->release();
+    if (ctx->d_summary) cudaFree(ctx->d_summary);
+    ctx->slot[0].release();
+    ctx->slot[1].release();
+    ctx->dev_slot.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int treat_b200_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return TREAT_B200_ERR_INVALID;
+    if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return TREAT_B200_ERR_NOMEM;
+    }
+    return TREAT_B200_OK;
+}
+void treat_b200_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m, const uint32_t *edit_site, int32_t K,
+                            const int32_t *alt_start, const int32_t *alt_end, int32_t n_alt, uint32_t edit_offset,
+                            int32_t tmpl_edit_stop, uint8_t edit_base)
+{
+    if (!ctx || !bases || !edit_site || m < 1 || K < 2 || n_alt != K - 2 || (n_alt > 0 && (!alt_start || !alt_end)))
+        return fail(ctx, TREAT_B200_ERR_INVALID, "set_template: bad arguments (need m >= 1, K >= 2, n_alt == K-2)");
+    if (m > kMaxTemplateBases || K > kMaxTemplates)
+        return fail(ctx, TREAT_B200_ERR_TOO_LONG, "set_template: template longer than 512 bases or more than 32 rows");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (edit_base >= 'a' && edit_base <= 'z') edit_base -= 32;
+    const int len = m + 1, len_pad = (len + 31) / 32 * 32;
+
+    // packed alphabet: the first three of "ACGT" that are not the edit base; everything else is code 3
+    std::vector<uint8_t> lut(256, 3);
+    {
+        int code = 0;
+        for (const char *c = "ACGT"; *c && code < 3; c++)
+            if ((uint8_t)*c != edit_base) lut[(uint8_t)*c] = (uint8_t)code++;
+    }
+    bool wide = false;
+    std::vector<uint8_t> tb(m), tbw(m);
+    for (int i = 0; i < m; i++) {
+        tbw[i] = bases[i];
+        tb[i] = lut[bases[i]];
+        if (tb[i] == 3) wide = true;
+    }
+    std::vector<uint8_t> tc8((size_t)K * len_pad, 0);
+    std::vector<uint32_t> tc32((size_t)K * len_pad, 0);
+    for (int k = 0; k < K; k++)
+        for (int i = 0; i < len; i++) {
+            const uint32_t c = edit_site[(size_t)k * len + i];
+            if (c >= 255u) wide = true;
+            tc8[(size_t)k * len_pad + i] = (uint8_t)std::min<uint32_t>(c, 255u);
+            tc32[(size_t)k * len_pad + i] = c;
+        }
+    std::vector<int32_t> alt(2 * std::max(n_alt, 1), 0);
+    for (int i = 0; i < n_alt; i++) {
+        alt[i] = alt_start[i];
+        alt[n_alt + i] = alt_end[i];
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, ctx->d_tb.reserve(m));
+    CK(ctx, ctx->d_tb_wide.reserve(m));
+    CK(ctx, ctx->d_tc8.reserve(tc8.size()));
+    CK(ctx, ctx->d_tc32.reserve(tc32.size() * 4));
+    CK(ctx, ctx->d_alt.reserve(alt.size() * 4));
+    CK(ctx, ctx->d_lut.reserve(256));
+    CK(ctx, cudaMemcpy(ctx->d_tb.p, tb.data(), m, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(ctx->d_tb_wide.p, tbw.data(), m, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(ctx->d_tc8.p, tc8.data(), tc8.size(), cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(ctx->d_tc32.p, tc32.data(), tc32.size() * 4, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(ctx->d_alt.p, alt.data(), alt.size() * 4, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(ctx->d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice));
+    ctx->lut = lut;
+    ctx->tmpl_wide = wide;
+    ctx->td = TemplateDev{};
+    ctx->td.alt = (const int32_t *)ctx->d_alt.p;
+    ctx->td.lut = (const uint8_t *)ctx->d_lut.p;
+    ctx->td.m = m;
+    ctx->td.len = len;
+    ctx->td.len_pad = len_pad;
+    ctx->td.K = K;
+    ctx->td.n_alt = n_alt;
+    ctx->td.edit_offset = (int32_t)edit_offset;
+    ctx->td.tmpl_edit_stop = tmpl_edit_stop;
+    ctx->td.edit_base = edit_base;
+    // summary counters are sized by the template
+    const uint32_t bins = (uint32_t)len + 2;
+    if (ctx->d_summary) cudaFree(ctx->d_summary);
+    ctx->d_summary = nullptr;
+    ctx->bins = bins;
+    const size_t sl = (TREAT_B200_SUMMARY_HEADER + 3 * (size_t)bins) * 8;
+    CK(ctx, cudaMalloc((void **)&ctx->d_summary, sl));
+    CK(ctx, cudaMemset(ctx->d_summary, 0, sl));
+    ctx->have_template = true;
+    return TREAT_B200_OK;
+}
+
+int treat_b200_use_template(treat_b200_ctx *ctx, const treat_b200_template *tmpl)
+{
+    if (!ctx || !tmpl) return TREAT_B200_ERR_INVALID;
+    const treat::Template &t = *reinterpret_cast<const treat::Template *>(tmpl);
+    const int m = (int)t.Bases.size(), K = t.Size(), len = m + 1;
+    std::vector<uint32_t> es((size_t)K * len);
+    for (int k = 0; k < K; k++) std::copy(t.EditSite[k].begin(), t.EditSite[k].end(), es.begin() + (size_t)k * len);
+    std::vector<int32_t> as, ae;
+    for (const auto &r : t.AltRegion) {
+        as.push_back(r.Start);
+        ae.push_back(r.End);
+    }
+    return treat_b200_set_template(ctx, (const uint8_t *)t.Bases.data(), m, es.data(), K, as.data(), ae.data(),
+                                   (int32_t)as.size(), t.EditOffset, t.EditStop, (uint8_t)t.EditBase);
+}
+
+uint32_t treat_b200_ops_stride(const treat_b200_ctx *ctx, uint32_t max_len)
+{
+    if (!ctx || !ctx->have_template) return 0;
+    return a16(((uint32_t)ctx->td.m + max_len + 3) / 4);
+}
+
+int treat_b200_synchronize(treat_b200_ctx *ctx)
+{
+    if (!ctx) return TREAT_B200_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (Slot *s : {&ctx->slot[0], &ctx->slot[1], &ctx->dev_slot})
+        if (s->stream) CK(ctx, cudaStreamSynchronize(s->stream));
+    return TREAT_B200_OK;
+}
+
+uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int treat_b200_packed_layout(const treat_b200_ctx *ctx, uint64_t N, uint32_t max_len, uint32_t wide,
+                             treat_b200_packed *out)
+{
+    if (!ctx || !out) return TREAT_B200_ERR_INVALID;
+    if (max_len > kMaxReadLen) return TREAT_B200_ERR_TOO_LONG;
+    memset(out, 0, sizeof *out);
+    out->N = N;
+    out->max_len = max_len;
+    out->wide = wide ? 1 : 0;
+    out->bases_stride = std::max(16u, wide ? a16(max_len) : a16((max_len + 3) / 4));
+    out->counts_stride = wide ? a16(4 * (max_len + 1)) : a16(max_len + 1);
+    return TREAT_B200_OK;
+}
+
+static int ensure_scalars(treat_b200_ctx *ctx, Slot &s)
+{
+    if (!s.scalars) CK(ctx, cudaMalloc((void **)&s.scalars, 8));
+    if (!s.h_scalars) CK(ctx, cudaMallocHost((void **)&s.h_scalars, 8));
+    return TREAT_B200_OK;
+}
+
+static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
+                   const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st)
+{
+    PackParams pp{};
+    pp.seqs = d_seqs;
+    pp.off = d_off;
+    pp.off_bias = off_bias;
+    pp.N = dst->N;
+    pp.n = dst->d_n;
+    pp.flags = dst->d_flags;
+    pp.bases = dst->d_bases;
+    pp.counts = dst->d_counts;
+    pp.raw_len = dst->d_raw_len;
+    pp.bases_stride = dst->bases_stride;
+    pp.counts_stride = dst->counts_stride;
+    pp.stage_cap = a16(dst->max_len + 1);
+    pp.lut = ctx->td.lut;
+    pp.edit_base = ctx->td.edit_base;
+    pp.scalars = d_scalars;
+    int e = launch_pack(pp, dst->wide != 0, ctx->num_sms, ctx->max_smem, st);
+    if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: read too long for shared-memory staging");
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_pack launch: ") + cudaGetErrorString((cudaError_t)e));
+    if (dst->N) ctx->launches++;
+    return TREAT_B200_OK;
+}
+
+static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t ncap, const uint32_t *d_read_count,
+                    uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st)
+{
+    if (src->N == 0) return TREAT_B200_OK;
+    const bool wide = src->wide != 0;
+    if (!wide && ctx->tmpl_wide)
+        return fail(ctx, TREAT_B200_ERR_INVALID, "align: this template needs wide-packed reads (wide=1)");
+    AlignParams ap{};
+    ap.n = src->d_n;
+    ap.rflags = src->d_flags;
+    ap.bases = src->d_bases;
+    ap.counts = src->d_counts;
+    ap.raw_len = src->d_raw_len;
+    ap.read_count = d_read_count;
+    ap.bases_stride = src->bases_stride;
+    ap.counts_stride = src->counts_stride;
+    ap.N = src->N;
+    ap.ncap = ncap;
+    ap.t = ctx->td;
+    ap.t.tb = (const uint8_t *)(wide ? ctx->d_tb_wide.p : ctx->d_tb.p);
+    ap.t.tcount = wide ? ctx->d_tc32.p : ctx->d_tc8.p;
+    ap.rec = d_rec;
+    ap.ops = (flags & TREAT_B200_WANT_OPS) ? d_ops : nullptr;
+    ap.ops_stride = ops_stride;
+    ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : ctx->d_summary;
+    ap.bins = ctx->bins;
+    ap.flags = flags;
+    if (ap.ops) {
+        if (ops_stride % 16 || ops_stride < a16(((uint32_t)ctx->td.m + ncap + 3) / 4))
+            return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small or not a multiple of 16");
+    }
+    if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
+    int e = launch_align(ap, wide, ctx->num_sms, ctx->max_smem, st);
+    if (e == -1000 || e == -1001)
+        return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: read/template geometry exceeds shared memory");
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_align launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
+    return TREAT_B200_OK;
+}
+
+static bool misaligned(const void *p) { return ((uintptr_t)p & 15u) != 0; }
+
+int treat_b200_pack_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
+                           const treat_b200_packed *dst, void *stream)
+{
+    if (!ctx || !dst || (dst->N && (!d_seqs || !d_seq_off))) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "pack: set a template first (edit base)");
+    if (dst->max_len > kMaxReadLen) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: read longer than 16384");
+    if (misaligned(dst->d_bases) || misaligned(dst->d_counts) || dst->bases_stride % 16 || dst->counts_stride % 16)
+        return fail(ctx, TREAT_B200_ERR_INVALID, "pack: packed buffers must be 16-byte aligned");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = ensure_scalars(ctx, ctx->dev_slot);
+    if (rc) return rc;
+    CK(ctx, cudaMemsetAsync(ctx->dev_slot.scalars, 0, 8, st));
+    return do_pack(ctx, d_seqs, d_seq_off, 0, dst, ctx->dev_slot.scalars, st);
+}
+
+int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed *src, const uint32_t *d_read_count,
+                                   uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride,
+                                   void *stream)
+{
+    if (!ctx || !src || !d_rec) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    if (misaligned(src->d_bases) || misaligned(src->d_counts) || misaligned(d_rec) || misaligned(d_ops))
+        return fail(ctx, TREAT_B200_ERR_INVALID, "align: buffers must be 16-byte aligned");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    // n <= raw length: size the launch for max_len (callers that know max n can pass it as max_len)
+    return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st);
+}
+
+// pack + (tiny sync for max n) + align on one slot's buffers
+static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
+                     const uint32_t *d_rc, uint64_t N, uint32_t max_len, uint32_t flags, treat_b200_record *d_rec,
+                     uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st, bool force_wide, bool *saturated)
+{
+    const bool wide = ctx->tmpl_wide || force_wide;
+    treat_b200_packed pk;
+    int rc = treat_b200_packed_layout(ctx, N, max_len, wide, &pk);
+    if (rc) return fail(ctx, rc, "align: read longer than 16384");
+    CK(ctx, s.n.reserve(N * 2));
+    CK(ctx, s.flags.reserve(N));
+    CK(ctx, s.bases.reserve(N * (size_t)pk.bases_stride));
+    CK(ctx, s.counts.reserve(N * (size_t)pk.counts_stride));
+    CK(ctx, s.raw_len.reserve(N * 4));
+    pk.d_n = (uint16_t *)s.n.p;
+    pk.d_flags = (uint8_t *)s.flags.p;
+    pk.d_bases = (uint8_t *)s.bases.p;
+    pk.d_counts = (uint8_t *)s.counts.p;
+    pk.d_raw_len = (uint32_t *)s.raw_len.p;
+    rc = ensure_scalars(ctx, s);
+    if (rc) return rc;
+    CK(ctx, cudaMemsetAsync(s.scalars, 0, 8, st));
+    rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));  // 8 bytes: max n sizes the align kernel's shared memory
+    const uint32_t max_n = s.h_scalars[0];
+    if (saturated) *saturated = s.h_scalars[1] != 0;
+    if (!wide && s.h_scalars[1]) return TREAT_B200_OK;  // caller re-runs this chunk on the wide path
+    return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st);
+}
+
+int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
+                                  const uint32_t *d_read_count, uint64_t N, uint32_t max_len, uint32_t flags,
+                                  treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, void *stream)
+{
+    if (!ctx || (N && (!d_seqs || !d_seq_off || !d_rec))) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    if (misaligned(d_rec) || misaligned(d_ops)) return fail(ctx, TREAT_B200_ERR_INVALID, "align: rec/ops must be 16-byte aligned");
+    if (N == 0) return TREAT_B200_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    bool sat = false;
+    int rc = run_chunk(ctx, ctx->dev_slot, d_seqs, d_seq_off, 0, d_read_count, N, max_len, flags, d_rec, d_ops,
+                       ops_stride, st, false, &sat);
+    if (rc) return rc;
+    if (sat && !ctx->tmpl_wide)
+        rc = run_chunk(ctx, ctx->dev_slot, d_seqs, d_seq_off, 0, d_read_count, N, max_len, flags, d_rec, d_ops,
+                       ops_stride, st, true, nullptr);
+    return rc;
+}
+
+int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off,
+                           const uint32_t *read_count, uint64_t N, uint32_t flags, treat_b200_record *rec, uint8_t *ops,
+                           uint32_t ops_stride)
+{
+    if (!ctx || (N && (!seqs || !seq_off || !rec))) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    if ((flags & TREAT_B200_WANT_OPS) && !ops) return fail(ctx, TREAT_B200_ERR_INVALID, "align: WANT_OPS without ops buffer");
+    if (N == 0) return TREAT_B200_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
+    for (int i = 0; i < 2; i++)
+        if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
+
+    int rc = TREAT_B200_OK;
+    uint64_t chunk_idx = 0;
+    for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += kChunkReads, chunk_idx++) {
+        const uint64_t cn = std::min<uint64_t>(kChunkReads, N - c0);
+        Slot &s = ctx->slot[chunk_idx & 1];
+        cudaStream_t st = s.stream;
+        CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk (incl. its D2H) is done
+        const uint64_t b0 = seq_off[c0], b1 = seq_off[c0 + cn];
+        uint32_t max_len = 0;
+        for (uint64_t i = c0; i < c0 + cn; i++) {
+            const uint64_t l = seq_off[i + 1] - seq_off[i];
+            if (seq_off[i + 1] < seq_off[i] || l > kMaxReadLen)
+                return fail(ctx, l > kMaxReadLen ? TREAT_B200_ERR_TOO_LONG : TREAT_B200_ERR_INVALID,
+                            "align: read offsets not monotone or read longer than 16384");
+            max_len = std::max<uint32_t>(max_len, (uint32_t)l);
+        }
+        const uint32_t need_stride = treat_b200_ops_stride(ctx, max_len);
+        if (want_ops && (ops_stride < need_stride || ops_stride % 16))
+            return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small (see treat_b200_ops_stride)");
+        CK(ctx, s.seqs.reserve(b1 - b0 + 16));
+        CK(ctx, s.off.reserve((cn + 1) * 8));
+        CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
+        if (read_count) CK(ctx, s.rc.reserve(cn * 4));
+        if (want_ops) CK(ctx, s.ops.reserve(cn * (size_t)ops_stride));
+        if (b1 > b0) CK(ctx, cudaMemcpyAsync(s.seqs.p, seqs + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(s.off.p, seq_off + c0, (cn + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (read_count) CK(ctx, cudaMemcpyAsync(s.rc.p, read_count + c0, cn * 4, cudaMemcpyHostToDevice, st));
+        bool sat = false;
+        rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0,
+                       read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len, flags, (treat_b200_record *)s.rec.p,
+                       (uint8_t *)s.ops.p, ops_stride, st, false, &sat);
+        if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
+            rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0,
+                           read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len, flags,
+                           (treat_b200_record *)s.rec.p, (uint8_t *)s.ops.p, ops_stride, st, true, nullptr);
+        if (rc) break;
+        CK(ctx, cudaMemcpyAsync(rec + c0, s.rec.p, cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, st));
+        if (want_ops)
+            CK(ctx, cudaMemcpyAsync(ops + c0 * (size_t)ops_stride, s.ops.p, cn * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream);
+        if (e != cudaSuccess && rc == TREAT_B200_OK) {
+            ctx->err = std::string("stream sync: ") + cudaGetErrorString(e);
+            rc = TREAT_B200_ERR_CUDA;
+        }
+    }
+    return rc;
+}
+
+uint32_t treat_b200_summary_bins(const treat_b200_ctx *ctx) { return ctx ? ctx->bins : 0; }
+uint64_t treat_b200_summary_len(const treat_b200_ctx *ctx)
+{
+    return ctx && ctx->have_template ? TREAT_B200_SUMMARY_HEADER + 3ull * ctx->bins : 0;
+}
+
+int treat_b200_get_summary(treat_b200_ctx *ctx, uint64_t *out, uint64_t len)
+{
+    if (!ctx || !out) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "summary: no template");
+    if (len < treat_b200_summary_len(ctx)) return fail(ctx, TREAT_B200_ERR_INVALID, "summary: buffer too small");
+    int rc = treat_b200_synchronize(ctx);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpy(out, ctx->d_summary, treat_b200_summary_len(ctx) * 8, cudaMemcpyDeviceToHost));
+    return TREAT_B200_OK;
+}
+
+int treat_b200_reset_summary(treat_b200_ctx *ctx)
+{
+    if (!ctx) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return TREAT_B200_OK;
+    int rc = treat_b200_synchronize(ctx);
+    if (rc) return rc;
+    CK(ctx, cudaMemset(ctx->d_summary, 0, treat_b200_summary_len(ctx) * 8));
+    return TREAT_B200_OK;
+}
+
+int treat_b200_summary_device_ptr(treat_b200_ctx *ctx, uint64_t **d_ptr)
+{
+    if (!ctx || !d_ptr) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "summary: no template");
+    *d_ptr = ctx->d_summary;
+    return TREAT_B200_OK;
+}
+
+int treat_b200_measure_int32_peak(treat_b200_ctx *ctx, double *lane_ops_per_s, double *sm_mhz_effective)
+{
+    if (!ctx || !lane_ops_per_s) return TREAT_B200_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int iters = 20000;
+    const size_t threads = (size_t)ctx->num_sms * 8 * 256;
+    int *d_out = nullptr;
+    CK(ctx, cudaMalloc((void **)&d_out, threads * 4));
+    cudaEvent_t e0, e1;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(ctx, cudaEventRecord(e0, ctx->stream));
+        int e = launch_int32_peak(ctx->num_sms, iters, d_out, ctx->stream);
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_int32_peak launch failed");
+        ctx->launches++;
+        CK(ctx, cudaEventRecord(e1, ctx->stream));
+        CK(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    const double ops = (double)threads * iters * 128.0;  // 8 x 8 x (add + max) per iteration
+    *lane_ops_per_s = ops / (best * 1e-3);
+    if (sm_mhz_effective) *sm_mhz_effective = *lane_ops_per_s / ((double)ctx->num_sms * 128.0) / 1e6;
+    return TREAT_B200_OK;
+}
+
+}  // extern "C"

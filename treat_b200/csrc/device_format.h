@@ -1,0 +1,78 @@
+// device_format.h -- parameter blocks shared by the kernels (kernels.cu) and the C ABI (capi.cu).
+#pragma once
+#include <cstdint>
+
+#include "../../include/treat_b200.h"
+
+namespace treat_b200 {
+
+// Largest template the one-pass wavefront handles: 32 lanes x 16 columns per lane.
+constexpr int kMaxTemplateBases = 512;
+// Raw reads longer than this are refused (ERR_TOO_LONG); keeps n in uint16 and bounds shared memory.
+constexpr uint32_t kMaxReadLen = 16384;
+constexpr int kMaxTemplates = 32;  // K = FE + PE + alternatives
+
+// Device copy of the Template (template.go:41-49) in the form the kernels read.
+struct TemplateDev {
+    const uint8_t *tb;      // [m] base codes (2-bit alphabet codes, or raw bytes on the wide path)
+    const void *tcount;     // [K][len_pad] EditSite, uint8 (packed path) or uint32 (wide path)
+    const int32_t *alt;     // [2*n_alt] alt_start..., alt_end...  (after SetOffset)
+    const uint8_t *lut;     // [256] upper-cased byte -> alphabet code (0..2, 3 = other)
+    int32_t m, len, len_pad, K, n_alt;
+    int32_t edit_offset, tmpl_edit_stop;
+    uint8_t edit_base;
+};
+
+struct PackParams {
+    const uint8_t *seqs;    // raw reads; read r = seqs[off[r]-off_bias .. off[r+1]-off_bias)
+    const uint64_t *off;
+    uint64_t off_bias;
+    uint64_t N;
+    uint16_t *n;
+    uint8_t *flags;
+    uint8_t *bases;
+    uint8_t *counts;
+    uint32_t *raw_len;
+    uint32_t bases_stride, counts_stride;
+    uint32_t stage_cap;     // per-warp staging capacity in bases (>= max_len + 1)
+    const uint8_t *lut;
+    uint8_t edit_base;
+    uint32_t *scalars;      // [0] max n (atomicMax), [1] any saturated edit-base run
+};
+
+struct AlignParams {
+    // packed reads
+    const uint16_t *n;
+    const uint8_t *rflags;
+    const uint8_t *bases;
+    const uint8_t *counts;
+    const uint32_t *raw_len;
+    const uint32_t *read_count;  // may be null -> 1
+    uint32_t bases_stride, counts_stride;
+    uint64_t N;
+    uint32_t ncap;               // largest n this launch is sized for
+    // template
+    TemplateDev t;
+    // outputs
+    treat_b200_record *rec;
+    uint8_t *ops;                // may be null
+    uint32_t ops_stride;
+    uint64_t *summary;           // may be null
+    uint32_t bins;
+    uint32_t flags;
+    // shared-memory carve-up (bytes, all multiples of 16)
+    uint32_t sm_tmpl_bytes;      // CTA-wide template section
+    uint32_t sm_warp_bytes;      // per-warp section
+    uint32_t sm_stage_b, sm_stage_c;  // stage buffer sizes (bases, counts)
+    uint32_t sm_rb, sm_dir, sm_ops, sm_t2f, sm_tbits;
+};
+
+// launchers (kernels.cu)
+int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
+int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
+// fills the shared-memory geometry of p for (m, K, ncap, wide); returns columns-per-lane or -1
+int plan_align(AlignParams &p, bool wide);
+int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream);
+int configure_kernels(int max_smem_optin);
+
+}  // namespace treat_b200

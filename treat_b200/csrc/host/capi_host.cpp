@@ -1,0 +1,195 @@
+// capi_host.cpp -- C exports of the host-side mirror (treat_host.hpp) declared in
+// include/treat_b200.h: fragments, templates, FASTA, text formatting.  No GPU work except
+// treat_b200_simple_align / treat_b200_cli_align, which call the batch entry point.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "treat_host.hpp"
+
+using treat::Fragment;
+using treat::Template;
+
+namespace {
+void set_err(char *err, size_t errlen, const std::string &msg)
+{
+    if (err && errlen) {
+        const size_t n = std::min(errlen - 1, msg.size());
+        memcpy(err, msg.data(), n);
+        err[n] = 0;
+    }
+}
+const Template *T(const treat_b200_template *t) { return reinterpret_cast<const Template *>(t); }
+int64_t emit(const std::string &s, char *out, size_t cap)
+{
+    if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
+    return (int64_t)s.size();
+}
+}  // namespace
+
+struct treat_b200_fasta {
+    treat::FastaBatch b;
+};
+
+extern "C" {
+
+uint32_t treat_b200_parse_merge_count(const char *id, size_t len) { return treat::parseMergeCount(std::string(id, len)); }
+
+int treat_b200_new_fragment(const uint8_t *seq, size_t len, int orientation, uint8_t base, uint8_t *bases_out,
+                            uint32_t *edit_site_out, size_t *n_out)
+{
+    if ((!seq && len) || !bases_out || !edit_site_out || !n_out) return TREAT_B200_ERR_INVALID;
+    Fragment f = treat::NewFragment("", std::string((const char *)seq, len),
+                                    orientation == TREAT_B200_REVERSE ? treat::REVERSE : treat::FORWARD, (char)base);
+    memcpy(bases_out, f.Bases.data(), f.Bases.size());
+    memcpy(edit_site_out, f.EditSite.data(), f.EditSite.size() * sizeof(uint32_t));
+    *n_out = f.Bases.size();
+    return TREAT_B200_OK;
+}
+
+int treat_b200_template_from_fasta(const char *path, int orientation, uint8_t base, int32_t offset,
+                                   treat_b200_template **out, char *err, size_t errlen)
+{
+    if (!path || !out) return TREAT_B200_ERR_INVALID;
+    *out = nullptr;
+    Template *t = new Template();
+    std::string e;
+    if (!treat::NewTemplateFromFasta(path, orientation == TREAT_B200_REVERSE ? treat::REVERSE : treat::FORWARD,
+                                     (char)base, t, &e)) {
+        delete t;
+        set_err(err, errlen, e);
+        return e.rfind("Invalid FASTA file", 0) == 0 ? TREAT_B200_ERR_IO : TREAT_B200_ERR_TEMPLATE;
+    }
+    if (offset) t->SetOffset(offset);
+    *out = reinterpret_cast<treat_b200_template *>(t);
+    return TREAT_B200_OK;
+}
+
+int treat_b200_template_new(const char *const *seqs, int32_t n_seqs, const int32_t *alt_start, const int32_t *alt_end,
+                            int32_t n_regions, int orientation, uint8_t base, treat_b200_template **out, char *err,
+                            size_t errlen)
+{
+    if (!seqs || !out || n_seqs < 0 || n_regions < 0) return TREAT_B200_ERR_INVALID;
+    *out = nullptr;
+    if (n_seqs < 2) {
+        set_err(err, errlen, "Must provide at least 2 templates. Full and Pre edited");
+        return TREAT_B200_ERR_TEMPLATE;
+    }
+    const treat::OrientationType o = orientation == TREAT_B200_REVERSE ? treat::REVERSE : treat::FORWARD;
+    std::vector<Fragment> fr;
+    for (int i = 0; i < n_seqs; i++) fr.push_back(treat::NewFragment("", seqs[i], o, (char)base));
+    std::vector<treat::AltRegion> regions;
+    for (int i = 0; i < n_regions; i++) regions.push_back({alt_start ? alt_start[i] : 0, alt_end ? alt_end[i] : 0});
+    Template *t = new Template();
+    std::string e;
+    if (!treat::NewTemplate(fr[0], fr[1], std::vector<Fragment>(fr.begin() + 2, fr.end()), regions, t, &e)) {
+        delete t;
+        set_err(err, errlen, e);
+        return TREAT_B200_ERR_TEMPLATE;
+    }
+    *out = reinterpret_cast<treat_b200_template *>(t);
+    return TREAT_B200_OK;
+}
+
+void treat_b200_template_set_offset(treat_b200_template *t, int32_t offset)
+{
+    if (t) reinterpret_cast<Template *>(t)->SetOffset(offset);
+}
+void treat_b200_template_free(treat_b200_template *t) { delete reinterpret_cast<Template *>(t); }
+int32_t treat_b200_template_size(const treat_b200_template *t) { return T(t)->Size(); }
+int32_t treat_b200_template_len(const treat_b200_template *t) { return T(t)->Len(); }
+int32_t treat_b200_template_edit_stop(const treat_b200_template *t) { return T(t)->EditStop; }
+uint32_t treat_b200_template_edit_offset(const treat_b200_template *t) { return T(t)->EditOffset; }
+uint8_t treat_b200_template_edit_base(const treat_b200_template *t) { return (uint8_t)T(t)->EditBase; }
+const uint8_t *treat_b200_template_bases(const treat_b200_template *t) { return (const uint8_t *)T(t)->Bases.data(); }
+const uint32_t *treat_b200_template_edit_site(const treat_b200_template *t, int32_t k)
+{
+    return (k < 0 || k >= T(t)->Size()) ? nullptr : T(t)->EditSite[k].data();
+}
+const uint32_t *treat_b200_template_base_index(const treat_b200_template *t) { return T(t)->BaseIndex.data(); }
+int32_t treat_b200_template_n_alt(const treat_b200_template *t) { return (int32_t)T(t)->AltRegion.size(); }
+int32_t treat_b200_template_alt_start(const treat_b200_template *t, int32_t i) { return T(t)->AltRegion[i].Start; }
+int32_t treat_b200_template_alt_end(const treat_b200_template *t, int32_t i) { return T(t)->AltRegion[i].End; }
+uint32_t treat_b200_template_max(const treat_b200_template *t, int32_t i) { return T(t)->Max(i); }
+
+int treat_b200_fasta_read(const char *path, treat_b200_fasta **out)
+{
+    if (!path || !out) return TREAT_B200_ERR_INVALID;
+    treat_b200_fasta *f = new treat_b200_fasta();
+    std::string e;
+    if (!treat::ReadFasta(path, &f->b, &e)) {
+        delete f;
+        *out = nullptr;
+        return TREAT_B200_ERR_IO;
+    }
+    *out = f;
+    return TREAT_B200_OK;
+}
+void treat_b200_fasta_free(treat_b200_fasta *f) { delete f; }
+uint64_t treat_b200_fasta_count(const treat_b200_fasta *f) { return f->b.size(); }
+const char *treat_b200_fasta_id(const treat_b200_fasta *f, uint64_t i) { return f->b.ids[i].c_str(); }
+const uint8_t *treat_b200_fasta_seqs(const treat_b200_fasta *f) { return f->b.seqs.data(); }
+const uint64_t *treat_b200_fasta_offsets(const treat_b200_fasta *f) { return f->b.offsets.data(); }
+const uint32_t *treat_b200_fasta_read_counts(const treat_b200_fasta *f) { return f->b.read_counts.data(); }
+
+int64_t treat_b200_format_alignment(const treat_b200_template *t, const treat_b200_record *rec, const uint8_t *ops,
+                                    const char *name, const uint8_t *seq, size_t seq_len, int32_t tw, char *out,
+                                    size_t cap)
+{
+    if (!t || !rec || !ops || (!seq && seq_len)) return TREAT_B200_ERR_INVALID;
+    if (tw > 0 && tw <= 4) return TREAT_B200_ERR_INVALID;  // the reference divides by tw-4 (align.go:450)
+    const Template &tm = *T(t);
+    Fragment frag = treat::NewFragment(name ? name : "", std::string((const char *)seq, seq_len), treat::FORWARD, tm.EditBase);
+    treat::Alignment a = treat::Alignment::FromRecord(*rec, ops, seq, seq_len);
+    return emit(a.WriteTo(frag, tm, tw), out, cap);
+}
+
+int64_t treat_b200_simple_align(treat_b200_ctx *ctx, const uint8_t *s1, size_t l1, const uint8_t *s2, size_t l2,
+                                uint8_t base, char *out1, char *out2, size_t cap)
+{
+    if (!ctx || (!s1 && l1) || (!s2 && l2)) return TREAT_B200_ERR_INVALID;
+    Fragment f1 = treat::NewFragment("1-1", std::string((const char *)s1, l1), treat::FORWARD, (char)base);
+    Fragment f2 = treat::NewFragment("2-1", std::string((const char *)s2, l2), treat::FORWARD, (char)base);
+    treat::Aligner eng(ctx);
+    std::string a1, a2, err;
+    if (!eng.SimpleAlign(f1, f2, &a1, &a2, &err)) return TREAT_B200_ERR_CUDA;
+    emit(a1, out1, cap);
+    return emit(a2, out2, cap);
+}
+
+int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *seq, size_t seq_len, uint8_t *out,
+                                  size_t cap)
+{
+    if (!rec) return TREAT_B200_ERR_INVALID;
+    treat::Alignment a = treat::Alignment::FromRecord(*rec, nullptr, seq, seq_len);
+    std::vector<uint8_t> b = a.MarshalBinary();
+    if (out && cap) memcpy(out, b.data(), std::min(cap, b.size()));
+    return (int64_t)b.size();
+}
+
+int treat_b200_cli_align(treat_b200_ctx *ctx, const char *template_path, const char *fragment_path, const char *s1,
+                         const char *s2, uint8_t base, int32_t offset, char **out, size_t *out_len, char *err,
+                         size_t errlen)
+{
+    if (!ctx || !out || !out_len) return TREAT_B200_ERR_INVALID;
+    std::string text, e;
+    const bool ok = treat::CliAlign(ctx, template_path ? template_path : "", fragment_path ? fragment_path : "",
+                                    s1 ? s1 : "", s2 ? s2 : "", std::string(1, (char)base), offset, &text, &e);
+    if (!ok) {
+        set_err(err, errlen, e);
+        *out = nullptr;
+        *out_len = 0;
+        return TREAT_B200_ERR_INVALID;
+    }
+    *out = (char *)malloc(text.size() + 1);
+    if (!*out) return TREAT_B200_ERR_NOMEM;
+    memcpy(*out, text.data(), text.size());
+    (*out)[text.size()] = 0;
+    *out_len = text.size();
+    return TREAT_B200_OK;
+}
+
+void treat_b200_free(void *p) { free(p); }
+
+}  // extern "C"

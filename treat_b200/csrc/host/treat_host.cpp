@@ -1,0 +1,556 @@
+// treat_host.cpp -- host-side mirror of package treat (see treat_host.hpp).  No DP here.
+#include "treat_host.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+
+namespace treat {
+
+namespace {
+
+inline char upper(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+inline bool isSpace(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }  // unicode.IsSpace, ASCII subset
+
+std::string trimSpace(const std::string &s)
+{
+    size_t b = 0, e = s.size();
+    while (b < e && isSpace(s[b])) b++;
+    while (e > b && isSpace(s[e - 1])) e--;
+    return s.substr(b, e - b);
+}
+
+// strconv.Atoi on a string of ASCII digits: false on int64 range error
+bool atoiDigits(const std::string &d, int64_t *out)
+{
+    uint64_t v = 0;
+    for (char c : d) {
+        const uint64_t x = (uint64_t)(c - '0');
+        if (v > (0x7fffffffffffffffULL - x) / 10) return false;
+        v = v * 10 + x;
+    }
+    *out = (int64_t)v;
+    return true;
+}
+
+// first match of `<key>(\d+)` in id (startPattern / endPattern of template.go:33-34)
+int findAttr(const std::string &id, const std::string &key)
+{
+    size_t p = 0;
+    while ((p = id.find(key, p)) != std::string::npos) {
+        size_t d = p + key.size(), e = d;
+        while (e < id.size() && id[e] >= '0' && id[e] <= '9') e++;
+        if (e > d) {
+            int64_t v;
+            if (!atoiDigits(id.substr(d, e - d), &v)) return 0;  // Atoi error -> 0 (template.go:70-72)
+            return (int)v;
+        }
+        p++;
+    }
+    return -1;
+}
+
+// writeBase, align.go:88-93
+inline void writeBase(std::string &buf, char base, uint32_t count, uint32_t max)
+{
+    buf.append(max - count, '-');
+    if (count > 0) buf.append(count, base);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ fragment.go
+
+uint32_t parseMergeCount(const std::string &recId)
+{
+    const std::string t = trimSpace(recId);
+    const std::string head = t.substr(0, t.find(' '));  // SplitN(..., " ", 2)[0]
+    // `.+[_\-](\d+)$`: greedy prefix, so the separator is the last '_' or '-'
+    const size_t sep = head.find_last_of("_-");
+    if (sep == std::string::npos || sep == 0 || sep + 1 >= head.size()) return 1;
+    const std::string digits = head.substr(sep + 1);
+    if (!std::all_of(digits.begin(), digits.end(), [](char c) { return c >= '0' && c <= '9'; })) return 1;
+    int64_t v;
+    if (!atoiDigits(digits, &v)) return 1;
+    return (uint32_t)v;
+}
+
+Fragment NewFragment(const std::string &name, const std::string &seqIn, OrientationType orientation, char base)
+{
+    Fragment f;
+    base = upper(base);
+    std::string seq(seqIn);
+    if (orientation == REVERSE) std::reverse(seq.begin(), seq.end());  // reversal only, no complement
+    std::transform(seq.begin(), seq.end(), seq.begin(), upper);
+    uint32_t run = 0;
+    for (char c : seq) {
+        if (c != base) {
+            f.EditSite.push_back(run);
+            run = 0;
+            f.Bases.push_back(c);
+        } else {
+            run++;
+        }
+    }
+    f.EditSite.push_back(run);
+    f.Name = name;
+    f.ReadCount = parseMergeCount(name);
+    f.EditBase = base;
+    return f;
+}
+
+std::string Fragment::String() const
+{
+    std::string s;
+    for (size_t i = 0; i < EditSite.size(); i++) {
+        s.append(EditSite[i], EditBase);
+        if (i < Bases.size()) s.push_back(Bases[i]);
+    }
+    return s;
+}
+
+std::string Fragment::ToFasta() const { return ">" + Name + "\n" + String(); }
+
+// ------------------------------------------------------------------ gofasta
+
+bool ReadFasta(const std::string &path, FastaBatch *out, std::string *err)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in) {
+        if (err) *err = "open " + path + ": no such file or directory";
+        return false;
+    }
+    std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    out->ids.clear();
+    out->seqs.clear();
+    out->offsets.assign(1, 0);
+    out->read_counts.clear();
+    size_t pos = data.find('>');  // bytes before the first record are skipped
+    bool open = false;
+    while (pos != std::string::npos && pos < data.size()) {
+        size_t eol = data.find('\n', pos);
+        if (eol == std::string::npos) eol = data.size();
+        size_t le = eol;
+        if (le > pos && data[le - 1] == '\r') le--;
+        if (data[pos] == '>') {
+            if (open) out->offsets.push_back(out->seqs.size());
+            out->ids.push_back(trimSpace(data.substr(pos + 1, le - pos - 1)));
+            open = true;
+        } else if (open) {
+            out->seqs.insert(out->seqs.end(), data.begin() + pos, data.begin() + le);
+        }
+        pos = eol + 1;
+    }
+    if (open) out->offsets.push_back(out->seqs.size());
+    out->read_counts.reserve(out->ids.size());
+    for (const auto &id : out->ids) out->read_counts.push_back(parseMergeCount(id));
+    return true;
+}
+
+// ------------------------------------------------------------------ template.go
+
+bool NewTemplate(const Fragment &full, const Fragment &pre, const std::vector<Fragment> &alt,
+                 const std::vector<AltRegion> &altRegion, Template *out, std::string *err)
+{
+    if (full.Bases != pre.Bases || full.EditBase != pre.EditBase) {
+        if (err) *err = "Invalid template sequences. Full and Pre templates must have the same non-edit bases";
+        return false;
+    }
+    for (const auto &a : alt) {
+        if (full.Bases != a.Bases || full.EditBase != a.EditBase) {
+            if (err) *err = "Invalid alt template sequence. All templates must have the same non-edit bases";
+            return false;
+        }
+    }
+    if (alt.size() != altRegion.size()) {
+        if (err) *err = "Invalid alt templates. Please specify the alt regions";
+        return false;
+    }
+    Template t;
+    t.Bases = full.Bases;
+    t.EditBase = full.EditBase;
+    t.EditSite.push_back(full.EditSite);
+    t.EditSite.push_back(pre.EditSite);
+    for (const auto &a : alt) t.EditSite.push_back(a.EditSite);
+    t.AltRegion = altRegion;
+    const int n = (int)t.EditSite[0].size();
+    uint32_t index = 0;
+    for (int i = 0; i < n; i++) {
+        index += std::max(t.EditSite[0][i], t.EditSite[1][i]);
+        if (i > 0 && i != n - 1) index++;
+        t.BaseIndex.push_back(index);
+    }
+    t.EditStop = n - 1;
+    for (int j = n - 1; j >= 0; j--) {
+        if (t.EditSite[0][j] != t.EditSite[1][j]) {
+            t.EditStop = (n - 1) - j;
+            break;
+        }
+    }
+    t.EditStop--;
+    *out = std::move(t);
+    return true;
+}
+
+bool NewTemplateFromFasta(const std::string &path, OrientationType orientation, char base, Template *out,
+                          std::string *err)
+{
+    FastaBatch fa;
+    std::string e;
+    if (!ReadFasta(path, &fa, &e)) {
+        if (err) *err = "Invalid FASTA file: " + e;
+        return false;
+    }
+    std::vector<Fragment> t;
+    std::vector<AltRegion> alt;
+    for (size_t i = 0; i < fa.size(); i++) {
+        t.push_back(NewFragment(fa.ids[i], fa.seq(i), orientation, base));
+        if (t.size() > 2) {
+            const int start = findAttr(fa.ids[i], "alt_start="), end = findAttr(fa.ids[i], "alt_stop=");
+            if (start > -1 && end > -1) alt.push_back(AltRegion{start, end});
+        }
+    }
+    if (t.size() < 2) {
+        if (err) *err = "Must provide at least 2 templates. Full and Pre edited";
+        return false;
+    }
+    return NewTemplate(t[0], t[1], std::vector<Fragment>(t.begin() + 2, t.end()), alt, out, err);
+}
+
+void Template::SetOffset(int offset)
+{
+    EditOffset = (uint32_t)offset;
+    EditStop += offset;
+    for (auto &r : AltRegion) {
+        r.Start -= offset;
+        r.End -= offset;
+    }
+}
+
+uint32_t Template::Max(int i) const
+{
+    uint32_t mx = 0;
+    for (const auto &row : EditSite) mx = std::max(mx, row[i]);
+    return mx;
+}
+
+std::string Template::String() const
+{
+    std::string s;
+    for (size_t i = 0; i < EditSite[0].size(); i++) {
+        s.append(EditSite[0][i], EditBase);
+        if (i < Bases.size()) s.push_back(Bases[i]);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------ align.go (text side)
+
+Alignment Alignment::FromRecord(const treat_b200_record &r, const uint8_t *packed_ops, const uint8_t *seq,
+                                size_t seq_len)
+{
+    Alignment a;
+    a.EditStop = r.edit_stop;
+    a.JuncStart = r.junc_start;
+    a.JuncEnd = r.junc_end;
+    a.JuncLen = r.junc_len;
+    a.ReadCount = r.read_count;
+    a.HasMutation = r.has_mutation;
+    a.AltEditing = r.alt_editing;
+    a.Mismatches = r.mismatches;
+    a.Indel = r.indel;
+    a.Score = r.score;
+    a.Status = r.status;
+    if (seq && r.junc_seq_len && (size_t)r.junc_seq_off + r.junc_seq_len <= seq_len) {
+        a.JuncSeq.assign((const char *)seq + r.junc_seq_off, r.junc_seq_len);
+        std::transform(a.JuncSeq.begin(), a.JuncSeq.end(), a.JuncSeq.begin(), upper);
+    }
+    if (packed_ops) {
+        a.Ops.resize(r.aln_len);
+        for (uint32_t c = 0; c < r.aln_len; c++) a.Ops[c] = (packed_ops[c >> 2] >> (2 * (c & 3))) & 3u;
+    }
+    return a;
+}
+
+std::string Alignment::WriteTo(const Fragment &frag, const Template &tmpl, int tw) const
+{
+    if (tw <= 0) tw = 80;
+    const int K = tmpl.Size();
+    std::vector<std::string> buf(K + 1);
+    std::string &rd = buf[K];
+    int fi = 0, ti = 0;
+    for (uint8_t op : Ops) {
+        if (op == TREAT_B200_OP_INS) {  // aln1[ai] == '-'
+            for (int k = 0; k < K; k++) {
+                writeBase(buf[k], tmpl.EditBase, 0, frag.EditSite[fi]);
+                buf[k].push_back('-');
+            }
+            writeBase(rd, frag.EditBase, frag.EditSite[fi], frag.EditSite[fi]);
+            rd.push_back(frag.Bases[fi]);
+            fi++;
+        } else if (op == TREAT_B200_OP_DEL) {  // aln2[ai] == '-'
+            const uint32_t mx = tmpl.Max(ti);
+            for (int k = 0; k < K; k++) {
+                writeBase(buf[k], tmpl.EditBase, tmpl.EditSite[k][ti], mx);
+                buf[k].push_back(tmpl.Bases[ti]);
+            }
+            writeBase(rd, '-', 0, mx);
+            rd.push_back('-');
+            ti++;
+        } else {
+            const uint32_t mx = std::max(tmpl.Max(ti), frag.EditSite[fi]);
+            for (int k = 0; k < K; k++) {
+                writeBase(buf[k], tmpl.EditBase, tmpl.EditSite[k][ti], mx);
+                buf[k].push_back(tmpl.Bases[ti]);
+            }
+            writeBase(rd, frag.EditBase, frag.EditSite[fi], mx);
+            rd.push_back(frag.Bases[fi]);
+            fi++;
+            ti++;
+        }
+    }
+    const uint32_t mx = std::max(tmpl.Max(ti), frag.EditSite[fi]);  // last edit site: edit bases only
+    for (int k = 0; k < K; k++) writeBase(buf[k], tmpl.EditBase, tmpl.EditSite[k][ti], mx);
+    writeBase(rd, frag.EditBase, frag.EditSite[fi], mx);
+
+    const size_t cols = (size_t)(tw - 4);
+    size_t rows = buf[0].size() / cols;
+    if (buf[0].size() % cols > 0) rows++;
+    std::vector<std::string> labels = {"FE", "PE"};
+    for (size_t i = 0; i < tmpl.AltRegion.size(); i++) labels.push_back("A" + std::to_string(i + 1));
+    labels.push_back("RD");
+
+    std::string out;
+    const std::string bar((size_t)tw, '=');
+    out += bar + "\n" + frag.Name + "\n" + bar + "\n";
+    char line[128];
+    snprintf(line, sizeof line, "JSS: %d\nESS: %d\nJES: %d\nJunc Len: %d\n", JuncStart, EditStop, JuncEnd, JuncLen);
+    out += line;
+    if (AltEditing > 0) {
+        snprintf(line, sizeof line, "Alt: %d\n", (int)AltEditing);
+        out += line;
+    }
+    out += bar + "\n\n";
+    for (size_t r = 0; r < rows; r++) {
+        for (size_t i = 0; i < buf.size(); i++) {
+            out += labels[i] + ": ";
+            const size_t lo = r * cols, hi = std::min(lo + cols, buf[i].size());
+            if (hi > lo) out.append(buf[i], lo, hi - lo);
+            out.push_back('\n');
+        }
+        out.push_back('\n');
+    }
+    return out;
+}
+
+std::vector<uint8_t> Alignment::MarshalBinary() const
+{
+    std::vector<uint8_t> b(36 + JuncSeq.size());
+    auto be32 = [&](size_t o, uint32_t v) {
+        b[o] = (uint8_t)(v >> 24);
+        b[o + 1] = (uint8_t)(v >> 16);
+        b[o + 2] = (uint8_t)(v >> 8);
+        b[o + 3] = (uint8_t)v;
+    };
+    be32(0, (uint32_t)EditStop);  // writeInt64 keeps the low 32 bits (align.go:288-293)
+    be32(4, (uint32_t)JuncStart);
+    be32(8, (uint32_t)JuncEnd);
+    be32(12, (uint32_t)JuncLen);
+    be32(16, ReadCount);
+    b[20] = HasMutation;
+    b[21] = AltEditing;
+    b[22] = Mismatches;
+    b[23] = Indel;
+    uint64_t bits;
+    memcpy(&bits, &Norm, 8);
+    be32(24, (uint32_t)(bits >> 32));
+    be32(28, (uint32_t)bits);
+    be32(32, (uint32_t)JuncSeq.size());
+    std::copy(JuncSeq.begin(), JuncSeq.end(), b.begin() + 36);
+    return b;
+}
+
+void SimpleAlignStrings(const Fragment &f1, const Fragment &f2, const std::vector<uint8_t> &ops, std::string *s1,
+                        std::string *s2)
+{
+    std::string &b0 = *s1, &b1 = *s2;
+    b0.clear();
+    b1.clear();
+    int fi = 0, ti = 0;
+    for (uint8_t op : ops) {
+        if (op == TREAT_B200_OP_INS) {
+            writeBase(b0, f1.EditBase, 0, f2.EditSite[fi]);
+            b0.push_back('-');
+            writeBase(b1, f2.EditBase, f2.EditSite[fi], f2.EditSite[fi]);
+            b1.push_back(f2.Bases[fi]);
+            fi++;
+        } else if (op == TREAT_B200_OP_DEL) {
+            writeBase(b0, f1.EditBase, f1.EditSite[ti], f1.EditSite[ti]);
+            b0.push_back(f1.Bases[ti]);
+            writeBase(b1, '-', 0, f1.EditSite[ti]);
+            b1.push_back('-');
+            ti++;
+        } else {
+            const uint32_t mx = std::max(f1.EditSite[ti], f2.EditSite[fi]);
+            writeBase(b0, f1.EditBase, f1.EditSite[ti], mx);
+            b0.push_back(f1.Bases[ti]);
+            writeBase(b1, f2.EditBase, f2.EditSite[fi], mx);
+            b1.push_back(f2.Bases[fi]);
+            fi++;
+            ti++;
+        }
+    }
+    const uint32_t mx = std::max(f1.EditSite[ti], f2.EditSite[fi]);
+    writeBase(b0, f1.EditBase, f1.EditSite[ti], mx);
+    writeBase(b1, f2.EditBase, f2.EditSite[fi], mx);
+}
+
+std::string PrintAlignment(const std::string &a1, const std::string &a2, int tw)
+{
+    std::string out;
+    const size_t n = a1.size(), cols = (size_t)tw;
+    for (size_t lo = 0; lo < n; lo += cols) {
+        const size_t hi = std::min(lo + cols, n);
+        out.append(a1, lo, hi - lo);
+        out.push_back('\n');
+        out.append(a2, lo, hi - lo);
+        out += "\n\n";
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------ batch engine
+
+bool Aligner::SetTemplate(const Template &t, std::string *err)
+{
+    int rc = treat_b200_use_template(ctx_, reinterpret_cast<const treat_b200_template *>(&t));
+    if (rc != TREAT_B200_OK) {
+        if (err) *err = std::string(treat_b200_strerror(rc)) + ": " + treat_b200_last_error(ctx_);
+        return false;
+    }
+    return true;
+}
+
+bool Aligner::AlignBatch(const FastaBatch &reads, bool excludeSnps, bool wantOps, std::vector<Alignment> *out,
+                         std::string *err)
+{
+    const uint64_t N = reads.size();
+    out->clear();
+    if (N == 0) return true;
+    uint32_t max_len = 0;
+    for (uint64_t i = 0; i < N; i++) max_len = std::max<uint32_t>(max_len, (uint32_t)(reads.offsets[i + 1] - reads.offsets[i]));
+    const uint32_t stride = treat_b200_ops_stride(ctx_, max_len);
+    std::vector<treat_b200_record> rec(N);
+    std::vector<uint8_t> ops(wantOps ? (size_t)N * stride : 0);
+    static const uint8_t kEmpty = 0;
+    const uint32_t flags = (excludeSnps ? TREAT_B200_EXCLUDE_SNPS : 0) | (wantOps ? TREAT_B200_WANT_OPS : 0);
+    int rc = treat_b200_align_batch(ctx_, reads.seqs.empty() ? &kEmpty : reads.seqs.data(), reads.offsets.data(),
+                                    reads.read_counts.data(), N, flags, rec.data(), wantOps ? ops.data() : nullptr, stride);
+    if (rc != TREAT_B200_OK) {
+        if (err) *err = std::string(treat_b200_strerror(rc)) + ": " + treat_b200_last_error(ctx_);
+        return false;
+    }
+    out->reserve(N);
+    for (uint64_t i = 0; i < N; i++)
+        out->push_back(Alignment::FromRecord(rec[i], wantOps ? ops.data() + i * stride : nullptr,
+                                             reads.seqs.data() + reads.offsets[i], reads.offsets[i + 1] - reads.offsets[i]));
+    return true;
+}
+
+bool Aligner::SimpleAlign(const Fragment &f1, const Fragment &f2, std::string *s1, std::string *s2, std::string *err)
+{
+    // nwalgo.Align(f1.Bases, f2.Bases, 1, -1, -1) on the GPU: f1 plays the template (FE = PE = f1)
+    if (f1.Bases.empty()) {  // nothing to align against: every read base is an insertion
+        SimpleAlignStrings(f1, f2, std::vector<uint8_t>(f2.Bases.size(), TREAT_B200_OP_INS), s1, s2);
+        return true;
+    }
+    Template t;
+    std::string e;
+    if (!NewTemplate(f1, f1, {}, {}, &t, &e)) {
+        if (err) *err = e;
+        return false;
+    }
+    if (!SetTemplate(t, err)) return false;
+    FastaBatch b;
+    b.ids.push_back(f2.Name);
+    const std::string raw = f2.String();
+    b.seqs.assign(raw.begin(), raw.end());
+    b.offsets = {0, (uint64_t)raw.size()};
+    b.read_counts.push_back(f2.ReadCount);
+    const uint32_t stride = treat_b200_ops_stride(ctx_, (uint32_t)raw.size());
+    treat_b200_record rec;
+    std::vector<uint8_t> ops(stride);
+    static const uint8_t kEmpty = 0;
+    int rc = treat_b200_align_batch(ctx_, b.seqs.empty() ? &kEmpty : b.seqs.data(), b.offsets.data(), nullptr, 1,
+                                    TREAT_B200_WANT_OPS | TREAT_B200_NO_SUMMARY, &rec, ops.data(), stride);
+    if (rc != TREAT_B200_OK) {
+        if (err) *err = std::string(treat_b200_strerror(rc)) + ": " + treat_b200_last_error(ctx_);
+        return false;
+    }
+    Alignment a = Alignment::FromRecord(rec, ops.data(), nullptr, 0);
+    // the edit base of f2 may differ from f1's only through the caller; the device stripped
+    // f2.String() with f1's edit base, which is the same rune in every reference call site
+    SimpleAlignStrings(f1, f2, a.Ops, s1, s2);
+    return true;
+}
+
+bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
+              const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
+              std::string *out, std::string *err)
+{
+    out->clear();
+    if (editBase.size() != 1) {
+        *err = "Please provide the edit base";
+        return false;
+    }
+    const char base = editBase[0];
+    if (s1.empty() != s2.empty()) {
+        *err = "Please provide 2 fragments to align";
+        return false;
+    }
+    Aligner eng(ctx);
+    if (!s1.empty() && !s2.empty()) {
+        Fragment f1 = NewFragment("1-1", s1, FORWARD, base), f2 = NewFragment("2-1", s2, FORWARD, base);
+        std::string a1, a2;
+        if (!eng.SimpleAlign(f1, f2, &a1, &a2, err)) return false;
+        *out = PrintAlignment(a1, a2, 80);
+        return true;
+    }
+    if (fragmentPath.empty()) {
+        *err = "Please provide either 2 sequences to align or a path to fragment FASTA file";
+        return false;
+    }
+    bool haveTemplate = false;
+    Template tmpl;
+    if (!templatePath.empty()) {
+        if (!NewTemplateFromFasta(templatePath, FORWARD, base, &tmpl, err)) return false;
+        tmpl.SetOffset(editOffset);
+        haveTemplate = true;
+    }
+    FastaBatch reads;
+    if (!ReadFasta(fragmentPath, &reads, err)) return false;
+    if (!haveTemplate) {
+        if (reads.size() < 2) {
+            *err = "Need 2 fragments to align";
+            return false;
+        }
+        Fragment f1 = NewFragment(reads.ids[0], reads.seq(0), FORWARD, base);
+        Fragment f2 = NewFragment(reads.ids[1], reads.seq(1), FORWARD, base);
+        std::string a1, a2;
+        if (!eng.SimpleAlign(f1, f2, &a1, &a2, err)) return false;
+        *out = PrintAlignment(a1, a2, 80);
+        return true;
+    }
+    if (!eng.SetTemplate(tmpl, err)) return false;
+    std::vector<Alignment> alns;
+    if (!eng.AlignBatch(reads, false, true, &alns, err)) return false;
+    for (size_t i = 0; i < reads.size(); i++) {
+        Fragment frag = NewFragment(reads.ids[i], reads.seq(i), FORWARD, base);
+        *out += alns[i].WriteTo(frag, tmpl, 80);
+    }
+    return true;
+}
+
+}  // namespace treat
