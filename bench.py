@@ -81,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -241,8 +241,10 @@ def run_ours(args):
     d_rc = torch.from_numpy(rc.astype(np.int32)).to(dev)
     d_rec = torch.empty(N * 48, dtype=torch.uint8, device=dev)
     d_ops = torch.empty(N * stride, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # explicit stream: the C ABI launches on it, the events time it
+    torch.cuda.set_stream(stream)
     sraw = stream.cuda_stream
+    assert sraw != 0
     flags = cabi.WANT_OPS
     summ = parallel.summary_tensor(eng)
 
@@ -361,7 +363,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = args.cpu_sample or min(N, 6144 * threads)
+        sample = args.cpu_sample or min(N, 40000 * threads)
         v, g, secs = cpu_sample_rate(t, p_trunc, seed, sample, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "gcups": g,
                "sample": "first %d reads of the workload, %d threads, %.1f s; CPU port of the Go path (oracle/treat_oracle.c), "

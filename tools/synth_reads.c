@@ -167,10 +167,10 @@ void synth_long_template(int m, int n_alt, uint64_t seed, uint8_t *bases, uint32
     for (int a = 0; a < n_alt; a++) {
         uint32_t *row = edit_site + (size_t)(2 + a) * len;
         memcpy(row, edit_site, sizeof(uint32_t) * (size_t)len);
-        const int s0 = 8 + (int)rnd(&st, (uint32_t)(len - 24));
+        const int s0 = len > 32 ? 8 + (int)rnd(&st, (uint32_t)(len - 24)) : (int)rnd(&st, (uint32_t)(len > 8 ? len - 8 : 1));
         alt_start[a] = s0;
         alt_end[a] = s0 + 7;
-        for (int s = s0; s <= s0 + 7; s++) {
+        for (int s = s0; s <= s0 + 7 && s < len; s++) {
             const int ti = len - 1 - s;
             uint32_t c;
             do c = rnd(&st, 9); while (c == edit_site[ti]);

@@ -145,13 +145,11 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
                 const int prev = below ? (int)(c0 + 31 - __clz(below)) : lastpos;
                 uint32_t cnt = (uint32_t)((int)j - prev - 1);
                 uint8_t code = ch;
+                if (cnt >= 255u) sat = true;  // informational on the wide path, which keeps exact counts
                 if (!WIDE) {
                     code = s_lut[ch];
                     widec |= (code == 3);
-                    if (cnt >= 255u) {
-                        cnt = 255u;
-                        sat = true;
-                    }
+                    if (cnt >= 255u) cnt = 255u;
                 }
                 s_code[idx] = code;
                 s_cnt[idx] = (cnt_t)cnt;
@@ -161,10 +159,8 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
         }
         if (lane == 0) {
             uint32_t cnt = (uint32_t)((int)L - 1 - lastpos);
-            if (!WIDE && cnt >= 255u) {
-                cnt = 255u;
-                sat = true;
-            }
+            if (cnt >= 255u) sat = true;
+            if (!WIDE && cnt >= 255u) cnt = 255u;
             s_cnt[nb] = (cnt_t)cnt;
         }
         __syncwarp();
