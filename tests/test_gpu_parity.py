@@ -191,8 +191,8 @@ def test_synthetic_long_template_vs_oracle(eng, tmp_path):
 
 
 def test_other_template_sizes(eng, tmp_path):
-    """Exercise every columns-per-lane instantiation (m = 20 .. 500)."""
-    for m in (20, 40, 100, 150, 230, 330, 500):
+    """Exercise every columns-per-lane instantiation (m = 20 .. 470)."""
+    for m in (20, 40, 100, 150, 200, 230, 300, 330, 470):
         _batch_vs_oracle(eng, synth.long_template(m, 2, seed=99 + m), tmp_path, 300, 1000 + m, p_trunc=0.3)
 
 
@@ -245,7 +245,7 @@ def test_edge_cases(eng, tmp_path):
         T.Aligner(0).align_batch(np.zeros(4, np.uint8), np.array([0, 4], np.uint64))  # no template
     big = T.NewFragment("fe", "AC" * 300)
     with pytest.raises(T.TreatError):
-        eng.SetTemplate(T.NewTemplate(big, big, None, None))  # 600 bases > 512
+        eng.SetTemplate(T.NewTemplate(big, big, None, None))  # 600 bases > 480
     with pytest.raises(T.TreatError):
         tm = T.NewTemplate(T.NewFragment("fe", "ACG"), T.NewFragment("pe", "ACG"), None, None)
         eng.NewAlignment(T.NewFragment("long-1", "A" * 20000), tm, False)

@@ -181,7 +181,7 @@ int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m
     if (!ctx || !bases || !edit_site || m < 1 || K < 2 || n_alt != K - 2 || (n_alt > 0 && (!alt_start || !alt_end)))
         return fail(ctx, TREAT_B200_ERR_INVALID, "set_template: bad arguments (need m >= 1, K >= 2, n_alt == K-2)");
     if (m > kMaxTemplateBases || K > kMaxTemplates)
-        return fail(ctx, TREAT_B200_ERR_TOO_LONG, "set_template: template longer than 512 bases or more than 32 rows");
+        return fail(ctx, TREAT_B200_ERR_TOO_LONG, "set_template: template longer than 480 bases or more than 32 rows");
     CK(ctx, cudaSetDevice(ctx->device));
     if (edit_base >= 'a' && edit_base <= 'z') edit_base -= 32;
     const int len = m + 1, len_pad = (len + 31) / 32 * 32;

@@ -6,8 +6,8 @@
 
 namespace treat_b200 {
 
-// Largest template the one-pass wavefront handles: 32 lanes x 16 columns per lane.
-constexpr int kMaxTemplateBases = 512;
+// Largest template the one-pass wavefront handles: 32 lanes x 15 columns per lane.
+constexpr int kMaxTemplateBases = 480;
 // Raw reads longer than this are refused (ERR_TOO_LONG); keeps n in uint16 and bounds shared memory.
 constexpr uint32_t kMaxReadLen = 16384;
 constexpr int kMaxTemplates = 32;  // K = FE + PE + alternatives

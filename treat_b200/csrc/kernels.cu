@@ -247,11 +247,31 @@ int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin,
 // ------------------------------------------------------------------------------------------
 // K2: align
 // ------------------------------------------------------------------------------------------
+// Score transform.  nwalgo fills F[i][j] = max(F[i-1][j-1] + (a==b ? 1 : -1), F[i-1][j] - 1,
+// F[i][j-1] - 1) with F[i][0] = -i, F[0][j] = -j.  With G = F + i + j the gap terms vanish:
+//     G[i][j] = max(G[i-1][j-1] + w, G[i-1][j], G[i][j-1]),  w = 3 on a match, 1 otherwise,
+//     G[i][0] = G[0][j] = 0,  F[m][n] = G[m][n] - m - n,
+// every horizontal / vertical difference of G lies in {0,1,2,3}, and nwalgo's pointer tests become
+//     max == hgap ("Up",   consumes the template base)  <=>  G[i][j] == G[i-1][j]
+//     max == vgap ("Left", consumes the read base)      <=>  G[i][j] == G[i][j-1].
+// A row with w = 0 leaves the previous row unchanged, so idle wavefront steps need no branch.
+//
+// Per lane and step the kernel stores ONE word: the CPL horizontal differences as base-4 digits
+// plus (left boundary value mod 4) on top.  From two such words (rows j and j-1) the traceback
+// recovers G mod 4 of any cell and therefore both pointer tests.
 template <int CPL>
 struct Dir {
-    using word_t = typename std::conditional<(CPL <= 8), uint16_t, uint32_t>::type;
-    static constexpr int kLeftShift = (CPL <= 8) ? 8 : 16;  // pL bits sit above the pU bits
+    using word_t = typename std::conditional<(CPL <= 7), uint16_t, uint32_t>::type;
+    static constexpr int kTop = (CPL <= 7) ? 14 : 30;            // bit position of (left & 3)
+    static constexpr uint32_t kOdd = (CPL <= 7) ? 0x1555u : 0x15555555u;   // low bits of the digits
+    static_assert(CPL <= 15, "direction word holds at most 15 base-4 digits");
 };
+
+// sum of the base-4 digits of x (mod 4 is all the caller needs)
+__device__ __forceinline__ uint32_t digit_sum(uint32_t x, uint32_t odd)
+{
+    return __popc(x & odd) + 2u * __popc(x & (odd << 1));
+}
 
 // Bit rows over template sites in array order ti = 0..len-1 (site number = len-1-ti), one
 // 32-bit word per lane, kept in shared memory: the willf/bitset sets of align.go:122-181.
@@ -307,12 +327,15 @@ struct BitRows {
     }
 };
 
+constexpr int kPadCode = 4;  // profile row with w = 0: a no-op row of the wavefront
+
 template <int CPL, bool WIDE>
 __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignParams p)
 {
-    using dir_t = typename Dir<CPL>::word_t;
+    using DT = Dir<CPL>;
+    using dir_t = typename DT::word_t;
     using cnt_t = typename std::conditional<WIDE, uint32_t, uint8_t>::type;
-    constexpr int LSH = Dir<CPL>::kLeftShift;
+    constexpr int NCH = (CPL + 3) / 4;  // uint4 chunks of the scoring profile per lane
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -327,19 +350,30 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
     unsigned long long *s_sum =
         reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(s_alt) + align16(8u * (n_alt ? n_alt : 1)));
     const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
+    // scoring profile: s_prof[(q*5 + code)*32 + lane] = w of columns lane*CPL + 4q .. +3
+    uint4 *s_prof = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(s_sum) + align16(8u * sum_len));
 
     for (int i = threadIdx.x; i < 32 * CPL; i += blockDim.x) s_tb[i] = i < m ? p.t.tb[i] : 0;
     for (int i = threadIdx.x; i < K * len_pad; i += blockDim.x)
         s_tcount[i] = reinterpret_cast<const cnt_t *>(p.t.tcount)[i];
     for (int i = threadIdx.x; i < 2 * n_alt; i += blockDim.x) s_alt[i] = p.t.alt[i];
     for (uint32_t i = threadIdx.x; i < sum_len; i += blockDim.x) s_sum[i] = 0ull;
+    if (!WIDE) {
+        uint32_t *pw = reinterpret_cast<uint32_t *>(s_prof);
+        for (int i = threadIdx.x; i < NCH * 5 * 32 * 4; i += blockDim.x) {
+            const int e = i & 3, ln = (i >> 2) & 31, c = (i >> 7) % 5, q = (i >> 7) / 5;
+            const int col = ln * CPL + q * 4 + e;
+            uint32_t w = c == kPadCode ? 0u : 1u;
+            if (c < 3 && q * 4 + e < CPL && col < m && p.t.tb[col] == c) w = 3u;
+            pw[i] = w;
+        }
+    }
 
     // ---- per-warp section ------------------------------------------------------------------
     uint8_t *wbase = smem + p.sm_tmpl_bytes + (size_t)warp * p.sm_warp_bytes;
-    uint8_t *s_stage[2];
-    s_stage[0] = wbase;
-    s_stage[1] = wbase + p.sm_stage_b + p.sm_stage_c;
-    uint8_t *s_rb = s_stage[1] + p.sm_stage_b + p.sm_stage_c;  // read bases as bytes, 32 bytes of pad in front
+    const uint32_t stage_bytes = p.sm_stage_b + p.sm_stage_c;
+    uint8_t *s_stage = wbase;                                  // two stage buffers back to back
+    uint8_t *s_rb = wbase + 2 * stage_bytes;                   // read bases as bytes, 32 pad bytes in front
     dir_t *s_dir = reinterpret_cast<dir_t *>(s_rb + p.sm_rb);
     uint8_t *s_ops = reinterpret_cast<uint8_t *>(s_dir) + p.sm_dir;
     uint16_t *s_t2f = reinterpret_cast<uint16_t *>(s_ops + p.sm_ops);
@@ -351,10 +385,10 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
         mbar_init(&s_bar[1], 1);
         fence_mbar_init();
     }
+    s_rb[lane] = kPadCode;  // rows "before" the read: no-op rows for lanes that have not started
     __syncthreads();
 
-    // ---- per-lane template registers ---------------------------------------------------------
-    int tcr[CPL];
+    int tcr[CPL];  // template bases of this lane's columns (wide path compares instead of a profile)
 #pragma unroll
     for (int k = 0; k < CPL; k++) {
         const int idx = lane * CPL + k;
@@ -362,6 +396,7 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
     }
     const int lanes_used = (m + CPL - 1) / CPL;
     const uint32_t lt = (1u << lane) - 1u;
+    const uint4 *prof_lane = s_prof + lane;
 
     const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
 
@@ -371,10 +406,11 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
             const uint32_t n = p.n[r];
             const uint32_t cb = WIDE ? align16(n) : align16((n + 3) / 4);
             const uint32_t cc = WIDE ? align16(4 * (n + 1)) : align16(n + 1);
+            uint8_t *dst = s_stage + slot * stage_bytes;
             fence_proxy_async();
             mbar_expect_tx(&s_bar[slot], cb + cc);
-            if (cb) bulk_g2s(s_stage[slot], p.bases + r * (uint64_t)p.bases_stride, cb, &s_bar[slot]);
-            bulk_g2s(s_stage[slot] + p.sm_stage_b, p.counts + r * (uint64_t)p.counts_stride, cc, &s_bar[slot]);
+            if (cb) bulk_g2s(dst, p.bases + r * (uint64_t)p.bases_stride, cb, &s_bar[slot]);
+            bulk_g2s(dst + p.sm_stage_b, p.counts + r * (uint64_t)p.counts_stride, cc, &s_bar[slot]);
         }
     };
 
@@ -386,20 +422,16 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
         const uint32_t parity = (it >> 1) & 1;
         const int n = (int)p.n[r];
         const uint8_t rflags = p.rflags[r];
-        if (n > (int)p.ncap) {  // cannot happen when ncap comes from K1's max; keep the launch safe
-            if (r + nw < p.N) issue(r + nw, slot ^ 1);
-            mbar_wait(&s_bar[slot], parity);
-            continue;
-        }
         // prefetch the next read of this warp while this one is aligned
         __syncwarp();
         if (r + nw < p.N) issue(r + nw, slot ^ 1);
         mbar_wait(&s_bar[slot], parity);
+        if (n > (int)p.ncap) continue;  // cannot happen when ncap comes from K1's max; keeps the launch safe
 
-        const uint8_t *st_b = s_stage[slot];
-        const cnt_t *rcount = reinterpret_cast<const cnt_t *>(s_stage[slot] + p.sm_stage_b);
+        const uint8_t *st_b = s_stage + slot * stage_bytes;
+        const cnt_t *rcount = reinterpret_cast<const cnt_t *>(st_b + p.sm_stage_b);
 
-        // ---- unpack read bases to bytes (index -32.. for idle lanes of the wavefront) -------
+        // ---- unpack read bases to one byte each; pad rows behind the read are no-op rows -----
         uint8_t *rb = s_rb + 32;
         if (!WIDE) {
             const uint32_t *pw = reinterpret_cast<const uint32_t *>(st_b);
@@ -413,81 +445,127 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
                 }
                 *reinterpret_cast<uint4 *>(rb + wi * 16) = make_uint4(o[0], o[1], o[2], o[3]);
             }
+            __syncwarp();
+            rb[n + lane] = kPadCode;
+            rb[n + 32 + lane] = kPadCode;
         } else {
             for (int i = lane; i < n; i += 32) rb[i] = st_b[i];
         }
         __syncwarp();
 
         // ---- fill: anti-diagonal wavefront ------------------------------------------------------
-        // F[i][j]: i template bases, j read bases consumed; lane owns i = lane*CPL+1 .. +CPL.
-        int H[CPL];  // F[i][j-1] for this lane's columns
+        // lane owns template bases i = lane*CPL+1 .. +CPL; at step t it works on read row j = t-lane+1.
+        int H[CPL];  // G[i][j-1] for this lane's columns
 #pragma unroll
-        for (int k = 0; k < CPL; k++) H[k] = -(lane * CPL + k + 1);
-        int diag = -(lane * CPL);  // F[i0-1][j-1]
+        for (int k = 0; k < CPL; k++) H[k] = 0;
+        int diag = 0;  // G[i0-1][j-1]
         const int steps = n > 0 ? n + lanes_used - 1 : 0;
+        const uint8_t *rbl = rb - lane;  // rbl[t] = read base of this lane's row at step t
+        uint4 pwc[NCH];
+        int cnext = 0;
+        if (!WIDE) {
+#pragma unroll
+            for (int q = 0; q < NCH; q++) pwc[q] = prof_lane[(q * 5 + rbl[0]) * 32];
+            cnext = rbl[1];
+        }
+        dir_t *dirp = s_dir + lane;
+#pragma unroll 2
         for (int t = 0; t < steps; t++) {
-            const int j = t - lane + 1;
-            const int recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
-            const int left = lane == 0 ? -j : recv;  // F[i0-1][j]
-            uint32_t w = 0;
-            if (j >= 1 && j <= n) {
-                const int rc = rb[j - 1];
-                int dg = diag, lf = left;
+            uint4 pwn[NCH];
+            int wv[CPL];
+            if (!WIDE) {
+#pragma unroll
+                for (int q = 0; q < NCH; q++) pwn[q] = prof_lane[(q * 5 + cnext) * 32];
+                cnext = rbl[t + 2];
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
-                    const int x = H[k] - 1;                       // vgap: F[i][j-1] + gap   ("Left")
-                    const int s = (rc == tcr[k]) ? 1 : -1;
-                    const int e = max(dg + s, x);
-                    const int f = max(e, lf - 1);                 // hgap: F[i-1][j] + gap   ("Up")
-                    w |= (e < lf ? 1u : 0u) << k;                 // max == hgap
-                    w |= (f == x ? 1u : 0u) << (LSH + k);         // max == vgap
-                    dg = H[k];
-                    lf = f;
-                    H[k] = f;
+                    const uint4 v = pwc[k >> 2];
+                    wv[k] = (int)((k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w);
                 }
-                diag = left;
+            } else {
+                const int idx = t - lane;
+                const bool live = idx >= 0 && idx < n;
+                const int rc = live ? (int)rbl[t] : 0x200;
+#pragma unroll
+                for (int k = 0; k < CPL; k++) wv[k] = live ? (rc == tcr[k] ? 3 : 1) : 0;
             }
-            s_dir[t * 32 + lane] = (dir_t)w;
+            const int recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
+            const int left = lane == 0 ? 0 : recv;  // G[i0-1][j]
+            int dg = diag, lf = left;
+            uint32_t S = 0;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                const int e = max(dg + wv[k], H[k]);
+                const int f = max(e, lf);
+                dg = H[k];
+                lf = f;
+                H[k] = f;
+                S += (uint32_t)f << (2 * k);
+            }
+            diag = left;
+            // digits: sum_k (f_k - f_{k-1}) 4^k = 4^CPL f_last - 3 S - left
+            const uint32_t word = ((uint32_t)lf << (2 * CPL)) - 3u * S - (uint32_t)left + (((uint32_t)left & 3u) << DT::kTop);
+            dirp[t * 32] = (dir_t)word;
+            if (!WIDE) {
+#pragma unroll
+                for (int q = 0; q < NCH; q++) pwc[q] = pwn[q];
+            }
         }
         __syncwarp();
 
-        // final score F[m][n] lives in lane (m-1)/CPL, column (m-1)%CPL
+        // final score F[m][n] = G[m][n] - m - n; G[m][n] lives in lane (m-1)/CPL, column (m-1)%CPL
         int fin = 0;
         {
             const int kl = (m - 1) % CPL;
 #pragma unroll
             for (int k = 0; k < CPL; k++)
                 if (k == kl) fin = H[k];
-            fin = __shfl_sync(FULL_MASK, fin, (m - 1) / CPL);
-            if (n == 0) fin = -m;
+            fin = __shfl_sync(FULL_MASK, fin, (m - 1) / CPL) - m - n;
         }
 
-        // ---- traceback (nwalgo: Up, then Left, then Diagonal) -----------------------------------
+        // ---- traceback (nwalgo: Up, then Left, then Diagonal), 32 cells of a diagonal run at a time
         int pos = m + n;
         {
             int i = m, j = n;
-            int ln = (m - 1) / CPL, k = (m - 1) % CPL;
-            while (i > 0 || j > 0) {
-                int op;
-                if (i == 0)
-                    op = TREAT_B200_OP_INS;
-                else if (j == 0)
-                    op = TREAT_B200_OP_DEL;
-                else {
-                    const uint32_t w = s_dir[(j - 1 + ln) * 32 + ln];
-                    op = ((w >> k) & 1u) ? TREAT_B200_OP_DEL : ((w >> (LSH + k)) & 1u) ? TREAT_B200_OP_INS : TREAT_B200_OP_MATCH;
-                }
-                --pos;
-                if (lane == 0) s_ops[pos] = (uint8_t)op;
-                if (op != TREAT_B200_OP_INS) {
-                    i--;
-                    if (--k < 0) {
-                        k = CPL - 1;
-                        ln--;
+            while (i > 0 && j > 0) {
+                const int ii = i - lane, jj = j - lane;
+                bool stop = true, is_up = false;
+                if (ii >= 1 && jj >= 1) {
+                    const int ln = (ii - 1) / CPL, k = (ii - 1) - ln * CPL;
+                    const int tt = jj - 1 + ln;
+                    const uint32_t w1 = s_dir[tt * 32 + ln];
+                    const uint32_t a = (w1 >> (2 * k)) & 3u;
+                    if (a == 0) {
+                        is_up = true;  // G[i][j] == G[i-1][j]
+                    } else {
+                        const uint32_t msk = (4u << (2 * k)) - 1u;
+                        const uint32_t g1 = (w1 >> DT::kTop) + digit_sum(w1 & msk, DT::kOdd);
+                        uint32_t g0 = 0;  // G[i][0] = 0
+                        if (jj >= 2) {
+                            const uint32_t w0 = s_dir[(tt - 1) * 32 + ln];
+                            g0 = (w0 >> DT::kTop) + digit_sum(w0 & msk, DT::kOdd);
+                        }
+                        stop = ((g1 - g0) & 3u) == 0;  // G[i][j] == G[i][j-1]: Left
                     }
                 }
-                if (op != TREAT_B200_OP_DEL) j--;
+                const uint32_t sm = __ballot_sync(FULL_MASK, stop);
+                const int run = sm ? __ffs(sm) - 1 : 32;  // diagonal moves before the first gap / edge
+                if (lane < run) s_ops[pos - 1 - lane] = TREAT_B200_OP_MATCH;
+                pos -= run;
+                i -= run;
+                j -= run;
+                if (run < 32 && i > 0 && j > 0) {
+                    const bool up = __shfl_sync(FULL_MASK, is_up, run);
+                    --pos;
+                    if (lane == 0) s_ops[pos] = up ? TREAT_B200_OP_DEL : TREAT_B200_OP_INS;
+                    if (up) i--; else j--;
+                }
             }
+            // first row / column: pointers are Left on row 0 and Up on column 0
+            for (int q = lane; q < i; q += 32) s_ops[pos - 1 - q] = TREAT_B200_OP_DEL;
+            pos -= i;
+            for (int q = lane; q < j; q += 32) s_ops[pos - 1 - q] = TREAT_B200_OP_INS;
+            pos -= j;
         }
         const int alen = m + n - pos;
         const uint8_t *ops = s_ops + pos;
@@ -683,7 +761,7 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
     }
 }
 
-static const int kCplSet[] = {1, 2, 4, 6, 8, 12, 16};
+static const int kCplSet[] = {1, 2, 4, 6, 7, 10, 12, 15};
 
 static int pick_cpl(int m)
 {
@@ -700,15 +778,16 @@ int plan_align(AlignParams &p, bool wide)
     if (cpl < 0 || m < 1) return -1;
     const uint32_t ncap = p.ncap;
     const uint32_t csz = wide ? 4u : 1u;
-    const uint32_t dsz = cpl <= 8 ? 2u : 4u;
+    const uint32_t dsz = cpl <= 7 ? 2u : 4u;
+    const uint32_t prof_bytes = wide ? 0u : (uint32_t)((cpl + 3) / 4) * 5u * 32u * 16u;
     const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
     p.sm_tmpl_bytes = align16(32 * cpl) + align16((uint32_t)(K * p.t.len_pad) * csz) +
-                      align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len);
+                      align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) + prof_bytes;
     p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
     p.sm_stage_b = wide ? align16(ncap) : align16((ncap + 3) / 4);
     if (p.sm_stage_b == 0) p.sm_stage_b = 16;
     p.sm_stage_c = wide ? align16(4 * (ncap + 1)) : align16(ncap + 1);
-    p.sm_rb = align16(ncap + 64);
+    p.sm_rb = align16(32 + ncap + 64 + 16);
     p.sm_dir = align16((ncap + 32) * 32 * dsz);
     p.sm_ops = align16((uint32_t)m + ncap + 4);
     p.sm_t2f = align16(2u * (uint32_t)p.t.len_pad);
@@ -747,9 +826,10 @@ int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_opti
     case 2: return launch_align_w<2>(p, wide, num_sms, max_smem_optin, stream);
     case 4: return launch_align_w<4>(p, wide, num_sms, max_smem_optin, stream);
     case 6: return launch_align_w<6>(p, wide, num_sms, max_smem_optin, stream);
-    case 8: return launch_align_w<8>(p, wide, num_sms, max_smem_optin, stream);
+    case 7: return launch_align_w<7>(p, wide, num_sms, max_smem_optin, stream);
+    case 10: return launch_align_w<10>(p, wide, num_sms, max_smem_optin, stream);
     case 12: return launch_align_w<12>(p, wide, num_sms, max_smem_optin, stream);
-    case 16: return launch_align_w<16>(p, wide, num_sms, max_smem_optin, stream);
+    case 15: return launch_align_w<15>(p, wide, num_sms, max_smem_optin, stream);
     default: return -1001;
     }
 }
@@ -770,9 +850,10 @@ int configure_kernels(int max_smem_optin)
     if ((e = set_attr<2>(max_smem_optin))) return e;
     if ((e = set_attr<4>(max_smem_optin))) return e;
     if ((e = set_attr<6>(max_smem_optin))) return e;
-    if ((e = set_attr<8>(max_smem_optin))) return e;
+    if ((e = set_attr<7>(max_smem_optin))) return e;
+    if ((e = set_attr<10>(max_smem_optin))) return e;
     if ((e = set_attr<12>(max_smem_optin))) return e;
-    if ((e = set_attr<16>(max_smem_optin))) return e;
+    if ((e = set_attr<15>(max_smem_optin))) return e;
     cudaError_t ce = cudaFuncSetAttribute(k_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (ce != cudaSuccess) return (int)ce;
     ce = cudaFuncSetAttribute(k_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
