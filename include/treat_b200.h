@@ -44,6 +44,8 @@ extern "C" {
 #define TREAT_B200_EXCLUDE_SNPS 0x1u /* NewAlignment(..., excludeSnps=true), storage.go:756 */
 #define TREAT_B200_WANT_OPS 0x2u     /* also return the traceback (gapped strings in 2-bit form) */
 #define TREAT_B200_NO_SUMMARY 0x4u   /* do not accumulate the per-context summary histograms */
+#define TREAT_B200_ONE_READ_PER_WARP 0x8u /* use the one-read-per-warp kernel even where the paired kernel applies */
+#define TREAT_B200_FULL_TRACEBACK_STORE 0x10u /* keep every direction word (global scratch) instead of the band */
 
 /* ---- per-read status bits ----------------------------------------------------------- */
 #define TREAT_B200_ST_REF_PANIC 0x1u  /* reference indexes frag.EditSite out of range here (align.go:250-257) */
@@ -165,6 +167,9 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
                                    uint8_t *d_ops, uint32_t ops_stride, void *stream);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx);
+/* tuning: rows of traceback words kept per lane in shared memory (0 = default 64); any value is
+ * exact, reads whose optimal path could leave the band are re-filled into global scratch */
+int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows);
 
 /* ---- summaries: device-resident uint64 counters --------------------- */
 uint32_t treat_b200_summary_bins(const treat_b200_ctx *ctx);

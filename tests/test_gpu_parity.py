@@ -168,12 +168,17 @@ def _batch_vs_oracle(eng, t, tmp_path, N, seed, p_trunc=0.0, offset=0, exclude=F
     assert np.array_equal(grec["raw_len"], lens)
     want = summary_from_records(orec, t.m, offset, om.EditStop)
     assert np.array_equal(eng.summary(), want)
+    # the one-read-per-warp kernel and the full (unbanded) traceback store must give the same bytes
+    k = min(N, 3001)
+    for extra in (cabi.ONE_READ_PER_WARP, cabi.FULL_TRACEBACK_STORE, cabi.ONE_READ_PER_WARP | cabi.FULL_TRACEBACK_STORE):
+        srec, sops = eng.align_batch(seqs[:int(off[k])], off[:k + 1], rc[:k], flags | extra | cabi.NO_SUMMARY)
+        assert np.array_equal(srec, grec[:k]) and np.array_equal(sops[:, :gops.shape[1]], gops[:k, :sops.shape[1]])
     return grec, orec, seqs, off
 
 
 def test_synthetic_rps12_vs_oracle(eng, tmp_path):
     """Config 3 shape (RPS12, K=5) at a size the oracle finishes in seconds: all records + all ops."""
-    grec, orec, seqs, off = _batch_vs_oracle(eng, synth.rps12_template(), tmp_path, 20000, synth.SEED_BASE + 3)
+    grec, orec, seqs, off = _batch_vs_oracle(eng, synth.rps12_template(), tmp_path, 20001, synth.SEED_BASE + 3)
     # JuncSeq is a window of the upper-cased raw read
     for i in np.nonzero(orec["junc_seq_len"] > 0)[0][:200]:
         s = seqs[int(off[i]):int(off[i + 1])].tobytes().upper()
@@ -188,6 +193,19 @@ def test_synthetic_rps12_offset_exclude(eng, tmp_path):
 def test_synthetic_long_template_vs_oracle(eng, tmp_path):
     """Config 5 shape: ~600-nt gene (m=300, K=10), variable-length reads with 5'/3' truncation."""
     _batch_vs_oracle(eng, synth.long_template(300, 8), tmp_path, 3000, synth.SEED_BASE + 5, p_trunc=0.2)
+
+
+def test_band_fallback(eng, tmp_path):
+    """Reads whose optimal path leaves the shared-memory band (long truncations, big deletions, a
+    deliberately tiny band) must be re-filled into the global scratch and stay exact."""
+    t = synth.rps12_template()
+    _batch_vs_oracle(eng, t, tmp_path, 4001, synth.SEED_BASE + 77, p_trunc=0.6)
+    from treat_b200.cabi import lib, check
+    for rows in (9, 20, 1000):
+        check(lib().treat_b200_set_band_rows(eng._ctx, rows), eng._ctx)
+        _batch_vs_oracle(eng, t, tmp_path, 2001, synth.SEED_BASE + 78 + rows, p_trunc=0.3)
+        _batch_vs_oracle(eng, synth.long_template(300, 8), tmp_path, 1001, synth.SEED_BASE + 79 + rows, p_trunc=0.3)
+    check(lib().treat_b200_set_band_rows(eng._ctx, 0), eng._ctx)
 
 
 def test_other_template_sizes(eng, tmp_path):

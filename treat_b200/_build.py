@@ -22,9 +22,9 @@ NVCC_FLAGS = [
 ]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra"]
 
-CUDA_SOURCES = ["kernels.cu", "capi.cu"]
+CUDA_SOURCES = ["pack_kernel.cu", "align_kernel.cu", "capi.cu"]
 CXX_SOURCES = ["host/treat_host.cpp", "host/capi_host.cpp"]
-HEADERS = ["device_format.h", "host/treat_host.hpp", "../../include/treat_b200.h"]
+HEADERS = ["device_format.h", "ptx_helpers.cuh", "host/treat_host.hpp", "../../include/treat_b200.h"]
 
 
 def _nvcc() -> str:

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libtreat_b200.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TOO_LONG, ERR_NO_TEMPLATE, ERR_NO_DEVICE, ERR_TEMPLATE, ERR_IO = range(-1, -9, -1)
 FORWARD, REVERSE = 1, -1
-EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY = 0x1, 0x2, 0x4
+EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY, ONE_READ_PER_WARP, FULL_TRACEBACK_STORE = 0x1, 0x2, 0x4, 0x8, 0x10
 ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16
@@ -65,6 +65,7 @@ SIGNATURES = {
     "treat_b200_pack_device": (C.c_int, [_P, _U8P, _P, C.POINTER(Packed), _P]),
     "treat_b200_align_packed_device": (C.c_int, [_P, C.POINTER(Packed), _P, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
     "treat_b200_launch_count": (C.c_uint64, [_P]),
+    "treat_b200_set_band_rows": (C.c_int, [_P, C.c_uint32]),
     "treat_b200_summary_bins": (C.c_uint32, [_P]),
     "treat_b200_summary_len": (C.c_uint64, [_P]),
     "treat_b200_get_summary": (C.c_int, [_P, _P, C.c_uint64]),

@@ -1,0 +1,1002 @@
+// align_kernel.cu -- K2 of the TREAT alignment hot path (sm_100a): nwalgo.Align + traceback +
+// computeT / findJSS / findJES / computeAltEditing / NewAlignment (align.go:95-279) on the device.
+//
+// One warp per read-template pair (k_align) or per TWO pairs (k_align2).  The DP is an
+// anti-diagonal wavefront: lane l owns template bases [l*CPL, (l+1)*CPL), the read streams through
+// as rows, lane l works on row t-l at step t and hands its right-edge cell to lane l+1 with
+// __shfl_up_sync.  Template, edit-site counts and the scoring profile live in shared memory;
+// packed reads are staged by cp.async.bulk (TMA) behind an mbarrier, one batch ahead.
+//
+// Score transform.  nwalgo fills F[i][j] = max(F[i-1][j-1] + (a==b ? 1 : -1), F[i-1][j] - 1,
+// F[i][j-1] - 1), F[i][0] = -i, F[0][j] = -j.  With G = F + i + j the gap terms vanish:
+//     G[i][j] = max(G[i-1][j-1] + w, G[i-1][j], G[i][j-1]),  w = 3 on a match, 1 otherwise,
+//     G[i][0] = G[0][j] = 0,  F[m][n] = G[m][n] - m - n,
+// every horizontal / vertical difference of G lies in {0,1,2,3}, and nwalgo's pointer tests are
+//     max == hgap ("Up",   consumes the template base)  <=>  G[i][j] == G[i-1][j]
+//     max == vgap ("Left", consumes the read base)      <=>  G[i][j] == G[i][j-1].
+// A row with w = 0 leaves the previous row unchanged, so idle wavefront steps need no branch.
+//
+// Direction storage.  Per lane and step ONE word: the CPL horizontal differences as base-4 digits
+// (built with IMADs: sum_k (f_k - f_{k-1}) 4^k = 4^CPL f_last - 3 sum_k f_k 4^k - left) plus
+// (left boundary value mod 4) on top.  From two such words (rows j and j-1) the traceback recovers
+// G mod 4 of any cell, hence both pointer tests; it walks 32 cells of a diagonal run per iteration.
+//
+// Band.  Only words whose cells lie within B diagonals of the main diagonal are kept (a window of
+// W = 2B + CPL + 1 steps per lane in shared memory).  Any optimal path with D deletions, I insertions
+// and X mismatches has 2D + I + 2X = m - S and D + 2I + 2X = n - S (S = F[m][n]), so it stays inside
+// the band whenever (m - S)/2 <= B and (n - S)/2 <= B; the warp checks this after the fill and
+// otherwise repeats the fill with every word written to an L2-resident global scratch.  Exact either
+// way; the band only shrinks shared memory so that more warps fit on an SM.
+//
+// k_align2 packs two reads into the 16-bit halves of every register (VIADDMNMX.S16x2 /
+// VIMNMX.S16x2, native DPX on sm_100a); the digit words of both reads come out of the same 32-bit
+// IMAD chain because the packing is a ring homomorphism mod 2^32.
+//
+// Integer dynamic programming: no tensor cores on purpose.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <type_traits>
+
+#include "device_format.h"
+#include "ptx_helpers.cuh"
+
+namespace treat_b200 {
+
+constexpr int kPadCode = 4;  // profile row with w = 0: a no-op row of the wavefront
+
+// ------------------------------------------------------------------------------------------
+// direction words
+// ------------------------------------------------------------------------------------------
+template <int CPL>
+struct Dir {
+    using word_t = typename std::conditional<(CPL <= 7), uint16_t, uint32_t>::type;
+    static constexpr int kTop = (CPL <= 7) ? 14 : 30;                     // bit position of (left & 3)
+    static constexpr uint32_t kOdd = (CPL <= 7) ? 0x1555u : 0x15555555u;  // low bits of the digits
+    static_assert(CPL <= 15, "direction word holds at most 15 base-4 digits");
+};
+
+// sum of the base-4 digits of x (the caller only needs it mod 4)
+__device__ __forceinline__ uint32_t digit_sum(uint32_t x, uint32_t odd)
+{
+    return __popc(x & odd) + 2u * __popc(x & (odd << 1));
+}
+
+// ------------------------------------------------------------------------------------------
+// scoring profile in shared memory: w for (read code row, lane, column of the lane) as 32-bit words,
+// laid out so that every lane fetches its CPL words with conflict-free vector loads
+// ------------------------------------------------------------------------------------------
+template <int CPL>
+struct Prof {
+    static constexpr int N4 = CPL / 4, REM = CPL % 4;
+    static constexpr int REMW = REM == 3 ? 4 : REM;  // words of the remainder chunk (3 -> padded to 4)
+    __host__ __device__ static constexpr uint32_t bytes(int rows) { return (uint32_t)rows * 32u * 4u * (N4 * 4 + REMW); }
+    // word index of (row, lane, column k)
+    __device__ static int index(int rows, int row, int lane, int k)
+    {
+        if (k < N4 * 4) return (((k >> 2) * rows + row) * 32 + lane) * 4 + (k & 3);
+        return N4 * rows * 128 + (row * 32 + lane) * REMW + (k - N4 * 4);
+    }
+    __device__ __forceinline__ static void load(const uint32_t *base, int rows, int row, int lane, uint32_t (&w)[CPL])
+    {
+#pragma unroll
+        for (int q = 0; q < N4; q++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(base + ((q * rows + row) * 32 + lane) * 4);
+            w[4 * q] = v.x;
+            w[4 * q + 1] = v.y;
+            w[4 * q + 2] = v.z;
+            w[4 * q + 3] = v.w;
+        }
+        const uint32_t *rp = base + N4 * rows * 128 + (row * 32 + lane) * REMW;
+        if (REM == 1) {
+            w[4 * N4] = rp[0];
+        } else if (REM == 2) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(rp);
+            w[4 * N4] = v.x;
+            w[4 * N4 + 1] = v.y;
+        } else if (REM == 3) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(rp);
+            w[4 * N4] = v.x;
+            w[4 * N4 + 1] = v.y;
+            w[4 * N4 + 2] = v.z;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Bit rows over template sites in array order ti = 0..len-1 (site number = len-1-ti), one 32-bit
+// word per lane, kept in shared memory: the willf/bitset sets of align.go:122-181.
+// ------------------------------------------------------------------------------------------
+struct BitRows {
+    const uint32_t *T;  // [K][tw]
+    int tw, len, lane;
+    // highest ti <= limit whose bit is clear in row k, or -1
+    __device__ __forceinline__ int highest_clear_le(int k, int limit) const
+    {
+        uint32_t w = 0;
+        const int lo = lane * 32;
+        if (lane < tw && lo <= limit) {
+            w = ~T[k * tw + lane];
+            if (limit - lo < 31) w &= (2u << (limit - lo)) - 1u;
+        }
+        const uint32_t any = __ballot_sync(FULL_MASK, w != 0);
+        if (!any) return -1;
+        const int hw = 31 - __clz(any);
+        const uint32_t wv = __shfl_sync(FULL_MASK, w, hw);
+        return hw * 32 + 31 - __clz(wv);
+    }
+    // lowest ti whose bit is clear in row k, or -1
+    __device__ __forceinline__ int lowest_clear(int k) const
+    {
+        uint32_t w = 0;
+        const int lo = lane * 32;
+        if (lane < tw) {
+            w = ~T[k * tw + lane];
+            if (len - 1 - lo < 31) w &= (2u << (len - 1 - lo)) - 1u;
+        }
+        const uint32_t any = __ballot_sync(FULL_MASK, w != 0);
+        if (!any) return -1;
+        const int lw = __ffs(any) - 1;
+        const uint32_t wv = __shfl_sync(FULL_MASK, w, lw);
+        return lw * 32 + __ffs(wv) - 1;
+    }
+    __device__ __forceinline__ bool any_set(int k) const
+    {
+        uint32_t w = 0;
+        const int lo = lane * 32;
+        if (lane < tw) {
+            w = T[k * tw + lane];
+            if (len - 1 - lo < 31) w &= (2u << (len - 1 - lo)) - 1u;
+        }
+        return __any_sync(FULL_MASK, w != 0);
+    }
+    // bitset.Test on a SITE number (out of range -> false, as willf/bitset does)
+    __device__ __forceinline__ bool test_site(int k, int site) const
+    {
+        if (site < 0 || site >= len) return false;
+        const int ti = len - 1 - site;
+        return (T[k * tw + (ti >> 5)] >> (ti & 31)) & 1u;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// shared-memory views
+// ------------------------------------------------------------------------------------------
+template <typename cnt_t>
+struct CtaSmem {
+    uint8_t *tb;               // [32*CPL] template bases (codes, or bytes on the wide path)
+    cnt_t *tcount;             // [K][len_pad] EditSite
+    int32_t *alt;              // [2*n_alt]
+    uint32_t *sum_lo, *sum_hi; // summary histograms of this CTA (64-bit counters as two words)
+    uint32_t sum_len;
+    uint32_t *prof;            // scoring profile
+};
+
+struct WarpSmem {
+    uint8_t *stage;    // 2 slots x reads-per-warp x (bases, counts)
+    uint8_t *rb;       // read bases (or pair codes) as bytes; 32 pad bytes in front
+    void *dir;         // direction words [steps][32]
+    uint32_t *ops2;    // traceback ops, 2 bits each, index p = 0 .. m+n-1 (alignment = [pos, m+n))
+    uint16_t *t2f;     // template site -> read base index (0xffff = deletion)
+    uint32_t *tbits;   // [K][tw]
+    uint64_t *bar;     // [2] mbarriers
+};
+
+template <typename cnt_t>
+__device__ __forceinline__ CtaSmem<cnt_t> carve_cta(uint8_t *smem, const AlignParams &p, int cpl)
+{
+    CtaSmem<cnt_t> c;
+    c.tb = smem;
+    c.tcount = reinterpret_cast<cnt_t *>(smem + align16(32 * cpl));
+    c.alt = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(c.tcount) +
+                                        align16((uint32_t)(p.t.K * p.t.len_pad * sizeof(cnt_t))));
+    c.sum_lo = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.alt) + align16(8u * (p.t.n_alt ? p.t.n_alt : 1)));
+    c.sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
+    c.sum_hi = c.sum_lo + c.sum_len;
+    c.prof = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.sum_lo) + align16(8u * c.sum_len));
+    return c;
+}
+
+__device__ __forceinline__ WarpSmem carve_warp(uint8_t *smem, const AlignParams &p, int warp)
+{
+    WarpSmem w;
+    uint8_t *b = smem + p.sm_tmpl_bytes + (size_t)warp * p.sm_warp_bytes;
+    w.stage = b;
+    w.rb = b + p.sm_stage_total;
+    w.dir = w.rb + p.sm_rb;
+    w.ops2 = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(w.dir) + p.sm_dir);
+    w.t2f = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(w.ops2) + p.sm_ops);
+    w.tbits = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(w.t2f) + p.sm_t2f);
+    w.bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(w.tbits) + p.sm_tbits);
+    return w;
+}
+
+template <typename cnt_t>
+__device__ __forceinline__ void load_template(const CtaSmem<cnt_t> &c, const AlignParams &p, int cpl)
+{
+    const int m = p.t.m;
+    for (int i = threadIdx.x; i < 32 * cpl; i += blockDim.x) c.tb[i] = i < m ? p.t.tb[i] : 0;
+    for (int i = threadIdx.x; i < p.t.K * p.t.len_pad; i += blockDim.x)
+        c.tcount[i] = reinterpret_cast<const cnt_t *>(p.t.tcount)[i];
+    for (int i = threadIdx.x; i < 2 * p.t.n_alt; i += blockDim.x) c.alt[i] = p.t.alt[i];
+    for (uint32_t i = threadIdx.x; i < 2 * c.sum_len; i += blockDim.x) c.sum_lo[i] = 0u;
+}
+
+// w of template column `col` against read code c (0..2 bases, 3 = other, 4 = pad row)
+__device__ __forceinline__ uint32_t score_w(const AlignParams &p, int c, int col)
+{
+    if (c == kPadCode) return 0u;
+    return (c < 3 && col < p.t.m && p.t.tb[col] == c) ? 3u : 1u;
+}
+
+// ------------------------------------------------------------------------------------------
+// traceback (nwalgo: Up, then Left, then Diagonal).  getw(step, lane) returns the direction word
+// of the read being traced.  Ops are OR-ed into the zeroed 2-bit array
+// ops2 at index p (matches are 0, so only gaps are written).  Returns pos (alignment = [pos, m+n)).
+// ------------------------------------------------------------------------------------------
+template <int CPL, typename GetW>
+__device__ __forceinline__ int traceback(GetW getw, uint32_t *ops2, int m, int n, int lane, int &ngaps)
+{
+    using DT = Dir<CPL>;
+    int pos = m + n, i = m, j = n;
+    ngaps = 0;
+    while (i > 0 && j > 0) {
+        const int ii = i - lane, jj = j - lane;
+        bool stop = true, is_up = false;
+        if (ii >= 1 && jj >= 1) {
+            const int ln = (ii - 1) / CPL, k = (ii - 1) - ln * CPL;
+            const int tt = jj - 1 + ln;
+            const uint32_t w1 = getw(tt, ln);
+            const uint32_t a = (w1 >> (2 * k)) & 3u;
+            if (a == 0) {
+                is_up = true;  // G[i][j] == G[i-1][j]
+            } else {
+                const uint32_t msk = (4u << (2 * k)) - 1u;
+                const uint32_t g1 = (w1 >> DT::kTop) + digit_sum(w1 & msk, DT::kOdd);
+                uint32_t g0 = 0;  // G[i][0] = 0
+                if (jj >= 2) {
+                    const uint32_t w0 = getw(tt - 1, ln);
+                    g0 = (w0 >> DT::kTop) + digit_sum(w0 & msk, DT::kOdd);
+                }
+                stop = ((g1 - g0) & 3u) == 0;  // G[i][j] == G[i][j-1]: Left
+            }
+        }
+        const uint32_t sm = __ballot_sync(FULL_MASK, stop);
+        const int run = sm ? __ffs(sm) - 1 : 32;  // diagonal moves before the first gap / matrix edge
+        pos -= run;
+        i -= run;
+        j -= run;
+        if (run < 32 && i > 0 && j > 0) {
+            const bool up = __shfl_sync(FULL_MASK, is_up, run);
+            --pos;
+            ngaps++;
+            if (lane == 0) ops2[pos >> 4] |= (up ? TREAT_B200_OP_DEL : TREAT_B200_OP_INS) << (2 * (pos & 15));
+            if (up) i--; else j--;
+        }
+    }
+    __syncwarp();
+    // first row / column: pointers are Left on row 0 and Up on column 0
+    const int rest = i + j;  // at most one of them is non-zero
+    if (rest) {
+        const uint32_t op = i ? TREAT_B200_OP_DEL : TREAT_B200_OP_INS;
+        for (int q = lane; q < rest; q += 32) {
+            const int pp = pos - 1 - q;
+            atomicOr(&ops2[pp >> 4], op << (2 * (pp & 15)));
+        }
+        pos -= rest;
+        ngaps += rest;
+    }
+    __syncwarp();
+    return pos;
+}
+
+// ------------------------------------------------------------------------------------------
+// everything after the traceback for one read: computeT, JSS/ESS/JES, alt editing, JuncSeq window,
+// record, summary counters, packed ops.  rbf(fi) returns the read base (code or byte) at index fi.
+// ------------------------------------------------------------------------------------------
+template <typename cnt_t, typename RbFn>
+__device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<cnt_t> &cs, const WarpSmem &ws, int lane,
+                                            uint64_t r, int n, uint32_t rflags, int score, int pos, int ngaps,
+                                            const cnt_t *rcount, RbFn rbf, unsigned long long &ctr)
+{
+    const int m = p.t.m, len = p.t.len, len_pad = p.t.len_pad, K = p.t.K, n_alt = p.t.n_alt;
+    const int tw = len_pad >> 5;
+    const int alen = m + n - pos;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t *ops2 = ws.ops2;
+
+    // ---- computeT part 1 (align.go:131-171): map template sites to read bases, count mismatches ----
+    int mism = 0;
+    const bool indel = ngaps != 0;
+    if (!indel) {
+        // no gap in the alignment: column c pairs template base c with read base c
+        for (int c0 = 0; c0 < m; c0 += 32) {
+            const int c = c0 + lane;
+            const bool mm = c < m && rbf(c) != (int)cs.tb[c];
+            mism += __popc(__ballot_sync(FULL_MASK, mm));
+        }
+    } else {
+        int ti_base = 0, fi_base = 0;
+        for (int c0 = 0; c0 < alen; c0 += 32) {
+            const int c = c0 + lane, pp = pos + c;
+            const int op = c < alen ? (int)((ops2[pp >> 4] >> (2 * (pp & 15))) & 3u) : 3;
+            const bool cT = op == TREAT_B200_OP_MATCH || op == TREAT_B200_OP_DEL;
+            const bool cR = op == TREAT_B200_OP_MATCH || op == TREAT_B200_OP_INS;
+            const uint32_t mT = __ballot_sync(FULL_MASK, cT), mR = __ballot_sync(FULL_MASK, cR);
+            const int ti = ti_base + __popc(mT & lt), fi = fi_base + __popc(mR & lt);
+            if (cT) ws.t2f[ti] = op == TREAT_B200_OP_MATCH ? (uint16_t)fi : (uint16_t)0xffff;
+            const bool mm = op == TREAT_B200_OP_MATCH && rbf(fi) != (int)cs.tb[ti];
+            mism += __popc(__ballot_sync(FULL_MASK, mm));
+            ti_base += __popc(mT);
+            fi_base += __popc(mR);
+        }
+        if (lane == 0) ws.t2f[m] = (uint16_t)n;  // last edit site (align.go:173-178)
+        __syncwarp();
+    }
+
+    // ---- computeT part 2: per template site compare edit-base counts, build the bit rows ----------
+    for (int wv = 0; wv < tw; wv++) {
+        const int ti = wv * 32 + lane;
+        const bool valid = ti < len;
+        uint32_t count = 0;
+        if (valid) {
+            const uint32_t f = indel ? (uint32_t)ws.t2f[ti] : (uint32_t)ti;
+            count = f == 0xffffu ? 0u : (uint32_t)rcount[f];
+        }
+        for (int k = 0; k < K; k++) {
+            const bool match = valid && (uint32_t)cs.tcount[k * len_pad + ti] == count;
+            const uint32_t word = __ballot_sync(FULL_MASK, match);
+            if (lane == 0) ws.tbits[k * tw + wv] = word;
+        }
+    }
+    __syncwarp();
+
+    // ---- findJSS / computeAltEditing / findJES / NewAlignment (align.go:95-120,183-279) -----------
+    BitRows B{ws.tbits, tw, len, lane};
+    int has_mutation = 0;
+    if (indel) has_mutation = 1;
+    if (((p.flags & TREAT_B200_EXCLUDE_SNPS) && mism >= 1) || mism >= 3) has_mutation = 1;
+
+    const int hc0 = B.highest_clear_le(0, len - 1);
+    const bool t0_all = hc0 < 0;
+    int junc_start = t0_all ? len - 1 : (!B.any_set(0) ? -1 : len - 1 - hc0);
+    int alt_editing = 0;
+    {
+        int shift = junc_start, alt = -1;
+        for (int k = 2; k < K; k++) {
+            if (B.test_site(k, shift)) {
+                alt = k - 2;
+                break;
+            }
+        }
+        if (alt >= 0 && shift == cs.alt[alt]) {
+            const int hc = B.highest_clear_le(alt + 2, len - 1 - shift);
+            const bool full_match = hc < 0;
+            if (!full_match) shift = len - 1 - hc;
+            if (full_match || shift >= cs.alt[n_alt + alt]) {
+                alt_editing = alt + 1;
+                if (full_match) {
+                    junc_start = len - 1;
+                } else {
+                    const int h0 = B.highest_clear_le(0, len - 1 - shift);
+                    if (h0 >= 0) junc_start = len - 1 - h0;
+                }
+            }
+        }
+    }
+    const int lc1 = B.lowest_clear(1);
+    int junc_end = lc1 < 0 ? -1 : len - 1 - lc1;
+    int edit_stop = junc_start - 1;
+    int junc_len = 0;
+    uint32_t js_off = 0, js_len = 0;
+    uint32_t status = rflags;
+    if (junc_end > edit_stop) {
+        junc_len = junc_end - edit_stop;
+        if (has_mutation == 0 && !t0_all) {
+            const int from = (len - 1) - junc_end, to = (len - 1) - edit_stop;
+            if (to > n + 1) {
+                status |= TREAT_B200_ST_REF_PANIC;  // Go: index out of range on frag.EditSite
+            } else {
+                // JuncSeq = EditBase x EditSite[i] + Bases[i] for i in [from, to): a window of the
+                // upper-cased raw read starting at the edit-base run in front of base `from`
+                uint32_t sf = 0, st = 0;
+                for (int q = lane; q < to; q += 32) {
+                    const uint32_t c = (uint32_t)rcount[q];
+                    st += c;
+                    if (q < from) sf += c;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    st += __shfl_xor_sync(FULL_MASK, st, o);
+                    sf += __shfl_xor_sync(FULL_MASK, sf, o);
+                }
+                js_off = sf + (uint32_t)min(from, n);
+                js_len = st + (uint32_t)min(to, n) - js_off;
+                if (js_len == 0) js_off = 0;
+            }
+        }
+    } else if (junc_end < edit_stop) {
+        junc_end = edit_stop;
+        junc_len = 0;
+    }
+    if (t0_all) {
+        junc_end = junc_start;
+        edit_stop = junc_start;
+        junc_len = 0;
+    }
+    const uint32_t read_count = p.read_count ? p.read_count[r] : 1u;
+
+    if (lane == 0) {
+        treat_b200_record o;
+        o.edit_stop = edit_stop + p.t.edit_offset;
+        o.junc_start = junc_start + p.t.edit_offset;
+        o.junc_end = junc_end + p.t.edit_offset;
+        o.junc_len = junc_len;
+        o.read_count = read_count;
+        o.has_mutation = (uint8_t)has_mutation;
+        o.alt_editing = (uint8_t)alt_editing;
+        o.mismatches = (uint8_t)(mism & 0xff);  // uint8 wraps (align.go:51,148)
+        o.indel = indel ? 1 : 0;
+        o.score = score;
+        o.junc_seq_off = js_off;
+        o.junc_seq_len = js_len;
+        o.aln_len = (uint16_t)alen;
+        o.n_bases = (uint16_t)n;
+        o.status = (uint8_t)status;
+        o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
+        o.raw_len = p.raw_len[r];
+        const uint4 *src = reinterpret_cast<const uint4 *>(&o);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.rec + r);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        dst[2] = src[2];
+    }
+
+    if (cs.sum_len) {
+        // cmd/treat/stats.go:140-187: lane L accumulates counter L of the summary header in a register
+        const unsigned long long rcw = read_count;
+        const int cls = has_mutation ? 2 : 1;
+        const int mm8 = mism & 0xff;
+        const int mcls = indel ? 3 : mm8 == 1 ? 5 : mm8 == 2 ? 6 : mm8 > 2 ? 4 : 0;
+        if (lane == 0 || lane == cls || (mcls && lane == mcls)) ctr += rcw;
+        if (lane == 7 || lane == 7 + cls || (mcls && lane == 7 + mcls) || lane == 14) ctr += 1ull;
+        if (lane == 15) ctr += (unsigned long long)m * (unsigned long long)n;
+        // cmd/treat/handlers.go:203-215: three histograms, one lane each
+        if (lane < 3 && !(edit_stop + p.t.edit_offset == p.t.tmpl_edit_stop && junc_len == 0)) {
+            const uint32_t bin = lane == 0 ? (uint32_t)(edit_stop + 2) : lane == 1 ? (uint32_t)junc_len : (uint32_t)(junc_end + 2);
+            if (bin < p.bins) {
+                const uint32_t idx = TREAT_B200_SUMMARY_HEADER + (uint32_t)lane * p.bins + bin;
+                const uint32_t old = atomicAdd(&cs.sum_lo[idx], read_count);
+                if (old + read_count < old) atomicAdd(&cs.sum_hi[idx], 1u);
+            }
+        }
+    }
+
+    // ---- traceback ops, 2 bits per column, in alignment order: a funnel shift of ops2 by pos ------
+    if (p.ops) {
+        uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + r * (uint64_t)p.ops_stride);
+        const int nwords = (int)(p.ops_stride / 4);
+        const int w0 = pos >> 4, sh = 2 * (pos & 15);
+        const int avail = (int)(p.sm_ops / 4) - 1;  // ops2 words that exist (all zero past the alignment)
+        for (int wi = lane; wi < nwords; wi += 32) {
+            uint32_t w = 0;
+            if (wi * 16 < alen) {
+                const int si = w0 + wi;
+                const uint32_t lo = ops2[si], hi = si + 1 <= avail ? ops2[si + 1] : 0u;
+                w = __funnelshift_r(lo, hi, sh);
+            }
+            go[wi] = w;
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// fill loops.  FULL = false: words inside the band go to the shared-memory window (row t - tlo);
+// FULL = true: every word goes to the warp's global scratch (row t).
+// ------------------------------------------------------------------------------------------
+template <int CPL, bool WIDE, bool FULL, typename dir_t>
+__device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rbl, const int (&tcr)[CPL], int n, int steps,
+                                         int lane, int (&H)[CPL], dir_t *out, int tlo, int W)
+{
+    using DT = Dir<CPL>;
+    constexpr int ROWS = 5;
+#pragma unroll
+    for (int k = 0; k < CPL; k++) H[k] = 0;  // G[i][0] = 0
+    int diag = 0;                            // G[i0-1][j-1]
+    uint32_t pwc[CPL];
+    int cnext = 0;
+    if (!WIDE) {
+        Prof<CPL>::load(prof, ROWS, rbl[0], lane, pwc);
+        cnext = rbl[1];
+    }
+    dir_t *o = out + lane - (FULL ? 0 : tlo * 32);
+#pragma unroll 2
+    for (int t = 0; t < steps; t++) {
+        uint32_t pwn[CPL];
+        int wv[CPL];
+        if (!WIDE) {
+            Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
+            cnext = rbl[t + 2];
+#pragma unroll
+            for (int k = 0; k < CPL; k++) wv[k] = (int)pwc[k];
+        } else {
+            const int idx = t - lane;
+            const bool live = idx >= 0 && idx < n;
+            const int rc = live ? (int)rbl[t] : 0x200;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) wv[k] = live ? (rc == tcr[k] ? 3 : 1) : 0;
+        }
+        const int recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
+        const int left = lane == 0 ? 0 : recv;  // G[i0-1][j]
+        int dg = diag, lf = left;
+        uint32_t S = 0;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) {
+            const int e = max(dg + wv[k], H[k]);
+            const int f = max(e, lf);
+            dg = H[k];
+            lf = f;
+            H[k] = f;
+            S += (uint32_t)f << (2 * k);
+        }
+        diag = left;
+        const uint32_t word = ((uint32_t)lf << (2 * CPL)) - 3u * S - (uint32_t)left + (((uint32_t)left & 3u) << DT::kTop);
+        if (FULL || (unsigned)(t - tlo) < (unsigned)W) o[t * 32] = (dir_t)word;
+        if (!WIDE) {
+#pragma unroll
+            for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
+        }
+    }
+    __syncwarp();
+}
+
+template <int CPL, bool FULL>
+__device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pcl, int steps, int lane, uint32_t (&H)[CPL],
+                                         uint32_t *out, int tlo, int W)
+{
+    using DT = Dir<CPL>;
+    constexpr int ROWS = 25;
+#pragma unroll
+    for (int k = 0; k < CPL; k++) H[k] = 0u;
+    uint32_t diag = 0u;
+    uint32_t pwc[CPL];
+    Prof<CPL>::load(prof, ROWS, pcl[0], lane, pwc);
+    int cnext = pcl[1];
+    uint32_t *o = out + lane - (FULL ? 0 : tlo * 32);
+#pragma unroll 2
+    for (int t = 0; t < steps; t++) {
+        uint32_t pwn[CPL];
+        Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
+        cnext = pcl[t + 2];
+        const uint32_t recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
+        const uint32_t left = lane == 0 ? 0u : recv;
+        uint32_t dg = diag, lf = left, S = 0;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) {
+            const uint32_t e = __viaddmax_s16x2(dg, pwc[k], H[k]);
+            const uint32_t f = __vmaxs2(e, lf);
+            dg = H[k];
+            lf = f;
+            H[k] = f;
+            S += f << (2 * k);
+        }
+        diag = left;
+        // both halves at once: arithmetic mod 2^32 keeps each 16-bit digit word exact
+        const uint32_t word = (lf << (2 * CPL)) - 3u * S - left + ((left & 0x00030003u) << DT::kTop);
+        if (FULL || (unsigned)(t - tlo) < (unsigned)W) o[t * 32] = word;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
+    }
+    __syncwarp();
+}
+
+// the optimal path stays within B diagonals of the main one (see the header comment)
+__device__ __forceinline__ bool band_ok(int m, int n, int score, int B) { return m - score <= 2 * B && n - score <= 2 * B; }
+
+__device__ __forceinline__ void flush_summary(const AlignParams &p, uint32_t sum_len, const uint32_t *lo, const uint32_t *hi,
+                                              int lane, unsigned long long ctr)
+{
+    if (!sum_len) return;
+    unsigned long long *g = reinterpret_cast<unsigned long long *>(p.summary);
+    if (lane < TREAT_B200_SUMMARY_HEADER && ctr) atomicAdd(&g[lane], ctr);
+    __syncthreads();
+    for (uint32_t i = TREAT_B200_SUMMARY_HEADER + threadIdx.x; i < sum_len; i += blockDim.x) {
+        const unsigned long long v = (unsigned long long)lo[i] | ((unsigned long long)hi[i] << 32);
+        if (v) atomicAdd(&g[i], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a: one read per warp (any CPL <= 15; the only kernel of the wide path)
+// ------------------------------------------------------------------------------------------
+template <int CPL, bool WIDE>
+__global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignParams p)
+{
+    using DT = Dir<CPL>;
+    using dir_t = typename DT::word_t;
+    using cnt_t = typename std::conditional<WIDE, uint32_t, uint8_t>::type;
+    constexpr int ROWS = 5;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int m = p.t.m;
+
+    const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, CPL);
+    load_template(cs, p, CPL);
+    if (!WIDE) {
+        for (int i = threadIdx.x; i < ROWS * 32 * CPL; i += blockDim.x) {
+            const int k = i % CPL, ln = (i / CPL) & 31, c = i / (CPL * 32);
+            cs.prof[Prof<CPL>::index(ROWS, c, ln, k)] = score_w(p, c, ln * CPL + k);
+        }
+    }
+    const WarpSmem ws = carve_warp(smem, p, warp);
+    const uint32_t stage_bytes = p.sm_stage_b + p.sm_stage_c;
+    dir_t *s_dir = reinterpret_cast<dir_t *>(ws.dir);
+    if (lane == 0) {
+        mbar_init(&ws.bar[0], 1);
+        mbar_init(&ws.bar[1], 1);
+        fence_mbar_init();
+    }
+    ws.rb[lane] = kPadCode;  // rows "before" the read: no-op rows for lanes that have not started
+    __syncthreads();
+
+    int tcr[CPL];  // template bases of this lane's columns (the wide path compares instead of a profile)
+#pragma unroll
+    for (int k = 0; k < CPL; k++) {
+        const int idx = lane * CPL + k;
+        tcr[k] = idx < m ? (int)cs.tb[idx] : 0x100;  // 0x100 never equals a read byte
+    }
+    const int lanes_used = (m + CPL - 1) / CPL;
+    const int ops_words = (int)(p.sm_ops / 4);
+    const int W = (int)p.band_rows, B = (W - CPL - 1) / 2;
+    const int tlo = lane * (CPL + 1) - B - 1;
+    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
+    dir_t *scratch = reinterpret_cast<dir_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
+    unsigned long long ctr = 0;
+
+    auto issue = [&](uint64_t r, int slot) {
+        if (lane == 0) {
+            const uint32_t n = p.n[r];
+            const uint32_t cb = WIDE ? align16(n) : align16((n + 3) / 4);
+            const uint32_t cc = WIDE ? align16(4 * (n + 1)) : align16(n + 1);
+            uint8_t *dst = ws.stage + slot * stage_bytes;
+            fence_proxy_async();
+            mbar_expect_tx(&ws.bar[slot], cb + cc);
+            if (cb) bulk_g2s(dst, p.bases + r * (uint64_t)p.bases_stride, cb, &ws.bar[slot]);
+            bulk_g2s(dst + p.sm_stage_b, p.counts + r * (uint64_t)p.counts_stride, cc, &ws.bar[slot]);
+        }
+    };
+
+    uint32_t it = 0;
+    if (gw < p.N) issue(gw, 0);
+    for (uint64_t r = gw; r < p.N; r += nw, it++) {
+        const int slot = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        const int n = (int)p.n[r];
+        const uint32_t rflags = p.rflags[r];
+        __syncwarp();
+        if (r + nw < p.N) issue(r + nw, slot ^ 1);  // prefetch the next read of this warp
+        mbar_wait(&ws.bar[slot], parity);
+        if (n > (int)p.ncap) continue;  // cannot happen when ncap comes from K1's max; keeps the launch safe
+
+        const uint8_t *st_b = ws.stage + slot * stage_bytes;
+        const cnt_t *rcount = reinterpret_cast<const cnt_t *>(st_b + p.sm_stage_b);
+
+        // ---- unpack read bases to one byte each; rows behind the read are no-op rows -----------
+        uint8_t *rb = ws.rb + 32;
+        if (!WIDE) {
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(st_b);
+            for (int wi = lane; wi * 16 < n; wi += 32) {
+                const uint32_t w = pw[wi];
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t x = (w >> (8 * q)) & 0xffu;
+                    o[q] = (x & 3u) | ((x & 0xcu) << 6) | ((x & 0x30u) << 12) | ((x & 0xc0u) << 18);
+                }
+                *reinterpret_cast<uint4 *>(rb + wi * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+            rb[n + lane] = kPadCode;
+            rb[n + 32 + lane] = kPadCode;
+        } else {
+            for (int i = lane; i < n; i += 32) rb[i] = st_b[i];
+        }
+        for (int i = lane; i < ops_words; i += 32) ws.ops2[i] = 0u;
+        __syncwarp();
+
+        // ---- fill (band in shared memory), score, certificate ------------------------------------
+        int H[CPL];
+        const int steps = n > 0 ? n + lanes_used - 1 : 0;
+        const uint8_t *rbl = rb - lane;  // rbl[t] = read base of this lane's row at step t
+        fill_one<CPL, WIDE, false>(cs.prof, rbl, tcr, n, steps, lane, H, s_dir, tlo, W);
+        auto final_score = [&]() {
+            // F[m][n] = G[m][n] - m - n; G[m][n] lives in lane (m-1)/CPL, column (m-1)%CPL
+            int fin = 0;
+            const int kl = (m - 1) % CPL;
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (k == kl) fin = H[k];
+            return __shfl_sync(FULL_MASK, fin, (m - 1) / CPL) - m - n;
+        };
+        const int score = final_score();
+        int ngaps, pos;
+        if (band_ok(m, n, score, B) && !p.force_full) {
+            pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)s_dir[(tt - (ln * (CPL + 1) - B - 1)) * 32 + ln]; },
+                                 ws.ops2, m, n, lane, ngaps);
+        } else {
+            // the path may leave the band: repeat the fill with every word kept (global scratch, L2)
+            fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, 0, 0);
+            pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)scratch[tt * 32 + ln]; }, ws.ops2, m, n, lane, ngaps);
+        }
+        finish_read<cnt_t>(p, cs, ws, lane, r, n, rflags, score, pos, ngaps, rcount, [&](int fi) { return (int)rb[fi]; }, ctr);
+    }
+    flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: TWO reads per warp in the 16-bit halves of every register (packed alphabet, CPL <= 7)
+// ------------------------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ AlignParams p)
+{
+    static_assert(CPL <= 7, "two 16-bit direction words per 32-bit store");
+    using cnt_t = uint8_t;
+    constexpr int ROWS = 25;  // (code of read A) * 5 + (code of read B)
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int m = p.t.m;
+
+    const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, CPL);
+    load_template(cs, p, CPL);
+    for (int i = threadIdx.x; i < ROWS * 32 * CPL; i += blockDim.x) {
+        const int k = i % CPL, ln = (i / CPL) & 31, row = i / (CPL * 32);
+        const int col = ln * CPL + k;
+        cs.prof[Prof<CPL>::index(ROWS, row, ln, k)] = score_w(p, row / 5, col) | (score_w(p, row % 5, col) << 16);
+    }
+    const WarpSmem ws = carve_warp(smem, p, warp);
+    const uint32_t read_bytes = p.sm_stage_b + p.sm_stage_c;  // one read inside a stage slot
+    const uint32_t slot_bytes = 2 * read_bytes;
+    uint32_t *s_dir = reinterpret_cast<uint32_t *>(ws.dir);
+    if (lane == 0) {
+        mbar_init(&ws.bar[0], 1);
+        mbar_init(&ws.bar[1], 1);
+        fence_mbar_init();
+    }
+    ws.rb[lane] = kPadCode * 5 + kPadCode;
+    __syncthreads();
+
+    const int lanes_used = (m + CPL - 1) / CPL;
+    const int ops_words = (int)(p.sm_ops / 4);
+    const int W = (int)p.band_rows, B = (W - CPL - 1) / 2;
+    const int tlo = lane * (CPL + 1) - B - 1;
+    const uint64_t npairs = (p.N + 1) / 2;
+    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
+    unsigned long long ctr = 0;
+
+    auto issue = [&](uint64_t q, int slot) {
+        if (lane == 0) {
+            uint8_t *dst = ws.stage + slot * slot_bytes;
+            const uint64_t r0 = 2 * q;
+            const uint32_t n0 = p.n[r0];
+            const bool has1 = r0 + 1 < p.N;
+            const uint32_t n1 = has1 ? p.n[r0 + 1] : 0u;
+            const uint32_t cb0 = align16((n0 + 3) / 4), cc0 = align16(n0 + 1);
+            const uint32_t cb1 = has1 ? align16((n1 + 3) / 4) : 0u, cc1 = has1 ? align16(n1 + 1) : 0u;
+            fence_proxy_async();
+            mbar_expect_tx(&ws.bar[slot], cb0 + cc0 + cb1 + cc1);
+            if (cb0) bulk_g2s(dst, p.bases + r0 * (uint64_t)p.bases_stride, cb0, &ws.bar[slot]);
+            bulk_g2s(dst + p.sm_stage_b, p.counts + r0 * (uint64_t)p.counts_stride, cc0, &ws.bar[slot]);
+            if (cb1) bulk_g2s(dst + read_bytes, p.bases + (r0 + 1) * (uint64_t)p.bases_stride, cb1, &ws.bar[slot]);
+            if (cc1) bulk_g2s(dst + read_bytes + p.sm_stage_b, p.counts + (r0 + 1) * (uint64_t)p.counts_stride, cc1, &ws.bar[slot]);
+        }
+    };
+
+    uint32_t it = 0;
+    if (gw < npairs) issue(gw, 0);
+    for (uint64_t q = gw; q < npairs; q += nw, it++) {
+        const int slot = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        const uint64_t r0 = 2 * q;
+        const bool has1 = r0 + 1 < p.N;
+        const int n0 = (int)p.n[r0], n1 = has1 ? (int)p.n[r0 + 1] : 0;
+        __syncwarp();
+        if (q + nw < npairs) issue(q + nw, slot ^ 1);  // prefetch the next pair of this warp
+        mbar_wait(&ws.bar[slot], parity);
+        if (n0 > (int)p.ncap || n1 > (int)p.ncap) continue;  // cannot happen (ncap = K1's max n)
+
+        const uint8_t *st0 = ws.stage + slot * slot_bytes, *st1 = st0 + read_bytes;
+        const int nmax = max(n0, n1);
+
+        // ---- pair codes: pc[j] = 5 * codeA(j) + codeB(j), pad code behind either read -----------
+        uint8_t *pc = ws.rb + 32;
+        {
+            const uint32_t *pw0 = reinterpret_cast<const uint32_t *>(st0), *pw1 = reinterpret_cast<const uint32_t *>(st1);
+            for (int j = lane; j < nmax + 64; j += 32) {
+                const int c0 = j < n0 ? (int)((pw0[j >> 4] >> (2 * (j & 15))) & 3u) : kPadCode;
+                const int c1 = j < n1 ? (int)((pw1[j >> 4] >> (2 * (j & 15))) & 3u) : kPadCode;
+                pc[j] = (uint8_t)(c0 * 5 + c1);
+            }
+        }
+        __syncwarp();
+
+        // ---- fill: both reads at once, G values in the 16-bit halves ----------------------------
+        uint32_t H[CPL];
+        const int steps = nmax > 0 ? nmax + lanes_used - 1 : 0;
+        const uint8_t *pcl = pc - lane;
+        fill_two<CPL, false>(cs.prof, pcl, steps, lane, H, s_dir, tlo, W);
+        uint32_t fin = 0;
+        {
+            const int kl = (m - 1) % CPL;
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (k == kl) fin = H[k];
+            fin = __shfl_sync(FULL_MASK, fin, (m - 1) / CPL);
+        }
+        const int score0 = (int)(fin & 0xffffu) - m - n0, score1 = (int)(fin >> 16) - m - n1;
+        const bool banded = band_ok(m, n0, score0, B) && (!has1 || band_ok(m, n1, score1, B)) && !p.force_full;
+        if (!banded) fill_two<CPL, true>(cs.prof, pcl, steps, lane, H, scratch, 0, 0);  // keep every word (global scratch)
+
+        // ---- per read: traceback + editing-site assembly ---------------------------------------
+        for (int h = 0; h < (has1 ? 2 : 1); h++) {
+            const int n = h ? n1 : n0;
+            const uint8_t *st = h ? st1 : st0;
+            const cnt_t *rcount = reinterpret_cast<const cnt_t *>(st + p.sm_stage_b);
+            for (int i = lane; i < ops_words; i += 32) ws.ops2[i] = 0u;
+            __syncwarp();
+            int ngaps, pos;
+            const int sh = 16 * h;
+            if (banded)
+                pos = traceback<CPL>([&](int tt, int ln) { return (s_dir[(tt - (ln * (CPL + 1) - B - 1)) * 32 + ln] >> sh) & 0xffffu; },
+                                     ws.ops2, m, n, lane, ngaps);
+            else
+                pos = traceback<CPL>([&](int tt, int ln) { return (scratch[tt * 32 + ln] >> sh) & 0xffffu; }, ws.ops2, m, n, lane, ngaps);
+            finish_read<cnt_t>(p, cs, ws, lane, r0 + h, n, p.rflags[r0 + h], h ? score1 : score0, pos, ngaps, rcount,
+                               [&](int fi) {
+                                   const int c = pc[fi];
+                                   return h ? c % 5 : c / 5;
+                               },
+                               ctr);
+        }
+    }
+    flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: geometry + launch
+// ------------------------------------------------------------------------------------------
+static const int kCplSet[] = {1, 2, 4, 6, 7, 10, 12, 15};
+
+static int pick_cpl(int m)
+{
+    const int need = (m + 31) / 32;
+    for (int c : kCplSet)
+        if (c >= need) return c;
+    return -1;
+}
+
+static uint32_t prof_bytes(int cpl, int rows)
+{
+    const int n4 = cpl / 4, rem = cpl % 4, remw = rem == 3 ? 4 : rem;
+    return (uint32_t)rows * 32u * 4u * (uint32_t)(n4 * 4 + remw);
+}
+
+int plan_align(AlignParams &p, bool wide)
+{
+    const int m = p.t.m, K = p.t.K;
+    const int cpl = pick_cpl(m);
+    if (cpl < 0 || m < 1) return -1;
+    const bool pair = !wide && cpl <= 7 && !p.force_single;
+    p.pair = pair ? 1 : 0;
+    const uint32_t ncap = p.ncap;
+    const uint32_t csz = wide ? 4u : 1u;
+    const uint32_t dsz = pair ? 4u : (cpl <= 7 ? 2u : 4u);
+    const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
+    p.sm_tmpl_bytes = align16(32 * cpl) + align16((uint32_t)(K * p.t.len_pad) * csz) +
+                      align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) +
+                      (wide ? 0u : prof_bytes(cpl, pair ? 25 : 5));
+    p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
+    p.sm_stage_b = wide ? align16(ncap) : align16((ncap + 3) / 4);
+    if (p.sm_stage_b == 0) p.sm_stage_b = 16;
+    p.sm_stage_c = wide ? align16(4 * (ncap + 1)) : align16(ncap + 1);
+    p.sm_stage_total = 2 * (pair ? 2 : 1) * (p.sm_stage_b + p.sm_stage_c);
+    p.sm_rb = align16(32 + ncap + 64 + 16);
+    // band window: never more rows than the fill has steps
+    const uint32_t full_rows = ncap + 32;
+    uint32_t rows = p.band_rows ? p.band_rows : 64u;
+    if (rows < (uint32_t)cpl + 3) rows = (uint32_t)cpl + 3;
+    if (rows > full_rows) rows = full_rows;
+    p.band_rows = rows;
+    p.sm_dir = align16(rows * 32 * dsz);
+    p.scratch_stride = full_rows * 32;  // direction words of one warp's full fill
+    p.sm_ops = align16((((uint32_t)m + ncap + 15) / 16 + 2) * 4);
+    p.sm_t2f = align16(2u * (uint32_t)p.t.len_pad);
+    p.sm_tbits = align16(4u * (uint32_t)K * (uint32_t)(p.t.len_pad / 32));
+    p.sm_warp_bytes = p.sm_stage_total + p.sm_rb + p.sm_dir + p.sm_ops + p.sm_t2f + p.sm_tbits + 16;
+    p.sm_warp_bytes = (p.sm_warp_bytes + 127u) & ~127u;
+    return cpl;
+}
+
+// warps per CTA for this geometry (0: does not fit)
+int align_warps(const AlignParams &p, int max_smem)
+{
+    long warps = ((long)max_smem - (long)p.sm_tmpl_bytes) / (long)p.sm_warp_bytes;
+    if (warps > 16) warps = 16;
+    return warps < 1 ? 0 : (int)warps;
+}
+
+// bytes of global scratch the launch needs (num_sms CTAs x warps x scratch_stride words)
+uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem)
+{
+    const uint32_t dsz = p.pair ? 4u : (pick_cpl(p.t.m) <= 7 ? 2u : 4u);
+    return (uint64_t)num_sms * (uint64_t)align_warps(p, max_smem) * (uint64_t)p.scratch_stride * dsz;
+}
+
+template <typename Kern>
+static int launch_k(Kern kern, const AlignParams &p, uint64_t units, int num_sms, int max_smem, void *stream)
+{
+    const int warps = align_warps(p, max_smem);
+    if (warps < 1) return -1000;  // geometry does not fit shared memory
+    const uint64_t need_blocks = (units + warps - 1) / warps;
+    uint64_t blocks = (uint64_t)num_sms;  // persistent: one CTA per SM
+    if (need_blocks < blocks) blocks = need_blocks;
+    if (blocks == 0) return 0;
+    const size_t smem = p.sm_tmpl_bytes + (size_t)warps * p.sm_warp_bytes;
+    kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+template <int CPL>
+static int launch_cpl(const AlignParams &p, bool wide, int num_sms, int max_smem, void *stream)
+{
+    if constexpr (CPL <= 7) {
+        if (p.pair) return launch_k(k_align2<CPL>, p, (p.N + 1) / 2, num_sms, max_smem, stream);
+    }
+    return wide ? launch_k(k_align<CPL, true>, p, p.N, num_sms, max_smem, stream)
+                : launch_k(k_align<CPL, false>, p, p.N, num_sms, max_smem, stream);
+}
+
+int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream)
+{
+    switch (pick_cpl(p.t.m)) {
+    case 1: return launch_cpl<1>(p, wide, num_sms, max_smem_optin, stream);
+    case 2: return launch_cpl<2>(p, wide, num_sms, max_smem_optin, stream);
+    case 4: return launch_cpl<4>(p, wide, num_sms, max_smem_optin, stream);
+    case 6: return launch_cpl<6>(p, wide, num_sms, max_smem_optin, stream);
+    case 7: return launch_cpl<7>(p, wide, num_sms, max_smem_optin, stream);
+    case 10: return launch_cpl<10>(p, wide, num_sms, max_smem_optin, stream);
+    case 12: return launch_cpl<12>(p, wide, num_sms, max_smem_optin, stream);
+    case 15: return launch_cpl<15>(p, wide, num_sms, max_smem_optin, stream);
+    default: return -1001;
+    }
+}
+
+template <int CPL>
+static int set_attr(int max_smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_align<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_align<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) return (int)e;
+    if constexpr (CPL <= 7) e = cudaFuncSetAttribute(k_align2<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    return (int)e;
+}
+
+int configure_align_kernels(int max_smem_optin)
+{
+    int e;
+    if ((e = set_attr<1>(max_smem_optin))) return e;
+    if ((e = set_attr<2>(max_smem_optin))) return e;
+    if ((e = set_attr<4>(max_smem_optin))) return e;
+    if ((e = set_attr<6>(max_smem_optin))) return e;
+    if ((e = set_attr<7>(max_smem_optin))) return e;
+    if ((e = set_attr<10>(max_smem_optin))) return e;
+    if ((e = set_attr<12>(max_smem_optin))) return e;
+    if ((e = set_attr<15>(max_smem_optin))) return e;
+    return 0;
+}
+
+}  // namespace treat_b200

@@ -69,7 +69,8 @@ struct treat_b200_ctx {
     bool have_template = false;
     bool tmpl_wide = false;  // template needs the wide path (non-alphabet base or count >= 255)
     TemplateDev td{};
-    DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut;
+    DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut, scratch;
+    uint32_t band_rows = 0;  // 0 = default window
     std::vector<uint8_t> lut;
     uint64_t *d_summary = nullptr;
     uint32_t bins = 0;
@@ -136,7 +137,8 @@ int treat_b200_create(int device, treat_b200_ctx **out)
         delete ctx;
         return TREAT_B200_ERR_CUDA;
     }
-    int e = configure_kernels(ctx->max_smem);
+    int e = configure_pack_kernels(ctx->max_smem);
+    if (!e) e = configure_align_kernels(ctx->max_smem);
     if (e) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -151,7 +153,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut}) b->release();
+    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->scratch}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
     ctx->slot[0].release();
     ctx->slot[1].release();
@@ -286,6 +288,13 @@ int treat_b200_synchronize(treat_b200_ctx *ctx)
 
 uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows)
+{
+    if (!ctx) return TREAT_B200_ERR_INVALID;
+    ctx->band_rows = rows;
+    return TREAT_B200_OK;
+}
+
 int treat_b200_packed_layout(const treat_b200_ctx *ctx, uint64_t N, uint32_t max_len, uint32_t wide,
                              treat_b200_packed *out)
 {
@@ -360,11 +369,24 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : ctx->d_summary;
     ap.bins = ctx->bins;
     ap.flags = flags;
+    ap.force_single = (flags & TREAT_B200_ONE_READ_PER_WARP) ? 1u : 0u;
+    ap.force_full = (flags & TREAT_B200_FULL_TRACEBACK_STORE) ? 1u : 0u;
+    ap.band_rows = ctx->band_rows;
     if (ap.ops) {
         if (ops_stride % 16 || ops_stride < a16(((uint32_t)ctx->td.m + ncap + 3) / 4))
             return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small or not a multiple of 16");
     }
     if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
+    {
+        // global scratch for reads whose path may leave the band (one region per resident warp)
+        const uint64_t need = align_scratch_bytes(ap, ctx->num_sms, ctx->max_smem);
+        if (need > ctx->scratch.cap) {
+            CK(ctx, cudaStreamSynchronize(st));
+            CK(ctx, cudaDeviceSynchronize());
+            CK(ctx, ctx->scratch.reserve(need));
+        }
+        ap.scratch = ctx->scratch.p;
+    }
     int e = launch_align(ap, wide, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000 || e == -1001)
         return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: read/template geometry exceeds shared memory");

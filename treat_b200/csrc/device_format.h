@@ -63,8 +63,15 @@ struct AlignParams {
     // shared-memory carve-up (bytes, all multiples of 16)
     uint32_t sm_tmpl_bytes;      // CTA-wide template section
     uint32_t sm_warp_bytes;      // per-warp section
-    uint32_t sm_stage_b, sm_stage_c;  // stage buffer sizes (bases, counts)
+    uint32_t sm_stage_b, sm_stage_c;  // one read inside a stage slot (bases, counts)
+    uint32_t sm_stage_total;     // both slots, all reads of a warp
     uint32_t sm_rb, sm_dir, sm_ops, sm_t2f, sm_tbits;
+    uint32_t pair;               // 1: k_align2 (two reads per warp), 0: k_align
+    uint32_t force_single;       // TREAT_B200_ONE_READ_PER_WARP
+    uint32_t force_full;         // TREAT_B200_FULL_TRACEBACK_STORE: always take the global-scratch path
+    uint32_t band_rows;          // W: direction-word rows kept per lane in shared memory
+    void *scratch;               // global scratch for full fills: [CTAs x warps][scratch_stride] words
+    uint32_t scratch_stride;
 };
 
 // launchers (kernels.cu)
@@ -72,7 +79,10 @@ int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin,
 int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
 // fills the shared-memory geometry of p for (m, K, ncap, wide); returns columns-per-lane or -1
 int plan_align(AlignParams &p, bool wide);
+int align_warps(const AlignParams &p, int max_smem);
+uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
 int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream);
-int configure_kernels(int max_smem_optin);
+int configure_pack_kernels(int max_smem_optin);
+int configure_align_kernels(int max_smem_optin);
 
 }  // namespace treat_b200
