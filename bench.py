@@ -356,7 +356,7 @@ def run_ours(args):
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * N * args.steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(len(seqs) + (N + 1) * 8 + N * 4),
-               "d2h_bytes_per_step": int(N * 48 + N * stride + 8),
+               "d2h_bytes_per_step": int(N * 48 + N * (((t.m + max_n + 3) // 4 + 15) // 16 * 16) + 8),
                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "treat_b200_align_batch (pinned host buffers)"}
         assert np.array_equal(h_rec, rec_dev), "host-buffer and device-buffer paths disagree"
 

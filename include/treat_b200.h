@@ -131,7 +131,9 @@ int treat_b200_use_template(treat_b200_ctx *ctx, const treat_b200_template *tmpl
  * seqs/seq_off: concatenated raw reads (any case), read i = seqs[seq_off[i] .. seq_off[i+1]);
  * read_count: Fragment.ReadCount per read (treat_b200_parse_merge_count) or NULL for 1;
  * rec: N records, caller owned; ops (may be NULL): ops_stride bytes per read, see
- * treat_b200_ops_stride; results are in input order. */
+ * treat_b200_ops_stride; results are in input order.  Of every ops row only the leading
+ * align16(ceil((m + max n of the chunk) / 4)) bytes are written (zero past the alignment); pass a
+ * zeroed buffer if the tail of the rows is to be compared. */
 int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off,
                            const uint32_t *read_count, uint64_t N, uint32_t flags, treat_b200_record *rec,
                            uint8_t *ops, uint32_t ops_stride);

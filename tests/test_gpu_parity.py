@@ -295,6 +295,45 @@ def test_device_resident_entry_point(eng, tmp_path):
     assert np.array_equal(d_ops.cpu().numpy().reshape(N, stride), hops)
 
 
+def test_speculative_chunks_are_validated(eng, tmp_path):
+    """Multi-chunk host batches launch the align kernel without waiting for the pack kernel's max n.
+    Chunks whose reads turn out longer than the guess, or hold a saturated edit-base run, must be
+    re-run: results and summaries stay exact."""
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 300_000
+    seqs, off, rc = synth.reads(t, N, seed=synth.SEED_BASE + 91)
+    raw = t.raw_sequences()[0]
+    special = {140_000: raw[:200] + "ACGGCA" * 9 + raw[200:],      # n = 163 + 54: longer than any earlier read
+               280_000: raw[:50] + "T" * 300 + raw[50:],            # saturated run (>= 255)
+               299_999: "ACG" * 150}
+    parts, lens, prev = [], np.diff(off.astype(np.int64)).copy(), 0
+    for idx in sorted(special):
+        parts.append(seqs[int(off[prev]):int(off[idx])])
+        parts.append(np.frombuffer(special[idx].encode(), dtype=np.uint8))
+        lens[idx] = len(special[idx])
+        prev = idx + 1
+    parts.append(seqs[int(off[prev]):int(off[N])])
+    seqs2 = np.concatenate(parts)
+    off2 = np.zeros(N + 1, dtype=np.uint64)
+    off2[1:] = np.cumsum(lens)
+    eng.reset_summary()
+    rec, ops = eng.align_batch(seqs2, off2, rc, cabi.WANT_OPS)
+    summ = eng.summary()
+    idx = np.unique(np.concatenate([np.arange(0, N, 37), np.array(sorted(special)), np.arange(139_990, 140_010)]))
+    sub = np.concatenate([seqs2[int(off2[i]):int(off2[i + 1])] for i in idx])
+    sub_off = np.zeros(len(idx) + 1, dtype=np.uint64)
+    sub_off[1:] = np.cumsum(lens[idx])
+    orec, oops, _ = O.align_batch(om, sub, sub_off, rc[idx], nthreads=8, ops_stride=ops.shape[1])
+    assert compare_records(rec[idx], orec) == []
+    assert np.array_equal(ops[idx], oops)
+    assert rec[280_000]["status"] & cabi.ST_SATURATED
+    assert np.array_equal(summ, summary_from_records(rec, t.m, 0, om.EditStop))
+    rec2, ops2 = eng.align_batch(seqs2, off2, rc, cabi.WANT_OPS)   # second call: hint already large
+    assert np.array_equal(rec, rec2) and np.array_equal(ops, ops2)
+
+
 def test_full_size_properties(eng, tmp_path):
     """Config 3 at full size (1M RPS12 reads): size-independent properties on every read, oracle
     parity on a stride sample, determinism across two runs and across batch splits."""

@@ -329,16 +329,18 @@ class Aligner:
     def align_batch(self, seqs: np.ndarray, seq_off: np.ndarray, read_count: Optional[np.ndarray] = None,
                     flags: int = WANT_OPS, rec: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None):
         """treat_b200_align_batch on host buffers; returns (records, ops or None)."""
-        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
-        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        if not (isinstance(seqs, np.ndarray) and seqs.dtype == np.uint8 and seqs.flags.c_contiguous):
+            seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        if not (isinstance(seq_off, np.ndarray) and seq_off.dtype == np.uint64 and seq_off.flags.c_contiguous):
+            seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         N = len(seq_off) - 1
         if rec is None:
             rec = np.zeros(N, dtype=RECORD_DTYPE)
         stride = 0
         if flags & WANT_OPS:
-            max_len = int(np.diff(seq_off.astype(np.int64)).max()) if N else 0
-            stride = self.ops_stride(max_len)
             if ops is None:
+                max_len = int((seq_off[1:] - seq_off[:-1]).max()) if N else 0
+                stride = self.ops_stride(max_len)
                 ops = np.zeros((N, stride), dtype=np.uint8)
             else:
                 stride = ops.shape[1]

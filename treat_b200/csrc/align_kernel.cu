@@ -17,12 +17,14 @@
 // A row with w = 0 leaves the previous row unchanged, so idle wavefront steps need no branch.
 //
 // Direction storage.  Per lane and step ONE word: the CPL horizontal differences as base-4 digits
-// (built with IMADs: sum_k (f_k - f_{k-1}) 4^k = 4^CPL f_last - 3 sum_k f_k 4^k - left) plus
-// (left boundary value mod 4) on top.  From two such words (rows j and j-1) the traceback recovers
-// G mod 4 of any cell, hence both pointer tests; it walks 32 cells of a diagonal run per iteration.
+// (built with IMADs: sum_k (f_k - f_{k-1}) 4^k = 4^CPL f_last - 3 sum_k f_k 4^k - left) plus the
+// vertical difference of the lane's left boundary cell on top.  From two such words (rows j, j-1) the
+// traceback gets dH of the cell and dV = dV(boundary) + sum of (dH_j - dH_{j-1}) over the lane's
+// columns up to the cell, hence both pointer tests; it walks 32 cells of a diagonal run per iteration.
 //
-// Band.  Only words whose cells lie within B diagonals of the main diagonal are kept (a window of
-// W = 2B + CPL + 1 steps per lane in shared memory).  Any optimal path with D deletions, I insertions
+// Band.  Only words whose cells lie within B diagonals of the main diagonal are kept: the fill runs
+// in chunks of P = CPL+1 steps and lane l keeps chunk u iff |u - l| <= C (a window of (2C+1) P rows
+// per lane in shared memory, B = C P - 1).  Any optimal path with D deletions, I insertions
 // and X mismatches has 2D + I + 2X = m - S and D + 2I + 2X = n - S (S = F[m][n]), so it stays inside
 // the band whenever (m - S)/2 <= B and (n - S)/2 <= B; the warp checks this after the fill and
 // otherwise repeats the fill with every word written to an L2-resident global scratch.  Exact either
@@ -44,6 +46,7 @@
 namespace treat_b200 {
 
 constexpr int kPadCode = 4;  // profile row with w = 0: a no-op row of the wavefront
+constexpr int kMaxWarpsPair = 32, kMaxWarpsOne = 16;  // resident warps per SM the register budget allows
 
 // ------------------------------------------------------------------------------------------
 // direction words
@@ -51,7 +54,7 @@ constexpr int kPadCode = 4;  // profile row with w = 0: a no-op row of the wavef
 template <int CPL>
 struct Dir {
     using word_t = typename std::conditional<(CPL <= 7), uint16_t, uint32_t>::type;
-    static constexpr int kTop = (CPL <= 7) ? 14 : 30;                     // bit position of (left & 3)
+    static constexpr int kTop = (CPL <= 7) ? 14 : 30;                     // bit position of dV(left boundary)
     static constexpr uint32_t kOdd = (CPL <= 7) ? 0x1555u : 0x15555555u;  // low bits of the digits
     static_assert(CPL <= 15, "direction word holds at most 15 base-4 digits");
 };
@@ -251,14 +254,11 @@ __device__ __forceinline__ int traceback(GetW getw, uint32_t *ops2, int m, int n
             if (a == 0) {
                 is_up = true;  // G[i][j] == G[i-1][j]
             } else {
+                // dV(i,j) = dV(left boundary of the lane, row j) + sum_{columns <= k} (dH(row j) - dH(row j-1))
                 const uint32_t msk = (4u << (2 * k)) - 1u;
-                const uint32_t g1 = (w1 >> DT::kTop) + digit_sum(w1 & msk, DT::kOdd);
-                uint32_t g0 = 0;  // G[i][0] = 0
-                if (jj >= 2) {
-                    const uint32_t w0 = getw(tt - 1, ln);
-                    g0 = (w0 >> DT::kTop) + digit_sum(w0 & msk, DT::kOdd);
-                }
-                stop = ((g1 - g0) & 3u) == 0;  // G[i][j] == G[i][j-1]: Left
+                uint32_t v = (w1 >> DT::kTop) + digit_sum(w1 & msk, DT::kOdd);
+                if (jj >= 2) v -= digit_sum(getw(tt - 1, ln) & msk, DT::kOdd);  // row 0 is all zero
+                stop = (v & 3u) == 0;  // G[i][j] == G[i][j-1]: Left
             }
         }
         const uint32_t sm = __ballot_sync(FULL_MASK, stop);
@@ -497,10 +497,10 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
 // ------------------------------------------------------------------------------------------
 template <int CPL, bool WIDE, bool FULL, typename dir_t>
 __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rbl, const int (&tcr)[CPL], int n, int steps,
-                                         int lane, int (&H)[CPL], dir_t *out, int tlo, int W)
+                                         int lane, int (&H)[CPL], dir_t *out, int C)
 {
     using DT = Dir<CPL>;
-    constexpr int ROWS = 5;
+    constexpr int ROWS = 5, P = CPL + 1;
 #pragma unroll
     for (int k = 0; k < CPL; k++) H[k] = 0;  // G[i][0] = 0
     int diag = 0;                            // G[i0-1][j-1]
@@ -510,42 +510,47 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
         Prof<CPL>::load(prof, ROWS, rbl[0], lane, pwc);
         cnext = rbl[1];
     }
-    dir_t *o = out + lane - (FULL ? 0 : tlo * 32);
-#pragma unroll 2
-    for (int t = 0; t < steps; t++) {
-        uint32_t pwn[CPL];
-        int wv[CPL];
-        if (!WIDE) {
-            Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
-            cnext = rbl[t + 2];
+    const int nchunks = (steps + P - 1) / P;
+    for (int u = 0; u < nchunks; u++) {
+        const bool keep = FULL || (unsigned)(u - lane + C) <= (unsigned)(2 * C);
+        dir_t *orow = out + (FULL ? u * P : (u - lane + C) * P) * 32 + lane;
+        const uint8_t *rbu = rbl + u * P;
 #pragma unroll
-            for (int k = 0; k < CPL; k++) wv[k] = (int)pwc[k];
-        } else {
-            const int idx = t - lane;
-            const bool live = idx >= 0 && idx < n;
-            const int rc = live ? (int)rbl[t] : 0x200;
+        for (int v = 0; v < P; v++) {
+            uint32_t pwn[CPL];
+            int wv[CPL];
+            if (!WIDE) {
+                Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
+                cnext = rbu[v + 2];
 #pragma unroll
-            for (int k = 0; k < CPL; k++) wv[k] = live ? (rc == tcr[k] ? 3 : 1) : 0;
-        }
-        const int recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
-        const int left = lane == 0 ? 0 : recv;  // G[i0-1][j]
-        int dg = diag, lf = left;
-        uint32_t S = 0;
+                for (int k = 0; k < CPL; k++) wv[k] = (int)pwc[k];
+            } else {
+                const int idx = u * P + v - lane;
+                const bool live = idx >= 0 && idx < n;
+                const int rc = live ? (int)rbu[v] : 0x200;
 #pragma unroll
-        for (int k = 0; k < CPL; k++) {
-            const int e = max(dg + wv[k], H[k]);
-            const int f = max(e, lf);
-            dg = H[k];
-            lf = f;
-            H[k] = f;
-            S += (uint32_t)f << (2 * k);
-        }
-        diag = left;
-        const uint32_t word = ((uint32_t)lf << (2 * CPL)) - 3u * S - (uint32_t)left + (((uint32_t)left & 3u) << DT::kTop);
-        if (FULL || (unsigned)(t - tlo) < (unsigned)W) o[t * 32] = (dir_t)word;
-        if (!WIDE) {
+                for (int k = 0; k < CPL; k++) wv[k] = live ? (rc == tcr[k] ? 3 : 1) : 0;
+            }
+            const int recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
+            const int left = lane == 0 ? 0 : recv;  // G[i0-1][j]
+            int dg = diag, lf = left;
+            uint32_t S = 0;
 #pragma unroll
-            for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
+            for (int k = 0; k < CPL; k++) {
+                const int e = max(dg + wv[k], H[k]);
+                const int f = max(e, lf);
+                dg = H[k];
+                lf = f;
+                H[k] = f;
+                S += (uint32_t)f << (2 * k);
+            }
+            const uint32_t word = ((uint32_t)lf << (2 * CPL)) - 3u * S - (uint32_t)left + ((uint32_t)(left - diag) << DT::kTop);
+            diag = left;
+            if (keep) orow[v * 32] = (dir_t)word;
+            if (!WIDE) {
+#pragma unroll
+                for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
+            }
         }
     }
     __syncwarp();
@@ -553,46 +558,51 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
 
 template <int CPL, bool FULL>
 __device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pcl, int steps, int lane, uint32_t (&H)[CPL],
-                                         uint32_t *out, int tlo, int W)
+                                         uint32_t *out, int C)
 {
     using DT = Dir<CPL>;
-    constexpr int ROWS = 25;
+    constexpr int ROWS = 25, P = CPL + 1;
 #pragma unroll
     for (int k = 0; k < CPL; k++) H[k] = 0u;
     uint32_t diag = 0u;
     uint32_t pwc[CPL];
     Prof<CPL>::load(prof, ROWS, pcl[0], lane, pwc);
     int cnext = pcl[1];
-    uint32_t *o = out + lane - (FULL ? 0 : tlo * 32);
-#pragma unroll 2
-    for (int t = 0; t < steps; t++) {
-        uint32_t pwn[CPL];
-        Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
-        cnext = pcl[t + 2];
-        const uint32_t recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
-        const uint32_t left = lane == 0 ? 0u : recv;
-        uint32_t dg = diag, lf = left, S = 0;
+    const int nchunks = (steps + P - 1) / P;
+    for (int u = 0; u < nchunks; u++) {
+        const bool keep = FULL || (unsigned)(u - lane + C) <= (unsigned)(2 * C);
+        uint32_t *orow = out + (FULL ? u * P : (u - lane + C) * P) * 32 + lane;
+        const uint8_t *pcu = pcl + u * P;
 #pragma unroll
-        for (int k = 0; k < CPL; k++) {
-            const uint32_t e = __viaddmax_s16x2(dg, pwc[k], H[k]);
-            const uint32_t f = __vmaxs2(e, lf);
-            dg = H[k];
-            lf = f;
-            H[k] = f;
-            S += f << (2 * k);
+        for (int v = 0; v < P; v++) {
+            uint32_t pwn[CPL];
+            Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
+            cnext = pcu[v + 2];
+            const uint32_t recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
+            const uint32_t left = lane == 0 ? 0u : recv;
+            uint32_t dg = diag, lf = left, S = 0;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                const uint32_t e = __viaddmax_s16x2(dg, pwc[k], H[k]);
+                const uint32_t f = __vmaxs2(e, lf);
+                dg = H[k];
+                lf = f;
+                H[k] = f;
+                S += f << (2 * k);
+            }
+            // both halves at once: arithmetic mod 2^32 keeps each 16-bit word exact (no borrow: left >= diag per half)
+            const uint32_t word = (lf << (2 * CPL)) - 3u * S - left + ((left - diag) << DT::kTop);
+            diag = left;
+            if (keep) orow[v * 32] = word;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
         }
-        diag = left;
-        // both halves at once: arithmetic mod 2^32 keeps each 16-bit digit word exact
-        const uint32_t word = (lf << (2 * CPL)) - 3u * S - left + ((left & 0x00030003u) << DT::kTop);
-        if (FULL || (unsigned)(t - tlo) < (unsigned)W) o[t * 32] = word;
-#pragma unroll
-        for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
     }
     __syncwarp();
 }
 
 // the optimal path stays within B diagonals of the main one (see the header comment)
-__device__ __forceinline__ bool band_ok(int m, int n, int score, int B) { return m - score <= 2 * B && n - score <= 2 * B; }
+__device__ __forceinline__ bool band_ok(int m, int n, int score, int B) { return B >= 0 && m - score <= 2 * B && n - score <= 2 * B; }
 
 __device__ __forceinline__ void flush_summary(const AlignParams &p, uint32_t sum_len, const uint32_t *lo, const uint32_t *hi,
                                               int lane, unsigned long long ctr)
@@ -649,8 +659,8 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
     }
     const int lanes_used = (m + CPL - 1) / CPL;
     const int ops_words = (int)(p.sm_ops / 4);
-    const int W = (int)p.band_rows, B = (W - CPL - 1) / 2;
-    const int tlo = lane * (CPL + 1) - B - 1;
+    constexpr int P = CPL + 1;
+    const int C = (int)p.band_chunks, B = C * P - 1;  // B < 0: nothing is certified, every read takes the full path
     const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
     dir_t *scratch = reinterpret_cast<dir_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
     unsigned long long ctr = 0;
@@ -678,7 +688,10 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
         __syncwarp();
         if (r + nw < p.N) issue(r + nw, slot ^ 1);  // prefetch the next read of this warp
         mbar_wait(&ws.bar[slot], parity);
-        if (n > (int)p.ncap) continue;  // cannot happen when ncap comes from K1's max; keeps the launch safe
+        if (n > (int)p.ncap) {  // only on a speculative launch (ncap guessed): the host re-runs the chunk
+            if (lane == 0 && p.skipped) atomicAdd(p.skipped, 1u);
+            continue;
+        }
 
         const uint8_t *st_b = ws.stage + slot * stage_bytes;
         const cnt_t *rcount = reinterpret_cast<const cnt_t *>(st_b + p.sm_stage_b);
@@ -700,6 +713,7 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
             __syncwarp();
             rb[n + lane] = kPadCode;
             rb[n + 32 + lane] = kPadCode;
+            if (lane < 16) rb[n + 64 + lane] = kPadCode;
         } else {
             for (int i = lane; i < n; i += 32) rb[i] = st_b[i];
         }
@@ -710,7 +724,7 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
         int H[CPL];
         const int steps = n > 0 ? n + lanes_used - 1 : 0;
         const uint8_t *rbl = rb - lane;  // rbl[t] = read base of this lane's row at step t
-        fill_one<CPL, WIDE, false>(cs.prof, rbl, tcr, n, steps, lane, H, s_dir, tlo, W);
+        fill_one<CPL, WIDE, false>(cs.prof, rbl, tcr, n, steps, lane, H, s_dir, C);
         auto final_score = [&]() {
             // F[m][n] = G[m][n] - m - n; G[m][n] lives in lane (m-1)/CPL, column (m-1)%CPL
             int fin = 0;
@@ -723,11 +737,11 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
         const int score = final_score();
         int ngaps, pos;
         if (band_ok(m, n, score, B) && !p.force_full) {
-            pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)s_dir[(tt - (ln * (CPL + 1) - B - 1)) * 32 + ln]; },
+            pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)s_dir[(tt - (ln - C) * P) * 32 + ln]; },
                                  ws.ops2, m, n, lane, ngaps);
         } else {
             // the path may leave the band: repeat the fill with every word kept (global scratch, L2)
-            fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, 0, 0);
+            fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, 0);
             pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)scratch[tt * 32 + ln]; }, ws.ops2, m, n, lane, ngaps);
         }
         finish_read<cnt_t>(p, cs, ws, lane, r, n, rflags, score, pos, ngaps, rcount, [&](int fi) { return (int)rb[fi]; }, ctr);
@@ -739,7 +753,7 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
 // K2b: TWO reads per warp in the 16-bit halves of every register (packed alphabet, CPL <= 7)
 // ------------------------------------------------------------------------------------------
 template <int CPL>
-__global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ AlignParams p)
+__global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_constant__ AlignParams p)
 {
     static_assert(CPL <= 7, "two 16-bit direction words per 32-bit store");
     using cnt_t = uint8_t;
@@ -770,8 +784,8 @@ __global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ Align
 
     const int lanes_used = (m + CPL - 1) / CPL;
     const int ops_words = (int)(p.sm_ops / 4);
-    const int W = (int)p.band_rows, B = (W - CPL - 1) / 2;
-    const int tlo = lane * (CPL + 1) - B - 1;
+    constexpr int P = CPL + 1;
+    const int C = (int)p.band_chunks, B = C * P - 1;
     const uint64_t npairs = (p.N + 1) / 2;
     const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
     uint32_t *scratch = reinterpret_cast<uint32_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
@@ -806,7 +820,10 @@ __global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ Align
         __syncwarp();
         if (q + nw < npairs) issue(q + nw, slot ^ 1);  // prefetch the next pair of this warp
         mbar_wait(&ws.bar[slot], parity);
-        if (n0 > (int)p.ncap || n1 > (int)p.ncap) continue;  // cannot happen (ncap = K1's max n)
+        if (n0 > (int)p.ncap || n1 > (int)p.ncap) {  // only on a speculative launch: the host re-runs the chunk
+            if (lane == 0 && p.skipped) atomicAdd(p.skipped, 1u);
+            continue;
+        }
 
         const uint8_t *st0 = ws.stage + slot * slot_bytes, *st1 = st0 + read_bytes;
         const int nmax = max(n0, n1);
@@ -815,7 +832,7 @@ __global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ Align
         uint8_t *pc = ws.rb + 32;
         {
             const uint32_t *pw0 = reinterpret_cast<const uint32_t *>(st0), *pw1 = reinterpret_cast<const uint32_t *>(st1);
-            for (int j = lane; j < nmax + 64; j += 32) {
+            for (int j = lane; j < nmax + 80; j += 32) {
                 const int c0 = j < n0 ? (int)((pw0[j >> 4] >> (2 * (j & 15))) & 3u) : kPadCode;
                 const int c1 = j < n1 ? (int)((pw1[j >> 4] >> (2 * (j & 15))) & 3u) : kPadCode;
                 pc[j] = (uint8_t)(c0 * 5 + c1);
@@ -827,7 +844,7 @@ __global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ Align
         uint32_t H[CPL];
         const int steps = nmax > 0 ? nmax + lanes_used - 1 : 0;
         const uint8_t *pcl = pc - lane;
-        fill_two<CPL, false>(cs.prof, pcl, steps, lane, H, s_dir, tlo, W);
+        fill_two<CPL, false>(cs.prof, pcl, steps, lane, H, s_dir, C);
         uint32_t fin = 0;
         {
             const int kl = (m - 1) % CPL;
@@ -838,7 +855,7 @@ __global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ Align
         }
         const int score0 = (int)(fin & 0xffffu) - m - n0, score1 = (int)(fin >> 16) - m - n1;
         const bool banded = band_ok(m, n0, score0, B) && (!has1 || band_ok(m, n1, score1, B)) && !p.force_full;
-        if (!banded) fill_two<CPL, true>(cs.prof, pcl, steps, lane, H, scratch, 0, 0);  // keep every word (global scratch)
+        if (!banded) fill_two<CPL, true>(cs.prof, pcl, steps, lane, H, scratch, 0);  // keep every word (global scratch)
 
         // ---- per read: traceback + editing-site assembly ---------------------------------------
         for (int h = 0; h < (has1 ? 2 : 1); h++) {
@@ -850,7 +867,7 @@ __global__ void __launch_bounds__(512, 1) k_align2(const __grid_constant__ Align
             int ngaps, pos;
             const int sh = 16 * h;
             if (banded)
-                pos = traceback<CPL>([&](int tt, int ln) { return (s_dir[(tt - (ln * (CPL + 1) - B - 1)) * 32 + ln] >> sh) & 0xffffu; },
+                pos = traceback<CPL>([&](int tt, int ln) { return (s_dir[(tt - (ln - C) * P) * 32 + ln] >> sh) & 0xffffu; },
                                      ws.ops2, m, n, lane, ngaps);
             else
                 pos = traceback<CPL>([&](int tt, int ln) { return (scratch[tt * 32 + ln] >> sh) & 0xffffu; }, ws.ops2, m, n, lane, ngaps);
@@ -903,14 +920,16 @@ int plan_align(AlignParams &p, bool wide)
     if (p.sm_stage_b == 0) p.sm_stage_b = 16;
     p.sm_stage_c = wide ? align16(4 * (ncap + 1)) : align16(ncap + 1);
     p.sm_stage_total = 2 * (pair ? 2 : 1) * (p.sm_stage_b + p.sm_stage_c);
-    p.sm_rb = align16(32 + ncap + 64 + 16);
-    // band window: never more rows than the fill has steps
-    const uint32_t full_rows = ncap + 32;
-    uint32_t rows = p.band_rows ? p.band_rows : 64u;
-    if (rows < (uint32_t)cpl + 3) rows = (uint32_t)cpl + 3;
-    if (rows > full_rows) rows = full_rows;
-    p.band_rows = rows;
-    p.sm_dir = align16(rows * 32 * dsz);
+    p.sm_rb = align16(32 + ncap + 80 + 16);
+    // band window: (2C+1) chunks of P = cpl+1 rows per lane; the fill pads its steps to whole chunks
+    const uint32_t P = (uint32_t)cpl + 1;
+    const uint32_t full_rows = ncap + 48;
+    const uint32_t want = p.band_rows ? p.band_rows : (pair ? 35u : 64u);
+    uint32_t C = want / P >= 1 ? (want / P - 1) / 2 : 0;
+    while (C > 0 && (2 * C + 1) * P > full_rows) C--;
+    p.band_chunks = C;
+    p.band_rows = (2 * C + 1) * P;
+    p.sm_dir = align16(p.band_rows * 32 * dsz);
     p.scratch_stride = full_rows * 32;  // direction words of one warp's full fill
     p.sm_ops = align16((((uint32_t)m + ncap + 15) / 16 + 2) * 4);
     p.sm_t2f = align16(2u * (uint32_t)p.t.len_pad);
@@ -924,7 +943,8 @@ int plan_align(AlignParams &p, bool wide)
 int align_warps(const AlignParams &p, int max_smem)
 {
     long warps = ((long)max_smem - (long)p.sm_tmpl_bytes) / (long)p.sm_warp_bytes;
-    if (warps > 16) warps = 16;
+    const long cap = p.pair ? kMaxWarpsPair : kMaxWarpsOne;
+    if (warps > cap) warps = cap;
     return warps < 1 ? 0 : (int)warps;
 }
 
@@ -983,6 +1003,24 @@ static int set_attr(int max_smem)
     if (e != cudaSuccess) return (int)e;
     if constexpr (CPL <= 7) e = cudaFuncSetAttribute(k_align2<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     return (int)e;
+}
+
+__global__ void k_merge_summary(unsigned long long *dst, unsigned long long *src, uint32_t len)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+        const unsigned long long v = src[i];
+        if (v) {
+            atomicAdd(&dst[i], v);
+            src[i] = 0ull;
+        }
+    }
+}
+
+int launch_merge_summary(uint64_t *dst, uint64_t *src, uint32_t len, void *stream)
+{
+    k_merge_summary<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(dst),
+                                                         reinterpret_cast<unsigned long long *>(src), len);
+    return (int)cudaGetLastError();
 }
 
 int configure_align_kernels(int max_smem_optin)

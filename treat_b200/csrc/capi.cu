@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,7 +19,8 @@ using namespace treat_b200;
 namespace {
 
 constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
-constexpr uint64_t kChunkReads = 1u << 18;  // reads per pipelined chunk of treat_b200_align_batch
+constexpr uint64_t kChunkReads = 1u << 17;  // reads per pipelined chunk of treat_b200_align_batch
+constexpr int kSlots = 3;                   // chunks in flight: H2D, kernels and D2H of different chunks overlap
 
 struct DevBuf {
     void *p = nullptr;
@@ -44,12 +47,16 @@ struct DevBuf {
 // device buffers of one in-flight chunk
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops;
-    uint32_t *scalars = nullptr;  // device [2]
-    uint32_t *h_scalars = nullptr;  // pinned [2]
+    DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops, summary;
+    uint32_t *scalars = nullptr;    // device [4]: max n, any saturated run, reads skipped by a speculative launch
+    uint32_t *h_scalars = nullptr;  // pinned [4]
+    // chunk whose speculative launch still has to be validated (treat_b200_align_batch)
+    bool pending = false;
+    uint64_t c0 = 0, cn = 0, b0 = 0;
+    uint32_t max_len = 0, dev_stride = 0;
     void release()
     {
-        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops}) b->release();
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary}) b->release();
         if (scalars) cudaFree(scalars);
         if (h_scalars) cudaFreeHost(h_scalars);
         if (stream) cudaStreamDestroy(stream);
@@ -71,10 +78,11 @@ struct treat_b200_ctx {
     TemplateDev td{};
     DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut, scratch;
     uint32_t band_rows = 0;  // 0 = default window
+    uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
     std::vector<uint8_t> lut;
     uint64_t *d_summary = nullptr;
     uint32_t bins = 0;
-    Slot slot[2];
+    Slot slot[kSlots];
     // scratch for the device-resident entry point
     Slot dev_slot;
 };
@@ -155,8 +163,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->scratch}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
-    ctx->slot[0].release();
-    ctx->slot[1].release();
+    for (Slot &sl : ctx->slot) sl.release();
     ctx->dev_slot.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -251,6 +258,7 @@ int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m
     CK(ctx, cudaMalloc((void **)&ctx->d_summary, sl));
     CK(ctx, cudaMemset(ctx->d_summary, 0, sl));
     ctx->have_template = true;
+    ctx->ncap_hint = 0;
     return TREAT_B200_OK;
 }
 
@@ -281,8 +289,9 @@ int treat_b200_synchronize(treat_b200_ctx *ctx)
     if (!ctx) return TREAT_B200_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    for (Slot *s : {&ctx->slot[0], &ctx->slot[1], &ctx->dev_slot})
-        if (s->stream) CK(ctx, cudaStreamSynchronize(s->stream));
+    for (Slot &sl : ctx->slot)
+        if (sl.stream) CK(ctx, cudaStreamSynchronize(sl.stream));
+    if (ctx->dev_slot.stream) CK(ctx, cudaStreamSynchronize(ctx->dev_slot.stream));
     return TREAT_B200_OK;
 }
 
@@ -311,8 +320,8 @@ int treat_b200_packed_layout(const treat_b200_ctx *ctx, uint64_t N, uint32_t max
 
 static int ensure_scalars(treat_b200_ctx *ctx, Slot &s)
 {
-    if (!s.scalars) CK(ctx, cudaMalloc((void **)&s.scalars, 8));
-    if (!s.h_scalars) CK(ctx, cudaMallocHost((void **)&s.h_scalars, 8));
+    if (!s.scalars) CK(ctx, cudaMalloc((void **)&s.scalars, 16));
+    if (!s.h_scalars) CK(ctx, cudaMallocHost((void **)&s.h_scalars, 16));
     return TREAT_B200_OK;
 }
 
@@ -343,7 +352,8 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
 }
 
 static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t ncap, const uint32_t *d_read_count,
-                    uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st)
+                    uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st,
+                    uint64_t *summary_override = nullptr, uint32_t *d_skipped = nullptr)
 {
     if (src->N == 0) return TREAT_B200_OK;
     const bool wide = src->wide != 0;
@@ -366,7 +376,8 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     ap.rec = d_rec;
     ap.ops = (flags & TREAT_B200_WANT_OPS) ? d_ops : nullptr;
     ap.ops_stride = ops_stride;
-    ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : ctx->d_summary;
+    ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : (summary_override ? summary_override : ctx->d_summary);
+    ap.skipped = d_skipped;
     ap.bins = ctx->bins;
     ap.flags = flags;
     ap.force_single = (flags & TREAT_B200_ONE_READ_PER_WARP) ? 1u : 0u;
@@ -409,7 +420,7 @@ int treat_b200_pack_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     int rc = ensure_scalars(ctx, ctx->dev_slot);
     if (rc) return rc;
-    CK(ctx, cudaMemsetAsync(ctx->dev_slot.scalars, 0, 8, st));
+    CK(ctx, cudaMemsetAsync(ctx->dev_slot.scalars, 0, 16, st));
     return do_pack(ctx, d_seqs, d_seq_off, 0, dst, ctx->dev_slot.scalars, st);
 }
 
@@ -428,9 +439,14 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
 }
 
 // pack + (tiny sync for max n) + align on one slot's buffers
+// ops_stride == 0: the ops go to the slot's own buffer with the tightest legal stride (returned in
+// *ops_stride_used), so that the host copy moves only what the batch needs.
+// spec_ncap != 0: speculative, sync-free variant: the align kernel is sized for spec_ncap, accumulates
+// into the slot's private summary and counts what it could not hold; the caller validates later.
 static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
                      const uint32_t *d_rc, uint64_t N, uint32_t max_len, uint32_t flags, treat_b200_record *d_rec,
-                     uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st, bool force_wide, bool *saturated)
+                     uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st, bool force_wide, bool *saturated,
+                     uint32_t *ops_stride_used = nullptr, uint32_t spec_ncap = 0)
 {
     const bool wide = ctx->tmpl_wide || force_wide;
     treat_b200_packed pk;
@@ -448,14 +464,43 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     pk.d_raw_len = (uint32_t *)s.raw_len.p;
     rc = ensure_scalars(ctx, s);
     if (rc) return rc;
-    CK(ctx, cudaMemsetAsync(s.scalars, 0, 8, st));
+    CK(ctx, cudaMemsetAsync(s.scalars, 0, 16, st));
     rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st);
     if (rc) return rc;
+    if (spec_ncap) {
+        const uint32_t ncap = std::min(spec_ncap, max_len);
+        if ((flags & TREAT_B200_WANT_OPS) && ops_stride == 0) {
+            ops_stride = a16(((uint32_t)ctx->td.m + ncap + 3) / 4);
+            CK(ctx, s.ops.reserve(N * (size_t)ops_stride));
+            d_ops = (uint8_t *)s.ops.p;
+        }
+        if (ops_stride_used) *ops_stride_used = ops_stride;
+        uint64_t *slot_sum = nullptr;
+        if (!(flags & TREAT_B200_NO_SUMMARY)) {
+            const size_t sl = treat_b200_summary_len(ctx) * 8;
+            if (s.summary.cap < sl) {
+                CK(ctx, s.summary.reserve(sl));
+                CK(ctx, cudaMemsetAsync(s.summary.p, 0, sl, st));
+            }
+            slot_sum = (uint64_t *)s.summary.p;
+        }
+        rc = do_align(ctx, &pk, ncap, d_rc, flags, d_rec, d_ops, ops_stride, st, slot_sum, s.scalars + 2);
+        if (rc) return rc;
+        CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, 16, cudaMemcpyDeviceToHost, st));
+        return TREAT_B200_OK;
+    }
     CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, 8, cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));  // 8 bytes: max n sizes the align kernel's shared memory
     const uint32_t max_n = s.h_scalars[0];
+    ctx->ncap_hint = std::max(ctx->ncap_hint, max_n);
     if (saturated) *saturated = s.h_scalars[1] != 0;
     if (!wide && s.h_scalars[1]) return TREAT_B200_OK;  // caller re-runs this chunk on the wide path
+    if ((flags & TREAT_B200_WANT_OPS) && ops_stride == 0) {
+        ops_stride = a16(((uint32_t)ctx->td.m + max_n + 3) / 4);
+        CK(ctx, s.ops.reserve(N * (size_t)ops_stride));
+        d_ops = (uint8_t *)s.ops.p;
+    }
+    if (ops_stride_used) *ops_stride_used = ops_stride;
     return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st);
 }
 
@@ -489,16 +534,71 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     if (N == 0) return TREAT_B200_OK;
     CK(ctx, cudaSetDevice(ctx->device));
     const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < kSlots; i++)
         if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
 
     int rc = TREAT_B200_OK;
     uint64_t chunk_idx = 0;
+    static const bool trace = getenv("TREAT_B200_TRACE") != nullptr;
+    static const bool no_spec = getenv("TREAT_B200_NO_SPECULATION") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_wait_slot = 0, t_enqueue = 0;
+    int redone = 0;
+
+    // copy a finished chunk's results to the caller's buffers (async on the slot stream)
+    auto copy_out = [&](Slot &s) -> int {
+        CK(ctx, cudaMemcpyAsync(rec + s.c0, s.rec.p, s.cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, s.stream));
+        // only the bytes the batch can use cross the bus: rows of dev_stride <= ops_stride bytes
+        if (want_ops)
+            CK(ctx, cudaMemcpy2DAsync(ops + s.c0 * (size_t)ops_stride, ops_stride, s.ops.p, s.dev_stride, s.dev_stride, s.cn,
+                                      cudaMemcpyDeviceToHost, s.stream));
+        return TREAT_B200_OK;
+    };
+    // pack + align with the exact max n (one 8-byte sync), wide re-run if an edit-base run saturated
+    auto run_exact = [&](Slot &s) -> int {
+        const uint32_t *d_rc = read_count ? (const uint32_t *)s.rc.p : nullptr;
+        bool sat = false;
+        int r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, flags,
+                          (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, false, &sat, &s.dev_stride);
+        if (r == TREAT_B200_OK && sat && !ctx->tmpl_wide)
+            r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, flags,
+                          (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, true, nullptr, &s.dev_stride);
+        return r;
+    };
+    // a speculative chunk is final once its stream is idle and nothing was skipped or saturated
+    auto settle = [&](Slot &s) -> int {
+        if (!s.pending) return TREAT_B200_OK;
+        s.pending = false;
+        CK(ctx, cudaStreamSynchronize(s.stream));
+        const uint32_t max_n = s.h_scalars[0], sat = s.h_scalars[1], skipped = s.h_scalars[2];
+        ctx->ncap_hint = std::max(ctx->ncap_hint, max_n);
+        const bool bad = skipped != 0 || (sat && !ctx->tmpl_wide);
+        if (!bad) {
+            if (!(flags & TREAT_B200_NO_SUMMARY)) {
+                int e = launch_merge_summary(ctx->d_summary, (uint64_t *)s.summary.p, (uint32_t)treat_b200_summary_len(ctx), s.stream);
+                if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_merge_summary launch failed");
+                ctx->launches++;
+            }
+            return TREAT_B200_OK;
+        }
+        redone++;
+        if (!(flags & TREAT_B200_NO_SUMMARY))
+            CK(ctx, cudaMemsetAsync(s.summary.p, 0, treat_b200_summary_len(ctx) * 8, s.stream));
+        int r = run_exact(s);
+        if (r) return r;
+        return copy_out(s);
+    };
+
     for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += kChunkReads, chunk_idx++) {
         const uint64_t cn = std::min<uint64_t>(kChunkReads, N - c0);
-        Slot &s = ctx->slot[chunk_idx & 1];
+        Slot &s = ctx->slot[chunk_idx % kSlots];
         cudaStream_t st = s.stream;
+        double t0 = now();
         CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk (incl. its D2H) is done
+        if ((rc = settle(s))) break;
+        double t1 = now();
+        t_wait_slot += t1 - t0;
         const uint64_t b0 = seq_off[c0], b1 = seq_off[c0 + cn];
         uint32_t max_len = 0;
         for (uint64_t i = c0; i < c0 + cn; i++) {
@@ -515,30 +615,41 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         CK(ctx, s.off.reserve((cn + 1) * 8));
         CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
         if (read_count) CK(ctx, s.rc.reserve(cn * 4));
-        if (want_ops) CK(ctx, s.ops.reserve(cn * (size_t)ops_stride));
         if (b1 > b0) CK(ctx, cudaMemcpyAsync(s.seqs.p, seqs + b0, b1 - b0, cudaMemcpyHostToDevice, st));
         CK(ctx, cudaMemcpyAsync(s.off.p, seq_off + c0, (cn + 1) * 8, cudaMemcpyHostToDevice, st));
         if (read_count) CK(ctx, cudaMemcpyAsync(s.rc.p, read_count + c0, cn * 4, cudaMemcpyHostToDevice, st));
-        bool sat = false;
-        rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0,
-                       read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len, flags, (treat_b200_record *)s.rec.p,
-                       (uint8_t *)s.ops.p, ops_stride, st, false, &sat);
-        if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
+        s.c0 = c0;
+        s.cn = cn;
+        s.b0 = b0;
+        s.max_len = max_len;
+        if (ctx->ncap_hint && !ctx->tmpl_wide && !no_spec) {
+            // no host sync: size the align kernel from the largest n seen so far (+ slack) and validate later
             rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0,
-                           read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len, flags,
-                           (treat_b200_record *)s.rec.p, (uint8_t *)s.ops.p, ops_stride, st, true, nullptr);
+                           read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len, flags, (treat_b200_record *)s.rec.p,
+                           nullptr, 0, st, false, nullptr, &s.dev_stride, ctx->ncap_hint + 8);
+            s.pending = rc == TREAT_B200_OK;
+        } else {
+            rc = run_exact(s);
+        }
         if (rc) break;
-        CK(ctx, cudaMemcpyAsync(rec + c0, s.rec.p, cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, st));
-        if (want_ops)
-            CK(ctx, cudaMemcpyAsync(ops + c0 * (size_t)ops_stride, s.ops.p, cn * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
+        rc = copy_out(s);
+        t_enqueue += now() - t1;
     }
-    for (int i = 0; i < 2; i++) {
+    const double t_loop = now();
+    for (int i = 0; i < kSlots; i++) {
+        int r = settle(ctx->slot[i]);
+        if (r && rc == TREAT_B200_OK) rc = r;
+    }
+    for (int i = 0; i < kSlots; i++) {
         cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream);
         if (e != cudaSuccess && rc == TREAT_B200_OK) {
             ctx->err = std::string("stream sync: ") + cudaGetErrorString(e);
             rc = TREAT_B200_ERR_CUDA;
         }
     }
+    if (trace)
+        fprintf(stderr, "[treat_b200] align_batch N=%llu chunks=%llu total %.2f ms: wait_slot %.2f enqueue %.2f drain %.2f, chunks re-run %d\n",
+                (unsigned long long)N, (unsigned long long)chunk_idx, now() - t_begin, t_wait_slot, t_enqueue, now() - t_loop, redone);
     return rc;
 }
 

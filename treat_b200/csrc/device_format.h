@@ -58,6 +58,7 @@ struct AlignParams {
     uint8_t *ops;                // may be null
     uint32_t ops_stride;
     uint64_t *summary;           // may be null
+    uint32_t *skipped;           // may be null: counts reads (pairs) a speculative launch could not hold
     uint32_t bins;
     uint32_t flags;
     // shared-memory carve-up (bytes, all multiples of 16)
@@ -69,7 +70,8 @@ struct AlignParams {
     uint32_t pair;               // 1: k_align2 (two reads per warp), 0: k_align
     uint32_t force_single;       // TREAT_B200_ONE_READ_PER_WARP
     uint32_t force_full;         // TREAT_B200_FULL_TRACEBACK_STORE: always take the global-scratch path
-    uint32_t band_rows;          // W: direction-word rows kept per lane in shared memory
+    uint32_t band_rows;          // direction-word rows kept per lane in shared memory = (2 band_chunks + 1)(CPL + 1)
+    uint32_t band_chunks;        // C: lane l keeps fill chunk u iff |u - l| <= C
     void *scratch;               // global scratch for full fills: [CTAs x warps][scratch_stride] words
     uint32_t scratch_stride;
 };
@@ -81,6 +83,7 @@ int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_opti
 int plan_align(AlignParams &p, bool wide);
 int align_warps(const AlignParams &p, int max_smem);
 uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
+int launch_merge_summary(uint64_t *dst, uint64_t *src, uint32_t len, void *stream);
 int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream);
 int configure_pack_kernels(int max_smem_optin);
 int configure_align_kernels(int max_smem_optin);
