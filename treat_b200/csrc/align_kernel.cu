@@ -173,6 +173,7 @@ struct CtaSmem {
     uint32_t *sum_lo, *sum_hi; // summary histograms of this CTA (64-bit counters as two words)
     uint32_t sum_len;
     uint32_t *prof;            // scoring profile
+    uint2 *tcp;                // [len_pad] EditSite of up to 8 templates per site, one byte each (packed path, K <= 8)
 };
 
 struct WarpSmem {
@@ -197,6 +198,7 @@ __device__ __forceinline__ CtaSmem<cnt_t> carve_cta(uint8_t *smem, const AlignPa
     c.sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
     c.sum_hi = c.sum_lo + c.sum_len;
     c.prof = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.sum_lo) + align16(8u * c.sum_len));
+    c.tcp = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(c.prof) + p.sm_prof_bytes);
     return c;
 }
 
@@ -223,6 +225,16 @@ __device__ __forceinline__ void load_template(const CtaSmem<cnt_t> &c, const Ali
         c.tcount[i] = reinterpret_cast<const cnt_t *>(p.t.tcount)[i];
     for (int i = threadIdx.x; i < 2 * p.t.n_alt; i += blockDim.x) c.alt[i] = p.t.alt[i];
     for (uint32_t i = threadIdx.x; i < 2 * c.sum_len; i += blockDim.x) c.sum_lo[i] = 0u;
+    if (sizeof(cnt_t) == 1 && p.t.K <= 8) {
+        for (int i = threadIdx.x; i < p.t.len_pad; i += blockDim.x) {
+            uint32_t lo = 0, hi = 0;
+            for (int k = 0; k < p.t.K; k++) {
+                const uint32_t c8 = reinterpret_cast<const uint8_t *>(p.t.tcount)[k * p.t.len_pad + i];
+                if (k < 4) lo |= c8 << (8 * k); else hi |= c8 << (8 * (k - 4));
+            }
+            c.tcp[i] = make_uint2(lo, hi);
+        }
+    }
 }
 
 // w of template column `col` against read code c (0..2 bases, 3 = other, 4 = pad row)
@@ -335,18 +347,41 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     }
 
     // ---- computeT part 2: per template site compare edit-base counts, build the bit rows ----------
-    for (int wv = 0; wv < tw; wv++) {
-        const int ti = wv * 32 + lane;
-        const bool valid = ti < len;
-        uint32_t count = 0;
-        if (valid) {
-            const uint32_t f = indel ? (uint32_t)ws.t2f[ti] : (uint32_t)ti;
-            count = f == 0xffffu ? 0u : (uint32_t)rcount[f];
+    if (sizeof(cnt_t) == 1 && K <= 8) {
+        // all (up to 8) templates of a site in one 8-byte load and two byte-wise compares
+        for (int wv = 0; wv < tw; wv++) {
+            const int ti = wv * 32 + lane;
+            const bool valid = ti < len;
+            uint32_t eq_lo = 0, eq_hi = 0;
+            if (valid) {
+                const uint32_t f = indel ? (uint32_t)ws.t2f[ti] : (uint32_t)ti;
+                const uint32_t c4 = (f == 0xffffu ? 0u : (uint32_t)rcount[f]) * 0x01010101u;
+                const uint2 t = cs.tcp[ti];
+                eq_lo = __vcmpeq4(t.x, c4);
+                eq_hi = __vcmpeq4(t.y, c4);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k < K) {
+                    const uint32_t word = __ballot_sync(FULL_MASK, ((k < 4 ? eq_lo : eq_hi) >> (8 * (k & 3))) & 1u);
+                    if (lane == k) ws.tbits[k * tw + wv] = word;
+                }
+            }
         }
-        for (int k = 0; k < K; k++) {
-            const bool match = valid && (uint32_t)cs.tcount[k * len_pad + ti] == count;
-            const uint32_t word = __ballot_sync(FULL_MASK, match);
-            if (lane == 0) ws.tbits[k * tw + wv] = word;
+    } else {
+        for (int wv = 0; wv < tw; wv++) {
+            const int ti = wv * 32 + lane;
+            const bool valid = ti < len;
+            uint32_t count = 0;
+            if (valid) {
+                const uint32_t f = indel ? (uint32_t)ws.t2f[ti] : (uint32_t)ti;
+                count = f == 0xffffu ? 0u : (uint32_t)rcount[f];
+            }
+            for (int k = 0; k < K; k++) {
+                const bool match = valid && (uint32_t)cs.tcount[k * len_pad + ti] == count;
+                const uint32_t word = __ballot_sync(FULL_MASK, match);
+                if (lane == 0) ws.tbits[k * tw + wv] = word;
+            }
         }
     }
     __syncwarp();
@@ -828,15 +863,20 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
         const uint8_t *st0 = ws.stage + slot * slot_bytes, *st1 = st0 + read_bytes;
         const int nmax = max(n0, n1);
 
-        // ---- pair codes: pc[j] = 5 * codeA(j) + codeB(j), pad code behind either read -----------
+        // ---- pair codes: pc[j] = 5 * codeA(j) + codeB(j), pad code behind either read; 4 per lane ---
         uint8_t *pc = ws.rb + 32;
         {
             const uint32_t *pw0 = reinterpret_cast<const uint32_t *>(st0), *pw1 = reinterpret_cast<const uint32_t *>(st1);
-            for (int j = lane; j < nmax + 80; j += 32) {
-                const int c0 = j < n0 ? (int)((pw0[j >> 4] >> (2 * (j & 15))) & 3u) : kPadCode;
-                const int c1 = j < n1 ? (int)((pw1[j >> 4] >> (2 * (j & 15))) & 3u) : kPadCode;
-                pc[j] = (uint8_t)(c0 * 5 + c1);
-            }
+            auto four = [](const uint32_t *pw, int j0, int n) {
+                // codes j0..j0+3 as bytes; positions >= n hold the pad code
+                const uint32_t x = j0 < n ? (pw[j0 >> 4] >> (2 * (j0 & 15))) & 0xffu : 0u;
+                const uint32_t c = (x & 3u) | ((x & 0xcu) << 6) | ((x & 0x30u) << 12) | ((x & 0xc0u) << 18);
+                const int live = min(max(n - j0, 0), 4);
+                const uint32_t keep = live >= 4 ? 0xffffffffu : (1u << (8 * live)) - 1u;
+                return (c & keep) | (0x04040404u & ~keep);
+            };
+            for (int j0 = 4 * lane; j0 < nmax + 80; j0 += 128)
+                *reinterpret_cast<uint32_t *>(pc + j0) = four(pw0, j0, n0) * 5u + four(pw1, j0, n1);
         }
         __syncwarp();
 
@@ -912,9 +952,10 @@ int plan_align(AlignParams &p, bool wide)
     const uint32_t csz = wide ? 4u : 1u;
     const uint32_t dsz = pair ? 4u : (cpl <= 7 ? 2u : 4u);
     const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
+    p.sm_prof_bytes = wide ? 0u : prof_bytes(cpl, pair ? 25 : 5);
     p.sm_tmpl_bytes = align16(32 * cpl) + align16((uint32_t)(K * p.t.len_pad) * csz) +
-                      align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) +
-                      (wide ? 0u : prof_bytes(cpl, pair ? 25 : 5));
+                      align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) + p.sm_prof_bytes +
+                      ((!wide && K <= 8) ? 8u * (uint32_t)p.t.len_pad : 0u);
     p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
     p.sm_stage_b = wide ? align16(ncap) : align16((ncap + 3) / 4);
     if (p.sm_stage_b == 0) p.sm_stage_b = 16;

@@ -340,7 +340,7 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     pp.raw_len = dst->d_raw_len;
     pp.bases_stride = dst->bases_stride;
     pp.counts_stride = dst->counts_stride;
-    pp.stage_cap = a16(dst->max_len + 1);
+    pp.stage_cap = a16(dst->max_len + 1 + 48);  // room for the zeroed tails the word-wise output reads
     pp.lut = ctx->td.lut;
     pp.edit_base = ctx->td.edit_base;
     pp.scalars = d_scalars;

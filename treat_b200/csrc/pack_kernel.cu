@@ -59,16 +59,19 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
 {
     using cnt_t = typename std::conditional<WIDE, uint32_t, uint8_t>::type;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *s_lut = smem;  // 256
+    uint8_t *s_lut = smem;  // 256: byte -> 2-bit code (0x80 = edit base) or, on the wide path, the upper-cased byte
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cap = p.stage_cap;  // multiple of 16
     uint8_t *s_code = smem + 256 + (size_t)warp * (cap + cap * sizeof(cnt_t));
     cnt_t *s_cnt = reinterpret_cast<cnt_t *>(s_code + cap);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
+    const uint8_t eb = p.edit_base;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint8_t up = (i >= 'a' && i <= 'z') ? (uint8_t)(i - 32) : (uint8_t)i;  // strings.ToUpper, ASCII
+        s_lut[i] = WIDE ? up : (up == eb ? (uint8_t)0x80 : p.lut[up]);
+    }
     __syncthreads();
 
     const uint32_t lt = (1u << lane) - 1u;
-    const uint8_t eb = p.edit_base;
     uint32_t warp_max_n = 0, warp_sat = 0;
     const uint64_t pw = blockDim.x >> 5;
     const uint64_t gw = (uint64_t)blockIdx.x * pw + warp, nw = (uint64_t)gridDim.x * pw;
@@ -79,32 +82,33 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
         uint32_t nb = 0;
         int lastpos = -1;
         bool sat = false, widec = false;
-        for (uint32_t c0 = 0; c0 < L; c0 += 32) {
-            const uint32_t j = c0 + lane;
-            uint8_t ch = eb;
-            if (j < L) {
-                ch = seq[j];
-                if (ch >= 'a' && ch <= 'z') ch -= 32;  // strings.ToUpper, ASCII
-            }
-            const bool isb = ch != eb;
+        // one 32-character chunk: ballot the non-edit bases, compact them, run lengths from the gaps
+        auto chunk = [&](uint32_t c0, uint32_t v, bool inside) {
+            const bool isb = inside && (WIDE ? v != eb : !(v & 0x80u));
             const uint32_t mask = __ballot_sync(FULL_MASK, isb);
             if (isb) {
                 const uint32_t below = mask & lt;
                 const uint32_t idx = nb + __popc(below);
                 const int prev = below ? (int)(c0 + 31 - __clz(below)) : lastpos;
-                uint32_t cnt = (uint32_t)((int)j - prev - 1);
-                uint8_t code = ch;
+                uint32_t cnt = (uint32_t)((int)(c0 + lane) - prev - 1);
                 if (cnt >= 255u) sat = true;  // informational on the wide path, which keeps exact counts
                 if (!WIDE) {
-                    code = s_lut[ch];
-                    widec |= (code == 3);
+                    widec |= (v == 3u);
                     if (cnt >= 255u) cnt = 255u;
                 }
-                s_code[idx] = code;
+                s_code[idx] = (uint8_t)v;
                 s_cnt[idx] = (cnt_t)cnt;
             }
             if (mask) lastpos = (int)(c0 + 31 - __clz(mask));
             nb += __popc(mask);
+        };
+        for (uint32_t c0 = 0; c0 < L; c0 += 64) {
+            // both loads first: two global round trips overlap
+            const uint32_t j0 = c0 + lane, j1 = j0 + 32;
+            const uint8_t r0 = j0 < L ? seq[j0] : (uint8_t)0, r1 = j1 < L ? seq[j1] : (uint8_t)0;
+            const uint32_t v0 = s_lut[r0], v1 = s_lut[r1];
+            chunk(c0, v0, j0 < L);
+            if (c0 + 32 < L) chunk(c0 + 32, v1, j1 < L);
         }
         if (lane == 0) {
             uint32_t cnt = (uint32_t)((int)L - 1 - lastpos);
@@ -114,51 +118,33 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
         }
         __syncwarp();
         const uint32_t n = nb;
+        // zero the tails so that the output below can move whole words
+        s_code[n + lane] = 0;
+        s_cnt[n + 1 + lane] = 0;
+        __syncwarp();
         const bool any_sat = __any_sync(FULL_MASK, sat), any_wide = __any_sync(FULL_MASK, widec);
         // bases
         uint32_t *gb = reinterpret_cast<uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
         if (!WIDE) {
             const uint32_t nwords = align16((n + 3) / 4) / 4;
             for (uint32_t wi = lane; wi < nwords; wi += 32) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const uint32_t bi = wi * 16 + q;
-                    const uint32_t c = bi < n ? s_code[bi] : 0u;
-                    w |= c << (2 * q);
-                }
-                gb[wi] = w;
+                // 16 codes (one byte each) -> 16 x 2 bits: (x * M) >> 24 gathers the four 2-bit fields of a word
+                const uint4 x = *reinterpret_cast<const uint4 *>(s_code + 16 * wi);
+                constexpr uint32_t M = 0x01041040u;
+                const uint32_t lo = __byte_perm(x.x * M, x.y * M, 0x0073), hi = __byte_perm(x.z * M, x.w * M, 0x0073);
+                gb[wi] = __byte_perm(lo, hi, 0x5410);
             }
         } else {
             const uint32_t nwords = align16(n) / 4;
-            for (uint32_t wi = lane; wi < nwords; wi += 32) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t bi = wi * 4 + q;
-                    const uint32_t c = bi < n ? s_code[bi] : 0u;
-                    w |= c << (8 * q);
-                }
-                gb[wi] = w;
-            }
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_code);
+            for (uint32_t wi = lane; wi < nwords; wi += 32) gb[wi] = src[wi];
         }
         // counts (n + 1 entries)
         uint32_t *gc = reinterpret_cast<uint32_t *>(p.counts + r * (uint64_t)p.counts_stride);
-        if (!WIDE) {
-            const uint32_t nwords = align16(n + 1) / 4;
-            for (uint32_t wi = lane; wi < nwords; wi += 32) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t ci = wi * 4 + q;
-                    const uint32_t c = ci <= n ? (uint32_t)s_cnt[ci] : 0u;
-                    w |= c << (8 * q);
-                }
-                gc[wi] = w;
-            }
-        } else {
-            const uint32_t nwords = align16(4 * (n + 1)) / 4;
-            for (uint32_t wi = lane; wi < nwords; wi += 32) gc[wi] = wi <= n ? (uint32_t)s_cnt[wi] : 0u;
+        {
+            const uint32_t nwords = WIDE ? align16(4 * (n + 1)) / 4 : align16(n + 1) / 4;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_cnt);
+            for (uint32_t wi = lane; wi < nwords; wi += 32) gc[wi] = src[wi];
         }
         if (lane == 0) {
             p.n[r] = (uint16_t)n;
