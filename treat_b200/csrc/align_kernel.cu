@@ -80,25 +80,32 @@ struct Prof {
         if (k < N4 * 4) return (((k >> 2) * rows + row) * 32 + lane) * 4 + (k & 3);
         return N4 * rows * 128 + (row * 32 + lane) * REMW + (k - N4 * 4);
     }
-    __device__ __forceinline__ static void load(const uint32_t *base, int rows, int row, int lane, uint32_t (&w)[CPL])
+    // per-lane view in the 32-bit shared window: both bases hold the lane term, a row costs one multiply-add each
+    struct Lane {
+        uint32_t a, b;
+        __device__ __forceinline__ Lane(const uint32_t *base, int rows, int lane)
+            : a(smem_u32(base + lane * 4)), b(smem_u32(base + N4 * rows * 128 + lane * REMW)) {}
+    };
+    template <int ROWS>
+    __device__ __forceinline__ static void load(const Lane &pl, int row, uint32_t (&w)[CPL])
     {
 #pragma unroll
         for (int q = 0; q < N4; q++) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(base + ((q * rows + row) * 32 + lane) * 4);
+            const uint4 v = lds_v4(pl.a + (uint32_t)(q * ROWS + row) * 512u);
             w[4 * q] = v.x;
             w[4 * q + 1] = v.y;
             w[4 * q + 2] = v.z;
             w[4 * q + 3] = v.w;
         }
-        const uint32_t *rp = base + N4 * rows * 128 + (row * 32 + lane) * REMW;
+        const uint32_t rp = pl.b + (uint32_t)row * (128u * REMW);
         if (REM == 1) {
-            w[4 * N4] = rp[0];
+            w[4 * N4] = lds_u32(rp);
         } else if (REM == 2) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(rp);
+            const uint2 v = lds_v2(rp);
             w[4 * N4] = v.x;
             w[4 * N4 + 1] = v.y;
         } else if (REM == 3) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(rp);
+            const uint4 v = lds_v4(rp);
             w[4 * N4] = v.x;
             w[4 * N4 + 1] = v.y;
             w[4 * N4 + 2] = v.z;
@@ -174,6 +181,7 @@ struct CtaSmem {
     uint32_t sum_len;
     uint32_t *prof;            // scoring profile
     uint2 *tcp;                // [len_pad] EditSite of up to 8 templates per site, one byte each (packed path, K <= 8)
+    uint32_t *dump;            // [16][32] words: where lanes outside their band window park their direction words
 };
 
 struct WarpSmem {
@@ -199,6 +207,7 @@ __device__ __forceinline__ CtaSmem<cnt_t> carve_cta(uint8_t *smem, const AlignPa
     c.sum_hi = c.sum_lo + c.sum_len;
     c.prof = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.sum_lo) + align16(8u * c.sum_len));
     c.tcp = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(c.prof) + p.sm_prof_bytes);
+    c.dump = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.tcp) + p.sm_tcp_bytes);
     return c;
 }
 
@@ -541,8 +550,9 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
     int diag = 0;                            // G[i0-1][j-1]
     uint32_t pwc[CPL];
     int cnext = 0;
+    const typename Prof<CPL>::Lane pl(prof, ROWS, lane);
     if (!WIDE) {
-        Prof<CPL>::load(prof, ROWS, rbl[0], lane, pwc);
+        Prof<CPL>::template load<ROWS>(pl, rbl[0], pwc);
         cnext = rbl[1];
     }
     const int nchunks = (steps + P - 1) / P;
@@ -555,7 +565,7 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
             uint32_t pwn[CPL];
             int wv[CPL];
             if (!WIDE) {
-                Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
+                Prof<CPL>::template load<ROWS>(pl, cnext, pwn);
                 cnext = rbu[v + 2];
 #pragma unroll
                 for (int k = 0; k < CPL; k++) wv[k] = (int)pwc[k];
@@ -593,29 +603,41 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
 
 template <int CPL, bool FULL>
 __device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pcl, int steps, int lane, uint32_t (&H)[CPL],
-                                         uint32_t *out, int C)
+                                         uint32_t *out, uint32_t *dump, int C)
 {
     using DT = Dir<CPL>;
     constexpr int ROWS = 25, P = CPL + 1;
 #pragma unroll
     for (int k = 0; k < CPL; k++) H[k] = 0u;
+    uint32_t nd14 = 0u;  // -(G[i0-1][j-1] << kTop), carried from the previous step
     uint32_t diag = 0u;
     uint32_t pwc[CPL];
-    Prof<CPL>::load(prof, ROWS, pcl[0], lane, pwc);
+    const typename Prof<CPL>::Lane pl(prof, ROWS, lane);
+    Prof<CPL>::template load<ROWS>(pl, pcl[0], pwc);
     int cnext = pcl[1];
     const int nchunks = (steps + P - 1) / P;
+    const uint32_t pcl32 = smem_u32(pcl);
+    const uint32_t dump32 = smem_u32(dump + lane), out32 = FULL ? 0u : smem_u32(out + lane);
     for (int u = 0; u < nchunks; u++) {
+        // lanes outside their band window write into a CTA-wide dump row: no predicate inside the chunk
         const bool keep = FULL || (unsigned)(u - lane + C) <= (unsigned)(2 * C);
-        uint32_t *orow = out + (FULL ? u * P : (u - lane + C) * P) * 32 + lane;
-        const uint8_t *pcu = pcl + u * P;
+        uint32_t *grow = out + u * (P * 32) + lane;                                   // FULL: global scratch row
+        const uint32_t srow = keep ? out32 + (uint32_t)(u - lane + C) * (P * 128u) : dump32;  // banded: shared row
+        const uint32_t pcu32 = pcl32 + (uint32_t)(u * P);
 #pragma unroll
         for (int v = 0; v < P; v++) {
             uint32_t pwn[CPL];
-            Prof<CPL>::load(prof, ROWS, cnext, lane, pwn);
-            cnext = pcu[v + 2];
+            Prof<CPL>::template load<ROWS>(pl, cnext, pwn);
+            cnext = (int)lds_u8(pcu32 + v + 2);
             const uint32_t recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
             const uint32_t left = lane == 0 ? 0u : recv;
-            uint32_t dg = diag, lf = left, S = 0;
+            // digits + dV(boundary) for both halves at once (mod 2^32 keeps each 16-bit word exact; left >= diag per half):
+            //   sum_k (f_k - f_{k-1}) 4^k + (left - diag) 2^kTop
+            // = f_last 4^(CPL-1) - 3 sum_{k<CPL-1} f_k 4^k - left + left 2^kTop - diag 2^kTop
+            const uint32_t nl14 = left * (0u - (1u << DT::kTop));
+            uint32_t acc = nd14 - nl14 - left;
+            nd14 = nl14;
+            uint32_t dg = diag, lf = left;
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 const uint32_t e = __viaddmax_s16x2(dg, pwc[k], H[k]);
@@ -623,12 +645,10 @@ __device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pc
                 dg = H[k];
                 lf = f;
                 H[k] = f;
-                S += f << (2 * k);
+                acc += f * (k == CPL - 1 ? (1u << (2 * (CPL - 1))) : 0u - (3u << (2 * k)));
             }
-            // both halves at once: arithmetic mod 2^32 keeps each 16-bit word exact (no borrow: left >= diag per half)
-            const uint32_t word = (lf << (2 * CPL)) - 3u * S - left + ((left - diag) << DT::kTop);
             diag = left;
-            if (keep) orow[v * 32] = word;
+            if (FULL) grow[v * 32] = acc; else sts_u32(srow + v * 128u, acc);
 #pragma unroll
             for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
         }
@@ -884,7 +904,7 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
         uint32_t H[CPL];
         const int steps = nmax > 0 ? nmax + lanes_used - 1 : 0;
         const uint8_t *pcl = pc - lane;
-        fill_two<CPL, false>(cs.prof, pcl, steps, lane, H, s_dir, C);
+        fill_two<CPL, false>(cs.prof, pcl, steps, lane, H, s_dir, cs.dump, C);
         uint32_t fin = 0;
         {
             const int kl = (m - 1) % CPL;
@@ -895,7 +915,7 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
         }
         const int score0 = (int)(fin & 0xffffu) - m - n0, score1 = (int)(fin >> 16) - m - n1;
         const bool banded = band_ok(m, n0, score0, B) && (!has1 || band_ok(m, n1, score1, B)) && !p.force_full;
-        if (!banded) fill_two<CPL, true>(cs.prof, pcl, steps, lane, H, scratch, 0);  // keep every word (global scratch)
+        if (!banded) fill_two<CPL, true>(cs.prof, pcl, steps, lane, H, scratch, cs.dump, 0);  // keep every word (global scratch)
 
         // ---- per read: traceback + editing-site assembly ---------------------------------------
         for (int h = 0; h < (has1 ? 2 : 1); h++) {
@@ -954,8 +974,9 @@ int plan_align(AlignParams &p, bool wide)
     const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
     p.sm_prof_bytes = wide ? 0u : prof_bytes(cpl, pair ? 25 : 5);
     p.sm_tmpl_bytes = align16(32 * cpl) + align16((uint32_t)(K * p.t.len_pad) * csz) +
-                      align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) + p.sm_prof_bytes +
-                      ((!wide && K <= 8) ? 8u * (uint32_t)p.t.len_pad : 0u);
+                      align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) + p.sm_prof_bytes;
+    p.sm_tcp_bytes = (!wide && K <= 8) ? 8u * (uint32_t)p.t.len_pad : 0u;
+    p.sm_tmpl_bytes += p.sm_tcp_bytes + 16u * 32u * 4u;  // + dump rows
     p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
     p.sm_stage_b = wide ? align16(ncap) : align16((ncap + 3) / 4);
     if (p.sm_stage_b == 0) p.sm_stage_b = 16;

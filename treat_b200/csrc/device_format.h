@@ -64,6 +64,7 @@ struct AlignParams {
     // shared-memory carve-up (bytes, all multiples of 16)
     uint32_t sm_tmpl_bytes;      // CTA-wide template section
     uint32_t sm_prof_bytes;      // scoring profile inside it
+    uint32_t sm_tcp_bytes;       // site-major packed template counts inside it
     uint32_t sm_warp_bytes;      // per-warp section
     uint32_t sm_stage_b, sm_stage_c;  // one read inside a stage slot (bases, counts)
     uint32_t sm_stage_total;     // both slots, all reads of a warp
