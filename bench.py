@@ -358,7 +358,12 @@ def run_ours(args):
                "h2d_bytes_per_step": int(len(seqs) + (N + 1) * 8 + N * 4),
                "d2h_bytes_per_step": int(N * 48 + N * (((t.m + max_n + 3) // 4 + 15) // 16 * 16) + 8),
                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "treat_b200_align_batch (pinned host buffers)"}
-        assert np.array_equal(h_rec, rec_dev), "host-buffer and device-buffer paths disagree"
+        if not np.array_equal(h_rec, rec_dev):
+            badi = np.nonzero(h_rec != rec_dev)[0]
+            log("MISMATCH host vs device at", len(badi), "reads, first:", badi[:8])
+            for i in badi[:4]:
+                log(int(i), h_rec[i], rec_dev[i])
+            raise AssertionError("host-buffer and device-buffer paths disagree")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

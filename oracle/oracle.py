@@ -178,9 +178,12 @@ class Fragment:
         self._p = ptr
 
     def __del__(self):
-        if self._p:
-            lib().orc_fragment_free(self._p)
-            self._p = None
+        try:
+            if self._p:
+                lib().orc_fragment_free(self._p)
+                self._p = None
+        except Exception:  # interpreter shutdown
+            pass
 
     Name = property(lambda s: s._p.contents.name.decode("latin-1"))
     ReadCount = property(lambda s: s._p.contents.read_count)
@@ -208,9 +211,12 @@ class Template:
         self._p = ptr
 
     def __del__(self):
-        if self._p:
-            lib().orc_template_free(self._p)
-            self._p = None
+        try:
+            if self._p:
+                lib().orc_template_free(self._p)
+                self._p = None
+        except Exception:  # interpreter shutdown
+            pass
 
     Bases = property(lambda s: C.string_at(s._p.contents.bases, s._p.contents.m).decode("latin-1"))
     EditOffset = property(lambda s: s._p.contents.edit_offset)
@@ -273,9 +279,12 @@ class Alignment:
         self._p = ptr
 
     def __del__(self):
-        if self._p:
-            lib().orc_alignment_free(self._p)
-            self._p = None
+        try:
+            if self._p:
+                lib().orc_alignment_free(self._p)
+                self._p = None
+        except Exception:  # interpreter shutdown
+            pass
 
     EditStop = property(lambda s: s._p.contents.edit_stop)
     JuncStart = property(lambda s: s._p.contents.junc_start)

@@ -334,6 +334,27 @@ def test_speculative_chunks_are_validated(eng, tmp_path):
     assert np.array_equal(rec, rec2) and np.array_equal(ops, ops2)
 
 
+def test_overlapping_chunks_with_fallbacks(eng, tmp_path):
+    """Several host chunks in flight, many reads on the global-scratch fallback (truncated reads against
+    a long template): launches of different chunks overlap on the GPU and must not share scratch."""
+    t = synth.long_template(300, 8)
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 400_000
+    seqs, off, rc = synth.reads(t, N, seed=synth.SEED_BASE + 5, p_trunc=0.2)
+    rec, ops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+    rec2, ops2 = eng.align_batch(seqs, off, rc, cabi.WANT_OPS | cabi.FULL_TRACEBACK_STORE)
+    assert np.array_equal(rec, rec2) and np.array_equal(ops, ops2)
+    idx = np.arange(0, N, 61)
+    lens = np.diff(off.astype(np.int64))
+    sub = np.concatenate([seqs[int(off[i]):int(off[i + 1])] for i in idx])
+    sub_off = np.zeros(len(idx) + 1, dtype=np.uint64)
+    sub_off[1:] = np.cumsum(lens[idx])
+    orec, oops, _ = O.align_batch(om, sub, sub_off, rc[idx], nthreads=8, ops_stride=ops.shape[1])
+    assert compare_records(rec[idx], orec) == []
+    assert np.array_equal(ops[idx], oops)
+
+
 def test_full_size_properties(eng, tmp_path):
     """Config 3 at full size (1M RPS12 reads): size-independent properties on every read, oracle
     parity on a stride sample, determinism across two runs and across batch splits."""

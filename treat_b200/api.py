@@ -89,9 +89,12 @@ class Template:
         self._h = handle
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().treat_b200_template_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().treat_b200_template_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def SetOffset(self, offset: int) -> None:
         lib().treat_b200_template_set_offset(self._h, offset)
@@ -310,7 +313,10 @@ class Aligner:
             self._ctx = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
     # ---- template --------------------------------------------------------------------------
     def SetTemplate(self, tmpl: Template) -> None:

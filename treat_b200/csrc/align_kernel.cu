@@ -541,7 +541,7 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
 // ------------------------------------------------------------------------------------------
 template <int CPL, bool WIDE, bool FULL, typename dir_t>
 __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rbl, const int (&tcr)[CPL], int n, int steps,
-                                         int lane, int (&H)[CPL], dir_t *out, int C)
+                                         int lane, int (&H)[CPL], dir_t *out, uint32_t *dump, int C)
 {
     using DT = Dir<CPL>;
     constexpr int ROWS = 5, P = CPL + 1;
@@ -556,30 +556,35 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
         cnext = rbl[1];
     }
     const int nchunks = (steps + P - 1) / P;
+    const uint32_t rbl32 = smem_u32(rbl);
+    const uint32_t dump32 = smem_u32(dump + lane), out32 = FULL ? 0u : smem_u32(out + lane);
     for (int u = 0; u < nchunks; u++) {
+        // lanes outside their band window write into a CTA-wide dump row: no predicate inside the chunk
         const bool keep = FULL || (unsigned)(u - lane + C) <= (unsigned)(2 * C);
-        dir_t *orow = out + (FULL ? u * P : (u - lane + C) * P) * 32 + lane;
-        const uint8_t *rbu = rbl + u * P;
+        dir_t *grow = out + u * (P * 32) + lane;  // FULL: global scratch row
+        const uint32_t srow = keep ? out32 + (uint32_t)(u - lane + C) * (P * 32u * (uint32_t)sizeof(dir_t)) : dump32;
+        const uint32_t rbu32 = rbl32 + (uint32_t)(u * P);
 #pragma unroll
         for (int v = 0; v < P; v++) {
             uint32_t pwn[CPL];
             int wv[CPL];
             if (!WIDE) {
                 Prof<CPL>::template load<ROWS>(pl, cnext, pwn);
-                cnext = rbu[v + 2];
+                cnext = (int)lds_u8(rbu32 + v + 2);
 #pragma unroll
                 for (int k = 0; k < CPL; k++) wv[k] = (int)pwc[k];
             } else {
                 const int idx = u * P + v - lane;
                 const bool live = idx >= 0 && idx < n;
-                const int rc = live ? (int)rbu[v] : 0x200;
+                const int rc = live ? (int)lds_u8(rbu32 + v) : 0x200;
 #pragma unroll
                 for (int k = 0; k < CPL; k++) wv[k] = live ? (rc == tcr[k] ? 3 : 1) : 0;
             }
             const int recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
             const int left = lane == 0 ? 0 : recv;  // G[i0-1][j]
+            // sum_k (f_k - f_{k-1}) 4^k + (left - diag) 2^kTop, as multiply-adds on the f values
+            uint32_t acc = ((uint32_t)(left - diag) << DT::kTop) - (uint32_t)left;
             int dg = diag, lf = left;
-            uint32_t S = 0;
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 const int e = max(dg + wv[k], H[k]);
@@ -587,11 +592,12 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
                 dg = H[k];
                 lf = f;
                 H[k] = f;
-                S += (uint32_t)f << (2 * k);
+                acc += (uint32_t)f * (k == CPL - 1 ? (1u << (2 * (CPL - 1))) : 0u - (3u << (2 * k)));
             }
-            const uint32_t word = ((uint32_t)lf << (2 * CPL)) - 3u * S - (uint32_t)left + ((uint32_t)(left - diag) << DT::kTop);
             diag = left;
-            if (keep) orow[v * 32] = (dir_t)word;
+            if (FULL) grow[v * 32] = (dir_t)acc;
+            else if (sizeof(dir_t) == 2) sts_u16(srow + v * 64u, acc);
+            else sts_u32(srow + v * 128u, acc);
             if (!WIDE) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
@@ -779,7 +785,7 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
         int H[CPL];
         const int steps = n > 0 ? n + lanes_used - 1 : 0;
         const uint8_t *rbl = rb - lane;  // rbl[t] = read base of this lane's row at step t
-        fill_one<CPL, WIDE, false>(cs.prof, rbl, tcr, n, steps, lane, H, s_dir, C);
+        fill_one<CPL, WIDE, false>(cs.prof, rbl, tcr, n, steps, lane, H, s_dir, cs.dump, C);
         auto final_score = [&]() {
             // F[m][n] = G[m][n] - m - n; G[m][n] lives in lane (m-1)/CPL, column (m-1)%CPL
             int fin = 0;
@@ -796,7 +802,7 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
                                  ws.ops2, m, n, lane, ngaps);
         } else {
             // the path may leave the band: repeat the fill with every word kept (global scratch, L2)
-            fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, 0);
+            fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, cs.dump, 0);
             pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)scratch[tt * 32 + ln]; }, ws.ops2, m, n, lane, ngaps);
         }
         finish_read<cnt_t>(p, cs, ws, lane, r, n, rflags, score, pos, ngaps, rcount, [&](int fi) { return (int)rb[fi]; }, ctr);

@@ -48,6 +48,7 @@ struct DevBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops, summary;
+    DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
     uint32_t *scalars = nullptr;    // device [4]: max n, any saturated run, reads skipped by a speculative launch
     uint32_t *h_scalars = nullptr;  // pinned [4]
     // chunk whose speculative launch still has to be validated (treat_b200_align_batch)
@@ -56,7 +57,7 @@ struct Slot {
     uint32_t max_len = 0, dev_stride = 0;
     void release()
     {
-        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary}) b->release();
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch}) b->release();
         if (scalars) cudaFree(scalars);
         if (h_scalars) cudaFreeHost(h_scalars);
         if (stream) cudaStreamDestroy(stream);
@@ -76,7 +77,7 @@ struct treat_b200_ctx {
     bool have_template = false;
     bool tmpl_wide = false;  // template needs the wide path (non-alphabet base or count >= 255)
     TemplateDev td{};
-    DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut, scratch;
+    DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut;
     uint32_t band_rows = 0;  // 0 = default window
     uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
     std::vector<uint8_t> lut;
@@ -161,7 +162,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->scratch}) b->release();
+    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
     for (Slot &sl : ctx->slot) sl.release();
     ctx->dev_slot.release();
@@ -353,7 +354,7 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
 
 static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t ncap, const uint32_t *d_read_count,
                     uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st,
-                    uint64_t *summary_override = nullptr, uint32_t *d_skipped = nullptr)
+                    DevBuf &scratch, uint64_t *summary_override = nullptr, uint32_t *d_skipped = nullptr)
 {
     if (src->N == 0) return TREAT_B200_OK;
     const bool wide = src->wide != 0;
@@ -391,12 +392,11 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     {
         // global scratch for reads whose path may leave the band (one region per resident warp)
         const uint64_t need = align_scratch_bytes(ap, ctx->num_sms, ctx->max_smem);
-        if (need > ctx->scratch.cap) {
-            CK(ctx, cudaStreamSynchronize(st));
-            CK(ctx, cudaDeviceSynchronize());
-            CK(ctx, ctx->scratch.reserve(need));
+        if (need > scratch.cap) {
+            CK(ctx, cudaStreamSynchronize(st));  // the only launches that use this buffer run on this stream
+            CK(ctx, scratch.reserve(need));
         }
-        ap.scratch = ctx->scratch.p;
+        ap.scratch = scratch.p;
     }
     int e = launch_align(ap, wide, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000 || e == -1001)
@@ -435,7 +435,7 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
     CK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     // n <= raw length: size the launch for max_len (callers that know max n can pass it as max_len)
-    return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st);
+    return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st, ctx->dev_slot.scratch);
 }
 
 // pack + (tiny sync for max n) + align on one slot's buffers
@@ -484,7 +484,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
             }
             slot_sum = (uint64_t *)s.summary.p;
         }
-        rc = do_align(ctx, &pk, ncap, d_rc, flags, d_rec, d_ops, ops_stride, st, slot_sum, s.scalars + 2);
+        rc = do_align(ctx, &pk, ncap, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, slot_sum, s.scalars + 2);
         if (rc) return rc;
         CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, 16, cudaMemcpyDeviceToHost, st));
         return TREAT_B200_OK;
@@ -501,7 +501,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         d_ops = (uint8_t *)s.ops.p;
     }
     if (ops_stride_used) *ops_stride_used = ops_stride;
-    return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st);
+    return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch);
 }
 
 int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
