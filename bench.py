@@ -147,7 +147,7 @@ def run_reference(args):
     if rank != 0:
         return
     t, p_trunc, seed = make_template(args.workload)
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0))
     sample = args.cpu_sample or 4096 * threads
     times, cells = [], 0.0
     from treat_b200 import synth
@@ -189,6 +189,22 @@ def pinned_array(nbytes):
     return arr, p
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Run this rank (and allocate its pinned buffers) on the CPUs next to its GPU: with 8 ranks on a
+    two-socket host the H2D/D2H copies otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as e:  # best effort
+        log("cpu affinity not set:", e)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -202,8 +218,16 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; treat_b200 has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    pin_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is set
+        if "TREAT_B200_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["TREAT_B200_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     t, p_trunc, seed = make_template(args.workload)
@@ -367,7 +391,8 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        os.sched_setaffinity(0, all_cpus)  # the CPU port gets every host core
+        threads = len(all_cpus)
         sample = args.cpu_sample or min(N, 40000 * threads)
         v, g, secs = cpu_sample_rate(t, p_trunc, seed, sample, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "gcups": g,
