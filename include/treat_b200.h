@@ -172,6 +172,9 @@ uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx);
 /* tuning: rows of traceback words kept per lane in shared memory (0 = default 64); any value is
  * exact, reads whose optimal path could leave the band are re-filled into global scratch */
 int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows);
+/* bounds-check flags of the kernels' index computations: always 0 unless the library was built with
+ * -DTREAT_B200_CHECKS (*checks_compiled says which); a substitute for compute-sanitizer on pools without it */
+int treat_b200_debug_flags(treat_b200_ctx *ctx, uint32_t *flags_out, int32_t *checks_compiled);
 
 /* ---- summaries: device-resident uint64 counters --------------------- */
 uint32_t treat_b200_summary_bins(const treat_b200_ctx *ctx);

@@ -398,3 +398,10 @@ def test_full_size_properties(eng, tmp_path):
     lo, hi = 300_000, 300_000 + 70_001
     rec3, ops3 = eng.align_batch(seqs[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo], rc[lo:hi], cabi.WANT_OPS)
     assert np.array_equal(rec3, rec[lo:hi]) and np.array_equal(ops3[:, :ops.shape[1]], ops[lo:hi, :ops3.shape[1]])
+
+
+def test_zz_kernel_bounds_flags_clean(eng):
+    """Runs last: no kernel index computation left its bounds during this module (meaningful when the
+    library was built with TREAT_B200_CHECKS=1; a normal build always reports zero)."""
+    flags, compiled = eng.debug_flags()
+    assert flags == 0, "kernel bounds-check flags: 0x%x (checks compiled: %s)" % (flags, compiled)

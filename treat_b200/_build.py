@@ -48,7 +48,15 @@ def _run(cmd, verbose):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    # TREAT_B200_CHECKS=1 compiles the kernels' bounds checks in (see treat_b200_debug_flags)
+    checks = ["-DTREAT_B200_CHECKS"] if os.environ.get("TREAT_B200_CHECKS") else []
+    force = force or bool(checks) != os.path.exists(os.path.join(OBJ, ".checks"))
     os.makedirs(OBJ, exist_ok=True)
+    marker = os.path.join(OBJ, ".checks")
+    if checks:
+        open(marker, "w").close()
+    elif os.path.exists(marker):
+        os.remove(marker)
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
@@ -58,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             if src.endswith(".cu"):
-                _run([_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o], verbose)
+                _run([_nvcc()] + NVCC_FLAGS + checks + ["-c", s, "-o", o], verbose)
             else:
                 _run([os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-c", s, "-o", o], verbose)
     if force or _stale(LIB, objs):

@@ -367,6 +367,12 @@ class Aligner:
     def synchronize(self) -> None:
         check(lib().treat_b200_synchronize(self._ctx), self._ctx)
 
+    def debug_flags(self) -> Tuple[int, bool]:
+        """(flag word, checks compiled in): non-zero flags mean a kernel index left its bounds."""
+        f, c = C.c_uint32(), C.c_int32()
+        check(lib().treat_b200_debug_flags(self._ctx, C.byref(f), C.byref(c)), self._ctx)
+        return f.value, bool(c.value)
+
     def launch_count(self) -> int:
         return lib().treat_b200_launch_count(self._ctx)
 

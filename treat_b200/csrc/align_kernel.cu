@@ -46,6 +46,19 @@
 namespace treat_b200 {
 
 constexpr int kPadCode = 4;  // profile row with w = 0: a no-op row of the wavefront
+
+// Optional bounds checks (build with -DTREAT_B200_CHECKS): compute-sanitizer is not available on the GPU pool,
+// so index computations that depend on the band certificate or on n can report into a flag word instead.
+#ifdef TREAT_B200_CHECKS
+#define TB_CHECK(p, cond, bit)                                   \
+    do {                                                         \
+        if (!(cond) && (p).dbg) atomicOr((p).dbg, 1u << (bit)); \
+    } while (0)
+#else
+#define TB_CHECK(p, cond, bit) \
+    do {                       \
+    } while (0)
+#endif
 constexpr int kMaxWarpsPair = 32, kMaxWarpsOne = 16;  // resident warps per SM the register budget allows
 
 // ------------------------------------------------------------------------------------------
@@ -325,6 +338,9 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     const int alen = m + n - pos;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t *ops2 = ws.ops2;
+    TB_CHECK(p, pos >= 0 && alen >= max(m, n) && alen <= m + n, 2);
+    TB_CHECK(p, ((uint32_t)(m + n + 15) / 16 + 2) * 4 <= p.sm_ops, 3);
+    TB_CHECK(p, n <= (int)p.ncap, 4);
 
     // ---- computeT part 1 (align.go:131-171): map template sites to read bases, count mismatches ----
     int mism = 0;
@@ -345,6 +361,8 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
             const bool cR = op == TREAT_B200_OP_MATCH || op == TREAT_B200_OP_INS;
             const uint32_t mT = __ballot_sync(FULL_MASK, cT), mR = __ballot_sync(FULL_MASK, cR);
             const int ti = ti_base + __popc(mT & lt), fi = fi_base + __popc(mR & lt);
+            TB_CHECK(p, !cT || (ti >= 0 && ti < m), 5);
+            TB_CHECK(p, op != TREAT_B200_OP_MATCH || (fi >= 0 && fi < n), 6);
             if (cT) ws.t2f[ti] = op == TREAT_B200_OP_MATCH ? (uint16_t)fi : (uint16_t)0xffff;
             const bool mm = op == TREAT_B200_OP_MATCH && rbf(fi) != (int)cs.tb[ti];
             mism += __popc(__ballot_sync(FULL_MASK, mm));
@@ -798,12 +816,21 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
         const int score = final_score();
         int ngaps, pos;
         if (band_ok(m, n, score, B) && !p.force_full) {
-            pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)s_dir[(tt - (ln - C) * P) * 32 + ln]; },
-                                 ws.ops2, m, n, lane, ngaps);
+            pos = traceback<CPL>(
+                [&](int tt, int ln) {
+                    TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
+                    return (uint32_t)s_dir[(tt - (ln - C) * P) * 32 + ln];
+                },
+                ws.ops2, m, n, lane, ngaps);
         } else {
             // the path may leave the band: repeat the fill with every word kept (global scratch, L2)
             fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, cs.dump, 0);
-            pos = traceback<CPL>([&](int tt, int ln) { return (uint32_t)scratch[tt * 32 + ln]; }, ws.ops2, m, n, lane, ngaps);
+            pos = traceback<CPL>(
+                [&](int tt, int ln) {
+                    TB_CHECK(p, (unsigned)(tt * 32 + ln) < p.scratch_stride, 1);
+                    return (uint32_t)scratch[tt * 32 + ln];
+                },
+                ws.ops2, m, n, lane, ngaps);
         }
         finish_read<cnt_t>(p, cs, ws, lane, r, n, rflags, score, pos, ngaps, rcount, [&](int fi) { return (int)rb[fi]; }, ctr);
     }
@@ -933,10 +960,19 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
             int ngaps, pos;
             const int sh = 16 * h;
             if (banded)
-                pos = traceback<CPL>([&](int tt, int ln) { return (s_dir[(tt - (ln - C) * P) * 32 + ln] >> sh) & 0xffffu; },
-                                     ws.ops2, m, n, lane, ngaps);
+                pos = traceback<CPL>(
+                    [&](int tt, int ln) {
+                        TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
+                        return (s_dir[(tt - (ln - C) * P) * 32 + ln] >> sh) & 0xffffu;
+                    },
+                    ws.ops2, m, n, lane, ngaps);
             else
-                pos = traceback<CPL>([&](int tt, int ln) { return (scratch[tt * 32 + ln] >> sh) & 0xffffu; }, ws.ops2, m, n, lane, ngaps);
+                pos = traceback<CPL>(
+                    [&](int tt, int ln) {
+                        TB_CHECK(p, (unsigned)(tt * 32 + ln) < p.scratch_stride, 1);
+                        return (scratch[tt * 32 + ln] >> sh) & 0xffffu;
+                    },
+                    ws.ops2, m, n, lane, ngaps);
             finish_read<cnt_t>(p, cs, ws, lane, r0 + h, n, p.rflags[r0 + h], h ? score1 : score0, pos, ngaps, rcount,
                                [&](int fi) {
                                    const int c = pc[fi];

@@ -80,6 +80,7 @@ struct treat_b200_ctx {
     DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut;
     uint32_t band_rows = 0;  // 0 = default window
     uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
+    uint32_t *d_dbg = nullptr;  // bounds-check flags (only written by TREAT_B200_CHECKS builds)
     std::vector<uint8_t> lut;
     uint64_t *d_summary = nullptr;
     uint32_t bins = 0;
@@ -146,6 +147,11 @@ int treat_b200_create(int device, treat_b200_ctx **out)
         delete ctx;
         return TREAT_B200_ERR_CUDA;
     }
+    if (cudaMalloc((void **)&ctx->d_dbg, 4) != cudaSuccess || cudaMemset(ctx->d_dbg, 0, 4) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return TREAT_B200_ERR_CUDA;
+    }
     int e = configure_pack_kernels(ctx->max_smem);
     if (!e) e = configure_align_kernels(ctx->max_smem);
     if (e) {
@@ -164,6 +170,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
+    if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     for (Slot &sl : ctx->slot) sl.release();
     ctx->dev_slot.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -298,6 +305,20 @@ int treat_b200_synchronize(treat_b200_ctx *ctx)
 
 uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int treat_b200_debug_flags(treat_b200_ctx *ctx, uint32_t *flags_out, int32_t *checks_compiled)
+{
+    if (!ctx || !flags_out) return TREAT_B200_ERR_INVALID;
+    int rc = treat_b200_synchronize(ctx);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpy(flags_out, ctx->d_dbg, 4, cudaMemcpyDeviceToHost));
+#ifdef TREAT_B200_CHECKS
+    if (checks_compiled) *checks_compiled = 1;
+#else
+    if (checks_compiled) *checks_compiled = 0;
+#endif
+    return TREAT_B200_OK;
+}
+
 int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows)
 {
     if (!ctx) return TREAT_B200_ERR_INVALID;
@@ -379,6 +400,7 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     ap.ops_stride = ops_stride;
     ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : (summary_override ? summary_override : ctx->d_summary);
     ap.skipped = d_skipped;
+    ap.dbg = ctx->d_dbg;
     ap.bins = ctx->bins;
     ap.flags = flags;
     ap.force_single = (flags & TREAT_B200_ONE_READ_PER_WARP) ? 1u : 0u;

@@ -59,6 +59,7 @@ struct AlignParams {
     uint32_t ops_stride;
     uint64_t *summary;           // may be null
     uint32_t *skipped;           // may be null: counts reads (pairs) a speculative launch could not hold
+    uint32_t *dbg;               // may be null: bounds-check flag word (TREAT_B200_CHECKS builds)
     uint32_t bins;
     uint32_t flags;
     // shared-memory carve-up (bytes, all multiples of 16)
