@@ -127,59 +127,35 @@ struct Prof {
 };
 
 // ------------------------------------------------------------------------------------------
-// Bit rows over template sites in array order ti = 0..len-1 (site number = len-1-ti), one 32-bit
-// word per lane, kept in shared memory: the willf/bitset sets of align.go:122-181.
+// Bit rows over template sites in array order ti = 0..len-1 (site number = len-1-ti): the willf/bitset
+// sets of align.go:122-181.  A row lives in registers, lane w holds bits ti = 32w .. 32w+31; queries are
+// one warp reduction (REDUX) each.
 // ------------------------------------------------------------------------------------------
-struct BitRows {
-    const uint32_t *T;  // [K][tw]
-    int tw, len, lane;
-    // highest ti <= limit whose bit is clear in row k, or -1
-    __device__ __forceinline__ int highest_clear_le(int k, int limit) const
+struct RowGeom {
+    int lane, len;
+    uint32_t vmask;  // bits of this lane's word that are real sites
+    __device__ __forceinline__ RowGeom(int lane_, int len_) : lane(lane_), len(len_)
     {
-        uint32_t w = 0;
+        const int rem = len - lane * 32;
+        vmask = rem <= 0 ? 0u : rem >= 32 ? 0xffffffffu : (1u << rem) - 1u;
+    }
+    // highest ti <= limit whose bit is clear, or -1
+    __device__ __forceinline__ int highest_clear_le(uint32_t row, int limit) const
+    {
+        uint32_t w = ~row & vmask;
         const int lo = lane * 32;
-        if (lane < tw && lo <= limit) {
-            w = ~T[k * tw + lane];
-            if (limit - lo < 31) w &= (2u << (limit - lo)) - 1u;
-        }
-        const uint32_t any = __ballot_sync(FULL_MASK, w != 0);
-        if (!any) return -1;
-        const int hw = 31 - __clz(any);
-        const uint32_t wv = __shfl_sync(FULL_MASK, w, hw);
-        return hw * 32 + 31 - __clz(wv);
+        if (lo > limit) w = 0;
+        else if (limit - lo < 31) w &= (2u << (limit - lo)) - 1u;
+        return __reduce_max_sync(FULL_MASK, w ? lo + 31 - __clz(w) : -1);
     }
-    // lowest ti whose bit is clear in row k, or -1
-    __device__ __forceinline__ int lowest_clear(int k) const
+    // lowest ti whose bit is clear, or -1
+    __device__ __forceinline__ int lowest_clear(uint32_t row) const
     {
-        uint32_t w = 0;
-        const int lo = lane * 32;
-        if (lane < tw) {
-            w = ~T[k * tw + lane];
-            if (len - 1 - lo < 31) w &= (2u << (len - 1 - lo)) - 1u;
-        }
-        const uint32_t any = __ballot_sync(FULL_MASK, w != 0);
-        if (!any) return -1;
-        const int lw = __ffs(any) - 1;
-        const uint32_t wv = __shfl_sync(FULL_MASK, w, lw);
-        return lw * 32 + __ffs(wv) - 1;
+        const uint32_t w = ~row & vmask;
+        const int r = __reduce_min_sync(FULL_MASK, w ? lane * 32 + __ffs(w) - 1 : 0x7fffffff);
+        return r == 0x7fffffff ? -1 : r;
     }
-    __device__ __forceinline__ bool any_set(int k) const
-    {
-        uint32_t w = 0;
-        const int lo = lane * 32;
-        if (lane < tw) {
-            w = T[k * tw + lane];
-            if (len - 1 - lo < 31) w &= (2u << (len - 1 - lo)) - 1u;
-        }
-        return __any_sync(FULL_MASK, w != 0);
-    }
-    // bitset.Test on a SITE number (out of range -> false, as willf/bitset does)
-    __device__ __forceinline__ bool test_site(int k, int site) const
-    {
-        if (site < 0 || site >= len) return false;
-        const int ti = len - 1 - site;
-        return (T[k * tw + (ti >> 5)] >> (ti & 31)) & 1u;
-    }
+    __device__ __forceinline__ bool any_set(uint32_t row) const { return __any_sync(FULL_MASK, (row & vmask) != 0); }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -193,7 +169,6 @@ struct CtaSmem {
     uint32_t *sum_lo, *sum_hi; // summary histograms of this CTA (64-bit counters as two words)
     uint32_t sum_len;
     uint32_t *prof;            // scoring profile
-    uint2 *tcp;                // [len_pad] EditSite of up to 8 templates per site, one byte each (packed path, K <= 8)
     uint32_t *dump;            // [16][32] words: where lanes outside their band window park their direction words
 };
 
@@ -203,7 +178,6 @@ struct WarpSmem {
     void *dir;         // direction words [steps][32]
     uint32_t *ops2;    // traceback ops, 2 bits each, index p = 0 .. m+n-1 (alignment = [pos, m+n))
     uint16_t *t2f;     // template site -> read base index (0xffff = deletion)
-    uint32_t *tbits;   // [K][tw]
     uint64_t *bar;     // [2] mbarriers
 };
 
@@ -219,8 +193,7 @@ __device__ __forceinline__ CtaSmem<cnt_t> carve_cta(uint8_t *smem, const AlignPa
     c.sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
     c.sum_hi = c.sum_lo + c.sum_len;
     c.prof = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.sum_lo) + align16(8u * c.sum_len));
-    c.tcp = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(c.prof) + p.sm_prof_bytes);
-    c.dump = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.tcp) + p.sm_tcp_bytes);
+    c.dump = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(c.prof) + p.sm_prof_bytes);
     return c;
 }
 
@@ -233,8 +206,7 @@ __device__ __forceinline__ WarpSmem carve_warp(uint8_t *smem, const AlignParams 
     w.dir = w.rb + p.sm_rb;
     w.ops2 = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(w.dir) + p.sm_dir);
     w.t2f = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(w.ops2) + p.sm_ops);
-    w.tbits = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(w.t2f) + p.sm_t2f);
-    w.bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(w.tbits) + p.sm_tbits);
+    w.bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(w.t2f) + p.sm_t2f);
     return w;
 }
 
@@ -247,16 +219,6 @@ __device__ __forceinline__ void load_template(const CtaSmem<cnt_t> &c, const Ali
         c.tcount[i] = reinterpret_cast<const cnt_t *>(p.t.tcount)[i];
     for (int i = threadIdx.x; i < 2 * p.t.n_alt; i += blockDim.x) c.alt[i] = p.t.alt[i];
     for (uint32_t i = threadIdx.x; i < 2 * c.sum_len; i += blockDim.x) c.sum_lo[i] = 0u;
-    if (sizeof(cnt_t) == 1 && p.t.K <= 8) {
-        for (int i = threadIdx.x; i < p.t.len_pad; i += blockDim.x) {
-            uint32_t lo = 0, hi = 0;
-            for (int k = 0; k < p.t.K; k++) {
-                const uint32_t c8 = reinterpret_cast<const uint8_t *>(p.t.tcount)[k * p.t.len_pad + i];
-                if (k < 4) lo |= c8 << (8 * k); else hi |= c8 << (8 * (k - 4));
-            }
-            c.tcp[i] = make_uint2(lo, hi);
-        }
-    }
 }
 
 // w of template column `col` against read code c (0..2 bases, 3 = other, 4 = pad row)
@@ -347,10 +309,12 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     const bool indel = ngaps != 0;
     if (!indel) {
         // no gap in the alignment: column c pairs template base c with read base c
-        for (int c0 = 0; c0 < m; c0 += 32) {
-            const int c = c0 + lane;
-            const bool mm = c < m && rbf(c) != (int)cs.tb[c];
-            mism += __popc(__ballot_sync(FULL_MASK, mm));
+        if (score != m) {  // score == m == n: every base matches, nothing to count
+            for (int c0 = 0; c0 < m; c0 += 32) {
+                const int c = c0 + lane;
+                const bool mm = c < m && rbf(c) != (int)cs.tb[c];
+                mism += __popc(__ballot_sync(FULL_MASK, mm));
+            }
         }
     } else {
         int ti_base = 0, fi_base = 0;
@@ -373,66 +337,59 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
         __syncwarp();
     }
 
-    // ---- computeT part 2: per template site compare edit-base counts, build the bit rows ----------
-    if (sizeof(cnt_t) == 1 && K <= 8) {
-        // all (up to 8) templates of a site in one 8-byte load and two byte-wise compares
+    // ---- computeT part 2: edit-base count of the read at every template site vs the templates.
+    // Only the FE and PE rows are always needed; an alternative template's row is built when the
+    // junction start sits on the first site of its region (align.go:186-205).
+    auto site_count = [&](int ti) -> uint32_t {  // the read's count aligned to template site ti (0 for a deletion)
+        const uint32_t f = indel ? (uint32_t)ws.t2f[ti] : (uint32_t)ti;
+        return f == 0xffffu ? 0u : (uint32_t)rcount[f];
+    };
+    auto build_row = [&](int k) -> uint32_t {  // lane w keeps bits ti = 32w..32w+31 of template k's match row
+        uint32_t row = 0;
         for (int wv = 0; wv < tw; wv++) {
             const int ti = wv * 32 + lane;
-            const bool valid = ti < len;
-            uint32_t eq_lo = 0, eq_hi = 0;
-            if (valid) {
-                const uint32_t f = indel ? (uint32_t)ws.t2f[ti] : (uint32_t)ti;
-                const uint32_t c4 = (f == 0xffffu ? 0u : (uint32_t)rcount[f]) * 0x01010101u;
-                const uint2 t = cs.tcp[ti];
-                eq_lo = __vcmpeq4(t.x, c4);
-                eq_hi = __vcmpeq4(t.y, c4);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (k < K) {
-                    const uint32_t word = __ballot_sync(FULL_MASK, ((k < 4 ? eq_lo : eq_hi) >> (8 * (k & 3))) & 1u);
-                    if (lane == k) ws.tbits[k * tw + wv] = word;
-                }
-            }
+            const bool match = ti < len && (uint32_t)cs.tcount[k * len_pad + ti] == site_count(ti);
+            const uint32_t word = __ballot_sync(FULL_MASK, match);
+            if (lane == wv) row = word;
         }
-    } else {
-        for (int wv = 0; wv < tw; wv++) {
-            const int ti = wv * 32 + lane;
-            const bool valid = ti < len;
-            uint32_t count = 0;
-            if (valid) {
-                const uint32_t f = indel ? (uint32_t)ws.t2f[ti] : (uint32_t)ti;
-                count = f == 0xffffu ? 0u : (uint32_t)rcount[f];
-            }
-            for (int k = 0; k < K; k++) {
-                const bool match = valid && (uint32_t)cs.tcount[k * len_pad + ti] == count;
-                const uint32_t word = __ballot_sync(FULL_MASK, match);
-                if (lane == 0) ws.tbits[k * tw + wv] = word;
-            }
+        return row;
+    };
+    uint32_t t0 = 0, t1 = 0;
+    for (int wv = 0; wv < tw; wv++) {
+        const int ti = wv * 32 + lane;
+        const bool valid = ti < len;
+        const uint32_t count = valid ? site_count(ti) : 0u;
+        const uint32_t w0 = __ballot_sync(FULL_MASK, valid && (uint32_t)cs.tcount[ti] == count);
+        const uint32_t w1 = __ballot_sync(FULL_MASK, valid && (uint32_t)cs.tcount[len_pad + ti] == count);
+        if (lane == wv) {
+            t0 = w0;
+            t1 = w1;
         }
     }
-    __syncwarp();
 
     // ---- findJSS / computeAltEditing / findJES / NewAlignment (align.go:95-120,183-279) -----------
-    BitRows B{ws.tbits, tw, len, lane};
+    const RowGeom G(lane, len);
     int has_mutation = 0;
     if (indel) has_mutation = 1;
     if (((p.flags & TREAT_B200_EXCLUDE_SNPS) && mism >= 1) || mism >= 3) has_mutation = 1;
 
-    const int hc0 = B.highest_clear_le(0, len - 1);
+    const int hc0 = G.highest_clear_le(t0, len - 1);
     const bool t0_all = hc0 < 0;
-    int junc_start = t0_all ? len - 1 : (!B.any_set(0) ? -1 : len - 1 - hc0);
+    int junc_start = t0_all ? len - 1 : (!G.any_set(t0) ? -1 : len - 1 - hc0);
     int alt_editing = 0;
-    {
+    if (K > 2 && junc_start >= 0 && junc_start < len) {  // bitset.Test is false out of range
         int shift = junc_start, alt = -1;
+        const int ti_s = len - 1 - shift;
+        const uint32_t cstar = site_count(ti_s);
         for (int k = 2; k < K; k++) {
-            if (B.test_site(k, shift)) {
+            if ((uint32_t)cs.tcount[k * len_pad + ti_s] == cstar) {
                 alt = k - 2;
                 break;
             }
         }
         if (alt >= 0 && shift == cs.alt[alt]) {
-            const int hc = B.highest_clear_le(alt + 2, len - 1 - shift);
+            const uint32_t ta = build_row(alt + 2);
+            const int hc = G.highest_clear_le(ta, len - 1 - shift);
             const bool full_match = hc < 0;
             if (!full_match) shift = len - 1 - hc;
             if (full_match || shift >= cs.alt[n_alt + alt]) {
@@ -440,13 +397,13 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
                 if (full_match) {
                     junc_start = len - 1;
                 } else {
-                    const int h0 = B.highest_clear_le(0, len - 1 - shift);
+                    const int h0 = G.highest_clear_le(t0, len - 1 - shift);
                     if (h0 >= 0) junc_start = len - 1 - h0;
                 }
             }
         }
     }
-    const int lc1 = B.lowest_clear(1);
+    const int lc1 = G.lowest_clear(t1);
     int junc_end = lc1 < 0 ? -1 : len - 1 - lc1;
     int edit_stop = junc_start - 1;
     int junc_len = 0;
@@ -814,8 +771,10 @@ __global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignP
             return __shfl_sync(FULL_MASK, fin, (m - 1) / CPL) - m - n;
         };
         const int score = final_score();
-        int ngaps, pos;
-        if (band_ok(m, n, score, B) && !p.force_full) {
+        int ngaps = 0, pos = n;  // alignment = ops2[pos, m + n)
+        if (score == m && n == m) {
+            // every base matches: the only optimal path is the main diagonal (m zero ops, already zeroed)
+        } else if (band_ok(m, n, score, B) && !p.force_full) {
             pos = traceback<CPL>(
                 [&](int tt, int ln) {
                     TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
@@ -957,9 +916,12 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
             const cnt_t *rcount = reinterpret_cast<const cnt_t *>(st + p.sm_stage_b);
             for (int i = lane; i < ops_words; i += 32) ws.ops2[i] = 0u;
             __syncwarp();
-            int ngaps, pos;
+            int ngaps = 0, pos = n;  // alignment = ops2[pos, m + n)
             const int sh = 16 * h;
-            if (banded)
+            const int score = h ? score1 : score0;
+            if (score == m && n == m) {
+                // every base matches: the only optimal path is the main diagonal (m zero ops, already zeroed)
+            } else if (banded)
                 pos = traceback<CPL>(
                     [&](int tt, int ln) {
                         TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
@@ -973,7 +935,7 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
                         return (scratch[tt * 32 + ln] >> sh) & 0xffffu;
                     },
                     ws.ops2, m, n, lane, ngaps);
-            finish_read<cnt_t>(p, cs, ws, lane, r0 + h, n, p.rflags[r0 + h], h ? score1 : score0, pos, ngaps, rcount,
+            finish_read<cnt_t>(p, cs, ws, lane, r0 + h, n, p.rflags[r0 + h], score, pos, ngaps, rcount,
                                [&](int fi) {
                                    const int c = pc[fi];
                                    return h ? c % 5 : c / 5;
@@ -1017,8 +979,7 @@ int plan_align(AlignParams &p, bool wide)
     p.sm_prof_bytes = wide ? 0u : prof_bytes(cpl, pair ? 25 : 5);
     p.sm_tmpl_bytes = align16(32 * cpl) + align16((uint32_t)(K * p.t.len_pad) * csz) +
                       align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) + p.sm_prof_bytes;
-    p.sm_tcp_bytes = (!wide && K <= 8) ? 8u * (uint32_t)p.t.len_pad : 0u;
-    p.sm_tmpl_bytes += p.sm_tcp_bytes + 16u * 32u * 4u;  // + dump rows
+    p.sm_tmpl_bytes += 16u * 32u * 4u;  // + dump rows
     p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
     p.sm_stage_b = wide ? align16(ncap) : align16((ncap + 3) / 4);
     if (p.sm_stage_b == 0) p.sm_stage_b = 16;
@@ -1037,8 +998,7 @@ int plan_align(AlignParams &p, bool wide)
     p.scratch_stride = full_rows * 32;  // direction words of one warp's full fill
     p.sm_ops = align16((((uint32_t)m + ncap + 15) / 16 + 2) * 4);
     p.sm_t2f = align16(2u * (uint32_t)p.t.len_pad);
-    p.sm_tbits = align16(4u * (uint32_t)K * (uint32_t)(p.t.len_pad / 32));
-    p.sm_warp_bytes = p.sm_stage_total + p.sm_rb + p.sm_dir + p.sm_ops + p.sm_t2f + p.sm_tbits + 16;
+    p.sm_warp_bytes = p.sm_stage_total + p.sm_rb + p.sm_dir + p.sm_ops + p.sm_t2f + 16;
     p.sm_warp_bytes = (p.sm_warp_bytes + 127u) & ~127u;
     return cpl;
 }

@@ -65,11 +65,10 @@ struct AlignParams {
     // shared-memory carve-up (bytes, all multiples of 16)
     uint32_t sm_tmpl_bytes;      // CTA-wide template section
     uint32_t sm_prof_bytes;      // scoring profile inside it
-    uint32_t sm_tcp_bytes;       // site-major packed template counts inside it
     uint32_t sm_warp_bytes;      // per-warp section
     uint32_t sm_stage_b, sm_stage_c;  // one read inside a stage slot (bases, counts)
     uint32_t sm_stage_total;     // both slots, all reads of a warp
-    uint32_t sm_rb, sm_dir, sm_ops, sm_t2f, sm_tbits;
+    uint32_t sm_rb, sm_dir, sm_ops, sm_t2f;
     uint32_t pair;               // 1: k_align2 (two reads per warp), 0: k_align
     uint32_t force_single;       // TREAT_B200_ONE_READ_PER_WARP
     uint32_t force_full;         // TREAT_B200_FULL_TRACEBACK_STORE: always take the global-scratch path

@@ -142,7 +142,9 @@ int64_t treat_b200_format_alignment(const treat_b200_template *t, const treat_b2
     const Template &tm = *T(t);
     Fragment frag = treat::NewFragment(name ? name : "", std::string((const char *)seq, seq_len), treat::FORWARD, tm.EditBase);
     treat::Alignment a = treat::Alignment::FromRecord(*rec, ops, seq, seq_len);
-    return emit(a.WriteTo(frag, tm, tw), out, cap);
+    const std::string text = a.WriteTo(frag, tm, tw);
+    if (text.empty()) return TREAT_B200_ERR_INVALID;  // record/ops do not belong to this read and template
+    return emit(text, out, cap);
 }
 
 int64_t treat_b200_simple_align(treat_b200_ctx *ctx, const uint8_t *s1, size_t l1, const uint8_t *s2, size_t l2,

@@ -274,9 +274,22 @@ Alignment Alignment::FromRecord(const treat_b200_record &r, const uint8_t *packe
     return a;
 }
 
+// ops must consume exactly the template's and the fragment's bases
+static bool opsConsistent(const std::vector<uint8_t> &ops, size_t m, size_t n)
+{
+    size_t ti = 0, fi = 0;
+    for (uint8_t op : ops) {
+        if (op > TREAT_B200_OP_INS) return false;
+        if (op != TREAT_B200_OP_INS) ti++;
+        if (op != TREAT_B200_OP_DEL) fi++;
+    }
+    return ti == m && fi == n;
+}
+
 std::string Alignment::WriteTo(const Fragment &frag, const Template &tmpl, int tw) const
 {
     if (tw <= 0) tw = 80;
+    if (!opsConsistent(Ops, tmpl.Bases.size(), frag.Bases.size())) return std::string();  // corrupt input: no text
     const int K = tmpl.Size();
     std::vector<std::string> buf(K + 1);
     std::string &rd = buf[K];
@@ -378,6 +391,7 @@ void SimpleAlignStrings(const Fragment &f1, const Fragment &f2, const std::vecto
     std::string &b0 = *s1, &b1 = *s2;
     b0.clear();
     b1.clear();
+    if (!opsConsistent(ops, f1.Bases.size(), f2.Bases.size())) return;
     int fi = 0, ti = 0;
     for (uint8_t op : ops) {
         if (op == TREAT_B200_OP_INS) {
