@@ -19,8 +19,8 @@ using namespace treat_b200;
 namespace {
 
 constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
-constexpr uint64_t kChunkReads = 1u << 17;  // reads per pipelined chunk of treat_b200_align_batch
-constexpr int kSlots = 3;                   // chunks in flight: H2D, kernels and D2H of different chunks overlap
+constexpr uint64_t kChunkReads = 1u << 16;  // reads per pipelined chunk of treat_b200_align_batch
+constexpr int kSlots = 4;                   // most chunks in flight: H2D, kernels and D2H of different chunks overlap
 
 struct DevBuf {
     void *p = nullptr;
@@ -562,6 +562,9 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     int rc = TREAT_B200_OK;
     uint64_t chunk_idx = 0;
     static const bool trace = getenv("TREAT_B200_TRACE") != nullptr;
+    // tuning knobs (defaults: 65536 reads per chunk, 4 chunks in flight)
+    static const uint64_t chunk_reads = getenv("TREAT_B200_CHUNK") ? std::max(1024ull, strtoull(getenv("TREAT_B200_CHUNK"), nullptr, 10)) : kChunkReads;
+    static const int n_slots = getenv("TREAT_B200_SLOTS") ? std::min(kSlots, std::max(1, atoi(getenv("TREAT_B200_SLOTS")))) : kSlots;
     static const bool no_spec = getenv("TREAT_B200_NO_SPECULATION") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
@@ -612,9 +615,9 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         return copy_out(s);
     };
 
-    for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += kChunkReads, chunk_idx++) {
-        const uint64_t cn = std::min<uint64_t>(kChunkReads, N - c0);
-        Slot &s = ctx->slot[chunk_idx % kSlots];
+    for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk_reads, chunk_idx++) {
+        const uint64_t cn = std::min<uint64_t>(chunk_reads, N - c0);
+        Slot &s = ctx->slot[chunk_idx % n_slots];
         cudaStream_t st = s.stream;
         double t0 = now();
         CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk (incl. its D2H) is done
