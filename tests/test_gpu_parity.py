@@ -1,5 +1,6 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact records, traceback
 ops and `treat align` text.  Run on the B200 box with -m gpu."""
+import os
 import random
 
 import numpy as np
@@ -398,6 +399,58 @@ def test_full_size_properties(eng, tmp_path):
     lo, hi = 300_000, 300_000 + 70_001
     rec3, ops3 = eng.align_batch(seqs[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo], rc[lo:hi], cabi.WANT_OPS)
     assert np.array_equal(rec3, rec[lo:hi]) and np.array_equal(ops3[:, :ops.shape[1]], ops[lo:hi, :ops3.shape[1]])
+
+
+def test_other_edit_base_is_isomorphic(eng, examples, tmp_path):
+    """Swapping the letters A and T everywhere and editing on 'A' must give the same records: exercises
+    the edit-base-dependent alphabet (codes for C, G, T; A stripped) against the oracle and itself."""
+    swap = bytes.maketrans(b"ATat", b"TAta")
+    tsrc = P.read_fasta(examples["templates.fa"])
+    p = tmp_path / "swapped.fa"
+    p.write_text("".join(">%s\n%s\n" % (i, s.encode().translate(swap).decode()) for i, s in tsrc))
+    reads = P.read_fasta(examples["clones.fa"])
+    t_T = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "T")
+    t_A = T.NewTemplateFromFasta(str(p), T.FORWARD, "a")
+    o_A = O.NewTemplateFromFasta(str(p), O.FORWARD, "a")
+    a_T = eng.NewAlignments(reads, t_T, False)
+    sw = [(i, s.encode().translate(swap).decode()) for i, s in reads]
+    a_A = eng.NewAlignments(sw, t_A, False)
+    for (rid, seq), x, y in zip(sw, a_T, a_A):
+        fx, fy = x.fields(), y.fields()
+        fx["junc_seq"] = fx["junc_seq"].encode().translate(swap).decode()
+        assert fx == fy, rid
+        assert x.ops() == y.ops()
+        of = O.NewFragment(rid, seq, O.FORWARD, "a")
+        oa = O.NewAlignment(of, o_A)
+        assert fy == oa.fields(), rid
+        assert y.WriteTo(T.NewFragment(rid, seq, T.FORWARD, "a"), t_A, 80) == oa.WriteTo(of, o_A, 80)
+
+
+def test_reverse_orientation(eng, examples):
+    """REVERSE fragments (fragment.go:95-97: plain reversal) through the Go-shaped API."""
+    tmpl = T.NewTemplateFromFasta(examples["test-templates.fa"], T.FORWARD, "t")
+    om = O.NewTemplateFromFasta(examples["test-templates.fa"], O.FORWARD, "t")
+    for rid, seq in P.read_fasta(examples["test-sample.fa"]):
+        fr = T.NewFragment(rid, seq[::-1], T.REVERSE, "t")
+        a = eng.NewAlignment(fr, tmpl, False)
+        of = O.NewFragment(rid, seq[::-1], O.REVERSE, "t")
+        oa = O.NewAlignment(of, om)
+        assert a.fields() == oa.fields(), rid
+        assert a.WriteTo(fr, tmpl, 80) == oa.WriteTo(of, om, 80)
+
+
+def test_treat_align_binary(examples):
+    """The treat_align executable (cmd/treat/align.go driver on the GPU) prints the oracle's bytes."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "treat_b200", "bin", "treat_align")
+    out = subprocess.run([exe, "-t", examples["templates.fa"], "-f", examples["clones.fa"], "-b", "T"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout == O.cli_align(template=examples["templates.fa"], fragment=examples["clones.fa"], base="T")
+    out = subprocess.run([exe, "-1", "ATCTGTATGT", "-2", "ATTCGATTG", "-b", "T"], capture_output=True, text=True, timeout=120)
+    assert out.stdout == "A-TCTGTA-TGT\nATTC-G-ATTG-\n\n"
+    bad = subprocess.run([exe, "-1", "ATCTGTATGT", "-b", "T"], capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0 and "Please provide 2 fragments to align" in bad.stderr
 
 
 def test_zz_kernel_bounds_flags_clean(eng):
