@@ -59,7 +59,9 @@ constexpr int kPadCode = 4;  // profile row with w = 0: a no-op row of the wavef
     do {                       \
     } while (0)
 #endif
-constexpr int kMaxWarpsPair = 32, kMaxWarpsOne = 16;  // resident warps per SM the register budget allows
+constexpr int kMaxWarpsPair = 32;  // resident warps per SM the register budget allows (k_align2: 63 registers)
+// one-read kernel: more columns per lane need more registers, so fewer warps
+__host__ __device__ constexpr int max_warps_one(int cpl) { return cpl <= 7 ? 24 : cpl <= 12 ? 20 : 16; }
 
 // ------------------------------------------------------------------------------------------
 // direction words
@@ -657,7 +659,7 @@ __device__ __forceinline__ void flush_summary(const AlignParams &p, uint32_t sum
 // K2a: one read per warp (any CPL <= 15; the only kernel of the wide path)
 // ------------------------------------------------------------------------------------------
 template <int CPL, bool WIDE>
-__global__ void __launch_bounds__(512, 1) k_align(const __grid_constant__ AlignParams p)
+__global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __grid_constant__ AlignParams p)
 {
     using DT = Dir<CPL>;
     using dir_t = typename DT::word_t;
@@ -1007,7 +1009,7 @@ int plan_align(AlignParams &p, bool wide)
 int align_warps(const AlignParams &p, int max_smem)
 {
     long warps = ((long)max_smem - (long)p.sm_tmpl_bytes) / (long)p.sm_warp_bytes;
-    const long cap = p.pair ? kMaxWarpsPair : kMaxWarpsOne;
+    const long cap = p.pair ? kMaxWarpsPair : max_warps_one(pick_cpl(p.t.m));
     if (warps > cap) warps = cap;
     return warps < 1 ? 0 : (int)warps;
 }
