@@ -243,6 +243,18 @@ int64_t treat_b200_simple_align(treat_b200_ctx *ctx, const uint8_t *s1, size_t l
 /* align.go:316-335 Alignment.MarshalBinary: 36-byte big-endian header + JuncSeq */
 int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *seq, size_t seq_len, uint8_t *out,
                                   size_t cap);
+/* cmd/treat/storage.go:758-770 (`treat load`): Alignment.MarshalBinary for a whole batch; blob i is
+ * out[out_off[i] .. out_off[i+1]).  Returns the total size in bytes; nothing is written when out is NULL
+ * or out_cap is too small (call once to size).  threads = host threads for the fill. */
+int64_t treat_b200_marshal_batch(const treat_b200_record *rec, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N,
+                                 uint8_t *out, uint64_t out_cap, uint64_t *out_off /* N+1 */, int32_t threads);
+/* cmd/treat/mutant.go:55-110 (`treat mutant`): census of the distinct gapped template strings (reads with an
+ * insertion) and gapped read strings (reads with a deletion), from the records + ops of an align call made
+ * with TREAT_B200_WANT_OPS.  *out is the text `treat mutant -n n` prints (release with treat_b200_free);
+ * entries with equal counts are ordered by string (Go's sort.Sort leaves that order unspecified). */
+int treat_b200_mutant_report(const treat_b200_template *t, const treat_b200_record *rec, const uint8_t *ops,
+                             uint32_t ops_stride, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N, int32_t n,
+                             char **out, size_t *out_len);
 /* cmd/treat/align.go:59-122 `treat align`: writes the exact stdout text to a malloc'ed
  * buffer (*out, release with treat_b200_free) */
 int treat_b200_cli_align(treat_b200_ctx *ctx, const char *template_path, const char *fragment_path,

@@ -369,3 +369,31 @@ def PrintAlignment(a1, a2, tw=80):  # cmd/treat/align.go:39-57
     for r in range(0, len(a1), tw):
         out += [a1[r:r + tw] + "\n", a2[r:r + tw] + "\n", "\n"]
     return "".join(out)
+
+
+def mutant(tmpl, frags, tie="ULD"):
+    """cmd/treat/mutant.go:70-89: counts of the distinct gapped template strings (reads with an insertion)
+    and gapped read strings (reads with a deletion).  Returns (tm, fm) dicts."""
+    tm, fm = {}, {}
+    for f in frags:
+        aln1, aln2, _ = nw_align(tmpl.Bases, f.Bases, 1, -1, -1, tie)
+        if "-" in aln1:
+            tm[aln1] = tm.get(aln1, 0) + 1
+        if "-" in aln2:
+            fm[aln2] = fm.get(aln2, 0) + 1
+    return tm, fm
+
+
+def mutant_report(tm, fm, n):
+    """cmd/treat/mutant.go:91-109 with ties ordered by string (Go's sort.Sort leaves them unspecified)."""
+    out = ["Template Indels\n"]
+    for cnt, (k, v) in enumerate(sorted(tm.items(), key=lambda kv: (-kv[1], kv[0])), 1):
+        out.append("%d: %s\n" % (v, k))
+        if cnt > n:
+            break
+    out.append("\nFragment Indels\n")
+    for cnt, (k, v) in enumerate(sorted(fm.items(), key=lambda kv: (-kv[1], kv[0])), 1):
+        out.append("%d: %s\n" % (v, k))
+        if cnt > n:
+            break
+    return "".join(out)

@@ -401,6 +401,30 @@ def test_full_size_properties(eng, tmp_path):
     assert np.array_equal(rec3, rec[lo:hi]) and np.array_equal(ops3[:, :ops.shape[1]], ops[lo:hi, :ops3.shape[1]])
 
 
+def test_load_and_mutant_rows_from_device_results(eng, tmp_path):
+    """SURVEY 8(f) rows on top of the device results: `treat load` blobs (MarshalBinary per read) and the
+    `treat mutant` census computed from the device's records + ops equal those from the oracle's."""
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 6000
+    seqs, off, rc = synth.reads(t, N, seed=synth.SEED_BASE + 55, p_trunc=0.05)
+    grec, gops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+    orec, oops, _ = O.align_batch(om, seqs, off, rc, nthreads=8, ops_stride=gops.shape[1])
+    blob, boff = T.marshal_batch(grec, seqs, off, threads=4)
+    for i in range(0, N, 97):
+        s = seqs[int(off[i]):int(off[i + 1])].tobytes().decode()
+        f = O.NewFragment("r-%d" % rc[i], s)
+        assert blob[int(boff[i]):int(boff[i + 1])].tobytes() == O.NewAlignment(f, om).MarshalBinary()
+    orec_p = np.zeros(N, dtype=cabi.RECORD_DTYPE)
+    for f in orec.dtype.names:
+        if f in orec_p.dtype.names and f != "pad":
+            orec_p[f] = orec[f]
+    got = T.mutant_report(tm, grec, gops, seqs, off, 20)
+    assert got == T.mutant_report(tm, orec_p, oops, seqs, off, 20)
+    assert got.count("\n") > 10
+
+
 def test_other_edit_base_is_isomorphic(eng, examples, tmp_path):
     """Swapping the letters A and T everywhere and editing on 'A' must give the same records: exercises
     the edit-base-dependent alphabet (codes for C, G, T; A stripped) against the oracle and itself."""

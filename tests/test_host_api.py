@@ -140,3 +140,36 @@ def test_format_and_marshal_vs_oracle(examples):
 def test_print_alignment():
     a, b = "A" * 170, "C" * 170
     assert T.PrintAlignment(a, b, 80) == P.PrintAlignment(a, b, 80)
+
+
+def test_marshal_batch_vs_oracle(examples):
+    """`treat load` record path: MarshalBinary for a batch (storage.go:758-770, align.go:316-335)."""
+    for tname, rname, base in (("templates.fa", "clones.fa", "T"), ("test-templates.fa", "test-sample.fa", "t")):
+        om = O.NewTemplateFromFasta(examples[tname], O.FORWARD, base)
+        fb = T.read_fasta(examples[rname])
+        orec, _, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, want_ops=False)
+        rec = _oracle_record_as_product(orec)
+        for threads in (1, 3):
+            blob, off = T.marshal_batch(rec, fb.seqs, fb.offsets, threads)
+            assert int(off[-1]) == len(blob)
+            for i in range(len(fb)):
+                oa = O.NewAlignment(O.NewFragment(fb.ids[i], fb.seq(i), O.FORWARD, base), om)
+                assert blob[int(off[i]):int(off[i + 1])].tobytes() == oa.MarshalBinary(), fb.ids[i]
+    blob, off = T.marshal_batch(rec[:0], fb.seqs, fb.offsets[:1])
+    assert len(blob) == 0 and off.tolist() == [0]
+
+
+def test_mutant_report_vs_oracle(examples):
+    """`treat mutant` (cmd/treat/mutant.go:55-110) from records + ops; ops here come from the oracle."""
+    tm = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "T")
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    pt = P.template_from_fasta(examples["templates.fa"], P.FORWARD, "T")
+    recs = P.read_fasta(examples["clones.fa"])
+    recs = recs + [(i + "x", s) for i, s in recs[7:13]] + recs[9:11]  # repeat some indel reads: counts > 1
+    fb = T.FastaBatch.from_records(recs)
+    orec, oops, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts)
+    rec = _oracle_record_as_product(orec)
+    want_tm, want_fm = P.mutant(pt, [P.Fragment(i, s, P.FORWARD, "T") for i, s in recs])
+    assert want_tm and want_fm
+    for n in (0, 1, 10):
+        assert T.mutant_report(tm, rec, oops, fb.seqs, fb.offsets, n) == P.mutant_report(want_tm, want_fm, n)

@@ -25,6 +25,7 @@ from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, RECORD_DTYPE, REVERSE, WAN
 __all__ = [
     "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
     "NewTemplate", "NewTemplateFromFasta", "parseMergeCount", "PrintAlignment", "read_fasta", "TreatError",
+    "marshal_batch", "mutant_report",
 ]
 
 
@@ -219,6 +220,43 @@ def read_fasta(path: str) -> FastaBatch:
         return FastaBatch(ids, seqs, off, rc)
     finally:
         lib().treat_b200_fasta_free(h)
+
+
+def marshal_batch(rec: np.ndarray, seqs: np.ndarray, seq_off: np.ndarray, threads: int = 4):
+    """Alignment.MarshalBinary (align.go:316-335) for a whole batch: returns (blob bytes, offsets[N+1])."""
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    N = len(rec)
+    dummy = np.zeros(1, np.uint8)
+    sp = seqs.ctypes.data if seqs.size else dummy.ctypes.data
+    need = lib().treat_b200_marshal_batch(rec.ctypes.data, sp, seq_off.ctypes.data, N, None, 0, None, 1)
+    if need < 0:
+        raise TreatError(int(need))
+    out = np.zeros(max(int(need), 1), dtype=np.uint8)
+    off = np.zeros(N + 1, dtype=np.uint64)
+    got = lib().treat_b200_marshal_batch(rec.ctypes.data, sp, seq_off.ctypes.data, N, out.ctypes.data, int(need),
+                                         off.ctypes.data, threads)
+    if got < 0:
+        raise TreatError(int(got))
+    return out[: int(need)], off
+
+
+def mutant_report(tmpl: "Template", rec: np.ndarray, ops: np.ndarray, seqs: np.ndarray, seq_off: np.ndarray, n: int = 10) -> str:
+    """`treat mutant` text (cmd/treat/mutant.go:55-110) from the records + ops of an align call."""
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE)
+    ops = np.ascontiguousarray(ops, dtype=np.uint8)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    out, ln = C.c_void_p(), C.c_size_t()
+    dummy = np.zeros(1, np.uint8)
+    check(lib().treat_b200_mutant_report(tmpl._h, rec.ctypes.data, ops.ctypes.data, ops.shape[1] if ops.ndim == 2 else 0,
+                                         seqs.ctypes.data if seqs.size else dummy.ctypes.data, seq_off.ctypes.data,
+                                         len(rec), n, C.byref(out), C.byref(ln)))
+    try:
+        return C.string_at(out.value, ln.value).decode("latin-1")
+    finally:
+        lib().treat_b200_free(out)
 
 
 def PrintAlignment(a1: str, a2: str, tw: int = 80) -> str:

@@ -101,6 +101,9 @@ SIGNATURES = {
     "treat_b200_format_alignment": (C.c_int64, [_P, _P, _U8P, C.c_char_p, _U8P, _SZ, C.c_int32, _P, _SZ]),
     "treat_b200_simple_align": (C.c_int64, [_P, _U8P, _SZ, _U8P, _SZ, C.c_uint8, _P, _P, _SZ]),
     "treat_b200_marshal_record": (C.c_int64, [_P, _U8P, _SZ, _U8P, _SZ]),
+    "treat_b200_marshal_batch": (C.c_int64, [_P, _U8P, _P, C.c_uint64, _U8P, C.c_uint64, _P, C.c_int32]),
+    "treat_b200_mutant_report": (C.c_int, [_P, _P, _U8P, C.c_uint32, _U8P, _P, C.c_uint64, C.c_int32, C.POINTER(_P),
+                                           C.POINTER(_SZ)]),
     "treat_b200_cli_align": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint8, C.c_int32,
                                        C.POINTER(_P), C.POINTER(_SZ), C.c_char_p, _SZ]),
     "treat_b200_free": (None, [_P]),

@@ -170,6 +170,32 @@ int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *s
     return (int64_t)b.size();
 }
 
+int64_t treat_b200_marshal_batch(const treat_b200_record *rec, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N,
+                                 uint8_t *out, uint64_t out_cap, uint64_t *out_off, int32_t threads)
+{
+    if (!rec && N) return TREAT_B200_ERR_INVALID;
+    if ((!seqs || !seq_off) && N) return TREAT_B200_ERR_INVALID;
+    const uint64_t need = treat::MarshalBatch(rec, seqs, seq_off, N, nullptr, nullptr, 1);
+    if (!out || !out_off || out_cap < need) return (int64_t)need;
+    for (uint64_t i = 0; i < N; i++)
+        if ((uint64_t)rec[i].junc_seq_off + rec[i].junc_seq_len > seq_off[i + 1] - seq_off[i]) return TREAT_B200_ERR_INVALID;
+    return (int64_t)treat::MarshalBatch(rec, seqs, seq_off, N, out, out_off, threads);
+}
+
+int treat_b200_mutant_report(const treat_b200_template *t, const treat_b200_record *rec, const uint8_t *ops,
+                             uint32_t ops_stride, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N, int32_t n,
+                             char **out, size_t *out_len)
+{
+    if (!t || !out || !out_len || (N && (!rec || !ops || !seqs || !seq_off))) return TREAT_B200_ERR_INVALID;
+    const std::string text = treat::MutantFromOps(*T(t), rec, ops, ops_stride, seqs, seq_off, N).Report(n);
+    *out = (char *)malloc(text.size() + 1);
+    if (!*out) return TREAT_B200_ERR_NOMEM;
+    memcpy(*out, text.data(), text.size());
+    (*out)[text.size()] = 0;
+    *out_len = text.size();
+    return TREAT_B200_OK;
+}
+
 int treat_b200_cli_align(treat_b200_ctx *ctx, const char *template_path, const char *fragment_path, const char *s1,
                          const char *s2, uint8_t base, int32_t offset, char **out, size_t *out_len, char *err,
                          size_t errlen)

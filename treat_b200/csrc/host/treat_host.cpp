@@ -6,6 +6,8 @@
 #include <cstring>
 #include <fstream>
 #include <iterator>
+#include <map>
+#include <thread>
 
 namespace treat {
 
@@ -433,6 +435,124 @@ std::string PrintAlignment(const std::string &a1, const std::string &a2, int tw)
         out += "\n\n";
     }
     return out;
+}
+
+// ------------------------------------------------------------------ treat load / treat mutant helpers
+
+uint64_t MarshalBatch(const treat_b200_record *rec, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N,
+                      uint8_t *out, uint64_t *out_off, int threads)
+{
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < N; i++) {
+        if (out_off) out_off[i] = total;
+        total += 36 + rec[i].junc_seq_len;
+    }
+    if (out_off) out_off[N] = total;
+    if (!out || !out_off) return total;
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; i++) {
+            const treat_b200_record &r = rec[i];
+            uint8_t *b = out + out_off[i];
+            auto be32 = [&](size_t o, uint32_t v) {
+                b[o] = (uint8_t)(v >> 24);
+                b[o + 1] = (uint8_t)(v >> 16);
+                b[o + 2] = (uint8_t)(v >> 8);
+                b[o + 3] = (uint8_t)v;
+            };
+            be32(0, (uint32_t)r.edit_stop);
+            be32(4, (uint32_t)r.junc_start);
+            be32(8, (uint32_t)r.junc_end);
+            be32(12, (uint32_t)r.junc_len);
+            be32(16, r.read_count);
+            b[20] = r.has_mutation;
+            b[21] = r.alt_editing;
+            b[22] = r.mismatches;
+            b[23] = r.indel;
+            memset(b + 24, 0, 8);  // Norm = 0.0 on this path
+            be32(32, r.junc_seq_len);
+            const uint8_t *src = seqs + seq_off[i] + r.junc_seq_off;
+            for (uint32_t k = 0; k < r.junc_seq_len; k++) b[36 + k] = (uint8_t)upper((char)src[k]);
+        }
+    };
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > N) threads = N ? (int)N : 1;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work, N * t / threads, N * (t + 1) / threads);
+    work(0, N / threads);
+    for (auto &th : pool) th.join();
+    return total;
+}
+
+MutantCensus MutantFromOps(const Template &tmpl, const treat_b200_record *rec, const uint8_t *ops, uint32_t ops_stride,
+                           const uint8_t *seqs, const uint64_t *seq_off, uint64_t N)
+{
+    std::map<std::string, int> tm, fm;
+    const char eb = tmpl.EditBase;
+    std::string aln1, aln2, bases;
+    for (uint64_t i = 0; i < N; i++) {
+        const treat_b200_record &r = rec[i];
+        if (!r.indel) continue;  // no '-' in either gapped string
+        // Fragment.Bases of this read (upper-cased, edit base stripped)
+        bases.clear();
+        for (uint64_t p = seq_off[i]; p < seq_off[i + 1]; p++) {
+            const char c = upper((char)seqs[p]);
+            if (c != eb) bases.push_back(c);
+        }
+        const uint8_t *o = ops + i * (uint64_t)ops_stride;
+        aln1.clear();
+        aln2.clear();
+        size_t ti = 0, fi = 0;
+        bool gap1 = false, gap2 = false, ok = true;
+        for (uint32_t c = 0; c < r.aln_len && ok; c++) {
+            const uint8_t op = (o[c >> 2] >> (2 * (c & 3))) & 3u;
+            if (op == TREAT_B200_OP_INS) {
+                ok = fi < bases.size();
+                aln1.push_back('-');
+                if (ok) aln2.push_back(bases[fi++]);
+                gap1 = true;
+            } else if (op == TREAT_B200_OP_DEL) {
+                ok = ti < tmpl.Bases.size();
+                if (ok) aln1.push_back(tmpl.Bases[ti++]);
+                aln2.push_back('-');
+                gap2 = true;
+            } else {
+                ok = ti < tmpl.Bases.size() && fi < bases.size();
+                if (ok) {
+                    aln1.push_back(tmpl.Bases[ti++]);
+                    aln2.push_back(bases[fi++]);
+                }
+            }
+        }
+        if (!ok) continue;  // ops do not belong to this read: skip rather than read out of bounds
+        if (gap1) tm[aln1]++;
+        if (gap2) fm[aln2]++;
+    }
+    MutantCensus out;
+    auto rank = [](const std::map<std::string, int> &m, std::vector<std::pair<std::string, int>> *v) {
+        v->assign(m.begin(), m.end());
+        std::stable_sort(v->begin(), v->end(), [](const auto &a, const auto &b) { return a.second > b.second; });
+    };
+    rank(tm, &out.tmpl);
+    rank(fm, &out.frag);
+    return out;
+}
+
+std::string MutantCensus::Report(int n) const
+{
+    // cmd/treat/mutant.go:91-109: the loops print before they test count > n, so n+1 lines at most
+    std::string s = "Template Indels\n";
+    int count = 0;
+    for (const auto &p : tmpl) {
+        s += std::to_string(p.second) + ": " + p.first + "\n";
+        if (++count > n) break;
+    }
+    s += "\nFragment Indels\n";
+    count = 0;
+    for (const auto &p : frag) {
+        s += std::to_string(p.second) + ": " + p.first + "\n";
+        if (++count > n) break;
+    }
+    return s;
 }
 
 // ------------------------------------------------------------------ batch engine

@@ -109,6 +109,20 @@ private:
     treat_b200_ctx *ctx_;
 };
 
+// `treat load` record path (cmd/treat/storage.go:758-770): Alignment.MarshalBinary for a whole batch.
+// Blob i is out[out_off[i] .. out_off[i+1]); returns the total size (call with out == nullptr to size).
+uint64_t MarshalBatch(const treat_b200_record *rec, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N,
+                      uint8_t *out, uint64_t *out_off, int threads);
+
+// `treat mutant` (cmd/treat/mutant.go:80-109): census of the distinct gapped template strings (reads with an
+// insertion) and gapped read strings (reads with a deletion), built from the device's traceback ops.
+struct MutantCensus {
+    std::vector<std::pair<std::string, int>> tmpl, frag;  // sorted by count (descending), then by string
+    std::string Report(int n) const;                      // the text `treat mutant -n n` prints
+};
+MutantCensus MutantFromOps(const Template &tmpl, const treat_b200_record *rec, const uint8_t *ops, uint32_t ops_stride,
+                           const uint8_t *seqs, const uint64_t *seq_off, uint64_t N);
+
 // `treat align` (cmd/treat/align.go:59-122): returns false + err where the reference calls logrus.Fatal
 bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
               const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
