@@ -340,8 +340,15 @@ def run_ours(args):
     pk_full = cabi.Packed()
     C.memmove(C.byref(pk_full), C.byref(pk), C.sizeof(pk))
     pk_full.max_len = max_len
+    # the DP kernel on every read (what the roofline is about) ...
     align_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_align_packed_device(
         eng._ctx, C.byref(pk), d_rc.data_ptr(), flags, d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw), eng._ctx), args.steps)
+    # ... and what the batch call launches: k_same_bases finishes the reads whose bases equal the template's without a
+    # DP and lists the others for the DP kernel
+    marks_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_align_packed_device(
+        eng._ctx, C.byref(pk), d_rc.data_ptr(), flags | cabi.USE_PACK_MARKS, d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw),
+        eng._ctx), args.steps)
+    same_frac = float((d_fl.cpu().numpy() & 0x80).astype(bool).mean())
     pack_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_pack_device(
         eng._ctx, d_seqs.data_ptr(), d_off.data_ptr(), C.byref(pk_full), sraw), eng._ctx), args.steps)
     n_arr = d_n.cpu().numpy().astype(np.int64) & 0xffff
@@ -375,8 +382,11 @@ def run_ours(args):
     # ---- end to end through the host-buffer C ABI call -------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        def step_host():
-            eng.align_batch(seqs, h_off, h_rc, flags, rec=h_rec, ops=h_ops)
+        # ops rows only for reads with a gap (the others are all-zero rows the host never needs): what NewAlignments uses
+        e2e_flags = flags | cabi.OPS_GAPPED_ONLY
+
+        def step_host(fl=e2e_flags):
+            eng.align_batch(seqs, h_off, h_rc, fl, rec=h_rec, ops=h_ops)
             red = summ.clone()
             parallel.allreduce_summary(red)
             return int(red[0].item())  # device->host read of the step's reduced summary
@@ -388,10 +398,23 @@ def run_ours(args):
             step_host()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        dev_stride = ((t.m + max_n + 3) // 4 + 15) // 16 * 16
+        n_gapped = int((rec_dev["indel"] != 0).sum())
         e2e = {"value": world * N * args.steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(len(seqs) + (N + 1) * 8 + N * 4),
-               "d2h_bytes_per_step": int(N * 48 + N * (((t.m + max_n + 3) // 4 + 15) // 16 * 16) + 8),
-               "ms_per_step": 1e3 * e2e_s / args.steps, "api": "treat_b200_align_batch (pinned host buffers)"}
+               "d2h_bytes_per_step": int(N * 48 + n_gapped * (dev_stride + 4) + 32 * ((N + 65535) // 65536) + 8),
+               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "api": "treat_b200_align_batch (pinned host buffers), records + ops rows of the %d reads with a gap "
+                      "(TREAT_B200_OPS_GAPPED_ONLY)" % n_gapped}
+        # the same call returning the ops row of every read
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host(flags)
+        barrier()
+        full_s = max_over_ranks(time.perf_counter() - t0)
+        e2e["every_ops_row"] = {"value": world * N * args.steps / full_s, "ms_per_step": 1e3 * full_s / args.steps,
+                                "d2h_bytes_per_step": int(N * 48 + N * dev_stride + 8)}
         if not np.array_equal(h_rec, rec_dev):
             badi = np.nonzero(h_rec != rec_dev)[0]
             log("MISMATCH host vs device at", len(badi), "reads, first:", badi[:8])
@@ -418,7 +441,8 @@ def run_ours(args):
             "config": {"workload": workload_name(args, t), "l2": "inputs larger than L2 (%.0f MB raw reads per GPU per step)" % (len(seqs) / 1e6),
                        "parallelism": "reads sharded over %d GPU(s), summary all-reduce only" % world,
                        "outputs": "48-byte record + %d-byte 2-bit ops per read" % stride},
-            "kernels_ms": {"k_pack": pack_ms, "k_align": align_ms},
+            "kernels_ms": {"k_pack": pack_ms, "k_same_bases+k_align(listed reads)": marks_ms, "k_align(every read)": align_ms},
+            "reads_equal_to_template_bases": same_frac,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }

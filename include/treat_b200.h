@@ -46,6 +46,13 @@ extern "C" {
 #define TREAT_B200_NO_SUMMARY 0x4u   /* do not accumulate the per-context summary histograms */
 #define TREAT_B200_ONE_READ_PER_WARP 0x8u /* use the one-read-per-warp kernel even where the paired kernel applies */
 #define TREAT_B200_FULL_TRACEBACK_STORE 0x10u /* keep every direction word (global scratch) instead of the band */
+#define TREAT_B200_DP_EVERY_READ 0x20u /* run the DP even for reads whose stripped bases equal the template's (results are the same) */
+#define TREAT_B200_OPS_GAPPED_ONLY 0x80u /* with WANT_OPS: write the ops row only of reads whose alignment has a gap
+                                            (record.indel != 0); the row of any other read would be all zero (m = n
+                                            match columns) and is left untouched, so D2H traffic shrinks to the gapped reads */
+#define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
+                                           under the template that is current now, so reads it marked as equal to the template
+                                           skip the DP; without this flag the stage call runs the DP for every read */
 
 /* ---- per-read status bits ----------------------------------------------------------- */
 #define TREAT_B200_ST_REF_PANIC 0x1u  /* reference indexes frag.EditSite out of range here (align.go:250-257) */
@@ -154,7 +161,7 @@ typedef struct treat_b200_packed {
     uint32_t bases_stride;   /* bytes per read, multiple of 16 */
     uint32_t counts_stride;  /* bytes per read, multiple of 16 */
     uint16_t *d_n;           /* [N] len(Fragment.Bases) */
-    uint8_t *d_flags;        /* [N] TREAT_B200_ST_WIDE_BASE | TREAT_B200_ST_SATURATED */
+    uint8_t *d_flags;        /* [N] TREAT_B200_ST_WIDE_BASE | TREAT_B200_ST_SATURATED | 0x80 (internal mark: bases equal the template) */
     uint8_t *d_bases;        /* [N][bases_stride] */
     uint8_t *d_counts;       /* [N][counts_stride]  Fragment.EditSite, n+1 entries */
     uint32_t *d_raw_len;     /* [N] */

@@ -169,9 +169,12 @@ def _batch_vs_oracle(eng, t, tmp_path, N, seed, p_trunc=0.0, offset=0, exclude=F
     assert np.array_equal(grec["raw_len"], lens)
     want = summary_from_records(orec, t.m, offset, om.EditStop)
     assert np.array_equal(eng.summary(), want)
-    # the one-read-per-warp kernel and the full (unbanded) traceback store must give the same bytes
+    # the one-read-per-warp kernel, the full (unbanded) traceback store and the DP for reads whose bases equal
+    # the template's (finished without a DP by default) must all give the same bytes
     k = min(N, 3001)
-    for extra in (cabi.ONE_READ_PER_WARP, cabi.FULL_TRACEBACK_STORE, cabi.ONE_READ_PER_WARP | cabi.FULL_TRACEBACK_STORE):
+    E = cabi.DP_EVERY_READ
+    for extra in (E, cabi.ONE_READ_PER_WARP, cabi.FULL_TRACEBACK_STORE, E | cabi.ONE_READ_PER_WARP, E | cabi.FULL_TRACEBACK_STORE,
+                  E | cabi.ONE_READ_PER_WARP | cabi.FULL_TRACEBACK_STORE):
         srec, sops = eng.align_batch(seqs[:int(off[k])], off[:k + 1], rc[:k], flags | extra | cabi.NO_SUMMARY)
         assert np.array_equal(srec, grec[:k]) and np.array_equal(sops[:, :gops.shape[1]], gops[:k, :sops.shape[1]])
     return grec, orec, seqs, off
@@ -294,6 +297,81 @@ def test_device_resident_entry_point(eng, tmp_path):
     drec = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
     assert np.array_equal(drec, hrec)
     assert np.array_equal(d_ops.cpu().numpy().reshape(N, stride), hops)
+
+
+def test_stage_calls_and_pack_marks(eng, tmp_path):
+    """pack_device + align_packed_device: with and without USE_PACK_MARKS the records equal the one-call result;
+    the mark (bit 7 of the flag byte) is set exactly for reads whose stripped bases equal the template's."""
+    import ctypes as C
+    import torch
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 6001
+    seqs, off, rc = synth.reads(t, N, seed=4242)
+    hrec, hops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS | cabi.NO_SUMMARY)
+    max_len = int(np.diff(off.astype(np.int64)).max())
+    pk = cabi.Packed()
+    cabi.check(cabi.lib().treat_b200_packed_layout(eng._ctx, N, max_len, 0, C.byref(pk)), eng._ctx)
+    dev = dict(n=torch.zeros(N, dtype=torch.int16, device="cuda"), flags=torch.zeros(N, dtype=torch.uint8, device="cuda"),
+               bases=torch.zeros(N * pk.bases_stride, dtype=torch.uint8, device="cuda"),
+               counts=torch.zeros(N * pk.counts_stride, dtype=torch.uint8, device="cuda"),
+               raw_len=torch.zeros(N, dtype=torch.int32, device="cuda"))
+    pk.d_n, pk.d_flags, pk.d_bases, pk.d_counts, pk.d_raw_len = (dev[k].data_ptr() for k in ("n", "flags", "bases", "counts", "raw_len"))
+    d_seqs = torch.from_numpy(seqs.copy()).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_rc = torch.from_numpy(rc.astype(np.int32)).cuda()
+    stride = hops.shape[1]
+    cabi.check(cabi.lib().treat_b200_pack_device(eng._ctx, d_seqs.data_ptr(), d_off.data_ptr(), C.byref(pk), None), eng._ctx)
+    eng.synchronize()
+    marks = (dev["flags"].cpu().numpy() & 0x80) != 0
+    m = t.m
+    want = np.array([int(r["n_bases"]) == m and int(r["score"]) == m for r in hrec])
+    assert np.array_equal(marks, want) and 0 < marks.sum() < N
+    for fl in (0, cabi.USE_PACK_MARKS, cabi.USE_PACK_MARKS | cabi.ONE_READ_PER_WARP):
+        d_rec = torch.zeros(N * 48, dtype=torch.uint8, device="cuda")
+        d_ops = torch.full((N * stride,), 0xee, dtype=torch.uint8, device="cuda")
+        cabi.check(cabi.lib().treat_b200_align_packed_device(eng._ctx, C.byref(pk), d_rc.data_ptr(),
+                                                             cabi.WANT_OPS | cabi.NO_SUMMARY | fl, d_rec.data_ptr(),
+                                                             d_ops.data_ptr(), stride, None), eng._ctx)
+        eng.synchronize()
+        assert np.array_equal(d_rec.cpu().numpy().view(cabi.RECORD_DTYPE), hrec), fl
+        assert np.array_equal(d_ops.cpu().numpy().reshape(N, stride), hops), fl
+
+
+def test_ops_for_gapped_reads_only(eng, tmp_path):
+    """OPS_GAPPED_ONLY: rows of reads with a gap equal the full output, every other row is left untouched; also with
+    many chunks, more gapped reads than the ahead-of-time copy holds, and on the device entry point."""
+    import torch
+    t = synth.long_template(300, 8)
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 150000  # three chunks
+    seqs, off, rc = synth.reads(t, N, seed=991, p_trunc=0.5)  # truncation: about half of the reads are gapped
+    frec, fops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS | cabi.NO_SUMMARY)
+    gapped = frec["indel"] != 0
+    assert 0.2 * N < gapped.sum() < 0.8 * N
+    srec = np.zeros(N, dtype=cabi.RECORD_DTYPE)
+    sops = np.full(fops.shape, 0xAB, dtype=np.uint8)
+    eng.align_batch(seqs, off, rc, cabi.WANT_OPS | cabi.NO_SUMMARY | cabi.OPS_GAPPED_ONLY, rec=srec, ops=sops)
+    assert np.array_equal(srec, frec)
+    assert np.array_equal(sops[gapped], fops[gapped])
+    assert (sops[~gapped] == 0xAB).all()
+    # device buffers: same contract, rows stay at their read's index
+    k = 20000
+    d_seqs = torch.from_numpy(seqs[:int(off[k])].copy()).cuda()
+    d_off = torch.from_numpy(off[:k + 1].astype(np.int64)).cuda()
+    d_rc = torch.from_numpy(rc[:k].astype(np.int32)).cuda()
+    stride = fops.shape[1]
+    d_rec = torch.zeros(k * 48, dtype=torch.uint8, device="cuda")
+    d_ops = torch.full((k * stride,), 0xAB, dtype=torch.uint8, device="cuda")
+    max_len = int(np.diff(off[:k + 1].astype(np.int64)).max())
+    eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), k, max_len,
+                           cabi.WANT_OPS | cabi.NO_SUMMARY | cabi.OPS_GAPPED_ONLY, d_rec.data_ptr(), d_ops.data_ptr(), stride)
+    eng.synchronize()
+    dops = d_ops.cpu().numpy().reshape(k, stride)
+    assert np.array_equal(d_rec.cpu().numpy().view(cabi.RECORD_DTYPE), frec[:k])
+    assert np.array_equal(dops[gapped[:k]], fops[:k][gapped[:k]]) and (dops[~gapped[:k]] == 0xAB).all()
 
 
 def test_speculative_chunks_are_validated(eng, tmp_path):

@@ -20,7 +20,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import cabi
-from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, RECORD_DTYPE, REVERSE, WANT_OPS, TreatError, check, lib)
+from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, OPS_GAPPED_ONLY, RECORD_DTYPE, REVERSE, WANT_OPS, TreatError, check, lib)
 
 __all__ = [
     "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
@@ -296,6 +296,8 @@ class Alignment:
 
     def ops(self) -> List[int]:
         n = int(self._rec[0]["aln_len"])
+        if not int(self._rec[0]["indel"]):
+            return [0] * n  # base over base; with OPS_GAPPED_ONLY the row is not even written
         return [(int(self._ops[c >> 2]) >> (2 * (c & 3))) & 3 for c in range(n)]
 
     def gapped(self, tmpl_bases: str, frag_bases: str) -> Tuple[str, str]:
@@ -440,7 +442,7 @@ class Aligner:
         `reads` is a FastaBatch or an iterable of (id, seq)."""
         batch = reads if isinstance(reads, FastaBatch) else FastaBatch.from_records(reads)
         self._ensure_template(tmpl)
-        flags = (EXCLUDE_SNPS if excludeSnps else 0) | (WANT_OPS if want_ops else 0)
+        flags = (EXCLUDE_SNPS if excludeSnps else 0) | (WANT_OPS | OPS_GAPPED_ONLY if want_ops else 0)
         rec, ops = self.align_batch(batch.seqs, batch.offsets, batch.read_counts, flags)
         return [Alignment(rec[i], None if ops is None else ops[i], batch.seq(i), self) for i in range(len(batch))]
 

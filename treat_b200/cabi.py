@@ -17,6 +17,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TOO_LONG, ERR_NO_TEMPLATE, ERR_NO_DEVICE, ERR_TEMPLATE, ERR_IO = range(-1, -9, -1)
 FORWARD, REVERSE = 1, -1
 EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY, ONE_READ_PER_WARP, FULL_TRACEBACK_STORE = 0x1, 0x2, 0x4, 0x8, 0x10
+DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY = 0x20, 0x40, 0x80
 ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16

@@ -410,7 +410,7 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     int edit_stop = junc_start - 1;
     int junc_len = 0;
     uint32_t js_off = 0, js_len = 0;
-    uint32_t status = rflags;
+    uint32_t status = rflags & ~kFlagSameBases;
     if (junc_end > edit_stop) {
         junc_len = junc_end - edit_stop;
         if (has_mutation == 0 && !t0_all) {
@@ -494,8 +494,17 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     }
 
     // ---- traceback ops, 2 bits per column, in alignment order: a funnel shift of ops2 by pos ------
-    if (p.ops) {
-        uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + r * (uint64_t)p.ops_stride);
+    if (p.ops && (indel || !p.ops_gapped_only)) {
+        uint64_t row = r;
+        if (p.ops_idx) {  // compacted output: claim the next row
+            uint32_t k = 0;
+            if (lane == 0) {
+                k = atomicAdd(p.ops_count, 1u);
+                p.ops_idx[k] = (uint32_t)r;
+            }
+            row = __shfl_sync(FULL_MASK, k, 0);
+        }
+        uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + row * (uint64_t)p.ops_stride);
         const int nwords = (int)(p.ops_stride / 4);
         const int w0 = pos >> 4, sh = 2 * (pos & 15);
         const int avail = (int)(p.sm_ops / 4) - 1;  // ops2 words that exist (all zero past the alignment)
@@ -699,11 +708,11 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
     const int ops_words = (int)(p.sm_ops / 4);
     constexpr int P = CPL + 1;
     const int C = (int)p.band_chunks, B = C * P - 1;  // B < 0: nothing is certified, every read takes the full path
-    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
+    const uint32_t gw = blockIdx.x * nwarps + warp, nw = gridDim.x * nwarps;  // a launch holds < 2^32 reads (host check)
     dir_t *scratch = reinterpret_cast<dir_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
     unsigned long long ctr = 0;
 
-    auto issue = [&](uint64_t r, int slot) {
+    auto issue = [&](uint32_t r, int slot) {
         if (lane == 0) {
             const uint32_t n = p.n[r];
             const uint32_t cb = WIDE ? align16(n) : align16((n + 3) / 4);
@@ -716,15 +725,19 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
         }
     };
 
+    // the reads of this launch: all of them, or the ones k_same_bases listed
+    const uint32_t total = p.list ? *p.list_count : (uint32_t)p.N;
+    auto read_at = [&](uint32_t u) -> uint32_t { return p.list ? p.list[u] : u; };
     uint32_t it = 0;
-    if (gw < p.N) issue(gw, 0);
-    for (uint64_t r = gw; r < p.N; r += nw, it++) {
+    if (gw < total) issue(read_at(gw), 0);
+    for (uint32_t u = gw; u < total; u += nw, it++) {
         const int slot = it & 1;
         const uint32_t parity = (it >> 1) & 1;
+        const uint32_t r = read_at(u);
         const int n = (int)p.n[r];
         const uint32_t rflags = p.rflags[r];
         __syncwarp();
-        if (r + nw < p.N) issue(r + nw, slot ^ 1);  // prefetch the next read of this warp
+        if (nw < total - u) issue(read_at(u + nw), slot ^ 1);  // prefetch the next read of this warp
         mbar_wait(&ws.bar[slot], parity);
         if (n > (int)p.ncap) {  // only on a speculative launch (ncap guessed): the host re-runs the chunk
             if (lane == 0 && p.skipped) atomicAdd(p.skipped, 1u);
@@ -835,39 +848,44 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
     const int ops_words = (int)(p.sm_ops / 4);
     constexpr int P = CPL + 1;
     const int C = (int)p.band_chunks, B = C * P - 1;
-    const uint64_t npairs = (p.N + 1) / 2;
-    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
+    // the reads of this launch: all of them, or the ones k_same_bases listed; pair q = reads 2q, 2q+1 of that sequence
+    const uint32_t total = p.list ? *p.list_count : (uint32_t)p.N;  // a launch holds < 2^32 reads (host check)
+    auto read_at = [&](uint32_t u) -> uint32_t { return p.list ? p.list[u] : u; };
+    const uint32_t npairs = total / 2 + (total & 1u);
+    const uint32_t gw = blockIdx.x * nwarps + warp, nw = gridDim.x * nwarps;
     uint32_t *scratch = reinterpret_cast<uint32_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
     unsigned long long ctr = 0;
 
-    auto issue = [&](uint64_t q, int slot) {
+    auto issue = [&](uint32_t q, int slot) {
         if (lane == 0) {
             uint8_t *dst = ws.stage + slot * slot_bytes;
-            const uint64_t r0 = 2 * q;
+            const uint32_t r0 = read_at(2 * q);
             const uint32_t n0 = p.n[r0];
-            const bool has1 = r0 + 1 < p.N;
-            const uint32_t n1 = has1 ? p.n[r0 + 1] : 0u;
+            const bool has1 = 2 * q + 1 < total;
+            const uint32_t r1 = has1 ? read_at(2 * q + 1) : r0;
+            const uint32_t n1 = has1 ? p.n[r1] : 0u;
             const uint32_t cb0 = align16((n0 + 3) / 4), cc0 = align16(n0 + 1);
             const uint32_t cb1 = has1 ? align16((n1 + 3) / 4) : 0u, cc1 = has1 ? align16(n1 + 1) : 0u;
             fence_proxy_async();
             mbar_expect_tx(&ws.bar[slot], cb0 + cc0 + cb1 + cc1);
             if (cb0) bulk_g2s(dst, p.bases + r0 * (uint64_t)p.bases_stride, cb0, &ws.bar[slot]);
             bulk_g2s(dst + p.sm_stage_b, p.counts + r0 * (uint64_t)p.counts_stride, cc0, &ws.bar[slot]);
-            if (cb1) bulk_g2s(dst + read_bytes, p.bases + (r0 + 1) * (uint64_t)p.bases_stride, cb1, &ws.bar[slot]);
-            if (cc1) bulk_g2s(dst + read_bytes + p.sm_stage_b, p.counts + (r0 + 1) * (uint64_t)p.counts_stride, cc1, &ws.bar[slot]);
+            if (cb1) bulk_g2s(dst + read_bytes, p.bases + r1 * (uint64_t)p.bases_stride, cb1, &ws.bar[slot]);
+            if (cc1) bulk_g2s(dst + read_bytes + p.sm_stage_b, p.counts + r1 * (uint64_t)p.counts_stride, cc1, &ws.bar[slot]);
         }
     };
 
     uint32_t it = 0;
     if (gw < npairs) issue(gw, 0);
-    for (uint64_t q = gw; q < npairs; q += nw, it++) {
+    for (uint32_t q = gw; q < npairs; q += nw, it++) {
         const int slot = it & 1;
         const uint32_t parity = (it >> 1) & 1;
-        const uint64_t r0 = 2 * q;
-        const bool has1 = r0 + 1 < p.N;
-        const int n0 = (int)p.n[r0], n1 = has1 ? (int)p.n[r0 + 1] : 0;
+        const uint32_t r0 = read_at(2 * q);
+        const bool has1 = 2 * q + 1 < total;
+        const uint32_t r1 = has1 ? read_at(2 * q + 1) : r0;
+        const int n0 = (int)p.n[r0], n1 = has1 ? (int)p.n[r1] : 0;
         __syncwarp();
-        if (q + nw < npairs) issue(q + nw, slot ^ 1);  // prefetch the next pair of this warp
+        if (nw < npairs - q) issue(q + nw, slot ^ 1);  // prefetch the next pair of this warp
         mbar_wait(&ws.bar[slot], parity);
         if (n0 > (int)p.ncap || n1 > (int)p.ncap) {  // only on a speculative launch: the host re-runs the chunk
             if (lane == 0 && p.skipped) atomicAdd(p.skipped, 1u);
@@ -937,13 +955,67 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
                         return (scratch[tt * 32 + ln] >> sh) & 0xffffu;
                     },
                     ws.ops2, m, n, lane, ngaps);
-            finish_read<cnt_t>(p, cs, ws, lane, r0 + h, n, p.rflags[r0 + h], score, pos, ngaps, rcount,
+            const uint32_t r = h ? r1 : r0;
+            finish_read<cnt_t>(p, cs, ws, lane, r, n, p.rflags[r], score, pos, ngaps, rcount,
                                [&](int fi) {
                                    const int c = pc[fi];
                                    return h ? c % 5 : c / 5;
                                },
                                ctr);
         }
+    }
+    flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2s: reads whose stripped bases equal the template's (kFlagSameBases, set by k_pack) need no DP.
+// The identity alignment scores m, every other path scores at most m - 2 (one gap costs a base of
+// each sequence, a mismatch costs 2), so it is the unique optimum and nwalgo's traceback returns it
+// whatever its tie order: score = m, no gap, no mismatch, read base i sits on template base i.
+// Such a read goes straight to the editing-site assembly, reading its counts from HBM; every other
+// read is appended to p.list for the DP kernels.  One warp per read, next read's loads in flight.
+// ------------------------------------------------------------------------------------------
+constexpr int kSameWarps = 16;
+
+__global__ void __launch_bounds__(kSameWarps * 32) k_same_bases(const __grid_constant__ AlignParams p)
+{
+    using cnt_t = uint8_t;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int m = p.t.m;
+
+    const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, (int)p.cpl);  // no profile, no dump rows in this plan
+    load_template(cs, p, (int)p.cpl);
+    uint32_t *zero = reinterpret_cast<uint32_t *>(smem + p.sm_tmpl_bytes);  // the all-match ops of such a read
+    for (uint32_t i = threadIdx.x; i < p.sm_ops / 4; i += blockDim.x) zero[i] = 0u;
+    uint4 *stage = reinterpret_cast<uint4 *>(smem + p.sm_tmpl_bytes + p.sm_ops + (size_t)warp * p.sm_cnt_stage);
+    WarpSmem ws{};
+    ws.ops2 = zero;
+    __syncthreads();
+
+    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
+    const bool mine = lane * 16 < m + 1;  // this lane's 16 counts exist
+    unsigned long long ctr = 0;
+    auto fetch = [&](uint64_t r, uint32_t &f, uint4 &c) {
+        f = p.rflags[r];
+        c = mine ? reinterpret_cast<const uint4 *>(p.counts + r * (uint64_t)p.counts_stride)[lane] : make_uint4(0, 0, 0, 0);
+    };
+    uint32_t f = 0, fn = 0;
+    uint4 c = make_uint4(0, 0, 0, 0), cn = c;
+    if (gw < p.N) fetch(gw, f, c);
+    for (uint64_t r = gw; r < p.N; r += nw) {
+        if (r + nw < p.N) fetch(r + nw, fn, cn);
+        if (f & kFlagSameBases) {
+            __syncwarp();
+            stage[lane] = c;
+            __syncwarp();
+            finish_read<cnt_t>(p, cs, ws, lane, r, m, f, /*score*/ m, /*pos*/ m, /*ngaps*/ 0,
+                               reinterpret_cast<const cnt_t *>(stage), [](int) { return 0; }, ctr);
+        } else if (lane == 0) {
+            p.list[atomicAdd(p.list_count, 1u)] = (uint32_t)r;
+        }
+        f = fn;
+        c = cn;
     }
     flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
 }
@@ -974,6 +1046,7 @@ int plan_align(AlignParams &p, bool wide)
     if (cpl < 0 || m < 1) return -1;
     const bool pair = !wide && cpl <= 7 && !p.force_single;
     p.pair = pair ? 1 : 0;
+    p.cpl = (uint32_t)cpl;
     const uint32_t ncap = p.ncap;
     const uint32_t csz = wide ? 4u : 1u;
     const uint32_t dsz = pair ? 4u : (cpl <= 7 ? 2u : 4u);
@@ -1058,6 +1131,29 @@ int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_opti
     case 15: return launch_cpl<15>(p, wide, num_sms, max_smem_optin, stream);
     default: return -1001;
     }
+}
+
+int launch_same_bases(const AlignParams &planned, int num_sms, void *stream)
+{
+    AlignParams p = planned;
+    const int m = p.t.m;
+    const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
+    p.sm_prof_bytes = 0;
+    p.sm_tmpl_bytes = align16(32 * p.cpl) + align16((uint32_t)(p.t.K * p.t.len_pad)) + align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) +
+                      align16(8u * sum_len);
+    p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
+    p.sm_ops = align16((((uint32_t)(2 * m) + 15) / 16 + 2) * 4);
+    p.sm_cnt_stage = 512;  // 32 lanes x 16 counts >= m + 1
+    if (p.ncap < (uint32_t)m) p.ncap = (uint32_t)m;
+    const size_t smem = p.sm_tmpl_bytes + p.sm_ops + (size_t)kSameWarps * p.sm_cnt_stage;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_same_bases, kSameWarps * 32, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    uint64_t blocks = (p.N + kSameWarps - 1) / kSameWarps;
+    if (blocks > (uint64_t)num_sms * per_sm) blocks = (uint64_t)num_sms * per_sm;
+    if (blocks == 0) return 0;
+    k_same_bases<<<(unsigned)blocks, kSameWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
 }
 
 template <int CPL>

@@ -21,6 +21,7 @@ namespace {
 constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
 constexpr uint64_t kChunkReads = 1u << 16;  // reads per pipelined chunk of treat_b200_align_batch
 constexpr int kSlots = 4;                   // most chunks in flight: H2D, kernels and D2H of different chunks overlap
+constexpr size_t kScalarBytes = 32;         // per-slot device scalars (8 words)
 
 struct DevBuf {
     void *p = nullptr;
@@ -48,18 +49,29 @@ struct DevBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops, summary;
+    DevBuf list;     // reads that need the DP (written by k_same_bases, read by the align kernels)
+    DevBuf ops_idx;  // OPS_GAPPED_ONLY: read index of every compacted ops row
+    // OPS_GAPPED_ONLY: pinned landing buffers of the compacted rows and their read indices
+    uint8_t *h_gap_rows = nullptr;
+    uint32_t *h_gap_idx = nullptr;
+    size_t gap_rows_cap = 0, gap_idx_cap = 0;
+    uint32_t gap_head = 0;     // rows copied ahead of knowing how many there are
+    bool scatter = false;      // compacted rows of this chunk still have to be placed into the caller's buffer
     DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
-    uint32_t *scalars = nullptr;    // device [4]: max n, any saturated run, reads skipped by a speculative launch
-    uint32_t *h_scalars = nullptr;  // pinned [4]
+    uint32_t *scalars = nullptr;    // device [8]: max n, any saturated run, reads skipped by a speculative launch, reads listed
+                                    // for the DP, compacted ops rows
+    uint32_t *h_scalars = nullptr;  // pinned [8]
     // chunk whose speculative launch still has to be validated (treat_b200_align_batch)
     bool pending = false;
     uint64_t c0 = 0, cn = 0, b0 = 0;
     uint32_t max_len = 0, dev_stride = 0;
     void release()
     {
-        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch}) b->release();
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &ops_idx}) b->release();
         if (scalars) cudaFree(scalars);
         if (h_scalars) cudaFreeHost(h_scalars);
+        if (h_gap_rows) cudaFreeHost(h_gap_rows);
+        if (h_gap_idx) cudaFreeHost(h_gap_idx);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -78,8 +90,10 @@ struct treat_b200_ctx {
     bool tmpl_wide = false;  // template needs the wide path (non-alphabet base or count >= 255)
     TemplateDev td{};
     DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut;
+    DevBuf d_tpk;  // template bases in the packed-read format (16 codes per word): k_pack marks reads that equal it
     uint32_t band_rows = 0;  // 0 = default window
     uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
+    uint32_t gap_hint = 0;   // most gapped reads seen in a chunk: sizes the ahead-of-time copy of compacted ops rows
     uint32_t *d_dbg = nullptr;  // bounds-check flags (only written by TREAT_B200_CHECKS builds)
     std::vector<uint8_t> lut;
     uint64_t *d_summary = nullptr;
@@ -168,7 +182,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut}) b->release();
+    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->d_tpk}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     for (Slot &sl : ctx->slot) sl.release();
@@ -244,6 +258,13 @@ int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m
     CK(ctx, cudaMemcpy(ctx->d_tc32.p, tc32.data(), tc32.size() * 4, cudaMemcpyHostToDevice));
     CK(ctx, cudaMemcpy(ctx->d_alt.p, alt.data(), alt.size() * 4, cudaMemcpyHostToDevice));
     CK(ctx, cudaMemcpy(ctx->d_lut.p, lut.data(), 256, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint32_t> tpk((size_t)(m + 15) / 16, 0u);
+        if (!wide)
+            for (int i = 0; i < m; i++) tpk[i >> 4] |= (uint32_t)tb[i] << (2 * (i & 15));
+        CK(ctx, ctx->d_tpk.reserve(tpk.size() * 4));
+        CK(ctx, cudaMemcpy(ctx->d_tpk.p, tpk.data(), tpk.size() * 4, cudaMemcpyHostToDevice));
+    }
     ctx->lut = lut;
     ctx->tmpl_wide = wide;
     ctx->td = TemplateDev{};
@@ -342,8 +363,8 @@ int treat_b200_packed_layout(const treat_b200_ctx *ctx, uint64_t N, uint32_t max
 
 static int ensure_scalars(treat_b200_ctx *ctx, Slot &s)
 {
-    if (!s.scalars) CK(ctx, cudaMalloc((void **)&s.scalars, 16));
-    if (!s.h_scalars) CK(ctx, cudaMallocHost((void **)&s.h_scalars, 16));
+    if (!s.scalars) CK(ctx, cudaMalloc((void **)&s.scalars, kScalarBytes));
+    if (!s.h_scalars) CK(ctx, cudaMallocHost((void **)&s.h_scalars, kScalarBytes));
     return TREAT_B200_OK;
 }
 
@@ -366,6 +387,8 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     pp.lut = ctx->td.lut;
     pp.edit_base = ctx->td.edit_base;
     pp.scalars = d_scalars;
+    pp.tpk = (!dst->wide && !ctx->tmpl_wide) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
+    pp.tm = (uint32_t)ctx->td.m;
     int e = launch_pack(pp, dst->wide != 0, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: read too long for shared-memory staging");
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_pack launch: ") + cudaGetErrorString((cudaError_t)e));
@@ -373,11 +396,25 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     return TREAT_B200_OK;
 }
 
+// optional device-side plumbing of one align launch
+struct AlignOpts {
+    uint64_t *summary = nullptr;      // accumulate here instead of the context's summary
+    uint32_t *skipped = nullptr;      // speculative launch: counts the reads it could not hold
+    DevBuf *list = nullptr;           // with list_count: finish reads marked by k_pack without a DP, align only the listed rest
+    uint32_t *list_count = nullptr;   //   (must be zero on entry)
+    uint32_t *ops_idx = nullptr;      // with ops_count: compact the ops rows (OPS_GAPPED_ONLY on the host-buffer path)
+    uint32_t *ops_count = nullptr;    //   (must be zero on entry)
+};
+
 static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t ncap, const uint32_t *d_read_count,
                     uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st,
-                    DevBuf &scratch, uint64_t *summary_override = nullptr, uint32_t *d_skipped = nullptr)
+                    DevBuf &scratch, const AlignOpts &o = AlignOpts())
 {
+    uint64_t *summary_override = o.summary;
+    uint32_t *d_skipped = o.skipped, *d_list_count = o.list_count;
+    DevBuf *list = o.list;
     if (src->N == 0) return TREAT_B200_OK;
+    if (src->N > 0x7fffffffull) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: more than 2^31 reads in one launch");
     const bool wide = src->wide != 0;
     if (!wide && ctx->tmpl_wide)
         return fail(ctx, TREAT_B200_ERR_INVALID, "align: this template needs wide-packed reads (wide=1)");
@@ -398,6 +435,11 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     ap.rec = d_rec;
     ap.ops = (flags & TREAT_B200_WANT_OPS) ? d_ops : nullptr;
     ap.ops_stride = ops_stride;
+    ap.ops_gapped_only = (flags & TREAT_B200_OPS_GAPPED_ONLY) ? 1u : 0u;
+    if (ap.ops && ap.ops_gapped_only && o.ops_idx && o.ops_count) {
+        ap.ops_idx = o.ops_idx;
+        ap.ops_count = o.ops_count;
+    }
     ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : (summary_override ? summary_override : ctx->d_summary);
     ap.skipped = d_skipped;
     ap.dbg = ctx->d_dbg;
@@ -419,6 +461,16 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
             CK(ctx, scratch.reserve(need));
         }
         ap.scratch = scratch.p;
+    }
+    // reads marked by k_pack as equal to the template are finished without a DP; the align kernel gets the rest.
+    // *d_list_count must be zero on entry (the callers clear the slot's scalars before the pack).
+    if (list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ)) {
+        CK(ctx, list->reserve(src->N * 4));
+        ap.list = (uint32_t *)list->p;
+        ap.list_count = d_list_count;
+        int e0 = launch_same_bases(ap, ctx->num_sms, st);
+        if (e0) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_same_bases launch: ") + cudaGetErrorString((cudaError_t)e0));
+        ctx->launches++;
     }
     int e = launch_align(ap, wide, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000 || e == -1001)
@@ -442,7 +494,7 @@ int treat_b200_pack_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     int rc = ensure_scalars(ctx, ctx->dev_slot);
     if (rc) return rc;
-    CK(ctx, cudaMemsetAsync(ctx->dev_slot.scalars, 0, 16, st));
+    CK(ctx, cudaMemsetAsync(ctx->dev_slot.scalars, 0, kScalarBytes, st));
     return do_pack(ctx, d_seqs, d_seq_off, 0, dst, ctx->dev_slot.scalars, st);
 }
 
@@ -457,6 +509,16 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
     CK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     // n <= raw length: size the launch for max_len (callers that know max n can pass it as max_len)
+    if (flags & TREAT_B200_USE_PACK_MARKS) {
+        // the caller vouches that src was packed under the current template: finish the marked reads without a DP
+        int rc = ensure_scalars(ctx, ctx->dev_slot);
+        if (rc) return rc;
+        CK(ctx, cudaMemsetAsync(ctx->dev_slot.scalars + 3, 0, 4, st));
+        AlignOpts o;
+        o.list = &ctx->dev_slot.list;
+        o.list_count = ctx->dev_slot.scalars + 3;
+        return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st, ctx->dev_slot.scratch, o);
+    }
     return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st, ctx->dev_slot.scratch);
 }
 
@@ -471,6 +533,19 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
                      uint32_t *ops_stride_used = nullptr, uint32_t spec_ncap = 0)
 {
     const bool wide = ctx->tmpl_wide || force_wide;
+    // ops into the slot's own buffer (host-buffer path): gapped-only rows are compacted there
+    const bool slot_own_ops = (flags & TREAT_B200_WANT_OPS) && d_ops == nullptr;
+    if (slot_own_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY)) CK(ctx, s.ops_idx.reserve(N * 4));
+    auto opts = [&](bool compact) {
+        AlignOpts o;
+        o.list = &s.list;
+        o.list_count = s.scalars + 3;
+        if (compact && (flags & TREAT_B200_OPS_GAPPED_ONLY)) {
+            o.ops_idx = (uint32_t *)s.ops_idx.p;
+            o.ops_count = s.scalars + 4;
+        }
+        return o;
+    };
     treat_b200_packed pk;
     int rc = treat_b200_packed_layout(ctx, N, max_len, wide, &pk);
     if (rc) return fail(ctx, rc, "align: read longer than 16384");
@@ -486,13 +561,13 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     pk.d_raw_len = (uint32_t *)s.raw_len.p;
     rc = ensure_scalars(ctx, s);
     if (rc) return rc;
-    CK(ctx, cudaMemsetAsync(s.scalars, 0, 16, st));
+    CK(ctx, cudaMemsetAsync(s.scalars, 0, kScalarBytes, st));
     rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st);
     if (rc) return rc;
     if (spec_ncap) {
         const uint32_t ncap = std::min(spec_ncap, max_len);
-        if ((flags & TREAT_B200_WANT_OPS) && ops_stride == 0) {
-            ops_stride = a16(((uint32_t)ctx->td.m + ncap + 3) / 4);
+        if ((flags & TREAT_B200_WANT_OPS) && d_ops == nullptr) {
+            if (ops_stride == 0) ops_stride = a16(((uint32_t)ctx->td.m + ncap + 3) / 4);
             CK(ctx, s.ops.reserve(N * (size_t)ops_stride));
             d_ops = (uint8_t *)s.ops.p;
         }
@@ -506,9 +581,12 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
             }
             slot_sum = (uint64_t *)s.summary.p;
         }
-        rc = do_align(ctx, &pk, ncap, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, slot_sum, s.scalars + 2);
+        AlignOpts o = opts(slot_own_ops);
+        o.summary = slot_sum;
+        o.skipped = s.scalars + 2;
+        rc = do_align(ctx, &pk, ncap, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, o);
         if (rc) return rc;
-        CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, 16, cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, st));
         return TREAT_B200_OK;
     }
     CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, 8, cudaMemcpyDeviceToHost, st));
@@ -517,13 +595,13 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     ctx->ncap_hint = std::max(ctx->ncap_hint, max_n);
     if (saturated) *saturated = s.h_scalars[1] != 0;
     if (!wide && s.h_scalars[1]) return TREAT_B200_OK;  // caller re-runs this chunk on the wide path
-    if ((flags & TREAT_B200_WANT_OPS) && ops_stride == 0) {
-        ops_stride = a16(((uint32_t)ctx->td.m + max_n + 3) / 4);
+    if ((flags & TREAT_B200_WANT_OPS) && d_ops == nullptr) {
+        if (ops_stride == 0) ops_stride = a16(((uint32_t)ctx->td.m + max_n + 3) / 4);
         CK(ctx, s.ops.reserve(N * (size_t)ops_stride));
         d_ops = (uint8_t *)s.ops.p;
     }
     if (ops_stride_used) *ops_stride_used = ops_stride;
-    return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch);
+    return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, opts(slot_own_ops));
 }
 
 int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
@@ -556,8 +634,11 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     if (N == 0) return TREAT_B200_OK;
     CK(ctx, cudaSetDevice(ctx->device));
     const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
-    for (int i = 0; i < kSlots; i++)
+    const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);  // only gapped reads' rows cross the bus
+    for (int i = 0; i < kSlots; i++) {
         if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
+        ctx->slot[i].pending = ctx->slot[i].scatter = false;  // nothing carries over from a call that failed half-way
+    }
 
     int rc = TREAT_B200_OK;
     uint64_t chunk_idx = 0;
@@ -571,13 +652,71 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     double t_wait_slot = 0, t_enqueue = 0;
     int redone = 0;
 
+    // pinned landing buffers for `rows` compacted ops rows of a slot
+    auto reserve_gap = [&](Slot &s, uint32_t rows) -> int {
+        const size_t need_rows = (size_t)rows * s.dev_stride, need_idx = (size_t)rows * 4;
+        if (need_rows > s.gap_rows_cap) {
+            CK(ctx, cudaStreamSynchronize(s.stream));
+            if (s.h_gap_rows) cudaFreeHost(s.h_gap_rows);
+            s.h_gap_rows = nullptr;
+            s.gap_rows_cap = 0;
+            CK(ctx, cudaMallocHost((void **)&s.h_gap_rows, need_rows + need_rows / 4 + 4096));
+            s.gap_rows_cap = need_rows + need_rows / 4 + 4096;
+        }
+        if (need_idx > s.gap_idx_cap) {
+            CK(ctx, cudaStreamSynchronize(s.stream));
+            if (s.h_gap_idx) cudaFreeHost(s.h_gap_idx);
+            s.h_gap_idx = nullptr;
+            s.gap_idx_cap = 0;
+            CK(ctx, cudaMallocHost((void **)&s.h_gap_idx, need_idx + need_idx / 4 + 4096));
+            s.gap_idx_cap = need_idx + need_idx / 4 + 4096;
+        }
+        return TREAT_B200_OK;
+    };
     // copy a finished chunk's results to the caller's buffers (async on the slot stream)
     auto copy_out = [&](Slot &s) -> int {
         CK(ctx, cudaMemcpyAsync(rec + s.c0, s.rec.p, s.cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, s.stream));
         // only the bytes the batch can use cross the bus: rows of dev_stride <= ops_stride bytes
-        if (want_ops)
+        if (want_ops && !sparse)
             CK(ctx, cudaMemcpy2DAsync(ops + s.c0 * (size_t)ops_stride, ops_stride, s.ops.p, s.dev_stride, s.dev_stride, s.cn,
                                       cudaMemcpyDeviceToHost, s.stream));
+        if (sparse) {
+            // the number of gapped reads is only known on the device: copy a guess now, the rest (if any) in place_rows
+            const uint32_t head = (uint32_t)std::min<uint64_t>(s.cn, std::max<uint32_t>(4096u, 2u * ctx->gap_hint));
+            int r = reserve_gap(s, head);
+            if (r) return r;
+            CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, s.stream));
+            CK(ctx, cudaMemcpyAsync(s.h_gap_idx, s.ops_idx.p, head * 4ull, cudaMemcpyDeviceToHost, s.stream));
+            CK(ctx, cudaMemcpyAsync(s.h_gap_rows, s.ops.p, head * (size_t)s.dev_stride, cudaMemcpyDeviceToHost, s.stream));
+            s.gap_head = head;
+            s.scatter = true;
+        }
+        return TREAT_B200_OK;
+    };
+    // OPS_GAPPED_ONLY: move the compacted rows of a finished chunk (stream idle) into the caller's ops buffer
+    auto place_rows = [&](Slot &s) -> int {
+        if (!s.scatter) return TREAT_B200_OK;
+        s.scatter = false;
+        const uint32_t cnt = s.h_scalars[4];
+        ctx->gap_hint = std::max(ctx->gap_hint, cnt);
+        if (cnt > s.gap_head) {  // more gapped reads than guessed: fetch the remaining rows now
+            const uint32_t head = s.gap_head;
+            std::vector<uint8_t> keep_rows(s.h_gap_rows, s.h_gap_rows + head * (size_t)s.dev_stride);
+            std::vector<uint32_t> keep_idx(s.h_gap_idx, s.h_gap_idx + head);
+            int r = reserve_gap(s, cnt);
+            if (r) return r;
+            memcpy(s.h_gap_rows, keep_rows.data(), keep_rows.size());
+            memcpy(s.h_gap_idx, keep_idx.data(), keep_idx.size() * 4);
+            CK(ctx, cudaMemcpyAsync(s.h_gap_idx + head, (uint32_t *)s.ops_idx.p + head, (cnt - head) * 4ull, cudaMemcpyDeviceToHost, s.stream));
+            CK(ctx, cudaMemcpyAsync(s.h_gap_rows + head * (size_t)s.dev_stride, (uint8_t *)s.ops.p + head * (size_t)s.dev_stride,
+                                    (cnt - head) * (size_t)s.dev_stride, cudaMemcpyDeviceToHost, s.stream));
+            CK(ctx, cudaStreamSynchronize(s.stream));
+        }
+        for (uint32_t k = 0; k < cnt; k++) {
+            uint8_t *dst = ops + (s.c0 + s.h_gap_idx[k]) * (size_t)ops_stride;
+            memcpy(dst, s.h_gap_rows + k * (size_t)s.dev_stride, s.dev_stride);
+            memset(dst + s.dev_stride, 0, ops_stride - s.dev_stride);
+        }
         return TREAT_B200_OK;
     };
     // pack + align with the exact max n (one 8-byte sync), wide re-run if an edit-base run saturated
@@ -593,9 +732,10 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     };
     // a speculative chunk is final once its stream is idle and nothing was skipped or saturated
     auto settle = [&](Slot &s) -> int {
-        if (!s.pending) return TREAT_B200_OK;
-        s.pending = false;
+        if (!s.pending && !s.scatter) return TREAT_B200_OK;
         CK(ctx, cudaStreamSynchronize(s.stream));
+        if (!s.pending) return place_rows(s);
+        s.pending = false;
         const uint32_t max_n = s.h_scalars[0], sat = s.h_scalars[1], skipped = s.h_scalars[2];
         ctx->ncap_hint = std::max(ctx->ncap_hint, max_n);
         const bool bad = skipped != 0 || (sat && !ctx->tmpl_wide);
@@ -605,14 +745,18 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
                 if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_merge_summary launch failed");
                 ctx->launches++;
             }
-            return TREAT_B200_OK;
+            return place_rows(s);
         }
         redone++;
+        s.scatter = false;  // the rows copied so far belong to the discarded launch
         if (!(flags & TREAT_B200_NO_SUMMARY))
             CK(ctx, cudaMemsetAsync(s.summary.p, 0, treat_b200_summary_len(ctx) * 8, s.stream));
         int r = run_exact(s);
         if (r) return r;
-        return copy_out(s);
+        if ((r = copy_out(s))) return r;
+        if (!s.scatter) return TREAT_B200_OK;
+        CK(ctx, cudaStreamSynchronize(s.stream));
+        return place_rows(s);
     };
 
     for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk_reads, chunk_idx++) {

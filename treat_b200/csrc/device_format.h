@@ -38,7 +38,13 @@ struct PackParams {
     const uint8_t *lut;
     uint8_t edit_base;
     uint32_t *scalars;      // [0] max n (atomicMax), [1] any saturated edit-base run
+    const uint32_t *tpk;    // packed path: the template's bases in the packed-read format (may be null: no marks)
+    uint32_t tm;            // template bases
 };
+
+// internal bit of the per-read flag byte written by k_pack: the read's stripped bases equal the template's
+// (n == m, every code equal).  Never reaches treat_b200_record.status.
+constexpr uint32_t kFlagSameBases = 0x80u;
 
 struct AlignParams {
     // packed reads
@@ -76,11 +82,24 @@ struct AlignParams {
     uint32_t band_chunks;        // C: lane l keeps fill chunk u iff |u - l| <= C
     void *scratch;               // global scratch for full fills: [CTAs x warps][scratch_stride] words
     uint32_t scratch_stride;
+    // read selection.  k_same_bases: reads whose flag byte lacks kFlagSameBases are appended to list/list_count.
+    // k_align / k_align2: when list is set, the reads to align are list[0 .. *list_count) instead of 0 .. N-1.
+    uint32_t *list;
+    uint32_t *list_count;
+    // ops output.  ops_gapped_only: rows of reads without a gap (all-zero rows) are not written.  ops_idx set:
+    // the written rows are compacted: row k = atomicAdd(ops_count) holds the ops of read ops_idx[k].
+    uint32_t ops_gapped_only;
+    uint32_t *ops_idx;
+    uint32_t *ops_count;
+    uint32_t cpl;                // template columns per lane (sizes the template section)
+    uint32_t sm_cnt_stage;       // k_same_bases: bytes per warp for the staged edit-site counts
 };
 
 // launchers (kernels.cu)
 int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
 int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
+// K2s: finishes the reads marked kFlagSameBases without a DP and lists the others (p is the plan_align'ed block)
+int launch_same_bases(const AlignParams &p, int num_sms, void *stream);
 // fills the shared-memory geometry of p for (m, K, ncap, wide); returns columns-per-lane or -1
 int plan_align(AlignParams &p, bool wide);
 int align_warps(const AlignParams &p, int max_smem);

@@ -270,8 +270,10 @@ Alignment Alignment::FromRecord(const treat_b200_record &r, const uint8_t *packe
         std::transform(a.JuncSeq.begin(), a.JuncSeq.end(), a.JuncSeq.begin(), upper);
     }
     if (packed_ops) {
-        a.Ops.resize(r.aln_len);
-        for (uint32_t c = 0; c < r.aln_len; c++) a.Ops[c] = (packed_ops[c >> 2] >> (2 * (c & 3))) & 3u;
+        // a read without a gap aligns base over base: its row is all zero and, with TREAT_B200_OPS_GAPPED_ONLY, not even written
+        a.Ops.assign(r.aln_len, (uint8_t)TREAT_B200_OP_MATCH);
+        if (r.indel)
+            for (uint32_t c = 0; c < r.aln_len; c++) a.Ops[c] = (packed_ops[c >> 2] >> (2 * (c & 3))) & 3u;
     }
     return a;
 }
@@ -579,7 +581,8 @@ bool Aligner::AlignBatch(const FastaBatch &reads, bool excludeSnps, bool wantOps
     std::vector<treat_b200_record> rec(N);
     std::vector<uint8_t> ops(wantOps ? (size_t)N * stride : 0);
     static const uint8_t kEmpty = 0;
-    const uint32_t flags = (excludeSnps ? TREAT_B200_EXCLUDE_SNPS : 0) | (wantOps ? TREAT_B200_WANT_OPS : 0);
+    // FromRecord never reads the (all-zero) ops row of a read without a gap, so only gapped reads' rows need to come back
+    const uint32_t flags = (excludeSnps ? TREAT_B200_EXCLUDE_SNPS : 0) | (wantOps ? TREAT_B200_WANT_OPS | TREAT_B200_OPS_GAPPED_ONLY : 0);
     int rc = treat_b200_align_batch(ctx_, reads.seqs.empty() ? &kEmpty : reads.seqs.data(), reads.offsets.data(),
                                     reads.read_counts.data(), N, flags, rec.data(), wantOps ? ops.data() : nullptr, stride);
     if (rc != TREAT_B200_OK) {

@@ -125,15 +125,21 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
         const bool any_sat = __any_sync(FULL_MASK, sat), any_wide = __any_sync(FULL_MASK, widec);
         // bases
         uint32_t *gb = reinterpret_cast<uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
+        bool same = false;  // stripped bases equal the template's: such a read needs no DP (see k_same_bases)
         if (!WIDE) {
             const uint32_t nwords = align16((n + 3) / 4) / 4;
+            const uint32_t twords = (p.tm + 15) / 16;
+            bool eq = p.tpk != nullptr && n == p.tm;
             for (uint32_t wi = lane; wi < nwords; wi += 32) {
                 // 16 codes (one byte each) -> 16 x 2 bits: (x * M) >> 24 gathers the four 2-bit fields of a word
                 const uint4 x = *reinterpret_cast<const uint4 *>(s_code + 16 * wi);
                 constexpr uint32_t M = 0x01041040u;
                 const uint32_t lo = __byte_perm(x.x * M, x.y * M, 0x0073), hi = __byte_perm(x.z * M, x.w * M, 0x0073);
-                gb[wi] = __byte_perm(lo, hi, 0x5410);
+                const uint32_t word = __byte_perm(lo, hi, 0x5410);
+                gb[wi] = word;
+                if (eq && wi < twords) eq = word == p.tpk[wi];  // codes past n are zero in both
             }
+            same = __all_sync(FULL_MASK, eq);
         } else {
             const uint32_t nwords = align16(n) / 4;
             const uint32_t *src = reinterpret_cast<const uint32_t *>(s_code);
@@ -148,7 +154,8 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
         }
         if (lane == 0) {
             p.n[r] = (uint16_t)n;
-            p.flags[r] = (uint8_t)((any_sat ? TREAT_B200_ST_SATURATED : 0) | (any_wide ? TREAT_B200_ST_WIDE_BASE : 0));
+            p.flags[r] = (uint8_t)((any_sat ? TREAT_B200_ST_SATURATED : 0) | (any_wide ? TREAT_B200_ST_WIDE_BASE : 0) |
+                                   (same ? kFlagSameBases : 0));
             p.raw_len[r] = L;
         }
         warp_max_n = max(warp_max_n, n);
