@@ -289,6 +289,66 @@ __device__ __forceinline__ int traceback(GetW getw, uint32_t *ops2, int m, int n
 }
 
 // ------------------------------------------------------------------------------------------
+// the 48-byte record and the summary counters of one read (align.go:41-55, stats.go:140-187, handlers.go:203-215)
+// ------------------------------------------------------------------------------------------
+template <typename cnt_t>
+__device__ __forceinline__ void emit_result(const AlignParams &p, const CtaSmem<cnt_t> &cs, int lane, uint64_t r, int n, int alen,
+                                            uint32_t status, int score, int edit_stop, int junc_start, int junc_end, int junc_len,
+                                            int has_mutation, int alt_editing, int mism, bool indel, uint32_t js_off,
+                                            uint32_t js_len, unsigned long long &ctr)
+{
+    const int m = p.t.m;
+    const uint32_t read_count = p.read_count ? p.read_count[r] : 1u;
+
+    if (lane == 0) {
+        treat_b200_record o;
+        o.edit_stop = edit_stop + p.t.edit_offset;
+        o.junc_start = junc_start + p.t.edit_offset;
+        o.junc_end = junc_end + p.t.edit_offset;
+        o.junc_len = junc_len;
+        o.read_count = read_count;
+        o.has_mutation = (uint8_t)has_mutation;
+        o.alt_editing = (uint8_t)alt_editing;
+        o.mismatches = (uint8_t)(mism & 0xff);  // uint8 wraps (align.go:51,148)
+        o.indel = indel ? 1 : 0;
+        o.score = score;
+        o.junc_seq_off = js_off;
+        o.junc_seq_len = js_len;
+        o.aln_len = (uint16_t)alen;
+        o.n_bases = (uint16_t)n;
+        o.status = (uint8_t)status;
+        o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
+        o.raw_len = p.raw_len[r];
+        const uint4 *src = reinterpret_cast<const uint4 *>(&o);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.rec + r);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        dst[2] = src[2];
+    }
+
+    if (cs.sum_len) {
+        // cmd/treat/stats.go:140-187: lane L accumulates counter L of the summary header in a register
+        const unsigned long long rcw = read_count;
+        const int cls = has_mutation ? 2 : 1;
+        const int mm8 = mism & 0xff;
+        const int mcls = indel ? 3 : mm8 == 1 ? 5 : mm8 == 2 ? 6 : mm8 > 2 ? 4 : 0;
+        if (lane == 0 || lane == cls || (mcls && lane == mcls)) ctr += rcw;
+        if (lane == 7 || lane == 7 + cls || (mcls && lane == 7 + mcls) || lane == 14) ctr += 1ull;
+        if (lane == 15) ctr += (unsigned long long)m * (unsigned long long)n;
+        // cmd/treat/handlers.go:203-215: three histograms, one lane each
+        if (lane < 3 && !(edit_stop + p.t.edit_offset == p.t.tmpl_edit_stop && junc_len == 0)) {
+            const uint32_t bin = lane == 0 ? (uint32_t)(edit_stop + 2) : lane == 1 ? (uint32_t)junc_len : (uint32_t)(junc_end + 2);
+            if (bin < p.bins) {
+                const uint32_t idx = TREAT_B200_SUMMARY_HEADER + (uint32_t)lane * p.bins + bin;
+                const uint32_t old = atomicAdd(&cs.sum_lo[idx], read_count);
+                if (old + read_count < old) atomicAdd(&cs.sum_hi[idx], 1u);
+            }
+        }
+    }
+
+}
+
+// ------------------------------------------------------------------------------------------
 // everything after the traceback for one read: computeT, JSS/ESS/JES, alt editing, JuncSeq window,
 // record, summary counters, packed ops.  rbf(fi) returns the read base (code or byte) at index fi.
 // ------------------------------------------------------------------------------------------
@@ -445,53 +505,8 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
         edit_stop = junc_start;
         junc_len = 0;
     }
-    const uint32_t read_count = p.read_count ? p.read_count[r] : 1u;
-
-    if (lane == 0) {
-        treat_b200_record o;
-        o.edit_stop = edit_stop + p.t.edit_offset;
-        o.junc_start = junc_start + p.t.edit_offset;
-        o.junc_end = junc_end + p.t.edit_offset;
-        o.junc_len = junc_len;
-        o.read_count = read_count;
-        o.has_mutation = (uint8_t)has_mutation;
-        o.alt_editing = (uint8_t)alt_editing;
-        o.mismatches = (uint8_t)(mism & 0xff);  // uint8 wraps (align.go:51,148)
-        o.indel = indel ? 1 : 0;
-        o.score = score;
-        o.junc_seq_off = js_off;
-        o.junc_seq_len = js_len;
-        o.aln_len = (uint16_t)alen;
-        o.n_bases = (uint16_t)n;
-        o.status = (uint8_t)status;
-        o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
-        o.raw_len = p.raw_len[r];
-        const uint4 *src = reinterpret_cast<const uint4 *>(&o);
-        uint4 *dst = reinterpret_cast<uint4 *>(p.rec + r);
-        dst[0] = src[0];
-        dst[1] = src[1];
-        dst[2] = src[2];
-    }
-
-    if (cs.sum_len) {
-        // cmd/treat/stats.go:140-187: lane L accumulates counter L of the summary header in a register
-        const unsigned long long rcw = read_count;
-        const int cls = has_mutation ? 2 : 1;
-        const int mm8 = mism & 0xff;
-        const int mcls = indel ? 3 : mm8 == 1 ? 5 : mm8 == 2 ? 6 : mm8 > 2 ? 4 : 0;
-        if (lane == 0 || lane == cls || (mcls && lane == mcls)) ctr += rcw;
-        if (lane == 7 || lane == 7 + cls || (mcls && lane == 7 + mcls) || lane == 14) ctr += 1ull;
-        if (lane == 15) ctr += (unsigned long long)m * (unsigned long long)n;
-        // cmd/treat/handlers.go:203-215: three histograms, one lane each
-        if (lane < 3 && !(edit_stop + p.t.edit_offset == p.t.tmpl_edit_stop && junc_len == 0)) {
-            const uint32_t bin = lane == 0 ? (uint32_t)(edit_stop + 2) : lane == 1 ? (uint32_t)junc_len : (uint32_t)(junc_end + 2);
-            if (bin < p.bins) {
-                const uint32_t idx = TREAT_B200_SUMMARY_HEADER + (uint32_t)lane * p.bins + bin;
-                const uint32_t old = atomicAdd(&cs.sum_lo[idx], read_count);
-                if (old + read_count < old) atomicAdd(&cs.sum_hi[idx], 1u);
-            }
-        }
-    }
+    emit_result<cnt_t>(p, cs, lane, r, n, alen, status, score, edit_stop, junc_start, junc_end, junc_len, has_mutation, alt_editing,
+                       mism, indel, js_off, js_len, ctr);
 
     // ---- traceback ops, 2 bits per column, in alignment order: a funnel shift of ops2 by pos ------
     if (p.ops && (indel || !p.ops_gapped_only)) {
@@ -519,6 +534,123 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
         }
     }
     __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// The same assembly for a read whose bases equal the template's (score m, no gap, no mismatch: read site ti is
+// template site ti), on bytes: lane l holds the 16 edit-site counts [16 l, 16 l + 16) of the read and of the FE / PE
+// rows in registers; "highest site where FE differs" / "lowest site where PE differs" are a clz / ffs on the XOR
+// words plus one REDUX each.  Returns false (nothing written) when the junction start sits on the first site of an
+// alternative template's region (align.go:186-205): those few reads take finish_read.
+// ------------------------------------------------------------------------------------------
+struct SameLane {
+    uint32_t fe[4], pe[4], valid[4];  // template rows 0 / 1 and the byte mask of real sites, this lane's 16 sites
+};
+
+__device__ __forceinline__ SameLane load_same_lane(const CtaSmem<uint8_t> &cs, const AlignParams &p, int lane)
+{
+    SameLane sl;
+    const int base = 16 * lane;
+    uint4 f = make_uint4(0, 0, 0, 0), q = f;
+    if (base < p.t.len_pad) {
+        f = *reinterpret_cast<const uint4 *>(cs.tcount + base);
+        q = *reinterpret_cast<const uint4 *>(cs.tcount + p.t.len_pad + base);
+    }
+    sl.fe[0] = f.x, sl.fe[1] = f.y, sl.fe[2] = f.z, sl.fe[3] = f.w;
+    sl.pe[0] = q.x, sl.pe[1] = q.y, sl.pe[2] = q.z, sl.pe[3] = q.w;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int live = min(max(p.t.len - base - 4 * i, 0), 4);
+        sl.valid[i] = live >= 4 ? 0xffffffffu : (1u << (8 * live)) - 1u;
+    }
+    return sl;
+}
+
+// byte mask of the sites below `limit` in word i of the lane whose first site is `base`
+__device__ __forceinline__ uint32_t below_mask(int limit, int base, int i)
+{
+    const int k = min(max(limit - base - 4 * i, 0), 4);
+    return k >= 4 ? 0xffffffffu : (1u << (8 * k)) - 1u;
+}
+
+__device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<uint8_t> &cs, int lane, uint64_t r, uint32_t rflags,
+                                            const uint4 &c, const SameLane &sl, unsigned long long &ctr)
+{
+    const int m = p.t.m, n = m, len = p.t.len, K = p.t.K, base = 16 * lane;
+    const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+    uint32_t df[4], dp[4];  // non-zero byte: the read's count differs from FE / PE at that site
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        df[i] = (cw[i] ^ sl.fe[i]) & sl.valid[i];
+        dp[i] = (cw[i] ^ sl.pe[i]) & sl.valid[i];
+    }
+    // findJSS (align.go:183-205): the highest array index whose FE bit is clear
+    int hl = -1, ll = 0x7fffffff;
+    bool fe_match = false;  // some real site where the read agrees with FE
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (df[i]) hl = base + 4 * i + ((31 - __clz(df[i])) >> 3);
+        const uint32_t x = df[i] | ~sl.valid[i];
+        fe_match |= ((x - 0x01010101u) & ~x & 0x80808080u) != 0u;
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; i--)
+        if (dp[i]) ll = base + 4 * i + ((__ffs(dp[i]) - 1) >> 3);
+    const int hc0 = __reduce_max_sync(FULL_MASK, hl);
+    const bool t0_all = hc0 < 0;
+    int junc_start = t0_all ? len - 1 : (!__any_sync(FULL_MASK, fe_match) ? -1 : len - 1 - hc0);
+    if (K > 2 && junc_start >= 0 && junc_start < len) {
+        // does the junction start sit on the first site of an alternative template's region that matches there?
+        const int ti_s = len - 1 - junc_start, q = (ti_s >> 2) & 3;
+        const uint32_t wsel = q == 0 ? cw[0] : q == 1 ? cw[1] : q == 2 ? cw[2] : cw[3];
+        const uint32_t cstar = (__shfl_sync(FULL_MASK, wsel, ti_s >> 4) >> (8 * (ti_s & 3))) & 0xffu;
+        for (int k = 2; k < K; k++) {
+            if ((uint32_t)cs.tcount[k * p.t.len_pad + ti_s] == cstar) {
+                if (junc_start == cs.alt[k - 2]) return false;
+                break;
+            }
+        }
+    }
+    const int lc1r = __reduce_min_sync(FULL_MASK, ll);
+    int junc_end = lc1r == 0x7fffffff ? -1 : len - 1 - lc1r;
+    int edit_stop = junc_start - 1, junc_len = 0;
+    uint32_t js_off = 0, js_len = 0, status = rflags & ~kFlagSameBases;
+    if (junc_end > edit_stop) {
+        junc_len = junc_end - edit_stop;
+        if (!t0_all) {  // has_mutation is 0 for such a read
+            const int from = (len - 1) - junc_end, to = (len - 1) - edit_stop;
+            if (to > n + 1) {
+                status |= TREAT_B200_ST_REF_PANIC;
+            } else {
+                uint32_t sf = 0, st = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    sf = __dp4a(cw[i] & below_mask(from, base, i), 0x01010101u, sf);
+                    st = __dp4a(cw[i] & below_mask(to, base, i), 0x01010101u, st);
+                }
+                sf = __reduce_add_sync(FULL_MASK, sf);
+                st = __reduce_add_sync(FULL_MASK, st);
+                js_off = sf + (uint32_t)min(from, n);
+                js_len = st + (uint32_t)min(to, n) - js_off;
+                if (js_len == 0) js_off = 0;
+            }
+        }
+    } else if (junc_end < edit_stop) {
+        junc_end = edit_stop;
+        junc_len = 0;
+    }
+    if (t0_all) {
+        junc_end = junc_start;
+        edit_stop = junc_start;
+        junc_len = 0;
+    }
+    emit_result<uint8_t>(p, cs, lane, r, n, /*alen*/ m, status, /*score*/ m, edit_stop, junc_start, junc_end, junc_len,
+                         /*has_mutation*/ 0, /*alt_editing*/ 0, /*mism*/ 0, /*indel*/ false, js_off, js_len, ctr);
+    if (p.ops && !p.ops_gapped_only) {  // m match columns: an all-zero row
+        uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + r * (uint64_t)p.ops_stride);
+        for (int wi = lane; wi < (int)(p.ops_stride / 4); wi += 32) go[wi] = 0u;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -977,7 +1109,16 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
 // ------------------------------------------------------------------------------------------
 constexpr int kSameWarps = 16;
 
-__global__ void __launch_bounds__(kSameWarps * 32) k_same_bases(const __grid_constant__ AlignParams p)
+// the general assembly for the few same-bases reads that touch an alternative template's region (kept out of line:
+// it would otherwise set the register count of the whole kernel)
+__device__ __noinline__ void finish_same_general(const AlignParams &p, const CtaSmem<uint8_t> &cs, const WarpSmem &ws, int lane,
+                                                 uint64_t r, uint32_t rflags, const uint8_t *rcount, unsigned long long &ctr)
+{
+    const int m = p.t.m;
+    finish_read<uint8_t>(p, cs, ws, lane, r, m, rflags, /*score*/ m, /*pos*/ m, /*ngaps*/ 0, rcount, [](int) { return 0; }, ctr);
+}
+
+__global__ void __launch_bounds__(kSameWarps * 32, 2) k_same_bases(const __grid_constant__ AlignParams p)
 {
     using cnt_t = uint8_t;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -995,6 +1136,7 @@ __global__ void __launch_bounds__(kSameWarps * 32) k_same_bases(const __grid_con
 
     const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
     const bool mine = lane * 16 < m + 1;  // this lane's 16 counts exist
+    const SameLane sl = load_same_lane(cs, p, lane);
     unsigned long long ctr = 0;
     auto fetch = [&](uint64_t r, uint32_t &f, uint4 &c) {
         f = p.rflags[r];
@@ -1006,11 +1148,12 @@ __global__ void __launch_bounds__(kSameWarps * 32) k_same_bases(const __grid_con
     for (uint64_t r = gw; r < p.N; r += nw) {
         if (r + nw < p.N) fetch(r + nw, fn, cn);
         if (f & kFlagSameBases) {
-            __syncwarp();
-            stage[lane] = c;
-            __syncwarp();
-            finish_read<cnt_t>(p, cs, ws, lane, r, m, f, /*score*/ m, /*pos*/ m, /*ngaps*/ 0,
-                               reinterpret_cast<const cnt_t *>(stage), [](int) { return 0; }, ctr);
+            if (!finish_same(p, cs, lane, r, f, c, sl, ctr)) {  // an alternative template's region: the general assembly
+                __syncwarp();
+                stage[lane] = c;
+                __syncwarp();
+                finish_same_general(p, cs, ws, lane, r, f, reinterpret_cast<const cnt_t *>(stage), ctr);
+            }
         } else if (lane == 0) {
             p.list[atomicAdd(p.list_count, 1u)] = (uint32_t)r;
         }
