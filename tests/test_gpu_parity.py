@@ -328,6 +328,11 @@ def test_stage_calls_and_pack_marks(eng, tmp_path):
     m = t.m
     want = np.array([int(r["n_bases"]) == m and int(r["score"]) == m for r in hrec])
     assert np.array_equal(marks, want) and 0 < marks.sum() < N
+    # bit 6: same length, exactly one base differs (score m - 2: the diagonal is the unique optimum, no DP either)
+    one = (dev["flags"].cpu().numpy() & 0x40) != 0
+    want1 = np.array([int(r["n_bases"]) == m and int(r["score"]) == m - 2 for r in hrec])
+    assert np.array_equal(one, want1) and one.sum() > 0
+    assert (hrec["mismatches"][one] == 1).all() and (hrec["indel"][one] == 0).all()
     for fl in (0, cabi.USE_PACK_MARKS, cabi.USE_PACK_MARKS | cabi.ONE_READ_PER_WARP):
         d_rec = torch.zeros(N * 48, dtype=torch.uint8, device="cuda")
         d_ops = torch.full((N * stride,), 0xee, dtype=torch.uint8, device="cuda")

@@ -355,7 +355,7 @@ __device__ __forceinline__ void emit_result(const AlignParams &p, const CtaSmem<
 template <typename cnt_t, typename RbFn>
 __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<cnt_t> &cs, const WarpSmem &ws, int lane,
                                             uint64_t r, int n, uint32_t rflags, int score, int pos, int ngaps,
-                                            const cnt_t *rcount, RbFn rbf, unsigned long long &ctr)
+                                            const cnt_t *rcount, RbFn rbf, unsigned long long &ctr, int mism_known = -1)
 {
     const int m = p.t.m, len = p.t.len, len_pad = p.t.len_pad, K = p.t.K, n_alt = p.t.n_alt;
     const int tw = len_pad >> 5;
@@ -369,7 +369,9 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     // ---- computeT part 1 (align.go:131-171): map template sites to read bases, count mismatches ----
     int mism = 0;
     const bool indel = ngaps != 0;
-    if (!indel) {
+    if (!indel && mism_known >= 0) {
+        mism = mism_known;  // the caller counted them (k_pack's one-mismatch mark)
+    } else if (!indel) {
         // no gap in the alignment: column c pairs template base c with read base c
         if (score != m) {  // score == m == n: every base matches, nothing to count
             for (int c0 = 0; c0 < m; c0 += 32) {
@@ -470,7 +472,7 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     int edit_stop = junc_start - 1;
     int junc_len = 0;
     uint32_t js_off = 0, js_len = 0;
-    uint32_t status = rflags & ~kFlagSameBases;
+    uint32_t status = rflags & ~kFlagsInternal;
     if (junc_end > edit_stop) {
         junc_len = junc_end - edit_stop;
         if (has_mutation == 0 && !t0_all) {
@@ -566,17 +568,14 @@ __device__ __forceinline__ SameLane load_same_lane(const CtaSmem<uint8_t> &cs, c
     return sl;
 }
 
-// byte mask of the sites below `limit` in word i of the lane whose first site is `base`
-__device__ __forceinline__ uint32_t below_mask(int limit, int base, int i)
+// G lanes work on one read (G = 16: two reads per warp, templates of up to 255 bases); gl = lane within the group,
+// gmask = the group's lanes, lead = its first lane.  s_mask[t] = 16 bytes with the t lowest set (t = 0..16).
+template <int G>
+__device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<uint8_t> &cs, const uint4 *s_mask, int gl,
+                                            unsigned gmask, int lead, uint64_t r, uint32_t rflags, const uint4 &c,
+                                            const SameLane &sl, unsigned long long &ctr)
 {
-    const int k = min(max(limit - base - 4 * i, 0), 4);
-    return k >= 4 ? 0xffffffffu : (1u << (8 * k)) - 1u;
-}
-
-__device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<uint8_t> &cs, int lane, uint64_t r, uint32_t rflags,
-                                            const uint4 &c, const SameLane &sl, unsigned long long &ctr)
-{
-    const int m = p.t.m, n = m, len = p.t.len, K = p.t.K, base = 16 * lane;
+    const int m = p.t.m, n = m, len = p.t.len, K = p.t.K, base = 16 * gl;
     const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
     uint32_t df[4], dp[4];  // non-zero byte: the read's count differs from FE / PE at that site
 #pragma unroll
@@ -596,14 +595,14 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
 #pragma unroll
     for (int i = 3; i >= 0; i--)
         if (dp[i]) ll = base + 4 * i + ((__ffs(dp[i]) - 1) >> 3);
-    const int hc0 = __reduce_max_sync(FULL_MASK, hl);
+    const int hc0 = __reduce_max_sync(gmask, hl);
     const bool t0_all = hc0 < 0;
-    int junc_start = t0_all ? len - 1 : (!__any_sync(FULL_MASK, fe_match) ? -1 : len - 1 - hc0);
+    int junc_start = t0_all ? len - 1 : (!__any_sync(gmask, fe_match) ? -1 : len - 1 - hc0);
     if (K > 2 && junc_start >= 0 && junc_start < len) {
         // does the junction start sit on the first site of an alternative template's region that matches there?
         const int ti_s = len - 1 - junc_start, q = (ti_s >> 2) & 3;
         const uint32_t wsel = q == 0 ? cw[0] : q == 1 ? cw[1] : q == 2 ? cw[2] : cw[3];
-        const uint32_t cstar = (__shfl_sync(FULL_MASK, wsel, ti_s >> 4) >> (8 * (ti_s & 3))) & 0xffu;
+        const uint32_t cstar = (__shfl_sync(gmask, wsel, lead + (ti_s >> 4)) >> (8 * (ti_s & 3))) & 0xffu;
         for (int k = 2; k < K; k++) {
             if ((uint32_t)cs.tcount[k * p.t.len_pad + ti_s] == cstar) {
                 if (junc_start == cs.alt[k - 2]) return false;
@@ -611,10 +610,10 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
             }
         }
     }
-    const int lc1r = __reduce_min_sync(FULL_MASK, ll);
+    const int lc1r = __reduce_min_sync(gmask, ll);
     int junc_end = lc1r == 0x7fffffff ? -1 : len - 1 - lc1r;
     int edit_stop = junc_start - 1, junc_len = 0;
-    uint32_t js_off = 0, js_len = 0, status = rflags & ~kFlagSameBases;
+    uint32_t js_off = 0, js_len = 0, status = rflags & ~kFlagsInternal;
     if (junc_end > edit_stop) {
         junc_len = junc_end - edit_stop;
         if (!t0_all) {  // has_mutation is 0 for such a read
@@ -622,14 +621,14 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
             if (to > n + 1) {
                 status |= TREAT_B200_ST_REF_PANIC;
             } else {
-                uint32_t sf = 0, st = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    sf = __dp4a(cw[i] & below_mask(from, base, i), 0x01010101u, sf);
-                    st = __dp4a(cw[i] & below_mask(to, base, i), 0x01010101u, st);
-                }
-                sf = __reduce_add_sync(FULL_MASK, sf);
-                st = __reduce_add_sync(FULL_MASK, st);
+                // edit bases in front of base `from` / `to`: byte sums over the sites below them
+                const uint4 mf = s_mask[min(max(from - base, 0), 16)], mt = s_mask[min(max(to - base, 0), 16)];
+                uint32_t sf = __dp4a(cw[0] & mf.x, 0x01010101u, 0u), st = __dp4a(cw[0] & mt.x, 0x01010101u, 0u);
+                sf = __dp4a(cw[1] & mf.y, 0x01010101u, sf), st = __dp4a(cw[1] & mt.y, 0x01010101u, st);
+                sf = __dp4a(cw[2] & mf.z, 0x01010101u, sf), st = __dp4a(cw[2] & mt.z, 0x01010101u, st);
+                sf = __dp4a(cw[3] & mf.w, 0x01010101u, sf), st = __dp4a(cw[3] & mt.w, 0x01010101u, st);
+                sf = __reduce_add_sync(gmask, sf);
+                st = __reduce_add_sync(gmask, st);
                 js_off = sf + (uint32_t)min(from, n);
                 js_len = st + (uint32_t)min(to, n) - js_off;
                 if (js_len == 0) js_off = 0;
@@ -644,11 +643,11 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
         edit_stop = junc_start;
         junc_len = 0;
     }
-    emit_result<uint8_t>(p, cs, lane, r, n, /*alen*/ m, status, /*score*/ m, edit_stop, junc_start, junc_end, junc_len,
+    emit_result<uint8_t>(p, cs, gl, r, n, /*alen*/ m, status, /*score*/ m, edit_stop, junc_start, junc_end, junc_len,
                          /*has_mutation*/ 0, /*alt_editing*/ 0, /*mism*/ 0, /*indel*/ false, js_off, js_len, ctr);
     if (p.ops && !p.ops_gapped_only) {  // m match columns: an all-zero row
         uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + r * (uint64_t)p.ops_stride);
-        for (int wi = lane; wi < (int)(p.ops_stride / 4); wi += 32) go[wi] = 0u;
+        for (int wi = gl; wi < (int)(p.ops_stride / 4); wi += G) go[wi] = 0u;
     }
     return true;
 }
@@ -1114,52 +1113,79 @@ constexpr int kSameWarps = 16;
 __device__ __noinline__ void finish_same_general(const AlignParams &p, const CtaSmem<uint8_t> &cs, const WarpSmem &ws, int lane,
                                                  uint64_t r, uint32_t rflags, const uint8_t *rcount, unsigned long long &ctr)
 {
-    const int m = p.t.m;
-    finish_read<uint8_t>(p, cs, ws, lane, r, m, rflags, /*score*/ m, /*pos*/ m, /*ngaps*/ 0, rcount, [](int) { return 0; }, ctr);
+    const int m = p.t.m, mism = (rflags & kFlagOneMismatch) ? 1 : 0;  // the diagonal: score m - 2 per mismatch, no gap
+    finish_read<uint8_t>(p, cs, ws, lane, r, m, rflags, /*score*/ m - 2 * mism, /*pos*/ m, /*ngaps*/ 0, rcount,
+                         [](int) { return 0; }, ctr, mism);
 }
 
+template <int G>
 __global__ void __launch_bounds__(kSameWarps * 32, 2) k_same_bases(const __grid_constant__ AlignParams p)
 {
     using cnt_t = uint8_t;
+    constexpr int RPW = 32 / G;  // reads per warp
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int gl = lane & (G - 1), grp = lane / G, lead = grp * G;
+    const unsigned gmask = G == 32 ? FULL_MASK : 0xffffu << lead;
     const int m = p.t.m;
 
     const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, (int)p.cpl);  // no profile, no dump rows in this plan
     load_template(cs, p, (int)p.cpl);
     uint32_t *zero = reinterpret_cast<uint32_t *>(smem + p.sm_tmpl_bytes);  // the all-match ops of such a read
     for (uint32_t i = threadIdx.x; i < p.sm_ops / 4; i += blockDim.x) zero[i] = 0u;
-    uint4 *stage = reinterpret_cast<uint4 *>(smem + p.sm_tmpl_bytes + p.sm_ops + (size_t)warp * p.sm_cnt_stage);
+    uint4 *s_mask = reinterpret_cast<uint4 *>(smem + p.sm_tmpl_bytes + p.sm_ops);  // [17]: t lowest bytes 0xff
+    if (threadIdx.x < 17) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = min(max((int)threadIdx.x - 4 * i, 0), 4);
+            w[i] = k >= 4 ? 0xffffffffu : (1u << (8 * k)) - 1u;
+        }
+        s_mask[threadIdx.x] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    uint4 *stage = reinterpret_cast<uint4 *>(smem + p.sm_tmpl_bytes + p.sm_ops + 17 * 16 + (size_t)warp * p.sm_cnt_stage);
     WarpSmem ws{};
     ws.ops2 = zero;
     __syncthreads();
 
     const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
-    const bool mine = lane * 16 < m + 1;  // this lane's 16 counts exist
-    const SameLane sl = load_same_lane(cs, p, lane);
+    const bool mine = gl * 16 < m + 1;  // this lane's 16 counts exist
+    const SameLane sl = load_same_lane(cs, p, gl);
     unsigned long long ctr = 0;
     auto fetch = [&](uint64_t r, uint32_t &f, uint4 &c) {
-        f = p.rflags[r];
-        c = mine ? reinterpret_cast<const uint4 *>(p.counts + r * (uint64_t)p.counts_stride)[lane] : make_uint4(0, 0, 0, 0);
+        f = 0u;
+        c = make_uint4(0, 0, 0, 0);
+        if (r < p.N) {
+            f = p.rflags[r];
+            if (mine) c = reinterpret_cast<const uint4 *>(p.counts + r * (uint64_t)p.counts_stride)[gl];
+        }
     };
     uint32_t f = 0, fn = 0;
     uint4 c = make_uint4(0, 0, 0, 0), cn = c;
-    if (gw < p.N) fetch(gw, f, c);
-    for (uint64_t r = gw; r < p.N; r += nw) {
-        if (r + nw < p.N) fetch(r + nw, fn, cn);
-        if (f & kFlagSameBases) {
-            if (!finish_same(p, cs, lane, r, f, c, sl, ctr)) {  // an alternative template's region: the general assembly
-                __syncwarp();
-                stage[lane] = c;
-                __syncwarp();
-                finish_same_general(p, cs, ws, lane, r, f, reinterpret_cast<const cnt_t *>(stage), ctr);
-            }
-        } else if (lane == 0) {
-            p.list[atomicAdd(p.list_count, 1u)] = (uint32_t)r;
+    fetch(gw * RPW + grp, f, c);
+    for (uint64_t r0 = gw * RPW; r0 < p.N; r0 += nw * RPW) {
+        const uint64_t r = r0 + grp;
+        fetch(r + nw * RPW, fn, cn);
+        bool general = false;  // the group's read needs the general assembly
+        if (r < p.N) {
+            if (f & kFlagSameBases) general = !finish_same<G>(p, cs, s_mask, gl, gmask, lead, r, f, c, sl, ctr);
+            else if (f & kFlagOneMismatch) general = true;  // one substitution: still the diagonal, general assembly
+            else if (gl == 0) p.list[atomicAdd(p.list_count, 1u)] = (uint32_t)r;
+        }
+        // an alternative template's region: the whole warp runs the general assembly, one read at a time
+        unsigned todo = __ballot_sync(FULL_MASK, general && gl == 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            __syncwarp();
+            if (lead == src) stage[gl] = c;
+            __syncwarp();
+            finish_same_general(p, cs, ws, lane, r0 + src / G, __shfl_sync(FULL_MASK, f, src), reinterpret_cast<const cnt_t *>(stage), ctr);
         }
         f = fn;
         c = cn;
     }
+    if (G == 16) ctr += __shfl_down_sync(FULL_MASK, ctr, 16);  // lane L and lane L + 16 both hold counter L
     flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
 }
 
@@ -1288,14 +1314,20 @@ int launch_same_bases(const AlignParams &planned, int num_sms, void *stream)
     p.sm_ops = align16((((uint32_t)(2 * m) + 15) / 16 + 2) * 4);
     p.sm_cnt_stage = 512;  // 32 lanes x 16 counts >= m + 1
     if (p.ncap < (uint32_t)m) p.ncap = (uint32_t)m;
-    const size_t smem = p.sm_tmpl_bytes + p.sm_ops + (size_t)kSameWarps * p.sm_cnt_stage;
+    const size_t smem = p.sm_tmpl_bytes + p.sm_ops + 17 * 16 + (size_t)kSameWarps * p.sm_cnt_stage;
+    const bool two = p.t.len <= 256;  // 16 lanes x 16 sites hold the read: two reads per warp
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_same_bases, kSameWarps * 32, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    uint64_t blocks = (p.N + kSameWarps - 1) / kSameWarps;
+    cudaError_t oe = two ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_same_bases<16>, kSameWarps * 32, smem)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_same_bases<32>, kSameWarps * 32, smem);
+    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint64_t per_block = (uint64_t)kSameWarps * (two ? 2 : 1);
+    uint64_t blocks = (p.N + per_block - 1) / per_block;
     if (blocks > (uint64_t)num_sms * per_sm) blocks = (uint64_t)num_sms * per_sm;
     if (blocks == 0) return 0;
-    k_same_bases<<<(unsigned)blocks, kSameWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    if (two)
+        k_same_bases<16><<<(unsigned)blocks, kSameWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    else
+        k_same_bases<32><<<(unsigned)blocks, kSameWarps * 32, smem, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 

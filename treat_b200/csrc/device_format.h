@@ -45,6 +45,10 @@ struct PackParams {
 // internal bit of the per-read flag byte written by k_pack: the read's stripped bases equal the template's
 // (n == m, every code equal).  Never reaches treat_b200_record.status.
 constexpr uint32_t kFlagSameBases = 0x80u;
+// same length as the template and exactly one base differs: the diagonal (score m - 2) is the unique optimum, because
+// an alignment of two equal-length sequences with g >= 1 gap pairs scores at most m - 3g.  Also internal.
+constexpr uint32_t kFlagOneMismatch = 0x40u;
+constexpr uint32_t kFlagsInternal = kFlagSameBases | kFlagOneMismatch;
 
 struct AlignParams {
     // packed reads

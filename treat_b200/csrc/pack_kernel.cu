@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_c
         uint32_t *gb = reinterpret_cast<uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
         uint4 *gc = reinterpret_cast<uint4 *>(p.counts + r * (uint64_t)p.counts_stride);
         const uint32_t bwords = align16((n + 3) / 4) / 4, cgroups = (n + 16) / 16, twords = (p.tm + 15) / 16;
-        bool eq = p.tpk != nullptr && n == p.tm;
+        uint32_t nd = (p.tpk != nullptr && n == p.tm) ? 0u : 2u;  // bases that differ from the template's (2: not comparable)
         for (uint32_t g = lane; g < max(bwords, cgroups); g += 32) {
             uint32_t word = 0;
             if (g < cgroups) {
@@ -376,13 +376,17 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_c
                 word = __byte_perm(lo16, hi16, 0x5410);
             }
             if (g < bwords) gb[g] = word;
-            if (eq && g < twords) eq = word == p.tpk[g];  // codes past n are zero in both
+            if (nd < 2u && g < twords) {  // codes past n are zero in both
+                const uint32_t x = word ^ p.tpk[g];
+                nd += __popc((x | (x >> 1)) & 0x55555555u);
+            }
         }
-        const bool same = __all_sync(FULL_MASK, eq);
+        const uint32_t ndiff = __reduce_add_sync(FULL_MASK, nd);
+        const bool same = ndiff == 0u, one = ndiff == 1u;
         if (lane == 0) {
             p.n[r] = (uint16_t)n;
             p.flags[r] = (uint8_t)((any_sat ? TREAT_B200_ST_SATURATED : 0) | (any_wide ? TREAT_B200_ST_WIDE_BASE : 0) |
-                                   (same ? kFlagSameBases : 0));
+                                   (same ? kFlagSameBases : 0) | (one ? kFlagOneMismatch : 0));
             p.raw_len[r] = L;
         }
         warp_max_n = max(warp_max_n, n);
