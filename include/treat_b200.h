@@ -49,7 +49,8 @@ extern "C" {
 #define TREAT_B200_DP_EVERY_READ 0x20u /* run the DP even for reads whose stripped bases equal the template's (results are the same) */
 #define TREAT_B200_OPS_GAPPED_ONLY 0x80u /* with WANT_OPS: write the ops row only of reads whose alignment has a gap
                                             (record.indel != 0); the row of any other read would be all zero (m = n
-                                            match columns) and is left untouched, so D2H traffic shrinks to the gapped reads */
+                                            match columns) and is unspecified (left untouched, or zeroed), so D2H traffic
+                                            can shrink to the gapped reads */
 #define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
                                            under the template that is current now, so reads it marked as equal to the template
                                            skip the DP; without this flag the stage call runs the DP for every read */

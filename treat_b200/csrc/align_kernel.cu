@@ -513,13 +513,13 @@ __device__ __forceinline__ void finish_read(const AlignParams &p, const CtaSmem<
     // ---- traceback ops, 2 bits per column, in alignment order: a funnel shift of ops2 by pos ------
     if (p.ops && (indel || !p.ops_gapped_only)) {
         uint64_t row = r;
-        if (p.ops_idx) {  // compacted output: claim the next row
+        if (p.ops_count && indel) {  // count the gapped reads; with ops_idx their rows are compacted: claim the next one
             uint32_t k = 0;
             if (lane == 0) {
                 k = atomicAdd(p.ops_count, 1u);
-                p.ops_idx[k] = (uint32_t)r;
+                if (p.ops_idx) p.ops_idx[k] = (uint32_t)r;
             }
-            row = __shfl_sync(FULL_MASK, k, 0);
+            if (p.ops_idx) row = __shfl_sync(FULL_MASK, k, 0);
         }
         uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + row * (uint64_t)p.ops_stride);
         const int nwords = (int)(p.ops_stride / 4);

@@ -56,7 +56,8 @@ struct Slot {
     uint32_t *h_gap_idx = nullptr;
     size_t gap_rows_cap = 0, gap_idx_cap = 0;
     uint32_t gap_head = 0;     // rows copied ahead of knowing how many there are
-    bool scatter = false;      // compacted rows of this chunk still have to be placed into the caller's buffer
+    bool scatter = false;      // the chunk's gapped-read count (and compacted rows) still have to be consumed on the host
+    bool sparse = false;       // this chunk returns only the gapped reads' ops rows, compacted
     DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
     uint32_t *scalars = nullptr;    // device [8]: max n, any saturated run, reads skipped by a speculative launch, reads listed
                                     // for the DP, compacted ops rows
@@ -436,9 +437,9 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     ap.ops = (flags & TREAT_B200_WANT_OPS) ? d_ops : nullptr;
     ap.ops_stride = ops_stride;
     ap.ops_gapped_only = (flags & TREAT_B200_OPS_GAPPED_ONLY) ? 1u : 0u;
-    if (ap.ops && ap.ops_gapped_only && o.ops_idx && o.ops_count) {
-        ap.ops_idx = o.ops_idx;
-        ap.ops_count = o.ops_count;
+    if (ap.ops && o.ops_count) {
+        ap.ops_count = o.ops_count;                        // gapped reads are counted ...
+        if (ap.ops_gapped_only) ap.ops_idx = o.ops_idx;    // ... and their rows compacted when only they are wanted
     }
     ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : (summary_override ? summary_override : ctx->d_summary);
     ap.skipped = d_skipped;
@@ -536,13 +537,13 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     // ops into the slot's own buffer (host-buffer path): gapped-only rows are compacted there
     const bool slot_own_ops = (flags & TREAT_B200_WANT_OPS) && d_ops == nullptr;
     if (slot_own_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY)) CK(ctx, s.ops_idx.reserve(N * 4));
-    auto opts = [&](bool compact) {
+    auto opts = [&](bool own) {
         AlignOpts o;
         o.list = &s.list;
         o.list_count = s.scalars + 3;
-        if (compact && (flags & TREAT_B200_OPS_GAPPED_ONLY)) {
-            o.ops_idx = (uint32_t *)s.ops_idx.p;
+        if (own) {
             o.ops_count = s.scalars + 4;
+            if (flags & TREAT_B200_OPS_GAPPED_ONLY) o.ops_idx = (uint32_t *)s.ops_idx.p;
         }
         return o;
     };
@@ -634,7 +635,10 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     if (N == 0) return TREAT_B200_OK;
     CK(ctx, cudaSetDevice(ctx->device));
     const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
-    const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);  // only gapped reads' rows cross the bus
+    // OPS_GAPPED_ONLY: only gapped reads' rows cross the bus, compacted on the device and placed by the host.  Placing
+    // rows costs host time per row, so a chunk is run that way only while few reads (< 1/32 so far) have gaps;
+    // otherwise every row is copied (rows of gapless reads then arrive as zeros, which the contract allows).
+    const bool sparse_ok = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
     for (int i = 0; i < kSlots; i++) {
         if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
         ctx->slot[i].pending = ctx->slot[i].scatter = false;  // nothing carries over from a call that failed half-way
@@ -677,6 +681,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     auto copy_out = [&](Slot &s) -> int {
         CK(ctx, cudaMemcpyAsync(rec + s.c0, s.rec.p, s.cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, s.stream));
         // only the bytes the batch can use cross the bus: rows of dev_stride <= ops_stride bytes
+        const bool sparse = s.sparse;
         if (want_ops && !sparse)
             CK(ctx, cudaMemcpy2DAsync(ops + s.c0 * (size_t)ops_stride, ops_stride, s.ops.p, s.dev_stride, s.dev_stride, s.cn,
                                       cudaMemcpyDeviceToHost, s.stream));
@@ -685,10 +690,12 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
             const uint32_t head = (uint32_t)std::min<uint64_t>(s.cn, std::max<uint32_t>(4096u, 2u * ctx->gap_hint));
             int r = reserve_gap(s, head);
             if (r) return r;
-            CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, s.stream));
             CK(ctx, cudaMemcpyAsync(s.h_gap_idx, s.ops_idx.p, head * 4ull, cudaMemcpyDeviceToHost, s.stream));
             CK(ctx, cudaMemcpyAsync(s.h_gap_rows, s.ops.p, head * (size_t)s.dev_stride, cudaMemcpyDeviceToHost, s.stream));
             s.gap_head = head;
+        }
+        if (want_ops) {  // the number of gapped reads of the chunk, for place_rows and for the next chunks' choice
+            CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, s.stream));
             s.scatter = true;
         }
         return TREAT_B200_OK;
@@ -698,7 +705,8 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         if (!s.scatter) return TREAT_B200_OK;
         s.scatter = false;
         const uint32_t cnt = s.h_scalars[4];
-        ctx->gap_hint = std::max(ctx->gap_hint, cnt);
+        ctx->gap_hint = std::max(ctx->gap_hint, (uint32_t)(cnt * (uint64_t)chunk_reads / std::max<uint64_t>(s.cn, 1)));
+        if (!s.sparse) return TREAT_B200_OK;  // every row was copied
         if (cnt > s.gap_head) {  // more gapped reads than guessed: fetch the remaining rows now
             const uint32_t head = s.gap_head;
             std::vector<uint8_t> keep_rows(s.h_gap_rows, s.h_gap_rows + head * (size_t)s.dev_stride);
@@ -715,7 +723,6 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         for (uint32_t k = 0; k < cnt; k++) {
             uint8_t *dst = ops + (s.c0 + s.h_gap_idx[k]) * (size_t)ops_stride;
             memcpy(dst, s.h_gap_rows + k * (size_t)s.dev_stride, s.dev_stride);
-            memset(dst + s.dev_stride, 0, ops_stride - s.dev_stride);
         }
         return TREAT_B200_OK;
     };
@@ -723,10 +730,11 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     auto run_exact = [&](Slot &s) -> int {
         const uint32_t *d_rc = read_count ? (const uint32_t *)s.rc.p : nullptr;
         bool sat = false;
-        int r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, flags,
+        const uint32_t cflags = s.sparse ? flags : flags & ~TREAT_B200_OPS_GAPPED_ONLY;
+        int r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, cflags,
                           (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, false, &sat, &s.dev_stride);
         if (r == TREAT_B200_OK && sat && !ctx->tmpl_wide)
-            r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, flags,
+            r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, cflags,
                           (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, true, nullptr, &s.dev_stride);
         return r;
     };
@@ -791,10 +799,12 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         s.cn = cn;
         s.b0 = b0;
         s.max_len = max_len;
+        s.sparse = sparse_ok && (uint64_t)ctx->gap_hint * 32 <= chunk_reads;
         if (ctx->ncap_hint && !ctx->tmpl_wide && !no_spec) {
             // no host sync: size the align kernel from the largest n seen so far (+ slack) and validate later
             rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0,
-                           read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len, flags, (treat_b200_record *)s.rec.p,
+                           read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len,
+                           s.sparse ? flags : flags & ~TREAT_B200_OPS_GAPPED_ONLY, (treat_b200_record *)s.rec.p,
                            nullptr, 0, st, false, nullptr, &s.dev_stride, ctx->ncap_hint + 8);
             s.pending = rc == TREAT_B200_OK;
         } else {
