@@ -12,8 +12,11 @@ collective, one all-reduce of the summary counters per step).
 One JSON line on rank 0:
   value      whole-job reads/s with the raw reads already resident in HBM (device-timed, max over ranks)
   e2e        the same through treat_b200_align_batch with pinned HOST buffers (H2D + kernels + D2H)
-  roofline   k_align (the dominant kernel) against the INT32 ALU peak measured live on this GPU;
-             roofline_hbm gives the same launch against the measured HBM copy bandwidth
+  roofline   the kernel that takes the largest share of a step: k_pack16 (NewFragment: streams the raw reads, writes
+             the packed ones) against the measured HBM copy bandwidth
+  roofline_dp   the DP kernel (k_align2, run on every read) against the INT32 ALU peak measured live on this GPU
+  kernels_ms    CUDA-event time of each stage alone; reads whose stripped bases equal the template's, or differ
+             in exactly one base, are finished without a DP (k_same_bases) -- exact, see DESIGN.md 4
   cpu_baseline  the CPU oracle (a C port of the Go path; the Go reference cannot be built here)
 
 --impl reference times that CPU port with all host threads on bounded samples of the same workload.
@@ -269,7 +272,9 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     sraw = stream.cuda_stream
     assert sraw != 0
-    flags = cabi.WANT_OPS
+    # records + the traceback ops of every read that has a gap: a read without a gap aligns base over base (its row
+    # would be all zero), so its alignment strings follow from the record alone -- what NewAlignments asks for
+    flags = cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY
     summ = parallel.summary_tensor(eng)
 
     def step_device():
@@ -352,40 +357,43 @@ def run_ours(args):
     pack_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_pack_device(
         eng._ctx, d_seqs.data_ptr(), d_off.data_ptr(), C.byref(pk_full), sraw), eng._ctx), args.steps)
     n_arr = d_n.cpu().numpy().astype(np.int64) & 0xffff
-    # algorithmic HBM bytes of one k_align launch: packed bases + counts + n/flags/raw_len/read_count in, record + ops out
-    alg_bytes = float(((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4 + 4) + N * 48 + ((t.m + n_arr + 3) // 4).sum())
-    int_ops = cells_per_step * INT_OPS_PER_CELL
-    roofline = {"bound": "int32", "kernel": "k_align2 (k_align for wide/long templates)", "achieved": int_ops / (align_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
-                "unit": "Tiop/s", "frac": int_ops / (align_ms * 1e-3) / int_peak,
-                "peak_source": "measured live: k_int32_peak (dependent-free add+max, all SMs)",
-                "ops_per_cell": INT_OPS_PER_CELL, "cells_per_launch": cells_per_step, "ms_per_launch": align_ms,
-                "gcups": cells_per_step / (align_ms * 1e-3) / 1e9, "traffic": None,
-                "note": "frac is against a SCALAR 8-op-per-cell roofline; the kernel needs ~1.5 instructions per cell "
-                        "(gap-free transform, two reads per register, IMAD-packed direction digits) and skips the "
-                        "traceback of all-match reads, so frac can exceed 1"}
-    # DRAM traffic per launch from the committed ncu capture (per read x reads of this launch)
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_align2"]
-        traffic = (tr["dram_read_bytes_per_read"] + tr["dram_write_bytes_per_read"]) * N if args.workload == "rps12" else None
-    except Exception:
-        traffic = None
-    roofline["traffic"] = traffic
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak, hbm_src = 6650.0, "fallback"
     if os.path.exists(peaks_path):
         hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    roofline_hbm = {"bound": "hbm", "kernel": "k_align2", "achieved": alg_bytes / (align_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": alg_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                    "bytes_per_launch": alg_bytes, "traffic": traffic}
+
+    def ncu_traffic(kernel):
+        # DRAM bytes per launch from the committed ncu capture (per read x reads of this launch)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+            return (tr["dram_read_bytes_per_read"] + tr["dram_write_bytes_per_read"]) * N if args.workload == "rps12" else None
+        except Exception:
+            return None
+    # k_pack16: raw characters + offsets in; 2-bit bases, counts, n / flags / raw_len out
+    pack_bytes = float(len(seqs) + N * 8 + ((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4))
+    roofline = {"bound": "hbm", "kernel": "k_pack16 (NewFragment for the batch; largest share of a step)",
+                "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms, "traffic": ncu_traffic("k_pack16"),
+                "note": "instruction-issue bound (about 500 warp instructions per read), not DRAM bound: see profiles/"}
+    # k_align2 on every read: algorithmic integer ops of the DP
+    alg_bytes = float(((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4 + 4) + N * 48 + ((t.m + n_arr + 3) // 4).sum())
+    int_ops = cells_per_step * INT_OPS_PER_CELL
+    roofline_dp = {"bound": "int32", "kernel": "k_align2 on every read (k_align for wide/long templates)",
+                   "achieved": int_ops / (align_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                   "unit": "Tiop/s", "frac": int_ops / (align_ms * 1e-3) / int_peak,
+                   "peak_source": "measured live: k_int32_peak (dependent-free add+max, all SMs)",
+                   "ops_per_cell": INT_OPS_PER_CELL, "cells_per_launch": cells_per_step, "ms_per_launch": align_ms,
+                   "gcups": cells_per_step / (align_ms * 1e-3) / 1e9, "traffic": ncu_traffic("k_align2"),
+                   "hbm_frac": alg_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak,
+                   "note": "frac is against a SCALAR 8-op-per-cell roofline; the kernel needs ~1.5 instructions per cell "
+                           "(gap-free transform, two reads per register, IMAD-packed direction digits), so frac can exceed 1"}
     del d_b, d_c, d_n, d_fl, d_rl
 
     # ---- end to end through the host-buffer C ABI call -------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        # ops rows only for reads with a gap (the others are all-zero rows the host never needs): what NewAlignments uses
-        e2e_flags = flags | cabi.OPS_GAPPED_ONLY
-
-        def step_host(fl=e2e_flags):
+        def step_host(fl=flags):
             eng.align_batch(seqs, h_off, h_rc, fl, rec=h_rec, ops=h_ops)
             red = summ.clone()
             parallel.allreduce_summary(red)
@@ -402,7 +410,9 @@ def run_ours(args):
         n_gapped = int((rec_dev["indel"] != 0).sum())
         e2e = {"value": world * N * args.steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(len(seqs) + (N + 1) * 8 + N * 4),
-               "d2h_bytes_per_step": int(N * 48 + n_gapped * (dev_stride + 4) + 32 * ((N + 65535) // 65536) + 8),
+               # the library compacts the gapped reads' rows only while they are rare (< 1/32 of a chunk), else every row
+               "d2h_bytes_per_step": int(N * 48 + (n_gapped * (dev_stride + 4) if n_gapped * 32 <= N else N * dev_stride)
+                                         + 32 * ((N + 65535) // 65536) + 8),
                "ms_per_step": 1e3 * e2e_s / args.steps,
                "api": "treat_b200_align_batch (pinned host buffers), records + ops rows of the %d reads with a gap "
                       "(TREAT_B200_OPS_GAPPED_ONLY)" % n_gapped}
@@ -410,7 +420,7 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step_host(flags)
+            step_host(cabi.WANT_OPS)
         barrier()
         full_s = max_over_ranks(time.perf_counter() - t0)
         e2e["every_ops_row"] = {"value": world * N * args.steps / full_s, "ms_per_step": 1e3 * full_s / args.steps,
@@ -440,10 +450,10 @@ def run_ours(args):
             "gcups": world * cells_per_step * args.steps / (dev_ms * 1e-3) / 1e9,
             "config": {"workload": workload_name(args, t), "l2": "inputs larger than L2 (%.0f MB raw reads per GPU per step)" % (len(seqs) / 1e6),
                        "parallelism": "reads sharded over %d GPU(s), summary all-reduce only" % world,
-                       "outputs": "48-byte record + %d-byte 2-bit ops per read" % stride},
+                       "outputs": "48-byte record per read + %d-byte 2-bit ops row per read with a gap" % stride},
             "kernels_ms": {"k_pack": pack_ms, "k_same_bases+k_align(listed reads)": marks_ms, "k_align(every read)": align_ms},
             "reads_equal_to_template_bases": same_frac,
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
