@@ -453,6 +453,8 @@ def run_ours(args):
                        "outputs": "48-byte record per read + %d-byte 2-bit ops row per read with a gap" % stride},
             "kernels_ms": {"k_pack": pack_ms, "k_same_bases+k_align(listed reads)": marks_ms, "k_align(every read)": align_ms},
             "reads_equal_to_template_bases": same_frac,
+            # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
+            "value_dp_every_read": world * N / ((pack_ms + align_ms) * 1e-3),
             "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -299,6 +299,40 @@ def test_device_resident_entry_point(eng, tmp_path):
     assert np.array_equal(d_ops.cpu().numpy().reshape(N, stride), hops)
 
 
+def test_pack_lengths_and_alignments(eng, tmp_path):
+    """k_pack16 takes 16-byte aligned blocks: every start misalignment, lengths around the block and the 512-character
+    pass boundaries, lower case, non-alphabet characters, long edit-base runs (below the saturation limit)."""
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    rng = random.Random(20261020)
+    reads = []
+    lens = [0, 1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 255, 256, 257, 495, 496, 497, 511, 512, 513, 527, 528, 1023, 1024, 1025, 3000]
+    for L in lens * 6:
+        kind = rng.randrange(4)
+        if kind == 0:
+            s = "".join(rng.choice("ACGT") for _ in range(L))
+        elif kind == 1:
+            s = "".join(rng.choice("acgtACGTTTTT") for _ in range(L))
+        elif kind == 2:
+            s = "".join(rng.choice("ACGTTTTTTTTTTTTTTTTTNn-") for _ in range(L))
+        else:  # edit-base runs that cross many blocks, still < 255
+            s = ""
+            while len(s) < L:
+                s += "T" * rng.randrange(0, 200) + rng.choice("ACG") * rng.randrange(1, 3)
+            s = s[:L]
+        reads.append(s)
+    for pad in range(17):  # shift the whole batch through every misalignment
+        batch = ["A" * pad] + reads
+        seqs = np.frombuffer("".join(batch).encode(), dtype=np.uint8).copy()
+        off = np.concatenate([[0], np.cumsum([len(x) for x in batch])]).astype(np.uint64)
+        rc = np.ones(len(batch), dtype=np.uint32)
+        grec, gops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS | cabi.NO_SUMMARY)
+        orec, oops, _ = O.align_batch(om, seqs, off, rc, nthreads=8, ops_stride=gops.shape[1])
+        assert compare_records(grec, orec) == [], pad
+        assert np.array_equal(gops, oops), pad
+
+
 def test_stage_calls_and_pack_marks(eng, tmp_path):
     """pack_device + align_packed_device: with and without USE_PACK_MARKS the records equal the one-call result;
     the mark (bit 7 of the flag byte) is set exactly for reads whose stripped bases equal the template's."""

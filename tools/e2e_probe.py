@@ -86,6 +86,31 @@ def main():
         print("full duplex %.0f MB each way: %.2f ms (%.1f GB/s per direction)" % (len(seqs) / 1e6, dd, len(seqs) / dd / 1e6), flush=True)
         print("raw copies: H2D %.0f MB %.2f ms (%.1f GB/s) | D2H %.0f MB %.2f ms (%.1f GB/s) | both %.2f ms" % (
             len(seqs) / 1e6, a, len(seqs) / a / 1e6, N * 48 / 1e6, b, N * 48 / b / 1e6, c), flush=True)
+    if os.environ.get("PROBE_RAW", "1") == "1":
+        # the copy pattern of align_batch without any kernel: 65,536-read chunks over 4 streams, per chunk
+        # H2D reads + offsets + counts, D2H records
+        CH = 65536
+        streams = [torch.cuda.Stream() for _ in range(4)]
+        t_off, t_rc = torch.from_numpy(h_off.view(np.int64)), torch.from_numpy(h_rc.view(np.int32))
+        d_off = torch.empty(N + 1, dtype=torch.int64, device="cuda")
+        d_rc = torch.empty(N, dtype=torch.int32, device="cuda")
+        offs = off.astype(np.int64)
+
+        def chunked(sync_reuse):
+            for ci, c0 in enumerate(range(0, N, CH)):
+                c1 = min(N, c0 + CH)
+                st = streams[ci % 4]
+                if sync_reuse:
+                    st.synchronize()
+                with torch.cuda.stream(st):
+                    d_in[offs[c0]:offs[c1]].copy_(tin[offs[c0]:offs[c1]], non_blocking=True)
+                    d_off[c0:c1 + 1].copy_(t_off[c0:c1 + 1], non_blocking=True)
+                    d_rc[c0:c1].copy_(t_rc[c0:c1], non_blocking=True)
+                    tout[c0 * 48:c1 * 48].copy_(d_out[c0 * 48:c1 * 48], non_blocking=True)
+            for st in streams:
+                st.synchronize()
+        print("chunked copies only (305 MB in, 48 MB out): %.2f ms free-running, %.2f ms with a sync at slot reuse" % (
+            timeit(lambda: chunked(False)), timeit(lambda: chunked(True))), flush=True)
     for name, fl, ops in (("records+ops", cabi.WANT_OPS, h_ops), ("rec+gapped ops", cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY, h_ops),
                           ("records only", 0, None)):
         ms = timeit(lambda: eng.align_batch(h_seqs, h_off, h_rc, fl, rec=h_rec, ops=ops))
