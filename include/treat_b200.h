@@ -239,6 +239,18 @@ const uint8_t *treat_b200_fasta_seqs(const treat_b200_fasta *f);     /* concaten
 const uint64_t *treat_b200_fasta_offsets(const treat_b200_fasta *f); /* count+1 */
 const uint32_t *treat_b200_fasta_read_counts(const treat_b200_fasta *f);
 
+/* FASTA ingest on the device: the record loop of gofasta.SimpleParser (cmd/treat/align.go:114, storage.go:738) with
+ * parseMergeCount (fragment.go:75-89), NewFragment and NewAlignment, straight from the bytes of the file.
+ * treat_b200_fasta_upload copies the file to the GPU (fasta may be pageable; pinned is faster), finds its records
+ * and returns their number and the longest sequence (size the ops rows with treat_b200_ops_stride(ctx, max_seq_len)).
+ * The file stays resident until the next upload, so it can be aligned against several templates.
+ * treat_b200_fasta_align aligns every record against the current template: rec[n_records] in file order; optional
+ * outputs: ops rows, each record's Id as (offset, length) into the file bytes (strings.TrimSpace applied), ReadCount.
+ * Record semantics are those of treat_b200_fasta_read (which runs on the host). */
+int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint64_t *n_records, uint32_t *max_seq_len);
+int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_record *rec, uint8_t *ops, uint32_t ops_stride,
+                           uint64_t *id_off, uint32_t *id_len, uint32_t *read_count);
+
 /* align.go:388-520 Alignment.WriteTo from a device result: text for one read.  Returns the
  * number of bytes needed; writes at most cap bytes to out (call twice or size generously). */
 int64_t treat_b200_format_alignment(const treat_b200_template *t, const treat_b200_record *rec,

@@ -333,6 +333,85 @@ def test_pack_lengths_and_alignments(eng, tmp_path):
         assert np.array_equal(gops, oops), pad
 
 
+def _fasta_device_vs_host(eng, tmp_path, text: bytes, tag: str, flags=None):
+    """upload_fasta/align_fasta (parse on the GPU) == read_fasta (host parser) + align_batch, field by field."""
+    path = os.path.join(str(tmp_path), tag + ".fa")
+    with open(path, "wb") as f:
+        f.write(text)
+    host = T.read_fasta(path)
+    n, ml = eng.upload_fasta(text)
+    assert n == len(host), tag
+    lens = np.diff(host.offsets.astype(np.int64))
+    assert ml == (int(lens.max()) if n else 0), tag
+    flags = cabi.WANT_OPS | cabi.NO_SUMMARY if flags is None else flags
+    rec, ops, ids, rcs = eng.align_fasta(flags)
+    assert ids == host.ids, tag
+    assert np.array_equal(rcs, host.read_counts), tag
+    if n:
+        hrec, hops = eng.align_batch(host.seqs, host.offsets, host.read_counts, flags)
+        assert np.array_equal(rec, hrec), tag
+        if hops is not None:
+            assert np.array_equal(ops[:, :hops.shape[1]], hops), tag
+    return n
+
+
+def test_fasta_ingest_on_device(eng, tmp_path):
+    """gofasta record loop + parseMergeCount on the device, against the host reader."""
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    rng = random.Random(77)
+    seqs, off, rc = synth.reads(t, 3000, seed=515)
+    reads = [seqs[int(off[i]):int(off[i + 1])].tobytes() for i in range(3000)]
+    names = ["r%d_%d" % (i, rc[i]) for i in range(3000)]
+    odd_ids = ["plain", "a_b_007", "x-3 tail_9", "_5", "5_", "q_12x", "big_99999999999999999999", "z_0", "  padded_4  \t", "",
+               "tab\tsep_8", "dash-17", "m_n-o_21 second_3", "r_4294967297"]
+    # (a) two-line records, odd ids
+    a = b"".join(b">" + (odd_ids[i % len(odd_ids)] if i % 7 == 0 else names[i]).encode() + b"\n" + reads[i] + b"\n" for i in range(3000))
+    _fasta_device_vs_host(eng, tmp_path, a, "two_line")
+    # (b) CRLF, no newline at the end / a lone CR at the end
+    b = b"".join(b">" + names[i].encode() + b"\r\n" + reads[i] + b"\r\n" for i in range(500))
+    _fasta_device_vs_host(eng, tmp_path, b, "crlf")
+    _fasta_device_vs_host(eng, tmp_path, b[:-2], "crlf_no_eol")
+    _fasta_device_vs_host(eng, tmp_path, b[:-1], "crlf_cr_at_eof")
+    # (c) wrapped sequences, blank lines, junk in front, the first '>' inside a line, '>' inside a sequence line
+    parts = [b"junk line\nmore junk>first_2 in a line\n"]
+    for i in range(700):
+        w = rng.choice([1, 7, 60, 61, 80, 1000])
+        r = reads[i]
+        body = b"\n".join(r[j:j + w] for j in range(0, len(r), w))
+        if i % 11 == 0:
+            body = body[:10] + b"\n\n" + body[10:]
+        if i % 13 == 0:
+            body = body[:5] + b">" + body[5:]
+        if i % 17 == 0:
+            body = body.replace(b"\n", b"\r\n", 2)
+        if i % 19 == 0:
+            body = b""
+        parts.append(body + b"\n>" + names[i].encode() + (b"  \n" if i % 3 else b"\n"))
+    parts.append(reads[700])
+    _fasta_device_vs_host(eng, tmp_path, b"".join(parts), "wrapped")
+    # (d) degenerate files
+    for tag, text in (("empty", b""), ("no_records", b"just text\nno records\n"), ("only_header", b">h_3"), ("only_gt", b">"),
+                      ("gt_newline", b">\n"), ("header_then_seq_no_eol", b">x_2\nACGTTTG")):
+        _fasta_device_vs_host(eng, tmp_path, text, tag)
+    # (e) a file that spans many tiles and scan blocks, records-only and gapped-only flags
+    seqs, off, rc = synth.reads(t, 200000, seed=616)
+    buf = bytearray()
+    for i in range(200000):
+        buf += b">s%d-%d\n" % (i, rc[i])
+        buf += seqs[int(off[i]):int(off[i + 1])].tobytes()
+        buf += b"\n"
+    assert _fasta_device_vs_host(eng, tmp_path, bytes(buf), "large", cabi.NO_SUMMARY) == 200000
+    # summaries accumulate like the host-buffer call's
+    eng.reset_summary()
+    eng.align_fasta(cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY, want_ids=False)
+    s1 = eng.summary().copy()
+    eng.reset_summary()
+    eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+    assert np.array_equal(s1, eng.summary())
+
+
 def test_stage_calls_and_pack_marks(eng, tmp_path):
     """pack_device + align_packed_device: with and without USE_PACK_MARKS the records equal the one-call result;
     the mark (bit 7 of the flag byte) is set exactly for reads whose stripped bases equal the template's."""

@@ -404,6 +404,41 @@ class Aligner:
         check(lib().treat_b200_align_batch_device(self._ctx, d_seqs, d_seq_off, d_read_count or None, N, max_len, flags,
                                                   d_rec, d_ops or None, ops_stride, stream or None), self._ctx)
 
+    def upload_fasta(self, data) -> Tuple[int, int]:
+        """treat_b200_fasta_upload: FASTA bytes (bytes, or a uint8 array, e.g. pinned) -> (records, longest sequence).
+        The parse runs on the GPU; the file stays resident for align_fasta()."""
+        if isinstance(data, (bytes, bytearray)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        n, ml = C.c_uint64(), C.c_uint32()
+        check(lib().treat_b200_fasta_upload(self._ctx, data.ctypes.data, data.size, C.byref(n), C.byref(ml)), self._ctx)
+        self._fasta = (data, n.value, ml.value)
+        return n.value, ml.value
+
+    def align_fasta(self, flags: int = WANT_OPS, rec: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None,
+                    want_ids: bool = True):
+        """treat_b200_fasta_align on the uploaded file: (records, ops or None, ids or None, read counts)."""
+        data, N, ml = self._fasta
+        if rec is None:
+            rec = np.zeros(N, dtype=RECORD_DTYPE)
+        stride = 0
+        if flags & WANT_OPS:
+            if ops is None:
+                stride = self.ops_stride(ml)
+                ops = np.zeros((N, stride), dtype=np.uint8)
+            else:
+                stride = ops.shape[1]
+        id_off = np.zeros(N, dtype=np.uint64)
+        id_len = np.zeros(N, dtype=np.uint32)
+        rcs = np.zeros(N, dtype=np.uint32)
+        check(lib().treat_b200_fasta_align(self._ctx, flags, rec.ctypes.data, ops.ctypes.data if (flags & WANT_OPS) else None, stride,
+                                           id_off.ctypes.data, id_len.ctypes.data, rcs.ctypes.data), self._ctx)
+        ids = None
+        if want_ids:
+            raw = data.tobytes()
+            ids = [raw[int(o):int(o) + int(n)].decode("latin-1") for o, n in zip(id_off, id_len)]
+        return rec, (ops if flags & WANT_OPS else None), ids, rcs
+
     def synchronize(self) -> None:
         check(lib().treat_b200_synchronize(self._ctx), self._ctx)
 

@@ -77,6 +77,28 @@ struct Slot {
     }
 };
 
+// reads that are not back to back in their buffer (FASTA records aligned in place)
+struct ReadSpan {
+    const uint64_t *begin;
+    const uint32_t *len;
+    uint64_t span;
+};
+
+// a FASTA file resident on the device with its record index (treat_b200_fasta_upload)
+struct FastaDev {
+    DevBuf file, tile_count, tile_off, sums, start, id_off, id_len, rc, seq_begin, seq_len, seq_off, seqs, scal;
+    uint64_t len = 0, N = 0, seq_bytes = 0;
+    uint32_t max_len = 0;
+    bool multi = false;      // some record has more than one sequence line: reads are compacted before packing
+    bool compacted = false;  // seqs / seq_off hold the compacted reads
+    bool open = false;
+    void release()
+    {
+        for (DevBuf *b : {&file, &tile_count, &tile_off, &sums, &start, &id_off, &id_len, &rc, &seq_begin, &seq_len, &seq_off, &seqs, &scal})
+            b->release();
+    }
+};
+
 }  // namespace
 
 struct treat_b200_ctx {
@@ -102,6 +124,7 @@ struct treat_b200_ctx {
     Slot slot[kSlots];
     // scratch for the device-resident entry point
     Slot dev_slot;
+    FastaDev fasta;
 };
 
 #define CK(ctx, expr)                                                                   \
@@ -188,6 +211,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     for (Slot &sl : ctx->slot) sl.release();
     ctx->dev_slot.release();
+    ctx->fasta.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -370,7 +394,7 @@ static int ensure_scalars(treat_b200_ctx *ctx, Slot &s)
 }
 
 static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
-                   const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st)
+                   const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st, const ReadSpan *span = nullptr)
 {
     PackParams pp{};
     pp.seqs = d_seqs;
@@ -390,6 +414,13 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     pp.scalars = d_scalars;
     pp.tpk = (!dst->wide && !ctx->tmpl_wide) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
     pp.tm = (uint32_t)ctx->td.m;
+    if (span && !dst->wide) {  // k_pack16 only
+        pp.begin = span->begin;
+        pp.len = span->len;
+        pp.span = span->span;
+    } else if (span) {
+        return fail(ctx, TREAT_B200_ERR_INVALID, "pack: in-place reads are not supported on the wide path");
+    }
     int e = launch_pack(pp, dst->wide != 0, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: read too long for shared-memory staging");
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_pack launch: ") + cudaGetErrorString((cudaError_t)e));
@@ -531,7 +562,7 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
 static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
                      const uint32_t *d_rc, uint64_t N, uint32_t max_len, uint32_t flags, treat_b200_record *d_rec,
                      uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st, bool force_wide, bool *saturated,
-                     uint32_t *ops_stride_used = nullptr, uint32_t spec_ncap = 0)
+                     uint32_t *ops_stride_used = nullptr, uint32_t spec_ncap = 0, const ReadSpan *span = nullptr)
 {
     const bool wide = ctx->tmpl_wide || force_wide;
     // ops into the slot's own buffer (host-buffer path): gapped-only rows are compacted there
@@ -563,7 +594,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     rc = ensure_scalars(ctx, s);
     if (rc) return rc;
     CK(ctx, cudaMemsetAsync(s.scalars, 0, kScalarBytes, st));
-    rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st);
+    rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span);
     if (rc) return rc;
     if (spec_ncap) {
         const uint32_t ncap = std::min(spec_ncap, max_len);
@@ -829,6 +860,173 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     if (trace)
         fprintf(stderr, "[treat_b200] align_batch N=%llu chunks=%llu total %.2f ms: wait_slot %.2f enqueue %.2f drain %.2f, chunks re-run %d\n",
                 (unsigned long long)N, (unsigned long long)chunk_idx, now() - t_begin, t_wait_slot, t_enqueue, now() - t_loop, redone);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FASTA bytes in, records out (gofasta.SimpleParser + parseMergeCount + NewFragment + NewAlignment on the device)
+// ---------------------------------------------------------------------------------------------
+int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint64_t *n_records, uint32_t *max_seq_len)
+{
+    if (!ctx || (len && !fasta) || !n_records) return TREAT_B200_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    FastaDev &fa = ctx->fasta;
+    cudaStream_t st = ctx->stream;
+    fa.open = false;
+    fa.compacted = false;
+    fa.len = len;
+    fa.N = 0;
+    fa.max_len = 0;
+    *n_records = 0;
+    if (max_seq_len) *max_seq_len = 0;
+    const uint64_t ntiles = (len + kFastaTileBytes - 1) / kFastaTileBytes;
+    CK(ctx, fa.file.reserve(len + 64));
+    CK(ctx, fa.tile_count.reserve((ntiles + 1) * 4));
+    CK(ctx, fa.tile_off.reserve((ntiles + 2) * 8));
+    CK(ctx, fa.sums.reserve((ntiles / 2048 + 4) * 8));
+    CK(ctx, fa.scal.reserve(64));
+    uint64_t *d_first = (uint64_t *)fa.scal.p;
+    uint32_t *d_scal = (uint32_t *)((uint8_t *)fa.scal.p + 16);
+    CK(ctx, cudaMemsetAsync(fa.scal.p, 0xff, 8, st));             // first '>' = none
+    CK(ctx, cudaMemsetAsync((uint8_t *)fa.scal.p + 8, 0, 56, st));
+    // upload in pieces; the record starts of a piece are counted while the next piece is on the bus
+    const uint64_t piece = 32ull << 20;  // a multiple of the tile size
+    for (uint64_t o = 0; o < len; o += piece) {
+        const uint64_t nb = std::min(piece, len - o);
+        CK(ctx, cudaMemcpyAsync((uint8_t *)fa.file.p + o, fasta + o, nb, cudaMemcpyHostToDevice, st));
+        int e = launch_fasta_mark((const uint8_t *)fa.file.p, len, o / kFastaTileBytes, (nb + kFastaTileBytes - 1) / kFastaTileBytes,
+                                  (uint32_t *)fa.tile_count.p, d_first, ctx->num_sms, st);
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_fasta_mark launch: ") + cudaGetErrorString((cudaError_t)e));
+        ctx->launches++;
+    }
+    if (len == 0) {
+        fa.open = true;
+        return TREAT_B200_OK;
+    }
+    int e = launch_scan_u32((const uint32_t *)fa.tile_count.p, ntiles, (uint64_t *)fa.tile_off.p, (uint64_t *)fa.sums.p, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches += 3;
+    uint64_t h[2] = {0, 0};  // line-start '>' count, first '>' position
+    CK(ctx, cudaMemcpyAsync(&h[0], (uint64_t *)fa.tile_off.p + ntiles, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(&h[1], d_first, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    const uint64_t first = h[1];
+    const bool extra = first < len && !(first == 0 || fasta[first - 1] == '\n');  // the first '>' sits inside a line
+    const uint64_t N = h[0] + (extra ? 1 : 0);
+    if (N > 0x7fffffffull) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "fasta: more than 2^31 records");
+    fa.N = N;
+    if (N) {
+        CK(ctx, fa.start.reserve(N * 8));
+        CK(ctx, fa.id_off.reserve(N * 8));
+        CK(ctx, fa.id_len.reserve(N * 4));
+        CK(ctx, fa.rc.reserve(N * 4));
+        CK(ctx, fa.seq_begin.reserve(N * 8));
+        CK(ctx, fa.seq_len.reserve(N * 4));
+        CK(ctx, fa.seq_off.reserve((N + 1) * 8));
+        CK(ctx, fa.sums.reserve((std::max(N, ntiles) / 2048 + 4) * 8));
+        e = launch_fasta_starts((const uint8_t *)fa.file.p, len, ntiles, (const uint64_t *)fa.tile_off.p, d_first, (uint64_t *)fa.start.p,
+                                ctx->num_sms, st);
+        if (!e)
+            e = launch_fasta_records((const uint8_t *)fa.file.p, len, (const uint64_t *)fa.start.p, N, (uint64_t *)fa.id_off.p,
+                                     (uint32_t *)fa.id_len.p, (uint32_t *)fa.rc.p, (uint64_t *)fa.seq_begin.p, (uint32_t *)fa.seq_len.p,
+                                     d_scal, ctx->num_sms, st);
+        if (!e) e = launch_scan_u32((const uint32_t *)fa.seq_len.p, N, (uint64_t *)fa.seq_off.p, (uint64_t *)fa.sums.p, st);
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("fasta index launch: ") + cudaGetErrorString((cudaError_t)e));
+        ctx->launches += 5;
+        uint32_t hs[2] = {0, 0};
+        CK(ctx, cudaMemcpyAsync(hs, d_scal, 8, cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaMemcpyAsync(&fa.seq_bytes, (uint64_t *)fa.seq_off.p + N, 8, cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaStreamSynchronize(st));
+        fa.max_len = hs[0];
+        fa.multi = hs[1] != 0;
+    }
+    fa.open = true;
+    *n_records = N;
+    if (max_seq_len) *max_seq_len = fa.max_len;
+    return TREAT_B200_OK;
+}
+
+int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_record *rec, uint8_t *ops, uint32_t ops_stride,
+                           uint64_t *id_off, uint32_t *id_len, uint32_t *read_count)
+{
+    if (!ctx) return TREAT_B200_ERR_INVALID;
+    FastaDev &fa = ctx->fasta;
+    if (!fa.open) return fail(ctx, TREAT_B200_ERR_INVALID, "fasta_align: no file uploaded (treat_b200_fasta_upload)");
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    const uint64_t N = fa.N;
+    if (N == 0) return TREAT_B200_OK;
+    if (!rec) return TREAT_B200_ERR_INVALID;
+    const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
+    if (want_ops && !ops) return fail(ctx, TREAT_B200_ERR_INVALID, "align: WANT_OPS without ops buffer");
+    if (fa.max_len > kMaxReadLen) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: read longer than 16384");
+    if (want_ops && (ops_stride < treat_b200_ops_stride(ctx, fa.max_len) || ops_stride % 16))
+        return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small (see treat_b200_ops_stride)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (id_off) CK(ctx, cudaMemcpyAsync(id_off, fa.id_off.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (id_len) CK(ctx, cudaMemcpyAsync(id_len, fa.id_len.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (read_count) CK(ctx, cudaMemcpyAsync(read_count, fa.rc.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int i = 0; i < 2; i++)
+        if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
+
+    // reads with line breaks inside (or a template that needs the wide path) are first copied into one contiguous buffer
+    auto compact = [&]() -> int {
+        if (fa.compacted) return TREAT_B200_OK;
+        CK(ctx, fa.seqs.reserve(fa.seq_bytes + 64));
+        int e = launch_fasta_compact((const uint8_t *)fa.file.p, fa.len, (const uint64_t *)fa.start.p, N, (const uint64_t *)fa.seq_begin.p,
+                                     (const uint64_t *)fa.seq_off.p, (uint8_t *)fa.seqs.p, ctx->num_sms, ctx->stream);
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_fasta_compact launch: ") + cudaGetErrorString((cudaError_t)e));
+        ctx->launches++;
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        fa.compacted = true;
+        return TREAT_B200_OK;
+    };
+    bool in_place = !fa.multi && !ctx->tmpl_wide;
+    if (!in_place) {
+        int r = compact();
+        if (r) return r;
+    }
+    const uint64_t chunk = 1ull << 20;
+    int rc = TREAT_B200_OK;
+    uint64_t k = 0;
+    for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk, k++) {
+        const uint64_t cn = std::min(chunk, N - c0);
+        Slot &s = ctx->slot[k & 1];
+        cudaStream_t st = s.stream;
+        CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk, including its copies to the host
+        CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
+        if (want_ops) CK(ctx, s.ops.reserve(cn * (size_t)ops_stride));
+        const uint32_t *d_rc = (const uint32_t *)fa.rc.p + c0;
+        bool sat = false;
+        if (want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY)) CK(ctx, cudaMemsetAsync(s.ops.p, 0, cn * (size_t)ops_stride, st));
+        if (in_place) {
+            const ReadSpan span{(const uint64_t *)fa.seq_begin.p + c0, (const uint32_t *)fa.seq_len.p + c0, fa.len};
+            rc = run_chunk(ctx, s, (const uint8_t *)fa.file.p, nullptr, 0, d_rc, cn, fa.max_len, flags, (treat_b200_record *)s.rec.p,
+                           want_ops ? (uint8_t *)s.ops.p : nullptr, ops_stride, st, false, &sat, nullptr, 0, &span);
+            if (rc == TREAT_B200_OK && sat) {  // an edit-base run >= 255: the wide kernels read contiguous reads
+                if ((rc = compact())) break;
+                in_place = false;
+            }
+        }
+        if (rc == TREAT_B200_OK && !in_place) {
+            rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
+                           (treat_b200_record *)s.rec.p, want_ops ? (uint8_t *)s.ops.p : nullptr, ops_stride, st, false, &sat);
+            if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
+                rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
+                               (treat_b200_record *)s.rec.p, want_ops ? (uint8_t *)s.ops.p : nullptr, ops_stride, st, true, nullptr);
+        }
+        if (rc) break;
+        CK(ctx, cudaMemcpyAsync(rec + c0, s.rec.p, cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, st));
+        if (want_ops) CK(ctx, cudaMemcpyAsync(ops + c0 * (size_t)ops_stride, s.ops.p, cn * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream);
+        if (e != cudaSuccess && rc == TREAT_B200_OK) {
+            ctx->err = std::string("stream sync: ") + cudaGetErrorString(e);
+            rc = TREAT_B200_ERR_CUDA;
+        }
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return rc;
 }
 

@@ -40,6 +40,11 @@ struct PackParams {
     uint32_t *scalars;      // [0] max n (atomicMax), [1] any saturated edit-base run
     const uint32_t *tpk;    // packed path: the template's bases in the packed-read format (may be null: no marks)
     uint32_t tm;            // template bases
+    // reads that are not back to back (k_pack16 only; FASTA records read in place): read r = seqs[begin[r], begin[r] + len[r])
+    // inside the buffer seqs[0, span).  begin == nullptr: the off[] form above.
+    const uint64_t *begin;
+    const uint32_t *len;
+    uint64_t span;
 };
 
 // internal bit of the per-read flag byte written by k_pack: the read's stripped bases equal the template's
@@ -109,6 +114,17 @@ int plan_align(AlignParams &p, bool wide);
 int align_warps(const AlignParams &p, int max_smem);
 uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
 int launch_merge_summary(uint64_t *dst, uint64_t *src, uint32_t len, void *stream);
+// FASTA ingest (fasta_kernel.cu)
+int launch_fasta_mark(const uint8_t *file, uint64_t len, uint64_t tile0, uint64_t ntiles, uint32_t *tile_count,
+                      uint64_t *first_gt, int num_sms, void *stream);
+int launch_scan_u32(const uint32_t *in, uint64_t n, uint64_t *out, uint64_t *sums, void *stream);
+int launch_fasta_starts(const uint8_t *file, uint64_t len, uint64_t ntiles, const uint64_t *tile_off, const uint64_t *first_gt,
+                        uint64_t *start, int num_sms, void *stream);
+int launch_fasta_records(const uint8_t *file, uint64_t len, const uint64_t *start, uint64_t N, uint64_t *id_off, uint32_t *id_len,
+                         uint32_t *read_count, uint64_t *seq_begin, uint32_t *seq_len, uint32_t *scalars, int num_sms, void *stream);
+int launch_fasta_compact(const uint8_t *file, uint64_t len, const uint64_t *start, uint64_t N, const uint64_t *seq_begin,
+                         const uint64_t *seq_off, uint8_t *seqs, int num_sms, void *stream);
+constexpr uint32_t kFastaTileBytes = 4096;  // bytes per tile of the record-start count
 int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream);
 int configure_pack_kernels(int max_smem_optin);
 int configure_align_kernels(int max_smem_optin);

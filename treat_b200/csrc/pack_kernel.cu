@@ -230,7 +230,19 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_c
     const uint32_t lt = (1u << lane) - 1u;
     const uintptr_t base_addr = reinterpret_cast<uintptr_t>(p.seqs);
     // the bytes of p.seqs this launch may touch: [lo, hi)
-    const int64_t lo = p.N ? (int64_t)(p.off[0] - p.off_bias) : 0, hi = p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
+    const int64_t lo = p.begin ? 0 : p.N ? (int64_t)(p.off[0] - p.off_bias) : 0;
+    const int64_t hi = p.begin ? (int64_t)p.span : p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
+    // start and length of read r
+    auto where = [&](uint64_t r, uint64_t &b, uint32_t &L) {
+        if (p.begin) {
+            b = p.begin[r];
+            L = p.len[r];
+        } else {
+            const uint64_t o0 = p.off[r], o1 = p.off[r + 1];
+            b = o0 - p.off_bias;
+            L = (uint32_t)(o1 - o0);
+        }
+    };
     // the 16-byte aligned block at offset x of p.seqs (byte loads where it sticks out of [lo, hi))
     auto load_block = [&](int64_t x) -> uint4 {
         if (x >= lo && x + 16 <= hi) return *reinterpret_cast<const uint4 *>(p.seqs + x);
@@ -256,26 +268,16 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_c
     uint32_t L_cur = 0, L_nxt = 0;
     uint4 blk = make_uint4(0, 0, 0, 0);
     if (gw < p.N) {
-        const uint64_t o0 = p.off[gw], o1 = p.off[gw + 1];
-        b_cur = o0 - p.off_bias;
-        L_cur = (uint32_t)(o1 - o0);
+        where(gw, b_cur, L_cur);
         blk = first_block(b_cur, L_cur);
     }
-    if (gw + nw < p.N) {
-        const uint64_t o0 = p.off[gw + nw], o1 = p.off[gw + nw + 1];
-        b_nxt = o0 - p.off_bias;
-        L_nxt = (uint32_t)(o1 - o0);
-    }
+    if (gw + nw < p.N) where(gw + nw, b_nxt, L_nxt);
     for (uint64_t r = gw; r < p.N; r += nw) {
         uint4 blk_n = make_uint4(0, 0, 0, 0);
         uint64_t b_nn = 0;
         uint32_t L_nn = 0;
         if (r + nw < p.N) blk_n = first_block(b_nxt, L_nxt);
-        if (r + 2 * nw < p.N) {
-            const uint64_t o0 = p.off[r + 2 * nw], o1 = p.off[r + 2 * nw + 1];
-            b_nn = o0 - p.off_bias;
-            L_nn = (uint32_t)(o1 - o0);
-        }
+        if (r + 2 * nw < p.N) where(r + 2 * nw, b_nn, L_nn);
 
         const uint32_t L = L_cur;
         const uint32_t a = (uint32_t)((base_addr + b_cur) & 15u);
