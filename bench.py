@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fasta", action="store_true", help="skip the FASTA-ingest measurement")
     return ap.parse_args()
 
 
@@ -432,6 +433,56 @@ def run_ours(args):
                 log(int(i), h_rec[i], rec_dev[i])
             raise AssertionError("host-buffer and device-buffer paths disagree")
 
+    # ---- from the bytes of a FASTA file: parse on the GPU vs the host reader -------------------
+    fasta = None
+    if rank == 0 and world == 1 and not args.no_fasta and not args.no_e2e:
+        parts = []
+        for i in range(N):
+            parts.append(b">r%d_%d\n" % (i, rc[i]))
+            parts.append(seqs[int(off[i]):int(off[i + 1])].tobytes())
+            parts.append(b"\n")
+        text = b"".join(parts)
+        del parts
+        h_txt = alloc(len(text))
+        h_txt[:] = np.frombuffer(text, dtype=np.uint8)
+        id_off, id_len, rcs = alloc(N * 8).view(np.uint64), alloc(N * 4).view(np.uint32), alloc(N * 4).view(np.uint32)
+
+        def step_fasta():
+            n_rec, ml = C.c_uint64(), C.c_uint32()
+            cabi.check(cabi.lib().treat_b200_fasta_upload(eng._ctx, h_txt.ctypes.data, h_txt.size, C.byref(n_rec), C.byref(ml)), eng._ctx)
+            cabi.check(cabi.lib().treat_b200_fasta_align(eng._ctx, flags, h_rec.ctypes.data, h_ops.ctypes.data, stride,
+                                                         id_off.ctypes.data, id_len.ctypes.data, rcs.ctypes.data), eng._ctx)
+            return n_rec.value
+        h_rec[:] = np.zeros(1, dtype=cabi.RECORD_DTYPE)[0]
+        assert step_fasta() == N
+        if not (np.array_equal(h_rec, rec_dev) and np.array_equal(rcs, rc)):
+            raise AssertionError("FASTA-ingest path disagrees with the device-buffer path")
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 5))
+        for _ in range(reps):
+            step_fasta()
+        fa_s = (time.perf_counter() - t0) / reps
+        # the host reader on the same bytes (page-cached file on tmpfs), one thread like gofasta.SimpleParser
+        shm = "/dev/shm/treat_b200_bench_%d.fa" % os.getpid()
+        try:
+            with open(shm, "wb") as f:
+                f.write(text)
+            hh = C.c_void_p()
+            t0 = time.perf_counter()
+            cabi.check(cabi.lib().treat_b200_fasta_read(shm.encode(), C.byref(hh)))
+            host_s = time.perf_counter() - t0
+            assert cabi.lib().treat_b200_fasta_count(hh) == N
+            cabi.lib().treat_b200_fasta_free(hh)
+        finally:
+            if os.path.exists(shm):
+                os.unlink(shm)
+        fasta = {"value": N / fa_s, "unit": UNIT, "ms_per_step": 1e3 * fa_s, "file_bytes": len(text),
+                 "api": "treat_b200_fasta_upload + treat_b200_fasta_align: file bytes in pinned host memory -> records, "
+                        "gapped ops rows, id index, read counts (parse, NewFragment, NewAlignment on the GPU)",
+                 "host_parser": {"value": N / host_s, "unit": UNIT, "seconds": host_s,
+                                 "what": "treat_b200_fasta_read (one host thread) on the same file from tmpfs, parse only"}}
+        del text
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)  # the CPU port gets every host core
@@ -455,7 +506,7 @@ def run_ours(args):
             "reads_equal_to_template_bases": same_frac,
             # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
             "value_dp_every_read": world * N / ((pack_ms + align_ms) * 1e-3),
-            "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -333,7 +333,7 @@ def test_pack_lengths_and_alignments(eng, tmp_path):
         assert np.array_equal(gops, oops), pad
 
 
-def _fasta_device_vs_host(eng, tmp_path, text: bytes, tag: str, flags=None):
+def _fasta_device_vs_host(eng, tmp_path, text: bytes, tag: str, flags=None, tm=None):
     """upload_fasta/align_fasta (parse on the GPU) == read_fasta (host parser) + align_batch, field by field."""
     path = os.path.join(str(tmp_path), tag + ".fa")
     with open(path, "wb") as f:
@@ -350,7 +350,12 @@ def _fasta_device_vs_host(eng, tmp_path, text: bytes, tag: str, flags=None):
     if n:
         hrec, hops = eng.align_batch(host.seqs, host.offsets, host.read_counts, flags)
         assert np.array_equal(rec, hrec), tag
-        if hops is not None:
+        if hops is not None and flags & cabi.OPS_GAPPED_ONLY:  # rows of the gapped reads only
+            g = hrec["indel"] != 0
+            frec, fops = eng.align_batch(host.seqs, host.offsets, host.read_counts, flags & ~cabi.OPS_GAPPED_ONLY)
+            used = (len(tm.Bases) + int(hrec["n_bases"].max()) + 3) // 4
+            assert g.any() and np.array_equal(ops[g][:, :used], fops[g][:, :used]), tag
+        elif hops is not None:
             assert np.array_equal(ops[:, :hops.shape[1]], hops), tag
     return n
 
@@ -403,6 +408,7 @@ def test_fasta_ingest_on_device(eng, tmp_path):
         buf += seqs[int(off[i]):int(off[i + 1])].tobytes()
         buf += b"\n"
     assert _fasta_device_vs_host(eng, tmp_path, bytes(buf), "large", cabi.NO_SUMMARY) == 200000
+    _fasta_device_vs_host(eng, tmp_path, bytes(buf), "large_gapped_rows", cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY | cabi.NO_SUMMARY, tm)
     # summaries accumulate like the host-buffer call's
     eng.reset_summary()
     eng.align_fasta(cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY, want_ids=False)

@@ -636,6 +636,29 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, opts(slot_own_ops));
 }
 
+// pinned landing buffers for `rows` compacted ops rows of a slot
+static int reserve_gap_rows(treat_b200_ctx *ctx, Slot &s, uint32_t rows)
+{
+    const size_t need_rows = (size_t)rows * s.dev_stride, need_idx = (size_t)rows * 4;
+    if (need_rows > s.gap_rows_cap) {
+        CK(ctx, cudaStreamSynchronize(s.stream));
+        if (s.h_gap_rows) cudaFreeHost(s.h_gap_rows);
+        s.h_gap_rows = nullptr;
+        s.gap_rows_cap = 0;
+        CK(ctx, cudaMallocHost((void **)&s.h_gap_rows, need_rows + need_rows / 4 + 4096));
+        s.gap_rows_cap = need_rows + need_rows / 4 + 4096;
+    }
+    if (need_idx > s.gap_idx_cap) {
+        CK(ctx, cudaStreamSynchronize(s.stream));
+        if (s.h_gap_idx) cudaFreeHost(s.h_gap_idx);
+        s.h_gap_idx = nullptr;
+        s.gap_idx_cap = 0;
+        CK(ctx, cudaMallocHost((void **)&s.h_gap_idx, need_idx + need_idx / 4 + 4096));
+        s.gap_idx_cap = need_idx + need_idx / 4 + 4096;
+    }
+    return TREAT_B200_OK;
+}
+
 int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
                                   const uint32_t *d_read_count, uint64_t N, uint32_t max_len, uint32_t flags,
                                   treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, void *stream)
@@ -687,27 +710,6 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     double t_wait_slot = 0, t_enqueue = 0;
     int redone = 0;
 
-    // pinned landing buffers for `rows` compacted ops rows of a slot
-    auto reserve_gap = [&](Slot &s, uint32_t rows) -> int {
-        const size_t need_rows = (size_t)rows * s.dev_stride, need_idx = (size_t)rows * 4;
-        if (need_rows > s.gap_rows_cap) {
-            CK(ctx, cudaStreamSynchronize(s.stream));
-            if (s.h_gap_rows) cudaFreeHost(s.h_gap_rows);
-            s.h_gap_rows = nullptr;
-            s.gap_rows_cap = 0;
-            CK(ctx, cudaMallocHost((void **)&s.h_gap_rows, need_rows + need_rows / 4 + 4096));
-            s.gap_rows_cap = need_rows + need_rows / 4 + 4096;
-        }
-        if (need_idx > s.gap_idx_cap) {
-            CK(ctx, cudaStreamSynchronize(s.stream));
-            if (s.h_gap_idx) cudaFreeHost(s.h_gap_idx);
-            s.h_gap_idx = nullptr;
-            s.gap_idx_cap = 0;
-            CK(ctx, cudaMallocHost((void **)&s.h_gap_idx, need_idx + need_idx / 4 + 4096));
-            s.gap_idx_cap = need_idx + need_idx / 4 + 4096;
-        }
-        return TREAT_B200_OK;
-    };
     // copy a finished chunk's results to the caller's buffers (async on the slot stream)
     auto copy_out = [&](Slot &s) -> int {
         CK(ctx, cudaMemcpyAsync(rec + s.c0, s.rec.p, s.cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, s.stream));
@@ -719,7 +721,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         if (sparse) {
             // the number of gapped reads is only known on the device: copy a guess now, the rest (if any) in place_rows
             const uint32_t head = (uint32_t)std::min<uint64_t>(s.cn, std::max<uint32_t>(4096u, 2u * ctx->gap_hint));
-            int r = reserve_gap(s, head);
+            int r = reserve_gap_rows(ctx, s, head);
             if (r) return r;
             CK(ctx, cudaMemcpyAsync(s.h_gap_idx, s.ops_idx.p, head * 4ull, cudaMemcpyDeviceToHost, s.stream));
             CK(ctx, cudaMemcpyAsync(s.h_gap_rows, s.ops.p, head * (size_t)s.dev_stride, cudaMemcpyDeviceToHost, s.stream));
@@ -742,7 +744,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
             const uint32_t head = s.gap_head;
             std::vector<uint8_t> keep_rows(s.h_gap_rows, s.h_gap_rows + head * (size_t)s.dev_stride);
             std::vector<uint32_t> keep_idx(s.h_gap_idx, s.h_gap_idx + head);
-            int r = reserve_gap(s, cnt);
+            int r = reserve_gap_rows(ctx, s, cnt);
             if (r) return r;
             memcpy(s.h_gap_rows, keep_rows.data(), keep_rows.size());
             memcpy(s.h_gap_idx, keep_idx.data(), keep_idx.size() * 4);
@@ -995,14 +997,17 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
         cudaStream_t st = s.stream;
         CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk, including its copies to the host
         CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
-        if (want_ops) CK(ctx, s.ops.reserve(cn * (size_t)ops_stride));
+        // ops: every row at the caller's stride, or (OPS_GAPPED_ONLY) only the gapped reads' rows, compacted by the kernels
+        const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
+        if (want_ops && !sparse) CK(ctx, s.ops.reserve(cn * (size_t)ops_stride));
+        uint8_t *d_ops = want_ops && !sparse ? (uint8_t *)s.ops.p : nullptr;
+        const uint32_t d_stride = sparse ? 0u : ops_stride;
         const uint32_t *d_rc = (const uint32_t *)fa.rc.p + c0;
         bool sat = false;
-        if (want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY)) CK(ctx, cudaMemsetAsync(s.ops.p, 0, cn * (size_t)ops_stride, st));
         if (in_place) {
             const ReadSpan span{(const uint64_t *)fa.seq_begin.p + c0, (const uint32_t *)fa.seq_len.p + c0, fa.len};
             rc = run_chunk(ctx, s, (const uint8_t *)fa.file.p, nullptr, 0, d_rc, cn, fa.max_len, flags, (treat_b200_record *)s.rec.p,
-                           want_ops ? (uint8_t *)s.ops.p : nullptr, ops_stride, st, false, &sat, nullptr, 0, &span);
+                           d_ops, d_stride, st, false, &sat, &s.dev_stride, 0, &span);
             if (rc == TREAT_B200_OK && sat) {  // an edit-base run >= 255: the wide kernels read contiguous reads
                 if ((rc = compact())) break;
                 in_place = false;
@@ -1010,14 +1015,29 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
         }
         if (rc == TREAT_B200_OK && !in_place) {
             rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
-                           (treat_b200_record *)s.rec.p, want_ops ? (uint8_t *)s.ops.p : nullptr, ops_stride, st, false, &sat);
+                           (treat_b200_record *)s.rec.p, d_ops, d_stride, st, false, &sat, &s.dev_stride);
             if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
                 rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
-                               (treat_b200_record *)s.rec.p, want_ops ? (uint8_t *)s.ops.p : nullptr, ops_stride, st, true, nullptr);
+                               (treat_b200_record *)s.rec.p, d_ops, d_stride, st, true, nullptr, &s.dev_stride);
         }
         if (rc) break;
         CK(ctx, cudaMemcpyAsync(rec + c0, s.rec.p, cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, st));
-        if (want_ops) CK(ctx, cudaMemcpyAsync(ops + c0 * (size_t)ops_stride, s.ops.p, cn * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
+        if (want_ops && !sparse)
+            CK(ctx, cudaMemcpyAsync(ops + c0 * (size_t)ops_stride, s.ops.p, cn * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
+        if (sparse) {  // fetch the compacted rows of the gapped reads and put them where they belong
+            CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, st));
+            CK(ctx, cudaStreamSynchronize(st));
+            const uint32_t cnt = s.h_scalars[4];
+            if (cnt) {
+                int r = reserve_gap_rows(ctx, s, cnt);
+                if (r) return r;
+                CK(ctx, cudaMemcpyAsync(s.h_gap_idx, s.ops_idx.p, cnt * 4ull, cudaMemcpyDeviceToHost, st));
+                CK(ctx, cudaMemcpyAsync(s.h_gap_rows, s.ops.p, cnt * (size_t)s.dev_stride, cudaMemcpyDeviceToHost, st));
+                CK(ctx, cudaStreamSynchronize(st));
+                for (uint32_t q = 0; q < cnt; q++)
+                    memcpy(ops + (c0 + s.h_gap_idx[q]) * (size_t)ops_stride, s.h_gap_rows + q * (size_t)s.dev_stride, s.dev_stride);
+            }
+        }
     }
     for (int i = 0; i < 2; i++) {
         cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream);

@@ -129,6 +129,7 @@ bool ReadFasta(const std::string &path, FastaBatch *out, std::string *err)
     out->seqs.clear();
     out->offsets.assign(1, 0);
     out->read_counts.clear();
+    out->seqs.reserve(data.size());
     size_t pos = data.find('>');  // bytes before the first record are skipped
     bool open = false;
     while (pos != std::string::npos && pos < data.size()) {
