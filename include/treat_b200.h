@@ -249,7 +249,31 @@ const uint32_t *treat_b200_fasta_read_counts(const treat_b200_fasta *f);
  * Record semantics are those of treat_b200_fasta_read (which runs on the host). */
 int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint64_t *n_records, uint32_t *max_seq_len);
 int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_record *rec, uint8_t *ops, uint32_t ops_stride,
-                           uint64_t *id_off, uint32_t *id_len, uint32_t *read_count);
+                           uint64_t *id_off, uint32_t *id_len, uint32_t *read_count, uint64_t *seq_off, uint32_t *seq_len);
+/* (seq_off, seq_len: where each record's sequence starts in the file and how many bytes it has without line breaks;
+ * record.junc_seq_off counts from there when the record has a single sequence line.)
+ *
+ * Streaming form: one call, nothing to size in advance.  The bytes are cut at record starts into pieces of ~32 MB; copy,
+ * index, alignment and delivery of four pieces overlap; every finished piece is handed to `sink` in file order (pointers
+ * are valid during the call only; a non-zero return stops the run).  This is the shape of the reference's loop
+ * (storage.go:738-785): the sink is where MarshalBinary + Put go. */
+typedef struct treat_b200_fasta_piece {
+    uint64_t first_record;         /* number of the piece's first record in the file */
+    uint64_t n;                    /* records in this piece */
+    const treat_b200_record *rec;  /* [n] */
+    const uint64_t *id_off;        /* [n] Id = file[id_off, id_off + id_len) */
+    const uint64_t *seq_off;       /* [n] first sequence byte in the file */
+    const uint32_t *id_len, *read_count, *seq_len; /* [n] */
+    const uint8_t *ops;            /* WANT_OPS: n_ops_rows rows of ops_stride bytes, else NULL */
+    const uint32_t *ops_index;     /* OPS_GAPPED_ONLY: row q belongs to record ops_index[q] of the piece; NULL: row q = record q */
+    uint64_t n_ops_rows;
+    uint32_t ops_stride;
+    uint32_t seq_in_place;         /* 1: every sequence of the piece is file[seq_off, seq_off + seq_len) (no line break inside) */
+} treat_b200_fasta_piece;
+typedef int (*treat_b200_fasta_sink)(void *user, const treat_b200_fasta_piece *piece);
+/* ops_stride: bytes per ops row when every record gets one (0: chosen per piece from its longest read, see piece->ops_stride) */
+int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, uint32_t ops_stride,
+                            treat_b200_fasta_sink sink, void *user, uint64_t *n_records);
 
 /* align.go:388-520 Alignment.WriteTo from a device result: text for one read.  Returns the
  * number of bytes needed; writes at most cap bytes to out (call twice or size generously). */

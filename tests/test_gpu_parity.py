@@ -6,6 +6,8 @@ import random
 import numpy as np
 import pytest
 
+os.environ.setdefault("TREAT_B200_FASTA_PIECE", "300000")  # small pieces: treat_b200_fasta_stream cuts even the test files
+
 import treat_b200 as T
 from treat_b200 import cabi, synth
 from oracle import oracle as O
@@ -357,6 +359,35 @@ def _fasta_device_vs_host(eng, tmp_path, text: bytes, tag: str, flags=None, tm=N
             assert g.any() and np.array_equal(ops[g][:, :used], fops[g][:, :used]), tag
         elif hops is not None:
             assert np.array_equal(ops[:, :hops.shape[1]], hops), tag
+    # the streaming form: same records, ids, counts and ops, delivered piece by piece in file order
+    pieces, total = eng.stream_fasta(text, flags)
+    assert total == n and sum(p["n"] for p in pieces) == n, tag
+    if n:
+        assert [p["first_record"] for p in pieces] == list(np.cumsum([0] + [p["n"] for p in pieces[:-1]])), tag
+        srec = np.concatenate([p["rec"] for p in pieces])
+        assert np.array_equal(srec, rec), tag
+        assert np.array_equal(np.concatenate([p["read_count"] for p in pieces]), rcs), tag
+        sid = [text[int(o):int(o) + int(l)].decode("latin-1") for p in pieces for o, l in zip(p["id_off"], p["id_len"])]
+        assert sid == host.ids, tag
+        slen = np.concatenate([p["seq_len"] for p in pieces])
+        assert np.array_equal(slen, lens), tag
+        for p in pieces:  # single-line sequences sit in the file exactly where seq_off says
+            if p["seq_in_place"]:
+                for i in range(0, p["n"], max(1, p["n"] // 50)):
+                    r = p["first_record"] + i
+                    assert text[int(p["seq_off"][i]):int(p["seq_off"][i]) + int(p["seq_len"][i])] == host.seq(r), tag
+        if flags & cabi.WANT_OPS:
+            if flags & cabi.OPS_GAPPED_ONLY:
+                for p in pieces:
+                    g = np.nonzero(p["rec"]["indel"] != 0)[0]
+                    assert sorted(p["ops_index"].tolist()) == g.tolist(), tag
+                    w = p["ops_stride"]
+                    for q, i in enumerate(p["ops_index"]):
+                        assert np.array_equal(p["ops"][q], ops[p["first_record"] + int(i)][:w]), tag
+            else:
+                for p in pieces:
+                    w = min(p["ops_stride"], ops.shape[1])
+                    assert np.array_equal(p["ops"][:, :w], ops[p["first_record"]:p["first_record"] + p["n"], :w]), tag
     return n
 
 

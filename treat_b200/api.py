@@ -432,12 +432,45 @@ class Aligner:
         id_len = np.zeros(N, dtype=np.uint32)
         rcs = np.zeros(N, dtype=np.uint32)
         check(lib().treat_b200_fasta_align(self._ctx, flags, rec.ctypes.data, ops.ctypes.data if (flags & WANT_OPS) else None, stride,
-                                           id_off.ctypes.data, id_len.ctypes.data, rcs.ctypes.data), self._ctx)
+                                           id_off.ctypes.data, id_len.ctypes.data, rcs.ctypes.data, None, None), self._ctx)
         ids = None
         if want_ids:
             raw = data.tobytes()
             ids = [raw[int(o):int(o) + int(n)].decode("latin-1") for o, n in zip(id_off, id_len)]
         return rec, (ops if flags & WANT_OPS else None), ids, rcs
+
+    def stream_fasta(self, data, flags: int = 0, ops_stride: int = 0):
+        """treat_b200_fasta_stream: yields one dict of numpy arrays (copies) per piece, in file order."""
+        from .cabi import FASTA_SINK
+        if isinstance(data, (bytes, bytearray)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        pieces = []
+
+        def arr(ptr, n, dt):
+            if not ptr or not n:
+                return np.zeros(0, dtype=dt)
+            nbytes = int(n) * np.dtype(dt).itemsize
+            return np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=dt).copy()
+
+        def sink(_user, pp):
+            q = pp.contents
+            n = q.n
+            d = dict(first_record=q.first_record, n=n, rec=arr(q.rec, n, RECORD_DTYPE), id_off=arr(q.id_off, n, np.uint64),
+                     seq_off=arr(q.seq_off, n, np.uint64), id_len=arr(q.id_len, n, np.uint32), read_count=arr(q.read_count, n, np.uint32),
+                     seq_len=arr(q.seq_len, n, np.uint32), ops_stride=q.ops_stride, seq_in_place=bool(q.seq_in_place), ops=None, ops_index=None)
+            if q.ops and q.n_ops_rows:
+                d["ops"] = arr(q.ops, q.n_ops_rows * q.ops_stride, np.uint8).reshape(q.n_ops_rows, q.ops_stride)
+            elif q.ops_stride:
+                d["ops"] = np.zeros((0, q.ops_stride), dtype=np.uint8)
+            if q.ops_index:
+                d["ops_index"] = arr(q.ops_index, q.n_ops_rows, np.uint32)
+            pieces.append(d)
+            return 0
+        cb = FASTA_SINK(sink)
+        total = C.c_uint64()
+        check(lib().treat_b200_fasta_stream(self._ctx, data.ctypes.data, data.size, flags, ops_stride, cb, None, C.byref(total)), self._ctx)
+        return pieces, total.value
 
     def synchronize(self) -> None:
         check(lib().treat_b200_synchronize(self._ctx), self._ctx)

@@ -46,6 +46,17 @@ class Packed(C.Structure):
     ]
 
 
+class FastaPiece(C.Structure):
+    """treat_b200_fasta_piece"""
+    _fields_ = [
+        ("first_record", C.c_uint64), ("n", C.c_uint64), ("rec", C.c_void_p), ("id_off", C.c_void_p), ("seq_off", C.c_void_p),
+        ("id_len", C.c_void_p), ("read_count", C.c_void_p), ("seq_len", C.c_void_p), ("ops", C.c_void_p), ("ops_index", C.c_void_p),
+        ("n_ops_rows", C.c_uint64), ("ops_stride", C.c_uint32), ("seq_in_place", C.c_uint32),
+    ]
+
+
+FASTA_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(FastaPiece))
+
 # name -> (restype, argtypes); must list every function include/treat_b200.h declares
 _P, _U8P, _SZ = C.c_void_p, C.c_void_p, C.c_size_t
 SIGNATURES = {
@@ -63,7 +74,8 @@ SIGNATURES = {
     "treat_b200_ops_stride": (C.c_uint32, [_P, C.c_uint32]),
     "treat_b200_synchronize": (C.c_int, [_P]),
     "treat_b200_fasta_upload": (C.c_int, [_P, _U8P, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
-    "treat_b200_fasta_align": (C.c_int, [_P, C.c_uint32, _P, _U8P, C.c_uint32, _P, _P, _P]),
+    "treat_b200_fasta_align": (C.c_int, [_P, C.c_uint32, _P, _U8P, C.c_uint32, _P, _P, _P, _P, _P]),
+    "treat_b200_fasta_stream": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
     "treat_b200_packed_layout": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(Packed)]),
     "treat_b200_pack_device": (C.c_int, [_P, _U8P, _P, C.POINTER(Packed), _P]),
     "treat_b200_align_packed_device": (C.c_int, [_P, C.POINTER(Packed), _P, C.c_uint32, _P, _U8P, C.c_uint32, _P]),

@@ -22,6 +22,7 @@ constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
 constexpr uint64_t kChunkReads = 1u << 16;  // reads per pipelined chunk of treat_b200_align_batch
 constexpr int kSlots = 4;                   // most chunks in flight: H2D, kernels and D2H of different chunks overlap
 constexpr size_t kScalarBytes = 32;         // per-slot device scalars (8 words)
+constexpr int kFastaSlots = 6;              // pieces in flight of treat_b200_fasta_stream: two being copied, index, align, deliver
 
 struct DevBuf {
     void *p = nullptr;
@@ -58,6 +59,8 @@ struct Slot {
     uint32_t gap_head = 0;     // rows copied ahead of knowing how many there are
     bool scatter = false;      // the chunk's gapped-read count (and compacted rows) still have to be consumed on the host
     bool sparse = false;       // this chunk returns only the gapped reads' ops rows, compacted
+    uint8_t *land = nullptr;   // treat_b200_fasta_stream: pinned landing buffer of a piece's results
+    size_t land_cap = 0;
     DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
     uint32_t *scalars = nullptr;    // device [8]: max n, any saturated run, reads skipped by a speculative launch, reads listed
                                     // for the DP, compacted ops rows
@@ -73,6 +76,7 @@ struct Slot {
         if (h_scalars) cudaFreeHost(h_scalars);
         if (h_gap_rows) cudaFreeHost(h_gap_rows);
         if (h_gap_idx) cudaFreeHost(h_gap_idx);
+        if (land) cudaFreeHost(land);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -89,6 +93,7 @@ struct FastaDev {
     DevBuf file, tile_count, tile_off, sums, start, id_off, id_len, rc, seq_begin, seq_len, seq_off, seqs, scal;
     uint64_t len = 0, N = 0, seq_bytes = 0;
     uint32_t max_len = 0;
+    uint64_t *h = nullptr;   // pinned [8]: line-start '>' count, first '>', (longest sequence | multi-line flag << 32), sequence bytes
     bool multi = false;      // some record has more than one sequence line: reads are compacted before packing
     bool compacted = false;  // seqs / seq_off hold the compacted reads
     bool open = false;
@@ -96,6 +101,8 @@ struct FastaDev {
     {
         for (DevBuf *b : {&file, &tile_count, &tile_off, &sums, &start, &id_off, &id_len, &rc, &seq_begin, &seq_len, &seq_off, &seqs, &scal})
             b->release();
+        if (h) cudaFreeHost(h);
+        h = nullptr;
     }
 };
 
@@ -124,7 +131,9 @@ struct treat_b200_ctx {
     Slot slot[kSlots];
     // scratch for the device-resident entry point
     Slot dev_slot;
-    FastaDev fasta;
+    FastaDev fasta;               // treat_b200_fasta_upload / treat_b200_fasta_align
+    FastaDev fasta_slot[kFastaSlots];  // pieces in flight of treat_b200_fasta_stream
+    Slot fslot[kFastaSlots];
 };
 
 #define CK(ctx, expr)                                                                   \
@@ -212,6 +221,8 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     for (Slot &sl : ctx->slot) sl.release();
     ctx->dev_slot.release();
     ctx->fasta.release();
+    for (FastaDev &f : ctx->fasta_slot) f.release();
+    for (Slot &sl : ctx->fslot) sl.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -346,6 +357,8 @@ int treat_b200_synchronize(treat_b200_ctx *ctx)
     for (Slot &sl : ctx->slot)
         if (sl.stream) CK(ctx, cudaStreamSynchronize(sl.stream));
     if (ctx->dev_slot.stream) CK(ctx, cudaStreamSynchronize(ctx->dev_slot.stream));
+    for (Slot &sl : ctx->fslot)
+        if (sl.stream) CK(ctx, cudaStreamSynchronize(sl.stream));
     return TREAT_B200_OK;
 }
 
@@ -868,19 +881,17 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
 // ---------------------------------------------------------------------------------------------
 // FASTA bytes in, records out (gofasta.SimpleParser + parseMergeCount + NewFragment + NewAlignment on the device)
 // ---------------------------------------------------------------------------------------------
-int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint64_t *n_records, uint32_t *max_seq_len)
+// stage A: copy the bytes, count the record starts of every tile, scan; the two numbers the host needs land in fa.h
+static int fasta_stage_copy_count(treat_b200_ctx *ctx, FastaDev &fa, const uint8_t *fasta, uint64_t len, cudaStream_t st)
 {
-    if (!ctx || (len && !fasta) || !n_records) return TREAT_B200_ERR_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
-    FastaDev &fa = ctx->fasta;
-    cudaStream_t st = ctx->stream;
     fa.open = false;
     fa.compacted = false;
     fa.len = len;
     fa.N = 0;
     fa.max_len = 0;
-    *n_records = 0;
-    if (max_seq_len) *max_seq_len = 0;
+    fa.seq_bytes = 0;
+    fa.multi = false;
+    if (!fa.h) CK(ctx, cudaMallocHost((void **)&fa.h, 64));
     const uint64_t ntiles = (len + kFastaTileBytes - 1) / kFastaTileBytes;
     CK(ctx, fa.file.reserve(len + 64));
     CK(ctx, fa.tile_count.reserve((ntiles + 1) * 4));
@@ -888,10 +899,12 @@ int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
     CK(ctx, fa.sums.reserve((ntiles / 2048 + 4) * 8));
     CK(ctx, fa.scal.reserve(64));
     uint64_t *d_first = (uint64_t *)fa.scal.p;
-    uint32_t *d_scal = (uint32_t *)((uint8_t *)fa.scal.p + 16);
-    CK(ctx, cudaMemsetAsync(fa.scal.p, 0xff, 8, st));             // first '>' = none
+    CK(ctx, cudaMemsetAsync(fa.scal.p, 0xff, 8, st));  // first '>' = none
     CK(ctx, cudaMemsetAsync((uint8_t *)fa.scal.p + 8, 0, 56, st));
-    // upload in pieces; the record starts of a piece are counted while the next piece is on the bus
+    fa.h[0] = 0;
+    fa.h[1] = ~0ull;
+    if (len == 0) return TREAT_B200_OK;
+    // in pieces: the record starts of a piece are counted while the next piece is on the bus
     const uint64_t piece = 32ull << 20;  // a multiple of the tile size
     for (uint64_t o = 0; o < len; o += piece) {
         const uint64_t nb = std::min(piece, len - o);
@@ -901,126 +914,164 @@ int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
         if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_fasta_mark launch: ") + cudaGetErrorString((cudaError_t)e));
         ctx->launches++;
     }
-    if (len == 0) {
-        fa.open = true;
-        return TREAT_B200_OK;
-    }
     int e = launch_scan_u32((const uint32_t *)fa.tile_count.p, ntiles, (uint64_t *)fa.tile_off.p, (uint64_t *)fa.sums.p, st);
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches += 3;
-    uint64_t h[2] = {0, 0};  // line-start '>' count, first '>' position
-    CK(ctx, cudaMemcpyAsync(&h[0], (uint64_t *)fa.tile_off.p + ntiles, 8, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaMemcpyAsync(&h[1], d_first, 8, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
-    const uint64_t first = h[1];
+    CK(ctx, cudaMemcpyAsync(&fa.h[0], (uint64_t *)fa.tile_off.p + ntiles, 8, cudaMemcpyDeviceToHost, st));  // line-start '>' count
+    CK(ctx, cudaMemcpyAsync(&fa.h[1], d_first, 8, cudaMemcpyDeviceToHost, st));                             // first '>' position
+    return TREAT_B200_OK;
+}
+
+// stage B (stage A complete on the host): record starts, ids, merge counts, sequence begin / length, scan; scalars land in fa.h
+static int fasta_stage_index(treat_b200_ctx *ctx, FastaDev &fa, const uint8_t *fasta, cudaStream_t st)
+{
+    const uint64_t len = fa.len, first = fa.h[1];
     const bool extra = first < len && !(first == 0 || fasta[first - 1] == '\n');  // the first '>' sits inside a line
-    const uint64_t N = h[0] + (extra ? 1 : 0);
+    const uint64_t N = len ? fa.h[0] + (extra ? 1 : 0) : 0;
     if (N > 0x7fffffffull) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "fasta: more than 2^31 records");
     fa.N = N;
-    if (N) {
-        CK(ctx, fa.start.reserve(N * 8));
-        CK(ctx, fa.id_off.reserve(N * 8));
-        CK(ctx, fa.id_len.reserve(N * 4));
-        CK(ctx, fa.rc.reserve(N * 4));
-        CK(ctx, fa.seq_begin.reserve(N * 8));
-        CK(ctx, fa.seq_len.reserve(N * 4));
-        CK(ctx, fa.seq_off.reserve((N + 1) * 8));
-        CK(ctx, fa.sums.reserve((std::max(N, ntiles) / 2048 + 4) * 8));
-        e = launch_fasta_starts((const uint8_t *)fa.file.p, len, ntiles, (const uint64_t *)fa.tile_off.p, d_first, (uint64_t *)fa.start.p,
+    fa.h[2] = fa.h[3] = 0;
+    if (!N) return TREAT_B200_OK;
+    const uint64_t ntiles = (len + kFastaTileBytes - 1) / kFastaTileBytes;
+    uint64_t *d_first = (uint64_t *)fa.scal.p;
+    uint32_t *d_scal = (uint32_t *)((uint8_t *)fa.scal.p + 16);
+    CK(ctx, fa.start.reserve(N * 8));
+    CK(ctx, fa.id_off.reserve(N * 8));
+    CK(ctx, fa.id_len.reserve(N * 4));
+    CK(ctx, fa.rc.reserve(N * 4));
+    CK(ctx, fa.seq_begin.reserve(N * 8));
+    CK(ctx, fa.seq_len.reserve(N * 4));
+    CK(ctx, fa.seq_off.reserve((N + 1) * 8));
+    CK(ctx, fa.sums.reserve((std::max(N, ntiles) / 2048 + 4) * 8));
+    int e = launch_fasta_starts((const uint8_t *)fa.file.p, len, ntiles, (const uint64_t *)fa.tile_off.p, d_first, (uint64_t *)fa.start.p,
                                 ctx->num_sms, st);
-        if (!e)
-            e = launch_fasta_records((const uint8_t *)fa.file.p, len, (const uint64_t *)fa.start.p, N, (uint64_t *)fa.id_off.p,
-                                     (uint32_t *)fa.id_len.p, (uint32_t *)fa.rc.p, (uint64_t *)fa.seq_begin.p, (uint32_t *)fa.seq_len.p,
-                                     d_scal, ctx->num_sms, st);
-        if (!e) e = launch_scan_u32((const uint32_t *)fa.seq_len.p, N, (uint64_t *)fa.seq_off.p, (uint64_t *)fa.sums.p, st);
-        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("fasta index launch: ") + cudaGetErrorString((cudaError_t)e));
-        ctx->launches += 5;
-        uint32_t hs[2] = {0, 0};
-        CK(ctx, cudaMemcpyAsync(hs, d_scal, 8, cudaMemcpyDeviceToHost, st));
-        CK(ctx, cudaMemcpyAsync(&fa.seq_bytes, (uint64_t *)fa.seq_off.p + N, 8, cudaMemcpyDeviceToHost, st));
-        CK(ctx, cudaStreamSynchronize(st));
-        fa.max_len = hs[0];
-        fa.multi = hs[1] != 0;
-    }
+    if (!e)
+        e = launch_fasta_records((const uint8_t *)fa.file.p, len, (const uint64_t *)fa.start.p, N, (uint64_t *)fa.id_off.p,
+                                 (uint32_t *)fa.id_len.p, (uint32_t *)fa.rc.p, (uint64_t *)fa.seq_begin.p, (uint32_t *)fa.seq_len.p, d_scal,
+                                 ctx->num_sms, st);
+    if (!e) e = launch_scan_u32((const uint32_t *)fa.seq_len.p, N, (uint64_t *)fa.seq_off.p, (uint64_t *)fa.sums.p, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("fasta index launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches += 5;
+    CK(ctx, cudaMemcpyAsync(&fa.h[2], d_scal, 8, cudaMemcpyDeviceToHost, st));                          // longest sequence, multi-line flag
+    CK(ctx, cudaMemcpyAsync(&fa.h[3], (uint64_t *)fa.seq_off.p + N, 8, cudaMemcpyDeviceToHost, st));   // sequence bytes
+    return TREAT_B200_OK;
+}
+
+// stage B complete on the host
+static void fasta_index_done(FastaDev &fa)
+{
+    fa.max_len = (uint32_t)(fa.h[2] & 0xffffffffu);
+    fa.multi = (fa.h[2] >> 32) != 0;
+    fa.seq_bytes = fa.h[3];
     fa.open = true;
-    *n_records = N;
+}
+
+// stage C: align records [c0, c0 + cn) of an indexed file on slot s: records (and ops) end up in the slot's device buffers.
+// sparse: OPS_GAPPED_ONLY rows compacted in s.ops with s.ops_idx and the count in s.scalars[4]; else rows at ops_stride.
+// spec_ncap != 0 (in-place reads only): no host sync -- the align kernel is sized for spec_ncap, accumulates into the slot's
+// private summary and counts what it could not hold; the caller validates s.h_scalars later (see run_chunk).
+static int fasta_align_chunk(treat_b200_ctx *ctx, FastaDev &fa, Slot &s, uint64_t c0, uint64_t cn, uint32_t flags, uint32_t ops_stride,
+                             bool *in_place, uint32_t spec_ncap = 0)
+{
+    cudaStream_t st = s.stream;
+    const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
+    const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
+    CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
+    if (want_ops && !sparse) CK(ctx, s.ops.reserve(cn * (size_t)ops_stride));
+    uint8_t *d_ops = want_ops && !sparse ? (uint8_t *)s.ops.p : nullptr;
+    const uint32_t d_stride = sparse ? 0u : ops_stride;
+    const uint32_t *d_rc = (const uint32_t *)fa.rc.p + c0;
+    // reads with line breaks inside (or a template that needs the wide path) are first copied into one contiguous buffer
+    auto compact = [&]() -> int {
+        if (fa.compacted) return TREAT_B200_OK;
+        CK(ctx, fa.seqs.reserve(fa.seq_bytes + 64));
+        int e = launch_fasta_compact((const uint8_t *)fa.file.p, fa.len, (const uint64_t *)fa.start.p, fa.N, (const uint64_t *)fa.seq_begin.p,
+                                     (const uint64_t *)fa.seq_off.p, (uint8_t *)fa.seqs.p, ctx->num_sms, st);
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_fasta_compact launch: ") + cudaGetErrorString((cudaError_t)e));
+        ctx->launches++;
+        fa.compacted = true;
+        return TREAT_B200_OK;
+    };
+    int rc = TREAT_B200_OK;
+    bool sat = false;
+    if (*in_place) {
+        const ReadSpan span{(const uint64_t *)fa.seq_begin.p + c0, (const uint32_t *)fa.seq_len.p + c0, fa.len};
+        rc = run_chunk(ctx, s, (const uint8_t *)fa.file.p, nullptr, 0, d_rc, cn, fa.max_len, flags, (treat_b200_record *)s.rec.p, d_ops,
+                       d_stride, st, false, &sat, &s.dev_stride, spec_ncap, &span);
+        if (spec_ncap) return rc;
+        if (rc == TREAT_B200_OK && sat) *in_place = false;  // an edit-base run >= 255: the wide kernels read contiguous reads
+    }
+    if (rc == TREAT_B200_OK && !*in_place) {
+        if ((rc = compact())) return rc;
+        rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
+                       (treat_b200_record *)s.rec.p, d_ops, d_stride, st, false, &sat, &s.dev_stride);
+        if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
+            rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
+                           (treat_b200_record *)s.rec.p, d_ops, d_stride, st, true, nullptr, &s.dev_stride);
+    }
+    return rc;
+}
+
+static int fasta_check_align(treat_b200_ctx *ctx, const FastaDev &fa, uint32_t flags, uint32_t ops_stride)
+{
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    if (fa.max_len > kMaxReadLen) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: read longer than 16384");
+    if ((flags & TREAT_B200_WANT_OPS) && (ops_stride < treat_b200_ops_stride(ctx, fa.max_len) || ops_stride % 16))
+        return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small (see treat_b200_ops_stride)");
+    return TREAT_B200_OK;
+}
+
+int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint64_t *n_records, uint32_t *max_seq_len)
+{
+    if (!ctx || (len && !fasta) || !n_records) return TREAT_B200_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    FastaDev &fa = ctx->fasta;
+    cudaStream_t st = ctx->stream;
+    *n_records = 0;
+    if (max_seq_len) *max_seq_len = 0;
+    int rc = fasta_stage_copy_count(ctx, fa, fasta, len, st);
+    if (rc) return rc;
+    CK(ctx, cudaStreamSynchronize(st));
+    if ((rc = fasta_stage_index(ctx, fa, fasta, st))) return rc;
+    CK(ctx, cudaStreamSynchronize(st));
+    fasta_index_done(fa);
+    *n_records = fa.N;
     if (max_seq_len) *max_seq_len = fa.max_len;
     return TREAT_B200_OK;
 }
 
 int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_record *rec, uint8_t *ops, uint32_t ops_stride,
-                           uint64_t *id_off, uint32_t *id_len, uint32_t *read_count)
+                           uint64_t *id_off, uint32_t *id_len, uint32_t *read_count, uint64_t *seq_off, uint32_t *seq_len)
 {
     if (!ctx) return TREAT_B200_ERR_INVALID;
     FastaDev &fa = ctx->fasta;
     if (!fa.open) return fail(ctx, TREAT_B200_ERR_INVALID, "fasta_align: no file uploaded (treat_b200_fasta_upload)");
-    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
     const uint64_t N = fa.N;
     if (N == 0) return TREAT_B200_OK;
     if (!rec) return TREAT_B200_ERR_INVALID;
     const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
+    const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
     if (want_ops && !ops) return fail(ctx, TREAT_B200_ERR_INVALID, "align: WANT_OPS without ops buffer");
-    if (fa.max_len > kMaxReadLen) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: read longer than 16384");
-    if (want_ops && (ops_stride < treat_b200_ops_stride(ctx, fa.max_len) || ops_stride % 16))
-        return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small (see treat_b200_ops_stride)");
+    int rc = fasta_check_align(ctx, fa, flags, ops_stride);
+    if (rc) return rc;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (id_off) CK(ctx, cudaMemcpyAsync(id_off, fa.id_off.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (id_len) CK(ctx, cudaMemcpyAsync(id_len, fa.id_len.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (read_count) CK(ctx, cudaMemcpyAsync(read_count, fa.rc.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (seq_off) CK(ctx, cudaMemcpyAsync(seq_off, fa.seq_begin.p, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (seq_len) CK(ctx, cudaMemcpyAsync(seq_len, fa.seq_len.p, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
     for (int i = 0; i < 2; i++)
         if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
-
-    // reads with line breaks inside (or a template that needs the wide path) are first copied into one contiguous buffer
-    auto compact = [&]() -> int {
-        if (fa.compacted) return TREAT_B200_OK;
-        CK(ctx, fa.seqs.reserve(fa.seq_bytes + 64));
-        int e = launch_fasta_compact((const uint8_t *)fa.file.p, fa.len, (const uint64_t *)fa.start.p, N, (const uint64_t *)fa.seq_begin.p,
-                                     (const uint64_t *)fa.seq_off.p, (uint8_t *)fa.seqs.p, ctx->num_sms, ctx->stream);
-        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_fasta_compact launch: ") + cudaGetErrorString((cudaError_t)e));
-        ctx->launches++;
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        fa.compacted = true;
-        return TREAT_B200_OK;
-    };
     bool in_place = !fa.multi && !ctx->tmpl_wide;
-    if (!in_place) {
-        int r = compact();
-        if (r) return r;
-    }
     const uint64_t chunk = 1ull << 20;
-    int rc = TREAT_B200_OK;
     uint64_t k = 0;
     for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk, k++) {
         const uint64_t cn = std::min(chunk, N - c0);
         Slot &s = ctx->slot[k & 1];
         cudaStream_t st = s.stream;
         CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk, including its copies to the host
-        CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
-        // ops: every row at the caller's stride, or (OPS_GAPPED_ONLY) only the gapped reads' rows, compacted by the kernels
-        const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
-        if (want_ops && !sparse) CK(ctx, s.ops.reserve(cn * (size_t)ops_stride));
-        uint8_t *d_ops = want_ops && !sparse ? (uint8_t *)s.ops.p : nullptr;
-        const uint32_t d_stride = sparse ? 0u : ops_stride;
-        const uint32_t *d_rc = (const uint32_t *)fa.rc.p + c0;
-        bool sat = false;
-        if (in_place) {
-            const ReadSpan span{(const uint64_t *)fa.seq_begin.p + c0, (const uint32_t *)fa.seq_len.p + c0, fa.len};
-            rc = run_chunk(ctx, s, (const uint8_t *)fa.file.p, nullptr, 0, d_rc, cn, fa.max_len, flags, (treat_b200_record *)s.rec.p,
-                           d_ops, d_stride, st, false, &sat, &s.dev_stride, 0, &span);
-            if (rc == TREAT_B200_OK && sat) {  // an edit-base run >= 255: the wide kernels read contiguous reads
-                if ((rc = compact())) break;
-                in_place = false;
-            }
-        }
-        if (rc == TREAT_B200_OK && !in_place) {
-            rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
-                           (treat_b200_record *)s.rec.p, d_ops, d_stride, st, false, &sat, &s.dev_stride);
-            if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
-                rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
-                               (treat_b200_record *)s.rec.p, d_ops, d_stride, st, true, nullptr, &s.dev_stride);
-        }
-        if (rc) break;
+        if ((rc = fasta_align_chunk(ctx, fa, s, c0, cn, flags, ops_stride, &in_place))) break;
         CK(ctx, cudaMemcpyAsync(rec + c0, s.rec.p, cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, st));
         if (want_ops && !sparse)
             CK(ctx, cudaMemcpyAsync(ops + c0 * (size_t)ops_stride, s.ops.p, cn * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
@@ -1029,8 +1080,7 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
             CK(ctx, cudaStreamSynchronize(st));
             const uint32_t cnt = s.h_scalars[4];
             if (cnt) {
-                int r = reserve_gap_rows(ctx, s, cnt);
-                if (r) return r;
+                if ((rc = reserve_gap_rows(ctx, s, cnt))) break;
                 CK(ctx, cudaMemcpyAsync(s.h_gap_idx, s.ops_idx.p, cnt * 4ull, cudaMemcpyDeviceToHost, st));
                 CK(ctx, cudaMemcpyAsync(s.h_gap_rows, s.ops.p, cnt * (size_t)s.dev_stride, cudaMemcpyDeviceToHost, st));
                 CK(ctx, cudaStreamSynchronize(st));
@@ -1047,6 +1097,218 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
         }
     }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// The same as one call that never holds the whole file on the device: the bytes are cut into pieces at record starts,
+// four pieces are in flight (copy + count, index, align, deliver), and every finished piece is handed to `sink` in file order.
+int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, uint32_t ops_stride,
+                            treat_b200_fasta_sink sink, void *user, uint64_t *n_records)
+{
+    if (!ctx || (len && !fasta) || !sink) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
+    const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
+    if (n_records) *n_records = 0;
+    for (int i = 0; i < kFastaSlots; i++)
+        if (!ctx->fslot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->fslot[i].stream, cudaStreamNonBlocking));
+    static const uint64_t piece_bytes = getenv("TREAT_B200_FASTA_PIECE") ? std::max(4096ull, strtoull(getenv("TREAT_B200_FASTA_PIECE"), nullptr, 10)) : (32ull << 20);
+    // cut points: every piece but the first starts at a '>' that opens a line
+    std::vector<uint64_t> cut{0};
+    while (cut.back() < len) {
+        uint64_t e = cut.back() + piece_bytes;
+        if (e >= len) {
+            cut.push_back(len);
+            break;
+        }
+        // the first record start at or behind the nominal end
+        const uint8_t *p = fasta + e;
+        uint64_t at = len;
+        while (p < fasta + len) {
+            const uint8_t *g = (const uint8_t *)memchr(p, '>', (size_t)(fasta + len - p));
+            if (!g) break;
+            if (g[-1] == '\n') {  // g > fasta: e >= piece_bytes > 0
+                at = (uint64_t)(g - fasta);
+                break;
+            }
+            p = g + 1;
+        }
+        cut.push_back(at);
+    }
+    const int64_t npieces = (int64_t)cut.size() - 1;
+    struct Piece {
+        uint64_t first = 0;   // number of its first record in the file
+        uint32_t stride = 0;  // bytes per ops row (ops_stride, or chosen from the piece's longest read when that is 0)
+        bool in_place = true;
+        bool spec = false;    // aligned without waiting for the pack kernel's longest read: validated before delivery
+    };
+    std::vector<Piece> pc((size_t)std::max<int64_t>(npieces, 0));
+    uint64_t total = 0;
+    int rc = TREAT_B200_OK;
+    // pinned landing buffers of one slot (grow only)
+    auto landing = [&](Slot &s, uint64_t n, uint32_t stride) -> int {
+        const size_t need = n * (sizeof(treat_b200_record) + 8 + 4 + 4 + 8 + 4) + (want_ops && !sparse ? n * (size_t)stride : 0) + 256;
+        if (need > s.land_cap) {
+            if (s.land) cudaFreeHost(s.land);
+            s.land = nullptr;
+            s.land_cap = 0;
+            CK(ctx, cudaMallocHost((void **)&s.land, need + need / 4));
+            s.land_cap = need + need / 4;
+        }
+        return TREAT_B200_OK;
+    };
+    // copies of a piece's results into its slot's landing buffer (async on the slot stream)
+    auto enqueue_results = [&](int64_t k) -> int {
+        Slot &s = ctx->fslot[k % kFastaSlots];
+        FastaDev &fa = ctx->fasta_slot[k % kFastaSlots];
+        int r = landing(s, fa.N, pc[k].stride);
+        if (r) return r;
+        const uint64_t n = fa.N;
+        uint8_t *l = s.land;
+        CK(ctx, cudaMemcpyAsync(l, s.rec.p, n * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, s.stream));
+        l += n * sizeof(treat_b200_record);
+        CK(ctx, cudaMemcpyAsync(l, fa.id_off.p, n * 8, cudaMemcpyDeviceToHost, s.stream));
+        l += n * 8;
+        CK(ctx, cudaMemcpyAsync(l, fa.seq_begin.p, n * 8, cudaMemcpyDeviceToHost, s.stream));
+        l += n * 8;
+        CK(ctx, cudaMemcpyAsync(l, fa.id_len.p, n * 4, cudaMemcpyDeviceToHost, s.stream));
+        l += n * 4;
+        CK(ctx, cudaMemcpyAsync(l, fa.rc.p, n * 4, cudaMemcpyDeviceToHost, s.stream));
+        l += n * 4;
+        CK(ctx, cudaMemcpyAsync(l, fa.seq_len.p, n * 4, cudaMemcpyDeviceToHost, s.stream));
+        l += n * 4;
+        if (want_ops && !sparse) CK(ctx, cudaMemcpyAsync(l, s.ops.p, n * (size_t)pc[k].stride, cudaMemcpyDeviceToHost, s.stream));
+        CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, s.stream));
+        return TREAT_B200_OK;
+    };
+    static const bool trace = getenv("TREAT_B200_TRACE") != nullptr;
+    static const bool trace2 = trace && atoi(getenv("TREAT_B200_TRACE")) >= 2;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tA = 0, tB = 0, tC = 0, tD = 0, tSink = 0;
+    const double t_begin = now();
+    for (int64_t t = 0; t < npieces + 4 && rc == TREAT_B200_OK; t++) {
+        double t0 = now();
+        // stage A: piece t
+        if (t < npieces) {
+            Slot &s = ctx->fslot[t % kFastaSlots];
+            rc = fasta_stage_copy_count(ctx, ctx->fasta_slot[t % kFastaSlots], fasta + cut[t], cut[t + 1] - cut[t], s.stream);
+            if (rc) break;
+        }
+        tA += now() - t0;
+        const double sA = now() - t_begin;
+        t0 = now();
+        // stage B: piece t - 2 (two pieces are on the bus or queued for it)
+        if (t - 2 >= 0 && t - 2 < npieces) {
+            const int64_t k = t - 2;
+            Slot &s = ctx->fslot[k % kFastaSlots];
+            CK(ctx, cudaStreamSynchronize(s.stream));
+            if ((rc = fasta_stage_index(ctx, ctx->fasta_slot[k % kFastaSlots], fasta + cut[k], s.stream))) break;
+        }
+        tB += now() - t0;
+        const double sB = now() - t_begin;
+        t0 = now();
+        // stage C: piece t - 3
+        if (t - 3 >= 0 && t - 3 < npieces) {
+            const int64_t k = t - 3;
+            Slot &s = ctx->fslot[k % kFastaSlots];
+            FastaDev &fa = ctx->fasta_slot[k % kFastaSlots];
+            CK(ctx, cudaStreamSynchronize(s.stream));
+            fasta_index_done(fa);
+            pc[k].first = total;
+            total += fa.N;
+            if (fa.N) {
+                pc[k].stride = ops_stride ? ops_stride : treat_b200_ops_stride(ctx, fa.max_len);
+                if ((rc = fasta_check_align(ctx, fa, flags, pc[k].stride))) break;
+                pc[k].in_place = !fa.multi && !ctx->tmpl_wide;
+                pc[k].spec = pc[k].in_place && ctx->ncap_hint != 0;
+                if ((rc = fasta_align_chunk(ctx, fa, s, 0, fa.N, flags, pc[k].stride, &pc[k].in_place, pc[k].spec ? ctx->ncap_hint + 8 : 0))) break;
+                if ((rc = enqueue_results(k))) break;
+            }
+        }
+        tC += now() - t0;
+        const double sC = now() - t_begin;
+        t0 = now();
+        // stage D: piece t - 4
+        if (t - 4 >= 0 && t - 4 < npieces) {
+            const int64_t k = t - 4;
+            Slot &s = ctx->fslot[k % kFastaSlots];
+            FastaDev &fa = ctx->fasta_slot[k % kFastaSlots];
+            CK(ctx, cudaStreamSynchronize(s.stream));
+            const uint64_t n = fa.N;
+            if (n && pc[k].spec) {  // validate the speculative launch (as treat_b200_align_batch does at slot reuse)
+                const uint32_t max_n = s.h_scalars[0], sat = s.h_scalars[1], skipped = s.h_scalars[2];
+                ctx->ncap_hint = std::max(ctx->ncap_hint, max_n);
+                if (skipped != 0 || (sat && !ctx->tmpl_wide)) {
+                    if (!(flags & TREAT_B200_NO_SUMMARY)) CK(ctx, cudaMemsetAsync(s.summary.p, 0, treat_b200_summary_len(ctx) * 8, s.stream));
+                    if ((rc = fasta_align_chunk(ctx, fa, s, 0, n, flags, pc[k].stride, &pc[k].in_place))) break;
+                    if ((rc = enqueue_results(k))) break;
+                    CK(ctx, cudaStreamSynchronize(s.stream));
+                } else if (!(flags & TREAT_B200_NO_SUMMARY)) {
+                    int e = launch_merge_summary(ctx->d_summary, (uint64_t *)s.summary.p, (uint32_t)treat_b200_summary_len(ctx), s.stream);
+                    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_merge_summary launch failed");
+                    ctx->launches++;
+                }
+            }
+            if (n) {
+                treat_b200_fasta_piece out;
+                memset(&out, 0, sizeof out);
+                uint8_t *l = s.land;
+                out.first_record = pc[k].first;
+                out.n = n;
+                out.rec = (const treat_b200_record *)l;
+                l += n * sizeof(treat_b200_record);
+                uint64_t *ido = (uint64_t *)l;
+                l += n * 8;
+                uint64_t *sqo = (uint64_t *)l;
+                l += n * 8;
+                for (uint64_t i = 0; i < n; i++) {  // piece offsets -> file offsets
+                    ido[i] += cut[k];
+                    sqo[i] += cut[k];
+                }
+                out.id_off = ido;
+                out.seq_off = sqo;
+                out.id_len = (const uint32_t *)l;
+                l += n * 4;
+                out.read_count = (const uint32_t *)l;
+                l += n * 4;
+                out.seq_len = (const uint32_t *)l;
+                l += n * 4;
+                out.seq_in_place = fa.multi ? 0 : 1;
+                if (want_ops && !sparse) {
+                    out.ops = l;
+                    out.ops_stride = pc[k].stride;
+                    out.n_ops_rows = n;
+                } else if (sparse) {
+                    const uint32_t cnt = s.h_scalars[4];
+                    if (cnt) {
+                        if ((rc = reserve_gap_rows(ctx, s, cnt))) break;
+                        CK(ctx, cudaMemcpyAsync(s.h_gap_idx, s.ops_idx.p, cnt * 4ull, cudaMemcpyDeviceToHost, s.stream));
+                        CK(ctx, cudaMemcpyAsync(s.h_gap_rows, s.ops.p, cnt * (size_t)s.dev_stride, cudaMemcpyDeviceToHost, s.stream));
+                        CK(ctx, cudaStreamSynchronize(s.stream));
+                    }
+                    out.ops = s.h_gap_rows;
+                    out.ops_stride = s.dev_stride;
+                    out.n_ops_rows = cnt;
+                    out.ops_index = s.h_gap_idx;
+                }
+                const double ts = now();
+                const int stop = sink(user, &out);
+                tSink += now() - ts;
+                if (stop) {
+                    rc = fail(ctx, TREAT_B200_ERR_INVALID, "fasta_stream: stopped by the sink");
+                    break;
+                }
+            }
+        }
+        tD += now() - t0;
+        if (trace2) fprintf(stderr, "[treat_b200]   step %lld: A done %.2f, B done %.2f, C done %.2f, D done %.2f ms\n", (long long)t, sA, sB, sC, now() - t_begin);
+    }
+    for (int i = 0; i < kFastaSlots; i++) cudaStreamSynchronize(ctx->fslot[i].stream);
+    if (trace)
+        fprintf(stderr, "[treat_b200] fasta_stream %lld pieces, %llu records, %.2f ms: copy+count %.2f, index %.2f, align %.2f, deliver %.2f (sink %.2f)\n",
+                (long long)npieces, (unsigned long long)total, now() - t_begin, tA, tB, tC, tD, tSink);
+    if (n_records) *n_records = total;
     return rc;
 }
 
