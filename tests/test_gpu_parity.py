@@ -251,6 +251,17 @@ def test_wide_paths(eng, tmp_path):
     assert all(a.Status & cabi.ST_SATURATED for a in alns[1:])
     for i, a in enumerate(alns):
         assert a.JuncSeq == O.NewAlignment(O.NewFragment(*recs[i]), om2).JuncSeq
+    # the same through the FASTA entry points (upload + align, and streamed): the saturated pieces fall back to
+    # compacted reads + the wide kernels, the wide template never reads in place
+    seqs, off, rcs = synth.reads(t, 5000, seed=31337)
+    body = [(("r%d_%d" % (i, rcs[i])), seqs[int(off[i]):int(off[i + 1])].tobytes().decode()) for i in range(5000)]
+    body[1234] = ("sat-7", raw[:80] + "T" * 300 + raw[80:])
+    body[4321] = ("sat-9", "T" * 999 + raw)
+    text = "".join(">%s\n%s\n" % b for b in body).encode()
+    _fasta_device_vs_host(eng, tmp_path, text, "saturated_reads")
+    eng.SetTemplate(tm)
+    text = "".join(">%s\n%s\n" % r for r in [("a-1", fe), ("b-2", pe), ("c-3", fe.replace("N", "R")), ("f-6", "N" * 30)] * 50).encode()
+    _fasta_device_vs_host(eng, tmp_path, text, "wide_template")
 
 
 def test_edge_cases(eng, tmp_path):

@@ -61,14 +61,16 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
     using cnt_t = typename std::conditional<WIDE, uint32_t, uint8_t>::type;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *s_lut = smem;  // 256: byte -> 2-bit code (0x80 = edit base) or, on the wide path, the upper-cased byte
+    uint8_t *s_other = smem + 256;  // 256, wide path: 1 = a base outside the packed alphabet (status bit ST_WIDE_BASE, as k_pack16 sets it)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cap = p.stage_cap;  // multiple of 16
-    uint8_t *s_code = smem + 256 + (size_t)warp * (cap + cap * sizeof(cnt_t));
+    uint8_t *s_code = smem + 512 + (size_t)warp * (cap + cap * sizeof(cnt_t));
     cnt_t *s_cnt = reinterpret_cast<cnt_t *>(s_code + cap);
     const uint8_t eb = p.edit_base;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const uint8_t up = (i >= 'a' && i <= 'z') ? (uint8_t)(i - 32) : (uint8_t)i;  // strings.ToUpper, ASCII
         s_lut[i] = WIDE ? up : (up == eb ? (uint8_t)0x80 : p.lut[up]);
+        s_other[i] = (up != eb && p.lut[up] == 3) ? 1 : 0;
     }
     __syncthreads();
 
@@ -96,6 +98,8 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
                 if (!WIDE) {
                     widec |= (v == 3u);
                     if (cnt >= 255u) cnt = 255u;
+                } else {
+                    widec |= s_other[v] != 0;
                 }
                 s_code[idx] = (uint8_t)v;
                 s_cnt[idx] = (cnt_t)cnt;
