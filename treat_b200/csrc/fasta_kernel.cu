@@ -238,6 +238,83 @@ __device__ uint32_t merge_count(const uint8_t *s, uint32_t n)
     return (uint32_t)v;
 }
 
+// 16-bit mask of the bytes of v equal to the byte replicated in c4
+__device__ __forceinline__ uint32_t eq_mask16(const uint4 &v, uint32_t c4)
+{
+    return eq_mask4(v.x, c4) | (eq_mask4(v.y, c4) << 4) | (eq_mask4(v.z, c4) << 8) | (eq_mask4(v.w, c4) << 12);
+}
+__device__ __forceinline__ bool has_byte(const uint4 &v, uint32_t c4)
+{
+    uint32_t r = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t z = w[i] ^ c4;
+        r |= (z - 0x01010101u) & ~z & 0x80808080u;
+    }
+    return r != 0u;
+}
+// bits [lo, hi) of a 16-bit mask, both clamped to 0..16
+__device__ __forceinline__ uint32_t range16(long long lo, long long hi)
+{
+    const int l = (int)min(max(lo, 0ll), 16ll), h = (int)min(max(hi, 0ll), 16ll);
+    return h > l ? ((1u << h) - 1u) & ~((1u << l) - 1u) : 0u;
+}
+
+// a record of any length, 32 bytes per step (the general form of the one-pass code in k_fasta_records)
+__device__ __noinline__ void fasta_record_slow(const FastaRecParams &p, uint64_t r, int lane, uint32_t *wmax, uint32_t *wmulti)
+{
+    const uint64_t b = p.start[r], e = r + 1 < p.N ? p.start[r + 1] : p.len;
+    // header line: [b + 1, eol)
+    uint64_t eol = e;
+    for (uint64_t x = b; x < e; x += 32) {
+        const uint64_t pos = x + lane;
+        const uint32_t m = __ballot_sync(FULL_MASK, pos < e && p.file[pos] == '\n');
+        if (m) {
+            eol = x + (uint32_t)(__ffs(m) - 1);
+            break;
+        }
+    }
+    // strings.TrimSpace of the header
+    uint64_t ib = eol, il = 0;  // first non-space, one past the last non-space
+    for (uint64_t x = b + 1; x < eol; x += 32) {
+        const uint64_t pos = x + lane;
+        const uint32_t m = __ballot_sync(FULL_MASK, pos < eol && !is_space(p.file[pos]));
+        if (m) {
+            if (ib == eol) ib = x + (uint32_t)(__ffs(m) - 1);
+            il = x + (uint32_t)(32 - __clz(m));
+        }
+    }
+    const uint32_t idn = il > ib ? (uint32_t)(il - ib) : 0u;
+    // sequence bytes: everything behind the header line that is not a line break
+    const uint64_t sb = eol < e ? eol + 1 : e;
+    uint32_t kept = 0;
+    uint64_t first_drop = e;
+    for (uint64_t x = sb; x < e; x += 32) {
+        const uint64_t pos = x + lane;
+        bool drop = false, in = pos < e;
+        if (in) {
+            const uint32_t c = p.file[pos];
+            drop = c == '\n' || (c == '\r' && (pos + 1 == p.len || p.file[pos + 1] == '\n'));
+        }
+        const uint32_t md = __ballot_sync(FULL_MASK, in && drop), mk = __ballot_sync(FULL_MASK, in && !drop);
+        if (md && first_drop == e) first_drop = x + (uint32_t)(__ffs(md) - 1);
+        kept += __popc(mk);
+    }
+    if (kept != (uint32_t)(first_drop - sb)) *wmulti = 1;  // a kept byte behind a dropped one: more than one line
+    if (lane == 0) {
+        p.id_off[r] = idn ? ib : (b + 1 < p.len ? b + 1 : p.len);
+        p.id_len[r] = idn;
+        p.read_count[r] = idn ? merge_count(p.file + ib, idn) : 1u;
+        p.seq_begin[r] = sb;
+        p.seq_len[r] = kept;
+    }
+    *wmax = max(*wmax, kept);
+}
+
+// One warp per record.  A record that fits 512 bytes from the 16-byte boundary below its '>' is handled in one pass:
+// lane l holds bytes [16 l, 16 l + 16) as a uint4; newline / CR positions are 16-bit masks from byte-SIMD compares,
+// the header end is a ballot + ffs, the sequence length a popcount + REDUX.
 __global__ void __launch_bounds__(256) k_fasta_records(const __grid_constant__ FastaRecParams p)
 {
     const int lane = threadIdx.x & 31;
@@ -245,44 +322,48 @@ __global__ void __launch_bounds__(256) k_fasta_records(const __grid_constant__ F
     uint32_t wmax = 0, wmulti = 0;
     for (uint64_t r = gw; r < p.N; r += nw) {
         const uint64_t b = p.start[r], e = r + 1 < p.N ? p.start[r + 1] : p.len;
-        // header line: [b + 1, eol)
+        const uint64_t ab = b & ~15ull;
+        if (e - ab > 512) {
+            fasta_record_slow(p, r, lane, &wmax, &wmulti);
+            continue;
+        }
+        const uint64_t x = ab + 16ull * lane;  // this lane's first byte
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (x < e) v = *reinterpret_cast<const uint4 *>(p.file + x);  // the buffer is padded past len
+        const uint32_t valid = range16((long long)b - (long long)x, (long long)e - (long long)x);
+        const uint32_t nl = eq_mask16(v, 0x0a0a0a0au) & valid;
+        // header line [b + 1, eol): the first newline of the record
+        const uint32_t fl = __ballot_sync(FULL_MASK, nl != 0u);
         uint64_t eol = e;
-        for (uint64_t x = b; x < e; x += 32) {
-            const uint64_t pos = x + lane;
-            const uint32_t m = __ballot_sync(FULL_MASK, pos < e && p.file[pos] == '\n');
-            if (m) {
-                eol = x + (uint32_t)(__ffs(m) - 1);
-                break;
-            }
+        if (fl) {
+            const int f = __ffs(fl) - 1;
+            eol = ab + 16ull * f + (uint32_t)(__shfl_sync(FULL_MASK, __ffs(nl) - 1, f));
         }
-        // strings.TrimSpace of the header
-        uint64_t ib = eol, il = 0;  // first non-space, one past the last non-space
-        for (uint64_t x = b + 1; x < eol; x += 32) {
-            const uint64_t pos = x + lane;
-            const uint32_t m = __ballot_sync(FULL_MASK, pos < eol && !is_space(p.file[pos]));
-            if (m) {
-                if (ib == eol) ib = x + (uint32_t)(__ffs(m) - 1);
-                il = x + (uint32_t)(32 - __clz(m));
-            }
-        }
-        const uint32_t idn = il > ib ? (uint32_t)(il - ib) : 0u;
-        // sequence bytes: everything behind the header line that is not a line break
         const uint64_t sb = eol < e ? eol + 1 : e;
-        uint32_t kept = 0;
+        // sequence bytes: behind the header line, not '\n', not a '\r' in front of a '\n' or at the end of the file
+        const uint32_t smask = valid & range16((long long)sb - (long long)x, 16);
+        uint32_t drop = nl & smask;
+        if (__any_sync(FULL_MASK, has_byte(v, 0x0d0d0d0du))) {
+            const uint32_t virt = (p.len >= x && p.len - x < 16) ? 1u << (uint32_t)(p.len - x) : 0u;  // the end of the file acts as '\n'
+            const uint32_t nlv = (eq_mask16(v, 0x0a0a0a0au) & range16(0, (long long)p.len - (long long)x)) | virt;
+            uint32_t nxt = __shfl_down_sync(FULL_MASK, nlv, 1) & 1u;
+            if (lane == 31) nxt = (x + 16 == p.len) ? 1u : 0u;  // nothing of this record lies beyond lane 31
+            drop |= eq_mask16(v, 0x0d0d0d0du) & ((nlv >> 1) | (nxt << 15)) & smask;
+        }
+        const uint32_t kept = __reduce_add_sync(FULL_MASK, (uint32_t)__popc(smask & ~drop));
+        const uint32_t dl = __ballot_sync(FULL_MASK, drop != 0u);
         uint64_t first_drop = e;
-        for (uint64_t x = sb; x < e; x += 32) {
-            const uint64_t pos = x + lane;
-            bool drop = false, in = pos < e;
-            if (in) {
-                const uint32_t c = p.file[pos];
-                drop = c == '\n' || (c == '\r' && (pos + 1 == p.len || p.file[pos + 1] == '\n'));
-            }
-            const uint32_t md = __ballot_sync(FULL_MASK, in && drop), mk = __ballot_sync(FULL_MASK, in && !drop);
-            if (md && first_drop == e) first_drop = x + (uint32_t)(__ffs(md) - 1);
-            kept += __popc(mk);
+        if (dl) {
+            const int f = __ffs(dl) - 1;
+            first_drop = ab + 16ull * f + (uint32_t)(__shfl_sync(FULL_MASK, __ffs(drop) - 1, f));
         }
         if (kept != (uint32_t)(first_drop - sb)) wmulti = 1;  // a kept byte behind a dropped one: more than one line
         if (lane == 0) {
+            // strings.TrimSpace of the header: the bytes were just loaded, these scans hit L1
+            uint64_t ib = b + 1, il = eol;
+            while (ib < il && is_space(p.file[ib])) ib++;
+            while (il > ib && is_space(p.file[il - 1])) il--;
+            const uint32_t idn = il > ib ? (uint32_t)(il - ib) : 0u;
             p.id_off[r] = idn ? ib : (b + 1 < p.len ? b + 1 : p.len);
             p.id_len[r] = idn;
             p.read_count[r] = idn ? merge_count(p.file + ib, idn) : 1u;
