@@ -232,6 +232,12 @@ uint32_t treat_b200_template_max(const treat_b200_template *t, int32_t i); /* Ma
 /* FASTA reader with gofasta.SimpleParser's record semantics (cmd/treat/align.go:114) */
 typedef struct treat_b200_fasta treat_b200_fasta;
 int treat_b200_fasta_read(const char *path, treat_b200_fasta **out);
+int treat_b200_fasta_parse(const uint8_t *bytes, uint64_t len, treat_b200_fasta **out); /* the same on bytes in memory */
+/* Cut the bytes of a FASTA file into `parts` slices of about equal size that start at record starts ('>' opening a line):
+ * offsets[parts + 1], offsets[0] = 0, offsets[parts] = len.  Parsing the slices one after the other gives the records of
+ * the whole file in order -- this is how a file is shared between GPUs (one slice per rank) and how
+ * treat_b200_fasta_stream cuts its pieces. */
+int treat_b200_fasta_split(const uint8_t *fasta, uint64_t len, uint32_t parts, uint64_t *offsets);
 void treat_b200_fasta_free(treat_b200_fasta *f);
 uint64_t treat_b200_fasta_count(const treat_b200_fasta *f);
 const char *treat_b200_fasta_id(const treat_b200_fasta *f, uint64_t i);

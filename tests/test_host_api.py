@@ -173,3 +173,49 @@ def test_mutant_report_vs_oracle(examples):
     assert want_tm and want_fm
     for n in (0, 1, 10):
         assert T.mutant_report(tm, rec, oops, fb.seqs, fb.offsets, n) == P.mutant_report(want_tm, want_fm, n)
+
+
+def _random_fasta(rng, n):
+    parts = []
+    if rng.random() < 0.5:
+        parts.append(b"junk before\nthe first>mid_3 line record\n")
+    for i in range(n):
+        L = rng.choice([0, 1, 30, 61, 200, 330])
+        seq = "".join(rng.choice("ACGT>") if rng.random() < 0.02 else rng.choice("ACGT") for _ in range(L)).encode()
+        w = rng.choice([10000, 60, 7])
+        body = b"\n".join(seq[j:j + w] for j in range(0, len(seq), w))
+        eol = b"\r\n" if rng.random() < 0.2 else b"\n"
+        parts.append(b">r%d_%d some text" % (i, rng.randrange(1, 99)) + eol + body + (eol if body or rng.random() < 0.5 else b""))
+        if rng.random() < 0.1:
+            parts.append(b"\n")
+    return b"".join(parts)
+
+
+def test_fasta_parse_bytes_and_split(tmp_path):
+    """treat_b200_fasta_parse == treat_b200_fasta_read, and the slices of treat_b200_fasta_split start at record starts:
+    parsing them one after the other gives the records of the whole file (how a file is shared between ranks and how
+    treat_b200_fasta_stream cuts its pieces)."""
+    import random
+    rng = random.Random(99)
+    for trial in range(12):
+        text = _random_fasta(rng, rng.choice([0, 1, 5, 200]))
+        path = tmp_path / ("f%d.fa" % trial)
+        path.write_bytes(text)
+        whole = T.read_fasta(str(path))
+        mem = T.parse_fasta(text)
+        assert mem.ids == whole.ids and np.array_equal(mem.offsets, whole.offsets)
+        assert np.array_equal(mem.seqs, whole.seqs) and np.array_equal(mem.read_counts, whole.read_counts)
+        ref = P.read_fasta(str(path))
+        assert [r[0] for r in ref] == whole.ids and [r[1].encode() for r in ref] == [whole.seq(i) for i in range(len(whole))]
+        for parts in (1, 2, 3, 8, 50):
+            off = T.fasta_split(text, parts)
+            assert off[0] == 0 and off[-1] == len(text) and (np.diff(off.astype(np.int64)) >= 0).all()
+            ids, seqs = [], []
+            for k in range(parts):
+                lo, hi = int(off[k]), int(off[k + 1])
+                if lo and lo < len(text):
+                    assert text[lo:lo + 1] == b">" and text[lo - 1:lo] == b"\n"
+                piece = T.parse_fasta(text[lo:hi])
+                ids += piece.ids
+                seqs += [piece.seq(i) for i in range(len(piece))]
+            assert ids == whole.ids and seqs == [whole.seq(i) for i in range(len(whole))], (trial, parts)

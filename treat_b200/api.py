@@ -205,10 +205,34 @@ class FastaBatch:
         return FastaBatch(ids, seqs, off, rc)
 
 
+def fasta_split(data, parts: int) -> np.ndarray:
+    """treat_b200_fasta_split: offsets[parts + 1] of slices of a FASTA file's bytes that start at record starts."""
+    if isinstance(data, (bytes, bytearray)):
+        data = np.frombuffer(data, dtype=np.uint8)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    off = np.zeros(parts + 1, dtype=np.uint64)
+    check(lib().treat_b200_fasta_split(data.ctypes.data if data.size else None, data.size, parts, off.ctypes.data))
+    return off
+
+
 def read_fasta(path: str) -> FastaBatch:
     """gofasta.SimpleParser record semantics (cmd/treat/align.go:114), whole file as one batch."""
     h = C.c_void_p()
     check(lib().treat_b200_fasta_read(_b(path), C.byref(h)))
+    return _fasta_batch(h)
+
+
+def parse_fasta(data) -> FastaBatch:
+    """The same on bytes in memory (treat_b200_fasta_parse)."""
+    if isinstance(data, (bytes, bytearray)):
+        data = np.frombuffer(data, dtype=np.uint8)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    h = C.c_void_p()
+    check(lib().treat_b200_fasta_parse(data.ctypes.data if data.size else None, data.size, C.byref(h)))
+    return _fasta_batch(h)
+
+
+def _fasta_batch(h) -> FastaBatch:
     try:
         L = lib()
         n = L.treat_b200_fasta_count(h)

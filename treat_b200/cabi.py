@@ -73,6 +73,8 @@ SIGNATURES = {
     "treat_b200_align_batch_device": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
     "treat_b200_ops_stride": (C.c_uint32, [_P, C.c_uint32]),
     "treat_b200_synchronize": (C.c_int, [_P]),
+    "treat_b200_fasta_parse": (C.c_int, [_U8P, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "treat_b200_fasta_split": (C.c_int, [_U8P, C.c_uint64, C.c_uint32, _P]),
     "treat_b200_fasta_upload": (C.c_int, [_P, _U8P, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "treat_b200_fasta_align": (C.c_int, [_P, C.c_uint32, _P, _U8P, C.c_uint32, _P, _P, _P, _P, _P]),
     "treat_b200_fasta_stream": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),

@@ -1122,18 +1122,7 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
             cut.push_back(len);
             break;
         }
-        // the first record start at or behind the nominal end
-        const uint8_t *p = fasta + e;
-        uint64_t at = len;
-        while (p < fasta + len) {
-            const uint8_t *g = (const uint8_t *)memchr(p, '>', (size_t)(fasta + len - p));
-            if (!g) break;
-            if (g[-1] == '\n') {  // g > fasta: e >= piece_bytes > 0
-                at = (uint64_t)(g - fasta);
-                break;
-            }
-            p = g + 1;
-        }
+        const uint64_t at = treat::FastaNextRecordStart(fasta, len, e);  // the first record start at or behind the nominal end
         cut.push_back(at);
     }
     const int64_t npieces = (int64_t)cut.size() - 1;

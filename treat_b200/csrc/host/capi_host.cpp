@@ -126,6 +126,20 @@ int treat_b200_fasta_read(const char *path, treat_b200_fasta **out)
     *out = f;
     return TREAT_B200_OK;
 }
+int treat_b200_fasta_parse(const uint8_t *bytes, uint64_t len, treat_b200_fasta **out)
+{
+    if ((!bytes && len) || !out) return TREAT_B200_ERR_INVALID;
+    treat_b200_fasta *f = new treat_b200_fasta();
+    treat::ParseFasta((const char *)bytes, (size_t)len, &f->b);
+    *out = f;
+    return TREAT_B200_OK;
+}
+int treat_b200_fasta_split(const uint8_t *fasta, uint64_t len, uint32_t parts, uint64_t *offsets)
+{
+    if ((!fasta && len) || !parts || !offsets) return TREAT_B200_ERR_INVALID;
+    treat::FastaSplit(fasta, len, parts, offsets);
+    return TREAT_B200_OK;
+}
 void treat_b200_fasta_free(treat_b200_fasta *f) { delete f; }
 uint64_t treat_b200_fasta_count(const treat_b200_fasta *f) { return f->b.size(); }
 const char *treat_b200_fasta_id(const treat_b200_fasta *f, uint64_t i) { return f->b.ids[i].c_str(); }

@@ -117,14 +117,9 @@ std::string Fragment::ToFasta() const { return ">" + Name + "\n" + String(); }
 
 // ------------------------------------------------------------------ gofasta
 
-bool ReadFasta(const std::string &path, FastaBatch *out, std::string *err)
+void ParseFasta(const char *bytes, size_t size, FastaBatch *out)
 {
-    std::ifstream in(path, std::ios::binary);
-    if (!in) {
-        if (err) *err = "open " + path + ": no such file or directory";
-        return false;
-    }
-    std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    const std::string_view data(bytes, size);
     out->ids.clear();
     out->seqs.clear();
     out->offsets.assign(1, 0);
@@ -132,14 +127,14 @@ bool ReadFasta(const std::string &path, FastaBatch *out, std::string *err)
     out->seqs.reserve(data.size());
     size_t pos = data.find('>');  // bytes before the first record are skipped
     bool open = false;
-    while (pos != std::string::npos && pos < data.size()) {
+    while (pos != std::string_view::npos && pos < data.size()) {
         size_t eol = data.find('\n', pos);
-        if (eol == std::string::npos) eol = data.size();
+        if (eol == std::string_view::npos) eol = data.size();
         size_t le = eol;
         if (le > pos && data[le - 1] == '\r') le--;
         if (data[pos] == '>') {
             if (open) out->offsets.push_back(out->seqs.size());
-            out->ids.push_back(trimSpace(data.substr(pos + 1, le - pos - 1)));
+            out->ids.push_back(trimSpace(std::string(data.substr(pos + 1, le - pos - 1))));
             open = true;
         } else if (open) {
             out->seqs.insert(out->seqs.end(), data.begin() + pos, data.begin() + le);
@@ -149,7 +144,41 @@ bool ReadFasta(const std::string &path, FastaBatch *out, std::string *err)
     if (open) out->offsets.push_back(out->seqs.size());
     out->read_counts.reserve(out->ids.size());
     for (const auto &id : out->ids) out->read_counts.push_back(parseMergeCount(id));
+}
+
+bool ReadFasta(const std::string &path, FastaBatch *out, std::string *err)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in) {
+        if (err) *err = "open " + path + ": no such file or directory";
+        return false;
+    }
+    std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    ParseFasta(data.data(), data.size(), out);
     return true;
+}
+
+uint64_t FastaNextRecordStart(const uint8_t *fasta, uint64_t len, uint64_t from)
+{
+    if (from == 0) return 0;  // the head of the file belongs to the first slice whatever it holds
+    const uint8_t *p = fasta + from, *end = fasta + len;
+    while (p < end) {
+        const uint8_t *g = (const uint8_t *)memchr(p, '>', (size_t)(end - p));
+        if (!g) break;
+        if (g[-1] == '\n') return (uint64_t)(g - fasta);
+        p = g + 1;
+    }
+    return len;
+}
+
+void FastaSplit(const uint8_t *fasta, uint64_t len, uint32_t parts, uint64_t *offsets)
+{
+    offsets[0] = 0;
+    for (uint32_t k = 1; k < parts; k++) {
+        const uint64_t nominal = (uint64_t)((unsigned __int128)len * k / parts);
+        offsets[k] = FastaNextRecordStart(fasta, len, std::max(nominal, offsets[k - 1]));
+    }
+    offsets[parts] = len;
 }
 
 // ------------------------------------------------------------------ template.go

@@ -68,6 +68,12 @@ struct FastaBatch {
     std::string seq(size_t i) const { return std::string(seqs.begin() + offsets[i], seqs.begin() + offsets[i + 1]); }
 };
 bool ReadFasta(const std::string &path, FastaBatch *out, std::string *err);
+void ParseFasta(const char *bytes, size_t size, FastaBatch *out);  // the same on bytes in memory
+// First '>' at or behind `from` that is the first byte of a line (every record but the first of a file starts at one);
+// len if there is none; from == 0 -> 0.
+uint64_t FastaNextRecordStart(const uint8_t *fasta, uint64_t len, uint64_t from);
+// `parts` slices of about equal size that start at record starts: offsets[parts + 1], offsets[0] = 0, offsets[parts] = len
+void FastaSplit(const uint8_t *fasta, uint64_t len, uint32_t parts, uint64_t *offsets);
 
 // align.go:41-55; filled from a treat_b200_record
 struct Alignment {

@@ -15,6 +15,16 @@ def shard_range(N: int, rank: int, world: int) -> Tuple[int, int]:
     return (N * rank) // world, (N * (rank + 1)) // world
 
 
+def fasta_shard(data, rank: int, world: int):
+    """The slice of a FASTA file's bytes owned by `rank`: cut at record starts (treat_b200_fasta_split), so every rank
+    parses whole records and the ranks' records, in rank order, are the file's records in order."""
+    from .api import fasta_split
+    if isinstance(data, (bytes, bytearray)):
+        data = np.frombuffer(data, dtype=np.uint8)
+    off = fasta_split(data, world)
+    return data[int(off[rank]):int(off[rank + 1])], int(off[rank])
+
+
 class _DevMem:
     """Expose a raw device pointer through __cuda_array_interface__ so torch can alias it."""
 
