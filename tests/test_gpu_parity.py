@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 os.environ.setdefault("TREAT_B200_FASTA_PIECE", "300000")  # small pieces: treat_b200_fasta_stream cuts even the test files
+os.environ.setdefault("TREAT_B200_FASTA_CHUNK", "30000")   # treat_b200_fasta_align: several chunks for the larger test files
 
 import treat_b200 as T
 from treat_b200 import cabi, synth
@@ -320,7 +321,8 @@ def test_pack_lengths_and_alignments(eng, tmp_path):
     eng.SetTemplate(tm)
     rng = random.Random(20261020)
     reads = []
-    lens = [0, 1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 255, 256, 257, 495, 496, 497, 511, 512, 513, 527, 528, 1023, 1024, 1025, 3000]
+    lens = [0, 1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 255, 256, 257, 495, 496, 497, 511, 512, 513, 527, 528, 1023, 1024, 1025, 3000,
+            16383, 16384]
     for L in lens * 6:
         kind = rng.randrange(4)
         if kind == 0:
@@ -335,6 +337,8 @@ def test_pack_lengths_and_alignments(eng, tmp_path):
                 s += "T" * rng.randrange(0, 200) + rng.choice("ACG") * rng.randrange(1, 3)
             s = s[:L]
         reads.append(s)
+    with pytest.raises(T.TreatError):  # longer than the 16,384-character limit
+        eng.align_batch(np.full(16385, ord("A"), dtype=np.uint8), np.array([0, 16385], dtype=np.uint64), None, cabi.NO_SUMMARY)
     for pad in range(17):  # shift the whole batch through every misalignment
         batch = ["A" * pad] + reads
         seqs = np.frombuffer("".join(batch).encode(), dtype=np.uint8).copy()

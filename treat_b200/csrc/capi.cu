@@ -1064,7 +1064,7 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
     for (int i = 0; i < 2; i++)
         if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
     bool in_place = !fa.multi && !ctx->tmpl_wide;
-    const uint64_t chunk = 1ull << 20;
+    static const uint64_t chunk = getenv("TREAT_B200_FASTA_CHUNK") ? std::max(1024ull, strtoull(getenv("TREAT_B200_FASTA_CHUNK"), nullptr, 10)) : (1ull << 20);
     uint64_t k = 0;
     for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk, k++) {
         const uint64_t cn = std::min(chunk, N - c0);
