@@ -407,7 +407,8 @@ static int ensure_scalars(treat_b200_ctx *ctx, Slot &s)
 }
 
 static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
-                   const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st, const ReadSpan *span = nullptr)
+                   const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st, const ReadSpan *span = nullptr,
+                   bool padded = false)
 {
     PackParams pp{};
     pp.seqs = d_seqs;
@@ -427,6 +428,7 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     pp.scalars = d_scalars;
     pp.tpk = (!dst->wide && !ctx->tmpl_wide) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
     pp.tm = (uint32_t)ctx->td.m;
+    pp.padded = padded && ((uintptr_t)d_seqs & 15u) == 0 ? 1u : 0u;
     if (span && !dst->wide) {  // k_pack16 only
         pp.begin = span->begin;
         pp.len = span->len;
@@ -575,7 +577,8 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
 static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
                      const uint32_t *d_rc, uint64_t N, uint32_t max_len, uint32_t flags, treat_b200_record *d_rec,
                      uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st, bool force_wide, bool *saturated,
-                     uint32_t *ops_stride_used = nullptr, uint32_t spec_ncap = 0, const ReadSpan *span = nullptr)
+                     uint32_t *ops_stride_used = nullptr, uint32_t spec_ncap = 0, const ReadSpan *span = nullptr,
+                     bool padded = false)
 {
     const bool wide = ctx->tmpl_wide || force_wide;
     // ops into the slot's own buffer (host-buffer path): gapped-only rows are compacted there
@@ -607,7 +610,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     rc = ensure_scalars(ctx, s);
     if (rc) return rc;
     CK(ctx, cudaMemsetAsync(s.scalars, 0, kScalarBytes, st));
-    rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span);
+    rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded);
     if (rc) return rc;
     if (spec_ncap) {
         const uint32_t ncap = std::min(spec_ncap, max_len);
@@ -778,10 +781,10 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         bool sat = false;
         const uint32_t cflags = s.sparse ? flags : flags & ~TREAT_B200_OPS_GAPPED_ONLY;
         int r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, cflags,
-                          (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, false, &sat, &s.dev_stride);
+                          (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, false, &sat, &s.dev_stride, 0, nullptr, true);
         if (r == TREAT_B200_OK && sat && !ctx->tmpl_wide)
             r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, cflags,
-                          (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, true, nullptr, &s.dev_stride);
+                          (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, true, nullptr, &s.dev_stride, 0, nullptr, true);
         return r;
     };
     // a speculative chunk is final once its stream is idle and nothing was skipped or saturated
@@ -851,7 +854,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
             rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0,
                            read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len,
                            s.sparse ? flags : flags & ~TREAT_B200_OPS_GAPPED_ONLY, (treat_b200_record *)s.rec.p,
-                           nullptr, 0, st, false, nullptr, &s.dev_stride, ctx->ncap_hint + 8);
+                           nullptr, 0, st, false, nullptr, &s.dev_stride, ctx->ncap_hint + 8, nullptr, true);
             s.pending = rc == TREAT_B200_OK;
         } else {
             rc = run_exact(s);
@@ -997,17 +1000,17 @@ static int fasta_align_chunk(treat_b200_ctx *ctx, FastaDev &fa, Slot &s, uint64_
     if (*in_place) {
         const ReadSpan span{(const uint64_t *)fa.seq_begin.p + c0, (const uint32_t *)fa.seq_len.p + c0, fa.len};
         rc = run_chunk(ctx, s, (const uint8_t *)fa.file.p, nullptr, 0, d_rc, cn, fa.max_len, flags, (treat_b200_record *)s.rec.p, d_ops,
-                       d_stride, st, false, &sat, &s.dev_stride, spec_ncap, &span);
+                       d_stride, st, false, &sat, &s.dev_stride, spec_ncap, &span, true);
         if (spec_ncap) return rc;
         if (rc == TREAT_B200_OK && sat) *in_place = false;  // an edit-base run >= 255: the wide kernels read contiguous reads
     }
     if (rc == TREAT_B200_OK && !*in_place) {
         if ((rc = compact())) return rc;
         rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
-                       (treat_b200_record *)s.rec.p, d_ops, d_stride, st, false, &sat, &s.dev_stride);
+                       (treat_b200_record *)s.rec.p, d_ops, d_stride, st, false, &sat, &s.dev_stride, 0, nullptr, true);
         if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
             rc = run_chunk(ctx, s, (const uint8_t *)fa.seqs.p, (const uint64_t *)fa.seq_off.p + c0, 0, d_rc, cn, fa.max_len, flags,
-                           (treat_b200_record *)s.rec.p, d_ops, d_stride, st, true, nullptr, &s.dev_stride);
+                           (treat_b200_record *)s.rec.p, d_ops, d_stride, st, true, nullptr, &s.dev_stride, 0, nullptr, true);
     }
     return rc;
 }

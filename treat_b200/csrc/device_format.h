@@ -45,6 +45,7 @@ struct PackParams {
     const uint64_t *begin;
     const uint32_t *len;
     uint64_t span;
+    uint32_t padded;        // seqs is 16-byte aligned and readable 16 bytes past its last byte (library-owned buffers)
 };
 
 // internal bit of the per-read flag byte written by k_pack: the read's stripped bases equal the template's

@@ -202,6 +202,18 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
     return v;
 }
 
+// a 16-byte block that sticks out of the bytes [lo, hi) the launch may touch: byte loads (first / last read of a caller's buffer)
+__device__ __noinline__ uint4 load_block_edge(const uint8_t *seqs, int64_t x, int64_t lo, int64_t hi)
+{
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int64_t y = x + q;
+        if (y >= lo && y < hi) w[q >> 2] |= (uint32_t)seqs[y] << (8 * (q & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_constant__ PackParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -248,15 +260,10 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_c
         }
     };
     // the 16-byte aligned block at offset x of p.seqs (byte loads where it sticks out of [lo, hi))
+    // (p.padded: the buffer is 16-byte aligned and readable 16 bytes past its end, so no block ever sticks out)
     auto load_block = [&](int64_t x) -> uint4 {
-        if (x >= lo && x + 16 <= hi) return *reinterpret_cast<const uint4 *>(p.seqs + x);
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int64_t y = x + q;
-            if (y >= lo && y < hi) w[q >> 2] |= (uint32_t)p.seqs[y] << (8 * (q & 3));
-        }
-        return make_uint4(w[0], w[1], w[2], w[3]);
+        if (p.padded || (x >= lo && x + 16 <= hi)) return *reinterpret_cast<const uint4 *>(p.seqs + x);
+        return load_block_edge(p.seqs, x, lo, hi);
     };
     // this lane's block of the first 32 of a read (anything past the read's last block: it is masked out later)
     auto first_block = [&](uint64_t b, uint32_t L) -> uint4 {
