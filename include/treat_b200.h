@@ -51,6 +51,7 @@ extern "C" {
                                             (record.indel != 0); the row of any other read would be all zero (m = n
                                             match columns) and is unspecified (left untouched, or zeroed), so D2H traffic
                                             can shrink to the gapped reads */
+#define TREAT_B200_HEATMAP 0x100u /* also accumulate the ESS x junction-length heat map (treat_b200_get_heatmap) */
 #define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
                                            under the template that is current now, so reads it marked as equal to the template
                                            skip the DP; without this flag the stage call runs the DP for every read */
@@ -191,6 +192,14 @@ int treat_b200_get_summary(treat_b200_ctx *ctx, uint64_t *out, uint64_t len);
 int treat_b200_reset_summary(treat_b200_ctx *ctx);
 /* device pointer of the counters, for an NCCL all-reduce issued by the caller */
 int treat_b200_summary_device_ptr(treat_b200_ctx *ctx, uint64_t **d_ptr);
+/* ESS x junction-length heat map of the web UI (cmd/treat/handlers.go:578-589), accumulated on the device by align calls
+ * that carry TREAT_B200_HEATMAP: heat[(EditStop - EditOffset) * dim + JuncLen] += ReadCount for records with
+ * EditStop >= EditOffset, dim = Template.Len().  (The reference adds Norm, the ReadCount-derived weight of `treat norm`;
+ * it blanks the cell (Template.EditStop, 0) when it renders -- left to the consumer.)  Cleared by treat_b200_reset_summary;
+ * across GPUs: all-reduce dim*dim uint64 from treat_b200_heatmap_device_ptr. */
+uint32_t treat_b200_heatmap_dim(const treat_b200_ctx *ctx);
+int treat_b200_get_heatmap(treat_b200_ctx *ctx, uint64_t *out, uint64_t len);
+int treat_b200_heatmap_device_ptr(treat_b200_ctx *ctx, uint64_t **d_ptr);
 
 /* ---- roofline helper: dependent-free INT32 add/max throughput of this GPU ---------- */
 int treat_b200_measure_int32_peak(treat_b200_ctx *ctx, double *lane_ops_per_s, double *sm_mhz_effective);

@@ -50,3 +50,13 @@ def compare_records(got, want, seqs=None, seq_off=None):
     if len(d):
         bad.append(("status.panic", d[:5].tolist()))
     return bad
+
+
+def heatmap_from_records(rec: np.ndarray, len_: int, offset: int) -> np.ndarray:
+    """cmd/treat/handlers.go:578-589 with ReadCount for Norm: heat[EditStop - offset][JuncLen] += ReadCount, EditStop >= offset."""
+    heat = np.zeros((len_, len_), dtype=np.uint64)
+    es = rec["edit_stop"].astype(np.int64) - offset
+    jl = rec["junc_len"].astype(np.int64)
+    ok = (es >= 0) & (es < len_) & (jl < len_)
+    np.add.at(heat, (es[ok], jl[ok]), rec["read_count"][ok].astype(np.uint64))
+    return heat

@@ -13,7 +13,7 @@ import treat_b200 as T
 from treat_b200 import cabi, synth
 from oracle import oracle as O
 from oracle import pyref as P
-from helpers import compare_records, summary_from_records
+from helpers import compare_records, heatmap_from_records, summary_from_records
 
 pytestmark = pytest.mark.gpu
 
@@ -462,6 +462,44 @@ def test_fasta_ingest_on_device(eng, tmp_path):
     eng.reset_summary()
     eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
     assert np.array_equal(s1, eng.summary())
+
+
+def test_heatmap_consumer(eng, tmp_path):
+    """the ESS x junction-length heat map accumulated on the device == the same from the oracle's records,
+    through the host-buffer call (speculative chunks), the device entry point and the FASTA stream; with an edit offset."""
+    import torch
+    t = synth.rps12_template()
+    for offset in (0, 7):
+        om, tm = _oracle_template(t, tmp_path, offset)
+        eng.SetTemplate(tm)
+        N = 150000
+        seqs, off, rc = synth.reads(t, N, seed=2024 + offset)
+        rc = (rc.astype(np.uint64) * 40000 % 4000000000 + 1).astype(np.uint32)  # large counts: sums pass 32 bits
+        orec, _, _ = O.align_batch(om, seqs, off, rc, want_ops=False, nthreads=8)
+        want = heatmap_from_records(orec, t.m + 1, offset)
+        assert want.sum() > 0 and int(want.max()) > 2 ** 32
+        eng.reset_summary()
+        eng.align_batch(seqs, off, rc, cabi.HEATMAP)
+        assert np.array_equal(eng.heatmap(), want)
+        eng.align_batch(seqs, off, rc, 0)  # without the flag nothing is added
+        assert np.array_equal(eng.heatmap(), want)
+        eng.reset_summary()
+        assert eng.heatmap().sum() == 0
+        # device entry point
+        k = 40000
+        d_seqs = torch.from_numpy(seqs[:int(off[k])].copy()).cuda()
+        d_off = torch.from_numpy(off[:k + 1].astype(np.int64)).cuda()
+        d_rc = torch.from_numpy(rc[:k].view(np.int32).copy()).cuda()
+        d_rec = torch.zeros(k * 48, dtype=torch.uint8, device="cuda")
+        eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), k, int(np.diff(off[:k + 1].astype(np.int64)).max()),
+                               cabi.HEATMAP, d_rec.data_ptr(), 0, 0)
+        assert np.array_equal(eng.heatmap(), heatmap_from_records(orec[:k], t.m + 1, offset))
+    # FASTA stream (pieces aligned speculatively, added when validated)
+    eng.reset_summary()
+    text = b"".join(b">h%d_%d\n" % (i, rc[i]) + seqs[int(off[i]):int(off[i + 1])].tobytes() + b"\n" for i in range(60000))
+    pieces, total = eng.stream_fasta(text, cabi.HEATMAP)
+    assert total == 60000
+    assert np.array_equal(eng.heatmap(), heatmap_from_records(orec[:60000], t.m + 1, 7))
 
 
 def test_stage_calls_and_pack_marks(eng, tmp_path):

@@ -518,6 +518,19 @@ class Aligner:
     def reset_summary(self) -> None:
         check(lib().treat_b200_reset_summary(self._ctx), self._ctx)
 
+    def heatmap(self) -> np.ndarray:
+        """ESS x junction-length heat map [dim, dim] accumulated by align calls with the HEATMAP flag (handlers.go:578-589)."""
+        d = lib().treat_b200_heatmap_dim(self._ctx)
+        out = np.zeros((d, d), dtype=np.uint64)
+        check(lib().treat_b200_get_heatmap(self._ctx, out.ctypes.data, d * d), self._ctx)
+        return out
+
+    def heatmap_device_ptr(self) -> Tuple[int, int]:
+        p = C.c_void_p()
+        check(lib().treat_b200_heatmap_device_ptr(self._ctx, C.byref(p)), self._ctx)
+        d = lib().treat_b200_heatmap_dim(self._ctx)
+        return p.value, d * d
+
     def summary_device_ptr(self) -> Tuple[int, int]:
         p = C.c_void_p()
         check(lib().treat_b200_summary_device_ptr(self._ctx, C.byref(p)), self._ctx)

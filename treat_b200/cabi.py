@@ -17,7 +17,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TOO_LONG, ERR_NO_TEMPLATE, ERR_NO_DEVICE, ERR_TEMPLATE, ERR_IO = range(-1, -9, -1)
 FORWARD, REVERSE = 1, -1
 EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY, ONE_READ_PER_WARP, FULL_TRACEBACK_STORE = 0x1, 0x2, 0x4, 0x8, 0x10
-DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY = 0x20, 0x40, 0x80
+DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY, HEATMAP = 0x20, 0x40, 0x80, 0x100
 ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16
@@ -73,6 +73,9 @@ SIGNATURES = {
     "treat_b200_align_batch_device": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
     "treat_b200_ops_stride": (C.c_uint32, [_P, C.c_uint32]),
     "treat_b200_synchronize": (C.c_int, [_P]),
+    "treat_b200_heatmap_dim": (C.c_uint32, [_P]),
+    "treat_b200_get_heatmap": (C.c_int, [_P, _P, C.c_uint64]),
+    "treat_b200_heatmap_device_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "treat_b200_fasta_parse": (C.c_int, [_U8P, C.c_uint64, C.POINTER(C.c_void_p)]),
     "treat_b200_fasta_split": (C.c_int, [_U8P, C.c_uint64, C.c_uint32, _P]),
     "treat_b200_fasta_upload": (C.c_int, [_P, _U8P, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),

@@ -1353,6 +1353,43 @@ __global__ void k_merge_summary(unsigned long long *dst, unsigned long long *src
     }
 }
 
+// ESS x junction-length heat map (cmd/treat/handlers.go:578-589): heat[EditStop - EditOffset][JuncLen] += ReadCount for
+// records with EditStop >= EditOffset (the reference adds Norm, the ReadCount-derived weight of `treat norm`).
+// One thread per record; lanes of a warp that hit the same cell combine first, so hot cells see one atomic per warp.
+__global__ void __launch_bounds__(256) k_heatmap(const treat_b200_record *rec, uint64_t N, int edit_offset, uint32_t n,
+                                                 unsigned long long *heat)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (N + stride - 1) / stride;  // whole warps stay in the loop for the warp votes
+    for (uint64_t k = 0; k < rounds; k++) {
+        const uint64_t i = k * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t cell = 0xffffffffu, rc = 0;
+        if (i < N) {
+            const int es = rec[i].edit_stop - edit_offset;
+            const uint32_t jl = rec[i].junc_len;
+            if (es >= 0 && (uint32_t)es < n && jl < n) {
+                cell = (uint32_t)es * n + jl;
+                rc = rec[i].read_count;
+            }
+        }
+        const unsigned peers = __match_any_sync(FULL_MASK, cell);
+        // REDUX adds 32-bit values; 32 read counts may need 37 bits: add the halves separately
+        unsigned long long tot;
+        const uint32_t lo = __reduce_add_sync(peers, rc & 0xffffu), hi = __reduce_add_sync(peers, rc >> 16);
+        tot = (unsigned long long)lo + ((unsigned long long)hi << 16);
+        if (cell != 0xffffffffu && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&heat[cell], tot);
+    }
+}
+
+int launch_heatmap(const treat_b200_record *d_rec, uint64_t N, int edit_offset, uint32_t n, uint64_t *d_heat, int num_sms, void *stream)
+{
+    if (!N) return 0;
+    uint64_t blocks = (N + 255) / 256;
+    if (blocks > (uint64_t)num_sms * 8) blocks = (uint64_t)num_sms * 8;
+    k_heatmap<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_rec, N, edit_offset, n, reinterpret_cast<unsigned long long *>(d_heat));
+    return (int)cudaGetLastError();
+}
+
 int launch_merge_summary(uint64_t *dst, uint64_t *src, uint32_t len, void *stream)
 {
     k_merge_summary<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(dst),

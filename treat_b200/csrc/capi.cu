@@ -128,6 +128,7 @@ struct treat_b200_ctx {
     std::vector<uint8_t> lut;
     uint64_t *d_summary = nullptr;
     uint32_t bins = 0;
+    uint64_t *d_heat = nullptr;  // [len][len] ESS x junction-length heat map (TREAT_B200_HEATMAP)
     Slot slot[kSlots];
     // scratch for the device-resident entry point
     Slot dev_slot;
@@ -217,6 +218,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     cudaDeviceSynchronize();
     for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->d_tpk}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
+    if (ctx->d_heat) cudaFree(ctx->d_heat);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     for (Slot &sl : ctx->slot) sl.release();
     ctx->dev_slot.release();
@@ -322,6 +324,10 @@ int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m
     const size_t sl = (TREAT_B200_SUMMARY_HEADER + 3 * (size_t)bins) * 8;
     CK(ctx, cudaMalloc((void **)&ctx->d_summary, sl));
     CK(ctx, cudaMemset(ctx->d_summary, 0, sl));
+    if (ctx->d_heat) cudaFree(ctx->d_heat);
+    ctx->d_heat = nullptr;
+    CK(ctx, cudaMalloc((void **)&ctx->d_heat, (size_t)len * len * 8));
+    CK(ctx, cudaMemset(ctx->d_heat, 0, (size_t)len * len * 8));
     ctx->have_template = true;
     ctx->ncap_hint = 0;
     return TREAT_B200_OK;
@@ -396,6 +402,16 @@ int treat_b200_packed_layout(const treat_b200_ctx *ctx, uint64_t N, uint32_t max
     out->wide = wide ? 1 : 0;
     out->bases_stride = std::max(16u, wide ? a16(max_len) : a16((max_len + 3) / 4));
     out->counts_stride = wide ? a16(4 * (max_len + 1)) : a16(max_len + 1);
+    return TREAT_B200_OK;
+}
+
+// heat map of a finished, validated range of records (TREAT_B200_HEATMAP)
+static int add_heatmap(treat_b200_ctx *ctx, uint32_t flags, const treat_b200_record *d_rec, uint64_t N, cudaStream_t st)
+{
+    if (!(flags & TREAT_B200_HEATMAP) || !N) return TREAT_B200_OK;
+    int e = launch_heatmap(d_rec, N, ctx->td.edit_offset, (uint32_t)ctx->td.len, ctx->d_heat, ctx->num_sms, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_heatmap launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
     return TREAT_B200_OK;
 }
 
@@ -649,7 +665,9 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         d_ops = (uint8_t *)s.ops.p;
     }
     if (ops_stride_used) *ops_stride_used = ops_stride;
-    return do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, opts(slot_own_ops));
+    rc = do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, opts(slot_own_ops));
+    if (rc) return rc;
+    return add_heatmap(ctx, flags, d_rec, N, st);  // a speculative launch is added once it is validated
 }
 
 // pinned landing buffers for `rows` compacted ops rows of a slot
@@ -802,6 +820,8 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
                 if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_merge_summary launch failed");
                 ctx->launches++;
             }
+            int hr = add_heatmap(ctx, flags, (const treat_b200_record *)s.rec.p, s.cn, s.stream);
+            if (hr) return hr;
             return place_rows(s);
         }
         redone++;
@@ -1236,10 +1256,13 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
                     if ((rc = fasta_align_chunk(ctx, fa, s, 0, n, flags, pc[k].stride, &pc[k].in_place))) break;
                     if ((rc = enqueue_results(k))) break;
                     CK(ctx, cudaStreamSynchronize(s.stream));
-                } else if (!(flags & TREAT_B200_NO_SUMMARY)) {
-                    int e = launch_merge_summary(ctx->d_summary, (uint64_t *)s.summary.p, (uint32_t)treat_b200_summary_len(ctx), s.stream);
-                    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_merge_summary launch failed");
-                    ctx->launches++;
+                } else {
+                    if (!(flags & TREAT_B200_NO_SUMMARY)) {
+                        int e = launch_merge_summary(ctx->d_summary, (uint64_t *)s.summary.p, (uint32_t)treat_b200_summary_len(ctx), s.stream);
+                        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_merge_summary launch failed");
+                        ctx->launches++;
+                    }
+                    if ((rc = add_heatmap(ctx, flags, (const treat_b200_record *)s.rec.p, n, s.stream))) break;
                 }
             }
             if (n) {
@@ -1328,6 +1351,29 @@ int treat_b200_reset_summary(treat_b200_ctx *ctx)
     int rc = treat_b200_synchronize(ctx);
     if (rc) return rc;
     CK(ctx, cudaMemset(ctx->d_summary, 0, treat_b200_summary_len(ctx) * 8));
+    CK(ctx, cudaMemset(ctx->d_heat, 0, (size_t)ctx->td.len * ctx->td.len * 8));
+    return TREAT_B200_OK;
+}
+
+uint32_t treat_b200_heatmap_dim(const treat_b200_ctx *ctx) { return ctx && ctx->have_template ? (uint32_t)ctx->td.len : 0; }
+
+int treat_b200_get_heatmap(treat_b200_ctx *ctx, uint64_t *out, uint64_t len)
+{
+    if (!ctx || !out) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "heatmap: no template");
+    const uint64_t n = (uint64_t)ctx->td.len * ctx->td.len;
+    if (len < n) return fail(ctx, TREAT_B200_ERR_INVALID, "heatmap: buffer too small (dim * dim)");
+    int rc = treat_b200_synchronize(ctx);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpy(out, ctx->d_heat, n * 8, cudaMemcpyDeviceToHost));
+    return TREAT_B200_OK;
+}
+
+int treat_b200_heatmap_device_ptr(treat_b200_ctx *ctx, uint64_t **d_ptr)
+{
+    if (!ctx || !d_ptr) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "heatmap: no template");
+    *d_ptr = ctx->d_heat;
     return TREAT_B200_OK;
 }
 

@@ -115,6 +115,7 @@ int plan_align(AlignParams &p, bool wide);
 int align_warps(const AlignParams &p, int max_smem);
 uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
 int launch_merge_summary(uint64_t *dst, uint64_t *src, uint32_t len, void *stream);
+int launch_heatmap(const treat_b200_record *d_rec, uint64_t N, int edit_offset, uint32_t n, uint64_t *d_heat, int num_sms, void *stream);
 // FASTA ingest (fasta_kernel.cu)
 int launch_fasta_mark(const uint8_t *file, uint64_t len, uint64_t tile0, uint64_t ntiles, uint32_t *tile_count,
                       uint64_t *first_gt, int num_sms, void *stream);

@@ -39,6 +39,13 @@ def summary_tensor(engine):
     return torch.as_tensor(_DevMem(ptr, n), device=f"cuda:{engine.device}")
 
 
+def heatmap_tensor(engine):
+    """torch int64 view (no copy) of the device-resident ESS x junction-length heat map, flattened [dim * dim]."""
+    import torch
+    ptr, n = engine.heatmap_device_ptr()
+    return torch.as_tensor(_DevMem(ptr, n), device=f"cuda:{engine.device}")
+
+
 def allreduce_summary(t, group=None):
     """Sum the counters over all ranks.  Exact integers: reduction order cannot change the result.
     `t` is an int64 tensor (device tensor -> NCCL over NVLink; CPU tensor -> gloo)."""
