@@ -202,18 +202,8 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
     return v;
 }
 
-// a 16-byte block that sticks out of the bytes [lo, hi) the launch may touch: byte loads (first / last read of a caller's buffer)
-__device__ __noinline__ uint4 load_block_edge(const uint8_t *seqs, int64_t x, int64_t lo, int64_t hi)
-{
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        const int64_t y = x + q;
-        if (y >= lo && y < hi) w[q >> 2] |= (uint32_t)seqs[y] << (8 * (q & 3));
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
+// SPAN: reads given as (begin, length) inside one buffer (FASTA records in place) instead of back-to-back offsets
+template <bool SPAN>
 __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_constant__ PackParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -246,11 +236,11 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_c
     const uint32_t lt = (1u << lane) - 1u;
     const uintptr_t base_addr = reinterpret_cast<uintptr_t>(p.seqs);
     // the bytes of p.seqs this launch may touch: [lo, hi)
-    const int64_t lo = p.begin ? 0 : p.N ? (int64_t)(p.off[0] - p.off_bias) : 0;
-    const int64_t hi = p.begin ? (int64_t)p.span : p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
+    const int64_t lo = SPAN ? 0 : p.N ? (int64_t)(p.off[0] - p.off_bias) : 0;
+    const int64_t hi = SPAN ? (int64_t)p.span : p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
     // start and length of read r
     auto where = [&](uint64_t r, uint64_t &b, uint32_t &L) {
-        if (p.begin) {
+        if (SPAN) {
             b = p.begin[r];
             L = p.len[r];
         } else {
@@ -263,7 +253,13 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32, 4) k_pack16(const __grid_c
     // (p.padded: the buffer is 16-byte aligned and readable 16 bytes past its end, so no block ever sticks out)
     auto load_block = [&](int64_t x) -> uint4 {
         if (p.padded || (x >= lo && x + 16 <= hi)) return *reinterpret_cast<const uint4 *>(p.seqs + x);
-        return load_block_edge(p.seqs, x, lo, hi);
+        uint32_t w[4] = {0u, 0u, 0u, 0u};  // first / last read of a caller's buffer: byte loads
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int64_t y = x + q;
+            if (y >= lo && y < hi) w[q >> 2] |= (uint32_t)p.seqs[y] << (8 * (q & 3));
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
     };
     // this lane's block of the first 32 of a read (anything past the read's last block: it is masked out later)
     auto first_block = [&](uint64_t b, uint32_t L) -> uint4 {
@@ -427,7 +423,8 @@ int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin,
     int per_sm = 0;
     cudaError_t oe = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack<true>, warps * 32, smem)
                      : v1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack<false>, warps * 32, smem)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack16, warps * 32, smem);
+          : p.begin ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack16<true>, warps * 32, smem)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack16<false>, warps * 32, smem);
     if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint64_t cap = (uint64_t)num_sms * per_sm;
     if (blocks > cap) blocks = cap;
@@ -436,8 +433,10 @@ int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin,
         k_pack<true><<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
     else if (v1)
         k_pack<false><<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    else if (p.begin)
+        k_pack16<true><<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
     else
-        k_pack16<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+        k_pack16<false><<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -448,7 +447,9 @@ int configure_pack_kernels(int max_smem_optin)
     if (ce != cudaSuccess) return (int)ce;
     ce = cudaFuncSetAttribute(k_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (ce != cudaSuccess) return (int)ce;
-    ce = cudaFuncSetAttribute(k_pack16, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    ce = cudaFuncSetAttribute(k_pack16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce != cudaSuccess) return (int)ce;
+    ce = cudaFuncSetAttribute(k_pack16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     return (int)ce;
 }
 
