@@ -358,15 +358,60 @@ __global__ void __launch_bounds__(256) k_fasta_records(const __grid_constant__ F
             first_drop = ab + 16ull * f + (uint32_t)(__shfl_sync(FULL_MASK, __ffs(drop) - 1, f));
         }
         if (kept != (uint32_t)(first_drop - sb)) wmulti = 1;  // a kept byte behind a dropped one: more than one line
-        if (lane == 0) {
-            // strings.TrimSpace of the header: the bytes were just loaded, these scans hit L1
-            uint64_t ib = b + 1, il = eol;
+        // header: strings.TrimSpace and parseMergeCount.  Up to 32 header bytes are handled by the warp, one byte per
+        // lane (the bytes were just loaded: L1 hits); longer headers, and counts of ten or more digits, by lane 0.
+        const uint32_t hl = (uint32_t)(eol - (b + 1));
+        uint64_t ib = b + 1;
+        uint32_t idn = 0, rcount = 1u;
+        if (hl <= 32) {
+            const uint32_t c = (uint32_t)lane < hl ? (uint32_t)p.file[b + 1 + lane] : (uint32_t)' ';
+            const uint32_t nsp = __ballot_sync(FULL_MASK, !is_space(c));
+            const uint32_t spm = __ballot_sync(FULL_MASK, c == ' ');
+            const uint32_t sepm = __ballot_sync(FULL_MASK, c == '_' || c == '-');
+            const uint32_t dig = __ballot_sync(FULL_MASK, c >= '0' && c <= '9');
+            if (nsp) {
+                const int first = __ffs(nsp) - 1, last = 31 - __clz(nsp);
+                idn = (uint32_t)(last - first + 1);
+                ib = b + 1 + first;
+                const uint32_t idm = (last == 31 ? 0xffffffffu : (2u << last) - 1u) & ~((1u << first) - 1u);
+                const uint32_t sp = spm & idm;
+                const int head_end = sp ? __ffs(sp) - 1 : last + 1;                 // first space-separated token: [first, head_end)
+                const uint32_t hm = idm & (head_end == 32 ? 0xffffffffu : (1u << head_end) - 1u);
+                const uint32_t sm = sepm & hm;
+                if (sm) {
+                    const int sep = 31 - __clz(sm);                                  // `.+[_\-](\d+)$`: the last '_' or '-' of the token
+                    const uint32_t dm = hm & ~((2u << sep) - 1u);                    // what follows it
+                    if (sep > first && dm != 0u && (dm & ~dig) == 0u) {
+                        const int nd = head_end - sep - 1;
+                        if (nd <= 9) {
+                            uint32_t term = 0;
+                            if ((dm >> lane) & 1u) {
+                                const int ex = head_end - 1 - lane;
+                                uint32_t pw = 1u;
+                                if (ex & 1) pw *= 10u;
+                                if (ex & 2) pw *= 100u;
+                                if (ex & 4) pw *= 10000u;
+                                if (ex & 8) pw *= 100000000u;
+                                term = (c - '0') * pw;
+                            }
+                            rcount = __reduce_add_sync(FULL_MASK, term);
+                        } else if (lane == 0) {
+                            rcount = merge_count(p.file + ib, idn);  // int64 range check and the cut to 32 bits
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            uint64_t il = eol;
             while (ib < il && is_space(p.file[ib])) ib++;
             while (il > ib && is_space(p.file[il - 1])) il--;
-            const uint32_t idn = il > ib ? (uint32_t)(il - ib) : 0u;
+            idn = il > ib ? (uint32_t)(il - ib) : 0u;
+            rcount = idn ? merge_count(p.file + ib, idn) : 1u;
+        }
+        if (lane == 0) {
             p.id_off[r] = idn ? ib : (b + 1 < p.len ? b + 1 : p.len);
             p.id_len[r] = idn;
-            p.read_count[r] = idn ? merge_count(p.file + ib, idn) : 1u;
+            p.read_count[r] = rcount;
             p.seq_begin[r] = sb;
             p.seq_len[r] = kept;
         }
