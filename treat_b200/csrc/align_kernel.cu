@@ -575,6 +575,9 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
                                             unsigned gmask, int lead, uint64_t r, uint32_t rflags, const uint4 &c,
                                             const SameLane &sl, unsigned long long &ctr)
 {
+    // no gap; no mismatch, or exactly one (kFlagOneMismatch: the diagonal still is the unique optimum, score m - 2)
+    const int mism = (rflags & kFlagOneMismatch) ? 1 : 0;
+    const int has_mutation = ((p.flags & TREAT_B200_EXCLUDE_SNPS) && mism) ? 1 : 0;  // align.go:240-241
     const int m = p.t.m, n = m, len = p.t.len, K = p.t.K, base = 16 * gl;
     const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
     uint32_t df[4], dp[4];  // non-zero byte: the read's count differs from FE / PE at that site
@@ -616,7 +619,7 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
     uint32_t js_off = 0, js_len = 0, status = rflags & ~kFlagsInternal;
     if (junc_end > edit_stop) {
         junc_len = junc_end - edit_stop;
-        if (!t0_all) {  // has_mutation is 0 for such a read
+        if (has_mutation == 0 && !t0_all) {
             const int from = (len - 1) - junc_end, to = (len - 1) - edit_stop;
             if (to > n + 1) {
                 status |= TREAT_B200_ST_REF_PANIC;
@@ -643,8 +646,8 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
         edit_stop = junc_start;
         junc_len = 0;
     }
-    emit_result<uint8_t>(p, cs, gl, r, n, /*alen*/ m, status, /*score*/ m, edit_stop, junc_start, junc_end, junc_len,
-                         /*has_mutation*/ 0, /*alt_editing*/ 0, /*mism*/ 0, /*indel*/ false, js_off, js_len, ctr);
+    emit_result<uint8_t>(p, cs, gl, r, n, /*alen*/ m, status, /*score*/ m - 2 * mism, edit_stop, junc_start, junc_end, junc_len,
+                         has_mutation, /*alt_editing*/ 0, mism, /*indel*/ false, js_off, js_len, ctr);
     if (p.ops && !p.ops_gapped_only) {  // m match columns: an all-zero row
         uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + r * (uint64_t)p.ops_stride);
         for (int wi = gl; wi < (int)(p.ops_stride / 4); wi += G) go[wi] = 0u;
@@ -1168,8 +1171,7 @@ __global__ void __launch_bounds__(kSameWarps * 32, 2) k_same_bases(const __grid_
         fetch(r + nw * RPW, fn, cn);
         bool general = false;  // the group's read needs the general assembly
         if (r < p.N) {
-            if (f & kFlagSameBases) general = !finish_same<G>(p, cs, s_mask, gl, gmask, lead, r, f, c, sl, ctr);
-            else if (f & kFlagOneMismatch) general = true;  // one substitution: still the diagonal, general assembly
+            if (f & kFlagsInternal) general = !finish_same<G>(p, cs, s_mask, gl, gmask, lead, r, f, c, sl, ctr);
             else if (gl == 0) p.list[atomicAdd(p.list_count, 1u)] = (uint32_t)r;
         }
         // an alternative template's region: the whole warp runs the general assembly, one read at a time
