@@ -269,9 +269,9 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
  * record.junc_seq_off counts from there when the record has a single sequence line.)
  *
  * Streaming form: one call, nothing to size in advance.  The bytes are cut at record starts into pieces of ~32 MB; copy,
- * index, alignment and delivery of four pieces overlap; every finished piece is handed to `sink` in file order (pointers
- * are valid during the call only; a non-zero return stops the run).  This is the shape of the reference's loop
- * (storage.go:738-785): the sink is where MarshalBinary + Put go. */
+ * index, alignment and delivery of up to six pieces overlap; every finished piece is handed to `sink` in file order
+ * (pointers are valid during the call only; a non-zero return stops the run; the sink must not call align functions of the
+ * same context).  This is the shape of the reference's loop (storage.go:738-785): the sink is where MarshalBinary + Put go. */
 typedef struct treat_b200_fasta_piece {
     uint64_t first_record;         /* number of the piece's first record in the file */
     uint64_t n;                    /* records in this piece */
