@@ -909,7 +909,6 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
         int H[CPL];
         const int steps = n > 0 ? n + lanes_used - 1 : 0;
         const uint8_t *rbl = rb - lane;  // rbl[t] = read base of this lane's row at step t
-        fill_one<CPL, WIDE, false>(cs.prof, rbl, tcr, n, steps, lane, H, s_dir, cs.dump, C);
         auto final_score = [&]() {
             // F[m][n] = G[m][n] - m - n; G[m][n] lives in lane (m-1)/CPL, column (m-1)%CPL
             int fin = 0;
@@ -919,11 +918,21 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
                 if (k == kl) fin = H[k];
             return __shfl_sync(FULL_MASK, fin, (m - 1) / CPL) - m - n;
         };
-        const int score = final_score();
+        // S <= min(m, n) - |m - n|, so the certificate (m - S <= 2B and n - S <= 2B) cannot hold when |m - n| > B:
+        // such a read (a truncated one, typically) goes straight to the full fill
+        bool full = p.force_full || abs(m - n) > B;
+        int score;
+        for (;;) {
+            if (full) fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, cs.dump, 0);  // every word kept (global scratch, L2)
+            else fill_one<CPL, WIDE, false>(cs.prof, rbl, tcr, n, steps, lane, H, s_dir, cs.dump, C);
+            score = final_score();
+            if (full || (score == m && n == m) || band_ok(m, n, score, B)) break;
+            full = true;  // the path may leave the band: repeat the fill
+        }
         int ngaps = 0, pos = n;  // alignment = ops2[pos, m + n)
         if (score == m && n == m) {
             // every base matches: the only optimal path is the main diagonal (m zero ops, already zeroed)
-        } else if (band_ok(m, n, score, B) && !p.force_full) {
+        } else if (!full) {
             pos = traceback<CPL>(
                 [&](int tt, int ln) {
                     TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
@@ -931,8 +940,6 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
                 },
                 ws.ops2, m, n, lane, ngaps);
         } else {
-            // the path may leave the band: repeat the fill with every word kept (global scratch, L2)
-            fill_one<CPL, WIDE, true>(cs.prof, rbl, tcr, n, steps, lane, H, scratch, cs.dump, 0);
             pos = traceback<CPL>(
                 [&](int tt, int ln) {
                     TB_CHECK(p, (unsigned)(tt * 32 + ln) < p.scratch_stride, 1);
@@ -1050,18 +1057,25 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
         uint32_t H[CPL];
         const int steps = nmax > 0 ? nmax + lanes_used - 1 : 0;
         const uint8_t *pcl = pc - lane;
-        fill_two<CPL, false>(cs.prof, pcl, steps, lane, H, s_dir, cs.dump, C);
-        uint32_t fin = 0;
-        {
+        // S <= min(m, n) - |m - n|: a read with |m - n| > B can never pass the band certificate, so such a pair goes
+        // straight to the full fill (every word kept in the global scratch)
+        bool full = p.force_full || abs(m - n0) > B || (has1 && abs(m - n1) > B);
+        int score0, score1;
+        for (;;) {
+            if (full) fill_two<CPL, true>(cs.prof, pcl, steps, lane, H, scratch, cs.dump, 0);
+            else fill_two<CPL, false>(cs.prof, pcl, steps, lane, H, s_dir, cs.dump, C);
+            uint32_t fin = 0;
             const int kl = (m - 1) % CPL;
 #pragma unroll
             for (int k = 0; k < CPL; k++)
                 if (k == kl) fin = H[k];
             fin = __shfl_sync(FULL_MASK, fin, (m - 1) / CPL);
+            score0 = (int)(fin & 0xffffu) - m - n0;
+            score1 = (int)(fin >> 16) - m - n1;
+            if (full || (band_ok(m, n0, score0, B) && (!has1 || band_ok(m, n1, score1, B)))) break;
+            full = true;  // a path may leave the band: repeat the fill
         }
-        const int score0 = (int)(fin & 0xffffu) - m - n0, score1 = (int)(fin >> 16) - m - n1;
-        const bool banded = band_ok(m, n0, score0, B) && (!has1 || band_ok(m, n1, score1, B)) && !p.force_full;
-        if (!banded) fill_two<CPL, true>(cs.prof, pcl, steps, lane, H, scratch, cs.dump, 0);  // keep every word (global scratch)
+        const bool banded = !full;
 
         // ---- per read: traceback + editing-site assembly ---------------------------------------
         for (int h = 0; h < (has1 ? 2 : 1); h++) {
