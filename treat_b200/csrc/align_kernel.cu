@@ -59,7 +59,12 @@ constexpr int kPadCode = 4;  // profile row with w = 0: a no-op row of the wavef
     do {                       \
     } while (0)
 #endif
-constexpr int kMaxWarpsPair = 32;  // resident warps per SM the register budget allows (k_align2: 63 registers)
+// resident warps per SM the register budget allows in k_align2 (64 registers up to 7 columns per lane)
+__host__ __device__ constexpr int max_warps_pair(int cpl) { return cpl <= 7 ? 32 : cpl <= 10 ? 20 : 16; }
+// k_align2's direction words: both reads' 16-bit words in one uint32 up to 7 columns per lane; beyond that two words per
+// read (columns 0..6 + boundary dV, columns 7..CPL-1), i.e. a uint2 per step
+template <int CPL>
+using pair_word_t = typename std::conditional<(CPL <= 7), uint32_t, uint2>::type;
 // one-read kernel: more columns per lane need more registers, so fewer warps
 __host__ __device__ constexpr int max_warps_one(int cpl) { return cpl <= 7 ? 24 : cpl <= 12 ? 20 : 16; }
 
@@ -729,10 +734,13 @@ __device__ __forceinline__ void fill_one(const uint32_t *prof, const uint8_t *rb
 
 template <int CPL, bool FULL>
 __device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pcl, int steps, int lane, uint32_t (&H)[CPL],
-                                         uint32_t *out, uint32_t *dump, int C)
+                                         pair_word_t<CPL> *out, uint32_t *dump, int C)
 {
-    using DT = Dir<CPL>;
     constexpr int ROWS = 25, P = CPL + 1;
+    constexpr bool TWO = CPL > 7;                      // two words per step
+    constexpr int G0 = TWO ? 7 : CPL;                  // columns in the first word
+    constexpr uint32_t kTop = 14;                      // bit position of dV(left boundary) in the first word
+    constexpr uint32_t ROWB = 32u * (uint32_t)sizeof(pair_word_t<CPL>);  // bytes of one step's words
 #pragma unroll
     for (int k = 0; k < CPL; k++) H[k] = 0u;
     uint32_t nd14 = 0u;  // -(G[i0-1][j-1] << kTop), carried from the previous step
@@ -743,12 +751,13 @@ __device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pc
     int cnext = pcl[1];
     const int nchunks = (steps + P - 1) / P;
     const uint32_t pcl32 = smem_u32(pcl);
-    const uint32_t dump32 = smem_u32(dump + lane), out32 = FULL ? 0u : smem_u32(out + lane);
+    const uint32_t dump32 = smem_u32(dump) + (uint32_t)lane * (uint32_t)sizeof(pair_word_t<CPL>);
+    const uint32_t out32 = FULL ? 0u : smem_u32(out + lane);
     for (int u = 0; u < nchunks; u++) {
         // lanes outside their band window write into a CTA-wide dump row: no predicate inside the chunk
         const bool keep = FULL || (unsigned)(u - lane + C) <= (unsigned)(2 * C);
-        uint32_t *grow = out + u * (P * 32) + lane;                                   // FULL: global scratch row
-        const uint32_t srow = keep ? out32 + (uint32_t)(u - lane + C) * (P * 128u) : dump32;  // banded: shared row
+        pair_word_t<CPL> *grow = out + u * (P * 32) + lane;                                  // FULL: global scratch row
+        const uint32_t srow = keep ? out32 + (uint32_t)(u - lane + C) * (P * ROWB) : dump32;  // banded: shared row
         const uint32_t pcu32 = pcl32 + (uint32_t)(u * P);
 #pragma unroll
         for (int v = 0; v < P; v++) {
@@ -758,10 +767,12 @@ __device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pc
             const uint32_t recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
             const uint32_t left = lane == 0 ? 0u : recv;
             // digits + dV(boundary) for both halves at once (mod 2^32 keeps each 16-bit word exact; left >= diag per half):
-            //   sum_k (f_k - f_{k-1}) 4^k + (left - diag) 2^kTop
-            // = f_last 4^(CPL-1) - 3 sum_{k<CPL-1} f_k 4^k - left + left 2^kTop - diag 2^kTop
-            const uint32_t nl14 = left * (0u - (1u << DT::kTop));
-            uint32_t acc = nd14 - nl14 - left;
+            //   sum_{k<G0} (f_k - f_{k-1}) 4^k + (left - diag) 2^kTop
+            // = f_{G0-1} 4^(G0-1) - 3 sum_{k<G0-1} f_k 4^k - left + left 2^kTop - diag 2^kTop
+            // and, for the columns of the second word (its "left" is f_{G0-1}):
+            //   sum_{k>=G0} (f_k - f_{k-1}) 4^(k-G0) = f_last 4^(CPL-1-G0) - 3 sum_{G0<=k<CPL-1} f_k 4^(k-G0) - f_{G0-1}
+            const uint32_t nl14 = left * (0u - (1u << kTop));
+            uint32_t acc = nd14 - nl14 - left, acc2 = 0u;
             nd14 = nl14;
             uint32_t dg = diag, lf = left;
 #pragma unroll
@@ -771,15 +782,40 @@ __device__ __forceinline__ void fill_two(const uint32_t *prof, const uint8_t *pc
                 dg = H[k];
                 lf = f;
                 H[k] = f;
-                acc += f * (k == CPL - 1 ? (1u << (2 * (CPL - 1))) : 0u - (3u << (2 * k)));
+                if (k < G0) {
+                    acc += f * (k == G0 - 1 ? (1u << (2 * (G0 - 1))) : 0u - (3u << (2 * k)));
+                    if (TWO && k == G0 - 1) acc2 -= f;
+                } else {
+                    constexpr int last2 = CPL - 1 - G0 > 0 ? CPL - 1 - G0 : 0;
+                    const int k2 = k >= G0 ? k - G0 : 0;
+                    acc2 += f * (k == CPL - 1 ? (1u << (2 * last2)) : 0u - (3u << (2 * k2)));
+                }
             }
             diag = left;
-            if (FULL) grow[v * 32] = acc; else sts_u32(srow + v * 128u, acc);
+            if constexpr (TWO) {
+                if (FULL) grow[v * 32] = make_uint2(acc, acc2);
+                else sts_v2(srow + v * ROWB, acc, acc2);
+            } else {
+                if (FULL) grow[v * 32] = acc;
+                else sts_u32(srow + v * ROWB, acc);
+            }
 #pragma unroll
             for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
         }
     }
     __syncwarp();
+}
+
+// the 16-bit (CPL <= 7) or 32-bit direction word of read h (0 / 1) out of a pair word, in the layout traceback<CPL> reads
+template <int CPL>
+__device__ __forceinline__ uint32_t pair_dir_word(const pair_word_t<CPL> &w, int h)
+{
+    if constexpr (CPL <= 7) {
+        return (w >> (16 * h)) & 0xffffu;
+    } else {
+        const uint32_t w0 = (w.x >> (16 * h)) & 0xffffu, w1 = (w.y >> (16 * h)) & 0xffffu;
+        return (w0 & 0x3fffu) | (w1 << 14) | ((w0 >> 14) << 30);  // digits 0..6, digits 7.., dV(boundary) at Dir<CPL>::kTop = 30
+    }
 }
 
 // the optimal path stays within B diagonals of the main one (see the header comment)
@@ -956,9 +992,9 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
 // K2b: TWO reads per warp in the 16-bit halves of every register (packed alphabet, CPL <= 7)
 // ------------------------------------------------------------------------------------------
 template <int CPL>
-__global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_constant__ AlignParams p)
+__global__ void __launch_bounds__(max_warps_pair(CPL) * 32, 1) k_align2(const __grid_constant__ AlignParams p)
 {
-    static_assert(CPL <= 7, "two 16-bit direction words per 32-bit store");
+    static_assert(CPL <= 15, "the second direction word holds at most 8 columns");
     using cnt_t = uint8_t;
     constexpr int ROWS = 25;  // (code of read A) * 5 + (code of read B)
 
@@ -976,7 +1012,7 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
     const WarpSmem ws = carve_warp(smem, p, warp);
     const uint32_t read_bytes = p.sm_stage_b + p.sm_stage_c;  // one read inside a stage slot
     const uint32_t slot_bytes = 2 * read_bytes;
-    uint32_t *s_dir = reinterpret_cast<uint32_t *>(ws.dir);
+    pair_word_t<CPL> *s_dir = reinterpret_cast<pair_word_t<CPL> *>(ws.dir);
     if (lane == 0) {
         mbar_init(&ws.bar[0], 1);
         mbar_init(&ws.bar[1], 1);
@@ -994,7 +1030,7 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
     auto read_at = [&](uint32_t u) -> uint32_t { return p.list ? p.list[u] : u; };
     const uint32_t npairs = total / 2 + (total & 1u);
     const uint32_t gw = blockIdx.x * nwarps + warp, nw = gridDim.x * nwarps;
-    uint32_t *scratch = reinterpret_cast<uint32_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
+    pair_word_t<CPL> *scratch = reinterpret_cast<pair_word_t<CPL> *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
     unsigned long long ctr = 0;
 
     auto issue = [&](uint32_t q, int slot) {
@@ -1085,7 +1121,6 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
             for (int i = lane; i < ops_words; i += 32) ws.ops2[i] = 0u;
             __syncwarp();
             int ngaps = 0, pos = n;  // alignment = ops2[pos, m + n)
-            const int sh = 16 * h;
             const int score = h ? score1 : score0;
             if (score == m && n == m) {
                 // every base matches: the only optimal path is the main diagonal (m zero ops, already zeroed)
@@ -1093,14 +1128,14 @@ __global__ void __launch_bounds__(kMaxWarpsPair * 32, 1) k_align2(const __grid_c
                 pos = traceback<CPL>(
                     [&](int tt, int ln) {
                         TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
-                        return (s_dir[(tt - (ln - C) * P) * 32 + ln] >> sh) & 0xffffu;
+                        return pair_dir_word<CPL>(s_dir[(tt - (ln - C) * P) * 32 + ln], h);
                     },
                     ws.ops2, m, n, lane, ngaps);
             else
                 pos = traceback<CPL>(
                     [&](int tt, int ln) {
                         TB_CHECK(p, (unsigned)(tt * 32 + ln) < p.scratch_stride, 1);
-                        return (scratch[tt * 32 + ln] >> sh) & 0xffffu;
+                        return pair_dir_word<CPL>(scratch[tt * 32 + ln], h);
                     },
                     ws.ops2, m, n, lane, ngaps);
             const uint32_t r = h ? r1 : r0;
@@ -1229,17 +1264,17 @@ int plan_align(AlignParams &p, bool wide)
     const int m = p.t.m, K = p.t.K;
     const int cpl = pick_cpl(m);
     if (cpl < 0 || m < 1) return -1;
-    const bool pair = !wide && cpl <= 7 && !p.force_single;
+    const bool pair = !wide && !p.force_single;
     p.pair = pair ? 1 : 0;
     p.cpl = (uint32_t)cpl;
     const uint32_t ncap = p.ncap;
     const uint32_t csz = wide ? 4u : 1u;
-    const uint32_t dsz = pair ? 4u : (cpl <= 7 ? 2u : 4u);
+    const uint32_t dsz = pair ? (cpl <= 7 ? 4u : 8u) : (cpl <= 7 ? 2u : 4u);
     const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
     p.sm_prof_bytes = wide ? 0u : prof_bytes(cpl, pair ? 25 : 5);
     p.sm_tmpl_bytes = align16(32 * cpl) + align16((uint32_t)(K * p.t.len_pad) * csz) +
                       align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) + p.sm_prof_bytes;
-    p.sm_tmpl_bytes += 16u * 32u * 4u;  // + dump rows
+    p.sm_tmpl_bytes += 16u * 32u * 8u;  // + dump rows (up to 16 steps of 8-byte words)
     p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
     p.sm_stage_b = wide ? align16(ncap) : align16((ncap + 3) / 4);
     if (p.sm_stage_b == 0) p.sm_stage_b = 16;
@@ -1267,7 +1302,7 @@ int plan_align(AlignParams &p, bool wide)
 int align_warps(const AlignParams &p, int max_smem)
 {
     long warps = ((long)max_smem - (long)p.sm_tmpl_bytes) / (long)p.sm_warp_bytes;
-    const long cap = p.pair ? kMaxWarpsPair : max_warps_one(pick_cpl(p.t.m));
+    const long cap = p.pair ? max_warps_pair(pick_cpl(p.t.m)) : max_warps_one(pick_cpl(p.t.m));
     if (warps > cap) warps = cap;
     return warps < 1 ? 0 : (int)warps;
 }
@@ -1275,7 +1310,7 @@ int align_warps(const AlignParams &p, int max_smem)
 // bytes of global scratch the launch needs (num_sms CTAs x warps x scratch_stride words)
 uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem)
 {
-    const uint32_t dsz = p.pair ? 4u : (pick_cpl(p.t.m) <= 7 ? 2u : 4u);
+    const uint32_t dsz = p.pair ? (pick_cpl(p.t.m) <= 7 ? 4u : 8u) : (pick_cpl(p.t.m) <= 7 ? 2u : 4u);
     return (uint64_t)num_sms * (uint64_t)align_warps(p, max_smem) * (uint64_t)p.scratch_stride * dsz;
 }
 
@@ -1296,9 +1331,7 @@ static int launch_k(Kern kern, const AlignParams &p, uint64_t units, int num_sms
 template <int CPL>
 static int launch_cpl(const AlignParams &p, bool wide, int num_sms, int max_smem, void *stream)
 {
-    if constexpr (CPL <= 7) {
-        if (p.pair) return launch_k(k_align2<CPL>, p, (p.N + 1) / 2, num_sms, max_smem, stream);
-    }
+    if (p.pair) return launch_k(k_align2<CPL>, p, (p.N + 1) / 2, num_sms, max_smem, stream);
     return wide ? launch_k(k_align<CPL, true>, p, p.N, num_sms, max_smem, stream)
                 : launch_k(k_align<CPL, false>, p, p.N, num_sms, max_smem, stream);
 }
@@ -1354,7 +1387,7 @@ static int set_attr(int max_smem)
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_align<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return (int)e;
-    if constexpr (CPL <= 7) e = cudaFuncSetAttribute(k_align2<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    e = cudaFuncSetAttribute(k_align2<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     return (int)e;
 }
 

@@ -515,6 +515,11 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
         if (ops_stride % 16 || ops_stride < a16(((uint32_t)ctx->td.m + ncap + 3) / 4))
             return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small or not a multiple of 16");
     }
+    // The reads k_same_bases leaves for the DP are the hard ones (truncated reads fill into the global scratch).  With more
+    // than 7 columns per lane the two-reads-per-warp kernel's scratch (8 bytes per lane and step) no longer fits L2 for
+    // them, so listed reads of long templates take the one-read kernel; the paired one serves whole batches.
+    const bool use_list = list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ);
+    if (use_list && ctx->td.m > 7 * 32) ap.force_single = 1u;
     if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
     {
         // global scratch for reads whose path may leave the band (one region per resident warp)
@@ -527,7 +532,7 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     }
     // reads marked by k_pack as equal to the template are finished without a DP; the align kernel gets the rest.
     // *d_list_count must be zero on entry (the callers clear the slot's scalars before the pack).
-    if (list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ)) {
+    if (use_list) {
         CK(ctx, list->reserve(src->N * 4));
         ap.list = (uint32_t *)list->p;
         ap.list_count = d_list_count;
