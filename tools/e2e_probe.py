@@ -109,6 +109,23 @@ def main():
                     tout[c0 * 48:c1 * 48].copy_(d_out[c0 * 48:c1 * 48], non_blocking=True)
             for st in streams:
                 st.synchronize()
+        # the same bytes with one stream per direction (D2H of a chunk waits for its H2D through an event)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def by_direction():
+            for ci, c0 in enumerate(range(0, N, CH)):
+                c1 = min(N, c0 + CH)
+                with torch.cuda.stream(s_in):
+                    d_in[offs[c0]:offs[c1]].copy_(tin[offs[c0]:offs[c1]], non_blocking=True)
+                    d_off[c0:c1 + 1].copy_(t_off[c0:c1 + 1], non_blocking=True)
+                    d_rc[c0:c1].copy_(t_rc[c0:c1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s_in)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev)
+                    tout[c0 * 48:c1 * 48].copy_(d_out[c0 * 48:c1 * 48], non_blocking=True)
+            s_in.synchronize(); s_out.synchronize()
+        print("chunked copies, one stream per direction: %.2f ms" % timeit(by_direction), flush=True)
         print("chunked copies only (305 MB in, 48 MB out): %.2f ms free-running, %.2f ms with a sync at slot reuse" % (
             timeit(lambda: chunked(False)), timeit(lambda: chunked(True))), flush=True)
     # zero-copy experiment: k_pack16 reads the raw reads straight from pinned host memory (UVA pointer), no H2D of them
