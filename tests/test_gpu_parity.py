@@ -221,6 +221,38 @@ def test_other_template_sizes(eng, tmp_path):
         _batch_vs_oracle(eng, synth.long_template(m, 2, seed=99 + m), tmp_path, 300, 1000 + m, p_trunc=0.3)
 
 
+def test_templates_longer_than_one_pass(eng, tmp_path):
+    """Templates of 481 .. 1023 bases run in column strips of 480 (k_align_strips): strip boundaries (481, 960, 961),
+    the largest template (Len = 1024 sites), truncated reads, offset + exclude-snps, and the same on the wide path
+    (a template base outside the packed alphabet)."""
+    for m, n_alt, N in ((481, 2, 300), (600, 8, 1500), (960, 2, 300), (961, 3, 300), (1023, 4, 600)):
+        _batch_vs_oracle(eng, synth.long_template(m, n_alt, seed=7 + m), tmp_path, N, 5000 + m, p_trunc=0.3)
+    _batch_vs_oracle(eng, synth.long_template(700, 4, seed=11), tmp_path, 500, 6001, p_trunc=0.2, offset=7, exclude=True)
+    # wide path: one template base becomes N (every read then differs from it in that base)
+    t = synth.long_template(700, 2, seed=12)
+    wb = bytearray(t.bases)
+    wb[wb.index(b"G", 500)] = ord("N")
+    tw = synth.TemplateArrays(bytes(wb), t.edit_site, t.alt_start, t.alt_end, "T")
+    wide_path = tw.write_fasta(str(tmp_path / "long_wide_n.fa"))
+    recs = list(zip(["fe", "pe"], tw.raw_sequences()))
+    tm = T.NewTemplateFromFasta(wide_path, T.FORWARD, "T")
+    om = O.NewTemplateFromFasta(wide_path, O.FORWARD, "T")
+    assert "N" in tm.Bases and len(tm.Bases) == 700
+    eng.SetTemplate(tm)
+    seqs, off, rc = synth.reads(t, 400, seed=6002, p_trunc=0.2)
+    grec, gops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+    orec, oops, _ = O.align_batch(om, seqs, off, rc, nthreads=8, ops_stride=gops.shape[1])
+    assert compare_records(grec, orec) == []
+    assert np.array_equal(gops, oops)
+    # single reads through the reference-shaped API, text and all
+    fe = T.NewFragment("fe", recs[0][1])
+    for name, sq in (("same-3", recs[0][1]), ("pe-1", recs[1][1]), ("cut-2", recs[0][1][40:-300]), ("none-1", "TTTT")):
+        a = eng.NewAlignment(T.NewFragment(name, sq), tm, False)
+        oa = O.NewAlignment(O.NewFragment(name, sq), om)
+        assert a.fields() == oa.fields() and a.WriteTo(T.NewFragment(name, sq), tm, 80) == oa.WriteTo(O.NewFragment(name, sq), om, 80)
+    assert fe.Len() > 700
+
+
 def test_wide_paths(eng, tmp_path):
     """Template with a non-ACG base, and a read with an edit-base run >= 255: both must take the
     wide kernels and stay exact."""
@@ -279,9 +311,9 @@ def test_edge_cases(eng, tmp_path):
     assert len(rec) == 0
     with pytest.raises(T.TreatError):
         T.Aligner(0).align_batch(np.zeros(4, np.uint8), np.array([0, 4], np.uint64))  # no template
-    big = T.NewFragment("fe", "AC" * 300)
+    big = T.NewFragment("fe", "AC" * 512)
     with pytest.raises(T.TreatError):
-        eng.SetTemplate(T.NewTemplate(big, big, None, None))  # 600 bases > 480
+        eng.SetTemplate(T.NewTemplate(big, big, None, None))  # 1024 bases > 1023 (Len <= 1024 sites)
     with pytest.raises(T.TreatError):
         tm = T.NewTemplate(T.NewFragment("fe", "ACG"), T.NewFragment("pe", "ACG"), None, None)
         eng.NewAlignment(T.NewFragment("long-1", "A" * 20000), tm, False)

@@ -989,6 +989,221 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
 }
 
 // ------------------------------------------------------------------------------------------
+// K2c: templates longer than one pass of the wavefront (32 lanes x 15 columns = 480 bases).  One read per warp; the
+// template is cut into column strips of 480 bases and the wavefront runs once per strip over all rows of the read.
+// The strip's right-edge column G[480 (s+1)][j] stays in a per-warp shared-memory array and is the left boundary of
+// strip s+1 (lane 0 reads edge[j] where the one-pass kernel has the constant 0; lane 31 writes its last cell back in
+// place, 31 steps behind the read).  Every direction word goes to the warp's global scratch, strip after strip, so
+// the traceback and everything behind it are the one-pass kernel's with a strip term in the word address.
+// ------------------------------------------------------------------------------------------
+constexpr int kStripCpl = 15, kStripCols = 32 * kStripCpl;
+
+template <bool WIDE>
+__device__ __forceinline__ void fill_strip(const uint32_t *prof, const uint8_t *rbl, const int (&tcr)[kStripCpl], int n, int steps,
+                                           int lane, int (&H)[kStripCpl], uint32_t *out, int *edge, bool first, bool has_next)
+{
+    constexpr int CPL = kStripCpl;
+    using DT = Dir<CPL>;
+    constexpr int ROWS = 5, P = CPL + 1;
+#pragma unroll
+    for (int k = 0; k < CPL; k++) H[k] = 0;  // G[i][0] = 0
+    int diag = 0;                            // G[i0-1][j-1]; column i0-1 of row 0 is 0 in every strip
+    uint32_t pwc[CPL];
+    int cnext = 0;
+    const typename Prof<CPL>::Lane pl(prof, ROWS, lane);
+    if (!WIDE) {
+        Prof<CPL>::template load<ROWS>(pl, rbl[0], pwc);
+        cnext = rbl[1];
+    }
+    const int nchunks = (steps + P - 1) / P;
+    const uint32_t rbl32 = smem_u32(rbl);
+    // lane 0's left boundary: 0 in the first strip, else the previous strip's right edge; rows behind the read keep
+    // the value of row n (a no-op row needs left <= G of its own first column, and the edge is being overwritten)
+    int e_cur = (first || n == 0) ? 0 : edge[1];
+    for (int u = 0; u < nchunks; u++) {
+        uint32_t *grow = out + u * (P * 32) + lane;
+        const uint32_t rbu32 = rbl32 + (uint32_t)(u * P);
+#pragma unroll
+        for (int v = 0; v < P; v++) {
+            const int t = u * P + v;
+            uint32_t pwn[CPL];
+            int wv[CPL];
+            if (!WIDE) {
+                Prof<CPL>::template load<ROWS>(pl, cnext, pwn);
+                cnext = (int)lds_u8(rbu32 + v + 2);
+#pragma unroll
+                for (int k = 0; k < CPL; k++) wv[k] = (int)pwc[k];
+            } else {
+                const int idx = t - lane;
+                const bool live = idx >= 0 && idx < n;
+                const int rc = live ? (int)lds_u8(rbu32 + v) : 0x200;
+#pragma unroll
+                for (int k = 0; k < CPL; k++) wv[k] = live ? (rc == tcr[k] ? 3 : 1) : 0;
+            }
+            int e_nxt = e_cur;
+            if (!first && lane == 0 && t + 2 <= n) e_nxt = edge[t + 2];  // row t + 2 of the next step, one step ahead
+            const int recv = __shfl_up_sync(FULL_MASK, H[CPL - 1], 1);
+            const int left = lane == 0 ? e_cur : recv;  // G[i0-1][j]
+            uint32_t acc = ((uint32_t)(left - diag) << DT::kTop) - (uint32_t)left;
+            int dg = diag, lf = left;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                const int e = max(dg + wv[k], H[k]);
+                const int f = max(e, lf);
+                dg = H[k];
+                lf = f;
+                H[k] = f;
+                acc += (uint32_t)f * (k == CPL - 1 ? (1u << (2 * (CPL - 1))) : 0u - (3u << (2 * k)));
+            }
+            diag = left;
+            grow[v * 32] = acc;
+            // right edge of a full strip: lane 31 finished row t - 30 in this step
+            if (has_next && lane == 31 && t >= 31 && t - 30 <= n) edge[t - 30] = H[CPL - 1];
+            e_cur = e_nxt;
+            if (!WIDE) {
+#pragma unroll
+                for (int k = 0; k < CPL; k++) pwc[k] = pwn[k];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(max_warps_one(kStripCpl) * 32, 1) k_align_strips(const __grid_constant__ AlignParams p)
+{
+    constexpr int CPL = kStripCpl, ROWS = 5;
+    using cnt_t = typename std::conditional<WIDE, uint32_t, uint8_t>::type;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int m = p.t.m, strips = (int)p.strips;
+
+    const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, CPL * strips);
+    load_template(cs, p, CPL * strips);
+    constexpr uint32_t kProfWords = Prof<CPL>::bytes(ROWS) / 4;
+    if (!WIDE) {
+        for (int i = threadIdx.x; i < ROWS * 32 * CPL * strips; i += blockDim.x) {
+            const int k = i % CPL, ln = (i / CPL) & 31, c = (i / (CPL * 32)) % ROWS, s = i / (CPL * 32 * ROWS);
+            cs.prof[s * kProfWords + Prof<CPL>::index(ROWS, c, ln, k)] = score_w(p, c, s * kStripCols + ln * CPL + k);
+        }
+    }
+    const WarpSmem ws = carve_warp(smem, p, warp);
+    int *edge = reinterpret_cast<int *>(ws.bar + 2);  // [ncap + 2] right edge of the strip filled last
+    const uint32_t stage_bytes = p.sm_stage_b + p.sm_stage_c;
+    if (lane == 0) {
+        mbar_init(&ws.bar[0], 1);
+        mbar_init(&ws.bar[1], 1);
+        fence_mbar_init();
+    }
+    ws.rb[lane] = kPadCode;
+    __syncthreads();
+
+    const int ops_words = (int)(p.sm_ops / 4);
+    const uint32_t gw = blockIdx.x * nwarps + warp, nw = gridDim.x * nwarps;
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(p.scratch) + gw * (uint64_t)p.scratch_stride;
+    const int strip_rows = (int)(p.scratch_stride / (32u * p.strips));  // scratch rows of one strip
+    unsigned long long ctr = 0;
+
+    auto issue = [&](uint32_t r, int slot) {
+        if (lane == 0) {
+            const uint32_t n = p.n[r];
+            const uint32_t cb = WIDE ? align16(n) : align16((n + 3) / 4);
+            const uint32_t cc = WIDE ? align16(4 * (n + 1)) : align16(n + 1);
+            uint8_t *dst = ws.stage + slot * stage_bytes;
+            fence_proxy_async();
+            mbar_expect_tx(&ws.bar[slot], cb + cc);
+            if (cb) bulk_g2s(dst, p.bases + r * (uint64_t)p.bases_stride, cb, &ws.bar[slot]);
+            bulk_g2s(dst + p.sm_stage_b, p.counts + r * (uint64_t)p.counts_stride, cc, &ws.bar[slot]);
+        }
+    };
+
+    const uint32_t total = (uint32_t)p.N;
+    uint32_t it = 0;
+    if (gw < total) issue(gw, 0);
+    for (uint32_t r = gw; r < total; r += nw, it++) {
+        const int slot = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        const int n = (int)p.n[r];
+        const uint32_t rflags = p.rflags[r];
+        __syncwarp();
+        if (nw < total - r) issue(r + nw, slot ^ 1);
+        mbar_wait(&ws.bar[slot], parity);
+        if (n > (int)p.ncap) {  // speculative launch (ncap guessed): the host re-runs the chunk
+            if (lane == 0 && p.skipped) atomicAdd(p.skipped, 1u);
+            continue;
+        }
+        const uint8_t *st_b = ws.stage + slot * stage_bytes;
+        const cnt_t *rcount = reinterpret_cast<const cnt_t *>(st_b + p.sm_stage_b);
+
+        uint8_t *rb = ws.rb + 32;
+        if (!WIDE) {
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(st_b);
+            for (int wi = lane; wi * 16 < n; wi += 32) {
+                const uint32_t w = pw[wi];
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t x = (w >> (8 * q)) & 0xffu;
+                    o[q] = (x & 3u) | ((x & 0xcu) << 6) | ((x & 0x30u) << 12) | ((x & 0xc0u) << 18);
+                }
+                *reinterpret_cast<uint4 *>(rb + wi * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+            rb[n + lane] = kPadCode;
+            rb[n + 32 + lane] = kPadCode;
+            if (lane < 16) rb[n + 64 + lane] = kPadCode;
+        } else {
+            for (int i = lane; i < n; i += 32) rb[i] = st_b[i];
+        }
+        for (int i = lane; i < ops_words; i += 32) ws.ops2[i] = 0u;
+        __syncwarp();
+
+        // ---- fill, strip after strip ------------------------------------------------------------
+        int H[CPL];
+        const uint8_t *rbl = rb - lane;
+        for (int s = 0; s < strips; s++) {
+            const int cols = min(kStripCols, m - s * kStripCols);
+            const int lanes_used = (cols + CPL - 1) / CPL;
+            const int steps = n > 0 ? n + lanes_used - 1 : 0;
+            int tcr[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                const int idx = s * kStripCols + lane * CPL + k;
+                tcr[k] = idx < m ? (int)cs.tb[idx] : 0x100;
+            }
+            TB_CHECK(p, ((steps + CPL) / (CPL + 1)) * (CPL + 1) <= strip_rows, 7);
+            fill_strip<WIDE>(cs.prof + s * kProfWords, rbl, tcr, n, steps, lane, H, scratch + (size_t)s * strip_rows * 32, edge,
+                             s == 0, s + 1 < strips);
+        }
+        // F[m][n] = G[m][n] - m - n; G[m][n] lives in the last strip
+        int score;
+        {
+            const int ml = m - 1 - (strips - 1) * kStripCols;
+            int fin = 0;
+            const int kl = ml % CPL;
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (k == kl) fin = H[k];
+            score = __shfl_sync(FULL_MASK, fin, ml / CPL) - m - n;
+        }
+        int ngaps = 0, pos = n;
+        if (!(score == m && n == m)) {
+            pos = traceback<CPL>(
+                [&](int tt, int ln) {  // ln counts lanes across strips; the word of (strip, lane, step tt - 32 strip)
+                    const int s = ln >> 5, l = ln & 31;
+                    const int row = s * strip_rows + (tt - ln + l);
+                    TB_CHECK(p, (unsigned)(row * 32 + l) < p.scratch_stride, 1);
+                    return scratch[row * 32 + l];
+                },
+                ws.ops2, m, n, lane, ngaps);
+        }
+        finish_read<cnt_t>(p, cs, ws, lane, r, n, rflags, score, pos, ngaps, rcount, [&](int fi) { return (int)rb[fi]; }, ctr);
+    }
+    flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
+}
+
+// ------------------------------------------------------------------------------------------
 // K2b: TWO reads per warp in the 16-bit halves of every register (packed alphabet, CPL <= 7)
 // ------------------------------------------------------------------------------------------
 template <int CPL>
@@ -1262,17 +1477,21 @@ static uint32_t prof_bytes(int cpl, int rows)
 int plan_align(AlignParams &p, bool wide)
 {
     const int m = p.t.m, K = p.t.K;
-    const int cpl = pick_cpl(m);
-    if (cpl < 0 || m < 1) return -1;
-    const bool pair = !wide && !p.force_single;
+    if (m < 1 || m > kMaxTemplateBases) return -1;
+    // longer than one pass of the wavefront: column strips of 480 bases, one read per warp (k_align_strips)
+    const int strips = m > kStripCols ? (m + kStripCols - 1) / kStripCols : 1;
+    const int cpl = strips > 1 ? kStripCpl : pick_cpl(m);
+    if (cpl < 0) return -1;
+    p.strips = (uint32_t)strips;
+    const bool pair = !wide && !p.force_single && strips == 1;
     p.pair = pair ? 1 : 0;
     p.cpl = (uint32_t)cpl;
     const uint32_t ncap = p.ncap;
     const uint32_t csz = wide ? 4u : 1u;
     const uint32_t dsz = pair ? (cpl <= 7 ? 4u : 8u) : (cpl <= 7 ? 2u : 4u);
     const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
-    p.sm_prof_bytes = wide ? 0u : prof_bytes(cpl, pair ? 25 : 5);
-    p.sm_tmpl_bytes = align16(32 * cpl) + align16((uint32_t)(K * p.t.len_pad) * csz) +
+    p.sm_prof_bytes = wide ? 0u : prof_bytes(cpl, pair ? 25 : 5) * (uint32_t)strips;
+    p.sm_tmpl_bytes = align16(32 * cpl * strips) + align16((uint32_t)(K * p.t.len_pad) * csz) +
                       align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) + align16(8u * sum_len) + p.sm_prof_bytes;
     p.sm_tmpl_bytes += 16u * 32u * 8u;  // + dump rows (up to 16 steps of 8-byte words)
     p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
@@ -1289,11 +1508,12 @@ int plan_align(AlignParams &p, bool wide)
     while (C > 0 && (2 * C + 1) * P > full_rows) C--;
     p.band_chunks = C;
     p.band_rows = (2 * C + 1) * P;
-    p.sm_dir = align16(p.band_rows * 32 * dsz);
-    p.scratch_stride = full_rows * 32;  // direction words of one warp's full fill
+    p.sm_dir = strips > 1 ? 0u : align16(p.band_rows * 32 * dsz);  // strips: every word goes to the scratch
+    p.scratch_stride = full_rows * 32 * (uint32_t)strips;  // direction words of one warp's full fill
     p.sm_ops = align16((((uint32_t)m + ncap + 15) / 16 + 2) * 4);
     p.sm_t2f = align16(2u * (uint32_t)p.t.len_pad);
     p.sm_warp_bytes = p.sm_stage_total + p.sm_rb + p.sm_dir + p.sm_ops + p.sm_t2f + 16;
+    if (strips > 1) p.sm_warp_bytes += align16(4u * (ncap + 2));  // right-edge column handed from strip to strip
     p.sm_warp_bytes = (p.sm_warp_bytes + 127u) & ~127u;
     return cpl;
 }
@@ -1302,7 +1522,7 @@ int plan_align(AlignParams &p, bool wide)
 int align_warps(const AlignParams &p, int max_smem)
 {
     long warps = ((long)max_smem - (long)p.sm_tmpl_bytes) / (long)p.sm_warp_bytes;
-    const long cap = p.pair ? max_warps_pair(pick_cpl(p.t.m)) : max_warps_one(pick_cpl(p.t.m));
+    const long cap = p.pair ? max_warps_pair((int)p.cpl) : max_warps_one((int)p.cpl);
     if (warps > cap) warps = cap;
     return warps < 1 ? 0 : (int)warps;
 }
@@ -1310,7 +1530,7 @@ int align_warps(const AlignParams &p, int max_smem)
 // bytes of global scratch the launch needs (num_sms CTAs x warps x scratch_stride words)
 uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem)
 {
-    const uint32_t dsz = p.pair ? (pick_cpl(p.t.m) <= 7 ? 4u : 8u) : (pick_cpl(p.t.m) <= 7 ? 2u : 4u);
+    const uint32_t dsz = p.pair ? (p.cpl <= 7 ? 4u : 8u) : (p.cpl <= 7 ? 2u : 4u);
     return (uint64_t)num_sms * (uint64_t)align_warps(p, max_smem) * (uint64_t)p.scratch_stride * dsz;
 }
 
@@ -1338,6 +1558,9 @@ static int launch_cpl(const AlignParams &p, bool wide, int num_sms, int max_smem
 
 int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream)
 {
+    if (p.strips > 1)
+        return wide ? launch_k(k_align_strips<true>, p, p.N, num_sms, max_smem_optin, stream)
+                    : launch_k(k_align_strips<false>, p, p.N, num_sms, max_smem_optin, stream);
     switch (pick_cpl(p.t.m)) {
     case 1: return launch_cpl<1>(p, wide, num_sms, max_smem_optin, stream);
     case 2: return launch_cpl<2>(p, wide, num_sms, max_smem_optin, stream);
@@ -1457,6 +1680,8 @@ int configure_align_kernels(int max_smem_optin)
     if ((e = set_attr<10>(max_smem_optin))) return e;
     if ((e = set_attr<12>(max_smem_optin))) return e;
     if ((e = set_attr<15>(max_smem_optin))) return e;
+    if ((e = (int)cudaFuncSetAttribute(k_align_strips<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin))) return e;
+    if ((e = (int)cudaFuncSetAttribute(k_align_strips<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin))) return e;
     return 0;
 }
 

@@ -250,7 +250,7 @@ int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m
     if (!ctx || !bases || !edit_site || m < 1 || K < 2 || n_alt != K - 2 || (n_alt > 0 && (!alt_start || !alt_end)))
         return fail(ctx, TREAT_B200_ERR_INVALID, "set_template: bad arguments (need m >= 1, K >= 2, n_alt == K-2)");
     if (m > kMaxTemplateBases || K > kMaxTemplates)
-        return fail(ctx, TREAT_B200_ERR_TOO_LONG, "set_template: template longer than 480 bases or more than 32 rows");
+        return fail(ctx, TREAT_B200_ERR_TOO_LONG, "set_template: template longer than 1023 bases or more than 32 rows");
     CK(ctx, cudaSetDevice(ctx->device));
     if (edit_base >= 'a' && edit_base <= 'z') edit_base -= 32;
     const int len = m + 1, len_pad = (len + 31) / 32 * 32;
@@ -442,7 +442,7 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     pp.lut = ctx->td.lut;
     pp.edit_base = ctx->td.edit_base;
     pp.scalars = d_scalars;
-    pp.tpk = (!dst->wide && !ctx->tmpl_wide) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
+    pp.tpk = (!dst->wide && !ctx->tmpl_wide && ctx->td.m <= kOnePassTemplateBases) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
     pp.tm = (uint32_t)ctx->td.m;
     pp.padded = padded && ((uintptr_t)d_seqs & 15u) == 0 ? 1u : 0u;
     if (span && !dst->wide) {  // k_pack16 only
@@ -518,7 +518,8 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     // The reads k_same_bases leaves for the DP are the hard ones (truncated reads fill into the global scratch).  With more
     // than 7 columns per lane the two-reads-per-warp kernel's scratch (8 bytes per lane and step) no longer fits L2 for
     // them, so listed reads of long templates take the one-read kernel; the paired one serves whole batches.
-    const bool use_list = list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ);
+    const bool use_list = list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ) &&
+                          ctx->td.m <= kOnePassTemplateBases;  // k_same_bases holds 512 sites; longer templates: DP for every read
     if (use_list && ctx->td.m > 7 * 32) ap.force_single = 1u;
     if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
     {

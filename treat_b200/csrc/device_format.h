@@ -6,8 +6,10 @@
 
 namespace treat_b200 {
 
-// Largest template the one-pass wavefront handles: 32 lanes x 15 columns per lane.
-constexpr int kMaxTemplateBases = 480;
+// One pass of the wavefront handles 32 lanes x 15 columns per lane = 480 template bases; longer templates run in
+// column strips (k_align_strips).  The site rows of the editing-site assembly hold 32 x 32 sites: m + 1 <= 1024.
+constexpr int kOnePassTemplateBases = 480;
+constexpr int kMaxTemplateBases = 1023;
 // Raw reads longer than this are refused (ERR_TOO_LONG); keeps n in uint16 and bounds shared memory.
 constexpr uint32_t kMaxReadLen = 16384;
 constexpr int kMaxTemplates = 32;  // K = FE + PE + alternatives
@@ -102,6 +104,7 @@ struct AlignParams {
     uint32_t *ops_idx;
     uint32_t *ops_count;
     uint32_t cpl;                // template columns per lane (sizes the template section)
+    uint32_t strips;             // column strips of 32 x cpl bases (1 unless the template is longer than 480 bases)
     uint32_t sm_cnt_stage;       // k_same_bases: bytes per warp for the staged edit-site counts
 };
 

@@ -51,25 +51,25 @@ int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream)
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: pack (NewFragment, fragment.go:91-121), one warp per read
+// K1, wide path (NewFragment, fragment.go:91-121): bases stay bytes, counts are uint32 -- for templates with a base
+// outside the packed alphabet or a count >= 255, and for chunks with an edit-base run >= 255.  One warp per read,
+// one character per lane: ballot the non-edit bases, compact them, run lengths from the gaps.
 // ------------------------------------------------------------------------------------------
 constexpr int kPackWarpsMax = 8;
 
-template <bool WIDE>
-__global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_constant__ PackParams p)
+__global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack_wide(const __grid_constant__ PackParams p)
 {
-    using cnt_t = typename std::conditional<WIDE, uint32_t, uint8_t>::type;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *s_lut = smem;  // 256: byte -> 2-bit code (0x80 = edit base) or, on the wide path, the upper-cased byte
-    uint8_t *s_other = smem + 256;  // 256, wide path: 1 = a base outside the packed alphabet (status bit ST_WIDE_BASE, as k_pack16 sets it)
+    uint8_t *s_up = smem;           // 256: byte -> upper-cased byte (strings.ToUpper, ASCII)
+    uint8_t *s_other = smem + 256;  // 256: 1 = a base outside the packed alphabet (status bit ST_WIDE_BASE, as k_pack16 sets it)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cap = p.stage_cap;  // multiple of 16
-    uint8_t *s_code = smem + 512 + (size_t)warp * (cap + cap * sizeof(cnt_t));
-    cnt_t *s_cnt = reinterpret_cast<cnt_t *>(s_code + cap);
+    uint8_t *s_code = smem + 512 + (size_t)warp * (5 * cap);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_code + cap);
     const uint8_t eb = p.edit_base;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const uint8_t up = (i >= 'a' && i <= 'z') ? (uint8_t)(i - 32) : (uint8_t)i;  // strings.ToUpper, ASCII
-        s_lut[i] = WIDE ? up : (up == eb ? (uint8_t)0x80 : p.lut[up]);
+        const uint8_t up = (i >= 'a' && i <= 'z') ? (uint8_t)(i - 32) : (uint8_t)i;
+        s_up[i] = up;
         s_other[i] = (up != eb && p.lut[up] == 3) ? 1 : 0;
     }
     __syncthreads();
@@ -85,24 +85,18 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
         uint32_t nb = 0;
         int lastpos = -1;
         bool sat = false, widec = false;
-        // one 32-character chunk: ballot the non-edit bases, compact them, run lengths from the gaps
         auto chunk = [&](uint32_t c0, uint32_t v, bool inside) {
-            const bool isb = inside && (WIDE ? v != eb : !(v & 0x80u));
+            const bool isb = inside && v != eb;
             const uint32_t mask = __ballot_sync(FULL_MASK, isb);
             if (isb) {
                 const uint32_t below = mask & lt;
                 const uint32_t idx = nb + __popc(below);
                 const int prev = below ? (int)(c0 + 31 - __clz(below)) : lastpos;
-                uint32_t cnt = (uint32_t)((int)(c0 + lane) - prev - 1);
-                if (cnt >= 255u) sat = true;  // informational on the wide path, which keeps exact counts
-                if (!WIDE) {
-                    widec |= (v == 3u);
-                    if (cnt >= 255u) cnt = 255u;
-                } else {
-                    widec |= s_other[v] != 0;
-                }
+                const uint32_t cnt = (uint32_t)((int)(c0 + lane) - prev - 1);
+                if (cnt >= 255u) sat = true;  // informational here: the counts stay exact
+                widec |= s_other[v] != 0;
                 s_code[idx] = (uint8_t)v;
-                s_cnt[idx] = (cnt_t)cnt;
+                s_cnt[idx] = cnt;
             }
             if (mask) lastpos = (int)(c0 + 31 - __clz(mask));
             nb += __popc(mask);
@@ -111,15 +105,14 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
             // both loads first: two global round trips overlap
             const uint32_t j0 = c0 + lane, j1 = j0 + 32;
             const uint8_t r0 = j0 < L ? seq[j0] : (uint8_t)0, r1 = j1 < L ? seq[j1] : (uint8_t)0;
-            const uint32_t v0 = s_lut[r0], v1 = s_lut[r1];
+            const uint32_t v0 = s_up[r0], v1 = s_up[r1];
             chunk(c0, v0, j0 < L);
             if (c0 + 32 < L) chunk(c0 + 32, v1, j1 < L);
         }
         if (lane == 0) {
-            uint32_t cnt = (uint32_t)((int)L - 1 - lastpos);
+            const uint32_t cnt = (uint32_t)((int)L - 1 - lastpos);
             if (cnt >= 255u) sat = true;
-            if (!WIDE && cnt >= 255u) cnt = 255u;
-            s_cnt[nb] = (cnt_t)cnt;
+            s_cnt[nb] = cnt;
         }
         __syncwarp();
         const uint32_t n = nb;
@@ -128,39 +121,20 @@ __global__ void __launch_bounds__(kPackWarpsMax * 32) k_pack(const __grid_consta
         s_cnt[n + 1 + lane] = 0;
         __syncwarp();
         const bool any_sat = __any_sync(FULL_MASK, sat), any_wide = __any_sync(FULL_MASK, widec);
-        // bases
         uint32_t *gb = reinterpret_cast<uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
-        bool same = false;  // stripped bases equal the template's: such a read needs no DP (see k_same_bases)
-        if (!WIDE) {
-            const uint32_t nwords = align16((n + 3) / 4) / 4;
-            const uint32_t twords = (p.tm + 15) / 16;
-            bool eq = p.tpk != nullptr && n == p.tm;
-            for (uint32_t wi = lane; wi < nwords; wi += 32) {
-                // 16 codes (one byte each) -> 16 x 2 bits: (x * M) >> 24 gathers the four 2-bit fields of a word
-                const uint4 x = *reinterpret_cast<const uint4 *>(s_code + 16 * wi);
-                constexpr uint32_t M = 0x01041040u;
-                const uint32_t lo = __byte_perm(x.x * M, x.y * M, 0x0073), hi = __byte_perm(x.z * M, x.w * M, 0x0073);
-                const uint32_t word = __byte_perm(lo, hi, 0x5410);
-                gb[wi] = word;
-                if (eq && wi < twords) eq = word == p.tpk[wi];  // codes past n are zero in both
-            }
-            same = __all_sync(FULL_MASK, eq);
-        } else {
+        {
             const uint32_t nwords = align16(n) / 4;
             const uint32_t *src = reinterpret_cast<const uint32_t *>(s_code);
             for (uint32_t wi = lane; wi < nwords; wi += 32) gb[wi] = src[wi];
         }
-        // counts (n + 1 entries)
-        uint32_t *gc = reinterpret_cast<uint32_t *>(p.counts + r * (uint64_t)p.counts_stride);
+        uint32_t *gc = reinterpret_cast<uint32_t *>(p.counts + r * (uint64_t)p.counts_stride);  // n + 1 counts
         {
-            const uint32_t nwords = WIDE ? align16(4 * (n + 1)) / 4 : align16(n + 1) / 4;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_cnt);
-            for (uint32_t wi = lane; wi < nwords; wi += 32) gc[wi] = src[wi];
+            const uint32_t nwords = align16(4 * (n + 1)) / 4;
+            for (uint32_t wi = lane; wi < nwords; wi += 32) gc[wi] = s_cnt[wi];
         }
         if (lane == 0) {
             p.n[r] = (uint16_t)n;
-            p.flags[r] = (uint8_t)((any_sat ? TREAT_B200_ST_SATURATED : 0) | (any_wide ? TREAT_B200_ST_WIDE_BASE : 0) |
-                                   (same ? kFlagSameBases : 0));
+            p.flags[r] = (uint8_t)((any_sat ? TREAT_B200_ST_SATURATED : 0) | (any_wide ? TREAT_B200_ST_WIDE_BASE : 0));
             p.raw_len[r] = L;
         }
         warp_max_n = max(warp_max_n, n);
@@ -416,23 +390,19 @@ int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin,
     int warps = (int)(((size_t)max_smem_optin - kPack16Hdr) / per_warp);
     if (warps < 1) return -1000;
     if (warps > kPackWarpsMax) warps = kPackWarpsMax;
-    const size_t smem = kPack16Hdr + per_warp * warps;  // k_pack only needs a 256-byte header
+    const size_t smem = kPack16Hdr + per_warp * warps;  // k_pack_wide only needs a 512-byte header
     uint64_t blocks = (p.N + warps - 1) / warps;
-    static const bool v1 = getenv("TREAT_B200_PACK_V1") != nullptr;  // A/B switch: the 1-character-per-lane kernel
     // persistent grid: as many CTAs as are resident at once
     int per_sm = 0;
-    cudaError_t oe = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack<true>, warps * 32, smem)
-                     : v1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack<false>, warps * 32, smem)
-          : p.begin ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack16<true>, warps * 32, smem)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack16<false>, warps * 32, smem);
+    cudaError_t oe = wide        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack_wide, warps * 32, smem)
+                     : p.begin   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack16<true>, warps * 32, smem)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack16<false>, warps * 32, smem);
     if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint64_t cap = (uint64_t)num_sms * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return 0;
     if (wide)
-        k_pack<true><<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
-    else if (v1)
-        k_pack<false><<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+        k_pack_wide<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
     else if (p.begin)
         k_pack16<true><<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
     else
@@ -443,9 +413,7 @@ int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin,
 
 int configure_pack_kernels(int max_smem_optin)
 {
-    cudaError_t ce = cudaFuncSetAttribute(k_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (ce != cudaSuccess) return (int)ce;
-    ce = cudaFuncSetAttribute(k_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    cudaError_t ce = cudaFuncSetAttribute(k_pack_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (ce != cudaSuccess) return (int)ce;
     ce = cudaFuncSetAttribute(k_pack16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (ce != cudaSuccess) return (int)ce;
