@@ -290,6 +290,25 @@ typedef int (*treat_b200_fasta_sink)(void *user, const treat_b200_fasta_piece *p
 int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, uint32_t ops_stride,
                             treat_b200_fasta_sink sink, void *user, uint64_t *n_records);
 
+/* Alignment.WriteTo (align.go:388-520) for a batch, on the device: the text block `treat align` prints per read (header
+ * with name / JSS / ESS / JES / Junc Len / Alt, then the gapped FE, PE, A*, RD rows wrapped at tw - 4 columns; tw <= 0
+ * means 80), built from the raw reads, the records and the ops rows of an align call made with TREAT_B200_WANT_OPS
+ * (one row per read: not OPS_GAPPED_ONLY).  All pointers are device pointers; names are concatenated like the reads
+ * (name r = d_names[d_name_off[r], d_name_off[r+1])).  The call computes d_text_off[N + 1] (text of read r =
+ * d_text[d_text_off[r], d_text_off[r+1])), returns the total in *text_bytes after one stream synchronisation, and
+ * writes the text when d_text is not NULL and text_cap is large enough (d_text = NULL: sizing call). */
+int treat_b200_text_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off, const uint8_t *d_names,
+                           const uint64_t *d_name_off, const treat_b200_record *d_rec, const uint8_t *d_ops,
+                           uint32_t ops_stride, uint64_t N, uint32_t max_len, int32_t tw, uint64_t *d_text_off,
+                           uint8_t *d_text, uint64_t text_cap, uint64_t *text_bytes, void *stream);
+/* `treat align -t templates.fa -f reads.fa` (cmd/treat/align.go:96-121) in one streaming call: FASTA bytes in, the exact
+ * stdout text out.  The file is cut at record starts into pieces (~8 MB); every piece is indexed, aligned and formatted on
+ * the device and its text handed to `sink` in file order while the next piece is in flight (text is valid during the
+ * callback only; a non-zero return stops the run).  flags: TREAT_B200_EXCLUDE_SNPS, TREAT_B200_NO_SUMMARY, TREAT_B200_HEATMAP. */
+typedef int (*treat_b200_text_sink)(void *user, const uint8_t *text, uint64_t len, uint64_t first_record, uint64_t n_records);
+int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, int32_t tw,
+                          treat_b200_text_sink sink, void *user, uint64_t *n_records);
+
 /* align.go:388-520 Alignment.WriteTo from a device result: text for one read.  Returns the
  * number of bytes needed; writes at most cap bytes to out (call twice or size generously). */
 int64_t treat_b200_format_alignment(const treat_b200_template *t, const treat_b200_record *rec,

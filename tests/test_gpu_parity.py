@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 os.environ.setdefault("TREAT_B200_FASTA_PIECE", "300000")  # small pieces: treat_b200_fasta_stream cuts even the test files
+os.environ.setdefault("TREAT_B200_TEXT_PIECE", "200000")   # treat_b200_fasta_text: several pieces per test file
 os.environ.setdefault("TREAT_B200_FASTA_CHUNK", "30000")   # treat_b200_fasta_align: several chunks for the larger test files
 
 import treat_b200 as T
@@ -494,6 +495,96 @@ def test_fasta_ingest_on_device(eng, tmp_path):
     eng.reset_summary()
     eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
     assert np.array_equal(s1, eng.summary())
+
+
+def _text_vs_oracle(eng, tmpl_path, text: bytes, tmp_path, tag, base="T", offset=0):
+    """treat_b200_fasta_text (parse + alignment + WriteTo on the GPU) == the oracle's `treat align` stdout."""
+    tm = T.NewTemplateFromFasta(tmpl_path, T.FORWARD, base)
+    tm.SetOffset(offset)
+    eng.SetTemplate(tm)
+    fpath = str(tmp_path / ("text_%s.fa" % tag))
+    with open(fpath, "wb") as fh:
+        fh.write(text)
+    got, n = eng.fasta_text(text)
+    want = O.cli_align(template=tmpl_path, fragment=fpath, base=base, offset=offset).encode("latin-1")
+    if got != want:
+        i = next((k for k in range(min(len(got), len(want))) if got[k] != want[k]), min(len(got), len(want)))
+        raise AssertionError("%s: text differs at byte %d of %d/%d: %r vs %r" % (tag, i, len(got), len(want), got[max(0, i - 200):i + 80], want[max(0, i - 200):i + 80]))
+    return n
+
+
+def test_write_to_on_device(eng, examples, tmp_path):
+    """Alignment.WriteTo (align.go:388-520) for whole files on the device: k_text via treat_b200_fasta_text and
+    treat_b200_text_device, byte for byte against the oracle's `treat align` output and the host formatter."""
+    # the reference's own example files (C1 / C2 of SURVEY 8d), with and without an offset, lower-case edit base
+    for t, f, base, off in (("simple-templates.fa", "simple-sequences.fa", "T", 0), ("templates.fa", "clones.fa", "T", 0),
+                            ("templates.fa", "sample-1.fa", "T", 10), ("test-templates.fa", "test-sample.fa", "t", 0)):
+        with open(examples[f], "rb") as fh:
+            _text_vs_oracle(eng, examples[t], fh.read(), tmp_path, f.replace(".", "_"), base, off)
+    # synthetic RPS12 reads (indels, substitutions, N) in several pieces; CRLF, wrapped sequences, odd headers, empty read
+    t = synth.rps12_template()
+    tpath = t.write_fasta(str(tmp_path / "rps12_text.fa"))
+    seqs, off, rc = synth.reads(t, 2500, seed=4242, p_trunc=0.05)
+    reads = [seqs[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(2500)]
+    body = "".join(">r%d_%d\n%s\n" % (i, rc[i], r) for i, r in enumerate(reads))
+    assert _text_vs_oracle(eng, tpath, body.encode(), tmp_path, "rps12") == 2500
+    odd = ">  spaced name_7  \r\n%s\r\n>wrapped-3\n%s\n%s\n\n>empty-1\n\n>lower_2\n%s\n>tt-1\nTTTTT\n>last-9\n%s" % (
+        reads[0], reads[1][:100], reads[1][100:], reads[2].lower(), reads[3])
+    assert _text_vs_oracle(eng, tpath, odd.encode(), tmp_path, "odd") == 6
+    sat = ">sat-7\n%s\n>plain-1\n%s\n" % (reads[4][:80] + "T" * 300 + reads[4][80:], reads[5])
+    assert _text_vs_oracle(eng, tpath, sat.encode(), tmp_path, "saturated") == 2
+    # long template, K = 10 (labels A1..A8) and K = 14 (labels A10..A12 are three characters wide), truncated reads
+    for m, n_alt, N in ((300, 8, 600), (90, 12, 300), (700, 3, 200)):
+        tl = synth.long_template(m, n_alt, seed=31 + m)
+        lp = tl.write_fasta(str(tmp_path / ("long_text_%d.fa" % m)))
+        seqs, off, rc = synth.reads(tl, N, seed=99 + m, p_trunc=0.3)
+        body = "".join(">q%d-%d\n%s\n" % (i, rc[i], seqs[int(off[i]):int(off[i + 1])].tobytes().decode()) for i in range(N))
+        assert _text_vs_oracle(eng, lp, body.encode(), tmp_path, "long%d" % m) == N
+    # wide template (a base outside the packed alphabet)
+    wb = bytearray(t.bases)
+    wb[wb.index(b"G", 60)] = ord("N")
+    tw_ = synth.TemplateArrays(bytes(wb), t.edit_site, t.alt_start, t.alt_end, "T")
+    wpath = tw_.write_fasta(str(tmp_path / "wide_text.fa"))
+    body = "".join(">w%d-1\n%s\n" % (i, r) for i, r in enumerate(reads[:300]))
+    assert _text_vs_oracle(eng, wpath, body.encode(), tmp_path, "wide") == 300
+    # treat_b200_text_device on device buffers, other terminal widths, against Alignment.WriteTo of the host mirror
+    import torch
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 700
+    sub = seqs_rps = None
+    seqs, off, rc = synth.reads(t, N, seed=777, p_trunc=0.1)
+    names = [("read %d_%d" % (i, rc[i])).encode() for i in range(N)]
+    noff = np.zeros(N + 1, dtype=np.int64)
+    noff[1:] = np.cumsum([len(x) for x in names])
+    max_len = int(np.diff(off.astype(np.int64)).max())
+    stride = eng.ops_stride(max_len)
+    d_seqs = torch.from_numpy(seqs.copy()).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_names = torch.from_numpy(np.frombuffer(b"".join(names), dtype=np.uint8).copy()).cuda()
+    d_noff = torch.from_numpy(noff).cuda()
+    d_rec = torch.zeros(N * 48, dtype=torch.uint8, device="cuda")
+    d_ops = torch.zeros(N * stride, dtype=torch.uint8, device="cuda")
+    d_toff = torch.zeros(N + 1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), 0, N, max_len, cabi.WANT_OPS | cabi.NO_SUMMARY, d_rec.data_ptr(),
+                           d_ops.data_ptr(), stride, st)
+    alns = eng.NewAlignments([(nm.decode(), seqs[int(off[i]):int(off[i + 1])].tobytes().decode()) for i, nm in enumerate(names)], tm)
+    for tw in (80, 0, 20, 133, 5):
+        args = (d_seqs.data_ptr(), d_off.data_ptr(), d_names.data_ptr(), d_noff.data_ptr(), d_rec.data_ptr(), d_ops.data_ptr(), stride, N,
+                max_len, tw, d_toff.data_ptr())
+        total = eng.text_device(*args, 0, 0, st)
+        d_text = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        assert eng.text_device(*args, d_text.data_ptr(), total, st) == total
+        torch.cuda.synchronize()
+        text = d_text.cpu().numpy().tobytes()
+        toff = d_toff.cpu().numpy()
+        assert toff[0] == 0 and toff[-1] == total
+        for i in range(0, N, 7 if tw in (80, 0) else 37):
+            frag = T.NewFragment(names[i].decode(), seqs[int(off[i]):int(off[i + 1])].tobytes().decode())
+            assert text[int(toff[i]):int(toff[i + 1])].decode() == alns[i].WriteTo(frag, tm, tw), (tw, i)
+    with pytest.raises(T.TreatError):
+        eng.text_device(*args[:9], 4, d_toff.data_ptr(), 0, 0, st)  # tw = 4: the reference divides by zero
 
 
 def test_heatmap_consumer(eng, tmp_path):

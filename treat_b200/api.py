@@ -496,6 +496,37 @@ class Aligner:
         check(lib().treat_b200_fasta_stream(self._ctx, data.ctypes.data, data.size, flags, ops_stride, cb, None, C.byref(total)), self._ctx)
         return pieces, total.value
 
+    def text_device(self, d_seqs: int, d_seq_off: int, d_names: int, d_name_off: int, d_rec: int, d_ops: int, ops_stride: int,
+                    N: int, max_len: int, tw: int, d_text_off: int, d_text: int = 0, text_cap: int = 0, stream: int = 0) -> int:
+        """treat_b200_text_device on raw device pointers: Alignment.WriteTo for a batch; returns the text size in bytes
+        (d_text = 0: sizing call)."""
+        total = C.c_uint64()
+        check(lib().treat_b200_text_device(self._ctx, d_seqs, d_seq_off, d_names, d_name_off, d_rec, d_ops, ops_stride, N, max_len, tw,
+                                           d_text_off, d_text or None, text_cap, C.byref(total), stream or None), self._ctx)
+        return total.value
+
+    def fasta_text(self, data, flags: int = 0, tw: int = 80, out=None) -> Tuple[bytes, int]:
+        """treat_b200_fasta_text: FASTA bytes -> the text `treat align -t ... -f ...` prints (parse, alignment and
+        WriteTo on the GPU).  Returns (text, records); with `out` (a binary file object) the pieces are written there
+        as they arrive and the returned text is empty."""
+        from .cabi import TEXT_SINK
+        if isinstance(data, (bytes, bytearray)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        parts = []
+
+        def sink(_user, ptr, n, _first, _nrec):
+            buf = C.string_at(ptr, n) if n else b""
+            if out is not None:
+                out.write(buf)
+            else:
+                parts.append(buf)
+            return 0
+        cb = TEXT_SINK(sink)
+        total = C.c_uint64()
+        check(lib().treat_b200_fasta_text(self._ctx, data.ctypes.data, data.size, flags, tw, cb, None, C.byref(total)), self._ctx)
+        return b"".join(parts), total.value
+
     def synchronize(self) -> None:
         check(lib().treat_b200_synchronize(self._ctx), self._ctx)
 

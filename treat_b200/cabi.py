@@ -56,6 +56,7 @@ class FastaPiece(C.Structure):
 
 
 FASTA_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(FastaPiece))
+TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64)
 
 # name -> (restype, argtypes); must list every function include/treat_b200.h declares
 _P, _U8P, _SZ = C.c_void_p, C.c_void_p, C.c_size_t
@@ -81,6 +82,9 @@ SIGNATURES = {
     "treat_b200_fasta_upload": (C.c_int, [_P, _U8P, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "treat_b200_fasta_align": (C.c_int, [_P, C.c_uint32, _P, _U8P, C.c_uint32, _P, _P, _P, _P, _P]),
     "treat_b200_fasta_stream": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
+    "treat_b200_text_device": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int32, _P, _P, C.c_uint64,
+                                        C.POINTER(C.c_uint64), _P]),
+    "treat_b200_fasta_text": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_int32, _P, _P, C.POINTER(C.c_uint64)]),
     "treat_b200_packed_layout": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(Packed)]),
     "treat_b200_pack_device": (C.c_int, [_P, _U8P, _P, C.POINTER(Packed), _P]),
     "treat_b200_align_packed_device": (C.c_int, [_P, C.POINTER(Packed), _P, C.c_uint32, _P, _U8P, C.c_uint32, _P]),

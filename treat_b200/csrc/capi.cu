@@ -62,6 +62,10 @@ struct Slot {
     uint8_t *land = nullptr;   // treat_b200_fasta_stream: pinned landing buffer of a piece's results
     size_t land_cap = 0;
     DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
+    DevBuf text, text_off, tlen, gtot, tsums;  // Alignment.WriteTo on the device (treat_b200_text_device / _fasta_text)
+    uint8_t *tland = nullptr;                  // pinned landing buffer of a piece's text
+    size_t tland_cap = 0;
+    uint64_t *h_text_total = nullptr;          // pinned [1]
     uint32_t *scalars = nullptr;    // device [8]: max n, any saturated run, reads skipped by a speculative launch, reads listed
                                     // for the DP, compacted ops rows
     uint32_t *h_scalars = nullptr;  // pinned [8]
@@ -71,7 +75,11 @@ struct Slot {
     uint32_t max_len = 0, dev_stride = 0;
     void release()
     {
-        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &ops_idx}) b->release();
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &ops_idx, &text,
+                          &text_off, &tlen, &gtot, &tsums})
+            b->release();
+        if (tland) cudaFreeHost(tland);
+        if (h_text_total) cudaFreeHost(h_text_total);
         if (scalars) cudaFree(scalars);
         if (h_scalars) cudaFreeHost(h_scalars);
         if (h_gap_rows) cudaFreeHost(h_gap_rows);
@@ -121,6 +129,7 @@ struct treat_b200_ctx {
     TemplateDev td{};
     DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut;
     DevBuf d_tpk;  // template bases in the packed-read format (16 codes per word): k_pack marks reads that equal it
+    DevBuf d_tmax; // Template.Max(i) (template.go:186) for every edit site: column widths of WriteTo
     uint32_t band_rows = 0;  // 0 = default window
     uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
     uint32_t gap_hint = 0;   // most gapped reads seen in a chunk: sizes the ahead-of-time copy of compacted ops rows
@@ -202,6 +211,7 @@ int treat_b200_create(int device, treat_b200_ctx **out)
     }
     int e = configure_pack_kernels(ctx->max_smem);
     if (!e) e = configure_align_kernels(ctx->max_smem);
+    if (!e) e = configure_text_kernels(ctx->max_smem);
     if (e) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -216,7 +226,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->d_tpk}) b->release();
+    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->d_tpk, &ctx->d_tmax}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
     if (ctx->d_heat) cudaFree(ctx->d_heat);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
@@ -302,6 +312,13 @@ int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m
             for (int i = 0; i < m; i++) tpk[i >> 4] |= (uint32_t)tb[i] << (2 * (i & 15));
         CK(ctx, ctx->d_tpk.reserve(tpk.size() * 4));
         CK(ctx, cudaMemcpy(ctx->d_tpk.p, tpk.data(), tpk.size() * 4, cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<uint32_t> tmax((size_t)len_pad, 0u);
+        for (int i = 0; i < len; i++)
+            for (int k = 0; k < K; k++) tmax[i] = std::max(tmax[i], edit_site[(size_t)k * len + i]);
+        CK(ctx, ctx->d_tmax.reserve(tmax.size() * 4));
+        CK(ctx, cudaMemcpy(ctx->d_tmax.p, tmax.data(), tmax.size() * 4, cudaMemcpyHostToDevice));
     }
     ctx->lut = lut;
     ctx->tmpl_wide = wide;
@@ -1329,6 +1346,189 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
     if (trace)
         fprintf(stderr, "[treat_b200] fasta_stream %lld pieces, %llu records, %.2f ms: copy+count %.2f, index %.2f, align %.2f, deliver %.2f (sink %.2f)\n",
                 (long long)npieces, (unsigned long long)total, now() - t_begin, tA, tB, tC, tD, tSink);
+    if (n_records) *n_records = total;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Alignment.WriteTo (align.go:388-520) for a batch on the device
+// ---------------------------------------------------------------------------------------------
+static void text_template(const treat_b200_ctx *ctx, TextParams &tp)
+{
+    tp.tb = (const uint8_t *)ctx->d_tb_wide.p;
+    tp.tc32 = (const uint32_t *)ctx->d_tc32.p;
+    tp.tmax = (const uint32_t *)ctx->d_tmax.p;
+    tp.m = ctx->td.m;
+    tp.len = ctx->td.len;
+    tp.len_pad = ctx->td.len_pad;
+    tp.K = ctx->td.K;
+    tp.edit_base = ctx->td.edit_base;
+}
+
+// pass 1 + scan: text_off[N + 1] on the device (tp holds the reads, names, records and ops); the total lands in *h_total
+static int text_sizes(treat_b200_ctx *ctx, Slot &s, TextParams &tp, uint64_t *d_text_off, cudaStream_t st)
+{
+    const uint64_t N = tp.N;
+    CK(ctx, s.tlen.reserve(N * 4));
+    CK(ctx, s.gtot.reserve(N * 4));
+    CK(ctx, s.tsums.reserve((N / 2048 + 4) * 8));
+    if (!s.h_text_total) CK(ctx, cudaMallocHost((void **)&s.h_text_total, 8));
+    tp.tlen = (uint32_t *)s.tlen.p;
+    tp.gtot = (uint32_t *)s.gtot.p;
+    int e = launch_text(tp, false, ctx->num_sms, ctx->max_smem, st);
+    if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "text: read/template geometry exceeds shared memory");
+    if (!e) e = launch_scan_u32((const uint32_t *)s.tlen.p, N, d_text_off, (uint64_t *)s.tsums.p, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_text launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches += 4;
+    CK(ctx, cudaMemcpyAsync(s.h_text_total, d_text_off + N, 8, cudaMemcpyDeviceToHost, st));
+    return TREAT_B200_OK;
+}
+
+static int text_write(treat_b200_ctx *ctx, TextParams &tp, const uint64_t *d_text_off, uint8_t *d_text, cudaStream_t st)
+{
+    tp.text_off = d_text_off;
+    tp.text = d_text;
+    int e = launch_text(tp, true, ctx->num_sms, ctx->max_smem, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_text launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
+    return TREAT_B200_OK;
+}
+
+static int text_tw(int32_t tw) { return tw <= 0 ? 80 : tw; }  // align.go:389-391
+
+int treat_b200_text_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off, const uint8_t *d_names,
+                           const uint64_t *d_name_off, const treat_b200_record *d_rec, const uint8_t *d_ops, uint32_t ops_stride,
+                           uint64_t N, uint32_t max_len, int32_t tw, uint64_t *d_text_off, uint8_t *d_text, uint64_t text_cap,
+                           uint64_t *text_bytes, void *stream)
+{
+    if (!ctx || !text_bytes || (N && (!d_seqs || !d_seq_off || !d_names || !d_name_off || !d_rec || !d_ops || !d_text_off)))
+        return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "text: no template");
+    tw = text_tw(tw);
+    if (tw < 5) return fail(ctx, TREAT_B200_ERR_INVALID, "text: tw must be at least 5 (rows wrap at tw - 4 columns)");
+    if (max_len > kMaxReadLen) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "text: read longer than 16384");
+    if (ops_stride % 4 || ops_stride < a16(((uint32_t)ctx->td.m + max_len + 3) / 4) || misaligned(d_ops))
+        return fail(ctx, TREAT_B200_ERR_INVALID, "text: ops rows as written by the align calls (see treat_b200_ops_stride)");
+    *text_bytes = 0;
+    if (N == 0) return TREAT_B200_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    TextParams tp{};
+    tp.seqs = d_seqs;
+    tp.off = d_seq_off;
+    tp.names = d_names;
+    tp.name_off = d_name_off;
+    tp.rec = d_rec;
+    tp.ops = d_ops;
+    tp.ops_stride = ops_stride;
+    tp.N = N;
+    tp.max_len = max_len;
+    tp.tw = tw;
+    text_template(ctx, tp);
+    int rc = text_sizes(ctx, ctx->dev_slot, tp, d_text_off, st);
+    if (rc) return rc;
+    CK(ctx, cudaStreamSynchronize(st));
+    *text_bytes = *ctx->dev_slot.h_text_total;
+    if (!d_text) return TREAT_B200_OK;  // sizing call
+    if (*text_bytes > text_cap) return fail(ctx, TREAT_B200_ERR_INVALID, "text: text buffer too small (call with d_text = NULL to size)");
+    return text_write(ctx, tp, d_text_off, d_text, st);
+}
+
+// `treat align -t templates.fa -f reads.fa` (cmd/treat/align.go:96-121) as one streaming call: the file is cut at record
+// starts, every piece is indexed, aligned and formatted on the device, and its text is handed to `sink` in file order
+// while the next piece is being processed (two pieces in flight).
+int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, int32_t tw,
+                          treat_b200_text_sink sink, void *user, uint64_t *n_records)
+{
+    if (!ctx || (len && !fasta) || !sink) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    tw = text_tw(tw);
+    if (tw < 5) return fail(ctx, TREAT_B200_ERR_INVALID, "text: tw must be at least 5 (rows wrap at tw - 4 columns)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (n_records) *n_records = 0;
+    for (int i = 0; i < 2; i++)
+        if (!ctx->fslot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->fslot[i].stream, cudaStreamNonBlocking));
+    static const uint64_t piece_bytes = getenv("TREAT_B200_TEXT_PIECE") ? std::max(4096ull, strtoull(getenv("TREAT_B200_TEXT_PIECE"), nullptr, 10)) : (8ull << 20);
+    const uint32_t aflags = (flags & ~(uint32_t)TREAT_B200_OPS_GAPPED_ONLY) | TREAT_B200_WANT_OPS;  // every read's ops row stays on the device
+    struct Pending {
+        bool live = false;
+        uint64_t first = 0, n = 0, bytes = 0;
+    } pend[2];
+    int rc = TREAT_B200_OK;
+    auto deliver = [&](int i) -> int {
+        if (!pend[i].live) return TREAT_B200_OK;
+        pend[i].live = false;
+        CK(ctx, cudaStreamSynchronize(ctx->fslot[i].stream));
+        if (sink(user, ctx->fslot[i].tland, pend[i].bytes, pend[i].first, pend[i].n))
+            return fail(ctx, TREAT_B200_ERR_INVALID, "fasta_text: stopped by the sink");
+        return TREAT_B200_OK;
+    };
+    uint64_t total = 0, k = 0;
+    for (uint64_t at = 0; at < len && rc == TREAT_B200_OK; k++) {
+        uint64_t end = at + piece_bytes;
+        end = end >= len ? len : treat::FastaNextRecordStart(fasta, len, end);
+        const int i = (int)(k & 1);
+        Slot &s = ctx->fslot[i];
+        FastaDev &fa = ctx->fasta_slot[i];
+        cudaStream_t st = s.stream;
+        if ((rc = deliver(i))) break;  // piece k - 2: its landing buffer is reused below
+        if ((rc = fasta_stage_copy_count(ctx, fa, fasta + at, end - at, st))) break;
+        CK(ctx, cudaStreamSynchronize(st));
+        if ((rc = fasta_stage_index(ctx, fa, fasta + at, st))) break;
+        CK(ctx, cudaStreamSynchronize(st));
+        fasta_index_done(fa);
+        at = end;
+        const uint64_t n = fa.N;
+        if (!n) continue;
+        const uint32_t stride = treat_b200_ops_stride(ctx, fa.max_len);
+        if ((rc = fasta_check_align(ctx, fa, aflags, stride))) break;
+        bool in_place = !fa.multi && !ctx->tmpl_wide;
+        if ((rc = fasta_align_chunk(ctx, fa, s, 0, n, aflags, stride, &in_place))) break;
+        TextParams tp{};
+        tp.seqs = in_place ? (const uint8_t *)fa.file.p : (const uint8_t *)fa.seqs.p;
+        if (in_place) {
+            tp.begin = (const uint64_t *)fa.seq_begin.p;
+            tp.len_ = (const uint32_t *)fa.seq_len.p;
+        } else {
+            tp.off = (const uint64_t *)fa.seq_off.p;
+        }
+        tp.names = (const uint8_t *)fa.file.p;
+        tp.name_off = (const uint64_t *)fa.id_off.p;
+        tp.name_len = (const uint32_t *)fa.id_len.p;
+        tp.rec = (const treat_b200_record *)s.rec.p;
+        tp.ops = (const uint8_t *)s.ops.p;
+        tp.ops_stride = stride;
+        tp.N = n;
+        tp.max_len = fa.max_len;
+        tp.tw = tw;
+        text_template(ctx, tp);
+        CK(ctx, s.text_off.reserve((n + 1) * 8));
+        if ((rc = text_sizes(ctx, s, tp, (uint64_t *)s.text_off.p, st))) break;
+        CK(ctx, cudaStreamSynchronize(st));
+        const uint64_t bytes = *s.h_text_total;
+        CK(ctx, s.text.reserve(bytes));
+        if (bytes > s.tland_cap) {
+            if (s.tland) cudaFreeHost(s.tland);
+            s.tland = nullptr;
+            s.tland_cap = 0;
+            CK(ctx, cudaMallocHost((void **)&s.tland, bytes + bytes / 4 + 4096));
+            s.tland_cap = bytes + bytes / 4 + 4096;
+        }
+        if ((rc = text_write(ctx, tp, (const uint64_t *)s.text_off.p, (uint8_t *)s.text.p, st))) break;
+        CK(ctx, cudaMemcpyAsync(s.tland, s.text.p, bytes, cudaMemcpyDeviceToHost, st));
+        pend[i].live = true;
+        pend[i].first = total;
+        pend[i].n = n;
+        pend[i].bytes = bytes;
+        total += n;
+    }
+    // the last two pieces, in file order
+    for (int j = 0; j < 2; j++) {
+        const int i = (int)((k + j) & 1);
+        const int r = rc == TREAT_B200_OK ? deliver(i) : TREAT_B200_OK;
+        if (r) rc = r;
+    }
+    for (int i = 0; i < 2; i++) cudaStreamSynchronize(ctx->fslot[i].stream);
     if (n_records) *n_records = total;
     return rc;
 }

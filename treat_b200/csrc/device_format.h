@@ -108,6 +108,39 @@ struct AlignParams {
     uint32_t sm_cnt_stage;       // k_same_bases: bytes per warp for the staged edit-site counts
 };
 
+// Alignment.WriteTo for a batch (text_kernel.cu)
+struct TextParams {
+    // raw reads: read r = seqs[off[r] - off_bias, off[r+1] - off_bias), or seqs[begin[r], begin[r] + len_[r]) when begin is set
+    const uint8_t *seqs;
+    const uint64_t *off;
+    uint64_t off_bias;
+    const uint64_t *begin;
+    const uint32_t *len_;
+    // names: name r = names[name_off[r], name_off[r+1]), or names[name_off[r], name_off[r] + name_len[r]) when name_len is set
+    const uint8_t *names;
+    const uint64_t *name_off;
+    const uint32_t *name_len;
+    const treat_b200_record *rec;
+    const uint8_t *ops;          // one row per read (gapless reads: all zero)
+    uint32_t ops_stride;
+    uint64_t N;
+    uint32_t max_len;            // longest raw read
+    int32_t tw;                  // terminal width (>= 5)
+    // template: bases as bytes, EditSite rows as uint32 [K][len_pad], Max(i) over the rows [len]
+    const uint8_t *tb;
+    const uint32_t *tc32;
+    const uint32_t *tmax;
+    int32_t m, len, len_pad, K;
+    uint8_t edit_base;
+    uint32_t *tlen;              // [N] pass 1: text bytes of read r
+    uint32_t *gtot;              // [N] pass 1 -> pass 2: length of the gapped rows
+    const uint64_t *text_off;    // [N+1] pass 2: exclusive scan of tlen
+    uint8_t *text;
+    uint32_t stage_cap, tmpl_in_smem;  // set by launch_text
+};
+int launch_text(TextParams &p, bool write, int num_sms, int max_smem_optin, void *stream);
+int configure_text_kernels(int max_smem_optin);
+
 // launchers (kernels.cu)
 int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
 int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
