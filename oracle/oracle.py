@@ -146,6 +146,9 @@ def lib():
         L.orc_align_batch.argtypes = [C.POINTER(_Template), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_text_batch.restype = C.c_void_p
+        L.orc_text_batch.argtypes = [C.POINTER(_Template), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_int,
+                                     C.c_void_p, C.POINTER(C.c_uint64)]
         L.orc_set_tie_order.argtypes = [C.c_int]
         L.orc_get_tie_order.restype = C.c_int
         _lib = L
@@ -366,3 +369,21 @@ def align_batch(tmpl: Template, seqs: np.ndarray, seq_off: np.ndarray, read_coun
         ops_stride or 0,
     )
     return rec, ops, tb
+
+
+def text_batch(tmpl: Template, seqs: np.ndarray, seq_off: np.ndarray, read_count=None, prefix: str = "", nthreads: int = 1):
+    """`treat align -t -f` stdout for reads named "<prefix><index>-<read_count>" (cmd/treat/align.go:113-121):
+    returns (text uint8 array, text_off uint64[N+1])."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    N = len(seq_off) - 1
+    rc = None if read_count is None else np.ascontiguousarray(read_count, dtype=np.uint32)
+    toff = np.zeros(N + 1, dtype=np.uint64)
+    total = C.c_uint64()
+    p = lib().orc_text_batch(tmpl._p, seqs.ctypes.data, seq_off.ctypes.data, rc.ctypes.data if rc is not None else None, N,
+                             prefix.encode(), nthreads, toff.ctypes.data, C.byref(total))
+    try:
+        text = np.frombuffer((C.c_uint8 * total.value).from_address(p), dtype=np.uint8).copy()
+    finally:
+        lib().orc_free(p)
+    return text, toff

@@ -1089,3 +1089,72 @@ uint64_t orc_align_batch(const orc_template *tmpl, const uint8_t *seqs, const ui
     free(th);
     return total;
 }
+
+/* ---------------------------------------------------------------- text of a batch (`treat align -t -f` stdout)
+ * The per-read loop of cmd/treat/align.go:113-121 -- NewFragment, NewAlignment, WriteTo(tw = 80) -- for reads
+ * [0, N) with names "<prefix><index>-<read_count>", threaded; the texts are concatenated in read order.  Returns
+ * a malloc'ed buffer (release with orc_free) and its length; text_off (N + 1, may be NULL) gets the offsets. */
+typedef struct {
+    const orc_template *tmpl;
+    const uint8_t *seqs;
+    const uint64_t *seq_off;
+    const uint32_t *read_count;
+    const char *prefix;
+    uint64_t lo, hi;
+    char **txt;
+    size_t *len;
+} text_job;
+
+static void *text_worker(void *arg)
+{
+    text_job *jb = arg;
+    char name[128];
+    for (uint64_t r = jb->lo; r < jb->hi; r++) {
+        const char *seq = (const char *)jb->seqs + jb->seq_off[r];
+        size_t L = (size_t)(jb->seq_off[r + 1] - jb->seq_off[r]);
+        snprintf(name, sizeof name, "%s%llu-%u", jb->prefix, (unsigned long long)r, jb->read_count ? jb->read_count[r] : 1u);
+        orc_fragment *fr = orc_new_fragment(name, seq, L, ORC_FORWARD, jb->tmpl->edit_base);
+        orc_alignment *a = orc_new_alignment(fr, jb->tmpl, 0);
+        jb->txt[r] = orc_write_to(a, fr, jb->tmpl, 80, &jb->len[r]);
+        orc_alignment_free(a);
+        orc_fragment_free(fr);
+    }
+    return NULL;
+}
+
+char *orc_text_batch(const orc_template *tmpl, const uint8_t *seqs, const uint64_t *seq_off, const uint32_t *read_count,
+                     uint64_t N, const char *prefix, int nthreads, uint64_t *text_off, uint64_t *total_out)
+{
+    if (nthreads < 1) nthreads = 1;
+    if ((uint64_t)nthreads > N && N > 0) nthreads = (int)N;
+    char **txt = xcalloc(N ? N : 1, sizeof *txt);
+    size_t *len = xcalloc(N ? N : 1, sizeof *len);
+    text_job *jobs = xcalloc((size_t)nthreads, sizeof *jobs);
+    pthread_t *th = xcalloc((size_t)nthreads, sizeof *th);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (text_job){tmpl, seqs, seq_off, read_count, prefix ? prefix : "", N * (uint64_t)t / (uint64_t)nthreads,
+                             N * (uint64_t)(t + 1) / (uint64_t)nthreads, txt, len};
+        if (nthreads == 1) text_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, text_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++)
+        if (nthreads > 1) pthread_join(th[t], NULL);
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < N; r++) total += len[r];
+    char *out = malloc(total ? total : 1);
+    if (!out) abort();
+    uint64_t at = 0;
+    for (uint64_t r = 0; r < N; r++) {
+        if (text_off) text_off[r] = at;
+        memcpy(out + at, txt[r], len[r]);
+        at += len[r];
+        free(txt[r]);
+    }
+    if (text_off) text_off[N] = at;
+    free(txt);
+    free(len);
+    free(jobs);
+    free(th);
+    if (total_out) *total_out = total;
+    return out;
+}

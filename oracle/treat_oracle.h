@@ -151,6 +151,10 @@ uint64_t orc_align_batch(const orc_template *tmpl, const uint8_t *seqs, const ui
 
 void orc_free(void *p);
 
+/* cmd/treat/align.go:113-121 for reads [0, N) named "<prefix><index>-<read_count>": concatenated WriteTo(tw = 80) texts */
+char *orc_text_batch(const orc_template *tmpl, const uint8_t *seqs, const uint64_t *seq_off, const uint32_t *read_count,
+                     uint64_t N, const char *prefix, int nthreads, uint64_t *text_off, uint64_t *total_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,10 +33,10 @@ int main(int argc, char **argv)
         fprintf(stderr, "FATA %s\n", treat_b200_strerror(rc));
         return 1;
     }
-    std::string out, err;
-    const bool ok = treat::CliAlign(ctx, t, f, s1, s2, base, offset, &out, &err);
-    if (ok) fwrite(out.data(), 1, out.size(), stdout);
-    else fprintf(stderr, "FATA %s\n", err.c_str());  // logrus.Fatal
+    std::string err;
+    const bool ok = treat::CliAlignStream(ctx, t, f, s1, s2, base, offset,
+                                          [](const char *p, size_t n) { return fwrite(p, 1, n, stdout) == n; }, &err);
+    if (!ok) fprintf(stderr, "FATA %s\n", err.c_str());  // logrus.Fatal
     treat_b200_destroy(ctx);
     return ok ? 0 : 1;
 }

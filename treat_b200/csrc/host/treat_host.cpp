@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iterator>
 #include <map>
 #include <thread>
@@ -663,11 +664,17 @@ bool Aligner::SimpleAlign(const Fragment &f1, const Fragment &f2, std::string *s
     return true;
 }
 
-bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
-              const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
-              std::string *out, std::string *err)
+static int cli_text_sink(void *user, const uint8_t *text, uint64_t len, uint64_t, uint64_t)
 {
-    out->clear();
+    const CliEmit &emit = *static_cast<const CliEmit *>(user);
+    return emit(reinterpret_cast<const char *>(text), (size_t)len) ? 0 : 1;
+}
+
+bool CliAlignStream(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
+                    const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
+                    const CliEmit &emit, std::string *err)
+{
+    auto put = [&](const std::string &t) { return emit(t.data(), t.size()); };
     if (editBase.size() != 1) {
         *err = "Please provide the edit base";
         return false;
@@ -682,23 +689,15 @@ bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::s
         Fragment f1 = NewFragment("1-1", s1, FORWARD, base), f2 = NewFragment("2-1", s2, FORWARD, base);
         std::string a1, a2;
         if (!eng.SimpleAlign(f1, f2, &a1, &a2, err)) return false;
-        *out = PrintAlignment(a1, a2, 80);
-        return true;
+        return put(PrintAlignment(a1, a2, 80));
     }
     if (fragmentPath.empty()) {
         *err = "Please provide either 2 sequences to align or a path to fragment FASTA file";
         return false;
     }
-    bool haveTemplate = false;
-    Template tmpl;
-    if (!templatePath.empty()) {
-        if (!NewTemplateFromFasta(templatePath, FORWARD, base, &tmpl, err)) return false;
-        tmpl.SetOffset(editOffset);
-        haveTemplate = true;
-    }
-    FastaBatch reads;
-    if (!ReadFasta(fragmentPath, &reads, err)) return false;
-    if (!haveTemplate) {
+    if (templatePath.empty()) {  // the first two records of the file against each other (cmd/treat/align.go:95-111)
+        FastaBatch reads;
+        if (!ReadFasta(fragmentPath, &reads, err)) return false;
         if (reads.size() < 2) {
             *err = "Need 2 fragments to align";
             return false;
@@ -707,17 +706,40 @@ bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::s
         Fragment f2 = NewFragment(reads.ids[1], reads.seq(1), FORWARD, base);
         std::string a1, a2;
         if (!eng.SimpleAlign(f1, f2, &a1, &a2, err)) return false;
-        *out = PrintAlignment(a1, a2, 80);
-        return true;
+        return put(PrintAlignment(a1, a2, 80));
     }
+    // every record of the file against the template (cmd/treat/align.go:113-121): FASTA parse, NewFragment, NewAlignment
+    // and WriteTo all run on the device; the text arrives piece by piece in file order
+    Template tmpl;
+    if (!NewTemplateFromFasta(templatePath, FORWARD, base, &tmpl, err)) return false;
+    tmpl.SetOffset(editOffset);
+    std::ifstream in(fragmentPath, std::ios::binary);
+    if (!in) {
+        *err = "open " + fragmentPath + ": no such file or directory";
+        return false;
+    }
+    const std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
     if (!eng.SetTemplate(tmpl, err)) return false;
-    std::vector<Alignment> alns;
-    if (!eng.AlignBatch(reads, false, true, &alns, err)) return false;
-    for (size_t i = 0; i < reads.size(); i++) {
-        Fragment frag = NewFragment(reads.ids[i], reads.seq(i), FORWARD, base);
-        *out += alns[i].WriteTo(frag, tmpl, 80);
+    const int rc = treat_b200_fasta_text(ctx, reinterpret_cast<const uint8_t *>(data.data()), data.size(), TREAT_B200_NO_SUMMARY, 80,
+                                         cli_text_sink, const_cast<CliEmit *>(&emit), nullptr);
+    if (rc != TREAT_B200_OK) {
+        *err = std::string(treat_b200_strerror(rc)) + ": " + treat_b200_last_error(ctx);
+        return false;
     }
     return true;
+}
+
+bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
+              const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
+              std::string *out, std::string *err)
+{
+    out->clear();
+    return CliAlignStream(ctx, templatePath, fragmentPath, s1, s2, editBase, editOffset,
+                          [out](const char *p, size_t n) {
+                              out->append(p, n);
+                              return true;
+                          },
+                          err);
 }
 
 }  // namespace treat

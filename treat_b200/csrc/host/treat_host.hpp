@@ -4,6 +4,7 @@
 // and WriteTo / SimpleAlign only expand the device's traceback ops into text.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -130,6 +131,12 @@ MutantCensus MutantFromOps(const Template &tmpl, const treat_b200_record *rec, c
                            const uint8_t *seqs, const uint64_t *seq_off, uint64_t N);
 
 // `treat align` (cmd/treat/align.go:59-122): returns false + err where the reference calls logrus.Fatal
+// The same with the text handed to `emit` as it is produced (file mode: one call per piece of the reads file, in file
+// order); emit returns false to stop.
+using CliEmit = std::function<bool(const char *, size_t)>;
+bool CliAlignStream(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
+                    const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
+                    const CliEmit &emit, std::string *err);
 bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
               const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
               std::string *out, std::string *err);
