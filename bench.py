@@ -497,7 +497,29 @@ def run_ours(args):
             stream_ms[name] = 1e3 * (time.perf_counter() - t0) / reps
         if not np.array_equal(h_rec, rec_dev):
             raise AssertionError("FASTA streaming path disagrees with the device-buffer path")
-        fasta = {"value": N / fa_s, "unit": UNIT, "ms_per_step": 1e3 * fa_s, "file_bytes": len(text),
+        # `treat align -t -f` text for the same file: parse, alignment and Alignment.WriteTo on the GPU, text to a sink
+        tbytes = [0]
+
+        def sink_text(_u, _ptr, n, _first, _nrec):
+            tbytes[0] += n
+            return 0
+        tcb = cabi.TEXT_SINK(sink_text)
+        ttot = C.c_uint64()
+
+        def step_text():
+            tbytes[0] = 0
+            cabi.check(cabi.lib().treat_b200_fasta_text(eng._ctx, h_txt.ctypes.data, h_txt.size, cabi.NO_SUMMARY, 80, tcb, None, C.byref(ttot)), eng._ctx)
+        step_text()
+        assert ttot.value == N
+        t0 = time.perf_counter()
+        for _ in range(2):
+            step_text()
+        text_s = (time.perf_counter() - t0) / 2
+        write_text = {"value": N / text_s, "unit": UNIT, "ms_per_step": 1e3 * text_s, "text_bytes": int(tbytes[0]),
+                      "d2h_gb_per_s": tbytes[0] / text_s / 1e9,
+                      "api": "treat_b200_fasta_text: file bytes -> the text `treat align -t -f` prints (k_text: WriteTo on the GPU), "
+                             "delivered piece by piece to a sink that only counts the bytes"}
+        fasta = {"value": N / fa_s, "unit": UNIT, "ms_per_step": 1e3 * fa_s, "file_bytes": len(text), "write_text": write_text,
                  "stream": {"value": N / (stream_ms["count"] * 1e-3), "unit": UNIT, "ms_per_step": stream_ms["count"],
                             "ms_per_step_sink_copies_records": stream_ms["copy_records"],
                             "api": "treat_b200_fasta_stream: ~32 MB pieces cut at record starts, copy / index / align / deliver overlapped"},
@@ -516,6 +538,17 @@ def run_ours(args):
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "gcups": g,
                "sample": "first %d reads of the workload, %d threads, %.1f s; CPU port of the Go path (oracle/treat_oracle.c), "
                          "lean mode: one DP per read, record + ops" % (sample, threads, secs)}
+        # what `treat align` itself does per read: NewAlignment + WriteTo (a second DP and the text)
+        from treat_b200 import synth as _synth
+        O, om = oracle_template(t)
+        fs = min(sample, 10000 * threads)
+        fseqs, foff, frc = _synth.reads(t, fs, seed=seed, p_trunc=p_trunc)
+        t0 = time.perf_counter()
+        ftext, _ = O.text_batch(om, fseqs, foff, frc, prefix="r", nthreads=threads)
+        fsecs = time.perf_counter() - t0
+        cpu["faithful"] = {"value": fs / fsecs, "unit": UNIT, "text_bytes": int(len(ftext)),
+                           "sample": "first %d reads, %d threads, %.1f s; NewFragment + NewAlignment + WriteTo per read "
+                                     "(two DPs and the text, as cmd/treat/align.go:113-121)" % (fs, threads, fsecs)}
 
     if rank == 0:
         line = {

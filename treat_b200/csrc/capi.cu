@@ -161,6 +161,22 @@ static int fail(treat_b200_ctx *ctx, int code, const std::string &msg)
     return code;
 }
 
+// Small device -> host read-backs the host waits on right away (sizes, counts): written by a one-warp kernel straight
+// into pinned host memory instead of a cudaMemcpyAsync, which would queue on the D2H copy engine behind the bulk result
+// copies of the other chunks in flight and stall the pipeline for their whole duration.
+static int peek(treat_b200_ctx *ctx, void *h_dst, const void *d_src, uint32_t bytes, cudaStream_t st)
+{
+    int e = launch_peek(h_dst, d_src, bytes, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_peek launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
+    return TREAT_B200_OK;
+}
+#define PEEK(ctx, dst, src, bytes, st)                     \
+    do {                                                   \
+        int _r = peek((ctx), (dst), (src), (bytes), (st)); \
+        if (_r) return _r;                                 \
+    } while (0)
+
 extern "C" {
 
 int treat_b200_abi_version(void) { return TREAT_B200_ABI_VERSION; }
@@ -676,7 +692,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, st));
         return TREAT_B200_OK;
     }
-    CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, 8, cudaMemcpyDeviceToHost, st));
+    PEEK(ctx, s.h_scalars, s.scalars, 8, st);
     CK(ctx, cudaStreamSynchronize(st));  // 8 bytes: max n sizes the align kernel's shared memory
     const uint32_t max_n = s.h_scalars[0];
     ctx->ncap_hint = std::max(ctx->ncap_hint, max_n);
@@ -963,8 +979,8 @@ static int fasta_stage_copy_count(treat_b200_ctx *ctx, FastaDev &fa, const uint8
     int e = launch_scan_u32((const uint32_t *)fa.tile_count.p, ntiles, (uint64_t *)fa.tile_off.p, (uint64_t *)fa.sums.p, st);
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches += 3;
-    CK(ctx, cudaMemcpyAsync(&fa.h[0], (uint64_t *)fa.tile_off.p + ntiles, 8, cudaMemcpyDeviceToHost, st));  // line-start '>' count
-    CK(ctx, cudaMemcpyAsync(&fa.h[1], d_first, 8, cudaMemcpyDeviceToHost, st));                             // first '>' position
+    PEEK(ctx, &fa.h[0], (uint64_t *)fa.tile_off.p + ntiles, 8, st);  // line-start '>' count
+    PEEK(ctx, &fa.h[1], d_first, 8, st);                             // first '>' position
     return TREAT_B200_OK;
 }
 
@@ -998,8 +1014,8 @@ static int fasta_stage_index(treat_b200_ctx *ctx, FastaDev &fa, const uint8_t *f
     if (!e) e = launch_scan_u32((const uint32_t *)fa.seq_len.p, N, (uint64_t *)fa.seq_off.p, (uint64_t *)fa.sums.p, st);
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("fasta index launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches += 5;
-    CK(ctx, cudaMemcpyAsync(&fa.h[2], d_scal, 8, cudaMemcpyDeviceToHost, st));                          // longest sequence, multi-line flag
-    CK(ctx, cudaMemcpyAsync(&fa.h[3], (uint64_t *)fa.seq_off.p + N, 8, cudaMemcpyDeviceToHost, st));   // sequence bytes
+    PEEK(ctx, &fa.h[2], d_scal, 8, st);                          // longest sequence, multi-line flag
+    PEEK(ctx, &fa.h[3], (uint64_t *)fa.seq_off.p + N, 8, st);   // sequence bytes
     return TREAT_B200_OK;
 }
 
@@ -1122,7 +1138,7 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
         if (want_ops && !sparse)
             CK(ctx, cudaMemcpyAsync(ops + c0 * (size_t)ops_stride, s.ops.p, cn * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
         if (sparse) {  // fetch the compacted rows of the gapped reads and put them where they belong
-            CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, st));
+            PEEK(ctx, s.h_scalars, s.scalars, kScalarBytes, st);
             CK(ctx, cudaStreamSynchronize(st));
             const uint32_t cnt = s.h_scalars[4];
             if (cnt) {
@@ -1380,7 +1396,7 @@ static int text_sizes(treat_b200_ctx *ctx, Slot &s, TextParams &tp, uint64_t *d_
     if (!e) e = launch_scan_u32((const uint32_t *)s.tlen.p, N, d_text_off, (uint64_t *)s.tsums.p, st);
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_text launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches += 4;
-    CK(ctx, cudaMemcpyAsync(s.h_text_total, d_text_off + N, 8, cudaMemcpyDeviceToHost, st));
+    PEEK(ctx, s.h_text_total, d_text_off + N, 8, st);
     return TREAT_B200_OK;
 }
 
@@ -1464,6 +1480,10 @@ int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t le
         return TREAT_B200_OK;
     };
     uint64_t total = 0, k = 0;
+    static const bool trace = getenv("TREAT_B200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tDeliver = 0, tCopy = 0, tIndex = 0, tAlign = 0, tSizes = 0, tWrite = 0;
+    const double t_begin = now();
     for (uint64_t at = 0; at < len && rc == TREAT_B200_OK; k++) {
         uint64_t end = at + piece_bytes;
         end = end >= len ? len : treat::FastaNextRecordStart(fasta, len, end);
@@ -1471,12 +1491,16 @@ int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t le
         Slot &s = ctx->fslot[i];
         FastaDev &fa = ctx->fasta_slot[i];
         cudaStream_t st = s.stream;
+        double t0 = now();
         if ((rc = deliver(i))) break;  // piece k - 2: its landing buffer is reused below
+        tDeliver += now() - t0, t0 = now();
         if ((rc = fasta_stage_copy_count(ctx, fa, fasta + at, end - at, st))) break;
         CK(ctx, cudaStreamSynchronize(st));
+        tCopy += now() - t0, t0 = now();
         if ((rc = fasta_stage_index(ctx, fa, fasta + at, st))) break;
         CK(ctx, cudaStreamSynchronize(st));
         fasta_index_done(fa);
+        tIndex += now() - t0, t0 = now();
         at = end;
         const uint64_t n = fa.N;
         if (!n) continue;
@@ -1484,6 +1508,7 @@ int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t le
         if ((rc = fasta_check_align(ctx, fa, aflags, stride))) break;
         bool in_place = !fa.multi && !ctx->tmpl_wide;
         if ((rc = fasta_align_chunk(ctx, fa, s, 0, n, aflags, stride, &in_place))) break;
+        tAlign += now() - t0, t0 = now();
         TextParams tp{};
         tp.seqs = in_place ? (const uint8_t *)fa.file.p : (const uint8_t *)fa.seqs.p;
         if (in_place) {
@@ -1506,6 +1531,7 @@ int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t le
         if ((rc = text_sizes(ctx, s, tp, (uint64_t *)s.text_off.p, st))) break;
         CK(ctx, cudaStreamSynchronize(st));
         const uint64_t bytes = *s.h_text_total;
+        tSizes += now() - t0, t0 = now();
         CK(ctx, s.text.reserve(bytes));
         if (bytes > s.tland_cap) {
             if (s.tland) cudaFreeHost(s.tland);
@@ -1521,7 +1547,9 @@ int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t le
         pend[i].n = n;
         pend[i].bytes = bytes;
         total += n;
+        tWrite += now() - t0;
     }
+    const double t_loop = now();
     // the last two pieces, in file order
     for (int j = 0; j < 2; j++) {
         const int i = (int)((k + j) & 1);
@@ -1529,6 +1557,9 @@ int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t le
         if (r) rc = r;
     }
     for (int i = 0; i < 2; i++) cudaStreamSynchronize(ctx->fslot[i].stream);
+    if (trace)
+        fprintf(stderr, "[treat_b200] fasta_text %llu pieces, %llu records, %.2f ms: wait+sink %.2f, copy+count %.2f, index %.2f, align %.2f, sizes %.2f, write(enqueue) %.2f, drain %.2f\n",
+                (unsigned long long)k, (unsigned long long)total, now() - t_begin, tDeliver, tCopy, tIndex, tAlign, tSizes, tWrite, now() - t_loop);
     if (n_records) *n_records = total;
     return rc;
 }

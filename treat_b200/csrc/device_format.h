@@ -163,6 +163,8 @@ int launch_fasta_records(const uint8_t *file, uint64_t len, const uint64_t *star
 int launch_fasta_compact(const uint8_t *file, uint64_t len, const uint64_t *start, uint64_t N, const uint64_t *seq_begin,
                          const uint64_t *seq_off, uint8_t *seqs, int num_sms, void *stream);
 constexpr uint32_t kFastaTileBytes = 4096;  // bytes per tile of the record-start count
+// up to 64 bytes from device memory into pinned host memory by a one-warp kernel (no copy-engine queue)
+int launch_peek(void *h_dst, const void *d_src, uint32_t bytes, void *stream);
 int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream);
 int configure_pack_kernels(int max_smem_optin);
 int configure_align_kernels(int max_smem_optin);

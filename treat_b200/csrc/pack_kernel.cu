@@ -50,6 +50,19 @@ int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream)
     return (int)cudaGetLastError();
 }
 
+// read-back of a few scalars into pinned (device-mapped) host memory; see peek() in capi.cu
+__global__ void k_peek(uint32_t *dst, const uint32_t *src, uint32_t nwords)
+{
+    if (threadIdx.x < nwords) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+int launch_peek(void *h_dst, const void *d_src, uint32_t bytes, void *stream)
+{
+    if (bytes > 128u || (bytes & 3u)) return (int)cudaErrorInvalidValue;
+    k_peek<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint32_t *>(h_dst), reinterpret_cast<const uint32_t *>(d_src), bytes / 4u);
+    return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // K1, wide path (NewFragment, fragment.go:91-121): bases stay bytes, counts are uint32 -- for templates with a base
 // outside the packed alphabet or a count >= 255, and for chunks with an edit-base run >= 255.  One warp per read,
