@@ -52,7 +52,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
-    ap.add_argument("--workload", default="rps12", choices=["rps12", "long"])
+    ap.add_argument("--workload", default="rps12", choices=["rps12", "long", "xlong"],
+                    help="rps12: BASELINE configs[2]; long: configs[4] (m = 300, K = 10); xlong: m = 700 (column strips)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -64,6 +65,8 @@ def make_template(workload):
     from treat_b200 import synth
     if workload == "rps12":
         return synth.rps12_template(), 0.0, synth.SEED_BASE + 3
+    if workload == "xlong":
+        return synth.long_template(700, 4), 0.2, synth.SEED_BASE + 7
     return synth.long_template(300, 8), 0.2, synth.SEED_BASE + 5
 
 

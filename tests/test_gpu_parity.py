@@ -226,7 +226,7 @@ def test_templates_longer_than_one_pass(eng, tmp_path):
     """Templates of 481 .. 1023 bases run in column strips of 480 (k_align_strips): strip boundaries (481, 960, 961),
     the largest template (Len = 1024 sites), truncated reads, offset + exclude-snps, and the same on the wide path
     (a template base outside the packed alphabet)."""
-    for m, n_alt, N in ((481, 2, 300), (600, 8, 1500), (960, 2, 300), (961, 3, 300), (1023, 4, 600)):
+    for m, n_alt, N in ((481, 2, 300), (505, 2, 300), (511, 3, 300), (512, 2, 300), (600, 8, 1500), (960, 2, 300), (961, 3, 300), (1023, 4, 600)):
         _batch_vs_oracle(eng, synth.long_template(m, n_alt, seed=7 + m), tmp_path, N, 5000 + m, p_trunc=0.3)
     _batch_vs_oracle(eng, synth.long_template(700, 4, seed=11), tmp_path, 500, 6001, p_trunc=0.2, offset=7, exclude=True)
     # wide path: one template base becomes N (every read then differs from it in that base)

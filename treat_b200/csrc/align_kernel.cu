@@ -1118,16 +1118,19 @@ __global__ void __launch_bounds__(max_warps_one(kStripCpl) * 32, 1) k_align_stri
         }
     };
 
-    const uint32_t total = (uint32_t)p.N;
+    // the reads of this launch: all of them, or the ones k_same_long listed
+    const uint32_t total = p.list ? *p.list_count : (uint32_t)p.N;
+    auto read_at = [&](uint32_t u) -> uint32_t { return p.list ? p.list[u] : u; };
     uint32_t it = 0;
-    if (gw < total) issue(gw, 0);
-    for (uint32_t r = gw; r < total; r += nw, it++) {
+    if (gw < total) issue(read_at(gw), 0);
+    for (uint32_t u = gw; u < total; u += nw, it++) {
         const int slot = it & 1;
         const uint32_t parity = (it >> 1) & 1;
+        const uint32_t r = read_at(u);
         const int n = (int)p.n[r];
         const uint32_t rflags = p.rflags[r];
         __syncwarp();
-        if (nw < total - r) issue(r + nw, slot ^ 1);
+        if (nw < total - u) issue(read_at(u + nw), slot ^ 1);
         mbar_wait(&ws.bar[slot], parity);
         if (n > (int)p.ncap) {  // speculative launch (ncap guessed): the host re-runs the chunk
             if (lane == 0 && p.skipped) atomicAdd(p.skipped, 1u);
@@ -1396,8 +1399,8 @@ __global__ void __launch_bounds__(kSameWarps * 32, 2) k_same_bases(const __grid_
     const unsigned gmask = G == 32 ? FULL_MASK : 0xffffu << lead;
     const int m = p.t.m;
 
-    const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, (int)p.cpl);  // no profile, no dump rows in this plan
-    load_template(cs, p, (int)p.cpl);
+    const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, (int)(p.cpl * p.strips));  // no profile, no dump rows in this plan
+    load_template(cs, p, (int)(p.cpl * p.strips));
     uint32_t *zero = reinterpret_cast<uint32_t *>(smem + p.sm_tmpl_bytes);  // the all-match ops of such a read
     for (uint32_t i = threadIdx.x; i < p.sm_ops / 4; i += blockDim.x) zero[i] = 0u;
     uint4 *s_mask = reinterpret_cast<uint4 *>(smem + p.sm_tmpl_bytes + p.sm_ops);  // [17]: t lowest bytes 0xff
@@ -1452,6 +1455,41 @@ __global__ void __launch_bounds__(kSameWarps * 32, 2) k_same_bases(const __grid_
         c = cn;
     }
     if (G == 16) ctr += __shfl_down_sync(FULL_MASK, ctr, 16);  // lane L and lane L + 16 both hold counter L
+    flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
+}
+
+// The same for templates of more than 511 bases (up to 1024 edit sites): one warp per read, the read's counts staged in
+// shared memory, the general assembly on the identity alignment.  A few hundred instructions against the ~10^6 cell
+// updates of the DP such a read would otherwise take.
+__global__ void __launch_bounds__(kSameWarps * 32, 2) k_same_long(const __grid_constant__ AlignParams p)
+{
+    using cnt_t = uint8_t;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int m = p.t.m, tcpl = (int)(p.cpl * p.strips);
+    const CtaSmem<cnt_t> cs = carve_cta<cnt_t>(smem, p, tcpl);
+    load_template(cs, p, tcpl);
+    uint32_t *zero = reinterpret_cast<uint32_t *>(smem + p.sm_tmpl_bytes);  // the all-match ops of such a read
+    for (uint32_t i = threadIdx.x; i < p.sm_ops / 4; i += blockDim.x) zero[i] = 0u;
+    uint4 *stage = reinterpret_cast<uint4 *>(smem + p.sm_tmpl_bytes + p.sm_ops + (size_t)warp * p.sm_cnt_stage);
+    WarpSmem ws{};
+    ws.ops2 = zero;
+    __syncthreads();
+    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
+    const int groups = (m + 1 + 15) / 16;
+    unsigned long long ctr = 0;
+    for (uint64_t r = gw; r < p.N; r += nw) {
+        const uint32_t f = p.rflags[r];
+        if (!(f & kFlagsInternal)) {
+            if (lane == 0) p.list[atomicAdd(p.list_count, 1u)] = (uint32_t)r;
+            continue;
+        }
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.counts + r * (uint64_t)p.counts_stride);
+        __syncwarp();
+        for (int g = lane; g < groups; g += 32) stage[g] = src[g];
+        __syncwarp();
+        finish_same_general(p, cs, ws, lane, r, f, reinterpret_cast<const cnt_t *>(stage), ctr);
+    }
     flush_summary(p, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
 }
 
@@ -1580,10 +1618,22 @@ int launch_same_bases(const AlignParams &planned, int num_sms, void *stream)
     const int m = p.t.m;
     const uint32_t sum_len = p.summary ? TREAT_B200_SUMMARY_HEADER + 3u * p.bins : 0u;
     p.sm_prof_bytes = 0;
-    p.sm_tmpl_bytes = align16(32 * p.cpl) + align16((uint32_t)(p.t.K * p.t.len_pad)) + align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) +
+    p.sm_tmpl_bytes = align16(32 * p.cpl * p.strips) + align16((uint32_t)(p.t.K * p.t.len_pad)) + align16(8u * (p.t.n_alt ? p.t.n_alt : 1)) +
                       align16(8u * sum_len);
     p.sm_tmpl_bytes = (p.sm_tmpl_bytes + 127u) & ~127u;
     p.sm_ops = align16((((uint32_t)(2 * m) + 15) / 16 + 2) * 4);
+    if (p.t.len > 512) {  // k_same_long: the counts of one read per warp, 16 bytes past the last site
+        p.sm_cnt_stage = align16((uint32_t)p.t.len) + 16u;
+        if (p.ncap < (uint32_t)m) p.ncap = (uint32_t)m;
+        const size_t smem_l = p.sm_tmpl_bytes + p.sm_ops + (size_t)kSameWarps * p.sm_cnt_stage;
+        int per = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_same_long, kSameWarps * 32, smem_l) != cudaSuccess || per < 1) per = 1;
+        uint64_t nb = (p.N + kSameWarps - 1) / kSameWarps;
+        if (nb > (uint64_t)num_sms * per) nb = (uint64_t)num_sms * per;
+        if (nb == 0) return 0;
+        k_same_long<<<(unsigned)nb, kSameWarps * 32, smem_l, (cudaStream_t)stream>>>(p);
+        return (int)cudaGetLastError();
+    }
     p.sm_cnt_stage = 512;  // 32 lanes x 16 counts >= m + 1
     if (p.ncap < (uint32_t)m) p.ncap = (uint32_t)m;
     const size_t smem = p.sm_tmpl_bytes + p.sm_ops + 17 * 16 + (size_t)kSameWarps * p.sm_cnt_stage;
@@ -1680,6 +1730,7 @@ int configure_align_kernels(int max_smem_optin)
     if ((e = set_attr<10>(max_smem_optin))) return e;
     if ((e = set_attr<12>(max_smem_optin))) return e;
     if ((e = set_attr<15>(max_smem_optin))) return e;
+    if ((e = (int)cudaFuncSetAttribute(k_same_long, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin))) return e;
     if ((e = (int)cudaFuncSetAttribute(k_align_strips<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin))) return e;
     if ((e = (int)cudaFuncSetAttribute(k_align_strips<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin))) return e;
     return 0;

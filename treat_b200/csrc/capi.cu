@@ -475,7 +475,7 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     pp.lut = ctx->td.lut;
     pp.edit_base = ctx->td.edit_base;
     pp.scalars = d_scalars;
-    pp.tpk = (!dst->wide && !ctx->tmpl_wide && ctx->td.m <= kOnePassTemplateBases) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
+    pp.tpk = (!dst->wide && !ctx->tmpl_wide) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
     pp.tm = (uint32_t)ctx->td.m;
     pp.padded = padded && ((uintptr_t)d_seqs & 15u) == 0 ? 1u : 0u;
     if (span && !dst->wide) {  // k_pack16 only
@@ -551,8 +551,7 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     // The reads k_same_bases leaves for the DP are the hard ones (truncated reads fill into the global scratch).  With more
     // than 7 columns per lane the two-reads-per-warp kernel's scratch (8 bytes per lane and step) no longer fits L2 for
     // them, so listed reads of long templates take the one-read kernel; the paired one serves whole batches.
-    const bool use_list = list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ) &&
-                          ctx->td.m <= kOnePassTemplateBases;  // k_same_bases holds 512 sites; longer templates: DP for every read
+    const bool use_list = list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ);
     if (use_list && ctx->td.m > 7 * 32) ap.force_single = 1u;
     if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
     {
