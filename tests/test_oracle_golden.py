@@ -238,3 +238,23 @@ def test_batch_driver_matches_scalar(fx, examples):
             got = [(ops[k, c // 4] >> (2 * (c % 4))) & 3 for c in range(r["aln_len"])]
             want = [2 if x == "-" else 1 if y == "-" else 0 for x, y in zip(aln1, aln2)]
             assert got == want
+
+
+def test_text_batch_matches_cli(fx, examples, tmp_path):
+    """orc_text_batch (the checker of the device-side WriteTo at scale) == orc_cli_align on the same reads written as a
+    FASTA file with the names it generates, which in turn is pinned to README.rst:70-82 by test_readme_block."""
+    from treat_b200 import synth
+    t = synth.rps12_template()
+    tp = t.write_fasta(str(tmp_path / "t.fa"))
+    om = O.NewTemplateFromFasta(tp, O.FORWARD, "T")
+    seqs, off, rc = synth.reads(t, 120, seed=9, p_trunc=0.2)
+    text, toff = O.text_batch(om, seqs, off, rc, prefix="r", nthreads=3)
+    fp = str(tmp_path / "r.fa")
+    with open(fp, "wb") as fh:
+        for i in range(120):
+            fh.write(b">r%d-%d\n" % (i, rc[i]) + seqs[int(off[i]):int(off[i + 1])].tobytes() + b"\n")
+    want = O.cli_align(template=tp, fragment=fp)
+    assert text.tobytes().decode("latin-1") == want
+    assert toff[0] == 0 and toff[-1] == len(text) and np.all(np.diff(toff.astype(np.int64)) > 0)
+    one = O.NewFragment("r7-%d" % rc[7], seqs[int(off[7]):int(off[8])].tobytes().decode())
+    assert text[int(toff[7]):int(toff[8])].tobytes().decode() == O.NewAlignment(one, om).WriteTo(one, om, 80)
