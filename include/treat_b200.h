@@ -333,6 +333,13 @@ int64_t treat_b200_marshal_batch(const treat_b200_record *rec, const uint8_t *se
 int treat_b200_mutant_report(const treat_b200_template *t, const treat_b200_record *rec, const uint8_t *ops,
                              uint32_t ops_stride, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N, int32_t n,
                              char **out, size_t *out_len);
+/* cmd/treat/stats.go:62-137 (`treat stats`): the block ShowStats prints for one gene -- rule, name, totals, template
+ * facts, the per-sample table -- from summary counters (treat_b200_get_summary, or their sum over GPUs / samples).
+ * samples[i] / summaries[i]: one row per sample (each summary holds at least 14 counters); the gene totals are their
+ * sums.  unique = --unique (count each read once), norm = --norm (totals only).  *out is malloc'ed (treat_b200_free). */
+int treat_b200_stats_text(const treat_b200_template *t, const char *gene, const char *const *samples,
+                          const uint64_t *const *summaries, int32_t n_samples, int32_t unique, int32_t norm, char **out,
+                          size_t *out_len);
 /* cmd/treat/align.go:59-122 `treat align`: writes the exact stdout text to a malloc'ed
  * buffer (*out, release with treat_b200_free) */
 int treat_b200_cli_align(treat_b200_ctx *ctx, const char *template_path, const char *fragment_path,

@@ -219,3 +219,51 @@ def test_fasta_parse_bytes_and_split(tmp_path):
                 ids += piece.ids
                 seqs += [piece.seq(i) for i in range(len(piece))]
             assert ids == whole.ids and seqs == [whole.seq(i) for i in range(len(whole))], (trial, parts)
+
+
+def _go_stats_block(gene, tmpl, rows, unique, norm):
+    """cmd/treat/stats.go:62-137 (ShowStats, one gene) restated with Python's printf verbs; rows = [(sample, Stats)] with
+    Stats = (Total, Std, NonStd, Indels, Snps, SingleMismatch, DoubleMismatch) (stats.go:33-41, 140-187)."""
+    def pct(x, y):
+        return 0.0 if y == 0 else x / y * 100.0
+    g = [sum(r[1][k] for r in rows) for k in range(7)]
+    out = ["=" * 80, gene, "=" * 80, "%20s%11d" % ("Total Alignments:", g[0])]
+    if not norm:
+        out += ["%20s%11d" % ("Standard:", g[1]), "%20s%11d" % ("Non-Standard:", g[2]), "%20s%11d" % ("1-Mismatch:", g[5]),
+                "%20s%11d" % ("2-Mismatch:", g[6]), "%20s%11d" % (">3-Mismatch:", g[4]), "%20s%11d" % ("Indels:", g[3])]
+    out += ["%20s%11d" % ("Template Edit Stop:", tmpl.EditStop), "%20s%11s" % ("Edit Base:", tmpl.EditBase),
+            "%20s%11d" % ("Alt Templates:", len(tmpl.AltRegion)), "-" * 80]
+    out.append("%-15s%9s%9s%5s%9s%5s%9s%5s%9s%5s" % ("Sample", "Total", "Std", "%", "Non-Std", "%", "1MM", "%", "2MM", "%")
+               if not norm else "%-15s%9s" % ("Sample", "Total"))
+    out.append("-" * 80)
+    for name, c in rows:
+        if len(name) > 12:
+            name = name[:12] + ".."
+        out.append("%-15s%9d%9d%5.1f%9d%5.1f%9d%5.1f%9d%5.1f" % (name, c[0], c[1], pct(c[1], c[0]), c[2], pct(c[2], c[0]), c[5],
+                                                                   pct(c[5], c[0]), c[6], pct(c[6], c[0]))
+                   if not norm else "%-15s%9d" % (name, c[0]))
+    return "\n".join(out) + "\n\n"
+
+
+def test_stats_text(examples):
+    """`treat stats` block (cmd/treat/stats.go:62-187) from summary counters: per-sample Stats from the oracle's records."""
+    from helpers import summary_from_records
+    tm = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "T")
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    samples = []
+    for name, f in (("clones", "clones.fa"), ("a-very-long-sample-name", "sample-1.fa"), ("empty", None)):
+        if f is None:
+            summ = np.zeros(16 + 3 * (tm.Len() + 2), dtype=np.uint64)
+        else:
+            reads = P.read_fasta(examples[f])
+            seqs = np.frombuffer("".join(s for _, s in reads).encode(), dtype=np.uint8)
+            off = np.cumsum([0] + [len(s) for _, s in reads]).astype(np.uint64)
+            rc = np.array([O.parseMergeCount(i) for i, _ in reads], dtype=np.uint32)
+            rec, _, _ = O.align_batch(om, seqs, off, rc)
+            summ = summary_from_records(rec, len(tm.Bases), 0, om.EditStop)
+        samples.append((name, summ))
+    for unique in (False, True):
+        for norm in (False, True):
+            rows = [(n, [int(x) for x in s[7 if unique else 0:][:7]]) for n, s in samples]
+            assert T.stats_text(tm, "RPS12", samples, unique, norm) == _go_stats_block("RPS12", tm, rows, unique, norm)
+    assert T.stats_text(tm, "none", [], False, False) == _go_stats_block("none", tm, [], False, False)

@@ -283,6 +283,20 @@ def mutant_report(tmpl: "Template", rec: np.ndarray, ops: np.ndarray, seqs: np.n
         lib().treat_b200_free(out)
 
 
+def stats_text(tmpl: "Template", gene: str, samples: Sequence[Tuple[str, np.ndarray]], unique: bool = False, norm: bool = False) -> str:
+    """`treat stats` block of one gene (cmd/treat/stats.go:62-137) from (sample name, summary counters) pairs."""
+    n = len(samples)
+    names = (C.c_char_p * max(n, 1))(*[_b(s[0]) for s in samples])
+    arrs = [np.ascontiguousarray(s[1], dtype=np.uint64) for s in samples]
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+    out, ln = C.c_void_p(), C.c_size_t()
+    check(lib().treat_b200_stats_text(tmpl._h, _b(gene), names, ptrs, n, int(unique), int(norm), C.byref(out), C.byref(ln)))
+    try:
+        return C.string_at(out.value, ln.value).decode("latin-1")
+    finally:
+        lib().treat_b200_free(out)
+
+
 def PrintAlignment(a1: str, a2: str, tw: int = 80) -> str:
     """cmd/treat/align.go:39-57"""
     out = []

@@ -210,6 +210,62 @@ int treat_b200_mutant_report(const treat_b200_template *t, const treat_b200_reco
     return TREAT_B200_OK;
 }
 
+int treat_b200_stats_text(const treat_b200_template *t, const char *gene, const char *const *samples,
+                          const uint64_t *const *summaries, int32_t n_samples, int32_t unique, int32_t norm, char **out,
+                          size_t *out_len)
+{
+    if (!t || !gene || !out || !out_len || n_samples < 0 || (n_samples && (!samples || !summaries))) return TREAT_B200_ERR_INVALID;
+    const treat::Template &tm = *T(t);
+    const int base = unique ? 7 : 0;  // COUNT_UNIQUE / COUNT_FRAG halves of the summary header
+    // Stats{Total, Std, NonStd, Indels, Snps, SingleMismatch, DoubleMismatch} (stats.go:33-41) in summary order
+    long long g[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n_samples; i++)
+        for (int k = 0; k < 7; k++) g[k] += (long long)summaries[i][base + k];
+    auto pct = [](long long x, long long y) { return y == 0 ? 0.0 : (double)x / (double)y * 100.0; };  // stats.go:54-60
+    std::string text;
+    char line[256];
+    auto put = [&](const char *fmt, auto... a) {
+        snprintf(line, sizeof line, fmt, a...);
+        text += line;
+    };
+    const std::string rule(80, '='), dash(80, '-');
+    text += rule + "\n" + gene + "\n" + rule + "\n";
+    put("%20s%11lld\n", "Total Alignments:", g[0]);
+    if (!norm) {
+        put("%20s%11lld\n", "Standard:", g[1]);
+        put("%20s%11lld\n", "Non-Standard:", g[2]);
+        put("%20s%11lld\n", "1-Mismatch:", g[5]);
+        put("%20s%11lld\n", "2-Mismatch:", g[6]);
+        put("%20s%11lld\n", ">3-Mismatch:", g[4]);
+        put("%20s%11lld\n", "Indels:", g[3]);
+    }
+    put("%20s%11d\n", "Template Edit Stop:", tm.EditStop);
+    put("%20s%11s\n", "Edit Base:", std::string(1, tm.EditBase).c_str());
+    put("%20s%11d\n", "Alt Templates:", (int)tm.AltRegion.size());
+    text += dash + "\n";
+    if (!norm) put("%-15s%9s%9s%5s%9s%5s%9s%5s%9s%5s\n", "Sample", "Total", "Std", "%", "Non-Std", "%", "1MM", "%", "2MM", "%");
+    else put("%-15s%9s\n", "Sample", "Total");
+    text += dash + "\n";
+    for (int i = 0; i < n_samples; i++) {
+        std::string name = samples[i] ? samples[i] : "";
+        if (name.size() > 12) name = name.substr(0, 12) + "..";
+        const uint64_t *c = summaries[i] + base;
+        if (!norm)
+            put("%-15s%9lld%9lld%5.1f%9lld%5.1f%9lld%5.1f%9lld%5.1f\n", name.c_str(), (long long)c[0], (long long)c[1],
+                pct((long long)c[1], (long long)c[0]), (long long)c[2], pct((long long)c[2], (long long)c[0]), (long long)c[5],
+                pct((long long)c[5], (long long)c[0]), (long long)c[6], pct((long long)c[6], (long long)c[0]));
+        else
+            put("%-15s%9lld\n", name.c_str(), (long long)c[0]);
+    }
+    text += "\n";
+    *out = (char *)malloc(text.size() + 1);
+    if (!*out) return TREAT_B200_ERR_NOMEM;
+    memcpy(*out, text.data(), text.size());
+    (*out)[text.size()] = 0;
+    *out_len = text.size();
+    return TREAT_B200_OK;
+}
+
 int treat_b200_cli_align(treat_b200_ctx *ctx, const char *template_path, const char *fragment_path, const char *s1,
                          const char *s2, uint8_t base, int32_t offset, char **out, size_t *out_len, char *err,
                          size_t errlen)
