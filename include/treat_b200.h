@@ -321,6 +321,10 @@ int64_t treat_b200_simple_align(treat_b200_ctx *ctx, const uint8_t *s1, size_t l
 /* align.go:316-335 Alignment.MarshalBinary: 36-byte big-endian header + JuncSeq */
 int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *seq, size_t seq_len, uint8_t *out,
                                   size_t cap);
+/* align.go:295-314 Alignment.UnmarshalBinary: the fields MarshalBinary stores, back into a record (edit_stop ..
+ * indel, read_count, junc_seq_len; the other fields are zero), Norm, and a pointer to the JuncSeq bytes inside the
+ * blob.  ERR_INVALID when the blob is shorter than its header says (the reference panics there). */
+int treat_b200_unmarshal_record(const uint8_t *blob, size_t len, treat_b200_record *rec, double *norm, const uint8_t **junc_seq);
 /* cmd/treat/storage.go:758-770 (`treat load`): Alignment.MarshalBinary for a whole batch; blob i is
  * out[out_off[i] .. out_off[i+1]).  Returns the total size in bytes; nothing is written when out is NULL
  * or out_cap is too small (call once to size).  threads = host threads for the fill. */

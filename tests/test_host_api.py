@@ -267,3 +267,21 @@ def test_stats_text(examples):
             rows = [(n, [int(x) for x in s[7 if unique else 0:][:7]]) for n, s in samples]
             assert T.stats_text(tm, "RPS12", samples, unique, norm) == _go_stats_block("RPS12", tm, rows, unique, norm)
     assert T.stats_text(tm, "none", [], False, False) == _go_stats_block("none", tm, [], False, False)
+
+
+def test_unmarshal_binary_round_trip(examples):
+    """Alignment.UnmarshalBinary (align.go:295-314) inverts MarshalBinary: blobs made by the oracle for clones.fa."""
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    for rid, seq in P.read_fasta(examples["clones.fa"]):
+        a = O.NewAlignment(O.NewFragment(rid, seq), om)
+        got = T.UnmarshalBinary(a.MarshalBinary())
+        assert got == dict(EditStop=a.EditStop, JuncStart=a.JuncStart, JuncEnd=a.JuncEnd, JuncLen=a.JuncLen, ReadCount=a.ReadCount,
+                           HasMutation=a.HasMutation, AltEditing=a.AltEditing, Mismatches=a.Mismatches, Indel=a.Indel, Norm=0.0,
+                           JuncSeq=a.JuncSeq), rid
+    # negative fields keep their sign (readInt64 is a 32-bit big-endian read, align.go:281-287); Norm is an IEEE double
+    import struct
+    blob = struct.pack(">iiiiIBBBBdI", -1, 0, -7, 3, 4000000000, 1, 2, 255, 1, 0.125, 3) + b"TTA"
+    got = T.UnmarshalBinary(blob)
+    assert (got["EditStop"], got["JuncEnd"], got["ReadCount"], got["Mismatches"], got["Norm"], got["JuncSeq"]) == (-1, -7, 4000000000, 255, 0.125, "TTA")
+    with pytest.raises(T.TreatError):
+        T.UnmarshalBinary(blob[:37])  # shorter than its header says: the reference panics

@@ -7,6 +7,6 @@ from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, OP_DEL, OP_INS, OP_MATCH, 
                    ST_SATURATED, ST_WIDE_BASE, SUMMARY_HEADER, WANT_OPS, TreatError)
 from .api import (Aligner, Alignment, FastaBatch, Fragment, NewFragment, NewTemplate, NewTemplateFromFasta,
                   PrintAlignment, Template, fasta_split, marshal_batch, mutant_report, parseMergeCount, parse_fasta,
-                  read_fasta, stats_text)
+                  read_fasta, stats_text, UnmarshalBinary)
 
 __version__ = "0.1.0"

@@ -283,6 +283,19 @@ def mutant_report(tmpl: "Template", rec: np.ndarray, ops: np.ndarray, seqs: np.n
         lib().treat_b200_free(out)
 
 
+def UnmarshalBinary(blob: bytes) -> dict:
+    """Alignment.UnmarshalBinary (align.go:295-314): the stored fields of a `treat load` blob."""
+    rec = np.zeros(1, dtype=RECORD_DTYPE)
+    norm, js = C.c_double(), C.c_void_p()
+    buf = C.create_string_buffer(bytes(blob), len(blob))
+    check(lib().treat_b200_unmarshal_record(C.cast(buf, C.c_void_p), len(blob), rec.ctypes.data, C.byref(norm), C.byref(js)))
+    r = rec[0]
+    return dict(EditStop=int(r["edit_stop"]), JuncStart=int(r["junc_start"]), JuncEnd=int(r["junc_end"]), JuncLen=int(r["junc_len"]),
+                ReadCount=int(r["read_count"]), HasMutation=int(r["has_mutation"]), AltEditing=int(r["alt_editing"]),
+                Mismatches=int(r["mismatches"]), Indel=int(r["indel"]), Norm=norm.value,
+                JuncSeq=C.string_at(js.value, int(r["junc_seq_len"])).decode("latin-1"))
+
+
 def stats_text(tmpl: "Template", gene: str, samples: Sequence[Tuple[str, np.ndarray]], unique: bool = False, norm: bool = False) -> str:
     """`treat stats` block of one gene (cmd/treat/stats.go:62-137) from (sample name, summary counters) pairs."""
     n = len(samples)

@@ -210,6 +210,27 @@ int treat_b200_mutant_report(const treat_b200_template *t, const treat_b200_reco
     return TREAT_B200_OK;
 }
 
+int treat_b200_unmarshal_record(const uint8_t *blob, size_t len, treat_b200_record *rec, double *norm, const uint8_t **junc_seq)
+{
+    if (!blob || !rec) return TREAT_B200_ERR_INVALID;
+    treat::Alignment a;
+    if (!a.UnmarshalBinary(blob, len)) return TREAT_B200_ERR_INVALID;
+    memset(rec, 0, sizeof *rec);
+    rec->edit_stop = a.EditStop;
+    rec->junc_start = a.JuncStart;
+    rec->junc_end = a.JuncEnd;
+    rec->junc_len = a.JuncLen;
+    rec->read_count = a.ReadCount;
+    rec->has_mutation = a.HasMutation;
+    rec->alt_editing = a.AltEditing;
+    rec->mismatches = a.Mismatches;
+    rec->indel = a.Indel;
+    rec->junc_seq_len = (uint32_t)a.JuncSeq.size();
+    if (norm) *norm = a.Norm;
+    if (junc_seq) *junc_seq = blob + 36;
+    return TREAT_B200_OK;
+}
+
 int treat_b200_stats_text(const treat_b200_template *t, const char *gene, const char *const *samples,
                           const uint64_t *const *summaries, int32_t n_samples, int32_t unique, int32_t norm, char **out,
                           size_t *out_len)

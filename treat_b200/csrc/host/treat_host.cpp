@@ -393,6 +393,27 @@ std::string Alignment::WriteTo(const Fragment &frag, const Template &tmpl, int t
     return out;
 }
 
+bool Alignment::UnmarshalBinary(const uint8_t *buf, size_t len)
+{
+    if (!buf || len < 36) return false;
+    auto be32 = [&](size_t o) { return ((uint32_t)buf[o] << 24) | ((uint32_t)buf[o + 1] << 16) | ((uint32_t)buf[o + 2] << 8) | (uint32_t)buf[o + 3]; };
+    const uint32_t seq_len = be32(32);
+    if ((size_t)seq_len > len - 36) return false;
+    EditStop = (int)(int32_t)be32(0);  // readInt64 sign-extends 32 bits (align.go:281-287)
+    JuncStart = (int)(int32_t)be32(4);
+    JuncEnd = (int)(int32_t)be32(8);
+    JuncLen = (int)(int32_t)be32(12);
+    ReadCount = be32(16);
+    HasMutation = buf[20];
+    AltEditing = buf[21];
+    Mismatches = buf[22];
+    Indel = buf[23];
+    const uint64_t bits = ((uint64_t)be32(24) << 32) | be32(28);
+    memcpy(&Norm, &bits, 8);
+    JuncSeq.assign(reinterpret_cast<const char *>(buf) + 36, seq_len);
+    return true;
+}
+
 std::vector<uint8_t> Alignment::MarshalBinary() const
 {
     std::vector<uint8_t> b(36 + JuncSeq.size());

@@ -93,6 +93,9 @@ struct Alignment {
     std::string WriteTo(const Fragment &frag, const Template &tmpl, int tw) const;
     // align.go:316-335
     std::vector<uint8_t> MarshalBinary() const;
+    // align.go:295-314: the inverse (36-byte big-endian header + JuncSeq); false when the blob is shorter than it says
+    // (the reference panics with a slice-bounds error there)
+    bool UnmarshalBinary(const uint8_t *buf, size_t len);
 };
 
 // align.go:337-386 string assembly from ops (ops computed by the GPU with f1 as the template)
