@@ -1387,22 +1387,28 @@ static int text_sizes(treat_b200_ctx *ctx, Slot &s, TextParams &tp, uint64_t *d_
     CK(ctx, s.tlen.reserve(N * 4));
     CK(ctx, s.gtot.reserve(N * 4));
     CK(ctx, s.tsums.reserve((N / 2048 + 4) * 8));
-    if (!s.h_text_total) CK(ctx, cudaMallocHost((void **)&s.h_text_total, 8));
+    if (!s.h_text_total) CK(ctx, cudaMallocHost((void **)&s.h_text_total, 16));
+    int sr = ensure_scalars(ctx, s);
+    if (sr) return sr;
     tp.tlen = (uint32_t *)s.tlen.p;
     tp.gtot = (uint32_t *)s.gtot.p;
+    tp.gmax = s.scalars + 7;  // the slot's last scalar word: longest row of the batch
+    CK(ctx, cudaMemsetAsync(tp.gmax, 0, 4, st));
     int e = launch_text(tp, false, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "text: read/template geometry exceeds shared memory");
     if (!e) e = launch_scan_u32((const uint32_t *)s.tlen.p, N, d_text_off, (uint64_t *)s.tsums.p, st);
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_text launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches += 4;
     PEEK(ctx, s.h_text_total, d_text_off + N, 8, st);
+    PEEK(ctx, s.h_text_total + 1, tp.gmax, 4, st);
     return TREAT_B200_OK;
 }
 
-static int text_write(treat_b200_ctx *ctx, TextParams &tp, const uint64_t *d_text_off, uint8_t *d_text, cudaStream_t st)
+static int text_write(treat_b200_ctx *ctx, Slot &s, TextParams &tp, const uint64_t *d_text_off, uint8_t *d_text, cudaStream_t st)
 {
     tp.text_off = d_text_off;
     tp.text = d_text;
+    tp.g_longest = (uint32_t)s.h_text_total[1];  // pass 1's longest row (the stream was synchronised since)
     int e = launch_text(tp, true, ctx->num_sms, ctx->max_smem, st);
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_text launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches++;
@@ -1446,7 +1452,7 @@ int treat_b200_text_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
     *text_bytes = *ctx->dev_slot.h_text_total;
     if (!d_text) return TREAT_B200_OK;  // sizing call
     if (*text_bytes > text_cap) return fail(ctx, TREAT_B200_ERR_INVALID, "text: text buffer too small (call with d_text = NULL to size)");
-    return text_write(ctx, tp, d_text_off, d_text, st);
+    return text_write(ctx, ctx->dev_slot, tp, d_text_off, d_text, st);
 }
 
 // `treat align -t templates.fa -f reads.fa` (cmd/treat/align.go:96-121) as one streaming call: the file is cut at record
@@ -1539,7 +1545,7 @@ int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t le
             CK(ctx, cudaMallocHost((void **)&s.tland, bytes + bytes / 4 + 4096));
             s.tland_cap = bytes + bytes / 4 + 4096;
         }
-        if ((rc = text_write(ctx, tp, (const uint64_t *)s.text_off.p, (uint8_t *)s.text.p, st))) break;
+        if ((rc = text_write(ctx, s, tp, (const uint64_t *)s.text_off.p, (uint8_t *)s.text.p, st))) break;
         CK(ctx, cudaMemcpyAsync(s.tland, s.text.p, bytes, cudaMemcpyDeviceToHost, st));
         pend[i].live = true;
         pend[i].first = total;

@@ -136,7 +136,9 @@ struct TextParams {
     uint32_t *gtot;              // [N] pass 1 -> pass 2: length of the gapped rows
     const uint64_t *text_off;    // [N+1] pass 2: exclusive scan of tlen
     uint8_t *text;
-    uint32_t stage_cap, tmpl_in_smem;  // set by launch_text
+    uint32_t *gmax;              // pass 1 (may be null): atomicMax of the row lengths
+    uint32_t g_longest;          // pass 2: that maximum (0: unknown -> column-wise writer)
+    uint32_t stage_cap, tmpl_in_smem, warp_bytes, col_cap;  // set by launch_text
 };
 int launch_text(TextParams &p, bool write, int num_sms, int max_smem_optin, void *stream);
 int configure_text_kernels(int max_smem_optin);

@@ -7,11 +7,15 @@
 //   pass 1 (WRITE = false): NewFragment on the warp (bases + edit-base run lengths into shared memory), the width of
 //       every alignment column (1 + max edit-base count over the rows that print one), hence the row length G and the
 //       text length; an exclusive scan over the reads turns the lengths into offsets.
-//   pass 2 (WRITE = true): the same walk; lane l owns column c0 + l, a warp scan of the widths gives its position x in the
-//       rows, and it writes its column of every row straight to the text: character p of the column is '-' while
-//       p < max - count, the edit base while p < max, then the base.  The byte address of (row k, position x) is
-//       arithmetic: chunk q = x / cols, all chunks but the last are full, rows inside a chunk are label + ": " + chars + "\n".
-// Integer / byte work, HBM (in practice PCIe D2H) bound: about 2.5 KB of text per RPS12 read.
+//   pass 2: the same walk, lane l owns column c0 + l and a warp scan of the widths gives its position x in the rows.
+//       Character p of a column is '-' while p < max - count, the edit base while p < max, then the base, and the byte
+//       address of (row k, position x) is arithmetic: chunk q = x / cols, all chunks but the last are full, rows inside a
+//       chunk are label + ": " + chars + "\n".
+//       MODE 2 (the normal case): the walk only records every column's position and (ti, fi, op) in shared memory plus
+//       an inverse map position -> column; then lane l takes row position xi + l, looks its column up once and writes
+//       that position of every row: 32 consecutive bytes of a line per store instruction.
+//       MODE 1 (reads too long for the shared-memory tables): each lane writes its own column of every row directly.
+// Integer / byte work, HBM (in practice PCIe D2H) bound: about 2.8 KB of text per RPS12 read.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -53,28 +57,35 @@ __device__ __forceinline__ uint8_t *put_str(uint8_t *o, const char *s)
     return o;
 }
 
-template <bool WRITE>
+// MODE 0: sizes only; 1: write, column-wise; 2: write, position-wise through shared-memory column tables
+template <int MODE>
 __global__ void __launch_bounds__(kTextWarps * 32) k_text(const __grid_constant__ TextParams p)
 {
+    constexpr bool WRITE = MODE != 0;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = p.m, len = p.len, K = p.K, R = K + 1;
     const uint32_t lt = (1u << lane) - 1u;
     // CTA-wide: label geometry, template bases, Max(i) (template.go:186), and the EditSite rows when they fit
     uint32_t *s_labsum = reinterpret_cast<uint32_t *>(smem);             // [R + 1] sum over rows j < k of (label_j + 3)
-    uint32_t *s_tmax = s_labsum + (kTextMaxRows + 1);                    // [len]
+    uint32_t *s_pre = s_labsum + (kTextMaxRows + 1);                     // [R] where row k's characters start inside its line block
+    uint32_t *s_tmax = s_pre + kTextMaxRows;                             // [len]
     uint32_t *s_tc = s_tmax + p.len_pad;                                 // [K][len_pad] (tmpl_in_smem)
     uint8_t *s_lab = reinterpret_cast<uint8_t *>(s_tc + (p.tmpl_in_smem ? (size_t)K * p.len_pad : 0));  // [R] label length
     uint8_t *s_tb = s_lab + 48;                                          // [m]
-    uint8_t *wbase = s_tb + align16((uint32_t)m) + (size_t)warp * (5u * p.stage_cap);
+    uint8_t *wbase = s_tb + align16((uint32_t)m) + (size_t)warp * p.warp_bytes;
     uint8_t *sb = wbase;                                                  // [cap] read bases, upper-cased
     uint32_t *sc = reinterpret_cast<uint32_t *>(wbase + p.stage_cap);     // [cap] Fragment.EditSite
+    // MODE 2: per alignment column its position in the rows and (ti | op << 11 | fi << 13); per row position its column
+    uint32_t *cx = sc + p.stage_cap, *ci = cx + p.col_cap;
+    uint16_t *cmap = reinterpret_cast<uint16_t *>(ci + p.col_cap);
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
         for (int k = 0; k < R; k++) {
             const uint32_t l = (k >= 2 && k < K && k - 1 >= 10) ? 3u : 2u;  // FE, PE, A1.., RD
             s_lab[k] = (uint8_t)l;
             s_labsum[k] = acc;
+            s_pre[k] = acc + l + 2u;
             acc += l + 3u;
         }
         s_labsum[R] = acc;
@@ -90,6 +101,7 @@ __global__ void __launch_bounds__(kTextWarps * 32) k_text(const __grid_constant_
     const uint8_t eb = p.edit_base;
 
     const uint64_t gw = (uint64_t)blockIdx.x * kTextWarps + warp, nw = (uint64_t)gridDim.x * kTextWarps;
+    uint32_t gmax = 0;  // MODE 0: longest row of this warp's reads
     for (uint64_t r = gw; r < p.N; r += nw) {
         // ---- NewFragment (fragment.go:91-121) on the warp: 32 characters per step ------------------------
         const uint64_t b = p.begin ? p.begin[r] : p.off[r] - p.off_bias;
@@ -164,7 +176,12 @@ __global__ void __launch_bounds__(kTextWarps * 32) k_text(const __grid_constant_
             }
             const uint32_t xc = xbase + incl - width;
             xbase += __shfl_sync(FULL_MASK, incl, 31);
-            if (WRITE && width) {
+            if (MODE == 2 && valid) {
+                cx[c] = xc;
+                ci[c] = (uint32_t)ti | (op << 11) | ((uint32_t)fi << 13);
+                for (uint32_t pp = 0; pp < width; pp++) cmap[xc + pp] = (uint16_t)c;
+            }
+            if (MODE == 1 && width) {
                 const uint32_t q0 = xc / cols, r0 = xc - q0 * cols;
                 const uint8_t tbase = ti < m ? s_tb[ti] : (uint8_t)'?', rbase = fi < n ? sb[fi] : (uint8_t)'?';
                 for (int k = 0; k < R; k++) {
@@ -194,8 +211,40 @@ __global__ void __launch_bounds__(kTextWarps * 32) k_text(const __grid_constant_
                 p.gtot[r] = g;
                 p.tlen[r] = hdr + (q - 1u) * block_full + s_labsum[R] + (uint32_t)R * l2 + 1u;
             }
+            gmax = max(gmax, xbase);
             __syncwarp();
             continue;
+        }
+        if (MODE == 2) {
+            // ---- 32 row positions per step: one column look-up per lane, then that position of every row ----
+            __syncwarp();
+            for (uint32_t xi = 0; xi < G; xi += 32) {
+                const uint32_t x = xi + lane;
+                if (x < G) {
+                    const uint32_t c = cmap[x], pp = x - cx[c], info = ci[c];
+                    const int ti = (int)(info & 0x7ffu), fi = (int)(info >> 13);
+                    const uint32_t op = (info >> 11) & 3u;
+                    const bool ins = op == TREAT_B200_OP_INS, del = op == TREAT_B200_OP_DEL;  // op 3: the last edit site
+                    const uint32_t cnt = del ? 0u : sc[fi];
+                    const uint32_t tmx = ins ? 0u : s_tmax[ti];
+                    const uint32_t mx = ins ? cnt : del ? tmx : max(tmx, cnt);
+                    const uint8_t tbase = ti < m ? s_tb[ti] : (uint8_t)'?', rbase = fi < n ? sb[fi] : (uint8_t)'?';
+                    const uint32_t q = x / cols, rr = x - q * cols, lq = q == nch - 1u ? ll : cols;
+                    uint8_t *at = out + hdr + (size_t)q * block_full + rr;
+                    // template rows: '-' x (max - count), edit base x count, base; all '-' for an insertion
+                    const uint32_t *tcol = tc + ti;
+                    const uint32_t lim = ins ? 0xffffffffu : mx;  // pp < lim: pad or edit base; pp == mx: the base
+                    for (int k = 0; k < K; k++) {
+                        const uint32_t e = *tcol;
+                        tcol += p.len_pad;
+                        const uint32_t ndash = ins ? 0xffffffffu : mx - min(e, mx);
+                        at[s_pre[k]] = pp < ndash ? (uint8_t)'-' : pp < lim ? eb : tbase;
+                        at += lq;
+                    }
+                    // RD row: all '-' for a deletion
+                    at[s_pre[K]] = (del || pp < mx - cnt) ? (uint8_t)'-' : pp < mx ? eb : rbase;
+                }
+            }
         }
         // ---- header (align.go:465-491) -------------------------------------------------------------------
         {
@@ -262,40 +311,52 @@ __global__ void __launch_bounds__(kTextWarps * 32) k_text(const __grid_constant_
         }
         __syncwarp();
     }
+    if (MODE == 0 && lane == 0 && gmax && p.gmax) atomicMax(p.gmax, gmax);
 }
 
 size_t text_smem_bytes(const TextParams &p, int warps)
 {
-    return (size_t)(kTextMaxRows + 1) * 4 + (size_t)p.len_pad * 4 + (p.tmpl_in_smem ? (size_t)p.K * p.len_pad * 4 : 0) + 48 +
-           align16((uint32_t)p.m) + (size_t)warps * 5u * p.stage_cap;
+    return (size_t)(2 * kTextMaxRows + 1) * 4 + (size_t)p.len_pad * 4 + (p.tmpl_in_smem ? (size_t)p.K * p.len_pad * 4 : 0) + 48 +
+           align16((uint32_t)p.m) + (size_t)warps * p.warp_bytes;
 }
 
-// p.stage_cap and p.tmpl_in_smem are set here
+// p.stage_cap, p.warp_bytes, p.col_cap and p.tmpl_in_smem are set here.  write: p.g_longest is the longest row (pass 1's
+// gmax): the position-wise writer is used when its shared-memory tables fit, else the column-wise one.
 int launch_text(TextParams &p, bool write, int num_sms, int max_smem_optin, void *stream)
 {
     if (p.N == 0) return 0;
     p.stage_cap = align16(p.max_len + 1u);
     p.tmpl_in_smem = (size_t)p.K * p.len_pad * 4 <= 64u * 1024u ? 1u : 0u;
+    p.col_cap = 0;
+    p.warp_bytes = 5u * p.stage_cap;
+    int mode = write ? 1 : 0;
+    if (write && p.g_longest) {
+        TextParams q = p;
+        q.col_cap = align16((uint32_t)p.m + p.max_len + 2u);
+        q.warp_bytes = 5u * q.stage_cap + 8u * q.col_cap + align16(2u * (p.g_longest + 32u));
+        if (q.col_cap < 65536u && text_smem_bytes(q, kTextWarps) <= (size_t)max_smem_optin / 2) {  // two CTAs per SM at least
+            p = q;
+            mode = 2;
+        }
+    }
     const size_t smem = text_smem_bytes(p, kTextWarps);
     if (smem > (size_t)max_smem_optin) return -1000;
+    auto kern = mode == 2 ? k_text<2> : mode == 1 ? k_text<1> : k_text<0>;
     int per_sm = 0;
-    cudaError_t oe = write ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_text<true>, kTextWarps * 32, smem)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_text<false>, kTextWarps * 32, smem);
-    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTextWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     uint64_t blocks = (p.N + kTextWarps - 1) / kTextWarps;
     if (blocks > (uint64_t)num_sms * per_sm) blocks = (uint64_t)num_sms * per_sm;
-    if (write)
-        k_text<true><<<(unsigned)blocks, kTextWarps * 32, smem, (cudaStream_t)stream>>>(p);
-    else
-        k_text<false><<<(unsigned)blocks, kTextWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    kern<<<(unsigned)blocks, kTextWarps * 32, smem, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 
 int configure_text_kernels(int max_smem_optin)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_text<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    cudaError_t e = cudaFuncSetAttribute(k_text<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaFuncSetAttribute(k_text<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    e = cudaFuncSetAttribute(k_text<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaFuncSetAttribute(k_text<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
 }
 
 }  // namespace treat_b200
