@@ -533,6 +533,12 @@ def test_write_to_on_device(eng, examples, tmp_path):
     assert _text_vs_oracle(eng, tpath, odd.encode(), tmp_path, "odd") == 6
     sat = ">sat-7\n%s\n>plain-1\n%s\n" % (reads[4][:80] + "T" * 300 + reads[4][80:], reads[5])
     assert _text_vs_oracle(eng, tpath, sat.encode(), tmp_path, "saturated") == 2
+    # very long reads: the position tables of k_text no longer fit shared memory (column-wise writer, fewer warps per CTA)
+    rng = random.Random(5)
+    big = "".join(rng.choice("ACGTTTT") for _ in range(15000))
+    mid = reads[6][:150] + "".join(rng.choice("ACGTT") for _ in range(5800)) + reads[6][150:]
+    longf = ">big-2\n%s\n>plain-1\n%s\n>mid-3\n%s\n" % (big, reads[7], mid)
+    assert _text_vs_oracle(eng, tpath, longf.encode(), tmp_path, "long_reads") == 3
     # long template, K = 10 (labels A1..A8) and K = 14 (labels A10..A12 are three characters wide), truncated reads
     for m, n_alt, N in ((300, 8, 600), (90, 12, 300), (700, 3, 200)):
         tl = synth.long_template(m, n_alt, seed=31 + m)

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kTextWarps * 32) k_text(const __grid_constant_
     const uint32_t block_full = s_labsum[R] + (uint32_t)R * cols + 1u;
     const uint8_t eb = p.edit_base;
 
-    const uint64_t gw = (uint64_t)blockIdx.x * kTextWarps + warp, nw = (uint64_t)gridDim.x * kTextWarps;
+    const uint64_t nwarps = blockDim.x >> 5;  // kTextWarps, fewer when very long reads need the shared memory
+    const uint64_t gw = (uint64_t)blockIdx.x * nwarps + warp, nw = (uint64_t)gridDim.x * nwarps;
     uint32_t gmax = 0;  // MODE 0: longest row of this warp's reads
     for (uint64_t r = gw; r < p.N; r += nw) {
         // ---- NewFragment (fragment.go:91-121) on the warp: 32 characters per step ------------------------
@@ -339,14 +340,16 @@ int launch_text(TextParams &p, bool write, int num_sms, int max_smem_optin, void
             mode = 2;
         }
     }
-    const size_t smem = text_smem_bytes(p, kTextWarps);
+    int warps = kTextWarps;  // fewer warps per CTA when the reads are so long that eight staging areas do not fit
+    while (warps > 1 && text_smem_bytes(p, warps) > (size_t)max_smem_optin) warps >>= 1;
+    const size_t smem = text_smem_bytes(p, warps);
     if (smem > (size_t)max_smem_optin) return -1000;
     auto kern = mode == 2 ? k_text<2> : mode == 1 ? k_text<1> : k_text<0>;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTextWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    uint64_t blocks = (p.N + kTextWarps - 1) / kTextWarps;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    uint64_t blocks = (p.N + warps - 1) / warps;
     if (blocks > (uint64_t)num_sms * per_sm) blocks = (uint64_t)num_sms * per_sm;
-    kern<<<(unsigned)blocks, kTextWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 
