@@ -361,6 +361,32 @@ def run_ours(args):
     pack_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_pack_device(
         eng._ctx, d_seqs.data_ptr(), d_off.data_ptr(), C.byref(pk_full), sraw), eng._ctx), args.steps)
     n_arr = d_n.cpu().numpy().astype(np.int64) & 0xffff
+    # ---- Alignment.WriteTo for the batch, everything resident in HBM (k_text: sizes, scan, write) ----------------
+    text_dev = None
+    if rank == 0 and world == 1 and not args.no_fasta:
+        tn = min(N, 250_000)  # 0.7 GB of text
+        names = np.frombuffer(b"".join(b"r%d-%d" % (i, rc[i]) for i in range(tn)), dtype=np.uint8)
+        noff = np.zeros(tn + 1, dtype=np.int64)
+        noff[1:] = np.cumsum([len(b"r%d-%d" % (i, rc[i])) for i in range(tn)])
+        d_names, d_noff = torch.from_numpy(names.copy()).to(dev), torch.from_numpy(noff).to(dev)
+        d_toff = torch.empty(tn + 1, dtype=torch.int64, device=dev)
+        # every read's ops row stays on the device for the formatter
+        eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), tn, max_len, cabi.WANT_OPS | cabi.NO_SUMMARY,
+                               d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw)
+        targs = (d_seqs.data_ptr(), d_off.data_ptr(), d_names.data_ptr(), d_noff.data_ptr(), d_rec.data_ptr(), d_ops.data_ptr(), stride,
+                 tn, max_len, 80, d_toff.data_ptr())
+        tbytes = eng.text_device(*targs, 0, 0, sraw)
+        d_text = torch.empty(tbytes, dtype=torch.uint8, device=dev)
+        text_ms = kernel_ms(lambda: eng.text_device(*targs, d_text.data_ptr(), tbytes, sraw), 5)
+        raw_bytes = int(off[tn])
+        text_dev = {"value": tn / (text_ms * 1e-3), "unit": UNIT, "ms_per_launch_pair": text_ms, "reads": tn, "text_bytes": int(tbytes),
+                    "text_gb_per_s": tbytes / (text_ms * 1e-3) / 1e9,
+                    # algorithmic HBM bytes: raw reads twice (both passes), records + ops rows twice, the text once
+                    "hbm_frac": (2 * raw_bytes + 2 * tn * (48 + stride) + tbytes) / (text_ms * 1e-3) / 1e9 / (
+                        float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0),
+                    "api": "treat_b200_text_device: k_text sizes + scan + k_text write for reads, names, records and ops rows in HBM "
+                           "(includes the one host synchronisation that returns the text size)"}
+        del d_text, d_names, d_noff, d_toff
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak, hbm_src = 6650.0, "fallback"
     if os.path.exists(peaks_path):
@@ -567,6 +593,7 @@ def run_ours(args):
             # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
             "value_dp_every_read": world * N / ((pack_ms + align_ms) * 1e-3),
             "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
+            "text_device": text_dev,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
