@@ -82,10 +82,45 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, pci_bus_id=None):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml, self.h, self.stop_flag, self.thread, self.samples = None, None, False, None, []
+        try:  # NVML in-process: a sample costs microseconds, so even a 10 ms timed region gets several
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append((n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM), n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM),
+                                     int(reasons(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def sample_now(self):
+        """One sample from the calling thread (used right after the last step is enqueued, while the GPU still runs)."""
+        if not self.nvml:
+            return
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.samples.append((n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM), n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM),
+                                 int(reasons(self.h))))
+        except Exception:
+            pass
 
     def start(self):
+        if self.nvml:
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -99,6 +134,14 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            seen = sorted(k for k, b in bits.items() if any(smp[2] & b for smp in self.samples))
+            sm = [smp[0] for smp in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smp[1] for smp in self.samples)) if sm else None,
+                    "reasons": seen, "samples": len(sm), "source": "NVML, sampled during the timed region"}
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -303,7 +346,12 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        bus = None
+    sampler = ClockSampler(local, bus)
     sampler.start()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -312,6 +360,7 @@ def run_ours(args):
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
+    sampler.sample_now()  # the queue is still draining: a sample inside the timed region even when it lasts milliseconds
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - l0
