@@ -321,6 +321,12 @@ int64_t treat_b200_simple_align(treat_b200_ctx *ctx, const uint8_t *s1, size_t l
 /* align.go:316-335 Alignment.MarshalBinary: 36-byte big-endian header + JuncSeq */
 int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *seq, size_t seq_len, uint8_t *out,
                                   size_t cap);
+/* The same on the device (`treat load`, cmd/treat/storage.go:758-770, with reads and records resident in HBM, e.g. after
+ * treat_b200_align_batch_device): d_blob_off[N + 1] and the blobs back to back in d_blob; *blob_bytes after one stream
+ * synchronisation; d_blob = NULL: sizing call. */
+int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off, const treat_b200_record *d_rec,
+                              uint64_t N, uint64_t *d_blob_off, uint8_t *d_blob, uint64_t blob_cap, uint64_t *blob_bytes,
+                              void *stream);
 /* align.go:295-314 Alignment.UnmarshalBinary: the fields MarshalBinary stores, back into a record (edit_stop ..
  * indel, read_count, junc_seq_len; the other fields are zero), Norm, and a pointer to the JuncSeq bytes inside the
  * blob.  ERR_INVALID when the blob is shorter than its header says (the reference panics there). */

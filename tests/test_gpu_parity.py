@@ -860,6 +860,42 @@ def test_load_and_mutant_rows_from_device_results(eng, tmp_path):
     assert got.count("\n") > 10
 
 
+def test_marshal_on_device(eng, tmp_path):
+    """`treat load` blobs (Alignment.MarshalBinary, align.go:316-335) built on the device == the host's marshal_batch == the
+    oracle's MarshalBinary, for reads with junction sequences, negative fields (offset 0, EditStop -1) and lower-case bases."""
+    import torch
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    N = 5000
+    seqs, off, rc = synth.reads(t, N, seed=synth.SEED_BASE + 91, p_trunc=0.05)
+    seqs = seqs.copy()
+    lo = int(off[10])
+    seqs[lo:int(off[400])] = np.frombuffer(seqs[lo:int(off[400])].tobytes().lower(), dtype=np.uint8)  # JuncSeq is upper-cased
+    max_len = int(np.diff(off.astype(np.int64)).max())
+    d_seqs = torch.from_numpy(seqs).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_rc = torch.from_numpy(rc.astype(np.int32)).cuda()
+    d_rec = torch.zeros(N * 48, dtype=torch.uint8, device="cuda")
+    d_boff = torch.zeros(N + 1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, cabi.NO_SUMMARY, d_rec.data_ptr(), 0, 0, st)
+    total = eng.marshal_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rec.data_ptr(), N, d_boff.data_ptr(), 0, 0, st)
+    d_blob = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    assert eng.marshal_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rec.data_ptr(), N, d_boff.data_ptr(), d_blob.data_ptr(), total, st) == total
+    torch.cuda.synchronize()
+    blob, boff = d_blob.cpu().numpy(), d_boff.cpu().numpy()
+    rec = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
+    hblob, hboff = T.marshal_batch(rec, seqs, off, threads=4)
+    assert np.array_equal(boff.astype(np.uint64), hboff) and np.array_equal(blob, hblob)
+    assert (rec["junc_seq_len"] > 0).sum() > 100
+    for i in list(range(0, N, 61)) + list(range(10, 60)):
+        f = O.NewFragment("r-%d" % rc[i], seqs[int(off[i]):int(off[i + 1])].tobytes().decode())
+        assert blob[int(boff[i]):int(boff[i + 1])].tobytes() == O.NewAlignment(f, om).MarshalBinary(), i
+    with pytest.raises(T.TreatError):
+        eng.marshal_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rec.data_ptr(), N, d_boff.data_ptr(), d_blob.data_ptr(), total - 1, st)
+
+
 def test_other_edit_base_is_isomorphic(eng, examples, tmp_path):
     """Swapping the letters A and T everywhere and editing on 'A' must give the same records: exercises
     the edit-base-dependent alphabet (codes for C, G, T; A stripped) against the oracle and itself."""

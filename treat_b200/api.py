@@ -532,6 +532,15 @@ class Aligner:
                                            d_text_off, d_text or None, text_cap, C.byref(total), stream or None), self._ctx)
         return total.value
 
+    def marshal_device(self, d_seqs: int, d_seq_off: int, d_rec: int, N: int, d_blob_off: int, d_blob: int = 0, blob_cap: int = 0,
+                       stream: int = 0) -> int:
+        """treat_b200_marshal_device on raw device pointers: Alignment.MarshalBinary for a batch; returns the size in bytes
+        (d_blob = 0: sizing call)."""
+        total = C.c_uint64()
+        check(lib().treat_b200_marshal_device(self._ctx, d_seqs, d_seq_off, d_rec, N, d_blob_off, d_blob or None, blob_cap,
+                                              C.byref(total), stream or None), self._ctx)
+        return total.value
+
     def fasta_text(self, data, flags: int = 0, tw: int = 80, out=None) -> Tuple[bytes, int]:
         """treat_b200_fasta_text: FASTA bytes -> the text `treat align -t ... -f ...` prints (parse, alignment and
         WriteTo on the GPU).  Returns (text, records); with `out` (a binary file object) the pieces are written there

@@ -1455,6 +1455,40 @@ int treat_b200_text_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
     return text_write(ctx, ctx->dev_slot, tp, d_text_off, d_text, st);
 }
 
+int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off, const treat_b200_record *d_rec,
+                              uint64_t N, uint64_t *d_blob_off, uint8_t *d_blob, uint64_t blob_cap, uint64_t *blob_bytes, void *stream)
+{
+    if (!ctx || !blob_bytes || (N && (!d_seqs || !d_seq_off || !d_rec || !d_blob_off))) return TREAT_B200_ERR_INVALID;
+    *blob_bytes = 0;
+    if (N == 0) return TREAT_B200_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    Slot &s = ctx->dev_slot;
+    CK(ctx, s.tlen.reserve(N * 4));
+    CK(ctx, s.tsums.reserve((N / 2048 + 4) * 8));
+    if (!s.h_text_total) CK(ctx, cudaMallocHost((void **)&s.h_text_total, 16));
+    int e = launch_marshal_sizes(d_rec, N, (uint32_t *)s.tlen.p, ctx->num_sms, st);
+    if (!e) e = launch_scan_u32((const uint32_t *)s.tlen.p, N, d_blob_off, (uint64_t *)s.tsums.p, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_marshal launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches += 4;
+    PEEK(ctx, s.h_text_total, d_blob_off + N, 8, st);
+    CK(ctx, cudaStreamSynchronize(st));
+    *blob_bytes = *s.h_text_total;
+    if (!d_blob) return TREAT_B200_OK;  // sizing call
+    if (*blob_bytes > blob_cap) return fail(ctx, TREAT_B200_ERR_INVALID, "marshal: blob buffer too small (call with d_blob = NULL to size)");
+    MarshalParams mp{};
+    mp.seqs = d_seqs;
+    mp.off = d_seq_off;
+    mp.rec = d_rec;
+    mp.N = N;
+    mp.blob_off = d_blob_off;
+    mp.blob = d_blob;
+    e = launch_marshal_write(mp, ctx->num_sms, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_marshal launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
+    return TREAT_B200_OK;
+}
+
 // `treat align -t templates.fa -f reads.fa` (cmd/treat/align.go:96-121) as one streaming call: the file is cut at record
 // starts, every piece is indexed, aligned and formatted on the device, and its text is handed to `sink` in file order
 // while the next piece is being processed (two pieces in flight).

@@ -141,6 +141,19 @@ struct TextParams {
     uint32_t stage_cap, tmpl_in_smem, warp_bytes, col_cap;  // set by launch_text
 };
 int launch_text(TextParams &p, bool write, int num_sms, int max_smem_optin, void *stream);
+// Alignment.MarshalBinary for a batch (text_kernel.cu)
+struct MarshalParams {
+    const uint8_t *seqs;         // raw reads, addressed like TextParams
+    const uint64_t *off;
+    uint64_t off_bias;
+    const uint64_t *begin;
+    const treat_b200_record *rec;
+    uint64_t N;
+    const uint64_t *blob_off;    // [N+1] exclusive scan of 36 + junc_seq_len
+    uint8_t *blob;
+};
+int launch_marshal_sizes(const treat_b200_record *d_rec, uint64_t N, uint32_t *d_blen, int num_sms, void *stream);
+int launch_marshal_write(const MarshalParams &p, int num_sms, void *stream);
 int configure_text_kernels(int max_smem_optin);
 
 // launchers (kernels.cu)

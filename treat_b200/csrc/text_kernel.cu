@@ -315,6 +315,74 @@ __global__ void __launch_bounds__(kTextWarps * 32) k_text(const __grid_constant_
     if (MODE == 0 && lane == 0 && gmax && p.gmax) atomicMax(p.gmax, gmax);
 }
 
+// ------------------------------------------------------------------------------------------
+// Alignment.MarshalBinary (align.go:316-335) for a batch: the blob `treat load` stores per read (cmd/treat/storage.go:
+// 758-770) -- 36-byte big-endian header (EditStop, JuncStart, JuncEnd, JuncLen, ReadCount, HasMutation, AltEditing,
+// Mismatches, Indel, Norm = 0.0, len(JuncSeq)) + JuncSeq, the upper-cased window of the raw read the record points at.
+// Sizes pass (36 + junc_seq_len), exclusive scan, write pass: eight lanes per read, one big-endian word each for the
+// header, then the JuncSeq bytes in steps of eight.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_marshal_sizes(const treat_b200_record *rec, uint64_t N, uint32_t *blen)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x)
+        blen[i] = 36u + rec[i].junc_seq_len;
+}
+
+__global__ void __launch_bounds__(256) k_marshal_write(const MarshalParams p)
+{
+    const uint32_t sub = threadIdx.x & 7u;  // lane within the group of eight that owns a read
+    const uint64_t groups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < p.N; r += groups) {
+        const treat_b200_record *rc = p.rec + r;
+        uint8_t *out = p.blob + p.blob_off[r];
+        const uint32_t jl = rc->junc_seq_len;
+        // header words 0..8: four int32, ReadCount, the four flag bytes (already in MarshalBinary order), Norm (two zero
+        // words), len(JuncSeq); lane `sub` writes word `sub`, lane 0 also word 8
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(rc);  // record bytes 0-23 = MarshalBinary field order
+        auto put_be = [&](uint32_t idx, uint32_t v) {
+            uint8_t *o = out + 4u * idx;
+            o[0] = (uint8_t)(v >> 24);
+            o[1] = (uint8_t)(v >> 16);
+            o[2] = (uint8_t)(v >> 8);
+            o[3] = (uint8_t)v;
+        };
+        if (sub < 5u) put_be(sub, w[sub]);
+        else if (sub == 5u) {  // HasMutation, AltEditing, Mismatches, Indel: single bytes, stored as they are
+            const uint32_t f = w[5];
+            out[20] = (uint8_t)f;
+            out[21] = (uint8_t)(f >> 8);
+            out[22] = (uint8_t)(f >> 16);
+            out[23] = (uint8_t)(f >> 24);
+        } else put_be(sub, 0u);  // words 6, 7: math.Float64bits(0.0)
+        if (sub == 0u) put_be(8u, jl);
+        const uint64_t b = p.begin ? p.begin[r] : p.off[r] - p.off_bias;
+        const uint8_t *src = p.seqs + b + rc->junc_seq_off;
+        for (uint32_t k = sub; k < jl; k += 8u) {
+            uint32_t v = src[k];
+            if (v >= 'a' && v <= 'z') v -= 32u;
+            out[36u + k] = (uint8_t)v;
+        }
+    }
+}
+
+int launch_marshal_sizes(const treat_b200_record *d_rec, uint64_t N, uint32_t *d_blen, int num_sms, void *stream)
+{
+    if (!N) return 0;
+    uint64_t blocks = (N + 255) / 256;
+    if (blocks > (uint64_t)num_sms * 8) blocks = (uint64_t)num_sms * 8;
+    k_marshal_sizes<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_rec, N, d_blen);
+    return (int)cudaGetLastError();
+}
+
+int launch_marshal_write(const MarshalParams &p, int num_sms, void *stream)
+{
+    if (!p.N) return 0;
+    uint64_t blocks = (p.N * 8 + 255) / 256;
+    if (blocks > (uint64_t)num_sms * 8) blocks = (uint64_t)num_sms * 8;
+    k_marshal_write<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
 size_t text_smem_bytes(const TextParams &p, int warps)
 {
     return (size_t)(2 * kTextMaxRows + 1) * 4 + (size_t)p.len_pad * 4 + (p.tmpl_in_smem ? (size_t)p.K * p.len_pad * 4 : 0) + 48 +
