@@ -49,6 +49,7 @@ struct DevBuf {
 // device buffers of one in-flight chunk
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaEvent_t h2d_done = nullptr;  // recorded behind the chunk's input copies: the next chunk's copies wait for it (see h2d_in_order)
     DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops, summary;
     DevBuf list;     // reads that need the DP (written by k_same_bases, read by the align kernels)
     DevBuf ops_idx;  // OPS_GAPPED_ONLY: read index of every compacted ops row
@@ -85,6 +86,7 @@ struct Slot {
         if (h_gap_rows) cudaFreeHost(h_gap_rows);
         if (h_gap_idx) cudaFreeHost(h_gap_idx);
         if (land) cudaFreeHost(land);
+        if (h2d_done) cudaEventDestroy(h2d_done);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -176,6 +178,22 @@ static int peek(treat_b200_ctx *ctx, void *h_dst, const void *d_src, uint32_t by
         int _r = peek((ctx), (dst), (src), (bytes), (st)); \
         if (_r) return _r;                                 \
     } while (0)
+
+// Input copies of different chunks sit on different streams, and the copy engines serve concurrent H2D copies side by
+// side: each then takes as long as all of them together, so every chunk's kernels start late and the last chunks all
+// finish copying at the very end, with their kernels and result copies still to come.  Chaining the copies with events
+// keeps the bus just as busy but delivers the chunks one after the other.
+static int h2d_in_order_begin(treat_b200_ctx *ctx, Slot &s, const Slot *prev)
+{
+    if (!s.h2d_done) CK(ctx, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+    if (prev && prev->h2d_done) CK(ctx, cudaStreamWaitEvent(s.stream, prev->h2d_done, 0));
+    return TREAT_B200_OK;
+}
+static int h2d_in_order_end(treat_b200_ctx *ctx, Slot &s)
+{
+    CK(ctx, cudaEventRecord(s.h2d_done, s.stream));
+    return TREAT_B200_OK;
+}
 
 extern "C" {
 
@@ -1242,8 +1260,10 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
         // stage A: piece t
         if (t < npieces) {
             Slot &s = ctx->fslot[t % kFastaSlots];
+            if ((rc = h2d_in_order_begin(ctx, s, t ? &ctx->fslot[(t - 1) % kFastaSlots] : nullptr))) break;
             rc = fasta_stage_copy_count(ctx, ctx->fasta_slot[t % kFastaSlots], fasta + cut[t], cut[t + 1] - cut[t], s.stream);
             if (rc) break;
+            if ((rc = h2d_in_order_end(ctx, s))) break;
         }
         tA += now() - t0;
         const double sA = now() - t_begin;
