@@ -157,6 +157,15 @@ def test_fuzz_vs_oracle(eng, examples, tname, base):
             assert alns[i].WriteTo(tf, tm, 80) == oa.WriteTo(of, om, 80)
             assert alns[i].JuncSeq == oa.JuncSeq
             assert alns[i].MarshalBinary() == oa.MarshalBinary()
+    # the same reads as a FASTA file through the device-side FASTA parse + WriteTo: every byte of `treat align`'s output
+    # (the empty sequence is written as a header-only record)
+    text = "".join(">%s\n%s\n" % (rid, sq) if sq else ">%s\n" % rid for rid, sq in recs).encode()
+    eng.SetTemplate(tm)
+    got, n = eng.fasta_text(text)
+    assert n == len(recs)
+    want = "".join(O.NewAlignment(O.NewFragment(rid, sq, O.FORWARD, base), om).WriteTo(O.NewFragment(rid, sq, O.FORWARD, base), om, 80)
+                   for rid, sq in recs)
+    assert got.decode("latin-1") == want
 
 
 def _batch_vs_oracle(eng, t, tmp_path, N, seed, p_trunc=0.0, offset=0, exclude=False, nthreads=8):
