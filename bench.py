@@ -616,6 +616,8 @@ def run_ours(args):
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "gcups": g,
                "sample": "first %d reads of the workload, %d threads, %.1f s; CPU port of the Go path (oracle/treat_oracle.c), "
                          "lean mode: one DP per read, record + ops" % (sample, threads, secs)}
+        v1, g1, s1 = cpu_sample_rate(t, p_trunc, seed, min(sample, 20000), 1)
+        cpu["single_thread"] = {"value": v1, "unit": UNIT, "gcups": g1, "sample": "first %d reads, 1 thread, %.1f s, lean mode" % (min(sample, 20000), s1)}
         # what `treat align` itself does per read: NewAlignment + WriteTo (a second DP and the text)
         from treat_b200 import synth as _synth
         O, om = oracle_template(t)

@@ -2,7 +2,7 @@
 the GPU path against the CPU oracle on ALL reads, and the `treat align` text (Alignment.WriteTo on the device, through
 treat_b200_fasta_text) byte for byte on the first --text-reads of them.  Test infrastructure: uses oracle/.
 
-    python tools/parity_full.py --reads 10000000 --text-reads 1000000 --out gpurun_out/parity_full.json
+    python tests/parity_full.py --reads 10000000 --text-reads 1000000 --out gpurun_out/parity_full.json
 """
 import argparse
 import json
@@ -14,7 +14,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # helpers
 
 
 def main():

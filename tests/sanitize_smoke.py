@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small run of every kernel variant for compute-sanitizer (memcheck / racecheck / synccheck):
-    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+    compute-sanitizer --tool memcheck python tests/sanitize_smoke.py
 Checks results against the oracle as it goes (test tooling)."""
 import os
 import sys
