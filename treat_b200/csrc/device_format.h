@@ -1,4 +1,4 @@
-// device_format.h -- parameter blocks shared by the kernels (kernels.cu) and the C ABI (capi.cu).
+// device_format.h -- parameter blocks shared by the kernels (*_kernel.cu) and the C ABI (capi.cu).
 #pragma once
 #include <cstdint>
 
@@ -156,7 +156,7 @@ int launch_marshal_sizes(const treat_b200_record *d_rec, uint64_t N, uint32_t *d
 int launch_marshal_write(const MarshalParams &p, int num_sms, void *stream);
 int configure_text_kernels(int max_smem_optin);
 
-// launchers (kernels.cu)
+// launchers (pack_kernel.cu, align_kernel.cu)
 int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
 int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
 // K2s: finishes the reads marked kFlagSameBases without a DP and lists the others (p is the plan_align'ed block)
