@@ -560,12 +560,13 @@ def run_ours(args):
             seen[0] += q.n
             return 0
         stream_ms = {}
-        for name, fn in (("count", sink_count), ("copy_records", sink_copy)):
+        for name, fn in (("count", sink_count), ("copy_records", sink_copy), ("blobs", sink_count)):
             cb = cabi.FASTA_SINK(fn)
             tot = C.c_uint64()
+            sflags = flags | cabi.WANT_BLOBS if name == "blobs" else flags  # `treat load`: MarshalBinary blobs built on the device
 
             def step_stream():
-                cabi.check(cabi.lib().treat_b200_fasta_stream(eng._ctx, h_txt.ctypes.data, h_txt.size, flags, 0, cb, None, C.byref(tot)), eng._ctx)
+                cabi.check(cabi.lib().treat_b200_fasta_stream(eng._ctx, h_txt.ctypes.data, h_txt.size, sflags, 0, cb, None, C.byref(tot)), eng._ctx)
             seen[0] = 0
             step_stream()
             assert tot.value == N and seen[0] == N
@@ -600,6 +601,7 @@ def run_ours(args):
         fasta = {"value": N / fa_s, "unit": UNIT, "ms_per_step": 1e3 * fa_s, "file_bytes": len(text), "write_text": write_text,
                  "stream": {"value": N / (stream_ms["count"] * 1e-3), "unit": UNIT, "ms_per_step": stream_ms["count"],
                             "ms_per_step_sink_copies_records": stream_ms["copy_records"],
+                            "ms_per_step_with_marshal_blobs": stream_ms["blobs"],
                             "api": "treat_b200_fasta_stream: ~32 MB pieces cut at record starts, copy / index / align / deliver overlapped"},
                  "api": "treat_b200_fasta_upload + treat_b200_fasta_align: file bytes in pinned host memory -> records, "
                         "gapped ops rows, id index, read counts (parse, NewFragment, NewAlignment on the GPU)",

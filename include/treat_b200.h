@@ -51,6 +51,7 @@ extern "C" {
                                             (record.indel != 0); the row of any other read would be all zero (m = n
                                             match columns) and is unspecified (left untouched, or zeroed), so D2H traffic
                                             can shrink to the gapped reads */
+#define TREAT_B200_WANT_BLOBS 0x200u /* treat_b200_fasta_stream only: also hand the sink every record's MarshalBinary blob (`treat load`) */
 #define TREAT_B200_HEATMAP 0x100u /* also accumulate the ESS x junction-length heat map (treat_b200_get_heatmap) */
 #define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
                                            under the template that is current now, so reads it marked as equal to the template
@@ -284,6 +285,10 @@ typedef struct treat_b200_fasta_piece {
     uint64_t n_ops_rows;
     uint32_t ops_stride;
     uint32_t seq_in_place;         /* 1: every sequence of the piece is file[seq_off, seq_off + seq_len) (no line break inside) */
+    /* TREAT_B200_WANT_BLOBS: Alignment.MarshalBinary of every record (align.go:316-335), built on the device: blob i =
+     * blob[blob_off[i], blob_off[i+1]) -- what cmd/treat/storage.go:758-770 puts into the alignment bucket; else NULL */
+    const uint8_t *blob;
+    const uint64_t *blob_off;      /* [n + 1] */
 } treat_b200_fasta_piece;
 typedef int (*treat_b200_fasta_sink)(void *user, const treat_b200_fasta_piece *piece);
 /* ops_stride: bytes per ops row when every record gets one (0: chosen per piece from its longest read, see piece->ops_stride) */

@@ -445,6 +445,17 @@ def _fasta_device_vs_host(eng, tmp_path, text: bytes, tag: str, flags=None, tm=N
                 for p in pieces:
                     w = min(p["ops_stride"], ops.shape[1])
                     assert np.array_equal(p["ops"][:, :w], ops[p["first_record"]:p["first_record"] + p["n"], :w]), tag
+    # `treat load` in one call: the sink also gets every record's MarshalBinary blob, built on the device
+    pieces_b, total_b = eng.stream_fasta(text, flags | cabi.WANT_BLOBS)
+    assert total_b == n
+    if n:
+        hblob, hboff = T.marshal_batch(rec, host.seqs, host.offsets, threads=2)
+        assert np.array_equal(np.concatenate([p["blob"] for p in pieces_b]), hblob), tag
+        at = 0
+        for p in pieces_b:
+            assert np.array_equal(p["blob_off"] + np.uint64(at), hboff[p["first_record"]:p["first_record"] + p["n"] + 1]), tag
+            at += int(p["blob_off"][-1])
+        assert np.array_equal(np.concatenate([p["rec"] for p in pieces_b]), rec), tag
     return n
 
 

@@ -516,6 +516,10 @@ class Aligner:
                 d["ops"] = np.zeros((0, q.ops_stride), dtype=np.uint8)
             if q.ops_index:
                 d["ops_index"] = arr(q.ops_index, q.n_ops_rows, np.uint32)
+            d["blob_off"] = d["blob"] = None
+            if q.blob_off:
+                d["blob_off"] = arr(q.blob_off, n + 1, np.uint64)
+                d["blob"] = arr(q.blob, int(d["blob_off"][-1]), np.uint8)
             pieces.append(d)
             return 0
         cb = FASTA_SINK(sink)

@@ -17,7 +17,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TOO_LONG, ERR_NO_TEMPLATE, ERR_NO_DEVICE, ERR_TEMPLATE, ERR_IO = range(-1, -9, -1)
 FORWARD, REVERSE = 1, -1
 EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY, ONE_READ_PER_WARP, FULL_TRACEBACK_STORE = 0x1, 0x2, 0x4, 0x8, 0x10
-DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY, HEATMAP = 0x20, 0x40, 0x80, 0x100
+DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY, HEATMAP, WANT_BLOBS = 0x20, 0x40, 0x80, 0x100, 0x200
 ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16
@@ -52,6 +52,7 @@ class FastaPiece(C.Structure):
         ("first_record", C.c_uint64), ("n", C.c_uint64), ("rec", C.c_void_p), ("id_off", C.c_void_p), ("seq_off", C.c_void_p),
         ("id_len", C.c_void_p), ("read_count", C.c_void_p), ("seq_len", C.c_void_p), ("ops", C.c_void_p), ("ops_index", C.c_void_p),
         ("n_ops_rows", C.c_uint64), ("ops_stride", C.c_uint32), ("seq_in_place", C.c_uint32),
+        ("blob", C.c_void_p), ("blob_off", C.c_void_p),
     ]
 
 

@@ -1179,6 +1179,9 @@ int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_recor
     return rc;
 }
 
+static int fasta_blobs_sizes(treat_b200_ctx *ctx, Slot &s, uint64_t n);
+static int fasta_blobs_write(treat_b200_ctx *ctx, Slot &s, const FastaDev &fa, bool in_place, uint64_t n);
+
 // The same as one call that never holds the whole file on the device: the bytes are cut into pieces at record starts,
 // four pieces are in flight (copy + count, index, align, deliver), and every finished piece is handed to `sink` in file order.
 int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, uint32_t ops_stride,
@@ -1323,9 +1326,19 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
                     if ((rc = add_heatmap(ctx, flags, (const treat_b200_record *)s.rec.p, n, s.stream))) break;
                 }
             }
+            if (n && (flags & TREAT_B200_WANT_BLOBS)) {  // the records are final now: MarshalBinary for the piece
+                if ((rc = fasta_blobs_sizes(ctx, s, n))) break;
+                CK(ctx, cudaStreamSynchronize(s.stream));
+                if ((rc = fasta_blobs_write(ctx, s, fa, pc[k].in_place, n))) break;
+                CK(ctx, cudaStreamSynchronize(s.stream));
+            }
             if (n) {
                 treat_b200_fasta_piece out;
                 memset(&out, 0, sizeof out);
+                if (flags & TREAT_B200_WANT_BLOBS) {
+                    out.blob_off = (const uint64_t *)s.tland;
+                    out.blob = s.tland + (n + 1) * 8;
+                }
                 uint8_t *l = s.land;
                 out.first_record = pc[k].first;
                 out.n = n;
@@ -1473,6 +1486,51 @@ int treat_b200_text_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
     if (!d_text) return TREAT_B200_OK;  // sizing call
     if (*text_bytes > text_cap) return fail(ctx, TREAT_B200_ERR_INVALID, "text: text buffer too small (call with d_text = NULL to size)");
     return text_write(ctx, ctx->dev_slot, tp, d_text_off, d_text, st);
+}
+
+// MarshalBinary blobs of the records in s.rec for the reads of an indexed FASTA piece: sizes + scan (total lands in
+// s.h_text_total after a stream sync), then the write into s.text and the copy of offsets + blobs to the pinned s.tland
+static int fasta_blobs_sizes(treat_b200_ctx *ctx, Slot &s, uint64_t n)
+{
+    cudaStream_t st = s.stream;
+    CK(ctx, s.tlen.reserve(n * 4));
+    CK(ctx, s.tsums.reserve((n / 2048 + 4) * 8));
+    CK(ctx, s.text_off.reserve((n + 1) * 8));
+    if (!s.h_text_total) CK(ctx, cudaMallocHost((void **)&s.h_text_total, 16));
+    int e = launch_marshal_sizes((const treat_b200_record *)s.rec.p, n, (uint32_t *)s.tlen.p, ctx->num_sms, st);
+    if (!e) e = launch_scan_u32((const uint32_t *)s.tlen.p, n, (uint64_t *)s.text_off.p, (uint64_t *)s.tsums.p, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_marshal launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches += 4;
+    PEEK(ctx, s.h_text_total, (uint64_t *)s.text_off.p + n, 8, st);
+    return TREAT_B200_OK;
+}
+static int fasta_blobs_write(treat_b200_ctx *ctx, Slot &s, const FastaDev &fa, bool in_place, uint64_t n)
+{
+    cudaStream_t st = s.stream;
+    const uint64_t total = *s.h_text_total, off_bytes = (n + 1) * 8;
+    CK(ctx, s.text.reserve(total + 16));
+    if (off_bytes + total > s.tland_cap) {
+        if (s.tland) cudaFreeHost(s.tland);
+        s.tland = nullptr;
+        s.tland_cap = 0;
+        const size_t want = off_bytes + total + (off_bytes + total) / 4 + 4096;
+        CK(ctx, cudaMallocHost((void **)&s.tland, want));
+        s.tland_cap = want;
+    }
+    MarshalParams mp{};
+    mp.seqs = in_place ? (const uint8_t *)fa.file.p : (const uint8_t *)fa.seqs.p;
+    if (in_place) mp.begin = (const uint64_t *)fa.seq_begin.p;
+    else mp.off = (const uint64_t *)fa.seq_off.p;
+    mp.rec = (const treat_b200_record *)s.rec.p;
+    mp.N = n;
+    mp.blob_off = (const uint64_t *)s.text_off.p;
+    mp.blob = (uint8_t *)s.text.p;
+    int e = launch_marshal_write(mp, ctx->num_sms, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_marshal launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(s.tland, s.text_off.p, off_bytes, cudaMemcpyDeviceToHost, st));
+    if (total) CK(ctx, cudaMemcpyAsync(s.tland + off_bytes, s.text.p, total, cudaMemcpyDeviceToHost, st));
+    return TREAT_B200_OK;
 }
 
 int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off, const treat_b200_record *d_rec,
