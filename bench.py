@@ -448,12 +448,19 @@ def run_ours(args):
             return (tr["dram_read_bytes_per_read"] + tr["dram_write_bytes_per_read"]) * N if args.workload == "rps12" else None
         except Exception:
             return None
+    def ncu_facts(kernel):
+        # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r01_*_ncu_full.md)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+            return {k: v for k, v in tr.items() if not k.startswith("dram_")}
+        except Exception:
+            return None
     # k_pack16: raw characters + offsets in; 2-bit bases, counts, n / flags / raw_len out
     pack_bytes = float(len(seqs) + N * 8 + ((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4))
     roofline = {"bound": "hbm", "kernel": "k_pack16 (NewFragment for the batch; largest share of a step)",
                 "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                "bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms, "traffic": ncu_traffic("k_pack16"),
+                "bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms, "traffic": ncu_traffic("k_pack16"), "ncu": ncu_facts("k_pack16"),
                 "note": "instruction-issue bound (about 500 warp instructions per read), not DRAM bound: see profiles/"}
     # k_align2 on every read: algorithmic integer ops of the DP
     alg_bytes = float(((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4 + 4) + N * 48 + ((t.m + n_arr + 3) // 4).sum())
@@ -463,7 +470,7 @@ def run_ours(args):
                    "unit": "Tiop/s", "frac": int_ops / (align_ms * 1e-3) / int_peak,
                    "peak_source": "measured live: k_int32_peak (dependent-free add+max, all SMs)",
                    "ops_per_cell": INT_OPS_PER_CELL, "cells_per_launch": cells_per_step, "ms_per_launch": align_ms,
-                   "gcups": cells_per_step / (align_ms * 1e-3) / 1e9, "traffic": ncu_traffic("k_align2"),
+                   "gcups": cells_per_step / (align_ms * 1e-3) / 1e9, "traffic": ncu_traffic("k_align2"), "ncu": ncu_facts("k_align2"),
                    "hbm_frac": alg_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak,
                    "note": "frac is against a SCALAR 8-op-per-cell roofline; the kernel needs ~1.5 instructions per cell "
                            "(gap-free transform, two reads per register, IMAD-packed direction digits), so frac can exceed 1"}
