@@ -120,8 +120,16 @@ const char *treat_b200_last_error(const treat_b200_ctx *ctx);
 /* device = CUDA ordinal (one process per GPU: pass LOCAL_RANK) */
 int treat_b200_create(int device, treat_b200_ctx **out);
 void treat_b200_destroy(treat_b200_ctx *ctx);
-/* pinned host memory for the batch buffers (any host pointer works; pinned is faster) */
+/* Pinned host memory for the batch buffers.  Any host pointer works: treat_b200_align_batch moves pageable buffers (Go
+ * slices, numpy arrays) through pinned staging buffers of its own with a few host copy threads (TREAT_B200_COPY_THREADS,
+ * default 5), because the driver would stage such copies itself and block the caller for their whole duration.  Measured
+ * on one B200 for 1 M RPS12 reads: 6.2 ms from / to pinned buffers, 6.4 ms with pageable outputs, 13.7 ms with pageable
+ * inputs and outputs (host memcpy bound; 35.7 ms without the staging).  For the full rate allocate the input buffers once
+ * with treat_b200_host_alloc and reuse them, or pin long-lived buffers of your own in place with treat_b200_host_register
+ * (page-locking costs milliseconds per 100 MB: do it once, not per call). */
 int treat_b200_host_alloc(void **out, size_t bytes);
+int treat_b200_host_register(void *p, size_t bytes);
+int treat_b200_host_unregister(void *p);
 void treat_b200_host_free(void *p);
 
 /* ---- template: replaces treat.NewTemplate / Template.SetOffset state (template.go:96-161) ----

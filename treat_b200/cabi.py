@@ -68,6 +68,8 @@ SIGNATURES = {
     "treat_b200_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "treat_b200_destroy": (None, [_P]),
     "treat_b200_host_alloc": (C.c_int, [C.POINTER(_P), _SZ]),
+    "treat_b200_host_register": (C.c_int, [_P, _SZ]),
+    "treat_b200_host_unregister": (C.c_int, [_P]),
     "treat_b200_host_free": (None, [_P]),
     "treat_b200_set_template": (C.c_int, [_P, _U8P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, C.c_uint32, C.c_int32, C.c_uint8]),
     "treat_b200_use_template": (C.c_int, [_P, _P]),

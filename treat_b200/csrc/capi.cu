@@ -8,7 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_format.h"
@@ -46,6 +49,77 @@ struct DevBuf {
     }
 };
 
+// Host threads that copy between the caller's pageable buffers and pinned staging buffers (see stage_in / unstage in
+// treat_b200_align_batch): one memcpy runs at 10 GB/s or so, a handful of them keep up with the PCIe link.
+struct CopyPool {
+    struct Job {
+        uint8_t *dst = nullptr;
+        const uint8_t *src = nullptr;
+        size_t n = 0;
+    };
+    std::vector<std::thread> th;
+    std::vector<Job> job;
+    std::mutex m;
+    std::condition_variable cv, done;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    void start(int n)
+    {
+        if (!th.empty() || n < 1) return;
+        job.resize((size_t)n);
+        for (int i = 0; i < n; i++)
+            th.emplace_back([this, i] {
+                uint64_t seen = 0;
+                for (;;) {
+                    Job j;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&] { return stop || gen != seen; });
+                        if (stop) return;
+                        seen = gen;
+                        j = job[(size_t)i];
+                    }
+                    if (j.n) memcpy(j.dst, j.src, j.n);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) done.notify_one();
+                    }
+                }
+            });
+    }
+    void copy(void *dst, const void *src, size_t n)
+    {
+        if (th.empty() || n < (1u << 20)) {
+            if (n) memcpy(dst, src, n);
+            return;
+        }
+        const size_t parts = th.size() + 1, each = ((n + parts - 1) / parts + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (size_t i = 0; i < th.size(); i++) {
+                const size_t lo = std::min(n, (i + 1) * each), hi = std::min(n, (i + 2) * each);
+                job[i] = Job{(uint8_t *)dst + lo, (const uint8_t *)src + lo, hi - lo};
+            }
+            pending = (int)th.size();
+            gen++;
+        }
+        cv.notify_all();
+        memcpy(dst, src, std::min(n, each));
+        std::unique_lock<std::mutex> lk(m);
+        done.wait(lk, [&] { return pending == 0; });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+};
+
 // device buffers of one in-flight chunk
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -60,8 +134,11 @@ struct Slot {
     uint32_t gap_head = 0;     // rows copied ahead of knowing how many there are
     bool scatter = false;      // the chunk's gapped-read count (and compacted rows) still have to be consumed on the host
     bool sparse = false;       // this chunk returns only the gapped reads' ops rows, compacted
-    uint8_t *land = nullptr;   // treat_b200_fasta_stream: pinned landing buffer of a piece's results
+    uint8_t *land = nullptr;   // pinned landing buffer of a piece's / chunk's results (fasta_stream; pageable outputs of align_batch)
     size_t land_cap = 0;
+    uint8_t *h_in = nullptr;   // pinned staging buffer of a chunk's inputs when the caller's buffers are pageable
+    size_t h_in_cap = 0;
+    bool unstage = false;      // the chunk's results sit in `land` and still have to be copied to the caller's buffers
     DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
     DevBuf text, text_off, tlen, gtot, tsums;  // Alignment.WriteTo on the device (treat_b200_text_device / _fasta_text)
     uint8_t *tland = nullptr;                  // pinned landing buffer of a piece's text
@@ -86,6 +163,7 @@ struct Slot {
         if (h_gap_rows) cudaFreeHost(h_gap_rows);
         if (h_gap_idx) cudaFreeHost(h_gap_idx);
         if (land) cudaFreeHost(land);
+        if (h_in) cudaFreeHost(h_in);
         if (h2d_done) cudaEventDestroy(h2d_done);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -143,6 +221,7 @@ struct treat_b200_ctx {
     Slot slot[kSlots];
     // scratch for the device-resident entry point
     Slot dev_slot;
+    CopyPool copy_pool;           // host copy threads, started on the first call that brings pageable buffers
     FastaDev fasta;               // treat_b200_fasta_upload / treat_b200_fasta_align
     FastaDev fasta_slot[kFastaSlots];  // pieces in flight of treat_b200_fasta_stream
     Slot fslot[kFastaSlots];
@@ -285,6 +364,24 @@ int treat_b200_host_alloc(void **out, size_t bytes)
 void treat_b200_host_free(void *p)
 {
     if (p) cudaFreeHost(p);
+}
+int treat_b200_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return TREAT_B200_ERR_INVALID;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return TREAT_B200_ERR_CUDA;
+    }
+    return TREAT_B200_OK;
+}
+int treat_b200_host_unregister(void *p)
+{
+    if (!p) return TREAT_B200_ERR_INVALID;
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return TREAT_B200_ERR_CUDA;
+    }
+    return TREAT_B200_OK;
 }
 
 int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m, const uint32_t *edit_site, int32_t K,
@@ -785,8 +882,37 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     const bool sparse_ok = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
     for (int i = 0; i < kSlots; i++) {
         if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
-        ctx->slot[i].pending = ctx->slot[i].scatter = false;  // nothing carries over from a call that failed half-way
+        ctx->slot[i].pending = ctx->slot[i].scatter = ctx->slot[i].unstage = false;  // nothing carries over from a call that failed half-way
     }
+    // Pageable caller buffers (a cgo caller's Go slices, numpy arrays): cudaMemcpyAsync would stage them inside the driver
+    // and block this thread, i.e. no overlap at all (35.7 instead of 6.2 ms per 1M reads).  Such buffers go through pinned
+    // staging buffers of the slot instead, filled / emptied by a few host copy threads.
+    auto pageable = [](const void *p) {
+        if (!p) return false;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return true;
+        }
+        return at.type == cudaMemoryTypeUnregistered;
+    };
+    static const bool no_staging = getenv("TREAT_B200_NO_STAGING") != nullptr;
+    const bool stage_in = !no_staging && (pageable(seqs) || pageable(seq_off) || pageable(read_count));
+    const bool stage_out = !no_staging && (pageable(rec) || (want_ops && pageable(ops)));
+    if (stage_in || stage_out) {
+        static const int copy_threads = getenv("TREAT_B200_COPY_THREADS") ? std::max(0, atoi(getenv("TREAT_B200_COPY_THREADS")))
+                                                                         : (int)std::min(5u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        ctx->copy_pool.start(copy_threads);
+    }
+    auto reserve_pinned = [&](uint8_t *&buf, size_t &cap, size_t need) -> int {
+        if (need <= cap) return TREAT_B200_OK;
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr;
+        cap = 0;
+        CK(ctx, cudaMallocHost((void **)&buf, need + need / 4 + 4096));
+        cap = need + need / 4 + 4096;
+        return TREAT_B200_OK;
+    };
 
     int rc = TREAT_B200_OK;
     uint64_t chunk_idx = 0;
@@ -802,12 +928,21 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
 
     // copy a finished chunk's results to the caller's buffers (async on the slot stream)
     auto copy_out = [&](Slot &s) -> int {
-        CK(ctx, cudaMemcpyAsync(rec + s.c0, s.rec.p, s.cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, s.stream));
-        // only the bytes the batch can use cross the bus: rows of dev_stride <= ops_stride bytes
         const bool sparse = s.sparse;
-        if (want_ops && !sparse)
-            CK(ctx, cudaMemcpy2DAsync(ops + s.c0 * (size_t)ops_stride, ops_stride, s.ops.p, s.dev_stride, s.dev_stride, s.cn,
-                                      cudaMemcpyDeviceToHost, s.stream));
+        if (stage_out) {  // into the slot's pinned landing buffer; unstage_out() moves it on once the stream is idle
+            const size_t rb = s.cn * sizeof(treat_b200_record), ob = want_ops && !sparse ? s.cn * (size_t)s.dev_stride : 0;
+            int r = reserve_pinned(s.land, s.land_cap, rb + ob);
+            if (r) return r;
+            CK(ctx, cudaMemcpyAsync(s.land, s.rec.p, rb, cudaMemcpyDeviceToHost, s.stream));
+            if (ob) CK(ctx, cudaMemcpyAsync(s.land + rb, s.ops.p, ob, cudaMemcpyDeviceToHost, s.stream));
+            s.unstage = true;
+        } else {
+            CK(ctx, cudaMemcpyAsync(rec + s.c0, s.rec.p, s.cn * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, s.stream));
+            // only the bytes the batch can use cross the bus: rows of dev_stride <= ops_stride bytes
+            if (want_ops && !sparse)
+                CK(ctx, cudaMemcpy2DAsync(ops + s.c0 * (size_t)ops_stride, ops_stride, s.ops.p, s.dev_stride, s.dev_stride, s.cn,
+                                          cudaMemcpyDeviceToHost, s.stream));
+        }
         if (sparse) {
             // the number of gapped reads is only known on the device: copy a guess now, the rest (if any) in place_rows
             const uint32_t head = (uint32_t)std::min<uint64_t>(s.cn, std::max<uint32_t>(4096u, 2u * ctx->gap_hint));
@@ -820,6 +955,23 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         if (want_ops) {  // the number of gapped reads of the chunk, for place_rows and for the next chunks' choice
             CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, s.stream));
             s.scatter = true;
+        }
+        return TREAT_B200_OK;
+    };
+    // pageable outputs: the chunk's records (and full ops rows) from the landing buffer to the caller (stream idle)
+    auto unstage_out = [&](Slot &s) -> int {
+        if (!s.unstage) return TREAT_B200_OK;
+        CK(ctx, cudaStreamSynchronize(s.stream));
+        s.unstage = false;
+        const size_t rb = s.cn * sizeof(treat_b200_record);
+        ctx->copy_pool.copy(rec + s.c0, s.land, rb);
+        if (want_ops && !s.sparse) {
+            if (s.dev_stride == ops_stride) {
+                ctx->copy_pool.copy(ops + s.c0 * (size_t)ops_stride, s.land + rb, s.cn * (size_t)ops_stride);
+            } else {
+                for (uint64_t i = 0; i < s.cn; i++)
+                    memcpy(ops + (s.c0 + i) * (size_t)ops_stride, s.land + rb + i * (size_t)s.dev_stride, s.dev_stride);
+            }
         }
         return TREAT_B200_OK;
     };
@@ -899,6 +1051,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         double t0 = now();
         CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk (incl. its D2H) is done
         if ((rc = settle(s))) break;
+        if ((rc = unstage_out(s))) break;
         double t1 = now();
         t_wait_slot += t1 - t0;
         const uint64_t b0 = seq_off[c0], b1 = seq_off[c0 + cn];
@@ -917,9 +1070,22 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         CK(ctx, s.off.reserve((cn + 1) * 8));
         CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
         if (read_count) CK(ctx, s.rc.reserve(cn * 4));
-        if (b1 > b0) CK(ctx, cudaMemcpyAsync(s.seqs.p, seqs + b0, b1 - b0, cudaMemcpyHostToDevice, st));
-        CK(ctx, cudaMemcpyAsync(s.off.p, seq_off + c0, (cn + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (read_count) CK(ctx, cudaMemcpyAsync(s.rc.p, read_count + c0, cn * 4, cudaMemcpyHostToDevice, st));
+        const uint8_t *src_seqs = seqs + b0;
+        const uint64_t *src_off = seq_off + c0;
+        const uint32_t *src_rc = read_count ? read_count + c0 : nullptr;
+        if (stage_in) {  // the slot's previous chunk is done, so its staging buffer is free
+            const size_t sb = (size_t)(b1 - b0), ob = (cn + 1) * 8, cb = read_count ? cn * 4 : 0, so = (sb + 15) & ~(size_t)15;
+            if ((rc = reserve_pinned(s.h_in, s.h_in_cap, so + ob + cb))) break;
+            ctx->copy_pool.copy(s.h_in, src_seqs, sb);
+            memcpy(s.h_in + so, src_off, ob);
+            if (cb) memcpy(s.h_in + so + ob, src_rc, cb);
+            src_seqs = s.h_in;
+            src_off = reinterpret_cast<const uint64_t *>(s.h_in + so);
+            src_rc = cb ? reinterpret_cast<const uint32_t *>(s.h_in + so + ob) : nullptr;
+        }
+        if (b1 > b0) CK(ctx, cudaMemcpyAsync(s.seqs.p, src_seqs, b1 - b0, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(s.off.p, src_off, (cn + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (read_count) CK(ctx, cudaMemcpyAsync(s.rc.p, src_rc, cn * 4, cudaMemcpyHostToDevice, st));
         s.c0 = c0;
         s.cn = cn;
         s.b0 = b0;
@@ -942,6 +1108,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     const double t_loop = now();
     for (int i = 0; i < kSlots; i++) {
         int r = settle(ctx->slot[i]);
+        if (r == TREAT_B200_OK && rc == TREAT_B200_OK) r = unstage_out(ctx->slot[i]);
         if (r && rc == TREAT_B200_OK) rc = r;
     }
     for (int i = 0; i < kSlots; i++) {
