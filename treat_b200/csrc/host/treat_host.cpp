@@ -734,21 +734,40 @@ bool CliAlignStream(treat_b200_ctx *ctx, const std::string &templatePath, const 
     Template tmpl;
     if (!NewTemplateFromFasta(templatePath, FORWARD, base, &tmpl, err)) return false;
     tmpl.SetOffset(editOffset);
-    std::ifstream in(fragmentPath, std::ios::binary);
-    if (!in) {
+    // the file's bytes go straight into pinned memory (the H2D copies then run by DMA beside the text coming back)
+    FILE *fp = fopen(fragmentPath.c_str(), "rb");
+    if (!fp) {
         *err = "open " + fragmentPath + ": no such file or directory";
         return false;
     }
-    const std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-    if (!eng.SetTemplate(tmpl, err)) return false;
-    const int rc = treat_b200_fasta_text(ctx, reinterpret_cast<const uint8_t *>(data.data()), data.size(), TREAT_B200_NO_SUMMARY, 80,
-                                         cli_text_sink, const_cast<CliEmit *>(&emit), nullptr);
-    if (rc != TREAT_B200_OK) {
-        *err = std::string(treat_b200_strerror(rc)) + ": " + treat_b200_last_error(ctx);
-        return false;
+    fseek(fp, 0, SEEK_END);
+    const long fsize = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    void *pinned = nullptr;
+    std::string fallback;
+    const uint8_t *data = nullptr;
+    size_t size = 0;
+    if (fsize > 0 && treat_b200_host_alloc(&pinned, (size_t)fsize) == TREAT_B200_OK) {
+        size = fread(pinned, 1, (size_t)fsize, fp);
+        data = static_cast<const uint8_t *>(pinned);
+    } else {  // not a regular file (a pipe), or no pinned memory: read it the plain way
+        char buf[1 << 16];
+        size_t k;
+        while ((k = fread(buf, 1, sizeof buf, fp)) > 0) fallback.append(buf, k);
+        data = reinterpret_cast<const uint8_t *>(fallback.data());
+        size = fallback.size();
     }
-    return true;
+    fclose(fp);
+    int rc = TREAT_B200_OK;
+    if (!eng.SetTemplate(tmpl, err)) rc = TREAT_B200_ERR_TEMPLATE;
+    else {
+        rc = treat_b200_fasta_text(ctx, data, size, TREAT_B200_NO_SUMMARY, 80, cli_text_sink, const_cast<CliEmit *>(&emit), nullptr);
+        if (rc != TREAT_B200_OK) *err = std::string(treat_b200_strerror(rc)) + ": " + treat_b200_last_error(ctx);
+    }
+    if (pinned) treat_b200_host_free(pinned);
+    return rc == TREAT_B200_OK;
 }
+
 
 bool CliAlign(treat_b200_ctx *ctx, const std::string &templatePath, const std::string &fragmentPath,
               const std::string &s1, const std::string &s2, const std::string &editBase, int editOffset,
