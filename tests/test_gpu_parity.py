@@ -548,6 +548,11 @@ def test_write_to_on_device(eng, examples, tmp_path):
     reads = [seqs[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(2500)]
     body = "".join(">r%d_%d\n%s\n" % (i, rc[i], r) for i, r in enumerate(reads))
     assert _text_vs_oracle(eng, tpath, body.encode(), tmp_path, "rps12") == 2500
+    # sharded the way ranks would take it (treat_b200_fasta_split): the slices' texts in rank order are the file's text
+    whole, _ = eng.fasta_text(body.encode())
+    cuts = T.fasta_split(body.encode(), 3)
+    assert len(cuts) == 4 and cuts[0] == 0 and cuts[-1] == len(body)
+    assert b"".join(eng.fasta_text(body.encode()[int(cuts[i]):int(cuts[i + 1])])[0] for i in range(3)) == whole
     odd = ">  spaced name_7  \r\n%s\r\n>wrapped-3\n%s\n%s\n\n>empty-1\n\n>lower_2\n%s\n>tt-1\nTTTTT\n>last-9\n%s" % (
         reads[0], reads[1][:100], reads[1][100:], reads[2].lower(), reads[3])
     assert _text_vs_oracle(eng, tpath, odd.encode(), tmp_path, "odd") == 6
