@@ -364,6 +364,9 @@ def run_ours(args):
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - l0
+    # the one collective of the path: the all-reduced "reads aligned" counter must hold every rank's reads of every step so far
+    reduced_reads = int(step_device()[14].item())
+    assert reduced_reads == world * N * (args.warmup + args.steps + 1), (reduced_reads, world, N)
     clocks = sampler.stop()
     rec_dev = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
     cells_per_step = float((rec_dev["n_bases"].astype(np.int64) * t.m).sum())
@@ -667,7 +670,7 @@ def run_ours(args):
             "value_dp_every_read": world * N / ((pack_ms + align_ms) * 1e-3),
             "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
             "text_device": text_dev,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "summary_reads_all_ranks": reduced_reads,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
