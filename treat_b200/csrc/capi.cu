@@ -139,6 +139,8 @@ struct Slot {
     uint8_t *h_in = nullptr;   // pinned staging buffer of a chunk's inputs when the caller's buffers are pageable
     size_t h_in_cap = 0;
     bool unstage = false;      // the chunk's results sit in `land` and still have to be copied to the caller's buffers
+    const uint64_t *doff = nullptr;  // the chunk's slice of the call's device copies of seq_off / read_count
+    const uint32_t *drc = nullptr;
     DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
     DevBuf text, text_off, tlen, gtot, tsums;  // Alignment.WriteTo on the device (treat_b200_text_device / _fasta_text)
     uint8_t *tland = nullptr;                  // pinned landing buffer of a piece's text
@@ -227,6 +229,10 @@ struct treat_b200_ctx {
     // scratch for the device-resident entry point
     Slot dev_slot;
     CopyPool copy_pool;           // host copy threads, started on the first call that brings pageable buffers
+    DevBuf d_off_all, d_rc_all;   // treat_b200_align_batch: the call's seq_off / read_count, copied once for all chunks
+    uint8_t *h_meta = nullptr;    //   their pinned staging buffer when the caller's arrays are pageable
+    size_t h_meta_cap = 0;
+    cudaEvent_t meta_done = nullptr;
     FastaDev fasta;               // treat_b200_fasta_upload / treat_b200_fasta_align
     FastaDev fasta_slot[kFastaSlots];  // pieces in flight of treat_b200_fasta_stream
     Slot fslot[kFastaSlots];
@@ -349,6 +355,10 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (ctx->d_heat) cudaFree(ctx->d_heat);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     for (Slot &sl : ctx->slot) sl.release();
+    ctx->d_off_all.release();
+    ctx->d_rc_all.release();
+    if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
+    if (ctx->meta_done) cudaEventDestroy(ctx->meta_done);
     ctx->dev_slot.release();
     ctx->fasta.release();
     for (FastaDev &f : ctx->fasta_slot) f.release();
@@ -919,6 +929,27 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         return TREAT_B200_OK;
     };
 
+    // seq_off and read_count of the whole call in two copies (instead of two small ones per chunk); the chunks' streams
+    // wait for them through an event
+    {
+        const size_t ob = (N + 1) * 8, cb = read_count ? N * 4 : 0;
+        CK(ctx, cudaStreamSynchronize(ctx->stream));  // a previous call's copies out of h_meta are done
+        CK(ctx, ctx->d_off_all.reserve(ob));
+        if (cb) CK(ctx, ctx->d_rc_all.reserve(cb));
+        const void *src_off = seq_off, *src_rc = read_count;
+        if (stage_in) {
+            int r = reserve_pinned(ctx->h_meta, ctx->h_meta_cap, ob + cb);
+            if (r) return r;
+            ctx->copy_pool.copy(ctx->h_meta, seq_off, ob);
+            if (cb) ctx->copy_pool.copy(ctx->h_meta + ob, read_count, cb);
+            src_off = ctx->h_meta;
+            src_rc = ctx->h_meta + ob;
+        }
+        CK(ctx, cudaMemcpyAsync(ctx->d_off_all.p, src_off, ob, cudaMemcpyHostToDevice, ctx->stream));
+        if (cb) CK(ctx, cudaMemcpyAsync(ctx->d_rc_all.p, src_rc, cb, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->meta_done) CK(ctx, cudaEventCreateWithFlags(&ctx->meta_done, cudaEventDisableTiming));
+        CK(ctx, cudaEventRecord(ctx->meta_done, ctx->stream));
+    }
     int rc = TREAT_B200_OK;
     uint64_t chunk_idx = 0;
     static const bool trace = getenv("TREAT_B200_TRACE") != nullptr;
@@ -1008,13 +1039,13 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     };
     // pack + align with the exact max n (one 8-byte sync), wide re-run if an edit-base run saturated
     auto run_exact = [&](Slot &s) -> int {
-        const uint32_t *d_rc = read_count ? (const uint32_t *)s.rc.p : nullptr;
+        const uint32_t *d_rc = s.drc;
         bool sat = false;
         const uint32_t cflags = s.sparse ? flags : flags & ~TREAT_B200_OPS_GAPPED_ONLY;
-        int r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, cflags,
+        int r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, s.doff, s.b0, d_rc, s.cn, s.max_len, cflags,
                           (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, false, &sat, &s.dev_stride, 0, nullptr, true);
         if (r == TREAT_B200_OK && sat && !ctx->tmpl_wide)
-            r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, s.b0, d_rc, s.cn, s.max_len, cflags,
+            r = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, s.doff, s.b0, d_rc, s.cn, s.max_len, cflags,
                           (treat_b200_record *)s.rec.p, nullptr, 0, s.stream, true, nullptr, &s.dev_stride, 0, nullptr, true);
         return r;
     };
@@ -1072,25 +1103,18 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         if (want_ops && (ops_stride < need_stride || ops_stride % 16))
             return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small (see treat_b200_ops_stride)");
         CK(ctx, s.seqs.reserve(b1 - b0 + 16));
-        CK(ctx, s.off.reserve((cn + 1) * 8));
         CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
-        if (read_count) CK(ctx, s.rc.reserve(cn * 4));
         const uint8_t *src_seqs = seqs + b0;
-        const uint64_t *src_off = seq_off + c0;
-        const uint32_t *src_rc = read_count ? read_count + c0 : nullptr;
         if (stage_in) {  // the slot's previous chunk is done, so its staging buffer is free
-            const size_t sb = (size_t)(b1 - b0), ob = (cn + 1) * 8, cb = read_count ? cn * 4 : 0, so = (sb + 15) & ~(size_t)15;
-            if ((rc = reserve_pinned(s.h_in, s.h_in_cap, so + ob + cb))) break;
+            const size_t sb = (size_t)(b1 - b0);
+            if ((rc = reserve_pinned(s.h_in, s.h_in_cap, sb))) break;
             ctx->copy_pool.copy(s.h_in, src_seqs, sb);
-            memcpy(s.h_in + so, src_off, ob);
-            if (cb) memcpy(s.h_in + so + ob, src_rc, cb);
             src_seqs = s.h_in;
-            src_off = reinterpret_cast<const uint64_t *>(s.h_in + so);
-            src_rc = cb ? reinterpret_cast<const uint32_t *>(s.h_in + so + ob) : nullptr;
         }
         if (b1 > b0) CK(ctx, cudaMemcpyAsync(s.seqs.p, src_seqs, b1 - b0, cudaMemcpyHostToDevice, st));
-        CK(ctx, cudaMemcpyAsync(s.off.p, src_off, (cn + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (read_count) CK(ctx, cudaMemcpyAsync(s.rc.p, src_rc, cn * 4, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaStreamWaitEvent(st, ctx->meta_done, 0));  // the call's seq_off / read_count are on the device
+        s.doff = (const uint64_t *)ctx->d_off_all.p + c0;
+        s.drc = read_count ? (const uint32_t *)ctx->d_rc_all.p + c0 : nullptr;
         s.c0 = c0;
         s.cn = cn;
         s.b0 = b0;
@@ -1098,8 +1122,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         s.sparse = sparse_ok && (uint64_t)ctx->gap_hint * 32 <= chunk_reads;
         if (ctx->ncap_hint && !ctx->tmpl_wide && !no_spec) {
             // no host sync: size the align kernel from the largest n seen so far (+ slack) and validate later
-            rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0,
-                           read_count ? (const uint32_t *)s.rc.p : nullptr, cn, max_len,
+            rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, s.doff, b0, s.drc, cn, max_len,
                            s.sparse ? flags : flags & ~TREAT_B200_OPS_GAPPED_ONLY, (treat_b200_record *)s.rec.p,
                            nullptr, 0, st, false, nullptr, &s.dev_stride, ctx->ncap_hint + 8, nullptr, true);
             s.pending = rc == TREAT_B200_OK;
