@@ -21,6 +21,7 @@ tcb = cabi.TEXT_SINK(lambda u, p, n, f, k: 0)
 tot = C.c_uint64()
 for tag, buf in (("pageable", pageable), ("pinned", pinned)):
     for name, fn in (("fasta_stream", lambda: cabi.lib().treat_b200_fasta_stream(eng._ctx, buf.ctypes.data, buf.size, cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY, 0, scb, None, C.byref(tot))),
+                     ("fasta_upload", lambda: cabi.lib().treat_b200_fasta_upload(eng._ctx, buf.ctypes.data, buf.size, C.byref(tot), None)),
                      ("fasta_text", lambda: cabi.lib().treat_b200_fasta_text(eng._ctx, buf.ctypes.data, buf.size, cabi.NO_SUMMARY, 80, tcb, None, C.byref(tot)))):
         for it in range(3):
             t0 = time.perf_counter()

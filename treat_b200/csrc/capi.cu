@@ -184,8 +184,9 @@ struct FastaDev {
     uint64_t len = 0, N = 0, seq_bytes = 0;
     uint32_t max_len = 0;
     uint64_t *h = nullptr;   // pinned [8]: line-start '>' count, first '>', (longest sequence | multi-line flag << 32), sequence bytes
-    uint8_t *h_stage = nullptr;  // pinned staging buffer of a piece whose source bytes are pageable (stream / text calls)
+    uint8_t *h_stage = nullptr;  // pinned staging buffer (two 32 MB halves) for source bytes that are pageable
     size_t h_stage_cap = 0;
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};  // the H2D copy out of each half
     bool multi = false;      // some record has more than one sequence line: reads are compacted before packing
     bool compacted = false;  // seqs / seq_off hold the compacted reads
     bool open = false;
@@ -198,6 +199,10 @@ struct FastaDev {
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr;
         h_stage_cap = 0;
+        for (cudaEvent_t &ev : stage_done) {
+            if (ev) cudaEventDestroy(ev);
+            ev = nullptr;
+        }
     }
 };
 
@@ -1173,19 +1178,24 @@ static int fasta_stage_copy_count(treat_b200_ctx *ctx, FastaDev &fa, const uint8
                                   bool stage_pageable = false)
 {
     static const bool no_staging = getenv("TREAT_B200_NO_STAGING") != nullptr;
-    if (stage_pageable && len && !no_staging && host_pageable(fasta)) {
-        if (len > fa.h_stage_cap) {
+    const uint64_t piece = 32ull << 20;  // a multiple of the tile size
+    const bool staged = stage_pageable && len && !no_staging && host_pageable(fasta);
+    if (staged) {  // two halves of one pinned buffer, a 32 MB piece each
+        const size_t need = (size_t)std::min<uint64_t>(len, 2 * piece);
+        if (need > fa.h_stage_cap) {
+            CK(ctx, cudaStreamSynchronize(st));
             if (fa.h_stage) cudaFreeHost(fa.h_stage);
             fa.h_stage = nullptr;
             fa.h_stage_cap = 0;
-            CK(ctx, cudaMallocHost((void **)&fa.h_stage, len + len / 4 + 4096));
-            fa.h_stage_cap = len + len / 4 + 4096;
+            const size_t want = need >= 2 * piece ? need : std::min<size_t>(2 * piece, need + need / 4 + 4096);
+            CK(ctx, cudaMallocHost((void **)&fa.h_stage, want));
+            fa.h_stage_cap = want;
         }
+        for (cudaEvent_t &ev : fa.stage_done)
+            if (!ev) CK(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         static const int copy_threads = getenv("TREAT_B200_COPY_THREADS") ? std::max(0, atoi(getenv("TREAT_B200_COPY_THREADS")))
                                                                          : (int)std::min(5u, std::max(1u, std::thread::hardware_concurrency() / 2));
         ctx->copy_pool.start(copy_threads);
-        ctx->copy_pool.copy(fa.h_stage, fasta, len);
-        fasta = fa.h_stage;
     }
     fa.open = false;
     fa.compacted = false;
@@ -1208,10 +1218,17 @@ static int fasta_stage_copy_count(treat_b200_ctx *ctx, FastaDev &fa, const uint8
     fa.h[1] = ~0ull;
     if (len == 0) return TREAT_B200_OK;
     // in pieces: the record starts of a piece are counted while the next piece is on the bus
-    const uint64_t piece = 32ull << 20;  // a multiple of the tile size
-    for (uint64_t o = 0; o < len; o += piece) {
+    for (uint64_t o = 0, k = 0; o < len; o += piece, k++) {
         const uint64_t nb = std::min(piece, len - o);
-        CK(ctx, cudaMemcpyAsync((uint8_t *)fa.file.p + o, fasta + o, nb, cudaMemcpyHostToDevice, st));
+        const uint8_t *src = fasta + o;
+        if (staged) {  // pageable bytes: through the half of the pinned buffer whose previous copy is done
+            uint8_t *half = fa.h_stage + (k & 1) * piece;
+            if (k >= 2) CK(ctx, cudaEventSynchronize(fa.stage_done[k & 1]));
+            ctx->copy_pool.copy(half, src, nb);
+            src = half;
+        }
+        CK(ctx, cudaMemcpyAsync((uint8_t *)fa.file.p + o, src, nb, cudaMemcpyHostToDevice, st));
+        if (staged) CK(ctx, cudaEventRecord(fa.stage_done[k & 1], st));
         int e = launch_fasta_mark((const uint8_t *)fa.file.p, len, o / kFastaTileBytes, (nb + kFastaTileBytes - 1) / kFastaTileBytes,
                                   (uint32_t *)fa.tile_count.p, d_first, ctx->num_sms, st);
         if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_fasta_mark launch: ") + cudaGetErrorString((cudaError_t)e));
@@ -1332,7 +1349,7 @@ int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
     cudaStream_t st = ctx->stream;
     *n_records = 0;
     if (max_seq_len) *max_seq_len = 0;
-    int rc = fasta_stage_copy_count(ctx, fa, fasta, len, st);
+    int rc = fasta_stage_copy_count(ctx, fa, fasta, len, st, true);
     if (rc) return rc;
     CK(ctx, cudaStreamSynchronize(st));
     if ((rc = fasta_stage_index(ctx, fa, fasta, st))) return rc;
