@@ -66,3 +66,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(d, f), errors="ignore").read()
                 assert "oracle" not in text.lower().replace("oracle/ ", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    """cgo (and any other FFI generator) compiles include/treat_b200.h as C: it must be valid C99 on its own."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "treat_b200.h"\nint main(void) { return sizeof(treat_b200_record) == 48 ? 0 : 1; }\n')
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(tmp_path / "hdr")])
+    assert subprocess.call([str(tmp_path / "hdr")]) == 0
