@@ -1538,6 +1538,8 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
                 pc[k].spec = pc[k].in_place && ctx->ncap_hint != 0;
                 if ((rc = fasta_align_chunk(ctx, fa, s, 0, fa.N, flags, pc[k].stride, &pc[k].in_place, pc[k].spec ? ctx->ncap_hint + 8 : 0))) break;
                 if ((rc = enqueue_results(k))) break;
+                // MarshalBinary sizes behind the align kernels (valid unless a speculative piece has to be re-run)
+                if ((flags & TREAT_B200_WANT_BLOBS) && (rc = fasta_blobs_sizes(ctx, s, fa.N))) break;
             }
         }
         tC += now() - t0;
@@ -1557,6 +1559,7 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
                     if (!(flags & TREAT_B200_NO_SUMMARY)) CK(ctx, cudaMemsetAsync(s.summary.p, 0, treat_b200_summary_len(ctx) * 8, s.stream));
                     if ((rc = fasta_align_chunk(ctx, fa, s, 0, n, flags, pc[k].stride, &pc[k].in_place))) break;
                     if ((rc = enqueue_results(k))) break;
+                    if ((flags & TREAT_B200_WANT_BLOBS) && (rc = fasta_blobs_sizes(ctx, s, n))) break;  // the records changed
                     CK(ctx, cudaStreamSynchronize(s.stream));
                 } else {
                     if (!(flags & TREAT_B200_NO_SUMMARY)) {
@@ -1567,9 +1570,7 @@ int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
                     if ((rc = add_heatmap(ctx, flags, (const treat_b200_record *)s.rec.p, n, s.stream))) break;
                 }
             }
-            if (n && (flags & TREAT_B200_WANT_BLOBS)) {  // the records are final now: MarshalBinary for the piece
-                if ((rc = fasta_blobs_sizes(ctx, s, n))) break;
-                CK(ctx, cudaStreamSynchronize(s.stream));
+            if (n && (flags & TREAT_B200_WANT_BLOBS)) {  // the records are final and the blobs' total size is on the host
                 if ((rc = fasta_blobs_write(ctx, s, fa, pc[k].in_place, n))) break;
                 CK(ctx, cudaStreamSynchronize(s.stream));
             }
