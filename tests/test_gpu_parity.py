@@ -565,7 +565,8 @@ def test_write_to_on_device(eng, examples, tmp_path):
     longf = ">big-2\n%s\n>plain-1\n%s\n>mid-3\n%s\n" % (big, reads[7], mid)
     assert _text_vs_oracle(eng, tpath, longf.encode(), tmp_path, "long_reads") == 3
     # long template, K = 10 (labels A1..A8) and K = 14 (labels A10..A12 are three characters wide), truncated reads
-    for m, n_alt, N in ((300, 8, 600), (90, 12, 300), (700, 3, 200)):
+    # ... and K = 32 on a 600-base template: labels up to A30, EditSite rows too large for k_text's shared memory
+    for m, n_alt, N in ((300, 8, 600), (90, 12, 300), (700, 3, 200), (600, 30, 150)):
         tl = synth.long_template(m, n_alt, seed=31 + m)
         lp = tl.write_fasta(str(tmp_path / ("long_text_%d.fa" % m)))
         seqs, off, rc = synth.reads(tl, N, seed=99 + m, p_trunc=0.3)
