@@ -968,6 +968,12 @@ def test_treat_align_binary(examples):
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert out.stdout == O.cli_align(template=examples["templates.fa"], fragment=examples["clones.fa"], base="T")
+    # the same tool written in C against include/treat_b200.h alone (examples/treat_align_capi.c: the calls a cgo binding makes)
+    capi = os.path.join(os.path.dirname(exe), "treat_align_capi")
+    for t, f, base, off in (("templates.fa", "clones.fa", "T", 0), ("templates.fa", "sample-1.fa", "T", 10), ("test-templates.fa", "test-sample.fa", "t", 0)):
+        out = subprocess.run([capi, "-t", examples[t], "-f", examples[f], "-b", base, "--offset", str(off)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        assert out.stdout == O.cli_align(template=examples[t], fragment=examples[f], base=base, offset=off)
     out = subprocess.run([exe, "-1", "ATCTGTATGT", "-2", "ATTCGATTG", "-b", "T"], capture_output=True, text=True, timeout=120)
     assert out.stdout == "A-TCTGTA-TGT\nATTC-G-ATTG-\n\n"
     bad = subprocess.run([exe, "-1", "ATCTGTATGT", "-b", "T"], capture_output=True, text=True, timeout=120)

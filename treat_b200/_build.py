@@ -76,6 +76,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or _stale(CLI, [cli_src, LIB] + hdrs):
         _run([os.environ.get("CXX", "g++")] + CXX_FLAGS + [cli_src, "-o", CLI, "-L" + PKG, "-ltreat_b200",
                                                            "-Wl,-rpath,$ORIGIN/.."], verbose)
+    # the same tool written against the C header alone, in C99: what a cgo binding compiles and links
+    capi_src = os.path.join(os.path.dirname(PKG), "examples", "treat_align_capi.c")
+    capi_exe = os.path.join(PKG, "bin", "treat_align_capi")
+    if os.path.exists(capi_src) and (force or _stale(capi_exe, [capi_src, LIB] + hdrs)):
+        _run([os.environ.get("CC", "gcc"), "-std=c99", "-O2", "-Wall", "-Wextra", "-pedantic", "-I" + os.path.join(os.path.dirname(PKG), "include"),
+              capi_src, "-o", capi_exe, "-L" + PKG, "-ltreat_b200", "-Wl,-rpath,$ORIGIN/.."], verbose)
     return LIB
 
 
