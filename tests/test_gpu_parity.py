@@ -584,7 +584,6 @@ def test_write_to_on_device(eng, examples, tmp_path):
     om, tm = _oracle_template(t, tmp_path)
     eng.SetTemplate(tm)
     N = 700
-    sub = seqs_rps = None
     seqs, off, rc = synth.reads(t, N, seed=777, p_trunc=0.1)
     names = [("read %d_%d" % (i, rc[i])).encode() for i in range(N)]
     noff = np.zeros(N + 1, dtype=np.int64)
