@@ -314,11 +314,18 @@ int treat_b200_text_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
                            const uint64_t *d_name_off, const treat_b200_record *d_rec, const uint8_t *d_ops,
                            uint32_t ops_stride, uint64_t N, uint32_t max_len, int32_t tw, uint64_t *d_text_off,
                            uint8_t *d_text, uint64_t text_cap, uint64_t *text_bytes, void *stream);
+/* The loop of cmd/treat/align.go:114-120 for records the caller already holds (host buffers; names concatenated like the
+ * reads, name r = names[name_off[r], name_off[r+1])): NewFragment, NewAlignment and WriteTo for reads [0, N) on the device,
+ * the text handed to `sink` chunk by chunk (32,768 reads) in read order; first_record counts reads.  The typedef of the
+ * sink is below.  flags: TREAT_B200_EXCLUDE_SNPS, TREAT_B200_NO_SUMMARY, TREAT_B200_HEATMAP. */
+typedef int (*treat_b200_text_sink)(void *user, const uint8_t *text, uint64_t len, uint64_t first_record, uint64_t n_records);
+int treat_b200_text_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off, const uint8_t *names,
+                          const uint64_t *name_off, uint64_t N, uint32_t flags, int32_t tw, treat_b200_text_sink sink,
+                          void *user);
 /* `treat align -t templates.fa -f reads.fa` (cmd/treat/align.go:96-121) in one streaming call: FASTA bytes in, the exact
  * stdout text out.  The file is cut at record starts into pieces (~8 MB); every piece is indexed, aligned and formatted on
  * the device and its text handed to `sink` in file order while the next piece is in flight (text is valid during the
  * callback only; a non-zero return stops the run).  flags: TREAT_B200_EXCLUDE_SNPS, TREAT_B200_NO_SUMMARY, TREAT_B200_HEATMAP. */
-typedef int (*treat_b200_text_sink)(void *user, const uint8_t *text, uint64_t len, uint64_t first_record, uint64_t n_records);
 int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, int32_t tw,
                           treat_b200_text_sink sink, void *user, uint64_t *n_records);
 

@@ -616,6 +616,13 @@ def test_write_to_on_device(eng, examples, tmp_path):
             assert text[int(toff[i]):int(toff[i + 1])].decode() == alns[i].WriteTo(frag, tm, tw), (tw, i)
     with pytest.raises(T.TreatError):
         eng.text_device(*args[:9], 4, d_toff.data_ptr(), 0, 0, st)  # tw = 4: the reference divides by zero
+    # treat_b200_text_batch: the same from host buffers in chunks (40,000 reads: two chunks), names as the oracle builds them
+    N2 = 40000
+    seqs2, off2, rc2 = synth.reads(t, N2, seed=778, p_trunc=0.02)
+    got = eng.text_batch(seqs2, off2, ["r%d-%d" % (i, rc2[i]) for i in range(N2)], cabi.NO_SUMMARY)
+    want, _ = O.text_batch(om, seqs2, off2, rc2, prefix="r", nthreads=8)
+    assert got == want.tobytes()
+    assert eng.text_batch(seqs2[:0], off2[:1], []) == b""
 
 
 def test_heatmap_consumer(eng, tmp_path):

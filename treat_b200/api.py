@@ -545,6 +545,31 @@ class Aligner:
                                               C.byref(total), stream or None), self._ctx)
         return total.value
 
+    def text_batch(self, seqs: np.ndarray, seq_off: np.ndarray, names: Sequence, flags: int = 0, tw: int = 80, out=None) -> bytes:
+        """treat_b200_text_batch: NewFragment + NewAlignment + WriteTo for reads the caller holds (ids in `names`); returns the
+        text `treat align` would print for them (or writes the chunks to `out` as they arrive)."""
+        from .cabi import TEXT_SINK
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        enc = [_b(x) for x in names]
+        nbuf = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+        noff = np.zeros(len(enc) + 1, dtype=np.uint64)
+        noff[1:] = np.cumsum([len(x) for x in enc])
+        parts = []
+
+        def sink(_user, ptr, n, _first, _nrec):
+            buf = C.string_at(ptr, n) if n else b""
+            if out is not None:
+                out.write(buf)
+            else:
+                parts.append(buf)
+            return 0
+        cb = TEXT_SINK(sink)
+        dummy = np.zeros(1, dtype=np.uint8)
+        check(lib().treat_b200_text_batch(self._ctx, seqs.ctypes.data if seqs.size else dummy.ctypes.data, seq_off.ctypes.data,
+                                          nbuf.ctypes.data, noff.ctypes.data, len(enc), flags, tw, cb, None), self._ctx)
+        return b"".join(parts)
+
     def fasta_text(self, data, flags: int = 0, tw: int = 80, out=None) -> Tuple[bytes, int]:
         """treat_b200_fasta_text: FASTA bytes -> the text `treat align -t ... -f ...` prints (parse, alignment and
         WriteTo on the GPU).  Returns (text, records); with `out` (a binary file object) the pieces are written there

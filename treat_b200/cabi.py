@@ -87,6 +87,7 @@ SIGNATURES = {
     "treat_b200_fasta_stream": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
     "treat_b200_text_device": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int32, _P, _P, C.c_uint64,
                                         C.POINTER(C.c_uint64), _P]),
+    "treat_b200_text_batch": (C.c_int, [_P, _U8P, _P, _U8P, _P, C.c_uint64, C.c_uint32, C.c_int32, _P, _P]),
     "treat_b200_fasta_text": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_int32, _P, _P, C.POINTER(C.c_uint64)]),
     "treat_b200_marshal_device": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64), _P]),
     "treat_b200_unmarshal_record": (C.c_int, [_P, _SZ, _P, C.POINTER(C.c_double), C.POINTER(_P)]),

@@ -143,6 +143,7 @@ struct Slot {
     const uint32_t *drc = nullptr;
     DevBuf scratch;  // global scratch of this slot's align launches (launches of different slots overlap on the GPU)
     DevBuf text, text_off, tlen, gtot, tsums;  // Alignment.WriteTo on the device (treat_b200_text_device / _fasta_text)
+    DevBuf names, name_off;                    // treat_b200_text_batch: the chunk's names
     uint8_t *tland = nullptr;                  // pinned landing buffer of a piece's text
     size_t tland_cap = 0;
     uint64_t *h_text_total = nullptr;          // pinned [1]
@@ -156,7 +157,7 @@ struct Slot {
     void release()
     {
         for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &ops_idx, &text,
-                          &text_off, &tlen, &gtot, &tsums})
+                          &text_off, &tlen, &gtot, &tsums, &names, &name_off})
             b->release();
         if (tland) cudaFreeHost(tland);
         if (h_text_total) cudaFreeHost(h_text_total);
@@ -1807,6 +1808,110 @@ int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const 
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_marshal launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches++;
     return TREAT_B200_OK;
+}
+
+// The loop of cmd/treat/align.go:114-120 for a caller that already holds the records (rec.Id, rec.Seq from gofasta):
+// NewFragment + NewAlignment + WriteTo for reads [0, N), chunk by chunk on two slots; the text of each chunk goes to the
+// sink in read order while the next chunk is being processed.
+int treat_b200_text_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off, const uint8_t *names,
+                          const uint64_t *name_off, uint64_t N, uint32_t flags, int32_t tw, treat_b200_text_sink sink, void *user)
+{
+    if (!ctx || !sink || (N && (!seqs || !seq_off || !names || !name_off))) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
+    tw = text_tw(tw);
+    if (tw < 5) return fail(ctx, TREAT_B200_ERR_INVALID, "text: tw must be at least 5 (rows wrap at tw - 4 columns)");
+    if (N == 0) return TREAT_B200_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2; i++)
+        if (!ctx->slot[i].stream) CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
+    const uint32_t aflags = (flags & ~(uint32_t)TREAT_B200_OPS_GAPPED_ONLY) | TREAT_B200_WANT_OPS;
+    const uint64_t chunk_reads = 32768;  // ~90 MB of text per chunk for RPS12-sized reads
+    struct Pending {
+        bool live = false;
+        uint64_t first = 0, n = 0, bytes = 0;
+    } pend[2];
+    auto deliver = [&](int i) -> int {
+        if (!pend[i].live) return TREAT_B200_OK;
+        pend[i].live = false;
+        CK(ctx, cudaStreamSynchronize(ctx->slot[i].stream));
+        if (sink(user, ctx->slot[i].tland, pend[i].bytes, pend[i].first, pend[i].n))
+            return fail(ctx, TREAT_B200_ERR_INVALID, "text_batch: stopped by the sink");
+        return TREAT_B200_OK;
+    };
+    int rc = TREAT_B200_OK;
+    uint64_t k = 0;
+    for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk_reads, k++) {
+        const uint64_t cn = std::min(chunk_reads, N - c0);
+        const int i = (int)(k & 1);
+        Slot &s = ctx->slot[i];
+        cudaStream_t st = s.stream;
+        if ((rc = deliver(i))) break;  // chunk k - 2: its buffers are reused below
+        const uint64_t b0 = seq_off[c0], b1 = seq_off[c0 + cn], nb0 = name_off[c0], nb1 = name_off[c0 + cn];
+        uint32_t max_len = 0;
+        for (uint64_t r = c0; r < c0 + cn; r++) {
+            const uint64_t l = seq_off[r + 1] - seq_off[r];
+            if (seq_off[r + 1] < seq_off[r] || name_off[r + 1] < name_off[r] || l > kMaxReadLen)
+                return fail(ctx, l > kMaxReadLen ? TREAT_B200_ERR_TOO_LONG : TREAT_B200_ERR_INVALID,
+                            "text_batch: offsets not monotone or read longer than 16384");
+            max_len = std::max<uint32_t>(max_len, (uint32_t)l);
+        }
+        const uint32_t stride = treat_b200_ops_stride(ctx, max_len);
+        CK(ctx, s.seqs.reserve(b1 - b0 + 16));
+        CK(ctx, s.off.reserve((cn + 1) * 8));
+        CK(ctx, s.names.reserve(nb1 - nb0 + 16));
+        CK(ctx, s.name_off.reserve((cn + 1) * 8));
+        CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
+        CK(ctx, s.ops.reserve(cn * (size_t)stride));
+        CK(ctx, s.text_off.reserve((cn + 1) * 8));
+        if (b1 > b0) CK(ctx, cudaMemcpyAsync(s.seqs.p, seqs + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(s.off.p, seq_off + c0, (cn + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (nb1 > nb0) CK(ctx, cudaMemcpyAsync(s.names.p, names + nb0, nb1 - nb0, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(s.name_off.p, name_off + c0, (cn + 1) * 8, cudaMemcpyHostToDevice, st));
+        bool sat = false;
+        rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0, nullptr, cn, max_len, aflags,
+                       (treat_b200_record *)s.rec.p, (uint8_t *)s.ops.p, stride, st, false, &sat);
+        if (rc == TREAT_B200_OK && sat && !ctx->tmpl_wide)
+            rc = run_chunk(ctx, s, (const uint8_t *)s.seqs.p, (const uint64_t *)s.off.p, b0, nullptr, cn, max_len, aflags,
+                           (treat_b200_record *)s.rec.p, (uint8_t *)s.ops.p, stride, st, true, nullptr);
+        if (rc) break;
+        TextParams tp{};
+        tp.seqs = (const uint8_t *)s.seqs.p;
+        tp.off = (const uint64_t *)s.off.p;
+        tp.off_bias = b0;
+        tp.names = (const uint8_t *)s.names.p - nb0;  // only ever indexed at name_off[r] >= nb0
+        tp.name_off = (const uint64_t *)s.name_off.p;
+        tp.rec = (const treat_b200_record *)s.rec.p;
+        tp.ops = (const uint8_t *)s.ops.p;
+        tp.ops_stride = stride;
+        tp.N = cn;
+        tp.max_len = max_len;
+        tp.tw = tw;
+        text_template(ctx, tp);
+        if ((rc = text_sizes(ctx, s, tp, (uint64_t *)s.text_off.p, st))) break;
+        CK(ctx, cudaStreamSynchronize(st));
+        const uint64_t bytes = *s.h_text_total;
+        CK(ctx, s.text.reserve(bytes));
+        if (bytes > s.tland_cap) {
+            if (s.tland) cudaFreeHost(s.tland);
+            s.tland = nullptr;
+            s.tland_cap = 0;
+            CK(ctx, cudaMallocHost((void **)&s.tland, bytes + bytes / 4 + 4096));
+            s.tland_cap = bytes + bytes / 4 + 4096;
+        }
+        if ((rc = text_write(ctx, s, tp, (const uint64_t *)s.text_off.p, (uint8_t *)s.text.p, st))) break;
+        CK(ctx, cudaMemcpyAsync(s.tland, s.text.p, bytes, cudaMemcpyDeviceToHost, st));
+        pend[i].live = true;
+        pend[i].first = c0;
+        pend[i].n = cn;
+        pend[i].bytes = bytes;
+    }
+    for (int j = 0; j < 2; j++) {
+        const int i = (int)((k + j) & 1);
+        const int r = rc == TREAT_B200_OK ? deliver(i) : TREAT_B200_OK;
+        if (r) rc = r;
+    }
+    for (int i = 0; i < 2; i++) cudaStreamSynchronize(ctx->slot[i].stream);
+    return rc;
 }
 
 // `treat align -t templates.fa -f reads.fa` (cmd/treat/align.go:96-121) as one streaming call: the file is cut at record
