@@ -59,16 +59,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         os.remove(marker)
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    objs = []
+    objs, jobs = [], []
     for src in CUDA_SOURCES + CXX_SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace("/", "_") + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             if src.endswith(".cu"):
-                _run([_nvcc()] + NVCC_FLAGS + checks + ["-c", s, "-o", o], verbose)
+                jobs.append([_nvcc()] + NVCC_FLAGS + checks + ["-c", s, "-o", o])
             else:
-                _run([os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-c", s, "-o", o], verbose)
+                jobs.append([os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-c", s, "-o", o])
+    if jobs:  # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
     if force or _stale(LIB, objs):
         _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
              + ["-cudart", "static", "-Xlinker", "--no-undefined"], verbose)
