@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fasta", action="store_true", help="skip the FASTA-ingest measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the strong-scaling parity leg (digests vs tests/golden)")
+    ap.add_argument("--no-side", action="store_true", help="skip the long-gene and noisy workload points")
     return ap.parse_args()
 
 
@@ -255,6 +257,168 @@ def pin_to_gpu_numa_node(gpu_index):
         log("cpu affinity not set:", e)
 
 
+
+# ---------------------------------------------------------------------------------------------
+# legs added around the main measurement
+# ---------------------------------------------------------------------------------------------
+PARITY_READS = 1_000_000
+
+
+def parity_leg(T, cabi, parallel, synth, eng, comm, args, t, seed, p_trunc, rank, world, barrier, max_over_ranks, alloc):
+    """Strong-scaling parity: the FIRST 1,000,000 reads of the workload shared between the N GPUs (contiguous ranges, host
+    buffers, every ops row), then SHA-256 over the ranks' canonical records, over their traceback ops and over the
+    all-reduced summary -- the same digests at every N, and for rps12 equal to the CPU port's committed in
+    tests/golden/parity_digests.json (tests/golden/make_digests.py)."""
+    import hashlib
+    P = PARITY_READS
+    lo, hi = parallel.shard_range(P, rank, world)
+    seqs, off, rc = synth.reads(t, hi - lo, seed=seed, first=lo, p_trunc=p_trunc, pinned_alloc=alloc)
+    max_len = int(np.diff(off.astype(np.int64)).max()) if hi > lo else 0
+    stride = eng.ops_stride(max_len)
+    rec = alloc((hi - lo) * 48).view(cabi.RECORD_DTYPE)
+    ops = alloc((hi - lo) * stride).reshape(hi - lo, stride)
+    h_off, h_rc = alloc((hi - lo + 1) * 8).view(np.uint64), alloc((hi - lo) * 4).view(np.uint32)
+    h_off[:], h_rc[:] = off, rc
+    eng.align_batch(seqs, h_off, h_rc, cabi.WANT_OPS | cabi.NO_SUMMARY, rec=rec, ops=ops)  # warm-up (buffers, clocks)
+    eng.reset_summary()
+    ops[:] = 0
+    barrier()
+    t0 = time.perf_counter()
+    eng.align_batch(seqs, h_off, h_rc, cabi.WANT_OPS, rec=rec, ops=ops)
+    red = comm.reduce_summary()
+    ms = 1e3 * max_over_ranks(time.perf_counter() - t0)
+    eng.reset_summary()
+    tag = "/dev/shm/treat_b200_parity_%s_%%d_%%s.bin" % os.environ.get("MASTER_PORT", str(os.getppid()))
+    parallel.canonical_records(rec).tofile(tag % (rank, "rec"))
+    parallel.compact_ops(rec, ops).tofile(tag % (rank, "ops"))
+    np.asarray(red).tofile(tag % (rank, "sum"))
+    np.concatenate([seqs, np.frombuffer(off[1:].tobytes() if rank else off.tobytes(), dtype=np.uint8)]).tofile(tag % (rank, "in"))
+    barrier()
+    out = None
+    if rank == 0:
+        def cat(kind):
+            h = hashlib.sha256()
+            for r in range(world):
+                with open(tag % (r, kind), "rb") as fh:
+                    while True:
+                        b = fh.read(1 << 24)
+                        if not b:
+                            break
+                        h.update(b)
+            return h.hexdigest()
+        sums = [np.fromfile(tag % (r, "sum"), dtype=np.uint64) for r in range(world)]
+        same_on_all = all(np.array_equal(x, sums[0]) for x in sums)
+        out = {"reads": P, "n_gpus": world, "records_sha256": cat("rec"), "ops_sha256": cat("ops"),
+               "summary_sha256": parallel.sha256_hex(sums[0]), "summary_identical_on_all_ranks": bool(same_on_all),
+               "summary_reads": int(sums[0][14]), "strong_scaling_e2e_ms": ms, "strong_scaling_e2e_reads_per_s": P / (ms * 1e-3),
+               "api": "treat_b200_align_batch per rank on its contiguous range (host buffers, every ops row) + "
+                      "treat_b200_comm_reduce_summary (the library's ncclAllReduce)"}
+        want = None
+        gp = os.path.join(ROOT, "tests", "golden", "parity_digests.json")
+        if os.path.exists(gp):
+            want = json.load(open(gp)).get(args.workload)
+        if want and want["reads"] == P and want["seed"] == seed and want["p_trunc"] == p_trunc:
+            out["golden"] = "tests/golden/parity_digests.json (CPU port of the Go path on the same reads)"
+            out["matches_golden"] = bool(out["records_sha256"] == want["records_sha256"] and out["ops_sha256"] == want["ops_sha256"]
+                                         and out["summary_sha256"] == want["summary_sha256"] and same_on_all)
+        else:
+            out["golden"] = None
+            out["matches_golden"] = None
+        if out["matches_golden"] is False or not same_on_all or out["summary_reads"] != P:
+            raise AssertionError("parity leg: digests differ from the oracle's: %s vs %s" % (out, want))
+    barrier()
+    for kind in ("rec", "ops", "sum", "in"):
+        try:
+            os.remove(tag % (rank, kind))
+        except OSError:
+            pass
+    return out
+
+
+def h2d_floor(cabi, eng, host_arr, nbytes, barrier, max_over_ranks, world):
+    """What the host's PCIe / memory path gives: one plain pinned cudaMemcpyAsync of a step's input bytes, all ranks at once."""
+    ms = C.c_double()
+    barrier()
+    t0 = time.perf_counter()
+    cabi.check(cabi.lib().treat_b200_measure_h2d(eng._ctx, host_arr.ctypes.data, nbytes, 5, C.byref(ms)), eng._ctx)
+    wall = time.perf_counter() - t0
+    worst = max_over_ranks(ms.value)
+    return {"h2d_floor_ms": worst, "h2d_floor_gb_per_s_per_gpu": nbytes / (worst * 1e-3) / 1e9,
+            "h2d_floor_gb_per_s_all_gpus": world * nbytes / (worst * 1e-3) / 1e9, "h2d_floor_this_rank_ms": ms.value,
+            "h2d_floor_what": "cudaMemcpyAsync H2D of the step's %d input bytes from pinned memory, 5 copies back to back, "
+                              "CUDA events, every rank at once, max over ranks (%.0f ms wall incl. warm-up)" % (nbytes, 1e3 * wall)}
+
+
+def side_workload(T, cabi, synth, eng, name, N, steps, alloc):
+    """A second workload point on this GPU (N = 1 only): device-resident and end-to-end reads/s, DP share, geometry."""
+    import torch
+    if name == "long":
+        t, p_trunc, seed, noise = synth.long_template(300, 8), 0.2, synth.SEED_BASE + 5, {}
+        what = "BASELINE configs[4]: long-gene set m=300 K=10, variable-length reads (20%% truncated by up to 100 bases)"
+    else:
+        t, p_trunc, seed, noise = synth.rps12_template(), 0.0, synth.SEED_BASE + 3, {"p_sub_base": 0.01, "p_indel_read": 0.05}
+        what = "RPS12 reads with sequencing noise: 1% substitutions per base and one more single-base indel in 5% of the reads"
+    with tempfile.TemporaryDirectory() as d:
+        tm = T.NewTemplateFromFasta(t.write_fasta(os.path.join(d, "tmpl.fa")), T.FORWARD, t.edit_base)
+    eng.SetTemplate(tm)
+    seqs, off, rc = synth.reads(t, N, seed=seed, p_trunc=p_trunc, pinned_alloc=alloc, **noise)
+    max_len = int(np.diff(off.astype(np.int64)).max())
+    stride = eng.ops_stride(max_len)
+    h_off, h_rc = alloc((N + 1) * 8).view(np.uint64), alloc(N * 4).view(np.uint32)
+    h_off[:], h_rc[:] = off, rc
+    h_rec = alloc(N * 48).view(cabi.RECORD_DTYPE)
+    h_ops = alloc(N * stride).reshape(N, stride)
+    flags = cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY
+    dev = torch.device("cuda", eng.device)
+    d_seqs = torch.from_numpy(np.ascontiguousarray(seqs)).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_rc = torch.from_numpy(rc.astype(np.int32)).to(dev)
+    d_rec = torch.empty(N * 48, dtype=torch.uint8, device=dev)
+    d_ops = torch.empty(N * stride, dtype=torch.uint8, device=dev)
+    sraw = torch.cuda.current_stream().cuda_stream
+
+    def step_dev(fl):
+        eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, fl,
+                               d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw)
+
+    def timed(fl):
+        for _ in range(2):
+            step_dev(fl)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream())
+        for _ in range(steps):
+            step_dev(fl)
+        b.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+    dev_ms = timed(flags)
+    dp_ms = timed(flags | cabi.DP_EVERY_READ)
+    rec = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
+    no_dp = (rec["indel"] == 0) & (rec["mismatches"] <= 1) & (rec["n_bases"] == t.m)
+    cells = rec["n_bases"].astype(np.int64) * t.m
+    for _ in range(2):
+        eng.align_batch(seqs, h_off, h_rc, flags, rec=h_rec, ops=h_ops)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.align_batch(seqs, h_off, h_rc, flags, rec=h_rec, ops=h_ops)
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    assert np.array_equal(h_rec, rec), "side workload %s: host-buffer and device-buffer paths disagree" % name
+    out = {"workload": what, "reads_per_step": N, "steps": steps, "reads_total": N * steps, "m": t.m, "K": t.K,
+           "raw_bytes_per_read": float(len(seqs)) / N, "max_raw_len": max_len,
+           "value": N / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms,
+           "value_dp_every_read": N / (dp_ms * 1e-3), "ms_per_step_dp_every_read": dp_ms,
+           "e2e": {"value": N / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(seqs) + (N + 1) * 8 + N * 4)},
+           "reads_finished_without_dp": float(no_dp.mean()), "reads_with_gap": float((rec["indel"] != 0).mean()),
+           "gcups_performed": float(cells[~no_dp].sum()) / (dev_ms * 1e-3) / 1e9,
+           "gcups_dp_every_read": float(cells.sum()) / (dp_ms * 1e-3) / 1e9}
+    geom = cabi.AlignGeometry()
+    if cabi.lib().treat_b200_align_geometry(eng._ctx, int(rec["n_bases"].max()), 0, C.byref(geom)) == 0:
+        out["geometry"] = {f: getattr(geom, f) for f, _ in cabi.AlignGeometry._fields_}
+    del d_seqs, d_off, d_rc, d_rec, d_ops
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -272,11 +436,7 @@ def run_ours(args):
     pin_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is set
-        if "TREAT_B200_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["TREAT_B200_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL_DEBUG (if the caller set it) stays: its lines go to stderr so that stdout keeps the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -285,6 +445,14 @@ def run_ours(args):
         tm = T.NewTemplateFromFasta(t.write_fasta(os.path.join(d, "tmpl.fa")), T.FORWARD, t.edit_base)
     eng = T.Aligner(local)
     eng.SetTemplate(tm)
+    # The one collective of the path (the summary counters) is the library's own ncclAllReduce (treat_b200_comm_*): rank 0
+    # makes the NCCL id, torch.distributed only carries its 128 bytes to the other ranks (plus barriers / max-over-ranks).
+    uid_t = torch.zeros(cabi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if world > 1:
+        if rank == 0:
+            uid_t.copy_(torch.frombuffer(bytearray(T.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid_t, 0)
+    comm = T.Comm(eng, world, rank, bytes(uid_t.cpu().numpy().tobytes()) if world > 1 else None)
 
     N = args.reads
     t0 = time.perf_counter()
@@ -322,14 +490,14 @@ def run_ours(args):
     # records + the traceback ops of every read that has a gap: a read without a gap aligns base over base (its row
     # would be all zero), so its alignment strings follow from the record alone -- what NewAlignments asks for
     flags = cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY
-    summ = parallel.summary_tensor(eng)
+    d_red = torch.zeros(parallel.summary_tensor(eng).numel(), dtype=torch.int64, device=dev)
 
     def step_device():
         eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, flags,
                                d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw)
-        red = summ.clone()
-        parallel.allreduce_summary(red)  # the only collective on the path: ~4 KB of uint64 counters
-        return red
+        # the only collective on the path: ~4 KB of uint64 counters, ncclAllReduce issued by the library on the same stream
+        comm.reduce_summary_device(d_red.data_ptr(), sraw)
+        return d_red
 
     def barrier():
         if world > 1:
@@ -370,6 +538,9 @@ def run_ours(args):
     clocks = sampler.stop()
     rec_dev = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
     cells_per_step = float((rec_dev["n_bases"].astype(np.int64) * t.m).sum())
+    # reads finished without a DP: no gap, at most one mismatch, as long as the template (k_pack's marks)
+    no_dp = (rec_dev["indel"] == 0) & (rec_dev["mismatches"] <= 1) & (rec_dev["n_bases"] == t.m)
+    cells_performed = float((rec_dev["n_bases"].astype(np.int64) * t.m)[~no_dp].sum())
     value = world * N * args.steps / (dev_ms * 1e-3)
 
     # ---- the dominant kernel alone (k_align on already-packed reads), CUDA events ----------------
@@ -484,9 +655,7 @@ def run_ours(args):
     if not args.no_e2e:
         def step_host(fl=flags):
             eng.align_batch(seqs, h_off, h_rc, fl, rec=h_rec, ops=h_ops)
-            red = summ.clone()
-            parallel.allreduce_summary(red)
-            return int(red[0].item())  # device->host read of the step's reduced summary
+            return int(comm.reduce_summary()[0])  # all-GPU counters of the step, read back to the host
         for _ in range(max(1, min(args.warmup, 2))):
             step_host()
         barrier()
@@ -514,6 +683,9 @@ def run_ours(args):
         full_s = max_over_ranks(time.perf_counter() - t0)
         e2e["every_ops_row"] = {"value": world * N * args.steps / full_s, "ms_per_step": 1e3 * full_s / args.steps,
                                 "d2h_bytes_per_step": int(N * 48 + N * dev_stride + 8)}
+        # the floor of this call: the same input bytes as one plain pinned H2D copy per rank, all ranks at once
+        e2e.update(h2d_floor(cabi, eng, seqs, int(len(seqs)), barrier, max_over_ranks, world))
+        e2e["frac_of_h2d_floor"] = e2e["h2d_floor_ms"] / e2e["ms_per_step"]
         if rank == 0 and world == 1:
             # the same call from pageable buffers (what a cgo caller passing Go slices has): staged through pinned buffers
             # by the library's host copy threads
@@ -525,7 +697,10 @@ def run_ours(args):
                 eng.align_batch(pg_seqs, pg_off, pg_rc, flags, rec=pg_rec, ops=pg_ops)
             pg_s = (time.perf_counter() - t0) / 3
             assert np.array_equal(pg_rec, rec_dev)
-            e2e["pageable_buffers"] = {"value": N / pg_s, "ms_per_step": 1e3 * pg_s}
+            e2e["pageable_buffers"] = {"value": N / pg_s, "ms_per_step": 1e3 * pg_s,
+                                       "what": "the same call from pageable caller buffers (Go slices, numpy arrays): the library "
+                                               "stages them through pinned buffers with host copy threads; callers that want the "
+                                               "pinned rate allocate with treat_b200_host_alloc (INTEGRATION.md)"}
             del pg_seqs, pg_rec, pg_ops
         if not np.array_equal(h_rec, rec_dev):
             badi = np.nonzero(h_rec != rec_dev)[0]
@@ -632,6 +807,18 @@ def run_ours(args):
                                  "what": "treat_b200_fasta_parse (one host thread) on the same bytes in memory, parse only"}}
         del text
 
+    # ---- strong-scaling parity leg: the first 1M reads shared between the N GPUs, digests vs the oracle's ------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_leg(T, cabi, parallel, synth, eng, comm, args, t, seed, p_trunc, rank, world, barrier, max_over_ranks, alloc)
+
+    # ---- other workload points on one GPU: BASELINE configs[4] (long genes) and a noisy RPS12 set ---------------------
+    side = {}
+    if rank == 0 and world == 1 and not args.no_side and args.workload == "rps12":
+        side["long"] = side_workload(T, cabi, synth, eng, "long", 500_000, 10, alloc)   # 5 M variable-length reads in all
+        side["noisy"] = side_workload(T, cabi, synth, eng, "noisy", 500_000, 6, alloc)
+        eng.SetTemplate(tm)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)  # the CPU port gets every host core
@@ -660,7 +847,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "gcups": world * cells_per_step * args.steps / (dev_ms * 1e-3) / 1e9,
+            # cells of the reads' full DP matrices per second -- NOT performed work: reads whose stripped bases equal the
+            # template's (or differ in one base) are finished without a DP (exact) ...
+            "gcups_effective": world * cells_per_step * args.steps / (dev_ms * 1e-3) / 1e9,
+            # ... and the cells the DP kernels actually filled per second in the same timed region
+            "gcups_performed": world * cells_performed * args.steps / (dev_ms * 1e-3) / 1e9,
             "config": {"workload": workload_name(args, t), "l2": "inputs larger than L2 (%.0f MB raw reads per GPU per step)" % (len(seqs) / 1e6),
                        "parallelism": "reads sharded over %d GPU(s), summary all-reduce only" % world,
                        "outputs": "48-byte record per read + %d-byte 2-bit ops row per read with a gap" % stride},
@@ -669,10 +860,14 @@ def run_ours(args):
             # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
             "value_dp_every_read": world * N / ((pack_ms + align_ms) * 1e-3),
             "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
-            "text_device": text_dev,
+            "text_device": text_dev, "parity": parity, "long": side.get("long"), "noisy": side.get("noisy"),
+            "nccl": {"version": cabi.lib().treat_b200_nccl_version() if world > 1 else None,
+                     "collective": "ncclAllReduce(uint64, sum) of the summary counters, issued by libtreat_b200.so "
+                                   "(treat_b200_comm_reduce_summary_device) once per step" if world > 1 else "none (1 GPU)"},
             "gpu_launches": int(launches), "clocks": clocks, "summary_reads_all_ranks": reduced_reads,
         }
         print(json.dumps(line), flush=True)
+    comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -190,6 +190,23 @@ uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx);
 /* tuning: rows of traceback words kept per lane in shared memory (0 = default 64); any value is
  * exact, reads whose optimal path could leave the band are re-filled into global scratch */
 int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows);
+/* Geometry of the DP launch for reads of up to max_n stripped bases against the current template (what SURVEY.md 8d asks to
+ * be reported for the long-gene configuration: shared memory per CTA, resident warps, traceback storage). */
+typedef struct treat_b200_geometry {
+    uint32_t cpl;                    /* template columns per lane of the wavefront */
+    uint32_t strips;                 /* column strips (1 unless the template has more than 480 bases) */
+    uint32_t reads_per_warp;         /* 2: k_align2 (16-bit halves), 1: k_align / k_align_strips */
+    uint32_t warps_per_cta;          /* one persistent CTA per SM */
+    uint32_t smem_cta_bytes;         /* dynamic shared memory of the CTA */
+    uint32_t smem_template_bytes;    /* of which: template, edit-site counts, scoring profile, summary bins (CTA-wide) */
+    uint32_t smem_warp_bytes;        /* of which per warp: TMA stage slots, read bases, band window, ops, site map */
+    uint32_t band_rows;              /* direction-word rows kept per lane in shared memory */
+    uint32_t band_diagonals;         /* B: a read is certified when (m - S)/2 <= B and (n - S)/2 <= B */
+    uint32_t scratch_bytes_per_warp; /* global (L2-resident) scratch a full fill writes */
+    uint32_t regs_per_thread;        /* of the kernel that would be launched */
+    uint32_t occupancy_warps_per_sm; /* resident warps = warps_per_cta (one CTA per SM) */
+} treat_b200_geometry;
+int treat_b200_align_geometry(treat_b200_ctx *ctx, uint32_t max_n, uint32_t flags, treat_b200_geometry *out);
 /* bounds-check flags of the kernels' index computations: always 0 unless the library was built with
  * -DTREAT_B200_CHECKS (*checks_compiled says which); a substitute for compute-sanitizer on pools without it */
 int treat_b200_debug_flags(treat_b200_ctx *ctx, uint32_t *flags_out, int32_t *checks_compiled);
@@ -212,6 +229,64 @@ int treat_b200_heatmap_device_ptr(treat_b200_ctx *ctx, uint64_t **d_ptr);
 
 /* ---- roofline helper: dependent-free INT32 add/max throughput of this GPU ---------- */
 int treat_b200_measure_int32_peak(treat_b200_ctx *ctx, double *lane_ops_per_s, double *sm_mhz_effective);
+/* Floor of the host-buffer calls: `reps` plain cudaMemcpyAsync H2D copies of host[0, bytes) (pinned memory for the DMA rate)
+ * into a device buffer of the context, timed with CUDA events on the context's stream: *ms_per_copy.  Run it on all ranks
+ * at once to see what the host's PCIe / memory path gives N GPUs together (bench.py: e2e.h2d_floor_ms). */
+int treat_b200_measure_h2d(treat_b200_ctx *ctx, const void *host, uint64_t bytes, int32_t reps, double *ms_per_copy);
+
+/* =====================================================================================
+ * Several GPUs.  Reads shard over the GPUs with no data-path exchange; the only collective is one
+ * ncclAllReduce(ncclUint64, ncclSum) over the summary counters (and the heat map) -- what `treat stats`
+ * (cmd/treat/stats.go:140-187) and the histogram handlers (cmd/treat/handlers.go:203-215) later read.  NCCL is loaded
+ * at run time (dlopen of libnccl.so.2) the first time a communicator is made, so a single-GPU caller needs no NCCL.
+ *
+ * Two forms:
+ *  (1) one process, n GPUs: treat_b200_group_* -- the library owns one context + one host worker thread per device and the
+ *      ncclCommInitAll communicators; a batch is cut into n contiguous read ranges (range i = [N*i/n, N*(i+1)/n)), so the
+ *      records, ops rows and their order are those of the one-GPU call.  This is the form a Go host uses.
+ *  (2) one process per GPU: treat_b200_comm_* on top of a plain context; the caller hands the 128-byte NCCL id of rank 0
+ *      to every rank by whatever means it has (a file, MPI, torch.distributed, a socket).
+ * ===================================================================================== */
+typedef struct treat_b200_group treat_b200_group;
+/* devices: n CUDA ordinals (NULL: 0..n-1).  n = 1 works without NCCL. */
+int treat_b200_group_create(const int *devices, int32_t n, treat_b200_group **out);
+void treat_b200_group_destroy(treat_b200_group *g);
+int32_t treat_b200_group_size(const treat_b200_group *g);
+treat_b200_ctx *treat_b200_group_ctx(treat_b200_group *g, int32_t i); /* device i's context (owned by the group) */
+const char *treat_b200_group_last_error(const treat_b200_group *g);
+/* treat_b200_set_template / treat_b200_use_template on every device of the group */
+int treat_b200_group_set_template(treat_b200_group *g, const uint8_t *bases, int32_t m, const uint32_t *edit_site, int32_t K,
+                                  const int32_t *alt_start, const int32_t *alt_end, int32_t n_alt, uint32_t edit_offset,
+                                  int32_t tmpl_edit_stop, uint8_t edit_base);
+int treat_b200_group_use_template(treat_b200_group *g, const treat_b200_template *tmpl);
+/* treat_b200_align_batch (same arguments, same results in the same order) with the reads shared between the group's GPUs:
+ * the per-read loop of cmd/treat/align.go:114-120 / cmd/treat/storage.go:738-785 for a whole batch on n devices. */
+int treat_b200_group_align_batch(treat_b200_group *g, const uint8_t *seqs, const uint64_t *seq_off, const uint32_t *read_count,
+                                 uint64_t N, uint32_t flags, treat_b200_record *rec, uint8_t *ops, uint32_t ops_stride);
+uint32_t treat_b200_group_ops_stride(const treat_b200_group *g, uint32_t max_len);
+/* All-GPU summary counters (layout of treat_b200_get_summary): one grouped ncclAllReduce over the devices' counters, result
+ * read from device `from_rank` (every device holds the same reduced array; pass 0).  The devices' own counters stay as
+ * they are.  treat_b200_group_heatmap: the same for the ESS x junction-length heat map (len = dim * dim). */
+int treat_b200_group_summary(treat_b200_group *g, int32_t from_rank, uint64_t *out, uint64_t len);
+int treat_b200_group_heatmap(treat_b200_group *g, int32_t from_rank, uint64_t *out, uint64_t len);
+int treat_b200_group_reset_summary(treat_b200_group *g);
+uint64_t treat_b200_group_launch_count(const treat_b200_group *g); /* kernels launched on all devices */
+
+typedef struct treat_b200_comm treat_b200_comm;
+#define TREAT_B200_COMM_ID_BYTES 128
+int treat_b200_comm_unique_id(uint8_t *id, size_t len); /* rank 0: ncclGetUniqueId; len >= TREAT_B200_COMM_ID_BYTES */
+int treat_b200_comm_create(treat_b200_ctx *ctx, int32_t nranks, int32_t rank, const uint8_t *id, size_t len, treat_b200_comm **out);
+void treat_b200_comm_destroy(treat_b200_comm *c);
+/* Sum of every rank's summary counters / heat map: blocking, result in host memory; the context's own counters stay as they
+ * are.  Every rank must call it (it is a collective). */
+int treat_b200_comm_reduce_summary(treat_b200_comm *c, uint64_t *out, uint64_t len);
+int treat_b200_comm_reduce_heatmap(treat_b200_comm *c, uint64_t *out, uint64_t len);
+/* The same without leaving the device: d_out[treat_b200_summary_len] = sum over ranks, enqueued on `stream` (a
+ * cudaStream_t; NULL = the context's stream) behind the align calls issued on it. */
+int treat_b200_comm_reduce_summary_device(treat_b200_comm *c, uint64_t *d_out, void *stream);
+const char *treat_b200_comm_last_error(const treat_b200_comm *c);
+/* version of the NCCL library in use (e.g. 22809), 0 when none could be loaded */
+int32_t treat_b200_nccl_version(void);
 
 /* =====================================================================================
  * Host-side mirror of the reference's Go API (no GPU work).  Implemented in C++ under

@@ -14,6 +14,9 @@
  *   p=0.05 one substitution, p=0.01 three substitutions, p=0.02 one single-base insertion or
  *   deletion, p=0.002 one 'N'; p_trunc: cut U{0..100} bases off the 5' or 3' end;
  *   ReadCount c ~ 1 + Geom(1/50).
+ * synth_reads_noisy adds, from a second stream keyed the same way (so the base model's draws stay as they are):
+ *   every base substituted with probability p_sub_base, and with probability p_indel_read one more single-base
+ *   insertion or deletion -- the "noisy" point of bench.py (sequencing errors on top of the editing pattern).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -48,17 +51,37 @@ uint64_t synth_max_len(int m, const uint32_t *edit_site, int K)
     return tot;
 }
 
+static const char alpha[3] = {'A', 'C', 'G'};
+
+/* one single-base insertion or deletion at a random base of (bs, cnt, n) */
+static int one_indel(uint64_t *st, uint8_t *bs, uint32_t *cnt, int n)
+{
+    const int p = (int)rnd(st, (uint32_t)n);
+    if (rnd(st, 2)) { /* deletion of base p: its edit-base run merges into the next site */
+        cnt[p + 1] += cnt[p];
+        memmove(bs + p, bs + p + 1, (size_t)(n - p - 1));
+        memmove(cnt + p, cnt + p + 1, sizeof(uint32_t) * (size_t)(n - p));
+        return n - 1;
+    }
+    /* insertion in front of base p, carrying no edit bases */
+    memmove(bs + p + 1, bs + p, (size_t)(n - p));
+    memmove(cnt + p + 1, cnt + p, sizeof(uint32_t) * (size_t)(n + 1 - p));
+    bs[p] = (uint8_t)alpha[rnd(st, 3)];
+    cnt[p] = 0;
+    return n + 1;
+}
+
 /* returns the number of sequence bytes written, or 0 if cap is too small */
-uint64_t synth_reads(const uint8_t *bases, int m, const uint32_t *edit_site, int K, const int *alt_start,
-                     const int *alt_end, uint8_t edit_base, uint64_t seed, uint64_t first, uint64_t N,
-                     double p_trunc, uint8_t *seqs, uint64_t cap, uint64_t *off, uint32_t *read_count)
+uint64_t synth_reads_noisy(const uint8_t *bases, int m, const uint32_t *edit_site, int K, const int *alt_start,
+                           const int *alt_end, uint8_t edit_base, uint64_t seed, uint64_t first, uint64_t N,
+                           double p_trunc, double p_sub_base, double p_indel_read, uint8_t *seqs, uint64_t cap,
+                           uint64_t *off, uint32_t *read_count)
 {
     const int len = m + 1;
     const uint32_t *FE = edit_site, *PE = edit_site + len;
-    uint32_t *cnt = malloc(sizeof(uint32_t) * (size_t)(len + 2));
-    uint8_t *bs = malloc((size_t)m + 4);
+    uint32_t *cnt = malloc(sizeof(uint32_t) * (size_t)(len + 4));
+    uint8_t *bs = malloc((size_t)m + 8);
     uint64_t pos = 0;
-    static const char alpha[3] = {'A', 'C', 'G'};
     off[0] = 0;
     for (uint64_t r = 0; r < N; r++) {
         uint64_t st = seed ^ ((first + r + 1) * 0xD1342543DE82EF95ULL);
@@ -97,22 +120,19 @@ uint64_t synth_reads(const uint8_t *bases, int m, const uint32_t *edit_site, int
             do c = alpha[rnd(&st, 3)]; while (c == (char)bs[p]);
             bs[p] = (uint8_t)c;
         }
-        if (uni(&st) < 0.02 && n > 1) {
-            const int p = (int)rnd(&st, (uint32_t)n);
-            if (rnd(&st, 2)) { /* deletion of base p: its edit-base run merges into the next site */
-                cnt[p + 1] += cnt[p];
-                memmove(bs + p, bs + p + 1, (size_t)(n - p - 1));
-                memmove(cnt + p, cnt + p + 1, sizeof(uint32_t) * (size_t)(n - p));
-                n--;
-            } else { /* insertion in front of base p, carrying no edit bases */
-                memmove(bs + p + 1, bs + p, (size_t)(n - p));
-                memmove(cnt + p + 1, cnt + p, sizeof(uint32_t) * (size_t)(n + 1 - p));
-                bs[p] = (uint8_t)alpha[rnd(&st, 3)];
-                cnt[p] = 0;
-                n++;
-            }
-        }
+        if (uni(&st) < 0.02 && n > 1) n = one_indel(&st, bs, cnt, n);
         if (uni(&st) < 0.002 && n > 0) bs[rnd(&st, (uint32_t)n)] = 'N';
+        if (p_sub_base > 0 || p_indel_read > 0) { /* sequencing noise, from its own stream */
+            uint64_t s2 = seed ^ ((first + r + 1) * 0x9FB21C651E98DF25ULL);
+            splitmix64(&s2);
+            for (int i = 0; i < n; i++)
+                if (uni(&s2) < p_sub_base) {
+                    char c;
+                    do c = alpha[rnd(&s2, 3)]; while (c == (char)bs[i]);
+                    bs[i] = (uint8_t)c;
+                }
+            if (uni(&s2) < p_indel_read && n > 1) n = one_indel(&s2, bs, cnt, n);
+        }
         int lo = 0, hi = n; /* bases kept: [lo, hi) */
         if (p_trunc > 0 && uni(&st) < p_trunc) {
             int cut = (int)rnd(&st, 101);
@@ -142,6 +162,14 @@ uint64_t synth_reads(const uint8_t *bases, int m, const uint32_t *edit_site, int
     free(cnt);
     free(bs);
     return pos;
+}
+
+uint64_t synth_reads(const uint8_t *bases, int m, const uint32_t *edit_site, int K, const int *alt_start,
+                     const int *alt_end, uint8_t edit_base, uint64_t seed, uint64_t first, uint64_t N,
+                     double p_trunc, uint8_t *seqs, uint64_t cap, uint64_t *off, uint32_t *read_count)
+{
+    return synth_reads_noisy(bases, m, edit_site, K, alt_start, alt_end, edit_base, seed, first, N, p_trunc, 0.0, 0.0, seqs,
+                             cap, off, read_count);
 }
 
 /* synthetic long-gene template set (config 5): m bases U{A,C,G}; FE counts with an RPS12-like

@@ -22,7 +22,7 @@ NVCC_FLAGS = [
 ]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra"]
 
-CUDA_SOURCES = ["pack_kernel.cu", "align_kernel.cu", "fasta_kernel.cu", "text_kernel.cu", "capi.cu"]
+CUDA_SOURCES = ["pack_kernel.cu", "align_kernel.cu", "fasta_kernel.cu", "text_kernel.cu", "capi.cu", "group.cu"]
 CXX_SOURCES = ["host/treat_host.cpp", "host/capi_host.cpp"]
 HEADERS = ["device_format.h", "ptx_helpers.cuh", "host/treat_host.hpp", "../../include/treat_b200.h"]
 
@@ -75,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
     if force or _stale(LIB, objs):
         _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
-             + ["-cudart", "static", "-Xlinker", "--no-undefined"], verbose)
+             + ["-cudart", "static", "-Xlinker", "--no-undefined", "-ldl"], verbose)
     cli_src = os.path.join(CSRC, "cli", "treat_align.cpp")
     if force or _stale(CLI, [cli_src, LIB] + hdrs):
         _run([os.environ.get("CXX", "g++")] + CXX_FLAGS + [cli_src, "-o", CLI, "-L" + PKG, "-ltreat_b200",

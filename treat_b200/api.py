@@ -25,7 +25,7 @@ from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, OPS_GAPPED_ONLY, RECORD_DT
 __all__ = [
     "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
     "NewTemplate", "NewTemplateFromFasta", "parseMergeCount", "PrintAlignment", "read_fasta", "TreatError",
-    "marshal_batch", "mutant_report",
+    "marshal_batch", "mutant_report", "DeviceGroup", "Comm",
 ]
 
 
@@ -679,3 +679,123 @@ class Aligner:
             return C.string_at(out.value, n.value).decode("latin-1")
         finally:
             lib().treat_b200_free(out)
+
+
+class DeviceGroup:
+    """Several GPUs of one process behind one handle (treat_b200_group_*): one context and one host worker thread per
+    device, the batch cut into contiguous read ranges, the summary counters summed by ncclAllReduce inside the library."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, n: Optional[int] = None):
+        devs = list(devices) if devices is not None else list(range(n or 1))
+        arr = (C.c_int * len(devs))(*devs)
+        self._g = C.c_void_p()
+        check(lib().treat_b200_group_create(arr, len(devs), C.byref(self._g)))
+        self.devices = devs
+
+    def _check(self, code: int) -> None:
+        if code != cabi.OK:
+            raise TreatError(code, lib().treat_b200_group_last_error(self._g).decode())
+
+    def close(self):
+        if getattr(self, "_g", None):
+            lib().treat_b200_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return lib().treat_b200_group_size(self._g)
+
+    def SetTemplate(self, tmpl: Template) -> None:
+        self._check(lib().treat_b200_group_use_template(self._g, tmpl._h))
+
+    def ops_stride(self, max_len: int) -> int:
+        return lib().treat_b200_group_ops_stride(self._g, max_len)
+
+    def align_batch(self, seqs: np.ndarray, seq_off: np.ndarray, read_count: Optional[np.ndarray] = None,
+                    flags: int = WANT_OPS, rec: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None):
+        """treat_b200_group_align_batch: same arguments and results as Aligner.align_batch, reads shared between the GPUs."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        N = len(seq_off) - 1
+        if rec is None:
+            rec = np.zeros(N, dtype=RECORD_DTYPE)
+        stride = 0
+        if flags & WANT_OPS:
+            if ops is None:
+                max_len = int((seq_off[1:] - seq_off[:-1]).max()) if N else 0
+                stride = self.ops_stride(max_len)
+                ops = np.zeros((N, stride), dtype=np.uint8)
+            else:
+                stride = ops.shape[1]
+        rc = None if read_count is None else np.ascontiguousarray(read_count, dtype=np.uint32)
+        dummy = np.zeros(1, np.uint8)
+        self._check(lib().treat_b200_group_align_batch(
+            self._g, seqs.ctypes.data if seqs.size else dummy.ctypes.data, seq_off.ctypes.data,
+            rc.ctypes.data if rc is not None else None, N, flags, rec.ctypes.data,
+            ops.ctypes.data if (flags & WANT_OPS) else None, stride))
+        return rec, (ops if flags & WANT_OPS else None)
+
+    def summary(self, from_rank: int = 0) -> np.ndarray:
+        """All-GPU summary counters (one grouped ncclAllReduce), read from device `from_rank`."""
+        n = lib().treat_b200_summary_len(lib().treat_b200_group_ctx(self._g, 0))
+        out = np.zeros(n, dtype=np.uint64)
+        self._check(lib().treat_b200_group_summary(self._g, from_rank, out.ctypes.data, n))
+        return out
+
+    def heatmap(self, from_rank: int = 0) -> np.ndarray:
+        d = lib().treat_b200_heatmap_dim(lib().treat_b200_group_ctx(self._g, 0))
+        out = np.zeros((d, d), dtype=np.uint64)
+        self._check(lib().treat_b200_group_heatmap(self._g, from_rank, out.ctypes.data, d * d))
+        return out
+
+    def reset_summary(self) -> None:
+        self._check(lib().treat_b200_group_reset_summary(self._g))
+
+    def launch_count(self) -> int:
+        return lib().treat_b200_group_launch_count(self._g)
+
+
+class Comm:
+    """One process per GPU: the library's own NCCL communicator over an Aligner's context (treat_b200_comm_*).  Rank 0
+    makes the id (Comm.unique_id()) and the host program hands it to the other ranks."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * cabi.COMM_ID_BYTES)()
+        check(lib().treat_b200_comm_unique_id(buf, cabi.COMM_ID_BYTES))
+        return bytes(buf)
+
+    def __init__(self, engine: Aligner, nranks: int, rank: int, uid: Optional[bytes] = None):
+        self._c = C.c_void_p()
+        self.engine, self.nranks, self.rank = engine, nranks, rank
+        buf = (C.c_uint8 * cabi.COMM_ID_BYTES).from_buffer_copy(uid) if uid else None
+        check(lib().treat_b200_comm_create(engine._ctx, nranks, rank, buf, cabi.COMM_ID_BYTES if uid else 0, C.byref(self._c)))
+
+    def _check(self, code: int) -> None:
+        if code != cabi.OK:
+            raise TreatError(code, lib().treat_b200_comm_last_error(self._c).decode())
+
+    def close(self):
+        if getattr(self, "_c", None):
+            lib().treat_b200_comm_destroy(self._c)
+            self._c = None
+
+    def reduce_summary(self) -> np.ndarray:
+        n = lib().treat_b200_summary_len(self.engine._ctx)
+        out = np.zeros(n, dtype=np.uint64)
+        self._check(lib().treat_b200_comm_reduce_summary(self._c, out.ctypes.data, n))
+        return out
+
+    def reduce_heatmap(self) -> np.ndarray:
+        d = lib().treat_b200_heatmap_dim(self.engine._ctx)
+        out = np.zeros((d, d), dtype=np.uint64)
+        self._check(lib().treat_b200_comm_reduce_heatmap(self._c, out.ctypes.data, d * d))
+        return out
+
+    def reduce_summary_device(self, d_out: int, stream: int = 0) -> None:
+        self._check(lib().treat_b200_comm_reduce_summary_device(self._c, d_out, stream or None))

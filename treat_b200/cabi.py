@@ -21,6 +21,7 @@ DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY, HEATMAP, WANT_BLOBS = 0x20, 0x40
 ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16
+COMM_ID_BYTES = 128
 
 RECORD_DTYPE = np.dtype(
     [
@@ -44,6 +45,13 @@ class Packed(C.Structure):
         ("d_n", C.c_void_p), ("d_flags", C.c_void_p), ("d_bases", C.c_void_p), ("d_counts", C.c_void_p),
         ("d_raw_len", C.c_void_p),
     ]
+
+
+class AlignGeometry(C.Structure):
+    """treat_b200_geometry"""
+    _fields_ = [(n, C.c_uint32) for n in ("cpl", "strips", "reads_per_warp", "warps_per_cta", "smem_cta_bytes", "smem_template_bytes",
+                                          "smem_warp_bytes", "band_rows", "band_diagonals", "scratch_bytes_per_warp", "regs_per_thread",
+                                          "occupancy_warps_per_sm")]
 
 
 class FastaPiece(C.Structure):
@@ -98,6 +106,7 @@ SIGNATURES = {
     "treat_b200_align_packed_device": (C.c_int, [_P, C.POINTER(Packed), _P, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
     "treat_b200_launch_count": (C.c_uint64, [_P]),
     "treat_b200_set_band_rows": (C.c_int, [_P, C.c_uint32]),
+    "treat_b200_align_geometry": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(AlignGeometry)]),
     "treat_b200_debug_flags": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "treat_b200_summary_bins": (C.c_uint32, [_P]),
     "treat_b200_summary_len": (C.c_uint64, [_P]),
@@ -105,6 +114,28 @@ SIGNATURES = {
     "treat_b200_reset_summary": (C.c_int, [_P]),
     "treat_b200_summary_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "treat_b200_measure_int32_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "treat_b200_measure_h2d": (C.c_int, [_P, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
+    "treat_b200_group_create": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    "treat_b200_group_destroy": (None, [_P]),
+    "treat_b200_group_size": (C.c_int32, [_P]),
+    "treat_b200_group_ctx": (_P, [_P, C.c_int32]),
+    "treat_b200_group_last_error": (C.c_char_p, [_P]),
+    "treat_b200_group_set_template": (C.c_int, [_P, _U8P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, C.c_uint32, C.c_int32, C.c_uint8]),
+    "treat_b200_group_use_template": (C.c_int, [_P, _P]),
+    "treat_b200_group_align_batch": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, _P, _U8P, C.c_uint32]),
+    "treat_b200_group_ops_stride": (C.c_uint32, [_P, C.c_uint32]),
+    "treat_b200_group_summary": (C.c_int, [_P, C.c_int32, _P, C.c_uint64]),
+    "treat_b200_group_heatmap": (C.c_int, [_P, C.c_int32, _P, C.c_uint64]),
+    "treat_b200_group_reset_summary": (C.c_int, [_P]),
+    "treat_b200_group_launch_count": (C.c_uint64, [_P]),
+    "treat_b200_comm_unique_id": (C.c_int, [_U8P, _SZ]),
+    "treat_b200_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, _U8P, _SZ, C.POINTER(_P)]),
+    "treat_b200_comm_destroy": (None, [_P]),
+    "treat_b200_comm_reduce_summary": (C.c_int, [_P, _P, C.c_uint64]),
+    "treat_b200_comm_reduce_heatmap": (C.c_int, [_P, _P, C.c_uint64]),
+    "treat_b200_comm_reduce_summary_device": (C.c_int, [_P, _P, _P]),
+    "treat_b200_comm_last_error": (C.c_char_p, [_P]),
+    "treat_b200_nccl_version": (C.c_int32, []),
     "treat_b200_parse_merge_count": (C.c_uint32, [C.c_char_p, _SZ]),
     "treat_b200_new_fragment": (C.c_int, [_U8P, _SZ, C.c_int, C.c_uint8, _U8P, _P, C.POINTER(_SZ)]),
     "treat_b200_template_from_fasta": (C.c_int, [C.c_char_p, C.c_int, C.c_uint8, C.c_int32, C.POINTER(_P), C.c_char_p, _SZ]),

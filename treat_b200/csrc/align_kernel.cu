@@ -1612,6 +1612,40 @@ int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_opti
     }
 }
 
+template <typename Kern>
+static int kernel_regs(Kern kern)
+{
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, kern) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.numRegs;
+}
+
+template <int CPL>
+static int regs_cpl(const AlignParams &p, bool wide)
+{
+    if (p.pair) return kernel_regs(k_align2<CPL>);
+    return wide ? kernel_regs(k_align<CPL, true>) : kernel_regs(k_align<CPL, false>);
+}
+
+int align_kernel_regs(const AlignParams &p, bool wide)
+{
+    if (p.strips > 1) return wide ? kernel_regs(k_align_strips<true>) : kernel_regs(k_align_strips<false>);
+    switch (pick_cpl(p.t.m)) {
+    case 1: return regs_cpl<1>(p, wide);
+    case 2: return regs_cpl<2>(p, wide);
+    case 4: return regs_cpl<4>(p, wide);
+    case 6: return regs_cpl<6>(p, wide);
+    case 7: return regs_cpl<7>(p, wide);
+    case 10: return regs_cpl<10>(p, wide);
+    case 12: return regs_cpl<12>(p, wide);
+    case 15: return regs_cpl<15>(p, wide);
+    default: return 0;
+    }
+}
+
 int launch_same_bases(const AlignParams &planned, int num_sms, void *stream)
 {
     AlignParams p = planned;

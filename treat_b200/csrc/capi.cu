@@ -560,6 +560,36 @@ int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows)
     return TREAT_B200_OK;
 }
 
+int treat_b200_align_geometry(treat_b200_ctx *ctx, uint32_t max_n, uint32_t flags, treat_b200_geometry *out)
+{
+    if (!ctx || !out) return TREAT_B200_ERR_INVALID;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "geometry: no template");
+    memset(out, 0, sizeof *out);
+    AlignParams ap{};
+    ap.t = ctx->td;
+    ap.ncap = max_n;
+    ap.bins = ctx->bins;
+    ap.summary = (flags & TREAT_B200_NO_SUMMARY) ? nullptr : ctx->d_summary;
+    ap.force_single = (flags & TREAT_B200_ONE_READ_PER_WARP) ? 1u : 0u;
+    ap.band_rows = ctx->band_rows;
+    if (plan_align(ap, ctx->tmpl_wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "geometry: template too long");
+    const int warps = align_warps(ap, ctx->max_smem);
+    if (warps < 1) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "geometry: read/template geometry exceeds shared memory");
+    out->cpl = ap.cpl;
+    out->strips = ap.strips;
+    out->reads_per_warp = ap.pair ? 2u : 1u;
+    out->warps_per_cta = (uint32_t)warps;
+    out->smem_template_bytes = ap.sm_tmpl_bytes;
+    out->smem_warp_bytes = ap.sm_warp_bytes;
+    out->smem_cta_bytes = ap.sm_tmpl_bytes + (uint32_t)warps * ap.sm_warp_bytes;
+    out->band_rows = ap.band_rows;
+    out->band_diagonals = ap.band_chunks ? ap.band_chunks * (ap.cpl + 1) - 1 : 0;
+    out->scratch_bytes_per_warp = (uint32_t)(align_scratch_bytes(ap, 1, ctx->max_smem) / (uint64_t)warps);
+    out->regs_per_thread = (uint32_t)align_kernel_regs(ap, ctx->tmpl_wide);
+    out->occupancy_warps_per_sm = (uint32_t)warps;
+    return TREAT_B200_OK;
+}
+
 int treat_b200_packed_layout(const treat_b200_ctx *ctx, uint64_t N, uint32_t max_len, uint32_t wide,
                              treat_b200_packed *out)
 {
@@ -2120,4 +2150,32 @@ int treat_b200_measure_int32_peak(treat_b200_ctx *ctx, double *lane_ops_per_s, d
     return TREAT_B200_OK;
 }
 
+int treat_b200_measure_h2d(treat_b200_ctx *ctx, const void *host, uint64_t bytes, int32_t reps, double *ms_per_copy)
+{
+    if (!ctx || !host || !bytes || reps < 1 || !ms_per_copy) return TREAT_B200_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    CK(ctx, cudaMalloc(&d, bytes));
+    cudaEvent_t e0, e1;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    CK(ctx, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));  // warm-up (page tables, clocks)
+    CK(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < reps; i++) CK(ctx, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaEventRecord(e1, ctx->stream));
+    CK(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *ms_per_copy = (double)ms / reps;
+    return TREAT_B200_OK;
+}
+
 }  // extern "C"
+
+namespace treat_b200 {
+int ctx_device(const treat_b200_ctx *ctx) { return ctx->device; }
+cudaStream_t ctx_stream(treat_b200_ctx *ctx) { return ctx->stream; }
+}  // namespace treat_b200

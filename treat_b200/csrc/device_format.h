@@ -164,6 +164,7 @@ int launch_same_bases(const AlignParams &p, int num_sms, void *stream);
 // fills the shared-memory geometry of p for (m, K, ncap, wide); returns columns-per-lane or -1
 int plan_align(AlignParams &p, bool wide);
 int align_warps(const AlignParams &p, int max_smem);
+int align_kernel_regs(const AlignParams &p, bool wide);  // registers per thread of the kernel launch_align would pick
 uint64_t align_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
 int launch_merge_summary(uint64_t *dst, uint64_t *src, uint32_t len, void *stream);
 int launch_heatmap(const treat_b200_record *d_rec, uint64_t N, int edit_offset, uint32_t n, uint64_t *d_heat, int num_sms, void *stream);
@@ -183,5 +184,11 @@ int launch_peek(void *h_dst, const void *d_src, uint32_t bytes, void *stream);
 int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream);
 int configure_pack_kernels(int max_smem_optin);
 int configure_align_kernels(int max_smem_optin);
+
+// context internals other translation units need (group.cu)
+int ctx_device(const treat_b200_ctx *ctx);
+#ifdef __CUDACC__
+cudaStream_t ctx_stream(treat_b200_ctx *ctx);
+#endif
 
 }  // namespace treat_b200

@@ -61,3 +61,36 @@ def reduced_summary(engine, group=None) -> np.ndarray:
     t = summary_tensor(engine).clone()
     allreduce_summary(t, group)
     return t.cpu().numpy().view(np.uint64)
+
+
+# ---- digests of a batch's results: the same bytes whatever the number of GPUs (bench.py's parity leg, tests) -------------
+_CANON_FIELDS = ("edit_stop", "junc_start", "junc_end", "junc_len", "read_count", "has_mutation", "alt_editing",
+                 "mismatches", "indel", "score", "junc_seq_off", "junc_seq_len", "aln_len", "n_bases", "status")
+
+
+def canonical_records(rec: np.ndarray) -> np.ndarray:
+    """The per-read record fields the reference defines (Alignment: align.go:41-55, score, JuncSeq window, lengths) as a
+    packed array: the JuncSeq offset only where a JuncSeq exists, of the status byte only the reference-panic bit."""
+    from .cabi import RECORD_DTYPE
+    out = np.zeros(len(rec), dtype=RECORD_DTYPE)
+    for f in _CANON_FIELDS:
+        out[f] = rec[f]
+    out["junc_seq_off"] = np.where(rec["junc_seq_len"] > 0, rec["junc_seq_off"], 0)
+    out["status"] = rec["status"] & 1
+    return out
+
+
+def compact_ops(rec: np.ndarray, ops: np.ndarray) -> np.ndarray:
+    """The bytes of every read's ops row that hold alignment columns (ceil(aln_len / 4) per read), back to back: the
+    traceback of the batch independent of the row stride."""
+    nbytes = (rec["aln_len"].astype(np.int64) + 3) // 4
+    keep = np.arange(ops.shape[1], dtype=np.int64)[None, :] < nbytes[:, None]
+    return ops[keep]
+
+
+def sha256_hex(*chunks) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for c in chunks:
+        h.update(memoryview(np.ascontiguousarray(c)).cast("B"))
+    return h.hexdigest()

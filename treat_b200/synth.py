@@ -39,6 +39,10 @@ def _l():
         L.synth_reads.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint8,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_uint64, C.c_void_p,
                                   C.c_void_p]
+        L.synth_reads_noisy.restype = C.c_uint64
+        L.synth_reads_noisy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint8,
+                                        C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.c_void_p]
         L.synth_long_template.restype = None
         L.synth_long_template.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -126,16 +130,17 @@ def long_template(m: int = 300, n_alt: int = 8, seed: int = SEED_BASE + 5) -> Te
 
 
 def reads(t: TemplateArrays, N: int, seed: int = SEED_BASE + 3, first: int = 0, p_trunc: float = 0.0,
-          pinned_alloc=None):
-    """Generate reads [first, first+N): returns (seqs uint8, seq_off uint64[N+1], read_count uint32[N])."""
+          pinned_alloc=None, p_sub_base: float = 0.0, p_indel_read: float = 0.0):
+    """Generate reads [first, first+N): returns (seqs uint8, seq_off uint64[N+1], read_count uint32[N]).
+    p_sub_base / p_indel_read: sequencing noise on top of the model (per-base substitutions, one more indel per read)."""
     L = _l()
-    mx = int(L.synth_max_len(t.m, t.edit_site.ctypes.data, t.K))
+    mx = int(L.synth_max_len(t.m, t.edit_site.ctypes.data, t.K)) + 2
     cap = mx * max(N, 1)
     seqs = pinned_alloc(cap) if pinned_alloc else np.empty(cap, dtype=np.uint8)
     off = np.zeros(N + 1, dtype=np.uint64)
     rc = np.zeros(N, dtype=np.uint32)
-    used = L.synth_reads(t.bases, t.m, t.edit_site.ctypes.data, t.K, t.alt_start.ctypes.data, t.alt_end.ctypes.data,
-                         ord(t.edit_base), seed, first, N, p_trunc, seqs.ctypes.data, cap, off.ctypes.data,
-                         rc.ctypes.data)
+    used = L.synth_reads_noisy(t.bases, t.m, t.edit_site.ctypes.data, t.K, t.alt_start.ctypes.data, t.alt_end.ctypes.data,
+                               ord(t.edit_base), seed, first, N, p_trunc, p_sub_base, p_indel_read, seqs.ctypes.data, cap,
+                               off.ctypes.data, rc.ctypes.data)
     assert used > 0 or N == 0
     return seqs[:used], off, rc
