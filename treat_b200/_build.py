@@ -22,9 +22,9 @@ NVCC_FLAGS = [
 ]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra"]
 
-CUDA_SOURCES = ["pack_kernel.cu", "align_kernel.cu", "fasta_kernel.cu", "text_kernel.cu", "capi.cu", "group.cu"]
+CUDA_SOURCES = ["pack_kernel.cu", "align_kernel.cu", "fused_kernel.cu", "fasta_kernel.cu", "text_kernel.cu", "capi.cu", "group.cu"]
 CXX_SOURCES = ["host/treat_host.cpp", "host/capi_host.cpp"]
-HEADERS = ["device_format.h", "ptx_helpers.cuh", "host/treat_host.hpp", "../../include/treat_b200.h"]
+HEADERS = ["device_format.h", "ptx_helpers.cuh", "assembly.cuh", "host/treat_host.hpp", "../../include/treat_b200.h"]
 
 
 def _nvcc() -> str:

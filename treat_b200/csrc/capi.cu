@@ -342,6 +342,7 @@ int treat_b200_create(int device, treat_b200_ctx **out)
     int e = configure_pack_kernels(ctx->max_smem);
     if (!e) e = configure_align_kernels(ctx->max_smem);
     if (!e) e = configure_text_kernels(ctx->max_smem);
+    if (!e) e = configure_fused_kernels(ctx->max_smem);
     if (e) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -621,11 +622,10 @@ static int ensure_scalars(treat_b200_ctx *ctx, Slot &s)
     return TREAT_B200_OK;
 }
 
-static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
-                   const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st, const ReadSpan *span = nullptr,
-                   bool padded = false)
+static int fill_pack_params(treat_b200_ctx *ctx, PackParams &pp, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
+                            const treat_b200_packed *dst, uint32_t *d_scalars, const ReadSpan *span, bool padded)
 {
-    PackParams pp{};
+    pp = PackParams{};
     pp.seqs = d_seqs;
     pp.off = d_off;
     pp.off_bias = off_bias;
@@ -651,6 +651,16 @@ static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d
     } else if (span) {
         return fail(ctx, TREAT_B200_ERR_INVALID, "pack: in-place reads are not supported on the wide path");
     }
+    return TREAT_B200_OK;
+}
+
+static int do_pack(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
+                   const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st, const ReadSpan *span = nullptr,
+                   bool padded = false)
+{
+    PackParams pp;
+    int rc = fill_pack_params(ctx, pp, d_seqs, d_off, off_bias, dst, d_scalars, span, padded);
+    if (rc) return rc;
     int e = launch_pack(pp, dst->wide != 0, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: read too long for shared-memory staging");
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_pack launch: ") + cudaGetErrorString((cudaError_t)e));
@@ -666,21 +676,21 @@ struct AlignOpts {
     uint32_t *list_count = nullptr;   //   (must be zero on entry)
     uint32_t *ops_idx = nullptr;      // with ops_count: compact the ops rows (OPS_GAPPED_ONLY on the host-buffer path)
     uint32_t *ops_count = nullptr;    //   (must be zero on entry)
+    bool listed = false;              // the list is already filled (k_pack_finish ran): no k_same_bases launch
 };
 
-static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t ncap, const uint32_t *d_read_count,
-                    uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st,
-                    DevBuf &scratch, const AlignOpts &o = AlignOpts())
+// the parameter block of an align launch (everything but the shared-memory plan, the scratch and the list)
+static int fill_align_params(treat_b200_ctx *ctx, AlignParams &ap, const treat_b200_packed *src, uint32_t ncap,
+                             const uint32_t *d_read_count, uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops,
+                             uint32_t ops_stride, const AlignOpts &o)
 {
     uint64_t *summary_override = o.summary;
-    uint32_t *d_skipped = o.skipped, *d_list_count = o.list_count;
-    DevBuf *list = o.list;
-    if (src->N == 0) return TREAT_B200_OK;
+    uint32_t *d_skipped = o.skipped;
     if (src->N > 0x7fffffffull) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: more than 2^31 reads in one launch");
     const bool wide = src->wide != 0;
     if (!wide && ctx->tmpl_wide)
         return fail(ctx, TREAT_B200_ERR_INVALID, "align: this template needs wide-packed reads (wide=1)");
-    AlignParams ap{};
+    ap = AlignParams{};
     ap.n = src->d_n;
     ap.rflags = src->d_flags;
     ap.bases = src->d_bases;
@@ -714,6 +724,20 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
         if (ops_stride % 16 || ops_stride < a16(((uint32_t)ctx->td.m + ncap + 3) / 4))
             return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small or not a multiple of 16");
     }
+    return TREAT_B200_OK;
+}
+
+static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t ncap, const uint32_t *d_read_count,
+                    uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, cudaStream_t st,
+                    DevBuf &scratch, const AlignOpts &o = AlignOpts())
+{
+    uint32_t *d_list_count = o.list_count;
+    DevBuf *list = o.list;
+    if (src->N == 0) return TREAT_B200_OK;
+    const bool wide = src->wide != 0;
+    AlignParams ap;
+    int frc = fill_align_params(ctx, ap, src, ncap, d_read_count, flags, d_rec, d_ops, ops_stride, o);
+    if (frc) return frc;
     // The reads k_same_bases leaves for the DP are the hard ones (truncated reads fill into the global scratch).  With more
     // than 7 columns per lane the two-reads-per-warp kernel's scratch (8 bytes per lane and step) no longer fits L2 for
     // them, so listed reads of long templates take the one-read kernel; the paired one serves whole batches.
@@ -732,12 +756,14 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     // reads marked by k_pack as equal to the template are finished without a DP; the align kernel gets the rest.
     // *d_list_count must be zero on entry (the callers clear the slot's scalars before the pack).
     if (use_list) {
-        CK(ctx, list->reserve(src->N * 4));
+        if (!o.listed) CK(ctx, list->reserve(src->N * 4));
         ap.list = (uint32_t *)list->p;
         ap.list_count = d_list_count;
-        int e0 = launch_same_bases(ap, ctx->num_sms, st);
-        if (e0) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_same_bases launch: ") + cudaGetErrorString((cudaError_t)e0));
-        ctx->launches++;
+        if (!o.listed) {
+            int e0 = launch_same_bases(ap, ctx->num_sms, st);
+            if (e0) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_same_bases launch: ") + cudaGetErrorString((cudaError_t)e0));
+            ctx->launches++;
+        }
     }
     int e = launch_align(ap, wide, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000 || e == -1001)
@@ -789,6 +815,33 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
     return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st, ctx->dev_slot.scratch);
 }
 
+// K1f: pack + finish the reads that need no DP in one launch (k_pack_finish); the rest is listed for do_align(listed = true)
+static int do_pack_finish(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_off, uint64_t off_bias,
+                          const treat_b200_packed *dst, uint32_t *d_scalars, cudaStream_t st, const ReadSpan *span, bool padded,
+                          const uint32_t *d_read_count, uint32_t flags, treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride,
+                          const AlignOpts &o)
+{
+    if (dst->N == 0) return TREAT_B200_OK;
+    PackParams pp;
+    int rc = fill_pack_params(ctx, pp, d_seqs, d_off, off_bias, dst, d_scalars, span, padded);
+    if (rc) return rc;
+    AlignParams ap;
+    // sized for the template's own length: the reads finished here have n = m; the ops stride is checked by do_align
+    if ((rc = fill_align_params(ctx, ap, dst, (uint32_t)ctx->td.m, d_read_count, flags, d_rec, nullptr, ops_stride, o))) return rc;
+    ap.ops = (flags & TREAT_B200_WANT_OPS) ? d_ops : nullptr;
+    CK(ctx, o.list->reserve(dst->N * 4));
+    ap.list = (uint32_t *)o.list->p;
+    ap.list_count = o.list_count;
+    ap.ops_idx = nullptr;  // reads finished here have no gap: with compacted rows they own none
+    ap.ops_count = nullptr;
+    ap.skipped = nullptr;
+    int e = launch_pack_finish(pp, ap, ctx->num_sms, ctx->max_smem, st);
+    if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: read too long for shared-memory staging");
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_pack_finish launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
+    return TREAT_B200_OK;
+}
+
 // pack + (tiny sync for max n) + align on one slot's buffers
 // ops_stride == 0: the ops go to the slot's own buffer with the tightest legal stride (returned in
 // *ops_stride_used), so that the host copy moves only what the batch needs.
@@ -830,7 +883,34 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     rc = ensure_scalars(ctx, s);
     if (rc) return rc;
     CK(ctx, cudaMemsetAsync(s.scalars, 0, kScalarBytes, st));
-    rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded);
+    // K1f: reads whose bases equal the template's (or differ in one base) are finished by the kernel that strips them
+    static const bool no_fuse = getenv("TREAT_B200_NO_FUSE") != nullptr;
+    const bool fuse = !no_fuse && !wide && ctx->d_tpk.p && ctx->td.len <= 512 && !(flags & TREAT_B200_DP_EVERY_READ);
+    if (fuse) {
+        if ((flags & TREAT_B200_WANT_OPS) && d_ops == nullptr) {
+            // slot-owned rows: the fused kernel zeroes the rows of the reads it finishes, so they exist before it runs
+            // (sized for the launch's largest possible n: the speculative bound, or the longest raw read)
+            if (ops_stride == 0) ops_stride = a16(((uint32_t)ctx->td.m + (spec_ncap ? std::min(spec_ncap, max_len) : max_len) + 3) / 4);
+            CK(ctx, s.ops.reserve(N * (size_t)ops_stride));
+            d_ops = (uint8_t *)s.ops.p;
+        }
+        // its counters go to the slot's private summary: they join the context's once the chunk is known to be final (a
+        // saturated edit-base run sends the chunk to the wide path, a speculative launch is validated later)
+        uint64_t *slot_sum = nullptr;
+        if (!(flags & TREAT_B200_NO_SUMMARY)) {
+            const size_t sl = treat_b200_summary_len(ctx) * 8;
+            if (s.summary.cap < sl) {
+                CK(ctx, s.summary.reserve(sl));
+                CK(ctx, cudaMemsetAsync(s.summary.p, 0, sl, st));
+            }
+            slot_sum = (uint64_t *)s.summary.p;
+        }
+        AlignOpts o = opts(false);
+        o.summary = slot_sum;
+        rc = do_pack_finish(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded, d_rc, flags, d_rec, d_ops, ops_stride, o);
+    } else {
+        rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded);
+    }
     if (rc) return rc;
     if (spec_ncap) {
         const uint32_t ncap = std::min(spec_ncap, max_len);
@@ -852,6 +932,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         AlignOpts o = opts(slot_own_ops);
         o.summary = slot_sum;
         o.skipped = s.scalars + 2;
+        o.listed = fuse;
         rc = do_align(ctx, &pk, ncap, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, o);
         if (rc) return rc;
         CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, st));
@@ -862,6 +943,15 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     const uint32_t max_n = s.h_scalars[0];
     ctx->ncap_hint = std::max(ctx->ncap_hint, max_n);
     if (saturated) *saturated = s.h_scalars[1] != 0;
+    if (fuse && !(flags & TREAT_B200_NO_SUMMARY)) {
+        if (s.h_scalars[1]) {  // the chunk goes to the wide path: what the fused kernel counted is dropped
+            CK(ctx, cudaMemsetAsync(s.summary.p, 0, treat_b200_summary_len(ctx) * 8, st));
+        } else {
+            int e = launch_merge_summary(ctx->d_summary, (uint64_t *)s.summary.p, (uint32_t)treat_b200_summary_len(ctx), st);
+            if (e) return fail(ctx, TREAT_B200_ERR_CUDA, "k_merge_summary launch failed");
+            ctx->launches++;
+        }
+    }
     if (!wide && s.h_scalars[1]) return TREAT_B200_OK;  // caller re-runs this chunk on the wide path
     if ((flags & TREAT_B200_WANT_OPS) && d_ops == nullptr) {
         if (ops_stride == 0) ops_stride = a16(((uint32_t)ctx->td.m + max_n + 3) / 4);
@@ -869,7 +959,9 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         d_ops = (uint8_t *)s.ops.p;
     }
     if (ops_stride_used) *ops_stride_used = ops_stride;
-    rc = do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, opts(slot_own_ops));
+    AlignOpts oa = opts(slot_own_ops);
+    oa.listed = fuse;
+    rc = do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, oa);
     if (rc) return rc;
     return add_heatmap(ctx, flags, d_rec, N, st);  // a speculative launch is added once it is validated
 }

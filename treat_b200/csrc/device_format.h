@@ -159,6 +159,11 @@ int configure_text_kernels(int max_smem_optin);
 // launchers (pack_kernel.cu, align_kernel.cu)
 int launch_pack(const PackParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
 int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_optin, void *stream);
+// K1f (fused_kernel.cu): NewFragment for the batch + the editing-site assembly of the reads that need no DP in one pass;
+// the other reads are packed to HBM and listed in q.list for launch_align
+bool pack_finish_applies(const PackParams &p, const AlignParams &q);
+int launch_pack_finish(const PackParams &p, const AlignParams &q, int num_sms, int max_smem_optin, void *stream);
+int configure_fused_kernels(int max_smem_optin);
 // K2s: finishes the reads marked kFlagSameBases without a DP and lists the others (p is the plan_align'ed block)
 int launch_same_bases(const AlignParams &p, int num_sms, void *stream);
 // fills the shared-memory geometry of p for (m, K, ncap, wide); returns columns-per-lane or -1
