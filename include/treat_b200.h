@@ -10,7 +10,8 @@
  * Conventions: plain pointers and sizes, no C++ or torch types; every function returns
  * TREAT_B200_OK (0) or a negative TREAT_B200_ERR_* code and never throws; the callee does
  * not retain caller pointers after return (cgo pointer rule); one context = one GPU =
- * one caller thread at a time.  There is NO CPU fallback: without a usable CUDA device
+ * one caller thread at a time and one call in flight (no internal locking; the device-buffer
+ * entry points say what "in flight" means for them).  There is NO CPU fallback: without a usable CUDA device
  * treat_b200_create fails with TREAT_B200_ERR_NO_DEVICE.
  */
 #ifndef TREAT_B200_H
@@ -155,8 +156,13 @@ int treat_b200_use_template(treat_b200_ctx *ctx, const treat_b200_template *tmpl
 int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off,
                            const uint32_t *read_count, uint64_t N, uint32_t flags, treat_b200_record *rec,
                            uint8_t *ops, uint32_t ops_stride);
-/* same with every buffer already resident in device memory of ctx's GPU; max_len =
- * max_i len(read i); runs asynchronously on `stream` (a cudaStream_t, NULL = ctx stream). */
+/* same with every buffer already resident in device memory of ctx's GPU; max_len = max_i len(read i).  The kernels are
+ * launched on `stream` (a cudaStream_t, NULL = ctx stream) and the results are ready when the work queued on that stream
+ * is.  The call is NOT fully asynchronous: it waits once for `stream` (an 8-byte read-back of the longest stripped read,
+ * which sizes the DP launch).  Contract: ONE call in flight per context.  The packed reads, the DP list and the scratch of
+ * a call live in the context, so a second call on the same context -- from another stream or thread, including
+ * treat_b200_pack_device / treat_b200_align_packed_device -- must not start before the work of the first has finished on
+ * its stream.  For concurrent streams use one context per stream. */
 int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
                                   const uint32_t *d_read_count, uint64_t N, uint32_t max_len, uint32_t flags,
                                   treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, void *stream);
@@ -185,6 +191,15 @@ int treat_b200_pack_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
 int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed *src,
                                    const uint32_t *d_read_count, uint32_t flags, treat_b200_record *d_rec,
                                    uint8_t *d_ops, uint32_t ops_stride, void *stream);
+/* Traceback tie order: which pointer wins when several of Up (template base over '-'), Left ('-' over read base) and
+ * Diagonal are optimal in a cell.  The DP itself lives in the un-vendored module github.com/aebruno/nwalgo (align.go:129,
+ * 338,393); its published source takes Up, then Left, then Diagonal (the default here).  The reference's own goldens pin
+ * only "Up beats Diagonal" (SURVEY.md 8c), which these three orders satisfy; should nwalgo turn out to differ, this call is
+ * the whole fix.  Scores, and every read whose optimal alignment is unique, do not depend on it. */
+#define TREAT_B200_TIE_ULD 0 /* Up > Left > Diagonal (nwalgo as published; default) */
+#define TREAT_B200_TIE_UDL 1 /* Up > Diagonal > Left */
+#define TREAT_B200_TIE_LUD 2 /* Left > Up > Diagonal */
+int treat_b200_set_tie_order(treat_b200_ctx *ctx, int32_t order);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx);
 /* tuning: rows of traceback words kept per lane in shared memory (0 = default 64); any value is

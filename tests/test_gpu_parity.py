@@ -991,3 +991,46 @@ def test_zz_kernel_bounds_flags_clean(eng):
     library was built with TREAT_B200_CHECKS=1; a normal build always reports zero)."""
     flags, compiled = eng.debug_flags()
     assert flags == 0, "kernel bounds-check flags: 0x%x (checks compiled: %s)" % (flags, compiled)
+
+
+def test_tie_orders_match_oracle(eng, examples, tmp_path):
+    """treat_b200_set_tie_order: the three traceback orders the reference's goldens allow (Up > Left > Diagonal as nwalgo
+    publishes it, Up > Diagonal > Left, Left > Up > Diagonal) against the oracle's switch, on reads with many ties
+    (indels next to repeats) and on the synthetic sets; records and every ops row."""
+    rng = random.Random(4711)
+    srcs = [s for _, s in P.read_fasta(examples["templates.fa"])]
+    recs = [("t-%d" % (i + 1), _mutate(rng, rng.choice(srcs))) for i in range(600)]
+    # homopolymer / dinucleotide repeats make Left-vs-Diagonal and Up-vs-Left ties certain
+    recs += [("rep-%d" % i, "AAAAGGGGAAAACCCC"[: 4 + i % 12] * (1 + i % 5) + "ACG" * (i % 7)) for i in range(120)]
+    fb = T.FastaBatch.from_records(recs)
+    tm = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "T")
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    differ = 0
+    base_ops = None
+    try:
+        for order in ("ULD", "UDL", "LUD"):
+            O.set_tie_order(order)
+            eng.set_tie_order(order)
+            eng.SetTemplate(tm)
+            for extra in (0, cabi.DP_EVERY_READ, cabi.ONE_READ_PER_WARP | cabi.DP_EVERY_READ, cabi.FULL_TRACEBACK_STORE):
+                grec, gops = eng.align_batch(fb.seqs, fb.offsets, fb.read_counts, cabi.WANT_OPS | extra)
+                orec, oops, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, ops_stride=gops.shape[1])
+                assert compare_records(grec, orec) == [], (order, extra)
+                assert np.array_equal(gops, oops), (order, extra)
+            if base_ops is None:
+                base_ops = gops.copy()
+            else:
+                differ += int((gops != base_ops).any(axis=1).sum())
+            # the synthetic RPS12 and long-gene sets (paired kernel with two words per step, scratch fills)
+            for t, n, tr in ((synth.rps12_template(), 6000, 0.1), (synth.long_template(300, 8), 1500, 0.3)):
+                omt, tmt = _oracle_template(t, tmp_path)
+                eng.SetTemplate(tmt)
+                seqs, off, rc = synth.reads(t, n, seed=synth.SEED_BASE + 90, p_trunc=tr, p_sub_base=0.01, p_indel_read=0.3)
+                grec, gops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS)
+                orec, oops, _ = O.align_batch(omt, seqs, off, rc, ops_stride=gops.shape[1])
+                assert compare_records(grec, orec) == [], order
+                assert np.array_equal(gops, oops), order
+        assert differ > 0  # the orders do give different alignments on this set: the switch is not a no-op
+    finally:
+        O.set_tie_order("ULD")
+        eng.set_tie_order("ULD")

@@ -595,6 +595,10 @@ class Aligner:
     def synchronize(self) -> None:
         check(lib().treat_b200_synchronize(self._ctx), self._ctx)
 
+    def set_tie_order(self, order: str = "ULD") -> None:
+        """Traceback tie order of the DP kernels: "ULD" (nwalgo as published), "UDL" or "LUD" (treat_b200_set_tie_order)."""
+        check(lib().treat_b200_set_tie_order(self._ctx, cabi.TIE_ORDERS.index(order)), self._ctx)
+
     def debug_flags(self) -> Tuple[int, bool]:
         """(flag word, checks compiled in): non-zero flags mean a kernel index left its bounds."""
         f, c = C.c_uint32(), C.c_int32()

@@ -22,6 +22,7 @@ ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16
 COMM_ID_BYTES = 128
+TIE_ORDERS = ("ULD", "UDL", "LUD")
 
 RECORD_DTYPE = np.dtype(
     [
@@ -106,6 +107,7 @@ SIGNATURES = {
     "treat_b200_align_packed_device": (C.c_int, [_P, C.POINTER(Packed), _P, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
     "treat_b200_launch_count": (C.c_uint64, [_P]),
     "treat_b200_set_band_rows": (C.c_int, [_P, C.c_uint32]),
+    "treat_b200_set_tie_order": (C.c_int, [_P, C.c_int32]),
     "treat_b200_align_geometry": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(AlignGeometry)]),
     "treat_b200_debug_flags": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "treat_b200_summary_bins": (C.c_uint32, [_P]),

@@ -132,8 +132,8 @@ __device__ __forceinline__ uint32_t score_w(const AlignParams &p, int c, int col
 // of the read being traced.  Ops are OR-ed into the zeroed 2-bit array
 // ops2 at index p (matches are 0, so only gaps are written).  Returns pos (alignment = [pos, m+n)).
 // ------------------------------------------------------------------------------------------
-template <int CPL, typename GetW>
-__device__ __forceinline__ int traceback(GetW getw, uint32_t *ops2, int m, int n, int lane, int &ngaps)
+template <int CPL, typename GetW, typename IsMatch>
+__device__ __forceinline__ int traceback(GetW getw, IsMatch is_match, uint32_t tie, uint32_t *ops2, int m, int n, int lane, int &ngaps)
 {
     using DT = Dir<CPL>;
     int pos = m + n, i = m, j = n;
@@ -145,15 +145,24 @@ __device__ __forceinline__ int traceback(GetW getw, uint32_t *ops2, int m, int n
             const int ln = (ii - 1) / CPL, k = (ii - 1) - ln * CPL;
             const int tt = jj - 1 + ln;
             const uint32_t w1 = getw(tt, ln);
-            const uint32_t a = (w1 >> (2 * k)) & 3u;
-            if (a == 0) {
-                is_up = true;  // G[i][j] == G[i-1][j]
+            const bool pU = ((w1 >> (2 * k)) & 3u) == 0u;  // G[i][j] == G[i-1][j]: Up is optimal
+            if (pU && tie != TREAT_B200_TIE_LUD) {
+                is_up = true;  // Up first (ULD, UDL)
             } else {
                 // dV(i,j) = dV(left boundary of the lane, row j) + sum_{columns <= k} (dH(row j) - dH(row j-1))
                 const uint32_t msk = (4u << (2 * k)) - 1u;
-                uint32_t v = (w1 >> DT::kTop) + digit_sum(w1 & msk, DT::kOdd);
-                if (jj >= 2) v -= digit_sum(getw(tt - 1, ln) & msk, DT::kOdd);  // row 0 is all zero
-                stop = (v & 3u) == 0;  // G[i][j] == G[i][j-1]: Left
+                const uint32_t w0 = jj >= 2 ? getw(tt - 1, ln) : 0u;  // row 0 is all zero
+                const uint32_t v = (w1 >> DT::kTop) + digit_sum(w1 & msk, DT::kOdd) - digit_sum(w0 & msk, DT::kOdd);
+                const bool pL = (v & 3u) == 0u;  // G[i][j] == G[i][j-1]: Left is optimal
+                if (tie == TREAT_B200_TIE_ULD) {
+                    stop = pL;
+                } else if (tie == TREAT_B200_TIE_LUD) {
+                    stop = pL || pU;
+                    is_up = !pL && pU;
+                } else {  // UDL: Diagonal beats Left; with Left optimal the diagonal is too iff G[i-1][j-1] + w == G[i][j-1],
+                          // i.e. dH(i, j-1) == w(i, j)
+                    stop = pL && ((w0 >> (2 * k)) & 3u) != (is_match(ii - 1, jj - 1) ? 3u : 1u);
+                }
             }
         }
         const uint32_t sm = __ballot_sync(FULL_MASK, stop);
@@ -478,6 +487,7 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
             full = true;  // the path may leave the band: repeat the fill
         }
         int ngaps = 0, pos = n;  // alignment = ops2[pos, m + n)
+        auto same_base = [&](int ti, int fi) { return (int)rb[fi] == (int)cs.tb[ti]; };  // template base ti == read base fi
         if (score == m && n == m) {
             // every base matches: the only optimal path is the main diagonal (m zero ops, already zeroed)
         } else if (!full) {
@@ -486,14 +496,14 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
                     TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
                     return (uint32_t)s_dir[(tt - (ln - C) * P) * 32 + ln];
                 },
-                ws.ops2, m, n, lane, ngaps);
+                same_base, p.tie, ws.ops2, m, n, lane, ngaps);
         } else {
             pos = traceback<CPL>(
                 [&](int tt, int ln) {
                     TB_CHECK(p, (unsigned)(tt * 32 + ln) < p.scratch_stride, 1);
                     return (uint32_t)scratch[tt * 32 + ln];
                 },
-                ws.ops2, m, n, lane, ngaps);
+                same_base, p.tie, ws.ops2, m, n, lane, ngaps);
         }
         finish_read<cnt_t>(p, cs, ws, lane, r, n, rflags, score, pos, ngaps, rcount, [&](int fi) { return (int)rb[fi]; }, ctr);
     }
@@ -711,7 +721,7 @@ __global__ void __launch_bounds__(max_warps_one(kStripCpl) * 32, 1) k_align_stri
                     TB_CHECK(p, (unsigned)(row * 32 + l) < p.scratch_stride, 1);
                     return scratch[row * 32 + l];
                 },
-                ws.ops2, m, n, lane, ngaps);
+                [&](int ti, int fi) { return (int)rb[fi] == (int)cs.tb[ti]; }, p.tie, ws.ops2, m, n, lane, ngaps);
         }
         finish_read<cnt_t>(p, cs, ws, lane, r, n, rflags, score, pos, ngaps, rcount, [&](int fi) { return (int)rb[fi]; }, ctr);
     }
@@ -852,6 +862,10 @@ __global__ void __launch_bounds__(max_warps_pair(CPL) * 32, 1) k_align2(const __
             __syncwarp();
             int ngaps = 0, pos = n;  // alignment = ops2[pos, m + n)
             const int score = h ? score1 : score0;
+            auto same_base = [&](int ti, int fi) {  // template base ti == base fi of read h
+                const int c = pc[fi];
+                return (h ? c % 5 : c / 5) == (int)cs.tb[ti];
+            };
             if (score == m && n == m) {
                 // every base matches: the only optimal path is the main diagonal (m zero ops, already zeroed)
             } else if (banded)
@@ -860,14 +874,14 @@ __global__ void __launch_bounds__(max_warps_pair(CPL) * 32, 1) k_align2(const __
                         TB_CHECK(p, (unsigned)(tt - (ln - C) * P) < p.band_rows && (unsigned)ln < 32u, 0);
                         return pair_dir_word<CPL>(s_dir[(tt - (ln - C) * P) * 32 + ln], h);
                     },
-                    ws.ops2, m, n, lane, ngaps);
+                    same_base, p.tie, ws.ops2, m, n, lane, ngaps);
             else
                 pos = traceback<CPL>(
                     [&](int tt, int ln) {
                         TB_CHECK(p, (unsigned)(tt * 32 + ln) < p.scratch_stride, 1);
                         return pair_dir_word<CPL>(scratch[tt * 32 + ln], h);
                     },
-                    ws.ops2, m, n, lane, ngaps);
+                    same_base, p.tie, ws.ops2, m, n, lane, ngaps);
             const uint32_t r = h ? r1 : r0;
             finish_read<cnt_t>(p, cs, ws, lane, r, n, p.rflags[r], score, pos, ngaps, rcount,
                                [&](int fi) {

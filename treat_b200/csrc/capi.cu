@@ -224,6 +224,7 @@ struct treat_b200_ctx {
     DevBuf d_tpk;  // template bases in the packed-read format (16 codes per word): k_pack marks reads that equal it
     DevBuf d_tmax; // Template.Max(i) (template.go:186) for every edit site: column widths of WriteTo
     uint32_t band_rows = 0;  // 0 = default window
+    uint32_t tie = TREAT_B200_TIE_ULD;  // traceback tie order (treat_b200_set_tie_order)
     uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
     uint32_t gap_hint = 0;   // most gapped reads seen in a chunk: sizes the ahead-of-time copy of compacted ops rows
     uint32_t *d_dbg = nullptr;  // bounds-check flags (only written by TREAT_B200_CHECKS builds)
@@ -554,6 +555,15 @@ int treat_b200_debug_flags(treat_b200_ctx *ctx, uint32_t *flags_out, int32_t *ch
     return TREAT_B200_OK;
 }
 
+int treat_b200_set_tie_order(treat_b200_ctx *ctx, int32_t order)
+{
+    if (!ctx) return TREAT_B200_ERR_INVALID;
+    if (order != TREAT_B200_TIE_ULD && order != TREAT_B200_TIE_UDL && order != TREAT_B200_TIE_LUD)
+        return fail(ctx, TREAT_B200_ERR_INVALID, "set_tie_order: ULD (0), UDL (1) or LUD (2)");
+    ctx->tie = (uint32_t)order;
+    return TREAT_B200_OK;
+}
+
 int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows)
 {
     if (!ctx) return TREAT_B200_ERR_INVALID;
@@ -720,6 +730,7 @@ static int fill_align_params(treat_b200_ctx *ctx, AlignParams &ap, const treat_b
     ap.force_single = (flags & TREAT_B200_ONE_READ_PER_WARP) ? 1u : 0u;
     ap.force_full = (flags & TREAT_B200_FULL_TRACEBACK_STORE) ? 1u : 0u;
     ap.band_rows = ctx->band_rows;
+    ap.tie = ctx->tie;
     if (ap.ops) {
         if (ops_stride % 16 || ops_stride < a16(((uint32_t)ctx->td.m + ncap + 3) / 4))
             return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small or not a multiple of 16");
@@ -1208,14 +1219,18 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         return place_rows(s);
     };
 
-    for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk_reads, chunk_idx++) {
+    // one chunk: wait for its slot, copy the reads in, launch, start the copies out.  Every failure returns from the
+    // lambda only; the caller drains the streams before it gives the error back (copies into the caller's buffers may
+    // still be in flight).
+    auto enqueue_chunk = [&](uint64_t c0) -> int {
+        int rc = TREAT_B200_OK;
         const uint64_t cn = std::min<uint64_t>(chunk_reads, N - c0);
         Slot &s = ctx->slot[chunk_idx % n_slots];
         cudaStream_t st = s.stream;
         double t0 = now();
         CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk (incl. its D2H) is done
-        if ((rc = settle(s))) break;
-        if ((rc = unstage_out(s))) break;
+        if ((rc = settle(s))) return rc;
+        if ((rc = unstage_out(s))) return rc;
         double t1 = now();
         t_wait_slot += t1 - t0;
         const uint64_t b0 = seq_off[c0], b1 = seq_off[c0 + cn];
@@ -1235,7 +1250,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         const uint8_t *src_seqs = seqs + b0;
         if (stage_in) {  // the slot's previous chunk is done, so its staging buffer is free
             const size_t sb = (size_t)(b1 - b0);
-            if ((rc = reserve_pinned(s.h_in, s.h_in_cap, sb))) break;
+            if ((rc = reserve_pinned(s.h_in, s.h_in_cap, sb))) return rc;
             ctx->copy_pool.copy(s.h_in, src_seqs, sb);
             src_seqs = s.h_in;
         }
@@ -1257,15 +1272,30 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         } else {
             rc = run_exact(s);
         }
-        if (rc) break;
+        if (rc) return rc;
         rc = copy_out(s);
         t_enqueue += now() - t1;
-    }
+        return rc;
+    };
+    for (uint64_t c0 = 0; c0 < N && rc == TREAT_B200_OK; c0 += chunk_reads, chunk_idx++) rc = enqueue_chunk(c0);
     const double t_loop = now();
-    for (int i = 0; i < kSlots; i++) {
-        int r = settle(ctx->slot[i]);
-        if (r == TREAT_B200_OK && rc == TREAT_B200_OK) r = unstage_out(ctx->slot[i]);
-        if (r && rc == TREAT_B200_OK) rc = r;
+    for (int i = 0; i < kSlots && rc == TREAT_B200_OK; i++) {
+        rc = settle(ctx->slot[i]);
+        if (rc == TREAT_B200_OK) rc = unstage_out(ctx->slot[i]);
+    }
+    if (rc != TREAT_B200_OK) {
+        // error exit: nothing of this call may still be writing into the caller's buffers when it returns, and what
+        // unsettled speculative chunks counted privately must not reach the context's summary in a later call
+        const std::string keep = ctx->err;
+        for (int i = 0; i < kSlots; i++) {
+            Slot &s = ctx->slot[i];
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            if (s.summary.p && s.stream) cudaMemsetAsync(s.summary.p, 0, s.summary.cap, s.stream);
+            s.pending = s.scatter = s.unstage = false;
+        }
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+        ctx->err = keep;
     }
     for (int i = 0; i < kSlots; i++) {
         cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream);

@@ -106,6 +106,7 @@ struct AlignParams {
     uint32_t cpl;                // template columns per lane (sizes the template section)
     uint32_t strips;             // column strips of 32 x cpl bases (1 unless the template is longer than 480 bases)
     uint32_t sm_cnt_stage;       // k_same_bases: bytes per warp for the staged edit-site counts
+    uint32_t tie;                // TREAT_B200_TIE_*: which pointer nwalgo's traceback takes when several are optimal
 };
 
 // Alignment.WriteTo for a batch (text_kernel.cu)
