@@ -125,7 +125,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t h2d_done = nullptr;  // recorded behind the chunk's input copies: the next chunk's copies wait for it (see h2d_in_order)
     DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops, summary;
-    DevBuf list;     // reads that need the DP (written by k_same_bases, read by the align kernels)
+    DevBuf list;     // reads that need the DP (written by k_same_bases / k_pack_finish*, read by the align kernels)
+    DevBuf long_list;  // reads too long for one pass of k_pack_finish2
     DevBuf ops_idx;  // OPS_GAPPED_ONLY: read index of every compacted ops row
     // OPS_GAPPED_ONLY: pinned landing buffers of the compacted rows and their read indices
     uint8_t *h_gap_rows = nullptr;
@@ -156,7 +157,7 @@ struct Slot {
     uint32_t max_len = 0, dev_stride = 0;
     void release()
     {
-        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &ops_idx, &text,
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &long_list, &ops_idx, &text,
                           &text_off, &tlen, &gtot, &tsums, &names, &name_off})
             b->release();
         if (tland) cudaFreeHost(tland);
@@ -653,7 +654,7 @@ static int fill_pack_params(treat_b200_ctx *ctx, PackParams &pp, const uint8_t *
     pp.scalars = d_scalars;
     pp.tpk = (!dst->wide && !ctx->tmpl_wide) ? (const uint32_t *)ctx->d_tpk.p : nullptr;
     pp.tm = (uint32_t)ctx->td.m;
-    pp.padded = padded && ((uintptr_t)d_seqs & 15u) == 0 ? 1u : 0u;
+    pp.padded = padded && ((uintptr_t)d_seqs & 31u) == 0 ? 1u : 0u;
     if (span && !dst->wide) {  // k_pack16 only
         pp.begin = span->begin;
         pp.len = span->len;
@@ -687,6 +688,8 @@ struct AlignOpts {
     uint32_t *ops_idx = nullptr;      // with ops_count: compact the ops rows (OPS_GAPPED_ONLY on the host-buffer path)
     uint32_t *ops_count = nullptr;    //   (must be zero on entry)
     bool listed = false;              // the list is already filled (k_pack_finish ran): no k_same_bases launch
+    DevBuf *long_list = nullptr;      // k_pack_finish2: reads too long for one of its passes (taken up by k_pack_finish)
+    uint32_t *long_count = nullptr;   //   (must be zero on entry)
 };
 
 // the parameter block of an align launch (everything but the shared-memory plan, the scratch and the list)
@@ -846,7 +849,26 @@ static int do_pack_finish(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint
     ap.ops_idx = nullptr;  // reads finished here have no gap: with compacted rows they own none
     ap.ops_count = nullptr;
     ap.skipped = nullptr;
-    int e = launch_pack_finish(pp, ap, ctx->num_sms, ctx->max_smem, st);
+    static const bool no_fuse2 = getenv("TREAT_B200_NO_FUSE2") != nullptr;
+    if (!no_fuse2 && o.long_list && o.long_count) {
+        CK(ctx, o.long_list->reserve(dst->N * 4));
+        pp.long_list = (uint32_t *)o.long_list->p;
+        pp.long_count = o.long_count;
+    }
+    int e;
+    if (!no_fuse2 && pack_finish2_applies(pp, ap)) {
+        // one pass per read, two reads per warp for templates of up to 255 bases ...
+        e = launch_pack_finish2(pp, ap, ctx->num_sms, ctx->max_smem, st);
+        if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: template too large for the fused kernel's shared memory");
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_pack_finish2 launch: ") + cudaGetErrorString((cudaError_t)e));
+        ctx->launches++;
+        // ... and the multi-pass form for the reads it listed as too long, if the chunk can hold any
+        const uint32_t one_pass = (ctx->td.len <= 256 ? 16u : 32u) * 32u - 31u;
+        if (dst->max_len <= one_pass) return TREAT_B200_OK;
+        pp.sel = pp.long_list;
+        pp.sel_count = pp.long_count;
+    }
+    e = launch_pack_finish(pp, ap, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: read too long for shared-memory staging");
     if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_pack_finish launch: ") + cudaGetErrorString((cudaError_t)e));
     ctx->launches++;
@@ -912,12 +934,14 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
             const size_t sl = treat_b200_summary_len(ctx) * 8;
             if (s.summary.cap < sl) {
                 CK(ctx, s.summary.reserve(sl));
-                CK(ctx, cudaMemsetAsync(s.summary.p, 0, sl, st));
+                CK(ctx, cudaMemsetAsync(s.summary.p, 0, s.summary.cap, st));  // all of it: a later, larger template uses more of the buffer
             }
             slot_sum = (uint64_t *)s.summary.p;
         }
         AlignOpts o = opts(false);
         o.summary = slot_sum;
+        o.long_list = &s.long_list;
+        o.long_count = s.scalars + 5;
         rc = do_pack_finish(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded, d_rc, flags, d_rec, d_ops, ops_stride, o);
     } else {
         rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded);
@@ -936,7 +960,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
             const size_t sl = treat_b200_summary_len(ctx) * 8;
             if (s.summary.cap < sl) {
                 CK(ctx, s.summary.reserve(sl));
-                CK(ctx, cudaMemsetAsync(s.summary.p, 0, sl, st));
+                CK(ctx, cudaMemsetAsync(s.summary.p, 0, s.summary.cap, st));  // all of it: a later, larger template uses more of the buffer
             }
             slot_sum = (uint64_t *)s.summary.p;
         }
@@ -1245,7 +1269,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         const uint32_t need_stride = treat_b200_ops_stride(ctx, max_len);
         if (want_ops && (ops_stride < need_stride || ops_stride % 16))
             return fail(ctx, TREAT_B200_ERR_INVALID, "align: ops_stride too small (see treat_b200_ops_stride)");
-        CK(ctx, s.seqs.reserve(b1 - b0 + 16));
+        CK(ctx, s.seqs.reserve(b1 - b0 + 32));
         CK(ctx, s.rec.reserve(cn * sizeof(treat_b200_record)));
         const uint8_t *src_seqs = seqs + b0;
         if (stage_in) {  // the slot's previous chunk is done, so its staging buffer is free
@@ -2008,7 +2032,7 @@ int treat_b200_text_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64
             max_len = std::max<uint32_t>(max_len, (uint32_t)l);
         }
         const uint32_t stride = treat_b200_ops_stride(ctx, max_len);
-        CK(ctx, s.seqs.reserve(b1 - b0 + 16));
+        CK(ctx, s.seqs.reserve(b1 - b0 + 32));
         CK(ctx, s.off.reserve((cn + 1) * 8));
         CK(ctx, s.names.reserve(nb1 - nb0 + 16));
         CK(ctx, s.name_off.reserve((cn + 1) * 8));

@@ -47,7 +47,13 @@ struct PackParams {
     const uint64_t *begin;
     const uint32_t *len;
     uint64_t span;
-    uint32_t padded;        // seqs is 16-byte aligned and readable 16 bytes past its last byte (library-owned buffers)
+    uint32_t padded;        // seqs is 32-byte aligned and readable 32 bytes past its last byte (library-owned buffers)
+    // k_pack_finish2: reads too long for one of its passes are appended here ...
+    uint32_t *long_list;
+    uint32_t *long_count;
+    // ... and k_pack_finish, given such a list, handles only reads sel[0 .. *sel_count)
+    const uint32_t *sel;
+    const uint32_t *sel_count;
 };
 
 // internal bit of the per-read flag byte written by k_pack: the read's stripped bases equal the template's
@@ -164,6 +170,8 @@ int launch_align(const AlignParams &p, bool wide, int num_sms, int max_smem_opti
 // the other reads are packed to HBM and listed in q.list for launch_align
 bool pack_finish_applies(const PackParams &p, const AlignParams &q);
 int launch_pack_finish(const PackParams &p, const AlignParams &q, int num_sms, int max_smem_optin, void *stream);
+bool pack_finish2_applies(const PackParams &p, const AlignParams &q);
+int launch_pack_finish2(const PackParams &p, const AlignParams &q, int num_sms, int max_smem_optin, void *stream);
 int configure_fused_kernels(int max_smem_optin);
 // K2s: finishes the reads marked kFlagSameBases without a DP and lists the others (p is the plan_align'ed block)
 int launch_same_bases(const AlignParams &p, int num_sms, void *stream);

@@ -11,6 +11,7 @@
 // Templates of up to 511 bases (32 lanes x 16 sites), packed alphabet; everything else takes k_pack16 + k_same_*.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "assembly.cuh"
@@ -124,21 +125,25 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 4) k_pack_finish(const __gri
     uint32_t warp_max_n = 0, warp_sat = 0;
     unsigned long long ctr = 0;
     const uint64_t gw = (uint64_t)blockIdx.x * kFusedWarps + warp, nw = (uint64_t)gridDim.x * kFusedWarps;
+    // the reads of this launch: all of them, or the ones k_pack_finish2 left (longer than one of its passes)
+    const uint64_t total = p.sel ? (uint64_t)*p.sel_count : p.N;
+    auto read_at = [&](uint64_t i) -> uint64_t { return p.sel ? (uint64_t)p.sel[i] : i; };
     // software pipeline: offsets two reads ahead, the first block one read ahead
     uint64_t b_cur = 0, b_nxt = 0;
     uint32_t L_cur = 0, L_nxt = 0;
     uint4 blk = make_uint4(0, 0, 0, 0);
-    if (gw < p.N) {
-        where(gw, b_cur, L_cur);
+    if (gw < total) {
+        where(read_at(gw), b_cur, L_cur);
         blk = first_block(b_cur, L_cur);
     }
-    if (gw + nw < p.N) where(gw + nw, b_nxt, L_nxt);
-    for (uint64_t r = gw; r < p.N; r += nw) {
+    if (gw + nw < total) where(read_at(gw + nw), b_nxt, L_nxt);
+    for (uint64_t ri = gw; ri < total; ri += nw) {
+        const uint64_t r = read_at(ri);
         uint4 blk_n = make_uint4(0, 0, 0, 0);
         uint64_t b_nn = 0;
         uint32_t L_nn = 0;
-        if (r + nw < p.N) blk_n = first_block(b_nxt, L_nxt);
-        if (r + 2 * nw < p.N) where(r + 2 * nw, b_nn, L_nn);
+        if (ri + nw < total) blk_n = first_block(b_nxt, L_nxt);
+        if (ri + 2 * nw < total) where(read_at(ri + 2 * nw), b_nn, L_nn);
 
         const uint32_t L = L_cur;
         const uint32_t a = (uint32_t)((base_addr + b_cur) & 15u);
@@ -286,47 +291,357 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 4) k_pack_finish(const __gri
     flush_summary(q, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
 }
 
+// ------------------------------------------------------------------------------------------
+// K1f, second form: G lanes per read (G = 16: two reads per warp, templates of up to 255 bases; G = 32: up to 511),
+// 32 raw characters per lane, so a read of up to 32 G characters is one pass and everything the warp does once per pass
+// (offsets, block loads, the scan, the epilogue, the editing-site assembly) is shared by two reads.
+//
+//   * count: the lane's bases with byte-SIMD compares on the raw words ((c & 0xDF) == edit base is exact for a letter)
+//     and one IDP.4A per word -- no look-up needed before the scan;
+//   * emit: one 16-bit pair per base, code | (read position + 1) << 2, position = a compile-time constant of the
+//     unrolled step plus a lane constant: LUT look-up (PRMT + LDS), compare, predicated STS + pointer bump.  The pairs of
+//     a read end up compacted in shared memory; a zero in front and (L + 1) behind close the sequence;
+//   * epilogue: lane g takes pairs [16 g, 16 g + 16): the codes go into one 2-bit word (PRMT + multiply-gather), the
+//     edit-site counts are the differences of neighbouring positions minus one (three byte-SIMD steps per two sites) --
+//     no run lengths are tracked while stripping and no lane ever patches another lane's count;
+//   * then as k_pack_finish: compare with the template's words, finish_same<G> on the registers, or pack + list.
+// Reads longer than 32 G - 31 characters go to p.long_list for k_pack_finish (the multi-pass form).
+// ------------------------------------------------------------------------------------------
+constexpr int kF2Warps = 8;
+__host__ __device__ constexpr uint32_t f2_group_bytes(int G) { return 2u * (32u * (uint32_t)G + 32u); }  // 8 pad + 32 G + 1 + 16 (+ 7) pairs
+
+template <int G, bool SPAN>
+__global__ void __launch_bounds__(kF2Warps * 32, 3) k_pack_finish2(const __grid_constant__ PackParams p, const __grid_constant__ AlignParams q)
+{
+    constexpr int RPW = 32 / G;
+    constexpr uint32_t GB = f2_group_bytes(G);
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane & (G - 1), grp = lane / G, lead = grp * G;
+    const unsigned gmask = G == 32 ? FULL_MASK : 0xffffu << lead;
+    const uint32_t smem32 = smem_u32(smem);
+    const uint32_t lut32 = (smem32 + 255u) & ~255u;  // 256-aligned: PRMT(word, lut32) splices a character into the address
+    uint8_t *s_lut = smem + (lut32 - smem32);
+    uint4 *s_mask = reinterpret_cast<uint4 *>(smem + kHdrMask);
+    uint32_t *s_tpk = reinterpret_cast<uint32_t *>(smem + kHdrTpk);
+    const CtaSmem<uint8_t> cs = carve_cta<uint8_t>(smem + kHdrBytes, q, 0);
+    uint32_t *zero = reinterpret_cast<uint32_t *>(smem + kHdrBytes + q.sm_tmpl_bytes);  // the all-match ops of a read without a gap
+    uint8_t *s_warp = smem + kHdrBytes + q.sm_tmpl_bytes + q.sm_ops + (size_t)warp * (RPW * GB);
+    uint8_t *s_grp = s_warp + grp * GB;  // this group's pairs: [0, 16) pad (pair -1 = 0 sits at byte 14), pairs from byte 16
+    const uint32_t grp32 = smem_u32(s_grp);
+    const uint8_t eb = p.edit_base;
+    const uint32_t tm = p.tm, twords = (tm + 15) / 16;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint8_t up = (i >= 'a' && i <= 'z') ? (uint8_t)(i - 32) : (uint8_t)i;  // strings.ToUpper, ASCII
+        s_lut[i] = up == eb ? (uint8_t)kLutEdit : p.lut[up];  // code 0..2, 3 = outside the alphabet
+    }
+    if (threadIdx.x < 17) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = min(max((int)threadIdx.x - 4 * i, 0), 4);
+            w[i] = k >= 4 ? 0xffffffffu : (1u << (8 * k)) - 1u;
+        }
+        s_mask[threadIdx.x] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (threadIdx.x < 32) s_tpk[threadIdx.x] = threadIdx.x < twords ? p.tpk[threadIdx.x] : 0u;
+    load_template(cs, q, 0);
+    for (uint32_t i = threadIdx.x; i < q.sm_ops / 4; i += blockDim.x) zero[i] = 0u;
+    if (gl < 8) reinterpret_cast<uint16_t *>(s_grp)[gl] = 0;  // the pad in front: "position 0" before the first base
+    WarpSmem ws{};
+    ws.ops2 = zero;
+    __syncthreads();
+
+    const SameLane sl = load_same_lane(cs, q, gl);
+    const uint32_t eb4 = (uint32_t)eb * 0x01010101u;
+    const uintptr_t base_addr = reinterpret_cast<uintptr_t>(p.seqs);
+    // the bytes of p.seqs this launch may touch: [lo, hi)
+    const int64_t lo = SPAN ? 0 : p.N ? (int64_t)(p.off[0] - p.off_bias) : 0;
+    const int64_t hi = SPAN ? (int64_t)p.span : p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
+    auto where = [&](uint64_t r, uint64_t &b, uint32_t &L) {
+        b = 0;
+        L = 0;
+        if (r >= p.N) return;
+        if (SPAN) {
+            b = p.begin[r];
+            L = p.len[r];
+        } else {
+            const uint64_t o0 = p.off[r], o1 = p.off[r + 1];
+            b = o0 - p.off_bias;
+            L = (uint32_t)(o1 - o0);
+        }
+    };
+    // this lane's two 16-byte blocks of a read (32-byte aligned in memory); zero when the lane is behind the read or the
+    // read is too long for one pass.  Blocks that stick out of [lo, hi) -- only at the ends of a caller's buffer -- are
+    // read byte by byte.
+    auto load_blocks = [&](uint64_t b, uint32_t L, uint4 &A, uint4 &B) {
+        A = make_uint4(0, 0, 0, 0);
+        B = A;
+        const uint32_t a = (uint32_t)((base_addr + b) & 31u);
+        const uint32_t nblk = (a + L + 31u) >> 5;
+        if (L == 0u || (uint32_t)gl >= nblk || nblk > (uint32_t)G) return;
+        const int64_t x = (int64_t)b - a + 32 * gl;
+        if (p.padded || (x >= lo && x + 32 <= hi)) {
+            A = *reinterpret_cast<const uint4 *>(p.seqs + x);
+            B = *reinterpret_cast<const uint4 *>(p.seqs + x + 16);
+            return;
+        }
+        uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int c = 0; c < 32; c++) {
+            const int64_t y = x + c;
+            if (y >= lo && y < hi) w[c >> 2] |= (uint32_t)p.seqs[y] << (8 * (c & 3));
+        }
+        A = make_uint4(w[0], w[1], w[2], w[3]);
+        B = make_uint4(w[4], w[5], w[6], w[7]);
+    };
+
+    uint32_t warp_max_n = 0, warp_sat = 0;
+    unsigned long long ctr = 0;
+    const uint64_t units = (p.N + RPW - 1) / RPW;
+    const uint64_t gw = (uint64_t)blockIdx.x * kF2Warps + warp, nw = (uint64_t)gridDim.x * kF2Warps;
+    // software pipeline: offsets two units ahead, the blocks one unit ahead
+    uint64_t b_cur = 0, b_nxt = 0;
+    uint32_t L_cur = 0, L_nxt = 0;
+    uint4 blkA = make_uint4(0, 0, 0, 0), blkB = blkA;
+    if (gw < units) {
+        where(gw * RPW + grp, b_cur, L_cur);
+        load_blocks(b_cur, L_cur, blkA, blkB);
+    }
+    if (gw + nw < units) where((gw + nw) * RPW + grp, b_nxt, L_nxt);
+    for (uint64_t u = gw; u < units; u += nw) {
+        uint4 nA = make_uint4(0, 0, 0, 0), nB = nA;
+        uint64_t b_nn = 0;
+        uint32_t L_nn = 0;
+        if (u + nw < units) load_blocks(b_nxt, L_nxt, nA, nB);
+        if (u + 2 * nw < units) where((u + 2 * nw) * RPW + grp, b_nn, L_nn);
+
+        const uint64_t r = u * RPW + grp;
+        const uint32_t a = (uint32_t)((base_addr + b_cur) & 31u);
+        const bool too_long = ((a + L_cur + 31u) >> 5) > (uint32_t)G;
+        const bool valid = r < p.N && !too_long;
+        const uint32_t L = valid ? L_cur : 0u;  // a read that is not handled here runs through as an empty one, without outputs
+        if (too_long && r < p.N && gl == 0) p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)r;
+
+        // characters outside the read become edit bases: keep bytes [vlo, vhi) of each block
+        const int pos0 = 32 * gl - (int)a;  // read position of this lane's first character
+        uint32_t w[8] = {blkA.x, blkA.y, blkA.z, blkA.w, blkB.x, blkB.y, blkB.z, blkB.w};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int ph = pos0 + 16 * h;
+            const int vlo = min(max(-ph, 0), 16), vhi = min(max((int)L - ph, 0), 16);
+            const uint4 mh = s_mask[vhi], ml = s_mask[vlo];
+            const uint32_t keep[4] = {mh.x & ~ml.x, mh.y & ~ml.y, mh.z & ~ml.z, mh.w & ~ml.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[4 * h + i] = (w[4 * h + i] & keep[i]) | (eb4 & ~keep[i]);
+        }
+        // bases of this lane: a byte of x is zero iff the character is the edit base (either case)
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t x = (w[i] & 0xdfdfdfdfu) ^ eb4;
+            const uint32_t t = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;
+            sum = __dp4a(t & 0x80808080u, 0x01010101u, sum);  // + 128 per base
+        }
+        const uint32_t nbl = sum >> 7;
+        uint32_t incl = nbl;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL_MASK, incl, d, G);
+            if (gl >= d) incl += t;
+        }
+        const uint32_t n = __shfl_sync(FULL_MASK, incl, G - 1, G);
+        // emit: pair = code | (read position + 1) << 2
+        uint32_t addr = grp32 + 16u + 2u * (incl - nbl);
+        const uint32_t vbase = (uint32_t)(pos0 + 1) << 2;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const uint32_t v = lds_u8n(__byte_perm(w[k >> 2], lut32, 0x7650 + (k & 3)));  // lut32 | character
+            if (v < kLutEdit) {
+                sts_u16r(addr, v + vbase + (uint32_t)(k << 2));
+                addr += 2u;
+            }
+        }
+        // behind the last base: position L + 1 closes the last run, then consecutive positions (zero counts, zero codes)
+        if (gl < 16) sts_u16r(grp32 + 16u + 2u * (n + (uint32_t)gl), (L + 1u + (uint32_t)gl) << 2);
+        __syncwarp();
+
+        // lane g turns pairs [16 g, 16 g + 16) into one word of 2-bit codes and 16 count bytes
+        const uint32_t bwords = align16((n + 3) / 4) / 4, cgroups = (n + 16) / 16;
+        auto group = [&](uint32_t g, uint4 &cnt, uint32_t &word, uint32_t &over) {
+            const uint32_t at = grp32 + 16u + 32u * g;
+            const uint4 x = lds_v4(at), y = lds_v4(at + 16u);
+            const uint32_t prev = lds_u16(at - 2u);
+            constexpr uint32_t M = 0x01041040u, C3 = 0x03030303u, PM = 0xfffcfffcu;
+            // 16 codes (low two bits of every pair) -> 16 x 2 bits: (c * M) >> 24 gathers the four 2-bit fields of a word
+            const uint32_t c0 = __byte_perm(x.x, x.y, 0x6420) & C3, c1 = __byte_perm(x.z, x.w, 0x6420) & C3;
+            const uint32_t c2 = __byte_perm(y.x, y.y, 0x6420) & C3, c3 = __byte_perm(y.z, y.w, 0x6420) & C3;
+            const uint32_t lo16 = __byte_perm(c0 * M, c1 * M, 0x0073), hi16 = __byte_perm(c2 * M, c3 * M, 0x0073);
+            word = __byte_perm(lo16, hi16, 0x5410);
+            // counts: (position - previous position - 1) for both halves of a word at once (positions grow: no borrow)
+            const uint32_t m[8] = {x.x & PM, x.y & PM, x.z & PM, x.w & PM, y.x & PM, y.y & PM, y.z & PM, y.w & PM};
+            uint32_t d[8];
+            d[0] = m[0] - __byte_perm(prev & 0xfffcu, m[0], 0x5410);
+#pragma unroll
+            for (int i = 1; i < 8; i++) d[i] = m[i] - __byte_perm(m[i - 1], m[i], 0x5432);
+            over |= (d[0] | d[1] | d[2] | d[3] | d[4] | d[5] | d[6] | d[7]) & 0xfc00fc00u;  // a run of 255 or more
+            cnt = make_uint4(__byte_perm(d[0] >> 2, d[1] >> 2, 0x6420) - 0x01010101u, __byte_perm(d[2] >> 2, d[3] >> 2, 0x6420) - 0x01010101u,
+                             __byte_perm(d[4] >> 2, d[5] >> 2, 0x6420) - 0x01010101u, __byte_perm(d[6] >> 2, d[7] >> 2, 0x6420) - 0x01010101u);
+        };
+        uint4 cnt = make_uint4(0, 0, 0, 0);
+        uint32_t word = 0, over = 0;
+        if ((uint32_t)gl < cgroups) group((uint32_t)gl, cnt, word, over);
+        uint32_t wide = word & (word >> 1) & 0x55555555u;  // a code 3: a base outside the alphabet
+        // reads of more than 16 G bases: the further groups only matter for the flags and the packed output below
+        for (uint32_t g = gl + G; g < cgroups; g += G) {
+            uint4 c2;
+            uint32_t w2;
+            group(g, c2, w2, over);
+            wide |= w2 & (w2 >> 1) & 0x55555555u;
+        }
+        const uint32_t fl = __reduce_or_sync(gmask, (over ? (uint32_t)TREAT_B200_ST_SATURATED : 0u) | (wide ? (uint32_t)TREAT_B200_ST_WIDE_BASE : 0u));
+        uint32_t rflags = fl;
+        // bases that differ from the template's (codes past n are zero in both words)
+        uint32_t ndiff = 2u;
+        if (n == tm) {
+            const uint32_t x = word ^ s_tpk[gl];
+            ndiff = __reduce_add_sync(gmask, __popc((x | (x >> 1)) & 0x55555555u));
+        }
+        bool general = false;
+        if (valid && ndiff <= 1u) {
+            // no DP: the identity alignment is the unique optimum (score m, or m - 2 with the one mismatch)
+            rflags |= ndiff ? kFlagOneMismatch : kFlagSameBases;
+            general = !finish_same<G>(q, cs, s_mask, gl, gmask, lead, r, rflags, cnt, sl, ctr, L);
+        } else if (valid) {
+            // left for the DP: the packed read goes to HBM, its index to the list
+            uint32_t *gb = reinterpret_cast<uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
+            uint4 *gc = reinterpret_cast<uint4 *>(p.counts + r * (uint64_t)p.counts_stride);
+            for (uint32_t g = gl; g < max(bwords, cgroups); g += G) {
+                if (g >= (uint32_t)G) {
+                    cnt = make_uint4(0, 0, 0, 0);
+                    word = 0;
+                    if (g < cgroups) group(g, cnt, word, over);
+                }
+                if (g < cgroups) gc[g] = cnt;
+                if (g < bwords) gb[g] = word;
+            }
+            if (gl == 0) {
+                p.n[r] = (uint16_t)n;
+                p.flags[r] = (uint8_t)rflags;
+                p.raw_len[r] = L;
+                q.list[atomicAdd(q.list_count, 1u)] = (uint32_t)r;
+            }
+        }
+        // the junction start sits on an alternative template's region: the whole warp runs the general assembly on the
+        // read's counts (as bytes in the pair area), one read at a time
+        unsigned todo = __ballot_sync(FULL_MASK, general && gl == 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            __syncwarp();
+            uint8_t *stage = s_warp + (src / G) * GB + 16;
+            if (lead == src) reinterpret_cast<uint4 *>(stage)[gl] = cnt;
+            __syncwarp();
+            finish_same_general(q, cs, ws, lane, u * RPW + (uint64_t)(src / G), __shfl_sync(FULL_MASK, rflags, src), stage, ctr,
+                                __shfl_sync(FULL_MASK, L, src));
+        }
+        if (valid) {
+            warp_max_n = max(warp_max_n, n);
+            warp_sat |= fl & TREAT_B200_ST_SATURATED;
+        }
+        __syncwarp();
+        b_cur = b_nxt, L_cur = L_nxt, blkA = nA, blkB = nB;
+        b_nxt = b_nn, L_nxt = L_nn;
+    }
+    warp_max_n = __reduce_max_sync(FULL_MASK, warp_max_n);
+    warp_sat = __reduce_or_sync(FULL_MASK, warp_sat);
+    if (lane == 0) {
+        if (warp_max_n) atomicMax(&p.scalars[0], warp_max_n);
+        if (warp_sat) atomicOr(&p.scalars[1], 1u);
+    }
+    if (G == 16) ctr += __shfl_down_sync(FULL_MASK, ctr, 16);  // lane L and lane L + 16 both hold counter L
+    flush_summary(q, cs.sum_len, cs.sum_lo, cs.sum_hi, lane, ctr);
+}
+
 // the fused launch applies to: packed alphabet, a template of at most 511 bases (32 lanes x 16 edit sites), marks on
 bool pack_finish_applies(const PackParams &p, const AlignParams &q)
 {
     return p.tpk != nullptr && q.t.len <= 512 && q.t.len >= 1 && q.list != nullptr && q.list_count != nullptr;
 }
 
-int launch_pack_finish(const PackParams &pack, const AlignParams &planned, int num_sms, int max_smem_optin, void *stream)
+static void fused_smem_plan(AlignParams &q)
 {
-    PackParams p = pack;
-    if (p.stage_cap < 256) p.stage_cap = 256;  // the general assembly stages 32 x 16 count bytes in the pair area
-    AlignParams q = planned;
     const uint32_t sum_len = q.summary ? TREAT_B200_SUMMARY_HEADER + 3u * q.bins : 0u;
     q.sm_prof_bytes = 0;
     q.sm_tmpl_bytes = align16((uint32_t)(q.t.K * q.t.len_pad)) + align16(8u * (q.t.n_alt ? q.t.n_alt : 1)) + align16(8u * sum_len);
     q.sm_tmpl_bytes = (q.sm_tmpl_bytes + 127u) & ~127u;
     q.sm_ops = align16((((uint32_t)(2 * q.t.m) + 15) / 16 + 2) * 4);
     if (q.ncap < (uint32_t)q.t.m) q.ncap = (uint32_t)q.t.m;
+}
+
+template <typename Kern>
+static int launch_fused(Kern kern, const PackParams &p, const AlignParams &q, uint64_t units_per_cta, uint64_t units, int threads,
+                        size_t smem, int num_sms, void *stream)
+{
+    uint64_t blocks = (units + units_per_cta - 1) / units_per_cta;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint64_t cap = (uint64_t)num_sms * per_sm;  // persistent grid: as many CTAs as are resident at once
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return 0;
+    kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(p, q);
+    return (int)cudaGetLastError();
+}
+
+// multi-pass form (one read per warp, reads of any length).  With pack.sel set it handles only the listed reads.
+int launch_pack_finish(const PackParams &pack, const AlignParams &planned, int num_sms, int max_smem_optin, void *stream)
+{
+    PackParams p = pack;
+    if (p.stage_cap < 256) p.stage_cap = 256;  // the general assembly stages 32 x 16 count bytes in the pair area
+    AlignParams q = planned;
+    fused_smem_plan(q);
     const size_t per_warp = (size_t)p.stage_cap * 2;
     const size_t fixed = (size_t)kHdrBytes + q.sm_tmpl_bytes + q.sm_ops;
     if (fixed + per_warp * kFusedWarps > (size_t)max_smem_optin) return -1000;
     const size_t smem = fixed + per_warp * kFusedWarps;
-    uint64_t blocks = (p.N + kFusedWarps - 1) / kFusedWarps;
-    int per_sm = 0;
-    cudaError_t oe = p.begin ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack_finish<true>, kFusedWarps * 32, smem)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pack_finish<false>, kFusedWarps * 32, smem);
-    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
-    const uint64_t cap = (uint64_t)num_sms * per_sm;  // persistent grid: as many CTAs as are resident at once
-    if (blocks > cap) blocks = cap;
-    if (blocks == 0) return 0;
-    if (p.begin)
-        k_pack_finish<true><<<(unsigned)blocks, kFusedWarps * 32, smem, (cudaStream_t)stream>>>(p, q);
-    else
-        k_pack_finish<false><<<(unsigned)blocks, kFusedWarps * 32, smem, (cudaStream_t)stream>>>(p, q);
-    return (int)cudaGetLastError();
+    const uint64_t units = p.sel ? std::min<uint64_t>(p.N, (uint64_t)num_sms * 64) : p.N;  // a list: its length is on the device
+    if (p.begin) return launch_fused(k_pack_finish<true>, p, q, kFusedWarps, units, kFusedWarps * 32, smem, num_sms, stream);
+    return launch_fused(k_pack_finish<false>, p, q, kFusedWarps, units, kFusedWarps * 32, smem, num_sms, stream);
+}
+
+// one-pass form: two reads per warp for templates of up to 255 bases, one read per warp up to 511; the edit base must be a
+// letter (byte-SIMD case folding).  Reads too long for a pass are appended to pack.long_list.
+bool pack_finish2_applies(const PackParams &p, const AlignParams &q)
+{
+    const uint8_t eb = p.edit_base;
+    return pack_finish_applies(p, q) && eb >= 'A' && eb <= 'Z' && p.long_list != nullptr && p.long_count != nullptr;
+}
+
+int launch_pack_finish2(const PackParams &p, const AlignParams &planned, int num_sms, int max_smem_optin, void *stream)
+{
+    AlignParams q = planned;
+    fused_smem_plan(q);
+    const bool two = q.t.len <= 256;
+    const size_t per_warp = two ? 2 * (size_t)f2_group_bytes(16) : (size_t)f2_group_bytes(32);
+    const size_t smem = (size_t)kHdrBytes + q.sm_tmpl_bytes + q.sm_ops + per_warp * kF2Warps;
+    if (smem > (size_t)max_smem_optin) return -1000;
+    const uint64_t units = two ? (p.N + 1) / 2 : p.N;
+    if (two) {
+        if (p.begin) return launch_fused(k_pack_finish2<16, true>, p, q, kF2Warps, units, kF2Warps * 32, smem, num_sms, stream);
+        return launch_fused(k_pack_finish2<16, false>, p, q, kF2Warps, units, kF2Warps * 32, smem, num_sms, stream);
+    }
+    if (p.begin) return launch_fused(k_pack_finish2<32, true>, p, q, kF2Warps, units, kF2Warps * 32, smem, num_sms, stream);
+    return launch_fused(k_pack_finish2<32, false>, p, q, kF2Warps, units, kF2Warps * 32, smem, num_sms, stream);
 }
 
 int configure_fused_kernels(int max_smem_optin)
 {
     cudaError_t ce = cudaFuncSetAttribute(k_pack_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (ce != cudaSuccess) return (int)ce;
-    ce = cudaFuncSetAttribute(k_pack_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_pack_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_pack_finish2<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_pack_finish2<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_pack_finish2<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_pack_finish2<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     return (int)ce;
 }
 
