@@ -584,6 +584,15 @@ def run_ours(args):
     pack_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_pack_device(
         eng._ctx, d_seqs.data_ptr(), d_off.data_ptr(), C.byref(pk_full), sraw), eng._ctx), args.steps)
     n_arr = d_n.cpu().numpy().astype(np.int64) & 0xffff
+    # the fused kernel alone (k_pack_finish2 + the multi-pass form for reads longer than one pass): what the batch call
+    # launches before the DP kernel.  TREAT_B200_SKIP_DP leaves the DP launch out (the 8-byte read-back of max n stays).
+    fused_ms = kernel_ms(lambda: eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len,
+                                                        flags | cabi.SKIP_DP | cabi.NO_SUMMARY, d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw),
+                         args.steps)
+    # the whole step with the DP forced on every read (TREAT_B200_DP_EVERY_READ: k_pack16 + k_align2 on all reads)
+    dp_every_ms = kernel_ms(lambda: eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len,
+                                                           flags | cabi.DP_EVERY_READ | cabi.NO_SUMMARY, d_rec.data_ptr(), d_ops.data_ptr(), stride,
+                                                           sraw), max(2, args.steps // 2))
     # ---- Alignment.WriteTo for the batch, everything resident in HBM (k_text: sizes, scan, write) ----------------
     text_dev = None
     if rank == 0 and world == 1 and not args.no_fasta:
@@ -618,24 +627,35 @@ def run_ours(args):
     def ncu_traffic(kernel):
         # DRAM bytes per launch from the committed ncu capture (per read x reads of this launch)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
             return (tr["dram_read_bytes_per_read"] + tr["dram_write_bytes_per_read"]) * N if args.workload == "rps12" else None
         except Exception:
             return None
     def ncu_facts(kernel):
         # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r01_*_ncu_full.md)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
             return {k: v for k, v in tr.items() if not k.startswith("dram_")}
         except Exception:
             return None
-    # k_pack16: raw characters + offsets in; 2-bit bases, counts, n / flags / raw_len out
+    # k_pack_finish2 (the fused kernel, largest share of a step): raw characters + offsets + read counts in, the 48-byte
+    # record out; for the reads left for the DP also the packed read (2-bit bases, counts, n / flags / raw_len) and a list entry
+    listed = ~no_dp
+    packed_bytes = float(((n_arr + 3) // 4 + (n_arr + 1))[listed].sum() + int(listed.sum()) * (2 + 1 + 4 + 4))
+    fused_bytes = float(len(seqs) + N * 8 + N * 4 + int(no_dp.sum()) * 48) + packed_bytes
+    roofline = {"bound": "hbm", "kernel": "k_pack_finish2 (NewFragment + editing-site assembly of the reads that need no DP; largest share of a step)",
+                "achieved": fused_bytes / (fused_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": fused_bytes / (fused_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms, "traffic": ncu_traffic("k_pack_finish2"), "ncu": ncu_facts("k_pack_finish2"),
+                "bytes_per_read": fused_bytes / N,
+                "note": "instruction-issue bound byte work (character classes, compaction, count differences, site compares), "
+                        "not DRAM bound: see profiles/; ms_per_launch includes the launch of the multi-pass form for reads "
+                        "longer than one pass and one 8-byte read-back"}
+    # the unfused NewFragment kernel (treat_b200_pack_device, used by the stage calls and for long / wide templates)
     pack_bytes = float(len(seqs) + N * 8 + ((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4))
-    roofline = {"bound": "hbm", "kernel": "k_pack16 (NewFragment for the batch; largest share of a step)",
-                "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                "bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms, "traffic": ncu_traffic("k_pack16"), "ncu": ncu_facts("k_pack16"),
-                "note": "instruction-issue bound (about 500 warp instructions per read), not DRAM bound: see profiles/"}
+    roofline_pack = {"bound": "hbm", "kernel": "k_pack16 (stage call treat_b200_pack_device)", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": pack_ms,
+                     "bytes_per_launch": pack_bytes}
     # k_align2 on every read: algorithmic integer ops of the DP
     alg_bytes = float(((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4 + 4) + N * 48 + ((t.m + n_arr + 3) // 4).sum())
     int_ops = cells_per_step * INT_OPS_PER_CELL
@@ -855,11 +875,14 @@ def run_ours(args):
             "config": {"workload": workload_name(args, t), "l2": "inputs larger than L2 (%.0f MB raw reads per GPU per step)" % (len(seqs) / 1e6),
                        "parallelism": "reads sharded over %d GPU(s), summary all-reduce only" % world,
                        "outputs": "48-byte record per read + %d-byte 2-bit ops row per read with a gap" % stride},
-            "kernels_ms": {"k_pack": pack_ms, "k_same_bases+k_align(listed reads)": marks_ms, "k_align(every read)": align_ms},
+            "kernels_ms": {"k_pack_finish2 (fused NewFragment + assembly)": fused_ms,
+                           "k_align2 (DP on the listed reads) = step - fused": max(dev_ms / args.steps - fused_ms, 0.0),
+                           "stage calls: k_pack16": pack_ms, "stage calls: k_same_bases+k_align(listed reads)": marks_ms,
+                           "k_align2 (DP on every read)": align_ms},
             "reads_equal_to_template_bases": same_frac,
             # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
-            "value_dp_every_read": world * N / ((pack_ms + align_ms) * 1e-3),
-            "roofline": roofline, "roofline_dp": roofline_dp, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
+            "value_dp_every_read": world * N / (dp_every_ms * 1e-3),
+            "roofline": roofline, "roofline_dp": roofline_dp, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
             "text_device": text_dev, "parity": parity, "long": side.get("long"), "noisy": side.get("noisy"),
             "nccl": {"version": cabi.lib().treat_b200_nccl_version() if world > 1 else None,
                      "collective": "ncclAllReduce(uint64, sum) of the summary counters, issued by libtreat_b200.so "

@@ -54,6 +54,8 @@ extern "C" {
                                             can shrink to the gapped reads */
 #define TREAT_B200_WANT_BLOBS 0x200u /* treat_b200_fasta_stream only: also hand the sink every record's MarshalBinary blob (`treat load`) */
 #define TREAT_B200_HEATMAP 0x100u /* also accumulate the ESS x junction-length heat map (treat_b200_get_heatmap) */
+#define TREAT_B200_SKIP_DP 0x400u /* measurement only (bench.py times the fused kernel alone with it): the DP launch for the reads
+                                     that need one is skipped, so their records are NOT written */
 #define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
                                            under the template that is current now, so reads it marked as equal to the template
                                            skip the DP; without this flag the stage call runs the DP for every read */

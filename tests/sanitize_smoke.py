@@ -36,6 +36,9 @@ check(eng, rps, 301, 3, 0.2, cabi.ONE_READ_PER_WARP)
 check(eng, rps, 301, 4, 0.2, cabi.FULL_TRACEBACK_STORE)
 check(eng, lng, 401, 5, 0.2)                                  # u32 direction words, K = 10
 check(eng, synth.long_template(40, 2), 301, 6, 0.3)
+check(eng, rps, 20001, 7, 0.05, cabi.DP_EVERY_READ)           # the paired DP kernel on every read
+check(eng, synth.long_template(700, 4), 201, 8, 0.2)          # column strips (m > 480)
+check(eng, synth.long_template(230, 3), 2001, 9, 0.1)         # fused kernel, one read per warp (257..512 edit sites)
 # wide path: template with a non-alphabet base, read with a saturated edit-base run
 d = tempfile.mkdtemp()
 p = os.path.join(d, "w.fa")
@@ -43,5 +46,11 @@ open(p, "w").write(">fe\nACNGTTAGC%s\n>pe\nACNGAGC%s\n" % ("AG" * 20, "AG" * 20)
 tm = T.NewTemplateFromFasta(p, T.FORWARD, "T")
 alns = eng.NewAlignments([("a-1", "ACNGTTAGC" + "AG" * 20), ("b-2", "ACNG" + "T" * 300 + "AGC" + "AG" * 20)], tm, False)
 assert alns[0].Score == 47
+# bounds-check flags of the kernels' data-dependent index computations (a build with -DTREAT_B200_CHECKS has them compiled in)
+flags, compiled = eng.debug_flags()
+print("debug_flags 0x%x checks_compiled %d" % (flags, compiled))
+assert flags == 0, "a kernel index left its bounds: 0x%x" % flags
+if os.environ.get("TREAT_B200_EXPECT_CHECKS"):
+    assert compiled, "this library was built without TREAT_B200_CHECKS"
 print("sanitize smoke ok")
 eng.close()

@@ -993,6 +993,23 @@ def test_zz_kernel_bounds_flags_clean(eng):
     assert flags == 0, "kernel bounds-check flags: 0x%x (checks compiled: %s)" % (flags, compiled)
 
 
+def test_zz_checked_build_bounds_clean():
+    """compute-sanitizer is closed on the GPU pool.  Substitute: a second library built with -DTREAT_B200_CHECKS (bounds checks
+    compiled into the kernels' data-dependent index computations: band window, scratch, ops array, site maps, pair area)
+    runs every kernel variant against the oracle in its own process; no check may fire."""
+    import subprocess
+    import sys
+    from treat_b200 import _build
+    lib = os.path.join(os.path.dirname(_build.LIB), "_build", "checked", "libtreat_b200.so")
+    if not os.path.exists(lib):
+        lib = _build.build_variant("checked", ["-DTREAT_B200_CHECKS"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TREAT_B200_LIB=lib, TREAT_B200_EXPECT_CHECKS="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "sanitize_smoke.py")], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "checks_compiled 1" in out.stdout and "debug_flags 0x0" in out.stdout
+
+
 def test_tie_orders_match_oracle(eng, examples, tmp_path):
     """treat_b200_set_tie_order: the three traceback orders the reference's goldens allow (Up > Left > Diagonal as nwalgo
     publishes it, Up > Diagonal > Left, Left > Up > Diagonal) against the oracle's switch, on reads with many ties

@@ -89,5 +89,39 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A second library with extra -D flags, in treat_b200/_build/<name>/libtreat_b200.so (e.g. the bounds-checked build the
+    GPU tests load next to the normal one: build_variant("checked", ["-DTREAT_B200_CHECKS"])).  Host objects are shared."""
+    vdir = os.path.join(OBJ, name)
+    os.makedirs(vdir, exist_ok=True)
+    build(verbose=verbose)  # the host objects and the normal library
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    tag = os.path.join(vdir, ".defines")
+    stale_defs = not os.path.exists(tag) or open(tag).read() != " ".join(defines)
+    objs, jobs = [], []
+    for src in CUDA_SOURCES:
+        s_, o = os.path.join(CSRC, src), os.path.join(vdir, src + ".o")
+        objs.append(o)
+        if stale_defs or _stale(o, [s_] + hdrs):
+            jobs.append([_nvcc()] + NVCC_FLAGS + list(defines) + ["-c", s_, "-o", o])
+    for src in CXX_SOURCES:
+        objs.append(os.path.join(OBJ, src.replace("/", "_") + ".o"))
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
+    lib = os.path.join(vdir, "libtreat_b200.so")
+    if jobs or _stale(lib, objs):
+        _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
+             + ["-cudart", "static", "-Xlinker", "--no-undefined", "-ldl"], verbose)
+    with open(tag, "w") as fh:
+        fh.write(" ".join(defines))
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose=True))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -14,6 +14,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in nsys / ncu timelines, a few ns when no tool is attached
+
 #include "device_format.h"
 #include "host/treat_host.hpp"
 
@@ -118,6 +120,14 @@ struct CopyPool {
         cv.notify_all();
         for (auto &t : th) t.join();
     }
+};
+
+// NVTX range around a host-side phase (copy in / pack + align launches / copy out / text / deliver)
+struct Nvtx {
+    explicit Nvtx(const char *name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+    Nvtx(const Nvtx &) = delete;
+    Nvtx &operator=(const Nvtx &) = delete;
 };
 
 // device buffers of one in-flight chunk
@@ -748,6 +758,7 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     uint32_t *d_list_count = o.list_count;
     DevBuf *list = o.list;
     if (src->N == 0) return TREAT_B200_OK;
+    Nvtx nv("launch k_align*: DP + traceback + assembly");
     const bool wide = src->wide != 0;
     AlignParams ap;
     int frc = fill_align_params(ctx, ap, src, ncap, d_read_count, flags, d_rec, d_ops, ops_stride, o);
@@ -836,6 +847,7 @@ static int do_pack_finish(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint
                           const AlignOpts &o)
 {
     if (dst->N == 0) return TREAT_B200_OK;
+    Nvtx nv("launch k_pack_finish*: NewFragment + assembly of reads without DP");
     PackParams pp;
     int rc = fill_pack_params(ctx, pp, d_seqs, d_off, off_bias, dst, d_scalars, span, padded);
     if (rc) return rc;
@@ -968,6 +980,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         o.summary = slot_sum;
         o.skipped = s.scalars + 2;
         o.listed = fuse;
+        if (fuse && (flags & TREAT_B200_SKIP_DP)) return TREAT_B200_OK;
         rc = do_align(ctx, &pk, ncap, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, o);
         if (rc) return rc;
         CK(ctx, cudaMemcpyAsync(s.h_scalars, s.scalars, kScalarBytes, cudaMemcpyDeviceToHost, st));
@@ -996,6 +1009,7 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
     if (ops_stride_used) *ops_stride_used = ops_stride;
     AlignOpts oa = opts(slot_own_ops);
     oa.listed = fuse;
+    if (fuse && (flags & TREAT_B200_SKIP_DP)) return TREAT_B200_OK;
     rc = do_align(ctx, &pk, max_n, d_rc, flags, d_rec, d_ops, ops_stride, st, s.scratch, oa);
     if (rc) return rc;
     return add_heatmap(ctx, flags, d_rec, N, st);  // a speculative launch is added once it is validated
@@ -1028,6 +1042,7 @@ int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, co
                                   const uint32_t *d_read_count, uint64_t N, uint32_t max_len, uint32_t flags,
                                   treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, void *stream)
 {
+    Nvtx nv_call("treat_b200_align_batch_device");
     if (!ctx || (N && (!d_seqs || !d_seq_off || !d_rec))) return TREAT_B200_ERR_INVALID;
     if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
     if (misaligned(d_rec) || misaligned(d_ops)) return fail(ctx, TREAT_B200_ERR_INVALID, "align: rec/ops must be 16-byte aligned");
@@ -1052,6 +1067,7 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
     if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
     if ((flags & TREAT_B200_WANT_OPS) && !ops) return fail(ctx, TREAT_B200_ERR_INVALID, "align: WANT_OPS without ops buffer");
     if (N == 0) return TREAT_B200_OK;
+    Nvtx nv_call("treat_b200_align_batch");
     CK(ctx, cudaSetDevice(ctx->device));
     const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
     // OPS_GAPPED_ONLY: only gapped reads' rows cross the bus, compacted on the device and placed by the host.  Placing
@@ -1252,9 +1268,13 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         Slot &s = ctx->slot[chunk_idx % n_slots];
         cudaStream_t st = s.stream;
         double t0 = now();
-        CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk (incl. its D2H) is done
-        if ((rc = settle(s))) return rc;
-        if ((rc = unstage_out(s))) return rc;
+        {
+            Nvtx nv("chunk: wait for slot + validate + deliver");
+            CK(ctx, cudaStreamSynchronize(st));  // the slot's previous chunk (incl. its D2H) is done
+            if ((rc = settle(s))) return rc;
+            if ((rc = unstage_out(s))) return rc;
+        }
+        Nvtx nv_enq("chunk: H2D + pack/align launches + D2H");
         double t1 = now();
         t_wait_slot += t1 - t0;
         const uint64_t b0 = seq_off[c0], b1 = seq_off[c0 + cn];
@@ -1354,6 +1374,7 @@ static bool host_pageable(const void *p)
 static int fasta_stage_copy_count(treat_b200_ctx *ctx, FastaDev &fa, const uint8_t *fasta, uint64_t len, cudaStream_t st,
                                   bool stage_pageable = false)
 {
+    Nvtx nv("fasta: H2D + record-start count");
     static const bool no_staging = getenv("TREAT_B200_NO_STAGING") != nullptr;
     const uint64_t piece = 32ull << 20;  // a multiple of the tile size
     const bool staged = stage_pageable && len && !no_staging && host_pageable(fasta);
@@ -1422,6 +1443,7 @@ static int fasta_stage_copy_count(treat_b200_ctx *ctx, FastaDev &fa, const uint8
 // stage B (stage A complete on the host): record starts, ids, merge counts, sequence begin / length, scan; scalars land in fa.h
 static int fasta_stage_index(treat_b200_ctx *ctx, FastaDev &fa, const uint8_t *fasta, cudaStream_t st)
 {
+    Nvtx nv("fasta: record index");
     const uint64_t len = fa.len, first = fa.h[1];
     const bool extra = first < len && !(first == 0 || fasta[first - 1] == '\n');  // the first '>' sits inside a line
     const uint64_t N = len ? fa.h[0] + (extra ? 1 : 0) : 0;
@@ -1470,6 +1492,7 @@ static void fasta_index_done(FastaDev &fa)
 static int fasta_align_chunk(treat_b200_ctx *ctx, FastaDev &fa, Slot &s, uint64_t c0, uint64_t cn, uint32_t flags, uint32_t ops_stride,
                              bool *in_place, uint32_t spec_ncap = 0)
 {
+    Nvtx nv("fasta: pack + align chunk");
     cudaStream_t st = s.stream;
     const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
     const bool sparse = want_ops && (flags & TREAT_B200_OPS_GAPPED_ONLY);
@@ -1520,6 +1543,7 @@ static int fasta_check_align(treat_b200_ctx *ctx, const FastaDev &fa, uint32_t f
 
 int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint64_t *n_records, uint32_t *max_seq_len)
 {
+    Nvtx nv_call("treat_b200_fasta_upload");
     if (!ctx || (len && !fasta) || !n_records) return TREAT_B200_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     FastaDev &fa = ctx->fasta;
@@ -1540,6 +1564,7 @@ int treat_b200_fasta_upload(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t 
 int treat_b200_fasta_align(treat_b200_ctx *ctx, uint32_t flags, treat_b200_record *rec, uint8_t *ops, uint32_t ops_stride,
                            uint64_t *id_off, uint32_t *id_len, uint32_t *read_count, uint64_t *seq_off, uint32_t *seq_len)
 {
+    Nvtx nv_call("treat_b200_fasta_align");
     if (!ctx) return TREAT_B200_ERR_INVALID;
     FastaDev &fa = ctx->fasta;
     if (!fa.open) return fail(ctx, TREAT_B200_ERR_INVALID, "fasta_align: no file uploaded (treat_b200_fasta_upload)");
@@ -1605,6 +1630,7 @@ static int fasta_blobs_write(treat_b200_ctx *ctx, Slot &s, const FastaDev &fa, b
 int treat_b200_fasta_stream(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, uint32_t ops_stride,
                             treat_b200_fasta_sink sink, void *user, uint64_t *n_records)
 {
+    Nvtx nv_call("treat_b200_fasta_stream");
     if (!ctx || (len && !fasta) || !sink) return TREAT_B200_ERR_INVALID;
     if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
     CK(ctx, cudaSetDevice(ctx->device));
@@ -1835,6 +1861,7 @@ static void text_template(const treat_b200_ctx *ctx, TextParams &tp)
 // pass 1 + scan: text_off[N + 1] on the device (tp holds the reads, names, records and ops); the total lands in *h_total
 static int text_sizes(treat_b200_ctx *ctx, Slot &s, TextParams &tp, uint64_t *d_text_off, cudaStream_t st)
 {
+    Nvtx nv("k_text: sizes + scan");
     const uint64_t N = tp.N;
     CK(ctx, s.tlen.reserve(N * 4));
     CK(ctx, s.gtot.reserve(N * 4));
@@ -1858,6 +1885,7 @@ static int text_sizes(treat_b200_ctx *ctx, Slot &s, TextParams &tp, uint64_t *d_
 
 static int text_write(treat_b200_ctx *ctx, Slot &s, TextParams &tp, const uint64_t *d_text_off, uint8_t *d_text, cudaStream_t st)
 {
+    Nvtx nv("k_text: write");
     tp.text_off = d_text_off;
     tp.text = d_text;
     tp.g_longest = (uint32_t)s.h_text_total[1];  // pass 1's longest row (the stream was synchronised since)
@@ -1874,6 +1902,7 @@ int treat_b200_text_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uin
                            uint64_t N, uint32_t max_len, int32_t tw, uint64_t *d_text_off, uint8_t *d_text, uint64_t text_cap,
                            uint64_t *text_bytes, void *stream)
 {
+    Nvtx nv_call("treat_b200_text_device");
     if (!ctx || !text_bytes || (N && (!d_seqs || !d_seq_off || !d_names || !d_name_off || !d_rec || !d_ops || !d_text_off)))
         return TREAT_B200_ERR_INVALID;
     if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "text: no template");
@@ -1955,6 +1984,7 @@ static int fasta_blobs_write(treat_b200_ctx *ctx, Slot &s, const FastaDev &fa, b
 int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off, const treat_b200_record *d_rec,
                               uint64_t N, uint64_t *d_blob_off, uint8_t *d_blob, uint64_t blob_cap, uint64_t *blob_bytes, void *stream)
 {
+    Nvtx nv_call("treat_b200_marshal_device");
     if (!ctx || !blob_bytes || (N && (!d_seqs || !d_seq_off || !d_rec || !d_blob_off))) return TREAT_B200_ERR_INVALID;
     *blob_bytes = 0;
     if (N == 0) return TREAT_B200_OK;
@@ -1992,6 +2022,7 @@ int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const 
 int treat_b200_text_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off, const uint8_t *names,
                           const uint64_t *name_off, uint64_t N, uint32_t flags, int32_t tw, treat_b200_text_sink sink, void *user)
 {
+    Nvtx nv_call("treat_b200_text_batch");
     if (!ctx || !sink || (N && (!seqs || !seq_off || !names || !name_off))) return TREAT_B200_ERR_INVALID;
     if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
     tw = text_tw(tw);
@@ -2096,6 +2127,7 @@ int treat_b200_text_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64
 int treat_b200_fasta_text(treat_b200_ctx *ctx, const uint8_t *fasta, uint64_t len, uint32_t flags, int32_t tw,
                           treat_b200_text_sink sink, void *user, uint64_t *n_records)
 {
+    Nvtx nv_call("treat_b200_fasta_text");
     if (!ctx || (len && !fasta) || !sink) return TREAT_B200_ERR_INVALID;
     if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "align: no template");
     tw = text_tw(tw);

@@ -312,7 +312,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 4) k_pack_finish(const __gri
 //     the summary counters as four running sums); otherwise the packed read goes to HBM and its index to the DP list.
 // Reads longer than a pass go to p.long_list for k_pack_finish (the multi-pass form).
 // ------------------------------------------------------------------------------------------
-constexpr int kF2Warps = 8;
+#ifndef TREAT_B200_F2_WARPS
+#define TREAT_B200_F2_WARPS 10
+#endif
+constexpr int kF2Warps = TREAT_B200_F2_WARPS;
 constexpr uint32_t kF2Pad = 16;  // bytes in front of a group's pairs: pair -1 (the read's offset in its first block) sits at byte 14
 __host__ __device__ constexpr uint32_t f2_group_bytes(int G) { return 2u * (32u * (uint32_t)G + 32u); }  // 8 pad + 32 G + 16 (+ 8) pairs
 constexpr uint32_t kHdrRange = 768;  // [33] folded prefix masks (k_pack_finish keeps its byte-mask table here)
@@ -351,7 +354,7 @@ struct F2Emit<0> {
 };
 
 #ifndef TREAT_B200_F2_MIN_CTAS
-#define TREAT_B200_F2_MIN_CTAS 3
+#define TREAT_B200_F2_MIN_CTAS 2  // 10 warps x 2 CTAs: 96 registers (no spilled prefetch registers), 20 resident warps per SM
 #endif
 template <int G, bool SPAN>
 __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_finish2(const __grid_constant__ PackParams p, const __grid_constant__ AlignParams q)
@@ -406,18 +409,21 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
     // the bytes of p.seqs this launch may touch: [lo, hi)
     const int64_t lo = SPAN ? 0 : p.N ? (int64_t)(p.off[0] - p.off_bias) : 0;
     const int64_t hi = SPAN ? (int64_t)p.span : p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
-    auto where = [&](uint32_t r, uint64_t &b, uint32_t &L) {
-        b = 0;
-        L = 0;
+    // where read r lies, as loaded (no arithmetic on the loaded values here: they are used one iteration later)
+    auto where = [&](uint32_t r, uint64_t &x0, uint64_t &x1) {
+        x0 = x1 = SPAN ? 0ull : p.off_bias;
         if (r >= N32) return;
         if (SPAN) {
-            b = p.begin[r];
-            L = p.len[r];
+            x0 = p.begin[r];
+            x1 = p.len[r];
         } else {
-            const uint64_t o0 = p.off[r], o1 = p.off[r + 1];
-            b = o0 - p.off_bias;
-            L = (uint32_t)(o1 - o0);
+            x0 = p.off[r];
+            x1 = p.off[r + 1];
         }
+    };
+    auto resolve = [&](uint64_t x0, uint64_t x1, uint64_t &b, uint32_t &L) {
+        b = SPAN ? x0 : x0 - p.off_bias;
+        L = SPAN ? (uint32_t)x1 : (uint32_t)(x1 - x0);
     };
     // this lane's two 16-byte blocks of a read (32-byte aligned in memory); zero when the lane is behind the read or the
     // read is too long for one pass.  Blocks that stick out of [lo, hi) -- only at the ends of a caller's buffer -- are
@@ -450,21 +456,23 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
     uint32_t accN = 0, accE = 0;                 // their numbers
     const uint32_t units = (uint32_t)((p.N + RPW - 1) / RPW);
     const uint32_t gw = blockIdx.x * kF2Warps + warp, nw = gridDim.x * kF2Warps;
-    // software pipeline: offsets two units ahead, the blocks one unit ahead
-    uint64_t b_cur = 0, b_nxt = 0;
+    // software pipeline: offsets two units ahead, the blocks one unit ahead; every load is issued a whole pass before its
+    // result is touched
+    uint64_t b_cur = 0, b_nxt = 0, x0_nxt = 0, x1_nxt = 0;
     uint32_t L_cur = 0, L_nxt = 0;
     uint4 blkA = make_uint4(0, 0, 0, 0), blkB = blkA;
     if (gw < units) {
-        where(gw * RPW + grp, b_cur, L_cur);
+        uint64_t x0, x1;
+        where(gw * RPW + grp, x0, x1);
+        resolve(x0, x1, b_cur, L_cur);
         load_blocks(b_cur, L_cur, blkA, blkB);
     }
-    if (gw + nw < units) where((gw + nw) * RPW + grp, b_nxt, L_nxt);
+    where((gw + nw) * RPW + grp, x0_nxt, x1_nxt);  // past the end: an empty read
     for (uint32_t u = gw; u < units; u += nw) {
-        uint4 nA = make_uint4(0, 0, 0, 0), nB = nA;
-        uint64_t b_nn = 0;
-        uint32_t L_nn = 0;
-        if (u + nw < units) load_blocks(b_nxt, L_nxt, nA, nB);
-        if (u + 2 * nw < units) where((u + 2 * nw) * RPW + grp, b_nn, L_nn);
+        uint4 nA, nB;
+        resolve(x0_nxt, x1_nxt, b_nxt, L_nxt);
+        load_blocks(b_nxt, L_nxt, nA, nB);
+        where((u + 2 * nw) * RPW + grp, x0_nxt, x1_nxt);
 
         const uint32_t r = u * RPW + grp;
         const uint32_t a = (base_lo + (uint32_t)b_cur) & 31u;  // the read starts at character a of lane 0's blocks
@@ -496,6 +504,7 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
         // ---- emit: pair = code | (character index in the lane blocks + 1) << 2 ------------------------------------
         uint32_t addr = pair32 + 2u * (incl - nbl);
         F2Emit<32>::run(w, lut32, vb, mask, addr);
+        TB_CHECK(q, addr == pair32 + 2u * incl && n <= 32u * (uint32_t)G, 8);  // the lane filled exactly its slice of the pair area
         // in front of the first base: the read's offset a ("the base before the first one sat at character a - 1");
         // behind the last base: the read's end closes the last run, then consecutive positions (zero counts, zero codes)
         if (gl == 0) sts_u16r(pair32 - 2u, a << 2);
@@ -612,6 +621,7 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
                     } else {
                         // JuncSeq = raw[just behind base from-1, just behind base to-1) (the trailing run for to = n + 1):
                         // the stored positions are those offsets
+                        TB_CHECK(q, from >= 0 && from < to && to <= (int)n + 1, 9);  // both positions lie inside the pair area
                         const uint32_t o0 = (lds_u16(pair32 + 2u * (uint32_t)from - 2u) >> 2) - a;
                         const uint32_t o1 = min((lds_u16(pair32 + 2u * (uint32_t)to - 2u) >> 2) - a, L);
                         js_len = o1 - o0;
@@ -692,7 +702,6 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
         }
         __syncwarp();
         b_cur = b_nxt, L_cur = L_nxt, blkA = nA, blkB = nB;
-        b_nxt = b_nn, L_nxt = L_nn;
     }
     warp_max_n = __reduce_max_sync(FULL_MASK, warp_max_n);
     warp_sat = __reduce_or_sync(FULL_MASK, warp_sat);
