@@ -527,13 +527,17 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
+    comm.join(sraw)  # the timed region ends when the last step's all-reduce has
     e1.record(stream)
     sampler.sample_now()  # the queue is still draining: a sample inside the timed region even when it lasts milliseconds
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - l0
     # the one collective of the path: the all-reduced "reads aligned" counter must hold every rank's reads of every step so far
-    reduced_reads = int(step_device()[14].item())
+    step_device()
+    comm.join(sraw)
+    torch.cuda.synchronize()
+    reduced_reads = int(d_red[14].item())
     assert reduced_reads == world * N * (args.warmup + args.steps + 1), (reduced_reads, world, N)
     clocks = sampler.stop()
     rec_dev = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
@@ -706,6 +710,15 @@ def run_ours(args):
         # the floor of this call: the same input bytes as one plain pinned H2D copy per rank, all ranks at once
         e2e.update(h2d_floor(cabi, eng, seqs, int(len(seqs)), barrier, max_over_ranks, world))
         e2e["frac_of_h2d_floor"] = e2e["h2d_floor_ms"] / e2e["ms_per_step"]
+        # ... and with everything the step moves: the inputs (reads, offsets, read counts) in and the results out at once
+        tms = C.c_double()
+        barrier()
+        cabi.check(cabi.lib().treat_b200_measure_transfer(eng._ctx, seqs.ctypes.data, min(int(e2e["h2d_bytes_per_step"]), seqs.base.nbytes if seqs.base is not None else seqs.nbytes),
+                                                          h_rec_raw.ctypes.data, min(int(e2e["d2h_bytes_per_step"]), h_rec_raw.nbytes), 5, C.byref(tms)), eng._ctx)
+        e2e["transfer_floor_ms"] = max_over_ranks(tms.value)
+        e2e["frac_of_transfer_floor"] = e2e["transfer_floor_ms"] / e2e["ms_per_step"]
+        e2e["transfer_floor_what"] = ("per step one pinned H2D copy of the step's input bytes and, on a second stream, one D2H copy of its "
+                                      "result bytes, every rank at once, max over ranks: what the box's PCIe / memory path allows")
         if rank == 0 and world == 1:
             # the same call from pageable buffers (what a cgo caller passing Go slices has): staged through pinned buffers
             # by the library's host copy threads

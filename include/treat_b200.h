@@ -168,6 +168,20 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
 int treat_b200_align_batch_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint64_t *d_seq_off,
                                   const uint32_t *d_read_count, uint64_t N, uint32_t max_len, uint32_t flags,
                                   treat_b200_record *d_rec, uint8_t *d_ops, uint32_t ops_stride, void *stream);
+/* The same with exact duplicates collapsed on the device first -- the step the TREAT workflow runs upstream of `treat load`
+ * (fastx_collapser: identical sequences become one record whose id carries the count that parseMergeCount reads back,
+ * fragment.go:43-55,75-89).  Reads whose upper-cased sequences are equal give the same Fragment (fragment.go:91-121), hence
+ * the same Alignment: only the first of them is aligned, with ReadCount = the sum of the members' counts (uint32 like
+ * Fragment.ReadCount).  Outputs, for the *n_unique distinct sequences in the order of their first occurrence:
+ *   rec[u], ops row u        the alignment of unique u (buffers sized for N: the caller cannot know n_unique before)
+ *   first[u]                 index in the input of the first read with that sequence (junc_seq_off refers to it)
+ *   member[r] (may be NULL)  for every input read the number u of its sequence
+ * The summary counters count every distinct sequence once ("unique", cmd/treat/stats.go --unique) and weigh it with the summed
+ * ReadCount -- what a load of the collapsed file gives.  Exact: candidates are found by a 64-bit hash and then compared byte
+ * for byte; a hash collision makes the library repeat the collapse with another seed. */
+int treat_b200_collapse_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off,
+                                    const uint32_t *read_count, uint64_t N, uint32_t flags, treat_b200_record *rec,
+                                    uint8_t *ops, uint32_t ops_stride, uint32_t *first, uint32_t *member, uint64_t *n_unique);
 /* bytes per read needed for the ops of reads up to max_len against the current template */
 uint32_t treat_b200_ops_stride(const treat_b200_ctx *ctx, uint32_t max_len);
 int treat_b200_synchronize(treat_b200_ctx *ctx);
@@ -250,6 +264,11 @@ int treat_b200_measure_int32_peak(treat_b200_ctx *ctx, double *lane_ops_per_s, d
  * into a device buffer of the context, timed with CUDA events on the context's stream: *ms_per_copy.  Run it on all ranks
  * at once to see what the host's PCIe / memory path gives N GPUs together (bench.py: e2e.h2d_floor_ms). */
 int treat_b200_measure_h2d(treat_b200_ctx *ctx, const void *host, uint64_t bytes, int32_t reps, double *ms_per_copy);
+/* The same with the results going the other way at the same time: per repetition one H2D copy of in_bytes and, on a second
+ * stream, one D2H copy of out_bytes into host_out; *ms_per_step = time until both are done.  PCIe is full duplex but the
+ * host's memory / IO path is shared by both directions. */
+int treat_b200_measure_transfer(treat_b200_ctx *ctx, const void *host_in, uint64_t in_bytes, void *host_out, uint64_t out_bytes,
+                                int32_t reps, double *ms_per_step);
 
 /* =====================================================================================
  * Several GPUs.  Reads shard over the GPUs with no data-path exchange; the only collective is one
@@ -298,9 +317,13 @@ void treat_b200_comm_destroy(treat_b200_comm *c);
  * are.  Every rank must call it (it is a collective). */
 int treat_b200_comm_reduce_summary(treat_b200_comm *c, uint64_t *out, uint64_t len);
 int treat_b200_comm_reduce_heatmap(treat_b200_comm *c, uint64_t *out, uint64_t len);
-/* The same without leaving the device: d_out[treat_b200_summary_len] = sum over ranks, enqueued on `stream` (a
- * cudaStream_t; NULL = the context's stream) behind the align calls issued on it. */
+/* The same without leaving the device: d_out[treat_b200_summary_len] = sum over ranks of the counters as they are once the
+ * work queued on `stream` (a cudaStream_t; NULL = the context's stream) so far has run.  A snapshot of the counters is
+ * taken on `stream`; the ncclAllReduce itself runs on the communicator's own stream, so the caller's next align call does
+ * not wait for the other ranks.  d_out is complete for work queued on a stream after treat_b200_comm_join(c, that stream)
+ * (or after treat_b200_comm_reduce_summary / cudaDeviceSynchronize). */
 int treat_b200_comm_reduce_summary_device(treat_b200_comm *c, uint64_t *d_out, void *stream);
+int treat_b200_comm_join(treat_b200_comm *c, void *stream);
 const char *treat_b200_comm_last_error(const treat_b200_comm *c);
 /* version of the NCCL library in use (e.g. 22809), 0 when none could be loaded */
 int32_t treat_b200_nccl_version(void);

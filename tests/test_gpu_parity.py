@@ -1051,3 +1051,74 @@ def test_tie_orders_match_oracle(eng, examples, tmp_path):
     finally:
         O.set_tie_order("ULD")
         eng.set_tie_order("ULD")
+
+
+def _collapse_case(eng, t, tmp_path, base_n, total_n, seed, p_trunc=0.0, lower_frac=0.2):
+    """A batch with many exact duplicates (sampled with replacement from base_n distinct reads, some of them in lower case)
+    against the oracle-side collapse: a dict of upper-cased sequences in order of first occurrence, ReadCounts summed."""
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    bseqs, boff, _ = synth.reads(t, base_n, seed=seed, p_trunc=p_trunc)
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, base_n, size=total_n)
+    rc = rng.integers(1, 50, size=total_n).astype(np.uint32)
+    parts = []
+    for i, q in enumerate(pick):
+        s = bseqs[int(boff[q]):int(boff[q + 1])].tobytes()
+        parts.append(s.lower() if rng.random() < lower_frac else s)
+    seqs = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    off = np.zeros(total_n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(p_) for p_ in parts])
+    # oracle-side collapse
+    seen, first, member, sums = {}, [], np.zeros(total_n, dtype=np.uint32), []
+    for i, s in enumerate(parts):
+        k = s.upper()
+        u = seen.get(k)
+        if u is None:
+            u = seen[k] = len(first)
+            first.append(i)
+            sums.append(0)
+        member[i] = u
+        sums[u] = (sums[u] + int(rc[i])) & 0xffffffff
+    first = np.array(first, dtype=np.uint32)
+    useqs = np.frombuffer(b"".join(parts[i] for i in first), dtype=np.uint8)
+    uoff = np.zeros(len(first) + 1, dtype=np.uint64)
+    uoff[1:] = np.cumsum([len(parts[i]) for i in first])
+    urc = np.array(sums, dtype=np.uint32)
+    eng.reset_summary()
+    grec, gops, gfirst, gmember = eng.collapse_align_batch(seqs, off, rc, cabi.WANT_OPS)
+    assert len(grec) == len(first) and len(first) <= base_n
+    assert np.array_equal(gfirst, first) and np.array_equal(gmember, member)
+    orec, oops, _ = O.align_batch(om, useqs, uoff, urc, nthreads=8, ops_stride=gops.shape[1])
+    assert compare_records(grec, orec) == []
+    assert np.array_equal(gops, oops)
+    assert np.array_equal(eng.summary(), summary_from_records(orec, t.m, 0, om.EditStop))
+    # the same records as aligning every read and picking the representatives (ReadCount aside)
+    arec, _ = eng.align_batch(seqs, off, rc, cabi.NO_SUMMARY)
+    for f in ("edit_stop", "junc_start", "junc_end", "junc_len", "score", "mismatches", "indel", "alt_editing", "junc_seq_len"):
+        assert np.array_equal(arec[f], grec[f][member]), f
+    return len(first) / total_n
+
+
+def test_collapse_exact_duplicates(eng, tmp_path):
+    """fastx_collapser on the device: >= 50 % duplicates, mixed case; uniques, members, summed ReadCounts, records,
+    ops and summary equal the oracle's on the collapsed set."""
+    frac = _collapse_case(eng, synth.rps12_template(), tmp_path, 9000, 40000, synth.SEED_BASE + 61, p_trunc=0.1)
+    assert frac < 0.5
+    _collapse_case(eng, synth.long_template(300, 8), tmp_path, 700, 3000, synth.SEED_BASE + 62, p_trunc=0.2)
+    # every read distinct, one read, and the wide path (a template base outside the packed alphabet)
+    assert _collapse_case(eng, synth.rps12_template(), tmp_path, 3000, 3000, synth.SEED_BASE + 63, lower_frac=0.0) <= 1.0
+    _collapse_case(eng, synth.rps12_template(), tmp_path, 1, 5, synth.SEED_BASE + 64)
+    p = tmp_path / "w.fa"
+    p.write_text(">fe\nACNGTTAGC%s\n>pe\nACNGAGC%s\n" % ("AG" * 20, "AG" * 20))
+    tm, om = T.NewTemplateFromFasta(str(p), T.FORWARD, "T"), O.NewTemplateFromFasta(str(p), O.FORWARD, "T")
+    eng.SetTemplate(tm)
+    reads = [b"ACNGTTAGC" + b"AG" * 20, b"acngttagc" + b"ag" * 20, b"ACNG" + b"T" * 300 + b"AGC" + b"AG" * 20, b"ACNGTTAGC" + b"AG" * 20]
+    seqs = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    off = np.array([0] + list(np.cumsum([len(r) for r in reads])), dtype=np.uint64)
+    grec, gops, gfirst, gmember = eng.collapse_align_batch(seqs, off, None, cabi.WANT_OPS)
+    assert list(gfirst) == [0, 2] and list(gmember) == [0, 0, 1, 0] and list(grec["read_count"]) == [3, 1]
+    useqs = np.frombuffer(reads[0] + reads[2], dtype=np.uint8)
+    uoff = np.array([0, len(reads[0]), len(reads[0]) + len(reads[2])], dtype=np.uint64)
+    orec, oops, _ = O.align_batch(om, useqs, uoff, np.array([3, 1], dtype=np.uint32), ops_stride=gops.shape[1])
+    assert compare_records(grec, orec) == [] and np.array_equal(gops, oops)

@@ -449,6 +449,32 @@ class Aligner:
             ops.ctypes.data if (flags & WANT_OPS) else None, stride), self._ctx)
         return rec, (ops if flags & WANT_OPS else None)
 
+    def collapse_align_batch(self, seqs: np.ndarray, seq_off: np.ndarray, read_count: Optional[np.ndarray] = None,
+                             flags: int = WANT_OPS, want_members: bool = True):
+        """treat_b200_collapse_align_batch: exact duplicates (equal upper-cased sequences) are collapsed on the device, only the
+        distinct sequences are aligned, with the members' ReadCounts summed (fastx_collapser upstream of `treat load`).
+        Returns (records[n_unique], ops[n_unique] or None, first[n_unique], member[N] or None)."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        N = len(seq_off) - 1
+        rec = np.zeros(N, dtype=RECORD_DTYPE)
+        stride, ops = 0, None
+        if flags & WANT_OPS:
+            max_len = int((seq_off[1:] - seq_off[:-1]).max()) if N else 0
+            stride = self.ops_stride(max_len)
+            ops = np.zeros((N, stride), dtype=np.uint8)
+        first = np.zeros(N, dtype=np.uint32)
+        member = np.zeros(N, dtype=np.uint32) if want_members else None
+        rc = None if read_count is None else np.ascontiguousarray(read_count, dtype=np.uint32)
+        nu = C.c_uint64()
+        dummy = np.zeros(1, np.uint8)
+        check(lib().treat_b200_collapse_align_batch(
+            self._ctx, seqs.ctypes.data if seqs.size else dummy.ctypes.data, seq_off.ctypes.data, rc.ctypes.data if rc is not None else None,
+            N, flags, rec.ctypes.data, ops.ctypes.data if ops is not None else None, stride, first.ctypes.data,
+            member.ctypes.data if member is not None else None, C.byref(nu)), self._ctx)
+        k = nu.value
+        return rec[:k], (ops[:k] if ops is not None else None), first[:k], member
+
     def align_batch_device(self, d_seqs: int, d_seq_off: int, d_read_count: int, N: int, max_len: int, flags: int,
                            d_rec: int, d_ops: int, ops_stride: int, stream: int = 0) -> None:
         """treat_b200_align_batch_device on raw device pointers (e.g. torch tensors' data_ptr())."""
@@ -802,4 +828,9 @@ class Comm:
         return out
 
     def reduce_summary_device(self, d_out: int, stream: int = 0) -> None:
+        """Snapshot on `stream`, ncclAllReduce on the communicator's stream (overlaps the caller's next step); see join()."""
         self._check(lib().treat_b200_comm_reduce_summary_device(self._c, d_out, stream or None))
+
+    def join(self, stream: int = 0) -> None:
+        """Work queued on `stream` after this call sees the results of every reduce_summary_device issued so far."""
+        self._check(lib().treat_b200_comm_join(self._c, stream or None))

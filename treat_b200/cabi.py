@@ -84,6 +84,7 @@ SIGNATURES = {
     "treat_b200_use_template": (C.c_int, [_P, _P]),
     "treat_b200_align_batch": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, _P, _U8P, C.c_uint32]),
     "treat_b200_align_batch_device": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
+    "treat_b200_collapse_align_batch": (C.c_int, [_P, _U8P, _P, _P, C.c_uint64, C.c_uint32, _P, _U8P, C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
     "treat_b200_ops_stride": (C.c_uint32, [_P, C.c_uint32]),
     "treat_b200_synchronize": (C.c_int, [_P]),
     "treat_b200_heatmap_dim": (C.c_uint32, [_P]),
@@ -117,6 +118,7 @@ SIGNATURES = {
     "treat_b200_summary_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "treat_b200_measure_int32_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "treat_b200_measure_h2d": (C.c_int, [_P, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
+    "treat_b200_measure_transfer": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "treat_b200_group_create": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
     "treat_b200_group_destroy": (None, [_P]),
     "treat_b200_group_size": (C.c_int32, [_P]),
@@ -136,6 +138,7 @@ SIGNATURES = {
     "treat_b200_comm_reduce_summary": (C.c_int, [_P, _P, C.c_uint64]),
     "treat_b200_comm_reduce_heatmap": (C.c_int, [_P, _P, C.c_uint64]),
     "treat_b200_comm_reduce_summary_device": (C.c_int, [_P, _P, _P]),
+    "treat_b200_comm_join": (C.c_int, [_P, _P]),
     "treat_b200_comm_last_error": (C.c_char_p, [_P]),
     "treat_b200_nccl_version": (C.c_int32, []),
     "treat_b200_parse_merge_count": (C.c_uint32, [C.c_char_p, _SZ]),

@@ -251,6 +251,11 @@ struct treat_b200_ctx {
     uint8_t *h_meta = nullptr;    //   their pinned staging buffer when the caller's arrays are pageable
     size_t h_meta_cap = 0;
     cudaEvent_t meta_done = nullptr;
+    // treat_b200_collapse_align_batch
+    struct {
+        DevBuf seqs, key, table, slot, head, rep, is_rep, sum, uidx, sums, first, begin, len, count, member, scal, rec, ops, gather, goff;
+        uint64_t *h = nullptr;  // pinned [4]: collisions | longest unique read << 32, n_unique
+    } col;
     FastaDev fasta;               // treat_b200_fasta_upload / treat_b200_fasta_align
     FastaDev fasta_slot[kFastaSlots];  // pieces in flight of treat_b200_fasta_stream
     Slot fslot[kFastaSlots];
@@ -379,6 +384,11 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     if (ctx->meta_done) cudaEventDestroy(ctx->meta_done);
     ctx->dev_slot.release();
+    for (DevBuf *b : {&ctx->col.seqs, &ctx->col.key, &ctx->col.table, &ctx->col.slot, &ctx->col.head, &ctx->col.rep, &ctx->col.is_rep, &ctx->col.sum,
+                      &ctx->col.uidx, &ctx->col.sums, &ctx->col.first, &ctx->col.begin, &ctx->col.len, &ctx->col.count, &ctx->col.member,
+                      &ctx->col.scal, &ctx->col.rec, &ctx->col.ops, &ctx->col.gather, &ctx->col.goff})
+        b->release();
+    if (ctx->col.h) cudaFreeHost(ctx->col.h);
     ctx->fasta.release();
     for (FastaDev &f : ctx->fasta_slot) f.release();
     for (Slot &sl : ctx->fslot) sl.release();
@@ -1352,6 +1362,122 @@ int treat_b200_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint6
         fprintf(stderr, "[treat_b200] align_batch N=%llu chunks=%llu total %.2f ms: wait_slot %.2f enqueue %.2f drain %.2f, chunks re-run %d\n",
                 (unsigned long long)N, (unsigned long long)chunk_idx, now() - t_begin, t_wait_slot, t_enqueue, now() - t_loop, redone);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact-duplicate collapse + alignment of the distinct sequences (collapse_kernel.cu)
+// ---------------------------------------------------------------------------------------------
+int treat_b200_collapse_align_batch(treat_b200_ctx *ctx, const uint8_t *seqs, const uint64_t *seq_off, const uint32_t *read_count,
+                                    uint64_t N, uint32_t flags, treat_b200_record *rec, uint8_t *ops, uint32_t ops_stride,
+                                    uint32_t *first, uint32_t *member, uint64_t *n_unique)
+{
+    if (!ctx || !n_unique || (N && (!seqs || !seq_off || !rec || !first))) return TREAT_B200_ERR_INVALID;
+    *n_unique = 0;
+    if (!ctx->have_template) return fail(ctx, TREAT_B200_ERR_NO_TEMPLATE, "collapse: no template");
+    const bool want_ops = (flags & TREAT_B200_WANT_OPS) != 0;
+    if (want_ops && !ops) return fail(ctx, TREAT_B200_ERR_INVALID, "collapse: WANT_OPS without ops buffer");
+    if (N == 0) return TREAT_B200_OK;
+    if (N > 0x7fffffffull) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "collapse: more than 2^31 reads in one call");
+    Nvtx nv_call("treat_b200_collapse_align_batch");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto &c = ctx->col;
+    const uint64_t b0 = seq_off[0], total = seq_off[N] - b0;
+    for (uint64_t i = 0; i < N; i++) {
+        const uint64_t l = seq_off[i + 1] - seq_off[i];
+        if (seq_off[i + 1] < seq_off[i] || l > kMaxReadLen)
+            return fail(ctx, l > kMaxReadLen ? TREAT_B200_ERR_TOO_LONG : TREAT_B200_ERR_INVALID,
+                        "collapse: read offsets not monotone or read longer than 16384");
+    }
+    uint32_t cap = 1024;
+    while (cap < 2 * N) cap <<= 1;
+    const uint32_t n32 = (uint32_t)N;
+    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, c.seqs.reserve(total + 64));
+    CK(ctx, ctx->d_off_all.reserve((N + 1) * 8));
+    if (read_count) CK(ctx, ctx->d_rc_all.reserve(N * 4));
+    CK(ctx, c.key.reserve(N * 8));
+    CK(ctx, c.table.reserve((size_t)cap * 8));
+    CK(ctx, c.head.reserve((size_t)cap * 4));
+    for (DevBuf *b : {&c.slot, &c.rep, &c.is_rep, &c.sum, &c.first, &c.len, &c.count, &c.member}) CK(ctx, b->reserve(N * 4));
+    CK(ctx, c.uidx.reserve((N + 1) * 8));
+    CK(ctx, c.begin.reserve(N * 8));
+    CK(ctx, c.sums.reserve((N / 2048 + 4) * 8));
+    CK(ctx, c.scal.reserve(64));
+    if (!c.h) CK(ctx, cudaMallocHost((void **)&c.h, 64));
+    if (total) CK(ctx, cudaMemcpyAsync(c.seqs.p, seqs + b0, total, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_off_all.p, seq_off, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (read_count) CK(ctx, cudaMemcpyAsync(ctx->d_rc_all.p, read_count, N * 4, cudaMemcpyHostToDevice, st));
+    const uint8_t *d_seqs = (const uint8_t *)c.seqs.p;
+    const uint64_t *d_off = (const uint64_t *)ctx->d_off_all.p;
+    const uint32_t *d_rc = read_count ? (const uint32_t *)ctx->d_rc_all.p : nullptr;
+    uint32_t *d_scal = (uint32_t *)c.scal.p;  // [0] collisions, [1] longest unique read
+    uint64_t nu = 0;
+    uint32_t max_len = 0;
+    for (uint32_t seed = 0x2545f491u, tries = 0;; seed = seed * 0x9e3779b1u + 1u, tries++) {
+        if (tries == 8) return fail(ctx, TREAT_B200_ERR_CUDA, "collapse: eight hash seeds in a row gave a collision");
+        CK(ctx, cudaMemsetAsync(c.table.p, 0, (size_t)cap * 8, st));
+        CK(ctx, cudaMemsetAsync(c.head.p, 0xff, (size_t)cap * 4, st));
+        CK(ctx, cudaMemsetAsync(c.sum.p, 0, N * 4, st));
+        CK(ctx, cudaMemsetAsync(c.scal.p, 0, 64, st));
+        int e = launch_collapse_hash(d_seqs, d_off, b0, n32, seed, (uint64_t *)c.key.p, ctx->num_sms, st);
+        if (!e) e = launch_collapse_table((const uint64_t *)c.key.p, n32, (uint64_t *)c.table.p, cap, (uint32_t *)c.slot.p, (uint32_t *)c.head.p,
+                                          ctx->num_sms, st);
+        if (!e) e = launch_collapse_verify(d_seqs, d_off, b0, d_rc, n32, (const uint32_t *)c.slot.p, (const uint32_t *)c.head.p, (uint32_t *)c.rep.p,
+                                           (uint32_t *)c.is_rep.p, (uint32_t *)c.sum.p, d_scal, d_scal + 1, ctx->num_sms, st);
+        if (!e) e = launch_scan_u32((const uint32_t *)c.is_rep.p, N, (uint64_t *)c.uidx.p, (uint64_t *)c.sums.p, st);
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("collapse launch: ") + cudaGetErrorString((cudaError_t)e));
+        ctx->launches += 7;
+        PEEK(ctx, &c.h[0], d_scal, 8, st);
+        PEEK(ctx, &c.h[1], (uint64_t *)c.uidx.p + N, 8, st);
+        CK(ctx, cudaStreamSynchronize(st));
+        if ((uint32_t)(c.h[0] & 0xffffffffu) == 0) {
+            max_len = (uint32_t)(c.h[0] >> 32);
+            nu = c.h[1];
+            break;
+        }
+    }
+    int e = launch_collapse_compact(d_off, b0, n32, (const uint32_t *)c.rep.p, (const uint32_t *)c.is_rep.p, (const uint64_t *)c.uidx.p,
+                                    (const uint32_t *)c.sum.p, (uint32_t *)c.first.p, (uint64_t *)c.begin.p, (uint32_t *)c.len.p,
+                                    (uint32_t *)c.count.p, member ? (uint32_t *)c.member.p : nullptr, ctx->num_sms, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_collapse_compact launch: ") + cudaGetErrorString((cudaError_t)e));
+    ctx->launches++;
+    const uint32_t need_stride = treat_b200_ops_stride(ctx, max_len);
+    if (want_ops && (ops_stride < need_stride || ops_stride % 16))
+        return fail(ctx, TREAT_B200_ERR_INVALID, "collapse: ops_stride too small (see treat_b200_ops_stride)");
+    CK(ctx, c.rec.reserve(nu * sizeof(treat_b200_record)));
+    if (want_ops) CK(ctx, c.ops.reserve(nu * (size_t)ops_stride));
+    uint8_t *d_ops = want_ops ? (uint8_t *)c.ops.p : nullptr;
+    // the distinct reads are aligned where they lie, as (begin, length) spans ...
+    const ReadSpan span{(const uint64_t *)c.begin.p, (const uint32_t *)c.len.p, total};
+    bool sat = false;
+    int rc = TREAT_B200_OK;
+    if (!ctx->tmpl_wide)
+        rc = run_chunk(ctx, ctx->dev_slot, d_seqs, nullptr, 0, (const uint32_t *)c.count.p, nu, max_len, flags, (treat_b200_record *)c.rec.p, d_ops,
+                       ops_stride, st, false, &sat, nullptr, 0, &span, true);
+    if (rc) return rc;
+    if (ctx->tmpl_wide || sat) {
+        // ... unless the wide path is needed (a template outside the packed alphabet, an edit-base run of 255 or more):
+        // its kernels read back-to-back reads, so the distinct ones are gathered first
+        CK(ctx, c.goff.reserve((nu + 1) * 8));
+        CK(ctx, c.gather.reserve(total + 64));
+        e = launch_scan_u32((const uint32_t *)c.len.p, nu, (uint64_t *)c.goff.p, (uint64_t *)c.sums.p, st);
+        if (!e)
+            e = launch_collapse_gather(d_seqs, (const uint64_t *)c.begin.p, (const uint32_t *)c.len.p, (const uint64_t *)c.goff.p, (uint32_t)nu,
+                                       (uint8_t *)c.gather.p, ctx->num_sms, st);
+        if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("collapse gather launch: ") + cudaGetErrorString((cudaError_t)e));
+        ctx->launches += 4;
+        rc = run_chunk(ctx, ctx->dev_slot, (const uint8_t *)c.gather.p, (const uint64_t *)c.goff.p, 0, (const uint32_t *)c.count.p, nu, max_len, flags,
+                       (treat_b200_record *)c.rec.p, d_ops, ops_stride, st, true, nullptr, nullptr, 0, nullptr, false);
+        if (rc) return rc;
+    }
+    CK(ctx, cudaMemcpyAsync(rec, c.rec.p, nu * sizeof(treat_b200_record), cudaMemcpyDeviceToHost, st));
+    if (want_ops) CK(ctx, cudaMemcpyAsync(ops, c.ops.p, nu * (size_t)ops_stride, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(first, c.first.p, nu * 4, cudaMemcpyDeviceToHost, st));
+    if (member) CK(ctx, cudaMemcpyAsync(member, c.member.p, N * 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    *n_unique = nu;
+    return TREAT_B200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2348,6 +2474,44 @@ int treat_b200_measure_h2d(treat_b200_ctx *ctx, const void *host, uint64_t bytes
     cudaEventDestroy(e1);
     cudaFree(d);
     *ms_per_copy = (double)ms / reps;
+    return TREAT_B200_OK;
+}
+
+int treat_b200_measure_transfer(treat_b200_ctx *ctx, const void *host_in, uint64_t in_bytes, void *host_out, uint64_t out_bytes,
+                                int32_t reps, double *ms_per_step)
+{
+    if (!ctx || !host_in || !in_bytes || !host_out || !out_bytes || reps < 1 || !ms_per_step) return TREAT_B200_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    void *d_in = nullptr, *d_out = nullptr;
+    CK(ctx, cudaMalloc(&d_in, in_bytes));
+    CK(ctx, cudaMalloc(&d_out, out_bytes));
+    cudaStream_t s2;
+    CK(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1, e2;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    CK(ctx, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    CK(ctx, cudaMemcpyAsync(d_in, host_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));  // warm-up
+    CK(ctx, cudaMemcpyAsync(host_out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaEventRecord(e0, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(s2, e0, 0));
+    for (int i = 0; i < reps; i++) {
+        CK(ctx, cudaMemcpyAsync(d_in, host_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(host_out, d_out, out_bytes, cudaMemcpyDeviceToHost, s2));
+    }
+    CK(ctx, cudaEventRecord(e2, s2));
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, e2, 0));
+    CK(ctx, cudaEventRecord(e1, ctx->stream));
+    CK(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    cudaStreamDestroy(s2);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    *ms_per_step = (double)ms / reps;
     return TREAT_B200_OK;
 }
 

@@ -199,6 +199,21 @@ int launch_int32_peak(int num_sms, int iters, int *d_out, void *stream);
 int configure_pack_kernels(int max_smem_optin);
 int configure_align_kernels(int max_smem_optin);
 
+// exact-duplicate collapse (collapse_kernel.cu)
+int launch_collapse_hash(const uint8_t *seqs, const uint64_t *off, uint64_t off_bias, uint32_t N, uint32_t seed, uint64_t *key,
+                         int num_sms, void *stream);
+int launch_collapse_table(const uint64_t *key, uint32_t N, uint64_t *table, uint32_t cap, uint32_t *slot, uint32_t *head, int num_sms,
+                          void *stream);
+int launch_collapse_verify(const uint8_t *seqs, const uint64_t *off, uint64_t off_bias, const uint32_t *read_count, uint32_t N,
+                           const uint32_t *slot, const uint32_t *head, uint32_t *rep, uint32_t *is_rep, uint32_t *sum, uint32_t *collisions,
+                           uint32_t *max_len, int num_sms, void *stream);
+int launch_collapse_compact(const uint64_t *off, uint64_t off_bias, uint32_t N, const uint32_t *rep, const uint32_t *is_rep,
+                            const uint64_t *uidx, const uint32_t *sum, uint32_t *first, uint64_t *begin, uint32_t *len, uint32_t *count,
+                            uint32_t *member, int num_sms, void *stream);
+
+int launch_collapse_gather(const uint8_t *seqs, const uint64_t *begin, const uint32_t *len, const uint64_t *dst_off, uint32_t N, uint8_t *dst,
+                           int num_sms, void *stream);
+
 // context internals other translation units need (group.cu)
 int ctx_device(const treat_b200_ctx *ctx);
 #ifdef __CUDACC__

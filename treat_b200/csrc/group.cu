@@ -162,9 +162,15 @@ struct treat_b200_comm {
     treat_b200_ctx *ctx = nullptr;
     int device = 0, nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // the collectives run here, beside the caller's stream
     uint64_t *d_red = nullptr;
     size_t red_cap = 0;
+    // treat_b200_comm_reduce_summary_device: two snapshots of the counters in turn, so that a reduction overlaps the next step
+    uint64_t *d_snap[2] = {nullptr, nullptr};
+    size_t snap_cap[2] = {0, 0};
+    cudaEvent_t snap_done[2] = {nullptr, nullptr}, red_done[2] = {nullptr, nullptr};
+    bool red_pending[2] = {false, false};
+    unsigned turn = 0;
     std::string err;
 };
 
@@ -469,14 +475,31 @@ void treat_b200_comm_destroy(treat_b200_comm *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->d_red) cudaFree(c->d_red);
+    for (int i = 0; i < 2; i++) {
+        if (c->d_snap[i]) cudaFree(c->d_snap[i]);
+        if (c->snap_done[i]) cudaEventDestroy(c->snap_done[i]);
+        if (c->red_done[i]) cudaEventDestroy(c->red_done[i]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 const char *treat_b200_comm_last_error(const treat_b200_comm *c) { return c ? c->err.c_str() : ""; }
 
+#define CCK(c, expr)                                                          \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            (c)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);    \
+            return TREAT_B200_ERR_CUDA;                                       \
+        }                                                                     \
+    } while (0)
+
+// The reduction runs on the communicator's own stream over a snapshot of the counters taken on the caller's stream, so the
+// caller's next align call does not wait for the other ranks: a rank that is late delays the reduction, not the kernels.
 int treat_b200_comm_reduce_summary_device(treat_b200_comm *c, uint64_t *d_out, void *stream)
 {
     if (!c || !d_out) return TREAT_B200_ERR_INVALID;
@@ -485,19 +508,45 @@ int treat_b200_comm_reduce_summary_device(treat_b200_comm *c, uint64_t *d_out, v
     if (rc) return rc;
     const uint64_t len = treat_b200_summary_len(c->ctx);
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx_stream(c->ctx);
-    if (cudaSetDevice(c->device) != cudaSuccess) return TREAT_B200_ERR_CUDA;
+    CCK(c, cudaSetDevice(c->device));
+    const int i = (int)(c->turn++ & 1u);
+    if (!c->snap_done[i]) {
+        CCK(c, cudaEventCreateWithFlags(&c->snap_done[i], cudaEventDisableTiming));
+        CCK(c, cudaEventCreateWithFlags(&c->red_done[i], cudaEventDisableTiming));
+    }
+    if (c->red_pending[i]) CCK(c, cudaStreamWaitEvent(st, c->red_done[i], 0));  // the reduction that last read this snapshot
+    if (c->snap_cap[i] < len * 8) {
+        CCK(c, cudaStreamSynchronize(c->stream));
+        if (c->d_snap[i]) cudaFree(c->d_snap[i]);
+        c->d_snap[i] = nullptr;
+        c->snap_cap[i] = 0;
+        CCK(c, cudaMalloc((void **)&c->d_snap[i], len * 8));
+        c->snap_cap[i] = len * 8;
+    }
+    CCK(c, cudaMemcpyAsync(c->d_snap[i], src, len * 8, cudaMemcpyDeviceToDevice, st));
+    CCK(c, cudaEventRecord(c->snap_done[i], st));
+    CCK(c, cudaStreamWaitEvent(c->stream, c->snap_done[i], 0));
     if (c->nranks == 1) {
-        if (cudaMemcpyAsync(d_out, src, len * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-            c->err = cudaGetErrorString(cudaGetLastError());
+        CCK(c, cudaMemcpyAsync(d_out, c->d_snap[i], len * 8, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        const int e = nccl().AllReduce(c->d_snap[i], d_out, (size_t)len, kNcclUint64, kNcclSum, c->comm, c->stream);
+        if (e != kNcclSuccess) {
+            c->err = nccl_error("ncclAllReduce", e);
             return TREAT_B200_ERR_CUDA;
         }
-        return TREAT_B200_OK;
     }
-    const int e = nccl().AllReduce(src, d_out, (size_t)len, kNcclUint64, kNcclSum, c->comm, st);
-    if (e != kNcclSuccess) {
-        c->err = nccl_error("ncclAllReduce", e);
-        return TREAT_B200_ERR_CUDA;
-    }
+    CCK(c, cudaEventRecord(c->red_done[i], c->stream));
+    c->red_pending[i] = true;
+    return TREAT_B200_OK;
+}
+
+int treat_b200_comm_join(treat_b200_comm *c, void *stream)
+{
+    if (!c) return TREAT_B200_ERR_INVALID;
+    CCK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx_stream(c->ctx);
+    const int last = (int)((c->turn + 1u) & 1u);  // the most recent reduction; the one before it precedes it on the same stream
+    if (c->turn && c->red_pending[last]) CCK(c, cudaStreamWaitEvent(st, c->red_done[last], 0));
     return TREAT_B200_OK;
 }
 
