@@ -714,7 +714,7 @@ def run_ours(args):
         tms = C.c_double()
         barrier()
         cabi.check(cabi.lib().treat_b200_measure_transfer(eng._ctx, seqs.ctypes.data, min(int(e2e["h2d_bytes_per_step"]), seqs.base.nbytes if seqs.base is not None else seqs.nbytes),
-                                                          h_rec_raw.ctypes.data, min(int(e2e["d2h_bytes_per_step"]), h_rec_raw.nbytes), 5, C.byref(tms)), eng._ctx)
+                                                          h_ops_raw.ctypes.data, min(int(e2e["d2h_bytes_per_step"]), h_ops_raw.nbytes), 5, C.byref(tms)), eng._ctx)  # (scratch: the ops buffer)
         e2e["transfer_floor_ms"] = max_over_ranks(tms.value)
         e2e["frac_of_transfer_floor"] = e2e["transfer_floor_ms"] / e2e["ms_per_step"]
         e2e["transfer_floor_what"] = ("per step one pinned H2D copy of the step's input bytes and, on a second stream, one D2H copy of its "

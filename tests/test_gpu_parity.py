@@ -1000,9 +1000,7 @@ def test_zz_checked_build_bounds_clean():
     import subprocess
     import sys
     from treat_b200 import _build
-    lib = os.path.join(os.path.dirname(_build.LIB), "_build", "checked", "libtreat_b200.so")
-    if not os.path.exists(lib):
-        lib = _build.build_variant("checked", ["-DTREAT_B200_CHECKS"])
+    lib = _build.build_variant("checked", ["-DTREAT_B200_CHECKS"])  # up to date after build(): nothing to compile then
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, TREAT_B200_LIB=lib, TREAT_B200_EXPECT_CHECKS="1")
     out = subprocess.run([sys.executable, os.path.join(root, "tests", "sanitize_smoke.py")], env=env, capture_output=True, text=True, timeout=900)
