@@ -852,6 +852,39 @@ def run_ours(args):
         side["noisy"] = side_workload(T, cabi, synth, eng, "noisy", 500_000, 6, alloc)
         eng.SetTemplate(tm)
 
+    # ---- exact-duplicate collapse on the device (fastx_collapser upstream of `treat load`) -----------------------------
+    collapse = None
+    if rank == 0 and world == 1 and not args.no_side and args.workload == "rps12":
+        cn, distinct = min(N, 500_000), 100_000
+        rng = np.random.default_rng(7)
+        pick = rng.integers(0, distinct, size=cn)
+        lens_c = lens[pick]
+        coff = np.zeros(cn + 1, dtype=np.uint64)
+        coff[1:] = np.cumsum(lens_c)
+        cseqs = alloc(int(coff[-1]))
+        src_off = off.astype(np.int64)
+        idx = np.repeat(src_off[pick] - coff[:-1].astype(np.int64), lens_c) + np.arange(int(coff[-1]), dtype=np.int64)
+        cseqs[:] = seqs[idx]
+        crc = rc[pick].copy()
+        t0 = time.perf_counter()
+        crec, _, cfirst, _ = eng.collapse_align_batch(cseqs, coff, crc, cabi.NO_SUMMARY, want_members=False)
+        for _ in range(3):
+            t0 = time.perf_counter()
+            crec, _, cfirst, _ = eng.collapse_align_batch(cseqs, coff, crc, cabi.NO_SUMMARY, want_members=False)
+        c_ms = 1e3 * (time.perf_counter() - t0)
+        arec = np.zeros(cn, dtype=cabi.RECORD_DTYPE)
+        for _ in range(2):
+            t0 = time.perf_counter()
+            eng.align_batch(cseqs, coff, crc, cabi.NO_SUMMARY, rec=arec)
+        a_ms = 1e3 * (time.perf_counter() - t0)
+        same = all(np.array_equal(arec[f][cfirst], crec[f]) for f in ("edit_stop", "junc_end", "junc_len", "score", "mismatches", "indel"))
+        collapse = {"reads": cn, "unique": int(len(crec)), "unique_fraction": len(crec) / cn, "ms_collapse_align": c_ms, "ms_align_every_read": a_ms,
+                    "records_returned": int(len(crec)), "agrees_with_uncollapsed": bool(same),
+                    "api": "treat_b200_collapse_align_batch vs treat_b200_align_batch on %d reads drawn from %d distinct ones "
+                           "(host buffers): duplicates collapse on the device, only the distinct sequences are aligned and returned" % (cn, distinct)}
+        if not same:
+            raise AssertionError("collapsed and uncollapsed records disagree")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)  # the CPU port gets every host core
@@ -896,7 +929,7 @@ def run_ours(args):
             # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
             "value_dp_every_read": world * N / (dp_every_ms * 1e-3),
             "roofline": roofline, "roofline_dp": roofline_dp, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
-            "text_device": text_dev, "parity": parity, "long": side.get("long"), "noisy": side.get("noisy"),
+            "text_device": text_dev, "parity": parity, "long": side.get("long"), "noisy": side.get("noisy"), "collapse": collapse,
             "nccl": {"version": cabi.lib().treat_b200_nccl_version() if world > 1 else None,
                      "collective": "ncclAllReduce(uint64, sum) of the summary counters, issued by libtreat_b200.so "
                                    "(treat_b200_comm_reduce_summary_device) once per step" if world > 1 else "none (1 GPU)"},

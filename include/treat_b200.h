@@ -362,7 +362,13 @@ int32_t treat_b200_template_alt_start(const treat_b200_template *t, int32_t i);
 int32_t treat_b200_template_alt_end(const treat_b200_template *t, int32_t i);
 uint32_t treat_b200_template_max(const treat_b200_template *t, int32_t i); /* Max(i) template.go:186 */
 
-/* FASTA reader with gofasta.SimpleParser's record semantics (cmd/treat/align.go:114) */
+/* FASTA reader with gofasta.SimpleParser's record semantics (cmd/treat/align.go:114).
+ * UNPINNED (like the traceback tie order): gofasta (github.com/aebruno/gofasta@e776ef625791, go.mod:6) is not vendored in the
+ * reference, and none of its tests says how header / sequence lines are trimmed.  Assumed here, by the host reader, the
+ * device parser and the test oracle alike: Id = the header line behind '>' with strings.TrimSpace applied; sequence lines
+ * are concatenated with only the line break ('\n', or '\r\n') removed -- a trailing blank or tab inside a sequence line
+ * stays in the sequence and counts as a base outside the alphabet; a last line without '\n' is kept; bytes before the
+ * first '>' are ignored.  If gofasta trims sequence lines, such files would differ. */
 typedef struct treat_b200_fasta treat_b200_fasta;
 int treat_b200_fasta_read(const char *path, treat_b200_fasta **out);
 int treat_b200_fasta_parse(const uint8_t *bytes, uint64_t len, treat_b200_fasta **out); /* the same on bytes in memory */

@@ -324,17 +324,19 @@ constexpr uint32_t kHdrRange = 768;  // [33] folded prefix masks (k_pack_finish 
 __host__ __device__ constexpr uint32_t f2_bit(int k) { return 8u * (uint32_t)(k & 3) + (uint32_t)(k >> 2); }
 
 // store `val` at addr and advance addr iff the mask bit is set
-template <uint32_t BIT>
-__device__ __forceinline__ void f2_emit(uint32_t &addr, uint32_t val, uint32_t mask)
+template <uint32_t BIT, uint32_t ADD>
+__device__ __forceinline__ void f2_emit(uint32_t &addr, uint32_t v, uint32_t vb, uint32_t mask)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-        "and.b32 t, %2, %3;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b32 t, val;\n\t"
+        "and.b32 t, %3, %4;\n\t"
         "setp.ne.u32 p, t, 0;\n\t"
-        "@p st.shared.u16 [%0], %1;\n\t"
+        "add.u32 val, %1, %2;\n\t"
+        "add.u32 val, val, %5;\n\t"
+        "@p st.shared.u16 [%0], val;\n\t"
         "@p add.u32 %0, %0, 2;\n\t}"
         : "+r"(addr)
-        : "r"(val), "r"(mask), "n"(1u << BIT)
+        : "r"(v), "r"(vb), "r"(mask), "n"(1u << BIT), "n"(ADD)
         : "memory");
 }
 
@@ -345,7 +347,7 @@ struct F2Emit {
         F2Emit<K - 1>::run(w, lut32, vb, mask, addr);
         constexpr int k = K - 1;
         const uint32_t v = lds_u8n(__byte_perm(w[k >> 2], lut32, 0x7650 + (k & 3)));  // lut32 | character
-        f2_emit<f2_bit(k)>(addr, v + vb + (uint32_t)(k << 2), mask);
+        f2_emit<f2_bit(k), (uint32_t)(k << 2)>(addr, v, vb, mask);
     }
 };
 template <>
@@ -403,7 +405,8 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
 
     const SameLane sl = load_same_lane(cs, q, gl);
     const uint32_t eb4 = (uint32_t)eb * 0x01010101u;
-    const uint32_t vb = (uint32_t)(32 * gl + 1) << 2;  // pair value of the lane's first character (code 0)
+    uint32_t vb = (uint32_t)(32 * gl + 1) << 2;  // pair value of the lane's first character (code 0)
+    asm volatile("" : "+r"(vb));  // one register, not an expression to rebuild at every use: the emit adds it once per character
     const uint32_t base_lo = (uint32_t)reinterpret_cast<uintptr_t>(p.seqs);
     const uint32_t N32 = (uint32_t)p.N;  // a launch holds < 2^31 reads (host check)
     // the bytes of p.seqs this launch may touch: [lo, hi)
