@@ -56,6 +56,8 @@ extern "C" {
 #define TREAT_B200_HEATMAP 0x100u /* also accumulate the ESS x junction-length heat map (treat_b200_get_heatmap) */
 #define TREAT_B200_SKIP_DP 0x400u /* measurement only (bench.py times the fused kernel alone with it): the DP launch for the reads
                                      that need one is skipped, so their records are NOT written */
+#define TREAT_B200_NO_BAND 0x800u /* do not run the banded / pure-deletion kernel in front of the full-matrix DP (results are the
+                                     same; tests compare both ways) */
 #define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
                                            under the template that is current now, so reads it marked as equal to the template
                                            skip the DP; without this flag the stage call runs the DP for every read */
@@ -238,6 +240,9 @@ typedef struct treat_b200_geometry {
     uint32_t occupancy_warps_per_sm; /* resident warps = warps_per_cta (one CTA per SM) */
 } treat_b200_geometry;
 int treat_b200_align_geometry(treat_b200_ctx *ctx, uint32_t max_n, uint32_t flags, treat_b200_geometry *out);
+/* which kernel finished the reads that needed a DP since the last reset: out3[0] pure deletions (leftmost embedding, no
+ * DP), out3[1] banded fill with an exactness certificate, out3[2] left for the full-matrix kernels (bench / tests) */
+int treat_b200_dp_stats(treat_b200_ctx *ctx, uint64_t *out3, int32_t reset);
 /* bounds-check flags of the kernels' index computations: always 0 unless the library was built with
  * -DTREAT_B200_CHECKS (*checks_compiled says which); a substitute for compute-sanitizer on pools without it */
 int treat_b200_debug_flags(treat_b200_ctx *ctx, uint32_t *flags_out, int32_t *checks_compiled);

@@ -186,8 +186,9 @@ def _batch_vs_oracle(eng, t, tmp_path, N, seed, p_trunc=0.0, offset=0, exclude=F
     # the template's (finished without a DP by default) must all give the same bytes
     k = min(N, 3001)
     E = cabi.DP_EVERY_READ
-    for extra in (E, cabi.ONE_READ_PER_WARP, cabi.FULL_TRACEBACK_STORE, E | cabi.ONE_READ_PER_WARP, E | cabi.FULL_TRACEBACK_STORE,
-                  E | cabi.ONE_READ_PER_WARP | cabi.FULL_TRACEBACK_STORE):
+    # (the first two also run k_band -- pure deletions, banded fill -- in front of the full-matrix kernels; NO_BAND does not)
+    for extra in (E, cabi.NO_BAND, E | cabi.NO_BAND, cabi.ONE_READ_PER_WARP, cabi.FULL_TRACEBACK_STORE, E | cabi.ONE_READ_PER_WARP,
+                  E | cabi.FULL_TRACEBACK_STORE, E | cabi.ONE_READ_PER_WARP | cabi.FULL_TRACEBACK_STORE):
         srec, sops = eng.align_batch(seqs[:int(off[k])], off[:k + 1], rc[:k], flags | extra | cabi.NO_SUMMARY)
         assert np.array_equal(srec, grec[:k]) and np.array_equal(sops[:, :gops.shape[1]], gops[:k, :sops.shape[1]])
     return grec, orec, seqs, off
@@ -1027,7 +1028,7 @@ def test_tie_orders_match_oracle(eng, examples, tmp_path):
             O.set_tie_order(order)
             eng.set_tie_order(order)
             eng.SetTemplate(tm)
-            for extra in (0, cabi.DP_EVERY_READ, cabi.ONE_READ_PER_WARP | cabi.DP_EVERY_READ, cabi.FULL_TRACEBACK_STORE):
+            for extra in (0, cabi.DP_EVERY_READ, cabi.NO_BAND, cabi.ONE_READ_PER_WARP | cabi.DP_EVERY_READ, cabi.FULL_TRACEBACK_STORE):
                 grec, gops = eng.align_batch(fb.seqs, fb.offsets, fb.read_counts, cabi.WANT_OPS | extra)
                 orec, oops, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, ops_stride=gops.shape[1])
                 assert compare_records(grec, orec) == [], (order, extra)
@@ -1046,6 +1047,97 @@ def test_tie_orders_match_oracle(eng, examples, tmp_path):
                 assert compare_records(grec, orec) == [], order
                 assert np.array_equal(gops, oops), order
         assert differ > 0  # the orders do give different alignments on this set: the switch is not a no-op
+    finally:
+        O.set_tie_order("ULD")
+        eng.set_tie_order("ULD")
+
+
+def test_band_and_pure_deletion_paths(eng, examples, tmp_path):
+    """k_band (band_kernel.cu) in front of the full-matrix kernels: reads whose bases are a subsequence of the template's
+    (truncated ends, deletions inside, repeats where only the LEFTMOST embedding is nwalgo's), reads a few edits away
+    (banded fill + certificate) and reads the certificate must refuse -- records and every ops row against the oracle,
+    for the three tie orders, with the path counters showing that all three routes were taken."""
+    rng = random.Random(99)
+    t = synth.rps12_template()
+    om, tm = _oracle_template(t, tmp_path)
+    eb = "T"
+    fe = t.raw_sequences()[0]
+    bases = t.bases.decode()
+
+    def with_counts(bs):
+        # a read with the given bases and random edit-base runs
+        return "".join(eb * rng.choice((0, 0, 1, 2, 5)) + b for b in bs) + eb * rng.randint(0, 3)
+
+    recs = []
+    for i in range(300):  # pure deletions: drop random bases, cut the ends
+        bs = list(bases)
+        for _ in range(rng.randint(0, 6)):
+            del bs[rng.randrange(len(bs))]
+        lo, hi = rng.choice((0, 0, rng.randint(0, 60))), rng.choice((0, 0, rng.randint(0, 60)))
+        bs = bs[lo:len(bs) - hi]
+        recs.append(("del-%d" % i, with_counts(bs)))
+    for i in range(300):  # a few substitutions / indels: certified by the band
+        bs = list(bases)
+        for _ in range(rng.randint(1, 8)):
+            k, pos = rng.randrange(3), rng.randrange(len(bs))
+            if k == 0:
+                del bs[pos]
+            elif k == 1:
+                bs.insert(pos, rng.choice("ACG"))
+            else:
+                bs[pos] = rng.choice("ACGN")
+        recs.append(("edit-%d" % i, with_counts(bs)))
+    for i in range(200):  # far from the template: the certificate fails, or the length difference leaves the band
+        bs = list(bases)
+        for _ in range(rng.randint(15, 60)):
+            k, pos = rng.randrange(3), rng.randrange(len(bs))
+            if k == 0:
+                del bs[pos]
+            elif k == 1:
+                bs.insert(pos, rng.choice("ACG"))
+            else:
+                bs[pos] = rng.choice("ACG")
+        recs.append(("far-%d" % i, with_counts(bs)))
+    recs += [("fe", fe), ("one", "A"), ("two", "CG"), ("first", bases[0]), ("last", bases[-1]), ("allT", eb * 7)]
+    fb = T.FastaBatch.from_records(recs)
+    try:
+        for order in ("ULD", "UDL", "LUD"):
+            O.set_tie_order(order)
+            eng.set_tie_order(order)
+            eng.SetTemplate(tm)
+            orec, oops, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, ops_stride=None)
+            eng.dp_stats()
+            for extra in (0, cabi.DP_EVERY_READ, cabi.NO_BAND):
+                grec, gops = eng.align_batch(fb.seqs, fb.offsets, fb.read_counts, cabi.WANT_OPS | extra)
+                w = min(gops.shape[1], oops.shape[1])
+                assert compare_records(grec, orec) == [], (order, extra)
+                assert np.array_equal(gops[:, :w], oops[:, :w]), (order, extra)
+                sub, band, full = eng.dp_stats()
+                if extra == 0:
+                    assert sub > 200 and band > 200 and full > 50, (sub, band, full)
+                elif extra == cabi.DP_EVERY_READ:
+                    assert sub == 0 and band > 400 and full > 50, (sub, band, full)
+                else:
+                    assert sub == band == full == 0
+        # a template with repeats: many embeddings of a truncated read exist, nwalgo's is the leftmost
+        rep = "ACG" * 30 + "AACCGG" * 10 + "ACG" * 10
+        tpath = tmp_path / "rep.fa"
+        tpath.write_text(">FE\n%s\n>PE\n%s\n" % ("T".join(rep), rep))
+        tm2 = T.NewTemplateFromFasta(str(tpath), T.FORWARD, "T")
+        om2 = O.NewTemplateFromFasta(str(tpath), O.FORWARD, "T")
+        recs2 = [("r-%d" % i, rep[rng.randint(0, 80):len(rep) - rng.randint(0, 80)]) for i in range(200)]
+        recs2 += [("s-%d" % i, "".join(c for c in rep if rng.random() > 0.1)) for i in range(200)]
+        fb2 = T.FastaBatch.from_records(recs2)
+        for order in ("ULD", "UDL", "LUD"):
+            O.set_tie_order(order)
+            eng.set_tie_order(order)
+            eng.SetTemplate(tm2)
+            orec, oops, _ = O.align_batch(om2, fb2.seqs, fb2.offsets, fb2.read_counts, ops_stride=None)
+            for extra in (0, cabi.DP_EVERY_READ, cabi.NO_BAND):
+                grec, gops = eng.align_batch(fb2.seqs, fb2.offsets, fb2.read_counts, cabi.WANT_OPS | extra)
+                w = min(gops.shape[1], oops.shape[1])
+                assert compare_records(grec, orec) == [], (order, extra)
+                assert np.array_equal(gops[:, :w], oops[:, :w]), (order, extra)
     finally:
         O.set_tie_order("ULD")
         eng.set_tie_order("ULD")

@@ -63,6 +63,7 @@ def main():
         step()
     e1.record(st)
     torch.cuda.synchronize()
+    print("reads that needed a DP per step: pure deletions %d, banded %d, full matrix %d" % tuple(v // (a.reps + 1) for v in eng.dp_stats()))
     print("%s: %d reads, %.3f ms per step (%.1f M reads/s), %d launches" % (
         a.workload, N, e0.elapsed_time(e1) / a.reps, N / (e0.elapsed_time(e1) / a.reps) / 1e3, eng.launch_count()))
     eng.close()

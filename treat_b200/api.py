@@ -631,6 +631,12 @@ class Aligner:
         check(lib().treat_b200_debug_flags(self._ctx, C.byref(f), C.byref(c)), self._ctx)
         return f.value, bool(c.value)
 
+    def dp_stats(self, reset: bool = True) -> Tuple[int, int, int]:
+        """Reads that needed a DP since the last reset: (pure deletions finished without one, banded fill, full matrix)."""
+        out = (C.c_uint64 * 3)()
+        check(lib().treat_b200_dp_stats(self._ctx, out, 1 if reset else 0), self._ctx)
+        return int(out[0]), int(out[1]), int(out[2])
+
     def launch_count(self) -> int:
         return lib().treat_b200_launch_count(self._ctx)
 

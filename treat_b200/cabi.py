@@ -18,6 +18,7 @@ ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_TOO_LONG, ERR_NO_TEMPLATE, ERR_NO_DEVICE, 
 FORWARD, REVERSE = 1, -1
 EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY, ONE_READ_PER_WARP, FULL_TRACEBACK_STORE = 0x1, 0x2, 0x4, 0x8, 0x10
 DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY, HEATMAP, WANT_BLOBS, SKIP_DP = 0x20, 0x40, 0x80, 0x100, 0x200, 0x400
+NO_BAND = 0x800
 ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16
@@ -111,6 +112,7 @@ SIGNATURES = {
     "treat_b200_set_tie_order": (C.c_int, [_P, C.c_int32]),
     "treat_b200_align_geometry": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(AlignGeometry)]),
     "treat_b200_debug_flags": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
+    "treat_b200_dp_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32]),
     "treat_b200_summary_bins": (C.c_uint32, [_P]),
     "treat_b200_summary_len": (C.c_uint64, [_P]),
     "treat_b200_get_summary": (C.c_int, [_P, _P, C.c_uint64]),

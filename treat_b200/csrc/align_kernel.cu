@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(max_warps_one(CPL) * 32, 1) k_align(const __gr
     constexpr int ROWS = 5;
 
     extern __shared__ __align__(128) uint8_t smem[];
+    if (p.list && *p.list_count == 0u) return;  // nothing was left for the DP: skip the template / profile set-up
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int m = p.t.m;
 
@@ -598,6 +599,7 @@ __global__ void __launch_bounds__(max_warps_one(kStripCpl) * 32, 1) k_align_stri
     using cnt_t = typename std::conditional<WIDE, uint32_t, uint8_t>::type;
 
     extern __shared__ __align__(128) uint8_t smem[];
+    if (p.list && *p.list_count == 0u) return;  // nothing was left for the DP
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int m = p.t.m, strips = (int)p.strips;
 
@@ -739,6 +741,7 @@ __global__ void __launch_bounds__(max_warps_pair(CPL) * 32, 1) k_align2(const __
     constexpr int ROWS = 25;  // (code of read A) * 5 + (code of read B)
 
     extern __shared__ __align__(128) uint8_t smem[];
+    if (p.list && *p.list_count == 0u) return;  // nothing was left for the DP: skip the template / profile set-up
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int m = p.t.m;
 

@@ -409,11 +409,13 @@ __device__ __forceinline__ SameLane load_same_lane(const CtaSmem<uint8_t> &cs, c
 template <int G>
 __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<uint8_t> &cs, const uint4 *s_mask, int gl,
                                             unsigned gmask, int lead, uint64_t r, uint32_t rflags, const uint4 &c,
-                                            const SameLane &sl, unsigned long long &ctr, uint32_t raw_len_known = 0xffffffffu)
+                                            const SameLane &sl, unsigned long long &ctr, uint32_t raw_len_known = 0xffffffffu,
+                                            int mism_known = -1)
 {
-    // no gap; no mismatch, or exactly one (kFlagOneMismatch: the diagonal still is the unique optimum, score m - 2)
-    const int mism = (rflags & kFlagOneMismatch) ? 1 : 0;
-    const int has_mutation = ((p.flags & TREAT_B200_EXCLUDE_SNPS) && mism) ? 1 : 0;  // align.go:240-241
+    // no gap; no mismatch, or exactly one (kFlagOneMismatch: the diagonal still is the unique optimum, score m - 2), or
+    // as many as the caller's traceback found on the diagonal (mism_known, k_band_finish)
+    const int mism = mism_known >= 0 ? mism_known : (rflags & kFlagOneMismatch) ? 1 : 0;
+    const int has_mutation = (((p.flags & TREAT_B200_EXCLUDE_SNPS) && mism >= 1) || mism >= 3) ? 1 : 0;  // align.go:240-241
     const int m = p.t.m, n = m, len = p.t.len, K = p.t.K, base = 16 * gl;
     const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
     uint32_t df[4], dp[4];  // non-zero byte: the read's count differs from FE / PE at that site
@@ -509,9 +511,9 @@ __device__ __forceinline__ void flush_summary(const AlignParams &p, uint32_t sum
 // it would otherwise set the register count of the whole kernel)
 static __device__ __noinline__ void finish_same_general(const AlignParams &p, const CtaSmem<uint8_t> &cs, const WarpSmem &ws, int lane,
                                                  uint64_t r, uint32_t rflags, const uint8_t *rcount, unsigned long long &ctr,
-                                                 uint32_t raw_len_known = 0xffffffffu)
+                                                 uint32_t raw_len_known = 0xffffffffu, int mism_known = -1)
 {
-    const int m = p.t.m, mism = (rflags & kFlagOneMismatch) ? 1 : 0;  // the diagonal: score m - 2 per mismatch, no gap
+    const int m = p.t.m, mism = mism_known >= 0 ? mism_known : (rflags & kFlagOneMismatch) ? 1 : 0;  // the diagonal: score m - 2 per mismatch, no gap
     finish_read<uint8_t>(p, cs, ws, lane, r, m, rflags, /*score*/ m - 2 * mism, /*pos*/ m, /*ngaps*/ 0, rcount,
                          [](int) { return 0; }, ctr, mism, raw_len_known);
 }

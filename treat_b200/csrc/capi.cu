@@ -137,6 +137,7 @@ struct Slot {
     DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops, summary;
     DevBuf list;     // reads that need the DP (written by k_same_bases / k_pack_finish*, read by the align kernels)
     DevBuf long_list;  // reads too long for one pass of k_pack_finish2
+    DevBuf list2;      // reads k_band leaves for the full-matrix kernels
     DevBuf ops_idx;  // OPS_GAPPED_ONLY: read index of every compacted ops row
     // OPS_GAPPED_ONLY: pinned landing buffers of the compacted rows and their read indices
     uint8_t *h_gap_rows = nullptr;
@@ -167,7 +168,7 @@ struct Slot {
     uint32_t max_len = 0, dev_stride = 0;
     void release()
     {
-        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &long_list, &ops_idx, &text,
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &long_list, &list2, &ops_idx, &text,
                           &text_off, &tlen, &gtot, &tsums, &names, &name_off})
             b->release();
         if (tland) cudaFreeHost(tland);
@@ -239,6 +240,7 @@ struct treat_b200_ctx {
     uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
     uint32_t gap_hint = 0;   // most gapped reads seen in a chunk: sizes the ahead-of-time copy of compacted ops rows
     uint32_t *d_dbg = nullptr;  // bounds-check flags (only written by TREAT_B200_CHECKS builds)
+    unsigned long long *d_dp_stats = nullptr;  // [4] reads k_band finished as pure deletions / by the banded fill / left for the full DP
     std::vector<uint8_t> lut;
     uint64_t *d_summary = nullptr;
     uint32_t bins = 0;
@@ -356,10 +358,17 @@ int treat_b200_create(int device, treat_b200_ctx **out)
         delete ctx;
         return TREAT_B200_ERR_CUDA;
     }
+    if (cudaMalloc((void **)&ctx->d_dp_stats, 32) != cudaSuccess || cudaMemset(ctx->d_dp_stats, 0, 32) != cudaSuccess) {
+        cudaFree(ctx->d_dbg);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return TREAT_B200_ERR_CUDA;
+    }
     int e = configure_pack_kernels(ctx->max_smem);
     if (!e) e = configure_align_kernels(ctx->max_smem);
     if (!e) e = configure_text_kernels(ctx->max_smem);
     if (!e) e = configure_fused_kernels(ctx->max_smem);
+    if (!e) e = configure_band_kernels(ctx->max_smem);
     if (e) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -378,6 +387,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (ctx->d_summary) cudaFree(ctx->d_summary);
     if (ctx->d_heat) cudaFree(ctx->d_heat);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    if (ctx->d_dp_stats) cudaFree(ctx->d_dp_stats);
     for (Slot &sl : ctx->slot) sl.release();
     ctx->d_off_all.release();
     ctx->d_rc_all.release();
@@ -562,6 +572,16 @@ int treat_b200_synchronize(treat_b200_ctx *ctx)
 
 uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int treat_b200_dp_stats(treat_b200_ctx *ctx, uint64_t *out3, int32_t reset)
+{
+    if (!ctx || !out3) return TREAT_B200_ERR_INVALID;
+    int rc = treat_b200_synchronize(ctx);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpy(out3, ctx->d_dp_stats, 24, cudaMemcpyDeviceToHost));
+    if (reset) CK(ctx, cudaMemset(ctx->d_dp_stats, 0, 32));
+    return TREAT_B200_OK;
+}
+
 int treat_b200_debug_flags(treat_b200_ctx *ctx, uint32_t *flags_out, int32_t *checks_compiled)
 {
     if (!ctx || !flags_out) return TREAT_B200_ERR_INVALID;
@@ -710,6 +730,9 @@ struct AlignOpts {
     bool listed = false;              // the list is already filled (k_pack_finish ran): no k_same_bases launch
     DevBuf *long_list = nullptr;      // k_pack_finish2: reads too long for one of its passes (taken up by k_pack_finish)
     uint32_t *long_count = nullptr;   //   (must be zero on entry)
+    DevBuf *list2 = nullptr;          // with list2_count: k_band runs first (pure deletions, banded fill) and leaves these reads
+    uint32_t *list2_count = nullptr;  //   for the full-matrix kernels
+    bool list2_zeroed = false;        //   the caller cleared the counter on this stream already
 };
 
 // the parameter block of an align launch (everything but the shared-memory plan, the scratch and the list)
@@ -777,11 +800,16 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     // than 7 columns per lane the two-reads-per-warp kernel's scratch (8 bytes per lane and step) no longer fits L2 for
     // them, so listed reads of long templates take the one-read kernel; the paired one serves whole batches.
     const bool use_list = list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ);
-    if (use_list && ctx->td.m > 7 * 32) ap.force_single = 1u;
+    if ((use_list || (o.list2 && !(flags & TREAT_B200_DP_EVERY_READ))) && ctx->td.m > 7 * 32) ap.force_single = 1u;
     if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
+    static const bool no_band_env = getenv("TREAT_B200_NO_BAND") != nullptr;
+    const bool want_band = !no_band_env && !wide && o.list2 && o.list2_count &&
+                           !(flags & (TREAT_B200_NO_BAND | TREAT_B200_FULL_TRACEBACK_STORE | TREAT_B200_ONE_READ_PER_WARP));
+    const uint64_t band_bytes = want_band ? band_scratch_bytes(ap, ctx->num_sms, ctx->max_smem) : 0;  // 0: k_band does not apply
     {
-        // global scratch for reads whose path may leave the band (one region per resident warp)
-        const uint64_t need = align_scratch_bytes(ap, ctx->num_sms, ctx->max_smem);
+        // global scratch for reads whose path may leave the band (one region per resident warp); k_band's direction words
+        // use the same buffer (the two launches follow each other on this stream)
+        const uint64_t need = std::max<uint64_t>(align_scratch_bytes(ap, ctx->num_sms, ctx->max_smem), band_bytes);
         if (need > scratch.cap) {
             CK(ctx, cudaStreamSynchronize(st));  // the only launches that use this buffer run on this stream
             CK(ctx, scratch.reserve(need));
@@ -799,6 +827,18 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
             if (e0) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_same_bases launch: ") + cudaGetErrorString((cudaError_t)e0));
             ctx->launches++;
         }
+    }
+    // K2b: pure deletions and reads a few edits away from the template (banded fill with an exactness certificate) are
+    // finished by k_band; what it cannot certify goes to list2 for the full-matrix kernels below
+    if (band_bytes) {
+        CK(ctx, o.list2->reserve(src->N * 4));
+        if (!o.list2_zeroed) CK(ctx, cudaMemsetAsync(o.list2_count, 0, 4, st));
+        const bool subseq = !(flags & TREAT_B200_DP_EVERY_READ);
+        int eb = launch_band(ap, (uint32_t *)o.list2->p, o.list2_count, scratch.p, subseq, ctx->d_dp_stats, ctx->num_sms, ctx->max_smem, st);
+        if (eb) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_band launch: ") + cudaGetErrorString((cudaError_t)eb));
+        ctx->launches++;
+        ap.list = (uint32_t *)o.list2->p;
+        ap.list_count = o.list2_count;
     }
     int e = launch_align(ap, wide, ctx->num_sms, ctx->max_smem, st);
     if (e == -1000 || e == -1001)
@@ -845,9 +885,18 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
         AlignOpts o;
         o.list = &ctx->dev_slot.list;
         o.list_count = ctx->dev_slot.scalars + 3;
+        o.list2 = &ctx->dev_slot.list2;
+        o.list2_count = ctx->dev_slot.scalars + 6;
         return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st, ctx->dev_slot.scratch, o);
     }
-    return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st, ctx->dev_slot.scratch);
+    {
+        int rc = ensure_scalars(ctx, ctx->dev_slot);
+        if (rc) return rc;
+        AlignOpts o;
+        o.list2 = &ctx->dev_slot.list2;
+        o.list2_count = ctx->dev_slot.scalars + 6;
+        return do_align(ctx, src, src->max_len, d_read_count, flags, d_rec, d_ops, ops_stride, st, ctx->dev_slot.scratch, o);
+    }
 }
 
 // K1f: pack + finish the reads that need no DP in one launch (k_pack_finish); the rest is listed for do_align(listed = true)
@@ -916,6 +965,9 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         AlignOpts o;
         o.list = &s.list;
         o.list_count = s.scalars + 3;
+        o.list2 = &s.list2;
+        o.list2_count = s.scalars + 6;
+        o.list2_zeroed = true;  // run_chunk clears the slot's scalars first
         if (own) {
             o.ops_count = s.scalars + 4;
             if (flags & TREAT_B200_OPS_GAPPED_ONLY) o.ops_idx = (uint32_t *)s.ops_idx.p;

@@ -173,6 +173,12 @@ int launch_pack_finish(const PackParams &p, const AlignParams &q, int num_sms, i
 bool pack_finish2_applies(const PackParams &p, const AlignParams &q);
 int launch_pack_finish2(const PackParams &p, const AlignParams &q, int num_sms, int max_smem_optin, void *stream);
 int configure_fused_kernels(int max_smem_optin);
+// K2b (band_kernel.cu): of the reads launch_align would get (p.list, or all of them), finishes the pure deletions and the
+// ones a banded fill certifies; the others are appended to list2.  band_scratch_bytes: global scratch it needs (0: n/a).
+uint64_t band_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
+int launch_band(const AlignParams &p, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, unsigned long long *stats,
+                int num_sms, int max_smem, void *stream);
+int configure_band_kernels(int max_smem_optin);
 // K2s: finishes the reads marked kFlagSameBases without a DP and lists the others (p is the plan_align'ed block)
 int launch_same_bases(const AlignParams &p, int num_sms, void *stream);
 // fills the shared-memory geometry of p for (m, K, ncap, wide); returns columns-per-lane or -1
