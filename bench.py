@@ -393,7 +393,15 @@ def side_workload(T, cabi, synth, eng, name, N, steps, alloc):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / steps
     dev_ms = timed(flags)
+    torch.cuda.synchronize()
+    eng.dp_stats()
+    step_dev(flags)
+    torch.cuda.synchronize()  # the step ran on this process's stream: the counters are final only behind it
+    paths = eng.dp_stats()  # (pure deletions, banded fill, full matrix) of one step, counted by the kernels
     dp_ms = timed(flags | cabi.DP_EVERY_READ)
+    full_ms = timed(flags | cabi.DP_EVERY_READ | cabi.NO_BAND)
+    step_dev(flags)
+    torch.cuda.synchronize()
     rec = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
     no_dp = (rec["indel"] == 0) & (rec["mismatches"] <= 1) & (rec["n_bases"] == t.m)
     cells = rec["n_bases"].astype(np.int64) * t.m
@@ -410,13 +418,35 @@ def side_workload(T, cabi, synth, eng, name, N, steps, alloc):
            "value_dp_every_read": N / (dp_ms * 1e-3), "ms_per_step_dp_every_read": dp_ms,
            "e2e": {"value": N / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(seqs) + (N + 1) * 8 + N * 4)},
            "reads_finished_without_dp": float(no_dp.mean()), "reads_with_gap": float((rec["indel"] != 0).mean()),
-           "gcups_performed": float(cells[~no_dp].sum()) / (dev_ms * 1e-3) / 1e9,
-           "gcups_dp_every_read": float(cells.sum()) / (dp_ms * 1e-3) / 1e9}
+           "dp_paths": {"pure_deletion_no_dp": paths[0] / N, "banded_fill": paths[1] / N, "full_matrix": paths[2] / N,
+                        "what": "fraction of the reads by the kernel that finished them after the fused kernel (k_band_classify / "
+                                "k_band_fill + k_band_finish / k_align*), counted on the device"},
+           "gcups_performed": performed_cells(rec, t.m)[0] / (dev_ms * 1e-3) / 1e9,
+           "gcups_effective_dp_every_read": float(cells.sum()) / (dp_ms * 1e-3) / 1e9,
+           "value_full_matrix_dp_every_read": N / (full_ms * 1e-3), "ms_per_step_full_matrix_dp_every_read": full_ms,
+           "gcups_full_matrix_dp_every_read": float(cells.sum()) / (full_ms * 1e-3) / 1e9}
     geom = cabi.AlignGeometry()
     if cabi.lib().treat_b200_align_geometry(eng._ctx, int(rec["n_bases"].max()), 0, C.byref(geom)) == 0:
         out["geometry"] = {f: getattr(geom, f) for f, _ in cabi.AlignGeometry._fields_}
     del d_seqs, d_off, d_rc, d_rec, d_ops
     return out
+
+
+def performed_cells(rec, m):
+    """DP cells the kernels fill for these records (what gcups_performed counts), from the records alone: reads the fused
+    kernel finishes (no gap, at most one mismatch, n = m) and pure deletions (gap-only reads with score 2n - m: leftmost
+    embedding) need none; reads within 15 bases of the template's length take the banded fill (32 diagonals x max(m, n)
+    rows; the few whose certificate fails are counted as banded too); the rest fill the whole m x n matrix."""
+    n = rec["n_bases"].astype(np.int64)
+    no_dp = (rec["indel"] == 0) & (rec["mismatches"] <= 1) & (n == m)
+    subseq = (rec["indel"] != 0) & (rec["mismatches"] == 0) & (n <= m) & (rec["score"].astype(np.int64) == 2 * n - m)
+    band = ~no_dp & ~subseq & (np.abs(n - m) < 16)
+    full = ~no_dp & ~subseq & ~band
+    cells = np.zeros(len(rec), dtype=np.int64)
+    cells[band] = 32 * np.maximum(n[band], m)
+    cells[full] = n[full] * m
+    return float(cells.sum()), {"no_dp": float(no_dp.mean()), "pure_deletion": float(subseq.mean()), "banded": float(band.mean()),
+                                "full_matrix": float(full.mean())}
 
 
 def run_ours(args):
@@ -544,7 +574,7 @@ def run_ours(args):
     cells_per_step = float((rec_dev["n_bases"].astype(np.int64) * t.m).sum())
     # reads finished without a DP: no gap, at most one mismatch, as long as the template (k_pack's marks)
     no_dp = (rec_dev["indel"] == 0) & (rec_dev["mismatches"] <= 1) & (rec_dev["n_bases"] == t.m)
-    cells_performed = float((rec_dev["n_bases"].astype(np.int64) * t.m)[~no_dp].sum())
+    cells_performed, path_frac = performed_cells(rec_dev, t.m)
     value = world * N * args.steps / (dev_ms * 1e-3)
 
     # ---- the dominant kernel alone (k_align on already-packed reads), CUDA events ----------------
@@ -576,9 +606,19 @@ def run_ours(args):
     pk_full = cabi.Packed()
     C.memmove(C.byref(pk_full), C.byref(pk), C.sizeof(pk))
     pk_full.max_len = max_len
-    # the DP kernel on every read (what the roofline is about) ...
+    # the DP stage on every read (what roofline_dp is about): k_band_classify / k_band_fill / k_band_finish, then k_align2 for
+    # the reads whose certificate fails ...
     align_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_align_packed_device(
         eng._ctx, C.byref(pk), d_rc.data_ptr(), flags, d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw), eng._ctx), args.steps)
+    eng.dp_stats()
+    cabi.check(cabi.lib().treat_b200_align_packed_device(eng._ctx, C.byref(pk), d_rc.data_ptr(), flags, d_rec.data_ptr(), d_ops.data_ptr(),
+                                                         stride, sraw), eng._ctx)
+    torch.cuda.synchronize()
+    dp_paths_every = eng.dp_stats()
+    # ... and the full m x n matrix of every read (k_align2 alone, TREAT_B200_NO_BAND): the kernel round 1 reported
+    full_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_align_packed_device(
+        eng._ctx, C.byref(pk), d_rc.data_ptr(), flags | cabi.NO_BAND, d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw), eng._ctx),
+        max(2, args.steps // 2))
     # ... and what the batch call launches: k_same_bases finishes the reads whose bases equal the template's without a
     # DP and lists the others for the DP kernel
     marks_ms = kernel_ms(lambda: cabi.check(cabi.lib().treat_b200_align_packed_device(
@@ -660,18 +700,31 @@ def run_ours(args):
     roofline_pack = {"bound": "hbm", "kernel": "k_pack16 (stage call treat_b200_pack_device)", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": pack_ms,
                      "bytes_per_launch": pack_bytes}
-    # k_align2 on every read: algorithmic integer ops of the DP
+    # the DP stage on every read.  Algorithmic work: m x n cells x 8 scalar integer ops; the banded fill
+    # performs 32 x max(m, n) cells for a read it certifies, so two figures are reported: `frac` on the cells the kernels
+    # actually fill, `frac_algorithmic` on the full matrices they replace (the banded kernel makes that one exceed 1).
     alg_bytes = float(((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4 + 4) + N * 48 + ((t.m + n_arr + 3) // 4).sum())
     int_ops = cells_per_step * INT_OPS_PER_CELL
-    roofline_dp = {"bound": "int32", "kernel": "k_align2 on every read (k_align for wide/long templates)",
-                   "achieved": int_ops / (align_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
-                   "unit": "Tiop/s", "frac": int_ops / (align_ms * 1e-3) / int_peak,
+    band_reads, full_reads = dp_paths_every[1], dp_paths_every[2]
+    near = np.abs(n_arr - t.m) < 16
+    cells_filled = float((32 * np.maximum(n_arr, t.m))[near].sum() + (n_arr * t.m)[~near].sum())
+    roofline_dp = {"bound": "int32", "kernel": "DP stage on every read: k_band_fill + k_band_finish (banded, certified), k_align2 for the rest",
+                   "achieved": cells_filled * INT_OPS_PER_CELL / (align_ms * 1e-3) / 1e12, "peak": int_peak / 1e12,
+                   "unit": "Tiop/s", "frac": cells_filled * INT_OPS_PER_CELL / (align_ms * 1e-3) / int_peak,
+                   "frac_algorithmic": int_ops / (align_ms * 1e-3) / int_peak,
                    "peak_source": "measured live: k_int32_peak (dependent-free add+max, all SMs)",
-                   "ops_per_cell": INT_OPS_PER_CELL, "cells_per_launch": cells_per_step, "ms_per_launch": align_ms,
-                   "gcups": cells_per_step / (align_ms * 1e-3) / 1e9, "traffic": ncu_traffic("k_align2"), "ncu": ncu_facts("k_align2"),
+                   "ops_per_cell": INT_OPS_PER_CELL, "cells_per_launch": cells_per_step, "cells_filled_per_launch": cells_filled,
+                   "ms_per_launch": align_ms,
+                   "gcups": cells_per_step / (align_ms * 1e-3) / 1e9, "gcups_performed": cells_filled / (align_ms * 1e-3) / 1e9,
+                   "reads_banded": int(band_reads), "reads_full_matrix": int(full_reads),
+                   "full_matrix_every_read": {"kernel": "k_align2 (TREAT_B200_NO_BAND)", "ms_per_launch": full_ms,
+                                              "gcups": cells_per_step / (full_ms * 1e-3) / 1e9,
+                                              "frac": int_ops / (full_ms * 1e-3) / int_peak},
+                   "traffic": ncu_traffic("k_band_fill"), "ncu": ncu_facts("k_band_fill"),
                    "hbm_frac": alg_bytes / (align_ms * 1e-3) / 1e9 / hbm_peak,
-                   "note": "frac is against a SCALAR 8-op-per-cell roofline; the kernel needs ~1.5 instructions per cell "
-                           "(gap-free transform, two reads per register, IMAD-packed direction digits), so frac can exceed 1"}
+                   "note": "frac counts the cells the kernels fill (a 32-diagonal band for certified reads) at 8 scalar ops per "
+                           "cell against the measured INT32 peak; the kernels need ~4 instructions per cell PAIR (two reads per "
+                           "register: PRMT score select, IMAD add, VIMNMX3.S16x2, IMAD direction digits), so frac can exceed 1"}
     del d_b, d_c, d_n, d_fl, d_rl
 
     # ---- end to end through the host-buffer C ABI call -------------------------------------------------
@@ -922,9 +975,12 @@ def run_ours(args):
                        "parallelism": "reads sharded over %d GPU(s), summary all-reduce only" % world,
                        "outputs": "48-byte record per read + %d-byte 2-bit ops row per read with a gap" % stride},
             "kernels_ms": {"k_pack_finish2 (fused NewFragment + assembly)": fused_ms,
-                           "k_align2 (DP on the listed reads) = step - fused": max(dev_ms / args.steps - fused_ms, 0.0),
+                           "k_band_* + k_align2 (reads that need a DP) = step - fused": max(dev_ms / args.steps - fused_ms, 0.0),
                            "stage calls: k_pack16": pack_ms, "stage calls: k_same_bases+k_align(listed reads)": marks_ms,
-                           "k_align2 (DP on every read)": align_ms},
+                           "DP stage on every read (k_band_* + k_align2)": align_ms,
+                           "k_align2 on every read (full matrix, NO_BAND)": full_ms},
+            "dp_paths": dict(path_frac, what="fraction of the reads by how they are finished: fused kernel without a DP, pure "
+                                             "deletion (leftmost embedding, no DP), banded fill, full matrix (from the records)"),
             "reads_equal_to_template_bases": same_frac,
             # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
             "value_dp_every_read": world * N / (dp_every_ms * 1e-3),

@@ -220,6 +220,10 @@ int treat_b200_align_packed_device(treat_b200_ctx *ctx, const treat_b200_packed 
 int treat_b200_set_tie_order(treat_b200_ctx *ctx, int32_t order);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t treat_b200_launch_count(const treat_b200_ctx *ctx);
+/* tuning: the banded fill in front of the full-matrix DP runs only when a launch has at least `reads` reads to align
+ * (default 16,384; environment TREAT_B200_BAND_MIN; 0 = always).  Below that its fixed latency exceeds what it saves, so
+ * only truncated reads (pure deletions, 16 or more bases short) take a shortcut.  Results do not depend on it. */
+int treat_b200_set_band_min_reads(treat_b200_ctx *ctx, uint32_t reads);
 /* tuning: rows of traceback words kept per lane in shared memory (0 = default 64); any value is
  * exact, reads whose optimal path could leave the band are re-filled into global scratch */
 int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows);
@@ -241,7 +245,8 @@ typedef struct treat_b200_geometry {
 } treat_b200_geometry;
 int treat_b200_align_geometry(treat_b200_ctx *ctx, uint32_t max_n, uint32_t flags, treat_b200_geometry *out);
 /* which kernel finished the reads that needed a DP since the last reset: out3[0] pure deletions (leftmost embedding, no
- * DP), out3[1] banded fill with an exactness certificate, out3[2] left for the full-matrix kernels (bench / tests) */
+ * DP), out3[1] banded fill with an exactness certificate, out3[2] left for the full-matrix kernels (bench / tests).
+ * Synchronises the context's own streams; work queued on a caller's stream must have finished before the call. */
 int treat_b200_dp_stats(treat_b200_ctx *ctx, uint64_t *out3, int32_t reset);
 /* bounds-check flags of the kernels' index computations: always 0 unless the library was built with
  * -DTREAT_B200_CHECKS (*checks_compiled says which); a substitute for compute-sanitizer on pools without it */

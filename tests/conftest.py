@@ -9,6 +9,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# the GPU tests work on small batches: let the banded fill (k_band_*) run at any size so that they exercise it
+# (the library's default only uses it for launches with 16,384 or more reads to align: treat_b200_set_band_min_reads)
+os.environ.setdefault("TREAT_B200_BAND_MIN", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -120,3 +120,41 @@ def test_certificate_covers_rps12_like_reads():
             aln1, aln2, score = O.nw_align(a, b)
             assert int(Fb[m][len(b)]) == score and traceback(Fb, a, b) == ops_of(aln1, aln2)
     assert ok == 12
+
+
+def test_pure_deletion_reads_align_to_their_leftmost_embedding():
+    """The shortcut of band_kernel.cu: when the read's bases are a subsequence of the template's, nwalgo's alignment is the
+    LEFTMOST embedding (every read base on the earliest template base it can take), score 2n - m, for each of the three tie
+    orders -- F[i][k] <= 2k - i with equality iff read[0:k] embeds in template[0:i], so Up is optimal exactly while the
+    prefix still embeds and Left never is.  Checked against the oracle on random and repetitive templates."""
+    rng = random.Random(5)
+
+    def leftmost(a, b):
+        pos, out = 0, []
+        for ch in b:
+            q = a.find(ch, pos)
+            if q < 0:
+                return None
+            out.append(q)
+            pos = q + 1
+        return out
+
+    checked = 0
+    try:
+        for order in ("ULD", "UDL", "LUD"):
+            O.set_tie_order(order)
+            for trial in range(300):
+                m = rng.randrange(5, 80)
+                a = "".join(rng.choice("ACG") for _ in range(m)) if trial % 3 else ("ACG" * 30 + "AACCGG" * 5)[:m]
+                b = "".join(c for c in a if rng.random() > 0.2)
+                if trial % 2:
+                    b = b[rng.randrange(0, len(b) // 2 + 1):len(b) - rng.randrange(0, len(b) // 2 + 1)]
+                if not b:
+                    continue
+                where = set(leftmost(a, b))
+                aln1, aln2, score = O.nw_align(a, b)
+                assert (aln1, aln2, score) == (a, "".join(a[i] if i in where else "-" for i in range(m)), 2 * len(b) - m), (order, a, b)
+                checked += 1
+    finally:
+        O.set_tie_order("ULD")
+    assert checked > 800

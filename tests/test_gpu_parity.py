@@ -1143,6 +1143,30 @@ def test_band_and_pure_deletion_paths(eng, examples, tmp_path):
         eng.set_tie_order("ULD")
 
 
+def test_band_min_reads_threshold(eng, tmp_path):
+    """treat_b200_set_band_min_reads: below the threshold a launch sends its band candidates to the full-matrix kernel (the
+    banded fill's fixed latency does not pay for a handful of reads) and keeps the pure-deletion route for truncated reads
+    only; results are the same either way."""
+    t = synth.long_template(300, 8)
+    om, tm = _oracle_template(t, tmp_path)
+    eng.SetTemplate(tm)
+    seqs, off, rc = synth.reads(t, 6000, seed=synth.SEED_BASE + 61, p_trunc=0.3, p_sub_base=0.005, p_indel_read=0.1)
+    orec, oops, _ = O.align_batch(om, seqs, off, rc, nthreads=8, ops_stride=None)
+    try:
+        got = {}
+        for thr in (0, 1 << 30):
+            eng.set_band_min_reads(thr)
+            eng.dp_stats()
+            grec, gops = eng.align_batch(seqs, off, rc, cabi.WANT_OPS | cabi.NO_SUMMARY)
+            w = min(gops.shape[1], oops.shape[1])
+            assert compare_records(grec, orec) == [] and np.array_equal(gops[:, :w], oops[:, :w]), thr
+            got[thr] = eng.dp_stats()
+        assert got[0][1] > 100 and got[0][0] > 500          # banded fill and pure deletions at any size
+        assert got[1 << 30][1] == 0 and got[1 << 30][0] > 500 and got[1 << 30][2] > got[0][2]  # no band: more reads in the full matrix
+    finally:
+        eng.set_band_min_reads(0)
+
+
 def _collapse_case(eng, t, tmp_path, base_n, total_n, seed, p_trunc=0.0, lower_frac=0.2):
     """A batch with many exact duplicates (sampled with replacement from base_n distinct reads, some of them in lower case)
     against the oracle-side collapse: a dict of upper-cased sequences in order of first occurrence, ReadCounts summed."""

@@ -631,6 +631,10 @@ class Aligner:
         check(lib().treat_b200_debug_flags(self._ctx, C.byref(f), C.byref(c)), self._ctx)
         return f.value, bool(c.value)
 
+    def set_band_min_reads(self, reads: int) -> None:
+        """The banded fill runs only for launches with at least this many reads to align (treat_b200_set_band_min_reads)."""
+        check(lib().treat_b200_set_band_min_reads(self._ctx, int(reads)), self._ctx)
+
     def dp_stats(self, reset: bool = True) -> Tuple[int, int, int]:
         """Reads that needed a DP since the last reset: (pure deletions finished without one, banded fill, full matrix)."""
         out = (C.c_uint64 * 3)()

@@ -109,6 +109,7 @@ SIGNATURES = {
     "treat_b200_align_packed_device": (C.c_int, [_P, C.POINTER(Packed), _P, C.c_uint32, _P, _U8P, C.c_uint32, _P]),
     "treat_b200_launch_count": (C.c_uint64, [_P]),
     "treat_b200_set_band_rows": (C.c_int, [_P, C.c_uint32]),
+    "treat_b200_set_band_min_reads": (C.c_int, [_P, C.c_uint32]),
     "treat_b200_set_tie_order": (C.c_int, [_P, C.c_int32]),
     "treat_b200_align_geometry": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(AlignGeometry)]),
     "treat_b200_debug_flags": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),

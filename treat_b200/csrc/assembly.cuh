@@ -130,10 +130,12 @@ template <typename cnt_t>
 __device__ __forceinline__ void emit_result(const AlignParams &p, const CtaSmem<cnt_t> &cs, int lane, uint64_t r, int n, int alen,
                                             uint32_t status, int score, int edit_stop, int junc_start, int junc_end, int junc_len,
                                             int has_mutation, int alt_editing, int mism, bool indel, uint32_t js_off,
-                                            uint32_t js_len, unsigned long long &ctr, uint32_t raw_len_known = 0xffffffffu)
+                                            uint32_t js_len, unsigned long long &ctr, uint32_t raw_len_known = 0xffffffffu,
+                                            uint32_t read_count_known = 0u)
 {
     const int m = p.t.m;
-    const uint32_t read_count = p.read_count ? p.read_count[r] : 1u;
+    // read_count_known = 0 means "not loaded yet" (a true ReadCount of 0, header "x-0", just takes the load below)
+    const uint32_t read_count = read_count_known ? read_count_known : p.read_count ? p.read_count[r] : 1u;
 
     if (lane == 0) {
         treat_b200_record o;
@@ -410,7 +412,7 @@ template <int G>
 __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<uint8_t> &cs, const uint4 *s_mask, int gl,
                                             unsigned gmask, int lead, uint64_t r, uint32_t rflags, const uint4 &c,
                                             const SameLane &sl, unsigned long long &ctr, uint32_t raw_len_known = 0xffffffffu,
-                                            int mism_known = -1)
+                                            int mism_known = -1, uint32_t read_count_known = 0u)
 {
     // no gap; no mismatch, or exactly one (kFlagOneMismatch: the diagonal still is the unique optimum, score m - 2), or
     // as many as the caller's traceback found on the diagonal (mism_known, k_band_finish)
@@ -485,7 +487,7 @@ __device__ __forceinline__ bool finish_same(const AlignParams &p, const CtaSmem<
         junc_len = 0;
     }
     emit_result<uint8_t>(p, cs, gl, r, n, /*alen*/ m, status, /*score*/ m - 2 * mism, edit_stop, junc_start, junc_end, junc_len,
-                         has_mutation, /*alt_editing*/ 0, mism, /*indel*/ false, js_off, js_len, ctr, raw_len_known);
+                         has_mutation, /*alt_editing*/ 0, mism, /*indel*/ false, js_off, js_len, ctr, raw_len_known, read_count_known);
     if (p.ops && !p.ops_gapped_only) {  // m match columns: an all-zero row
         uint32_t *go = reinterpret_cast<uint32_t *>(p.ops + r * (uint64_t)p.ops_stride);
         for (int wi = gl; wi < (int)(p.ops_stride / 4); wi += G) go[wi] = 0u;

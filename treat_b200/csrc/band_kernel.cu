@@ -33,6 +33,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <mutex>
 
 #include "assembly.cuh"
 #include "device_format.h"
@@ -150,6 +151,7 @@ struct BandParams {
     uint32_t rows;          // rows of one batch's scratch region (largest row index + 1)
     uint32_t ncapb;         // largest n the fill is sized for (m + 15, or the launch's ncap if smaller)
     uint32_t subseq;        // 1: the pure-deletion shortcut is on
+    uint32_t min_reads;     // fewer reads to align than this: no banded fill (k_band_classify)
     unsigned long long *stats;  // [3] reads finished as pure deletions / by the banded fill / left for launch_align (may be null)
     uint32_t sel_words;     // words of one copy of the selector table
     uint32_t pk_stride;     // words per packed read in shared memory (odd)
@@ -174,20 +176,21 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
     const int m = p.t.m;
     uint16_t *s_next = reinterpret_cast<uint16_t *>(smem);  // [3][m + 2]: next position >= i of code c (m: none)
     if (b.subseq) {
-        if (threadIdx.x < 3) {
-            const int c = threadIdx.x;
-            int nx = m;
-            s_next[c * (m + 2) + m] = (uint16_t)m;
-            s_next[c * (m + 2) + m + 1] = (uint16_t)m;
-            for (int i = m - 1; i >= 0; i--) {
-                if ((int)p.t.tb[i] == c) nx = i;
-                s_next[c * (m + 2) + i] = (uint16_t)nx;
-            }
+        uint8_t *s_tb = smem + align16(6u * ((uint32_t)m + 2));  // [m] template codes
+        for (int i = threadIdx.x; i < m; i += blockDim.x) s_tb[i] = p.t.tb[i];
+        __syncthreads();
+        // every entry on its own: scan forward to the next occurrence (three steps on average)
+        for (int x = threadIdx.x; x < 3 * (m + 2); x += blockDim.x) {
+            const int c = x / (m + 2);
+            int i = x - c * (m + 2);
+            while (i < m && (int)s_tb[i] != c) i++;
+            s_next[x] = (uint16_t)min(i, m);
         }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
+    const bool small = total < b.min_reads;
     uint32_t st_pass = 0;
     // whole warps stay in the loop: the three list appends are one atomic per warp and list
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -202,8 +205,14 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
             cat = kCatPass;
             if (n >= 1 && n <= (int)b.ncapb && n <= (int)p.ncap) {
                 src = reinterpret_cast<const uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
-                bool sub = b.subseq && n <= m;
+                // (with n = m an embedding means equal bases: the kernels in front of this one finish those reads; if one does
+                //  arrive here the banded fill takes it)
+                // a short list: the banded fill's fixed latency (one warp walks ~m rows for its 64 reads) is not worth it, the
+                // full-matrix kernel spreads each read over a warp; truncated reads still take the pure-deletion route
+                bool sub = b.subseq && n < m && (!small || m - n >= kBandLo);
                 if (sub) {  // leftmost embedding of the read in the template, if there is one
+                    // an embedding skips exactly m - n template bases: read base k sits at position >= k, at most k + (m - n)
+                    const int slack = m - n;
                     int pos = 0;
                     uint32_t w = 0;
                     for (int k = 0; k < n; k++) {
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
                             break;
                         }
                         const int q = (int)s_next[c * (m + 2) + pos];
-                        if (q >= m) {
+                        if (q > k + slack) {  // includes q = m: no further occurrence
                             sub = false;
                             break;
                         }
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
                     }
                 }
                 if (sub) cat = kCatSubseq;
-                else if (abs(m - n) < kBandLo) cat = kCatBand;
+                else if (abs(m - n) < kBandLo && !small) cat = kCatBand;
             }
         }
         __syncwarp();
@@ -509,28 +518,31 @@ __global__ void __launch_bounds__(kBandFinishWarps * 32, 3) k_band_finish(const 
             me = b.meta[b.first + (x - S)];
         }
     };
-    auto fetch2 = [&](uint32_t x, uint32_t r, uint32_t &nf, uint4 &c) {
+    auto fetch2 = [&](uint32_t x, uint32_t r, uint32_t &nf, uint32_t &rcn, uint4 &c) {
         nf = 0u;
+        rcn = 1u;
         c = make_uint4(0, 0, 0, 0);
         if (x < total) {
             nf = (uint32_t)p.n[r] | ((uint32_t)p.rflags[r] << 16);
+            if (p.read_count) rcn = p.read_count[r];
             if (mine) c = reinterpret_cast<const uint4 *>(p.counts + r * (uint64_t)p.counts_stride)[lane];
         }
     };
-    uint32_t r_cur, me_cur, nf_cur, r_nxt, me_nxt;
+    uint32_t r_cur, me_cur, nf_cur, rc_cur, r_nxt, me_nxt;
     uint4 c_cur;
     fetch1(gw, r_cur, me_cur);
-    fetch2(gw, r_cur, nf_cur, c_cur);
+    fetch2(gw, r_cur, nf_cur, rc_cur, c_cur);
     fetch1(gw + nw, r_nxt, me_nxt);
     for (uint32_t x = gw; x < total; x += nw) {
-        uint32_t r_nn, me_nn, nf_nxt;
+        uint32_t r_nn, me_nn, nf_nxt, rc_nxt;
         uint4 c_nxt;
-        fetch2(x + nw, r_nxt, nf_nxt, c_nxt);
+        fetch2(x + nw, r_nxt, nf_nxt, rc_nxt, c_nxt);
         fetch1(x + 2 * nw, r_nn, me_nn);
         const uint32_t r = r_cur, me = me_cur, rflags = nf_cur >> 16;
         const int n = (int)(nf_cur & 0xffffu);
         const uint4 c = c_cur;
-        r_cur = r_nxt, me_cur = me_nxt, nf_cur = nf_nxt, c_cur = c_nxt;
+        const uint32_t read_count = rc_cur;
+        r_cur = r_nxt, me_cur = me_nxt, nf_cur = nf_nxt, rc_cur = rc_nxt, c_cur = c_nxt;
         r_nxt = r_nn, me_nxt = me_nn;
 
         const bool band = x >= S;
@@ -554,7 +566,7 @@ __global__ void __launch_bounds__(kBandFinishWarps * 32, 3) k_band_finish(const 
         if (diag_only && same_ok) {
             // no gap: the assembly on count bytes in registers (lane l: sites 16 l .. 16 l + 15), (m - score) / 2 mismatches
             const int mism = (m - score) >> 1;
-            if (!finish_same<32>(p, cs, s_bmask, lane, FULL_MASK, 0, r, rflags, c, sl, ctr, 0xffffffffu, mism)) {
+            if (!finish_same<32>(p, cs, s_bmask, lane, FULL_MASK, 0, r, rflags, c, sl, ctr, 0xffffffffu, mism, read_count)) {
                 __syncwarp();
                 reinterpret_cast<uint4 *>(s_cnt)[lane] = c;  // 512 bytes: b_off_cnt holds at least that (band_plan)
                 for (int i = lane; i < ops_words; i += 32) ws.ops2[i] = 0u;
@@ -617,7 +629,7 @@ static bool band_plan(const AlignParams &planned, AlignParams &q, BandParams &b,
     warps_a = (int)std::min<long>(kBandWarps, ((long)max_smem - (long)b.a_cta_bytes) / (long)b.a_warp_bytes);
     warps_b = (int)std::min<long>(kBandFinishWarps, ((long)max_smem - (long)b.b_cta_bytes) / (long)b.b_warp_bytes);
     if (warps_a < 1 || warps_b < 1) return false;
-    if (6u * ((uint32_t)m + 2) > 48u * 1024u) return false;  // k_band_classify's next-occurrence table
+    if (7u * ((uint32_t)m + 2) + 32u > 48u * 1024u) return false;  // k_band_classify's next-occurrence table + template codes
     // reads per round: what the scratch cap holds, in whole batches
     const uint64_t per_batch = (uint64_t)b.rows * 512ull;
     uint64_t batches = std::max<uint64_t>(1, kBandScratchCap / per_batch);
@@ -643,9 +655,8 @@ static BandLayout band_layout(const AlignParams &q, const BandParams &b)
     at += q.N * 4ull;
     L.band_list = at;
     at += q.N * 4ull;
-    at = (at + 15ull) & ~15ull;
-    L.counters = at;
-    L.total = at + 16ull;
+    L.counters = 0;
+    L.total = (at + 15ull) & ~15ull;
     return L;
 }
 
@@ -660,16 +671,40 @@ uint64_t band_scratch_bytes(const AlignParams &planned, int num_sms, int max_sme
     return band_layout(q, b).total;
 }
 
+int occupancy_cached(const void *kern, int threads, size_t smem)
+{
+    struct Entry {
+        const void *kern;
+        int threads;
+        size_t smem;
+        int per_sm;
+    };
+    static std::mutex mu;
+    static Entry cache[64];
+    static int used = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (int i = 0; i < used; i++)
+            if (cache[i].kern == kern && cache[i].threads == threads && cache[i].smem == smem) return cache[i].per_sm;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    if (used < 64) cache[used++] = Entry{kern, threads, smem, per_sm};
+    return per_sm;
+}
+
 template <typename Kern>
 static uint64_t resident_ctas(Kern kern, int threads, size_t smem, int num_sms, int cap_per_sm)
 {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    return (uint64_t)num_sms * std::max(1, std::min(per_sm, cap_per_sm));
+    return (uint64_t)num_sms * std::max(1, std::min(occupancy_cached((const void *)kern, threads, smem), cap_per_sm));
 }
 
-int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, unsigned long long *stats,
-                int num_sms, int max_smem, void *stream)
+int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, uint32_t min_reads,
+                unsigned long long *stats, int num_sms, int max_smem, void *stream)
 {
     AlignParams q;
     BandParams b{};
@@ -681,17 +716,16 @@ int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_cou
     b.list2 = list2;
     b.list2_count = list2_count;
     b.subseq = subseq ? 1u : 0u;
+    b.min_reads = min_reads;
     b.stats = stats;
     b.scratch = reinterpret_cast<uint4 *>(base + L.dir);
     b.meta = reinterpret_cast<uint32_t *>(base + L.meta);
     b.masks = reinterpret_cast<uint32_t *>(base + L.masks);
     b.sub_list = reinterpret_cast<uint32_t *>(base + L.sub_list);
     b.band_list = reinterpret_cast<uint32_t *>(base + L.band_list);
-    b.sub_count = reinterpret_cast<uint32_t *>(base + L.counters);
-    b.band_count = b.sub_count + 1;
-    cudaError_t ce = cudaMemsetAsync(b.sub_count, 0, 16, st);
-    if (ce != cudaSuccess) return (int)ce;
-    const size_t smem_c = subseq ? 6u * ((size_t)q.t.m + 2) : 0;
+    b.sub_count = list2_count + 1;  // the caller's three counters: reads left for launch_align, pure deletions, band reads
+    b.band_count = list2_count + 2;
+    const size_t smem_c = subseq ? align16(6u * ((uint32_t)q.t.m + 2)) + align16((uint32_t)q.t.m) : 0;
     const size_t smem_a = b.a_cta_bytes + (size_t)wa * b.a_warp_bytes, smem_b = b.b_cta_bytes + (size_t)wb * b.b_warp_bytes;
     static const int cap_a = getenv("TREAT_B200_BAND_CTAS") ? atoi(getenv("TREAT_B200_BAND_CTAS")) : TREAT_B200_BAND_MIN_CTAS;
     const uint64_t res_a = resident_ctas(k_band_fill, wa * 32, smem_a, num_sms, cap_a);

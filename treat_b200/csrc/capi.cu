@@ -26,7 +26,7 @@ namespace {
 constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
 constexpr uint64_t kChunkReads = 1u << 16;  // reads per pipelined chunk of treat_b200_align_batch
 constexpr int kSlots = 4;                   // most chunks in flight: H2D, kernels and D2H of different chunks overlap
-constexpr size_t kScalarBytes = 32;         // per-slot device scalars (8 words)
+constexpr size_t kScalarBytes = 64;         // per-slot device scalars (16 words; [6..8]: k_band's three list counters)
 constexpr int kFastaSlots = 6;              // pieces in flight of treat_b200_fasta_stream: two being copied, index, align, deliver
 
 struct DevBuf {
@@ -236,6 +236,7 @@ struct treat_b200_ctx {
     DevBuf d_tpk;  // template bases in the packed-read format (16 codes per word): k_pack marks reads that equal it
     DevBuf d_tmax; // Template.Max(i) (template.go:186) for every edit site: column widths of WriteTo
     uint32_t band_rows = 0;  // 0 = default window
+    uint32_t band_min_reads = 16384;  // k_band's banded fill only pays for itself when a launch has at least this many reads to align
     uint32_t tie = TREAT_B200_TIE_ULD;  // traceback tie order (treat_b200_set_tie_order)
     uint32_t ncap_hint = 0;  // largest n seen with this template: sizes speculative align launches
     uint32_t gap_hint = 0;   // most gapped reads seen in a chunk: sizes the ahead-of-time copy of compacted ops rows
@@ -364,6 +365,7 @@ int treat_b200_create(int device, treat_b200_ctx **out)
         delete ctx;
         return TREAT_B200_ERR_CUDA;
     }
+    if (const char *bm = getenv("TREAT_B200_BAND_MIN")) ctx->band_min_reads = (uint32_t)strtoul(bm, nullptr, 10);
     int e = configure_pack_kernels(ctx->max_smem);
     if (!e) e = configure_align_kernels(ctx->max_smem);
     if (!e) e = configure_text_kernels(ctx->max_smem);
@@ -605,6 +607,13 @@ int treat_b200_set_tie_order(treat_b200_ctx *ctx, int32_t order)
     return TREAT_B200_OK;
 }
 
+int treat_b200_set_band_min_reads(treat_b200_ctx *ctx, uint32_t reads)
+{
+    if (!ctx) return TREAT_B200_ERR_INVALID;
+    ctx->band_min_reads = reads;
+    return TREAT_B200_OK;
+}
+
 int treat_b200_set_band_rows(treat_b200_ctx *ctx, uint32_t rows)
 {
     if (!ctx) return TREAT_B200_ERR_INVALID;
@@ -832,9 +841,10 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     // finished by k_band; what it cannot certify goes to list2 for the full-matrix kernels below
     if (band_bytes) {
         CK(ctx, o.list2->reserve(src->N * 4));
-        if (!o.list2_zeroed) CK(ctx, cudaMemsetAsync(o.list2_count, 0, 4, st));
+        if (!o.list2_zeroed) CK(ctx, cudaMemsetAsync(o.list2_count, 0, 12, st));  // + the pure-deletion and band list counters
         const bool subseq = !(flags & TREAT_B200_DP_EVERY_READ);
-        int eb = launch_band(ap, (uint32_t *)o.list2->p, o.list2_count, scratch.p, subseq, ctx->d_dp_stats, ctx->num_sms, ctx->max_smem, st);
+        int eb = launch_band(ap, (uint32_t *)o.list2->p, o.list2_count, scratch.p, subseq, ctx->band_min_reads, ctx->d_dp_stats, ctx->num_sms,
+                             ctx->max_smem, st);
         if (eb) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_band launch: ") + cudaGetErrorString((cudaError_t)eb));
         ctx->launches++;
         ap.list = (uint32_t *)o.list2->p;

@@ -175,9 +175,12 @@ int launch_pack_finish2(const PackParams &p, const AlignParams &q, int num_sms, 
 int configure_fused_kernels(int max_smem_optin);
 // K2b (band_kernel.cu): of the reads launch_align would get (p.list, or all of them), finishes the pure deletions and the
 // ones a banded fill certifies; the others are appended to list2.  band_scratch_bytes: global scratch it needs (0: n/a).
+// list2_count points at three zeroed words: reads left for launch_align, pure deletions, band reads.
 uint64_t band_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
-int launch_band(const AlignParams &p, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, unsigned long long *stats,
-                int num_sms, int max_smem, void *stream);
+// min_reads: with fewer reads to align than this the banded fill is not worth its fixed latency; band candidates then go
+// to list2 and only reads at least 16 bases shorter than the template are tested for the pure-deletion route.
+int launch_band(const AlignParams &p, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, uint32_t min_reads,
+                unsigned long long *stats, int num_sms, int max_smem, void *stream);
 int configure_band_kernels(int max_smem_optin);
 // K2s: finishes the reads marked kFlagSameBases without a DP and lists the others (p is the plan_align'ed block)
 int launch_same_bases(const AlignParams &p, int num_sms, void *stream);
@@ -219,6 +222,12 @@ int launch_collapse_compact(const uint64_t *off, uint64_t off_bias, uint32_t N, 
 
 int launch_collapse_gather(const uint8_t *seqs, const uint64_t *begin, const uint32_t *len, const uint64_t *dst_off, uint32_t N, uint8_t *dst,
                            int num_sms, void *stream);
+
+#ifdef __CUDACC__
+// resident CTAs per SM of a launch shape, asked of the runtime once per shape: the query costs far more than a launch, and
+// treat_b200_align_batch launches every chunk's kernels through the same few shapes
+int occupancy_cached(const void *kern, int threads, size_t smem);
+#endif
 
 // context internals other translation units need (group.cu)
 int ctx_device(const treat_b200_ctx *ctx);

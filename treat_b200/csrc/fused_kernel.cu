@@ -747,8 +747,7 @@ static int launch_fused(Kern kern, const PackParams &p, const AlignParams &q, ui
                         size_t smem, int num_sms, void *stream)
 {
     uint64_t blocks = (units + units_per_cta - 1) / units_per_cta;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int per_sm = occupancy_cached((const void *)kern, threads, smem);
     const uint64_t cap = (uint64_t)num_sms * per_sm;  // persistent grid: as many CTAs as are resident at once
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return 0;
