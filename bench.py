@@ -676,7 +676,7 @@ def run_ours(args):
         except Exception:
             return None
     def ncu_facts(kernel):
-        # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r01_*_ncu_full.md)
+        # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r02b_*_ncu_full.md)
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
             return {k: v for k, v in tr.items() if not k.startswith("dram_")}
