@@ -139,12 +139,13 @@ struct BandParams {
     uint32_t *list2;        // reads left for launch_align
     uint32_t *list2_count;
     uint32_t *sub_list;     // reads whose bases are a subsequence of the template's (pure deletions)
+    uint32_t *sub_slot;     // ... and the slot of masks that holds each one's embedding
     uint32_t *sub_count;
     uint32_t *band_list;    // reads for the banded fill
     uint32_t *band_count;
     uint4 *scratch;         // [batch of the round][rows][32] direction words
     uint32_t *meta;         // [read of band_list] diagonal-only flag << 8 | score << 16
-    uint32_t *masks;        // [read of sub_list][mwords] template positions the read's bases are matched to
+    uint32_t *masks;        // [read k_band_classify looked at][mwords] template positions the read's bases are matched to
     uint32_t first;         // k_band_fill / k_band_finish: the round covers band_list[first, first + round_reads)
     uint32_t round_reads;   // multiple of 64
     uint32_t mode;          // k_band_finish: 0 = the reads of sub_list, 1 = the band reads of the round
@@ -175,8 +176,9 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
     if (total == 0u) return;
     const int m = p.t.m;
     uint16_t *s_next = reinterpret_cast<uint16_t *>(smem);  // [3][m + 2]: next position >= i of code c (m: none)
+    uint32_t *s_tpk = reinterpret_cast<uint32_t *>(smem + align16(6u * ((uint32_t)m + 2)));  // template, 16 codes per word (+ 2 zero words)
     if (b.subseq) {
-        uint8_t *s_tb = smem + align16(6u * ((uint32_t)m + 2));  // [m] template codes
+        uint8_t *s_tb = reinterpret_cast<uint8_t *>(s_tpk) + align16(4u * (((uint32_t)m + 15) / 16 + 2));  // [m] template codes
         for (int i = threadIdx.x; i < m; i += blockDim.x) s_tb[i] = p.t.tb[i];
         __syncthreads();
         // every entry on its own: scan forward to the next occurrence (three steps on average)
@@ -186,11 +188,20 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
             while (i < m && (int)s_tb[i] != c) i++;
             s_next[x] = (uint16_t)min(i, m);
         }
+        for (int w = threadIdx.x; w < (m + 15) / 16 + 2; w += blockDim.x) {
+            uint32_t v = 0;
+            for (int k = 0; k < 16; k++) {
+                const int i = 16 * w + k;
+                if (i < m) v |= (uint32_t)s_tb[i] << (2 * k);
+            }
+            s_tpk[w] = v;
+        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const bool small = total < b.min_reads;
+    const int rwords = (int)(p.bases_stride / 4);  // words of a packed read's row
     uint32_t st_pass = 0;
     // whole warps stay in the loop: the three list appends are one atomic per warp and list
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -198,26 +209,32 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
         const uint32_t x = x0 + lane;
         uint32_t r = 0;
         int n = 0, cat = kCatNone;
-        const uint32_t *src = nullptr;
         if (x < total) {
             r = p.list ? p.list[x] : x;
             n = (int)p.n[r];
             cat = kCatPass;
             if (n >= 1 && n <= (int)b.ncapb && n <= (int)p.ncap) {
-                src = reinterpret_cast<const uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(p.bases + r * (uint64_t)p.bases_stride);
                 // (with n = m an embedding means equal bases: the kernels in front of this one finish those reads; if one does
                 //  arrive here the banded fill takes it)
                 // a short list: the banded fill's fixed latency (one warp walks ~m rows for its 64 reads) is not worth it, the
                 // full-matrix kernel spreads each read over a warp; truncated reads still take the pure-deletion route
                 bool sub = b.subseq && n < m && (!small || m - n >= kBandLo);
-                if (sub) {  // leftmost embedding of the read in the template, if there is one
-                    // an embedding skips exactly m - n template bases: read base k sits at position >= k, at most k + (m - n)
+                if (sub) {
+                    // Leftmost embedding of the read in the template, if there is one, 16 bases per step: the next read base goes
+                    // to the template's next occurrence of its code (it may sit at most m - n positions late: an embedding skips
+                    // exactly that many template bases), then both sequences are compared word-wise as far as they agree.  The
+                    // matched template positions are written as a bit mask into slot x as the walk goes (a failed walk leaves a
+                    // partial mask nobody reads).
                     const int slack = m - n;
-                    int pos = 0;
-                    uint32_t w = 0;
-                    for (int k = 0; k < n; k++) {
-                        if ((k & 15) == 0) w = src[k >> 4];
-                        const uint32_t c = (w >> (2 * (k & 15))) & 3u;
+                    uint32_t *mk = b.masks + (size_t)x * b.mwords;
+                    int pos = 0, k = 0, wi = 0;
+                    uint32_t cur = 0;
+                    while (k < n) {
+                        const int rw = k >> 4, rs = 2 * (k & 15);
+                        const uint32_t r0 = src[rw], r1 = rw + 1 < rwords ? src[rw + 1] : 0u;
+                        const uint32_t rbits = __funnelshift_r(r0, r1, rs);  // read bases k .. k + 15
+                        const uint32_t c = rbits & 3u;
                         if (c == 3u) {
                             sub = false;
                             break;
@@ -227,7 +244,29 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
                             sub = false;
                             break;
                         }
-                        pos = q + 1;
+                        const int tw = q >> 4;
+                        const uint32_t tbits = __funnelshift_r(s_tpk[tw], s_tpk[tw + 1], 2 * (q & 15));  // template bases q .. q + 15
+                        const uint32_t df = tbits ^ rbits;  // base 0 agrees
+                        int e = df ? (__ffs(df) - 1) >> 1 : 16;
+                        e = min(e, min(n - k, m - q));
+                        while (wi < (q >> 5)) {
+                            mk[wi++] = cur;
+                            cur = 0u;
+                        }
+                        const uint32_t bits = (1u << e) - 1u, sh = (uint32_t)q & 31u;
+                        cur |= bits << sh;
+                        if (sh + (uint32_t)e > 32u) {
+                            mk[wi++] = cur;
+                            cur = bits >> (32u - sh);
+                        }
+                        pos = q + e;
+                        k += e;
+                    }
+                    if (sub) {
+                        while (wi < (int)b.mwords) {
+                            mk[wi++] = cur;
+                            cur = 0u;
+                        }
                     }
                 }
                 if (sub) cat = kCatSubseq;
@@ -252,24 +291,7 @@ __global__ void __launch_bounds__(kClassifyThreads) k_band_classify(const __grid
         if (cat == kCatSubseq) {
             const uint32_t z = b_sub + __popc(m_sub & lt);
             b.sub_list[z] = r;
-            uint32_t *mk = b.masks + (size_t)z * b.mwords;
-            int pos = 0, wi = 0;
-            uint32_t w = 0, cur = 0;
-            for (int k = 0; k < n; k++) {
-                if ((k & 15) == 0) w = src[k >> 4];
-                const uint32_t c = (w >> (2 * (k & 15))) & 3u;
-                const int q = (int)s_next[c * (m + 2) + pos];
-                while (wi < (q >> 5)) {
-                    mk[wi++] = cur;
-                    cur = 0u;
-                }
-                cur |= 1u << (q & 31);
-                pos = q + 1;
-            }
-            while (wi < (int)b.mwords) {
-                mk[wi++] = cur;
-                cur = 0u;
-            }
+            b.sub_slot[z] = x;  // where its mask is
         }
     }
     if (b.stats && st_pass) atomicAdd(&b.stats[2], (unsigned long long)st_pass);
@@ -513,6 +535,7 @@ __global__ void __launch_bounds__(kBandFinishWarps * 32, 3) k_band_finish(const 
         me = 0u;
         if (x < S) {
             r = b.sub_list[x];
+            me = b.sub_slot[x];  // pure deletions carry their mask slot where band reads carry score and marks
         } else if (x < total) {
             r = b.band_list[b.first + (x - S)];
             me = b.meta[b.first + (x - S)];
@@ -578,7 +601,7 @@ __global__ void __launch_bounds__(kBandFinishWarps * 32, 3) k_band_finish(const 
             continue;
         }
         ctr += band_finish_slow(p, b, smem, wb, lane, x - S, band, diag_only, mine, r, n, rflags, score, c,
-                                band ? nullptr : b.masks + (size_t)x * b.mwords);
+                                band ? nullptr : b.masks + (size_t)me * b.mwords);
     }
     if (b.stats && lane == 0) {
         if (st_sub) atomicAdd(&b.stats[0], (unsigned long long)st_sub);
@@ -629,7 +652,7 @@ static bool band_plan(const AlignParams &planned, AlignParams &q, BandParams &b,
     warps_a = (int)std::min<long>(kBandWarps, ((long)max_smem - (long)b.a_cta_bytes) / (long)b.a_warp_bytes);
     warps_b = (int)std::min<long>(kBandFinishWarps, ((long)max_smem - (long)b.b_cta_bytes) / (long)b.b_warp_bytes);
     if (warps_a < 1 || warps_b < 1) return false;
-    if (7u * ((uint32_t)m + 2) + 32u > 48u * 1024u) return false;  // k_band_classify's next-occurrence table + template codes
+    if (8u * ((uint32_t)m + 2) + 64u > 48u * 1024u) return false;  // k_band_classify's next-occurrence table + template codes
     // reads per round: what the scratch cap holds, in whole batches
     const uint64_t per_batch = (uint64_t)b.rows * 512ull;
     uint64_t batches = std::max<uint64_t>(1, kBandScratchCap / per_batch);
@@ -640,7 +663,7 @@ static bool band_plan(const AlignParams &planned, AlignParams &q, BandParams &b,
 
 // global memory of a launch: direction words of a round, meta, the embedding masks, the two lists and their counters
 struct BandLayout {
-    uint64_t dir, meta, masks, sub_list, band_list, counters, total;
+    uint64_t dir, meta, masks, sub_list, sub_slot, band_list, counters, total;
 };
 static BandLayout band_layout(const AlignParams &q, const BandParams &b)
 {
@@ -652,6 +675,8 @@ static BandLayout band_layout(const AlignParams &q, const BandParams &b)
     L.masks = at;
     at += q.N * (uint64_t)b.mwords * 4ull;
     L.sub_list = at;
+    at += q.N * 4ull;
+    L.sub_slot = at;
     at += q.N * 4ull;
     L.band_list = at;
     at += q.N * 4ull;
@@ -722,10 +747,11 @@ int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_cou
     b.meta = reinterpret_cast<uint32_t *>(base + L.meta);
     b.masks = reinterpret_cast<uint32_t *>(base + L.masks);
     b.sub_list = reinterpret_cast<uint32_t *>(base + L.sub_list);
+    b.sub_slot = reinterpret_cast<uint32_t *>(base + L.sub_slot);
     b.band_list = reinterpret_cast<uint32_t *>(base + L.band_list);
     b.sub_count = list2_count + 1;  // the caller's three counters: reads left for launch_align, pure deletions, band reads
     b.band_count = list2_count + 2;
-    const size_t smem_c = subseq ? align16(6u * ((uint32_t)q.t.m + 2)) + align16((uint32_t)q.t.m) : 0;
+    const size_t smem_c = subseq ? align16(6u * ((uint32_t)q.t.m + 2)) + align16(4u * (((uint32_t)q.t.m + 15) / 16 + 2)) + align16((uint32_t)q.t.m) : 0;
     const size_t smem_a = b.a_cta_bytes + (size_t)wa * b.a_warp_bytes, smem_b = b.b_cta_bytes + (size_t)wb * b.b_warp_bytes;
     static const int cap_a = getenv("TREAT_B200_BAND_CTAS") ? atoi(getenv("TREAT_B200_BAND_CTAS")) : TREAT_B200_BAND_MIN_CTAS;
     const uint64_t res_a = resident_ctas(k_band_fill, wa * 32, smem_a, num_sms, cap_a);

@@ -340,19 +340,24 @@ __device__ __forceinline__ void f2_emit(uint32_t &addr, uint32_t v, uint32_t vb,
         : "memory");
 }
 
+// the lane's 32 characters as two interleaved chains (characters 0..15 through addr, 16..31 through addr2): each chain's
+// pointer bump depends on the one before it, two of them in flight halve the time a warp waits on that dependency
 template <int K>
 struct F2Emit {
-    __device__ __forceinline__ static void run(const uint32_t (&w)[8], uint32_t lut32, uint32_t vb, uint32_t mask, uint32_t &addr)
+    __device__ __forceinline__ static void run(const uint32_t (&w)[8], uint32_t lut32, uint32_t vb, uint32_t mask, uint32_t &addr,
+                                               uint32_t &addr2)
     {
-        F2Emit<K - 1>::run(w, lut32, vb, mask, addr);
-        constexpr int k = K - 1;
+        F2Emit<K - 1>::run(w, lut32, vb, mask, addr, addr2);
+        constexpr int k = K - 1, k2 = k + 16;
         const uint32_t v = lds_u8n(__byte_perm(w[k >> 2], lut32, 0x7650 + (k & 3)));  // lut32 | character
+        const uint32_t v2 = lds_u8n(__byte_perm(w[k2 >> 2], lut32, 0x7650 + (k2 & 3)));
         f2_emit<f2_bit(k), (uint32_t)(k << 2)>(addr, v, vb, mask);
+        f2_emit<f2_bit(k2), (uint32_t)(k2 << 2)>(addr2, v2, vb, mask);
     }
 };
 template <>
 struct F2Emit<0> {
-    __device__ __forceinline__ static void run(const uint32_t (&)[8], uint32_t, uint32_t, uint32_t, uint32_t &) {}
+    __device__ __forceinline__ static void run(const uint32_t (&)[8], uint32_t, uint32_t, uint32_t, uint32_t &, uint32_t &) {}
 };
 
 #ifndef TREAT_B200_F2_MIN_CTAS
@@ -506,8 +511,12 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
         const uint32_t n = __shfl_sync(FULL_MASK, incl, G - 1, G);
         // ---- emit: pair = code | (character index in the lane blocks + 1) << 2 ------------------------------------
         uint32_t addr = pair32 + 2u * (incl - nbl);
-        F2Emit<32>::run(w, lut32, vb, mask, addr);
-        TB_CHECK(q, addr == pair32 + 2u * incl && n <= 32u * (uint32_t)G, 8);  // the lane filled exactly its slice of the pair area
+        // characters 0..15 of the lane are the bits 8 b + i with i < 4 of the folded mask
+        uint32_t addr2 = addr + 2u * (uint32_t)__popc(mask & 0x0f0f0f0fu);
+        const uint32_t addr_mid = addr2;
+        F2Emit<16>::run(w, lut32, vb, mask, addr, addr2);
+        TB_CHECK(q, addr == addr_mid && addr2 == pair32 + 2u * incl && n <= 32u * (uint32_t)G, 8);  // the lane filled exactly its slice of the pair area
+        (void)addr_mid;
         // in front of the first base: the read's offset a ("the base before the first one sat at character a - 1");
         // behind the last base: the read's end closes the last run, then consecutive positions (zero counts, zero codes)
         if (gl == 0) sts_u16r(pair32 - 2u, a << 2);
