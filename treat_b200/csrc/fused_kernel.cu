@@ -340,24 +340,27 @@ __device__ __forceinline__ void f2_emit(uint32_t &addr, uint32_t v, uint32_t vb,
         : "memory");
 }
 
-// the lane's 32 characters as two interleaved chains (characters 0..15 through addr, 16..31 through addr2): each chain's
-// pointer bump depends on the one before it, two of them in flight halve the time a warp waits on that dependency
+// the lane's 32 characters as four interleaved chains (characters 0..7, 8..15, 16..23, 24..31, each through its own pointer):
+// a chain's pointer bump depends on the one before it; four of them in flight cut the time a warp waits on that dependency
 template <int K>
 struct F2Emit {
-    __device__ __forceinline__ static void run(const uint32_t (&w)[8], uint32_t lut32, uint32_t vb, uint32_t mask, uint32_t &addr,
-                                               uint32_t &addr2)
+    __device__ __forceinline__ static void run(const uint32_t (&w)[8], uint32_t lut32, uint32_t vb, uint32_t mask, uint32_t (&addr)[4])
     {
-        F2Emit<K - 1>::run(w, lut32, vb, mask, addr, addr2);
-        constexpr int k = K - 1, k2 = k + 16;
-        const uint32_t v = lds_u8n(__byte_perm(w[k >> 2], lut32, 0x7650 + (k & 3)));  // lut32 | character
+        F2Emit<K - 1>::run(w, lut32, vb, mask, addr);
+        constexpr int k0 = K - 1, k1 = k0 + 8, k2 = k0 + 16, k3 = k0 + 24;
+        const uint32_t v0 = lds_u8n(__byte_perm(w[k0 >> 2], lut32, 0x7650 + (k0 & 3)));  // lut32 | character
+        const uint32_t v1 = lds_u8n(__byte_perm(w[k1 >> 2], lut32, 0x7650 + (k1 & 3)));
         const uint32_t v2 = lds_u8n(__byte_perm(w[k2 >> 2], lut32, 0x7650 + (k2 & 3)));
-        f2_emit<f2_bit(k), (uint32_t)(k << 2)>(addr, v, vb, mask);
-        f2_emit<f2_bit(k2), (uint32_t)(k2 << 2)>(addr2, v2, vb, mask);
+        const uint32_t v3 = lds_u8n(__byte_perm(w[k3 >> 2], lut32, 0x7650 + (k3 & 3)));
+        f2_emit<f2_bit(k0), (uint32_t)(k0 << 2)>(addr[0], v0, vb, mask);
+        f2_emit<f2_bit(k1), (uint32_t)(k1 << 2)>(addr[1], v1, vb, mask);
+        f2_emit<f2_bit(k2), (uint32_t)(k2 << 2)>(addr[2], v2, vb, mask);
+        f2_emit<f2_bit(k3), (uint32_t)(k3 << 2)>(addr[3], v3, vb, mask);
     }
 };
 template <>
 struct F2Emit<0> {
-    __device__ __forceinline__ static void run(const uint32_t (&)[8], uint32_t, uint32_t, uint32_t, uint32_t &, uint32_t &) {}
+    __device__ __forceinline__ static void run(const uint32_t (&)[8], uint32_t, uint32_t, uint32_t, uint32_t (&)[4]) {}
 };
 
 #ifndef TREAT_B200_F2_MIN_CTAS
@@ -510,13 +513,17 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
         }
         const uint32_t n = __shfl_sync(FULL_MASK, incl, G - 1, G);
         // ---- emit: pair = code | (character index in the lane blocks + 1) << 2 ------------------------------------
-        uint32_t addr = pair32 + 2u * (incl - nbl);
-        // characters 0..15 of the lane are the bits 8 b + i with i < 4 of the folded mask
-        uint32_t addr2 = addr + 2u * (uint32_t)__popc(mask & 0x0f0f0f0fu);
-        const uint32_t addr_mid = addr2;
-        F2Emit<16>::run(w, lut32, vb, mask, addr, addr2);
-        TB_CHECK(q, addr == addr_mid && addr2 == pair32 + 2u * incl && n <= 32u * (uint32_t)G, 8);  // the lane filled exactly its slice of the pair area
-        (void)addr_mid;
+        // characters 8 c .. 8 c + 7 of the lane are the bits 8 b + i with i in {2 c, 2 c + 1} of the folded mask
+        uint32_t addr[4];
+        addr[0] = pair32 + 2u * (incl - nbl);
+        addr[1] = addr[0] + 2u * (uint32_t)__popc(mask & 0x03030303u);
+        addr[2] = addr[0] + 2u * (uint32_t)__popc(mask & 0x0f0f0f0fu);
+        addr[3] = addr[0] + 2u * (uint32_t)__popc(mask & 0x3f3f3f3fu);
+        const uint32_t a1 = addr[1], a2 = addr[2], a3 = addr[3];
+        F2Emit<8>::run(w, lut32, vb, mask, addr);
+        // every chain filled exactly its slice of the lane's slice of the pair area
+        TB_CHECK(q, addr[0] == a1 && addr[1] == a2 && addr[2] == a3 && addr[3] == pair32 + 2u * incl && n <= 32u * (uint32_t)G, 8);
+        (void)a1, (void)a2, (void)a3;
         // in front of the first base: the read's offset a ("the base before the first one sat at character a - 1");
         // behind the last base: the read's end closes the last run, then consecutive positions (zero counts, zero codes)
         if (gl == 0) sts_u16r(pair32 - 2u, a << 2);
