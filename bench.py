@@ -227,7 +227,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -695,6 +695,18 @@ def run_ours(args):
                 "note": "instruction-issue bound byte work (character classes, compaction, count differences, site compares), "
                         "not DRAM bound: see profiles/; ms_per_launch includes the launch of the multi-pass form for reads "
                         "longer than one pass and one 8-byte read-back"}
+    # the same kernel against the bound that actually limits it: warp instructions issued per second (from the committed ncu
+    # capture's instruction count per read) against 4 issue slots per SM and clock
+    facts = ncu_facts("k_pack_finish2")
+    if facts and facts.get("warp_instructions_per_read") and args.workload == "rps12":
+        props = torch.cuda.get_device_properties(dev)
+        mhz = float(clocks.get("sm_mhz") or 1965.0) if isinstance(clocks, dict) else 1965.0
+        issue_peak = props.multi_processor_count * 4 * mhz * 1e6
+        issued = facts["warp_instructions_per_read"] * N / (fused_ms * 1e-3)
+        roofline["issue"] = {"bound": "warp instructions issued", "achieved": issued / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s",
+                             "frac": issued / issue_peak, "warp_instructions_per_read": facts["warp_instructions_per_read"],
+                             "note": "instruction count per read from profiles/r02_traffic.json (ncu), time measured here; the HBM "
+                                     "fraction above is low because ~390 warp instructions per ~300-byte read, not memory, bound the kernel"}
     # the unfused NewFragment kernel (treat_b200_pack_device, used by the stage calls and for long / wide templates)
     pack_bytes = float(len(seqs) + N * 8 + ((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4))
     roofline_pack = {"bound": "hbm", "kernel": "k_pack16 (stage call treat_b200_pack_device)", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
@@ -991,7 +1003,7 @@ def run_ours(args):
                                    "(treat_b200_comm_reduce_summary_device) once per step" if world > 1 else "none (1 GPU)"},
             "gpu_launches": int(launches), "clocks": clocks, "summary_reads_all_ranks": reduced_reads,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     comm.close()
     if world > 1:
         dist.barrier()
@@ -999,8 +1011,28 @@ def run_ours(args):
     eng.close()
 
 
+_RESULT_FD = None
+
+
+def emit_line(line):
+    """The ONE JSON line of this run, on the process's real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    # stdout carries exactly one JSON line.  Libraries print there too (NCCL writes its "NCCL version ..." line to stdout when
+    # NCCL_DEBUG=VERSION -- NCCL_DEBUG_FILE is only honoured from WARN up --, torch.distributed has its banners): keep the real
+    # stdout for the result and point file descriptor 1 at stderr for everything else.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     import __graft_entry__ as g
     lib = os.path.join(ROOT, "treat_b200", "libtreat_b200.so")
     if not os.path.exists(lib) or int(os.environ.get("LOCAL_RANK", "0")) == 0 and os.environ.get("TREAT_B200_REBUILD"):
