@@ -58,6 +58,9 @@ extern "C" {
                                      that need one is skipped, so their records are NOT written */
 #define TREAT_B200_NO_BAND 0x800u /* do not run the banded / pure-deletion kernel in front of the full-matrix DP (results are the
                                      same; tests compare both ways) */
+#define TREAT_B200_NO_FRONTIER 0x1000u /* do not run k_frontier (reads that are the template edited up to a frontier, finished from
+                                          two string compares on the raw characters) in front of the fused kernels (results are
+                                          the same; tests compare both ways) */
 #define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
                                            under the template that is current now, so reads it marked as equal to the template
                                            skip the DP; without this flag the stage call runs the DP for every read */

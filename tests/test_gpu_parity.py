@@ -187,7 +187,7 @@ def _batch_vs_oracle(eng, t, tmp_path, N, seed, p_trunc=0.0, offset=0, exclude=F
     k = min(N, 3001)
     E = cabi.DP_EVERY_READ
     # (the first two also run k_band -- pure deletions, banded fill -- in front of the full-matrix kernels; NO_BAND does not)
-    for extra in (E, cabi.NO_BAND, E | cabi.NO_BAND, cabi.ONE_READ_PER_WARP, cabi.FULL_TRACEBACK_STORE, E | cabi.ONE_READ_PER_WARP,
+    for extra in (E, cabi.NO_FRONTIER, cabi.NO_BAND, E | cabi.NO_BAND, cabi.ONE_READ_PER_WARP, cabi.FULL_TRACEBACK_STORE, E | cabi.ONE_READ_PER_WARP,
                   E | cabi.FULL_TRACEBACK_STORE, E | cabi.ONE_READ_PER_WARP | cabi.FULL_TRACEBACK_STORE):
         srec, sops = eng.align_batch(seqs[:int(off[k])], off[:k + 1], rc[:k], flags | extra | cabi.NO_SUMMARY)
         assert np.array_equal(srec, grec[:k]) and np.array_equal(sops[:, :gops.shape[1]], gops[:k, :sops.shape[1]])
@@ -1236,3 +1236,64 @@ def test_collapse_exact_duplicates(eng, tmp_path):
     uoff = np.array([0, len(reads[0]), len(reads[0]) + len(reads[2])], dtype=np.uint64)
     orec, oops, _ = O.align_batch(om, useqs, uoff, np.array([3, 1], dtype=np.uint32), ops_stride=gops.shape[1])
     assert compare_records(grec, orec) == [] and np.array_equal(gops, oops)
+
+
+def test_frontier_kernel_edges(eng, tmp_path):
+    """k_frontier (reads finished from two string compares on the raw characters): FE / PE themselves, edit bases added
+    or removed at either end, lower case, foreign characters, junctions of every length, reads at every alignment in
+    memory and longer than one pass -- records, ops and summary equal to the oracle's and to the run without the kernel."""
+    for t in (synth.rps12_template(), synth.long_template()):
+        om, tm = _oracle_template(t, tmp_path)
+        eng.SetTemplate(tm)
+        raws = t.raw_sequences()
+        F, P = raws[0], raws[1]
+        rng = random.Random(20261020)
+        cases = [F, P, F.lower(), "T" + F, "TT" + P, F + "T", P + "TTT", F[1:], P[:-1], "", "T", "TTTT", P[:50] + F[len(F) - 200:],
+                 P[:120] + "TTTTT" + F[len(F) - 60:], F.replace("A", "N", 1), P[:30] + "\x00" + P[31:], P[:40] + " " + F[len(F) - 100:],
+                 "T" * 300 + F, F + "T" * 700, P[:10] + "T" * 260 + F[len(F) - 30:], "t" * 5 + P.lower()] + raws[2:]
+        es = t.edit_site
+        for _ in range(1500):
+            # a read of the model: FE below a frontier, a junction with arbitrary counts, PE above it ...
+            ess = rng.randint(-1, t.m)
+            jl = min(rng.choice([0, 0, 1, 2, 3, 5, 8, 13, 30, 80]), t.m - ess)
+            cnt = [int(es[0, i]) if (t.m - i) <= ess else (rng.randint(0, 9) if (t.m - i) <= ess + jl else int(es[1, i])) for i in range(t.m + 1)]
+            bs = list(t.bases.decode())
+            u = rng.random()
+            if u < 0.08:    # ... sometimes with a substitution, a foreign character, a deleted or an inserted base
+                bs[rng.randrange(t.m)] = rng.choice("ACGN")
+            elif u < 0.12:
+                k = rng.randrange(t.m)
+                del bs[k]
+                cnt[k + 1] += cnt[k]
+                del cnt[k]
+            elif u < 0.16:
+                k = rng.randrange(t.m)
+                bs.insert(k, rng.choice("ACG"))
+                cnt.insert(k, 0)
+            sq = "".join("T" * c + b for c, b in zip(cnt, bs)) + "T" * cnt[-1]
+            if rng.random() < 0.1:
+                sq = sq.lower()
+            cases.append(sq)
+        raw = "".join(cases).encode("latin-1")
+        off = np.zeros(len(cases) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(c) for c in cases])
+        seqs = np.frombuffer(raw, dtype=np.uint8).copy()
+        rc = np.arange(1, len(cases) + 1, dtype=np.uint32)
+        flags = cabi.WANT_OPS
+        eng.reset_summary()
+        grec, gops = eng.align_batch(seqs, off, rc, flags)
+        gsum = eng.summary()
+        orec, oops, _ = O.align_batch(om, seqs, off, rc, nthreads=8, ops_stride=gops.shape[1])
+        assert compare_records(grec, orec) == []
+        assert np.array_equal(gops, oops)
+        assert np.array_equal(gsum, summary_from_records(orec, t.m, 0, om.EditStop))
+        eng.reset_summary()
+        nrec, nops = eng.align_batch(seqs, off, rc, flags | cabi.NO_FRONTIER)
+        assert np.array_equal(nrec, grec) and np.array_equal(nops, gops) and np.array_equal(eng.summary(), gsum)
+        # every start alignment of the first read inside its 64-byte block
+        for shift in (1, 3, 15, 16, 17, 31, 33, 47, 63):
+            s2 = np.concatenate([np.full(shift, ord("G"), dtype=np.uint8), seqs])
+            o2 = np.concatenate([[0], off + shift]).astype(np.uint64)
+            r2 = np.concatenate([[7], rc]).astype(np.uint32)
+            srec, sops = eng.align_batch(s2, o2, r2, flags | cabi.NO_SUMMARY)
+            assert np.array_equal(srec[1:], grec) and np.array_equal(sops[1:, :gops.shape[1]], gops[:, :sops.shape[1]])

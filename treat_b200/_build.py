@@ -22,7 +22,7 @@ NVCC_FLAGS = [
 ]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra"]
 
-CUDA_SOURCES = ["pack_kernel.cu", "align_kernel.cu", "fused_kernel.cu", "band_kernel.cu", "fasta_kernel.cu", "text_kernel.cu", "collapse_kernel.cu", "capi.cu", "group.cu"]
+CUDA_SOURCES = ["pack_kernel.cu", "align_kernel.cu", "fused_kernel.cu", "frontier_kernel.cu", "band_kernel.cu", "fasta_kernel.cu", "text_kernel.cu", "collapse_kernel.cu", "capi.cu", "group.cu"]
 CXX_SOURCES = ["host/treat_host.cpp", "host/capi_host.cpp"]
 HEADERS = ["device_format.h", "ptx_helpers.cuh", "assembly.cuh", "host/treat_host.hpp", "../../include/treat_b200.h"]
 

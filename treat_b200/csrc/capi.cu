@@ -137,6 +137,7 @@ struct Slot {
     DevBuf seqs, off, rc, n, flags, bases, counts, raw_len, rec, ops, summary;
     DevBuf list;     // reads that need the DP (written by k_same_bases / k_pack_finish*, read by the align kernels)
     DevBuf long_list;  // reads too long for one pass of k_pack_finish2
+    DevBuf rest_list;  // reads k_frontier leaves for k_pack_finish2
     DevBuf list2;      // reads k_band leaves for the full-matrix kernels
     DevBuf ops_idx;  // OPS_GAPPED_ONLY: read index of every compacted ops row
     // OPS_GAPPED_ONLY: pinned landing buffers of the compacted rows and their read indices
@@ -168,7 +169,7 @@ struct Slot {
     uint32_t max_len = 0, dev_stride = 0;
     void release()
     {
-        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &long_list, &list2, &ops_idx, &text,
+        for (DevBuf *b : {&seqs, &off, &rc, &n, &flags, &bases, &counts, &raw_len, &rec, &ops, &summary, &scratch, &list, &long_list, &rest_list, &list2, &ops_idx, &text,
                           &text_off, &tlen, &gtot, &tsums, &names, &name_off})
             b->release();
         if (tland) cudaFreeHost(tland);
@@ -234,6 +235,8 @@ struct treat_b200_ctx {
     TemplateDev td{};
     DevBuf d_tb, d_tb_wide, d_tc8, d_tc32, d_alt, d_lut;
     DevBuf d_tpk;  // template bases in the packed-read format (16 codes per word): k_pack marks reads that equal it
+    DevBuf d_frontier;              // k_frontier: shared-memory image of the template (shifted copies of the FE / PE strings, tables)
+    FrontierGeom fr_geom{};         //   its layout; image_bytes == 0: the kernel does not apply to this template
     DevBuf d_tmax; // Template.Max(i) (template.go:186) for every edit site: column widths of WriteTo
     uint32_t band_rows = 0;  // 0 = default window
     uint32_t band_min_reads = 16384;  // k_band's banded fill only pays for itself when a launch has at least this many reads to align
@@ -370,6 +373,7 @@ int treat_b200_create(int device, treat_b200_ctx **out)
     if (!e) e = configure_align_kernels(ctx->max_smem);
     if (!e) e = configure_text_kernels(ctx->max_smem);
     if (!e) e = configure_fused_kernels(ctx->max_smem);
+    if (!e) e = configure_frontier_kernels(ctx->max_smem);
     if (!e) e = configure_band_kernels(ctx->max_smem);
     if (e) {
         cudaStreamDestroy(ctx->stream);
@@ -385,7 +389,7 @@ void treat_b200_destroy(treat_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->d_tpk, &ctx->d_tmax}) b->release();
+    for (DevBuf *b : {&ctx->d_tb, &ctx->d_tb_wide, &ctx->d_tc8, &ctx->d_tc32, &ctx->d_alt, &ctx->d_lut, &ctx->d_tpk, &ctx->d_tmax, &ctx->d_frontier}) b->release();
     if (ctx->d_summary) cudaFree(ctx->d_summary);
     if (ctx->d_heat) cudaFree(ctx->d_heat);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
@@ -499,6 +503,20 @@ int treat_b200_set_template(treat_b200_ctx *ctx, const uint8_t *bases, int32_t m
             for (int i = 0; i < m; i++) tpk[i >> 4] |= (uint32_t)tb[i] << (2 * (i & 15));
         CK(ctx, ctx->d_tpk.reserve(tpk.size() * 4));
         CK(ctx, cudaMemcpy(ctx->d_tpk.p, tpk.data(), tpk.size() * 4, cudaMemcpyHostToDevice));
+    }
+    {
+        // k_frontier: the FE / PE rows re-inflated to raw strings, as a shared-memory image
+        std::vector<uint8_t> image;
+        FrontierGeom fg{};
+        std::vector<uint8_t> up(bases, bases + m);
+        for (uint8_t &c : up)
+            if (c >= 'a' && c <= 'z') c -= 32;
+        ctx->fr_geom = FrontierGeom{};
+        if (!wide && build_frontier_image(up.data(), m, edit_site, edit_site + len, alt_start, n_alt, edit_base, image, fg)) {
+            CK(ctx, ctx->d_frontier.reserve(image.size()));
+            CK(ctx, cudaMemcpy(ctx->d_frontier.p, image.data(), image.size(), cudaMemcpyHostToDevice));
+            ctx->fr_geom = fg;
+        }
     }
     {
         std::vector<uint32_t> tmax((size_t)len_pad, 0u);
@@ -739,6 +757,8 @@ struct AlignOpts {
     bool listed = false;              // the list is already filled (k_pack_finish ran): no k_same_bases launch
     DevBuf *long_list = nullptr;      // k_pack_finish2: reads too long for one of its passes (taken up by k_pack_finish)
     uint32_t *long_count = nullptr;   //   (must be zero on entry)
+    DevBuf *rest_list = nullptr;      // k_frontier: reads it leaves for k_pack_finish2
+    uint32_t *rest_count = nullptr;   //   (must be zero on entry)
     DevBuf *list2 = nullptr;          // with list2_count: k_band runs first (pure deletions, banded fill) and leaves these reads
     uint32_t *list2_count = nullptr;  //   for the full-matrix kernels
     bool list2_zeroed = false;        //   the caller cleared the counter on this stream already
@@ -937,6 +957,25 @@ static int do_pack_finish(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint
         pp.long_count = o.long_count;
     }
     int e;
+    // K0: reads that are the template edited up to a frontier are finished from their raw characters; the fused kernels
+    // below then see only what it lists
+    static const bool no_frontier = getenv("TREAT_B200_NO_FRONTIER") != nullptr;
+    if (!no_frontier && !(flags & TREAT_B200_NO_FRONTIER) && !no_fuse2 && o.rest_list && o.rest_count && ctx->fr_geom.image_bytes && pack_finish2_applies(pp, ap)) {
+        FrontierParams fp{};
+        fp.image = (const uint8_t *)ctx->d_frontier.p;
+        fp.g = ctx->fr_geom;
+        CK(ctx, o.rest_list->reserve(dst->N * 4));
+        fp.rest = (uint32_t *)o.rest_list->p;
+        fp.rest_count = o.rest_count;
+        if (frontier_applies(pp, ap, fp)) {
+            e = launch_frontier(pp, ap, fp, ctx->num_sms, ctx->max_smem, st);
+            if (e == -1000) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "pack: template too large for k_frontier's shared memory");
+            if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_frontier launch: ") + cudaGetErrorString((cudaError_t)e));
+            ctx->launches++;
+            pp.sel = fp.rest;
+            pp.sel_count = fp.rest_count;
+        }
+    }
     if (!no_fuse2 && pack_finish2_applies(pp, ap)) {
         // one pass per read, two reads per warp for templates of up to 255 bases ...
         e = launch_pack_finish2(pp, ap, ctx->num_sms, ctx->max_smem, st);
@@ -1026,6 +1065,8 @@ static int run_chunk(treat_b200_ctx *ctx, Slot &s, const uint8_t *d_seqs, const 
         o.summary = slot_sum;
         o.long_list = &s.long_list;
         o.long_count = s.scalars + 5;
+        o.rest_list = &s.rest_list;
+        o.rest_count = s.scalars + 9;
         rc = do_pack_finish(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded, d_rc, flags, d_rec, d_ops, ops_stride, o);
     } else {
         rc = do_pack(ctx, d_seqs, d_off, off_bias, &pk, s.scalars, st, span, padded);

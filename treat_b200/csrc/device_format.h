@@ -1,6 +1,7 @@
 // device_format.h -- parameter blocks shared by the kernels (*_kernel.cu) and the C ABI (capi.cu).
 #pragma once
 #include <cstdint>
+#include <vector>
 
 #include "../../include/treat_b200.h"
 
@@ -173,6 +174,28 @@ int launch_pack_finish(const PackParams &p, const AlignParams &q, int num_sms, i
 bool pack_finish2_applies(const PackParams &p, const AlignParams &q);
 int launch_pack_finish2(const PackParams &p, const AlignParams &q, int num_sms, int max_smem_optin, void *stream);
 int configure_fused_kernels(int max_smem_optin);
+// K0 (frontier_kernel.cu): reads that are the template edited up to a frontier -- a prefix of the pre-edited string, a
+// junction, a suffix of the fully edited string -- are finished from two string compares on the raw characters; all other
+// reads are appended to f.rest for the fused kernels above (which then run with pack.sel = f.rest).
+struct FrontierGeom {
+    uint32_t image_bytes;  // shared-memory image of the template (multiple of 16)
+    uint32_t off_keep, off_p, off_f, off_pcum, off_fsuf, off_ppos, off_ftail, off_bases, off_alt;
+    uint32_t sp, sf;       // bytes per shifted copy of P / F
+    uint32_t Lp, Lf, tm;   // raw lengths of the pre-edited / fully edited strings, template bases
+    uint32_t mid_cap;      // longest junction (raw characters) that cannot hold a saturating edit-base run
+};
+struct FrontierParams {
+    const uint8_t *image;
+    FrontierGeom g;
+    uint32_t *rest;        // reads left for the general path ...
+    uint32_t *rest_count;  // ... and their number (zero on entry)
+};
+// host: builds the image for a template (false: the kernel does not apply to it)
+bool build_frontier_image(const uint8_t *bases, int m, const uint32_t *fe, const uint32_t *pe, const int32_t *alt_start, int n_alt,
+                          uint8_t edit_base, std::vector<uint8_t> &image, FrontierGeom &g);
+bool frontier_applies(const PackParams &p, const AlignParams &q, const FrontierParams &f);
+int launch_frontier(const PackParams &p, const AlignParams &q, const FrontierParams &f, int num_sms, int max_smem_optin, void *stream);
+int configure_frontier_kernels(int max_smem_optin);
 // K2b (band_kernel.cu): of the reads launch_align would get (p.list, or all of them), finishes the pure deletions and the
 // ones a banded fill certifies; the others are appended to list2.  band_scratch_bytes: global scratch it needs (0: n/a).
 // list2_count points at three zeroed words: reads left for launch_align, pure deletions, band reads.

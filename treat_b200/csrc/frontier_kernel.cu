@@ -1,0 +1,509 @@
+// frontier_kernel.cu -- K0: the reads that are "the template, edited up to a frontier" are finished straight from their
+// raw characters; no base is stripped, no edit-site count is formed.
+//
+// With R the upper-cased raw read and F / P the fully edited / pre-edited template re-inflated to raw strings (the rows
+// Template.EditSite[0] / [1] of template.go:41-49 around Template.Bases), NewFragment + NewAlignment (fragment.go:91-121,
+// align.go:95-279) of a read whose stripped bases equal the template's reduce to two string compares:
+//   * findJSS (align.go:110-120): the highest site whose count differs from FE is m - bs, bs = bases inside the longest
+//     common SUFFIX of R and F; T[0] is all ones iff R == F;
+//   * findJES (align.go:95-108): the lowest site whose count differs from PE is bp, bp = bases inside the longest common
+//     PREFIX of R and P; T[1] is all ones iff R == P;
+//   * the bases ARE the template's iff the characters between that prefix and that suffix, edit bases dropped, are
+//     Bases[bp .. m - bs) (and, when prefix and suffix overlap, iff bp + the bases behind the prefix add up to m);
+//   * JuncSeq (align.go:247-258) is the window of R from just behind base bp - 1 to just behind base m - bs: both offsets
+//     are table look-ups on P and F.
+// tests/test_frontier_model.py states the same in Python and checks it against the CPU restatement of the Go path.
+//
+// One group of G lanes per read, 32 / G reads per warp; lane gl holds the 16-byte blocks gl, G + gl, 2 G + gl, 3 G + gl of
+// the read's 64 G-byte window (so every load, of the read and of the tables, is a run of consecutive 16-byte blocks across
+// the group: coalesced in HBM, conflict-free in shared memory).  Per block the four words are XORed against P (aligned to
+// the read's start) and F (aligned to its end) -- 16 shifted copies of each in shared memory make every operand an
+// aligned LDS.128 --, masked to the read's extent with case folding ((w ^ P) & 0xDF.. per byte is exact for letters), and
+// the first / last non-zero byte is kept with selects; one REDUX per side gives the prefix length t and the suffix
+// length s.  The characters in between (the junction: ~30 on RPS12) are checked by the whole warp, one read after the
+// other, 32 characters per round from a staged copy of the blocks, against the template's bases (rank = ballot prefix
+// count).
+// Everything else -- a substitution, an indel, a foreign character, a junction start on an alternative template's region
+// (align.go:186-205), a read whose last run differs from FE's (findJSS may answer -1), a read longer than a pass -- is
+// appended to f.rest and taken by k_pack_finish2 / k_pack_finish exactly as before.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "assembly.cuh"
+#include "device_format.h"
+#include "ptx_helpers.cuh"
+
+namespace treat_b200 {
+
+namespace {
+constexpr uint32_t kFrNB = 64;      // raw characters per lane
+constexpr uint32_t kFrGuardP = 64;  // zero bytes in front of P inside a shifted copy (a block of P starts up to 48 bytes early)
+constexpr uint32_t kFrGuardF = 16;  // zero block in front of F (block offsets are clamped into the copy)
+#ifndef TREAT_B200_FR_WARPS
+#define TREAT_B200_FR_WARPS 8
+#endif
+#ifndef TREAT_B200_FR_MIN_CTAS
+#define TREAT_B200_FR_MIN_CTAS 3
+#endif
+constexpr int kFrWarps = TREAT_B200_FR_WARPS;
+__host__ __device__ constexpr uint32_t fr_copy_bytes(uint32_t guard, uint32_t len) { return guard + ((15u + len + 15u) & ~15u) + 16u; }
+}  // namespace
+
+// ---- host: the shared-memory image of a template (built once per treat_b200_set_template) ----------------------
+// bases: m upper-case letters; fe / pe: m + 1 counts each; alt_start: n_alt site numbers.  Returns false when the kernel
+// does not apply (characters that are not upper-case letters, strings too long for a pass, counts near saturation).
+bool build_frontier_image(const uint8_t *bases, int m, const uint32_t *fe, const uint32_t *pe, const int32_t *alt_start, int n_alt,
+                          uint8_t edit_base, std::vector<uint8_t> &image, FrontierGeom &g)
+{
+    g = FrontierGeom{};
+    if (m < 1 || m > 511 || edit_base < 'A' || edit_base > 'Z') return false;
+    uint32_t max_fe = 0, max_pe = 0;
+    std::vector<uint8_t> F, P;
+    std::vector<uint16_t> ppos(m + 1, 0), ftail(m + 1, 0);
+    for (int i = 0; i <= m; i++) {
+        max_fe = std::max(max_fe, fe[i]);
+        max_pe = std::max(max_pe, pe[i]);
+        if (fe[i] > 254u || pe[i] > 254u) return false;
+        F.insert(F.end(), fe[i], edit_base);
+        P.insert(P.end(), pe[i], edit_base);
+        if (i < m) {
+            if (bases[i] < 'A' || bases[i] > 'Z' || bases[i] == edit_base) return false;
+            F.push_back(bases[i]);
+            P.push_back(bases[i]);
+            ppos[i + 1] = (uint16_t)P.size();  // raw offset just behind base i of P
+        }
+    }
+    if (max_fe + max_pe > 200u) return false;  // a run in the read = a piece of a P run + the junction + a piece of an F run: stays below 255
+    const uint32_t Lf = (uint32_t)F.size(), Lp = (uint32_t)P.size();
+    if (std::max(Lf, Lp) + 16u > 32u * kFrNB - (kFrNB - 1u)) return false;
+    {
+        int k = 0;
+        for (int i = (int)Lf - 1; i >= 0; i--)
+            if (F[i] != edit_base) ftail[++k] = (uint16_t)(Lf - 1 - i);  // characters of F behind base m - k
+    }
+    g.Lf = Lf, g.Lp = Lp, g.tm = (uint32_t)m;
+    g.mid_cap = 254u - max_fe - max_pe;
+    g.sp = fr_copy_bytes(kFrGuardP, Lp), g.sf = fr_copy_bytes(kFrGuardF, Lf);
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) {
+        const uint32_t at = o;
+        o += (bytes + 15u) & ~15u;
+        return at;
+    };
+    g.off_keep = take(17 * 16);  // row c: the c lowest bytes 0xDF
+    g.off_p = take(16 * g.sp);
+    g.off_f = take(16 * g.sf);
+    g.off_pcum = take(2 * (Lp + 1));
+    g.off_fsuf = take(2 * (Lf + 1));
+    g.off_ppos = take(2 * (m + 1));
+    g.off_ftail = take(2 * (m + 1));
+    g.off_bases = take((uint32_t)m + 48);  // zeros behind the bases: a rank past the template never matches
+    g.off_alt = take((uint32_t)m + 1);
+    g.image_bytes = o;
+    image.assign(o, 0);
+    for (uint32_t c = 0; c <= 16; c++) memset(&image[g.off_keep + c * 16], 0xdf, c);
+    for (uint32_t c = 0; c < 16; c++) {
+        memcpy(&image[g.off_p + c * g.sp + kFrGuardP + c], P.data(), Lp);
+        memcpy(&image[g.off_f + c * g.sf + kFrGuardF + c], F.data(), Lf);
+    }
+    uint16_t *pcum = reinterpret_cast<uint16_t *>(&image[g.off_pcum]), *fsuf = reinterpret_cast<uint16_t *>(&image[g.off_fsuf]);
+    for (uint32_t i = 0; i < Lp; i++) pcum[i + 1] = (uint16_t)(pcum[i] + (P[i] != edit_base));
+    for (uint32_t i = 0; i < Lf; i++) fsuf[i + 1] = (uint16_t)(fsuf[i] + (F[Lf - 1 - i] != edit_base));
+    memcpy(&image[g.off_ppos], ppos.data(), 2 * (m + 1));
+    memcpy(&image[g.off_ftail], ftail.data(), 2 * (m + 1));
+    memcpy(&image[g.off_bases], bases, m);
+    for (int k = 0; k < n_alt; k++)
+        if (alt_start[k] >= 0 && alt_start[k] <= m) image[g.off_alt + alt_start[k]] = 1;
+    return true;
+}
+
+namespace {
+
+__device__ __forceinline__ uint32_t sel(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
+
+// first / last non-zero byte of sixteen words handed over four at a time (block j = words 4 j .. 4 j + 3), branch-free
+struct FirstNz {
+    uint32_t y[4] = {0u, 0u, 0u, 0u}, yo = 0u, jb = 0u;
+    __device__ __forceinline__ void block(uint32_t j, const uint32_t (&x)[4])
+    {
+        const uint32_t o = x[0] | x[1] | x[2] | x[3];
+        const bool take = yo == 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) y[k] = sel(take, x[k], y[k]);
+        jb = sel(take, j, jb);
+        yo = sel(take, o, yo);
+    }
+    // byte index inside the kept block (valid when yo != 0)
+    __device__ __forceinline__ uint32_t byte_in_block() const
+    {
+        const bool a = y[0] != 0u, b = y[1] != 0u, c = y[2] != 0u;
+        const uint32_t k = a ? 0u : b ? 4u : c ? 8u : 12u;
+        const uint32_t w = a ? y[0] : b ? y[1] : c ? y[2] : y[3];
+        return k + ((uint32_t)(__ffs((int)w) - 1) >> 3);
+    }
+};
+struct LastNz {
+    uint32_t y[4] = {0u, 0u, 0u, 0u}, yo = 0u, jb = 0u;
+    __device__ __forceinline__ void block(uint32_t j, const uint32_t (&x)[4])
+    {
+        const uint32_t o = x[0] | x[1] | x[2] | x[3];
+        const bool take = o != 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) y[k] = sel(take, x[k], y[k]);
+        jb = sel(take, j, jb);
+        yo = sel(take, o, yo);
+    }
+    __device__ __forceinline__ uint32_t byte_in_block() const
+    {
+        const bool a = y[3] != 0u, b = y[2] != 0u, c = y[1] != 0u;
+        const uint32_t k = a ? 12u : b ? 8u : c ? 4u : 0u;
+        const uint32_t w = a ? y[3] : b ? y[2] : c ? y[1] : y[0];
+        return k + ((uint32_t)(31 - __clz((int)w)) >> 3);
+    }
+};
+
+}  // namespace
+
+template <int G, bool SPAN>
+__global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_frontier(const __grid_constant__ PackParams p, const __grid_constant__ AlignParams q,
+                                                                                    const __grid_constant__ FrontierParams f)
+{
+    constexpr int RPW = 32 / G;
+    constexpr uint32_t WIN = kFrNB * G;   // bytes of a read's window (64 G, 64-byte aligned in memory)
+    constexpr uint32_t JS = 16u * G;      // a lane's blocks are JS bytes apart
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane & (G - 1), grp = lane / G, lead = grp * G;
+    const uint32_t lt = (1u << lane) - 1u;
+    const FrontierGeom &g = f.g;
+    // ---- the template's image, this CTA's histograms, one 2 KB staging area per warp ---------------------------------
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(f.image);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (uint32_t i = threadIdx.x; i < g.image_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    const uint32_t sum_len = q.summary ? TREAT_B200_SUMMARY_HEADER + 3u * q.bins : 0u;
+    const uint32_t sum_bytes = align16(8u * sum_len);
+    uint32_t *sum_lo = reinterpret_cast<uint32_t *>(smem + g.image_bytes), *sum_hi = sum_lo + sum_len;
+    for (uint32_t i = threadIdx.x; i < 2 * sum_len; i += blockDim.x) sum_lo[i] = 0u;
+    __syncthreads();
+    const uint32_t s32 = smem_u32(smem);
+    const uint32_t stage32 = s32 + g.image_bytes + sum_bytes + (uint32_t)warp * 2048u;
+    const uint32_t keep32 = s32 + g.off_keep, pc32 = s32 + g.off_p, fc32 = s32 + g.off_f;
+    const uint16_t *s_pcum = reinterpret_cast<const uint16_t *>(smem + g.off_pcum), *s_fsuf = reinterpret_cast<const uint16_t *>(smem + g.off_fsuf);
+    const uint16_t *s_ppos = reinterpret_cast<const uint16_t *>(smem + g.off_ppos), *s_ftail = reinterpret_cast<const uint16_t *>(smem + g.off_ftail);
+    const uint32_t bases32 = s32 + g.off_bases;
+    const uint8_t *s_alt = smem + g.off_alt;
+    const uint32_t Lp = g.Lp, Lf = g.Lf, tm = g.tm;
+    const uint32_t eb = p.edit_base;
+    const int K = q.t.K;
+    const int p_top = (int)g.sp - 16, f_top = (int)g.sf - 16;  // the zero block that ends a copy
+
+    const uint32_t base_lo = (uint32_t)reinterpret_cast<uintptr_t>(p.seqs);
+    const uint32_t N32 = (uint32_t)p.N;
+    const int64_t lo = SPAN ? 0 : p.N ? (int64_t)(p.off[0] - p.off_bias) : 0;
+    const int64_t hi = SPAN ? (int64_t)p.span : p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
+    auto where = [&](uint32_t r, uint64_t &x0, uint64_t &x1) {
+        x0 = x1 = SPAN ? 0ull : p.off_bias;
+        if (r >= N32) return;
+        if (SPAN) {
+            x0 = p.begin[r];
+            x1 = p.len[r];
+        } else {
+            x0 = p.off[r];
+            x1 = p.off[r + 1];
+        }
+    };
+    auto resolve = [&](uint64_t x0, uint64_t x1, uint64_t &b, uint32_t &L) {
+        b = SPAN ? x0 : x0 - p.off_bias;
+        L = SPAN ? (uint32_t)x1 : (uint32_t)(x1 - x0);
+    };
+    // this lane's four 16-byte blocks of a read's window; zero where the block lies behind the read or the read is too
+    // long for one pass.  A window whose used blocks stick out of [lo, hi) -- at the ends of a caller's buffer -- is read
+    // byte by byte.
+    auto load_blocks = [&](uint64_t b, uint32_t L, uint4 (&blk)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) blk[j] = make_uint4(0, 0, 0, 0);
+        const uint32_t a = (base_lo + (uint32_t)b) & (kFrNB - 1u);
+        const uint32_t nb16 = (a + L + 15u) >> 4;  // 16-byte blocks the read touches
+        if (L == 0u || a + L > WIN) return;
+        const int64_t w0 = (int64_t)b - a;  // the window starts here
+        if (w0 >= lo && w0 + (int64_t)(16u * nb16) <= hi) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.seqs + w0) + gl;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((uint32_t)(G * j + gl) < nb16) blk[j] = src[G * j];
+            return;
+        }
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+            for (int c = 0; c < 16; c++) {
+                const int64_t y = w0 + (int64_t)(JS * j + 16u * gl) + c;
+                const uint32_t v = (y >= lo && y < hi) ? (uint32_t)p.seqs[y] << (8 * (c & 3)) : 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (i == (c >> 2)) w[i] |= v;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++)
+                if (jj == j) blk[jj] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    };
+
+    unsigned long long accA = 0;  // sum of ReadCount over the reads finished here (group-uniform)
+    uint32_t accN = 0;            // their number
+    const uint32_t units = (uint32_t)((p.N + RPW - 1) / RPW);
+    const uint32_t gw = blockIdx.x * kFrWarps + warp, nw = gridDim.x * kFrWarps;
+    uint64_t b_cur = 0, b_nxt = 0, x0_nxt = 0, x1_nxt = 0;
+    uint32_t L_cur = 0, L_nxt = 0;
+    uint4 blk[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) blk[j] = make_uint4(0, 0, 0, 0);
+    if (gw < units) {
+        uint64_t x0, x1;
+        where(gw * RPW + grp, x0, x1);
+        resolve(x0, x1, b_cur, L_cur);
+        load_blocks(b_cur, L_cur, blk);
+    }
+    where((gw + nw) * RPW + grp, x0_nxt, x1_nxt);
+    for (uint32_t u = gw; u < units; u += nw) {
+        uint4 nxt[4];
+        resolve(x0_nxt, x1_nxt, b_nxt, L_nxt);
+        load_blocks(b_nxt, L_nxt, nxt);
+        where((u + 2 * nw) * RPW + grp, x0_nxt, x1_nxt);
+
+        const uint32_t r = u * RPW + grp;
+        const uint32_t a = (base_lo + (uint32_t)b_cur) & (kFrNB - 1u);  // the read starts at byte a of its window
+        const bool in_batch = r < N32;
+        const uint32_t L = (in_batch && a + L_cur <= WIN) ? L_cur : 0u;
+        const uint32_t read_count = (in_batch && q.read_count) ? q.read_count[r] : 1u;
+
+        // ---- R against P from the read's start and against F from its end ---------------------------------------
+        // window byte X is P[X - a]; P[i] sits at byte kFrGuardP + c + i of copy c = a & 15
+        const int po = (int)(kFrGuardP + 16u * (uint32_t)gl) - (int)(a & ~15u);  // >= 16
+        const uint32_t pa32 = pc32 + (a & 15u) * g.sp;
+        // window byte X is F[X - d], d = a + L - Lf; F[i] sits at byte kFrGuardF + c + i of copy c = d & 15
+        const int d = (int)(a + L) - (int)Lf;
+        const int fo = (int)(kFrGuardF + 16u * (uint32_t)gl) - (d & ~15);
+        const uint32_t fa32 = fc32 + ((uint32_t)d & 15u) * g.sf;
+        const int e_hi = (int)(a + L) - 16 * gl, e_lo = (int)a - 16 * gl;  // the read covers bytes [e_lo, e_hi) counted from this lane's first block
+        FirstNz fp;
+        LastNz lf;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sts_v4(stage32 + (uint32_t)grp * WIN + JS * j + 16u * (uint32_t)gl, blk[j]);
+            uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)(JS * j), 0), 16));
+            if (j == 0) {  // only the first block of a lane can start in front of the read (a < 64)
+                const uint4 kl = lds_v4(keep32 + 16u * (uint32_t)min(max(e_lo, 0), 16));
+                kp = make_uint4(kp.x & ~kl.x, kp.y & ~kl.y, kp.z & ~kl.z, kp.w & ~kl.w);
+            }
+            const uint4 pw = lds_v4(pa32 + (uint32_t)min(po + (int)(JS * j), p_top));
+            const uint4 fw = lds_v4(fa32 + (uint32_t)min(max(fo + (int)(JS * j), 0), f_top));
+            const uint32_t w[4] = {blk[j].x, blk[j].y, blk[j].z, blk[j].w};
+            const uint32_t xp[4] = {(w[0] ^ pw.x) & kp.x, (w[1] ^ pw.y) & kp.y, (w[2] ^ pw.z) & kp.z, (w[3] ^ pw.w) & kp.w};
+            const uint32_t xf[4] = {(w[0] ^ fw.x) & kp.x, (w[1] ^ fw.y) & kp.y, (w[2] ^ fw.z) & kp.z, (w[3] ^ fw.w) & kp.w};
+            fp.block(j, xp);
+            lf.block(j, xf);
+        }
+        // window offsets of the lane's first / last difference, then of the group's
+        const uint32_t wp = fp.yo ? JS * fp.jb + 16u * (uint32_t)gl + fp.byte_in_block() : 0x7fffffffu;
+        const int wf = lf.yo ? (int)(JS * lf.jb + 16u * (uint32_t)gl + lf.byte_in_block()) : -1;
+        uint32_t gp = wp;
+        int gf = wf;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {  // (a REDUX over part of a warp runs once per group)
+            gp = min(gp, __shfl_xor_sync(FULL_MASK, gp, o));
+            gf = max(gf, __shfl_xor_sync(FULL_MASK, gf, o));
+        }
+        const uint32_t t = min(gp != 0x7fffffffu ? gp - a : L, min(L, Lp));             // common prefix of R and P
+        const uint32_t s = min(gf >= 0 ? L - 1u - ((uint32_t)gf - a) : L, min(L, Lf));  // common suffix of R and F
+        const uint32_t bp = s_pcum[t], bs = s_fsuf[s];
+        const bool t0_all = s == L && L == Lf, pe_all = t == L && L == Lp;
+        const bool overlap = t + s >= L;
+        const uint32_t n_mid = overlap ? 0u : L - s - t;
+        // findJSS answers len - 1 for R == F, else bs (-1 is possible only with bs == 0: left to the general path); a junction
+        // start on the first site of an alternative template's region is decided by computeAltEditing (align.go:183-235);
+        // a junction longer than mid_cap may hold a saturating run
+        const int junc_start = t0_all ? (int)tm : (int)bs;
+        const bool cand = L != 0u && (t0_all || bs >= 1u) && !(K > 2 && s_alt[junc_start] != 0) && n_mid <= g.mid_cap;
+
+        // ---- the characters between prefix and suffix against Bases[bp ..): the whole warp, one read after the other ----
+        bool mid_ok = true;
+        uint32_t mid_bases = 0;
+        __syncwarp();
+        {
+            const uint32_t my_nm = cand ? n_mid : 0u;
+            const uint32_t my_at = stage32 + (uint32_t)grp * WIN + a + t;
+#pragma unroll
+            for (int k = 0; k < RPW; k++) {
+                const uint32_t nm = __shfl_sync(FULL_MASK, my_nm, k * G);
+                if (nm == 0u) continue;
+                const uint32_t at = __shfl_sync(FULL_MASK, my_at, k * G) + (uint32_t)lane;
+                const uint32_t rank0 = bases32 + __shfl_sync(FULL_MASK, bp, k * G);
+                uint32_t rank = rank0;
+                bool okk = true;
+                for (uint32_t i0 = 0; i0 < nm; i0 += 32u) {
+                    const bool in = i0 + (uint32_t)lane < nm;
+                    uint32_t cu = eb;
+                    if (in) cu = lds_u8(at + i0) & 0xdfu;
+                    const bool isb = cu != eb;
+                    const uint32_t bal = __ballot_sync(FULL_MASK, isb);
+                    const uint32_t want = lds_u8(rank + (uint32_t)__popc(bal & lt));
+                    rank += (uint32_t)__popc(bal);
+                    if (__any_sync(FULL_MASK, isb && want != cu)) {
+                        okk = false;
+                        break;
+                    }
+                }
+                if (grp == k) {
+                    mid_ok = okk;
+                    mid_bases = rank - rank0;
+                }
+            }
+        }
+        __syncwarp();
+        const bool ident = overlap ? bp + (uint32_t)s_fsuf[L - t] == tm : (mid_ok && bp + mid_bases + bs == tm);
+        const bool ok = cand && ident;
+
+        if (ok) {
+            int junc_end = pe_all ? -1 : (int)(tm - bp);
+            int edit_stop = junc_start - 1, junc_len = 0;
+            uint32_t js_off = 0, js_len = 0;
+            if (junc_end > edit_stop) {
+                junc_len = junc_end - edit_stop;
+                if (!t0_all) {
+                    const uint32_t o0 = s_ppos[bp], o1 = L - (uint32_t)s_ftail[bs];
+                    js_len = o1 - o0;
+                    js_off = js_len ? o0 : 0u;
+                }
+            } else if (junc_end < edit_stop) {
+                junc_end = edit_stop;
+            }
+            if (t0_all) {
+                junc_end = junc_start;
+                edit_stop = junc_start;
+                junc_len = 0;
+            }
+            const int off = q.t.edit_offset;
+            if (gl == 0) {
+                uint4 *dst = reinterpret_cast<uint4 *>(q.rec + r);
+                dst[0] = make_uint4((uint32_t)(edit_stop + off), (uint32_t)(junc_start + off), (uint32_t)(junc_end + off), (uint32_t)junc_len);
+                dst[1] = make_uint4(read_count, 0u, tm, js_off);
+                dst[2] = make_uint4(js_len, tm | (tm << 16), 0u, L);
+            }
+            accA += read_count;
+            accN += 1u;
+            // cmd/treat/handlers.go:203-215: three histograms, one lane each
+            if (sum_len && gl < 3 && !(edit_stop + off == q.t.tmpl_edit_stop && junc_len == 0)) {
+                const uint32_t bin = gl == 0 ? (uint32_t)(edit_stop + 2) : gl == 1 ? (uint32_t)junc_len : (uint32_t)(junc_end + 2);
+                if (bin < q.bins) {
+                    const uint32_t idx = TREAT_B200_SUMMARY_HEADER + (uint32_t)gl * q.bins + bin;
+                    const uint32_t old = atomicAdd(&sum_lo[idx], read_count);
+                    if (old + read_count < old) atomicAdd(&sum_hi[idx], 1u);
+                }
+            }
+            if (q.ops && !q.ops_gapped_only) {  // m match columns: an all-zero row
+                uint32_t *go = reinterpret_cast<uint32_t *>(q.ops + r * (uint64_t)q.ops_stride);
+                for (int wi = gl; wi < (int)(q.ops_stride / 4); wi += G) go[wi] = 0u;
+            }
+        }
+        // everything else goes to the general path, one list append per warp
+        {
+            const uint32_t todo = __ballot_sync(FULL_MASK, in_batch && !ok && gl == 0);
+            if (todo) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(f.rest_count, (uint32_t)__popc(todo));
+                at = __shfl_sync(FULL_MASK, at, 0);
+                if (in_batch && !ok && gl == 0) f.rest[at + (uint32_t)__popc(todo & lt)] = r;
+            }
+        }
+        b_cur = b_nxt, L_cur = L_nxt;
+#pragma unroll
+        for (int j = 0; j < 4; j++) blk[j] = nxt[j];
+    }
+    // the header counters of the reads finished above (cmd/treat/stats.go:140-187): none has a gap or a mismatch
+    if (G < 32) {
+#pragma unroll
+        for (int o = 16; o >= G; o >>= 1) {
+            accA += __shfl_xor_sync(FULL_MASK, accA, o);
+            accN += __shfl_xor_sync(FULL_MASK, accN, o);
+        }
+    }
+    if (lane == 0 && accN) atomicMax(&p.scalars[0], tm);
+    unsigned long long ctr = 0;
+    if (sum_len) {
+        const unsigned long long Nn = accN;
+        ctr = (lane == 0 || lane == 1) ? accA : (lane == 7 || lane == 8 || lane == 14) ? Nn
+              : lane == 15 ? Nn * (unsigned long long)tm * (unsigned long long)tm : 0ull;
+    }
+    flush_summary(q, sum_len, sum_lo, sum_hi, lane, ctr);
+}
+
+bool frontier_applies(const PackParams &p, const AlignParams &q, const FrontierParams &f)
+{
+    return f.image != nullptr && f.rest != nullptr && f.rest_count != nullptr && f.g.image_bytes != 0 && f.g.tm == (uint32_t)q.t.m && p.tpk != nullptr &&
+           p.edit_base >= 'A' && p.edit_base <= 'Z';
+}
+
+// lanes per read: the smallest group whose pass (64 G - 63 characters at the worst alignment) holds reads a little longer
+// than the longer template string
+static int frontier_group(const FrontierGeom &g)
+{
+    const uint32_t need = std::max(g.Lf, g.Lp) + 16u;
+    for (int G : {8, 16, 32})
+        if (need <= (uint32_t)G * kFrNB - (kFrNB - 1u)) return G;
+    return 0;
+}
+
+template <typename Kern>
+static int launch_frontier_kernel(Kern kern, const PackParams &p, const AlignParams &q, const FrontierParams &f, int rpw, size_t smem, int num_sms,
+                                  void *stream)
+{
+    const uint64_t units = (p.N + rpw - 1) / rpw;
+    uint64_t blocks = (units + kFrWarps - 1) / kFrWarps;
+    const int per_sm = occupancy_cached((const void *)kern, kFrWarps * 32, smem);
+    const uint64_t cap = (uint64_t)num_sms * per_sm;  // persistent grid
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return 0;
+    kern<<<(unsigned)blocks, kFrWarps * 32, smem, (cudaStream_t)stream>>>(p, q, f);
+    return (int)cudaGetLastError();
+}
+
+int launch_frontier(const PackParams &p, const AlignParams &q, const FrontierParams &f, int num_sms, int max_smem_optin, void *stream)
+{
+    const uint32_t sum_len = q.summary ? TREAT_B200_SUMMARY_HEADER + 3u * q.bins : 0u;
+    const size_t smem = (size_t)f.g.image_bytes + align16(8u * sum_len) + (size_t)kFrWarps * 2048u;
+    const int G = frontier_group(f.g);
+    if (G == 0 || smem > (size_t)max_smem_optin) return -1000;
+    const bool span = p.begin != nullptr;
+    switch (G) {
+    case 8:
+        return span ? launch_frontier_kernel(k_frontier<8, true>, p, q, f, 4, smem, num_sms, stream)
+                    : launch_frontier_kernel(k_frontier<8, false>, p, q, f, 4, smem, num_sms, stream);
+    case 16:
+        return span ? launch_frontier_kernel(k_frontier<16, true>, p, q, f, 2, smem, num_sms, stream)
+                    : launch_frontier_kernel(k_frontier<16, false>, p, q, f, 2, smem, num_sms, stream);
+    default:
+        return span ? launch_frontier_kernel(k_frontier<32, true>, p, q, f, 1, smem, num_sms, stream)
+                    : launch_frontier_kernel(k_frontier<32, false>, p, q, f, 1, smem, num_sms, stream);
+    }
+}
+
+int configure_frontier_kernels(int max_smem_optin)
+{
+    cudaError_t ce = cudaFuncSetAttribute(k_frontier<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    return (int)ce;
+}
+
+}  // namespace treat_b200

@@ -421,9 +421,12 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
     const int64_t lo = SPAN ? 0 : p.N ? (int64_t)(p.off[0] - p.off_bias) : 0;
     const int64_t hi = SPAN ? (int64_t)p.span : p.N ? (int64_t)(p.off[p.N] - p.off_bias) : 0;
     // where read r lies, as loaded (no arithmetic on the loaded values here: they are used one iteration later)
-    auto where = [&](uint32_t r, uint64_t &x0, uint64_t &x1) {
+    // the reads of this launch: all of them, or the ones k_frontier left (p.sel: their indices, *p.sel_count of them)
+    const uint32_t total = p.sel ? min(*p.sel_count, N32) : N32;
+    auto where = [&](uint32_t i, uint64_t &x0, uint64_t &x1) {
         x0 = x1 = SPAN ? 0ull : p.off_bias;
-        if (r >= N32) return;
+        if (i >= total) return;
+        const uint32_t r = p.sel ? p.sel[i] : i;
         if (SPAN) {
             x0 = p.begin[r];
             x1 = p.len[r];
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
     unsigned long long ctr = 0;                  // counters of reads that took the general assembly (lane L: counter L)
     unsigned long long accA = 0, accC = 0;       // sum of ReadCount over the reads finished here / over those with one mismatch
     uint32_t accN = 0, accE = 0;                 // their numbers
-    const uint32_t units = (uint32_t)((p.N + RPW - 1) / RPW);
+    const uint32_t units = (total + RPW - 1) / RPW;
     const uint32_t gw = blockIdx.x * kF2Warps + warp, nw = gridDim.x * kF2Warps;
     // software pipeline: offsets two units ahead, the blocks one unit ahead; every load is issued a whole pass before its
     // result is touched
@@ -485,12 +488,14 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
         load_blocks(b_nxt, L_nxt, nA, nB);
         where((u + 2 * nw) * RPW + grp, x0_nxt, x1_nxt);
 
-        const uint32_t r = u * RPW + grp;
+        const uint32_t ri = u * RPW + grp;
+        const bool in_batch = ri < total;
+        const uint32_t r = (p.sel && in_batch) ? p.sel[ri] : ri;
         const uint32_t a = (base_lo + (uint32_t)b_cur) & 31u;  // the read starts at character a of lane 0's blocks
         const bool too_long = ((a + L_cur + 31u) >> 5) > (uint32_t)G;
-        const bool valid = r < N32 && !too_long;
+        const bool valid = in_batch && !too_long;
         const uint32_t L = valid ? L_cur : 0u;  // a read that is not handled here runs through as an empty one, without outputs
-        if (too_long && r < N32 && gl == 0) p.long_list[atomicAdd(p.long_count, 1u)] = r;
+        if (too_long && in_batch && gl == 0) p.long_list[atomicAdd(p.long_count, 1u)] = r;
         const uint32_t read_count = (valid && q.read_count) ? q.read_count[r] : 1u;  // needed at the very end: in flight meanwhile
 
         // ---- which of the lane's 32 characters are bases of the read -------------------------------------------
@@ -712,7 +717,7 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
             if (lead == src) reinterpret_cast<uint4 *>(stage)[gl] = cnt;
             __syncwarp();
             const uint32_t rf = rflags | (mism ? kFlagOneMismatch : kFlagSameBases);
-            finish_same_general(q, cs, ws, lane, (uint64_t)(u * RPW + (uint32_t)(src / G)), __shfl_sync(FULL_MASK, rf, src), stage, ctr,
+            finish_same_general(q, cs, ws, lane, (uint64_t)__shfl_sync(FULL_MASK, r, src), __shfl_sync(FULL_MASK, rf, src), stage, ctr,
                                 __shfl_sync(FULL_MASK, L, src));
         }
         if (valid) {

@@ -85,6 +85,10 @@ __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
