@@ -12,11 +12,12 @@ collective, one all-reduce of the summary counters per step).
 One JSON line on rank 0:
   value      whole-job reads/s with the raw reads already resident in HBM (device-timed, max over ranks)
   e2e        the same through treat_b200_align_batch with pinned HOST buffers (H2D + kernels + D2H)
-  roofline   the kernel that takes the largest share of a step: k_pack16 (NewFragment: streams the raw reads, writes
-             the packed ones) against the measured HBM copy bandwidth
-  roofline_dp   the DP kernel (k_align2, run on every read) against the INT32 ALU peak measured live on this GPU
+  roofline   the kernel that takes the largest share of a step: k_frontier (finishes the reads that are the template
+             edited up to a frontier from their raw characters) against the measured HBM copy bandwidth, timed alone
+  roofline_fused  k_frontier + k_pack_finish2 (every read that needs no DP finished, the others packed and listed)
+  roofline_dp   the DP stage (k_band_* / k_align2, run on every read) against the INT32 ALU peak measured live on this GPU
   kernels_ms    CUDA-event time of each stage alone; reads whose stripped bases equal the template's, or differ
-             in exactly one base, are finished without a DP (k_same_bases) -- exact, see DESIGN.md 4
+             in exactly one base, are finished without a DP -- exact, see DESIGN.md 4
   cpu_baseline  the CPU oracle (a C port of the Go path; the Go reference cannot be built here)
 
 --impl reference times that CPU port with all host threads on bounded samples of the same workload.
@@ -633,6 +634,18 @@ def run_ours(args):
     fused_ms = kernel_ms(lambda: eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len,
                                                         flags | cabi.SKIP_DP | cabi.NO_SUMMARY, d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw),
                          args.steps)
+    # k_frontier alone (TREAT_B200_FRONTIER_ONLY: nothing runs behind it): the kernel that takes the largest share of a step.
+    # Which reads it finishes is read off the records: the buffer is filled with 0xFF first, a finished read has its length in
+    # the last word.
+    d_rec.fill_(0xff)
+    frontier_args = (d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, flags | cabi.SKIP_DP | cabi.FRONTIER_ONLY | cabi.NO_SUMMARY,
+                     d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw)
+    eng.align_batch_device(*frontier_args)
+    torch.cuda.synchronize()
+    by_frontier = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)["raw_len"] != 0xffffffff
+    frontier_ms = kernel_ms(lambda: eng.align_batch_device(*frontier_args), args.steps) if by_frontier.any() else None
+    eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, flags | cabi.NO_SUMMARY, d_rec.data_ptr(),
+                           d_ops.data_ptr(), stride, sraw)  # the records of the whole batch again
     # the whole step with the DP forced on every read (TREAT_B200_DP_EVERY_READ: k_pack16 + k_align2 on all reads)
     dp_every_ms = kernel_ms(lambda: eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len,
                                                            flags | cabi.DP_EVERY_READ | cabi.NO_SUMMARY, d_rec.data_ptr(), d_ops.data_ptr(), stride,
@@ -671,14 +684,14 @@ def run_ours(args):
     def ncu_traffic(kernel):
         # DRAM bytes per launch from the committed ncu capture (per read x reads of this launch)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json")))[kernel]
             return (tr["dram_read_bytes_per_read"] + tr["dram_write_bytes_per_read"]) * N if args.workload == "rps12" else None
         except Exception:
             return None
     def ncu_facts(kernel):
-        # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r02b_*_ncu_full.md)
+        # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r03_*_ncu_full.md)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json")))[kernel]
             return {k: v for k, v in tr.items() if not k.startswith("dram_")}
         except Exception:
             return None
@@ -687,26 +700,38 @@ def run_ours(args):
     listed = ~no_dp
     packed_bytes = float(((n_arr + 3) // 4 + (n_arr + 1))[listed].sum() + int(listed.sum()) * (2 + 1 + 4 + 4))
     fused_bytes = float(len(seqs) + N * 8 + N * 4 + int(no_dp.sum()) * 48) + packed_bytes
-    roofline = {"bound": "hbm", "kernel": "k_pack_finish2 (NewFragment + editing-site assembly of the reads that need no DP; largest share of a step)",
-                "achieved": fused_bytes / (fused_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": fused_bytes / (fused_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                "bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms, "traffic": ncu_traffic("k_pack_finish2"), "ncu": ncu_facts("k_pack_finish2"),
-                "bytes_per_read": fused_bytes / N,
-                "note": "instruction-issue bound byte work (character classes, compaction, count differences, site compares), "
-                        "not DRAM bound: see profiles/; ms_per_launch includes the launch of the multi-pass form for reads "
-                        "longer than one pass and one 8-byte read-back"}
+    roofline_fused = {"bound": "hbm", "kernel": "k_frontier + k_pack_finish2 on the reads it leaves (NewFragment + editing-site assembly of "
+                                                "every read that needs no DP, the others packed and listed)",
+                      "achieved": fused_bytes / (fused_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": fused_bytes / (fused_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                      "bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms, "bytes_per_read": fused_bytes / N,
+                      "note": "ms_per_launch covers both launches (plus the multi-pass form for reads longer than one pass) and one 8-byte read-back"}
+    if frontier_ms is not None:
+        # k_frontier: raw characters + offsets + read counts in; the 48-byte record of every read it finishes and a 4-byte list
+        # entry for every other read out
+        n_fr = int(by_frontier.sum())
+        fr_bytes = float(len(seqs) + N * 8 + N * 4 + n_fr * 48 + (N - n_fr) * 4)
+        roofline = {"bound": "hbm", "kernel": "k_frontier (NewFragment + NewAlignment of the reads that are the template edited up to a frontier, "
+                                              "from two string compares on the raw characters; largest share of a step)",
+                    "achieved": fr_bytes / (frontier_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": fr_bytes / (frontier_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "bytes_per_launch": fr_bytes, "ms_per_launch": frontier_ms, "traffic": ncu_traffic("k_frontier"), "ncu": ncu_facts("k_frontier"),
+                    "bytes_per_read": fr_bytes / N, "reads_finished": n_fr / N,
+                    "note": "byte work on the raw characters (XOR against the two template strings, first / last difference, junction "
+                            "check): issue slots, not DRAM, are the nearer bound -- see `issue` and profiles/"}
+    else:  # the template does not take k_frontier (wide alphabet, very long strings): the fused kernel is the dominant one
+        roofline = dict(roofline_fused)
     # the same kernel against the bound that actually limits it: warp instructions issued per second (from the committed ncu
     # capture's instruction count per read) against 4 issue slots per SM and clock
-    facts = ncu_facts("k_pack_finish2")
-    if facts and facts.get("warp_instructions_per_read") and args.workload == "rps12":
+    facts = ncu_facts("k_frontier")
+    if frontier_ms is not None and facts and facts.get("warp_instructions_per_read") and args.workload == "rps12":
         props = torch.cuda.get_device_properties(dev)
         mhz = float(clocks.get("sm_mhz") or 1965.0) if isinstance(clocks, dict) else 1965.0
         issue_peak = props.multi_processor_count * 4 * mhz * 1e6
-        issued = facts["warp_instructions_per_read"] * N / (fused_ms * 1e-3)
+        issued = facts["warp_instructions_per_read"] * N / (frontier_ms * 1e-3)
         roofline["issue"] = {"bound": "warp instructions issued", "achieved": issued / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s",
                              "frac": issued / issue_peak, "warp_instructions_per_read": facts["warp_instructions_per_read"],
-                             "note": "instruction count per read from profiles/r02_traffic.json (ncu), time measured here; the HBM "
-                                     "fraction above is low because ~390 warp instructions per ~300-byte read, not memory, bound the kernel"}
+                             "note": "instruction count per read from profiles/r03_traffic.json (ncu), time measured here"}
     # the unfused NewFragment kernel (treat_b200_pack_device, used by the stage calls and for long / wide templates)
     pack_bytes = float(len(seqs) + N * 8 + ((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4))
     roofline_pack = {"bound": "hbm", "kernel": "k_pack16 (stage call treat_b200_pack_device)", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
@@ -986,7 +1011,8 @@ def run_ours(args):
             "config": {"workload": workload_name(args, t), "l2": "inputs larger than L2 (%.0f MB raw reads per GPU per step)" % (len(seqs) / 1e6),
                        "parallelism": "reads sharded over %d GPU(s), summary all-reduce only" % world,
                        "outputs": "48-byte record per read + %d-byte 2-bit ops row per read with a gap" % stride},
-            "kernels_ms": {"k_pack_finish2 (fused NewFragment + assembly)": fused_ms,
+            "kernels_ms": {"k_frontier": frontier_ms,
+                           "k_frontier + k_pack_finish2 (NewFragment + assembly of every read without a DP)": fused_ms,
                            "k_band_* + k_align2 (reads that need a DP) = step - fused": max(dev_ms / args.steps - fused_ms, 0.0),
                            "stage calls: k_pack16": pack_ms, "stage calls: k_same_bases+k_align(listed reads)": marks_ms,
                            "DP stage on every read (k_band_* + k_align2)": align_ms,
@@ -996,7 +1022,7 @@ def run_ours(args):
             "reads_equal_to_template_bases": same_frac,
             # the same step with the DP forced on every read (k_pack16 + k_align2 on all reads), from the stage timings
             "value_dp_every_read": world * N / (dp_every_ms * 1e-3),
-            "roofline": roofline, "roofline_dp": roofline_dp, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
+            "roofline": roofline, "roofline_fused": roofline_fused, "roofline_dp": roofline_dp, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta,
             "text_device": text_dev, "parity": parity, "long": side.get("long"), "noisy": side.get("noisy"), "collapse": collapse,
             "nccl": {"version": cabi.lib().treat_b200_nccl_version() if world > 1 else None,
                      "collective": "ncclAllReduce(uint64, sum) of the summary counters, issued by libtreat_b200.so "

@@ -61,6 +61,8 @@ extern "C" {
 #define TREAT_B200_NO_FRONTIER 0x1000u /* do not run k_frontier (reads that are the template edited up to a frontier, finished from
                                           two string compares on the raw characters) in front of the fused kernels (results are
                                           the same; tests compare both ways) */
+#define TREAT_B200_FRONTIER_ONLY 0x2000u /* measurement only (bench.py times k_frontier alone with it): nothing runs behind k_frontier,
+                                            so the records of the reads it leaves to the other kernels are NOT written */
 #define TREAT_B200_USE_PACK_MARKS 0x40u /* treat_b200_align_packed_device only: the reads were packed by treat_b200_pack_device
                                            under the template that is current now, so reads it marked as equal to the template
                                            skip the DP; without this flag the stage call runs the DP for every read */

@@ -20,6 +20,7 @@ EXCLUDE_SNPS, WANT_OPS, NO_SUMMARY, ONE_READ_PER_WARP, FULL_TRACEBACK_STORE = 0x
 DP_EVERY_READ, USE_PACK_MARKS, OPS_GAPPED_ONLY, HEATMAP, WANT_BLOBS, SKIP_DP = 0x20, 0x40, 0x80, 0x100, 0x200, 0x400
 NO_BAND = 0x800
 NO_FRONTIER = 0x1000
+FRONTIER_ONLY = 0x2000
 ST_REF_PANIC, ST_WIDE_BASE, ST_SATURATED = 0x1, 0x2, 0x4
 OP_MATCH, OP_DEL, OP_INS = 0, 1, 2
 SUMMARY_HEADER = 16

@@ -974,6 +974,7 @@ static int do_pack_finish(treat_b200_ctx *ctx, const uint8_t *d_seqs, const uint
             ctx->launches++;
             pp.sel = fp.rest;
             pp.sel_count = fp.rest_count;
+            if (flags & TREAT_B200_FRONTIER_ONLY) return TREAT_B200_OK;  // measurement: the rest stays unaligned
         }
     }
     if (!no_fuse2 && pack_finish2_applies(pp, ap)) {

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     constexpr uint32_t JS = 16u * G;      // a lane's blocks are JS bytes apart
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gl = lane & (G - 1), grp = lane / G, lead = grp * G;
+    const int gl = lane & (G - 1), grp = lane / G;
     const uint32_t lt = (1u << lane) - 1u;
     const FrontierGeom &g = f.g;
     // ---- the template's image, this CTA's histograms, one 2 KB staging area per warp ---------------------------------
@@ -272,10 +272,14 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         load_blocks(b_cur, L_cur, blk);
     }
     where((gw + nw) * RPW + grp, x0_nxt, x1_nxt);
+    const uint32_t mystage32 = stage32 + (uint32_t)grp * WIN + 16u * (uint32_t)gl;  // this lane's block j sits JS j bytes further
     for (uint32_t u = gw; u < units; u += nw) {
-        uint4 nxt[4];
+        // the blocks loaded an iteration ago go to the staging area (every later step reads them from there), and the same
+        // registers take the next read's blocks: those loads are in flight for the whole iteration
+#pragma unroll
+        for (int j = 0; j < 4; j++) sts_v4(mystage32 + JS * j, blk[j]);  // (the previous iteration's readers are past their __syncwarp)
         resolve(x0_nxt, x1_nxt, b_nxt, L_nxt);
-        load_blocks(b_nxt, L_nxt, nxt);
+        load_blocks(b_nxt, L_nxt, blk);
         where((u + 2 * nw) * RPW + grp, x0_nxt, x1_nxt);
 
         const uint32_t r = u * RPW + grp;
@@ -295,9 +299,12 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         const int e_hi = (int)(a + L) - 16 * gl, e_lo = (int)a - 16 * gl;  // the read covers bytes [e_lo, e_hi) counted from this lane's first block
         FirstNz fp;
         LastNz lf;
+        // blocks past the longest read of the warp are skipped by all lanes
+        const uint32_t nb_max = __reduce_max_sync(FULL_MASK, (a + L + 15u) >> 4);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            sts_v4(stage32 + (uint32_t)grp * WIN + JS * j + 16u * (uint32_t)gl, blk[j]);
+            if (j >= 2 && (uint32_t)(G * j) >= nb_max) continue;
+            const uint4 wv = lds_v4(mystage32 + JS * j);
             uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)(JS * j), 0), 16));
             if (j == 0) {  // only the first block of a lane can start in front of the read (a < 64)
                 const uint4 kl = lds_v4(keep32 + 16u * (uint32_t)min(max(e_lo, 0), 16));
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             }
             const uint4 pw = lds_v4(pa32 + (uint32_t)min(po + (int)(JS * j), p_top));
             const uint4 fw = lds_v4(fa32 + (uint32_t)min(max(fo + (int)(JS * j), 0), f_top));
-            const uint32_t w[4] = {blk[j].x, blk[j].y, blk[j].z, blk[j].w};
+            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
             const uint32_t xp[4] = {(w[0] ^ pw.x) & kp.x, (w[1] ^ pw.y) & kp.y, (w[2] ^ pw.z) & kp.z, (w[3] ^ pw.w) & kp.w};
             const uint32_t xf[4] = {(w[0] ^ fw.x) & kp.x, (w[1] ^ fw.y) & kp.y, (w[2] ^ fw.z) & kp.z, (w[3] ^ fw.w) & kp.w};
             fp.block(j, xp);
@@ -338,21 +345,21 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         uint32_t mid_bases = 0;
         __syncwarp();
         {
-            const uint32_t my_nm = cand ? n_mid : 0u;
+            // (junction length | bases in front of it << 16) and the staged address of its first character
+            const uint32_t my_nb = (cand ? n_mid : 0u) | (bp << 16);
             const uint32_t my_at = stage32 + (uint32_t)grp * WIN + a + t;
 #pragma unroll
             for (int k = 0; k < RPW; k++) {
-                const uint32_t nm = __shfl_sync(FULL_MASK, my_nm, k * G);
-                if (nm == 0u) continue;
-                const uint32_t at = __shfl_sync(FULL_MASK, my_at, k * G) + (uint32_t)lane;
-                const uint32_t rank0 = bases32 + __shfl_sync(FULL_MASK, bp, k * G);
+                const uint32_t nb = __shfl_sync(FULL_MASK, my_nb, k * G);
+                int left = (int)(nb & 0xffffu);
+                if (left == 0) continue;
+                uint32_t at = __shfl_sync(FULL_MASK, my_at, k * G) + (uint32_t)lane;  // (reads past the junction stay inside the staging area + its pad)
+                const uint32_t rank0 = bases32 + (nb >> 16);
                 uint32_t rank = rank0;
                 bool okk = true;
-                for (uint32_t i0 = 0; i0 < nm; i0 += 32u) {
-                    const bool in = i0 + (uint32_t)lane < nm;
-                    uint32_t cu = eb;
-                    if (in) cu = lds_u8(at + i0) & 0xdfu;
-                    const bool isb = cu != eb;
+                do {
+                    const uint32_t cu = lds_u8(at) & 0xdfu;
+                    const bool isb = lane < left && cu != eb;
                     const uint32_t bal = __ballot_sync(FULL_MASK, isb);
                     const uint32_t want = lds_u8(rank + (uint32_t)__popc(bal & lt));
                     rank += (uint32_t)__popc(bal);
@@ -360,7 +367,9 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
                         okk = false;
                         break;
                     }
-                }
+                    at += 32u;
+                    left -= 32;
+                } while (left > 0);
                 if (grp == k) {
                     mid_ok = okk;
                     mid_bases = rank - rank0;
@@ -424,8 +433,6 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             }
         }
         b_cur = b_nxt, L_cur = L_nxt;
-#pragma unroll
-        for (int j = 0; j < 4; j++) blk[j] = nxt[j];
     }
     // the header counters of the reads finished above (cmd/treat/stats.go:140-187): none has a gap or a mismatch
     if (G < 32) {
@@ -478,7 +485,7 @@ static int launch_frontier_kernel(Kern kern, const PackParams &p, const AlignPar
 int launch_frontier(const PackParams &p, const AlignParams &q, const FrontierParams &f, int num_sms, int max_smem_optin, void *stream)
 {
     const uint32_t sum_len = q.summary ? TREAT_B200_SUMMARY_HEADER + 3u * q.bins : 0u;
-    const size_t smem = (size_t)f.g.image_bytes + align16(8u * sum_len) + (size_t)kFrWarps * 2048u;
+    const size_t smem = (size_t)f.g.image_bytes + align16(8u * sum_len) + (size_t)kFrWarps * 2048u + 512u;  // + pad: the junction check reads whole rounds of 32 characters
     const int G = frontier_group(f.g);
     if (G == 0 || smem > (size_t)max_smem_optin) return -1000;
     const bool span = p.begin != nullptr;
