@@ -1279,17 +1279,17 @@ def test_frontier_kernel_edges(eng, tmp_path):
         off[1:] = np.cumsum([len(c) for c in cases])
         seqs = np.frombuffer(raw, dtype=np.uint8).copy()
         rc = np.arange(1, len(cases) + 1, dtype=np.uint32)
-        flags = cabi.WANT_OPS
-        eng.reset_summary()
-        grec, gops = eng.align_batch(seqs, off, rc, flags)
-        gsum = eng.summary()
-        orec, oops, _ = O.align_batch(om, seqs, off, rc, nthreads=8, ops_stride=gops.shape[1])
-        assert compare_records(grec, orec) == []
-        assert np.array_equal(gops, oops)
-        assert np.array_equal(gsum, summary_from_records(orec, t.m, 0, om.EditStop))
-        eng.reset_summary()
-        nrec, nops = eng.align_batch(seqs, off, rc, flags | cabi.NO_FRONTIER)
-        assert np.array_equal(nrec, grec) and np.array_equal(nops, gops) and np.array_equal(eng.summary(), gsum)
+        for flags, exclude in ((cabi.WANT_OPS | cabi.EXCLUDE_SNPS, True), (cabi.WANT_OPS, False)):
+            eng.reset_summary()
+            grec, gops = eng.align_batch(seqs, off, rc, flags)
+            gsum = eng.summary()
+            orec, oops, _ = O.align_batch(om, seqs, off, rc, exclude_snps=exclude, nthreads=8, ops_stride=gops.shape[1])
+            assert compare_records(grec, orec) == []
+            assert np.array_equal(gops, oops)
+            assert np.array_equal(gsum, summary_from_records(orec, t.m, 0, om.EditStop))
+            eng.reset_summary()
+            nrec, nops = eng.align_batch(seqs, off, rc, flags | cabi.NO_FRONTIER)
+            assert np.array_equal(nrec, grec) and np.array_equal(nops, gops) and np.array_equal(eng.summary(), gsum)
         # every start alignment of the first read inside its 64-byte block
         for shift in (1, 3, 15, 16, 17, 31, 33, 47, 63):
             s2 = np.concatenate([np.full(shift, ord("G"), dtype=np.uint8), seqs])

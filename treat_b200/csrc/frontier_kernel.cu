@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     for (uint32_t i = threadIdx.x; i < 2 * sum_len; i += blockDim.x) sum_lo[i] = 0u;
     __syncthreads();
     const uint32_t s32 = smem_u32(smem);
-    const uint32_t stage32 = s32 + g.image_bytes + sum_bytes + (uint32_t)warp * 2048u;
+    const uint32_t warp32 = s32 + g.image_bytes + sum_bytes + (uint32_t)warp * 4096u;     // two halves of 2 KB: the reads being worked on, the next ones
+    const uint32_t lane32 = warp32 + (uint32_t)grp * (kFrNB * G) + 16u * (uint32_t)gl;     // this lane's first block inside a half
     const uint32_t keep32 = s32 + g.off_keep, pc32 = s32 + g.off_p, fc32 = s32 + g.off_f;
     const uint16_t *s_pcum = reinterpret_cast<const uint16_t *>(smem + g.off_pcum), *s_fsuf = reinterpret_cast<const uint16_t *>(smem + g.off_fsuf);
     const uint16_t *s_ppos = reinterpret_cast<const uint16_t *>(smem + g.off_ppos), *s_ftail = reinterpret_cast<const uint16_t *>(smem + g.off_ftail);
@@ -222,68 +223,67 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         b = SPAN ? x0 : x0 - p.off_bias;
         L = SPAN ? (uint32_t)x1 : (uint32_t)(x1 - x0);
     };
-    // this lane's four 16-byte blocks of a read's window; zero where the block lies behind the read or the read is too
-    // long for one pass.  A window whose used blocks stick out of [lo, hi) -- at the ends of a caller's buffer -- is read
-    // byte by byte.
-    auto load_blocks = [&](uint64_t b, uint32_t L, uint4 (&blk)[4]) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) blk[j] = make_uint4(0, 0, 0, 0);
+    // this lane's four 16-byte blocks of a read's window go straight to the staging area (cp.async, L2 only); blocks behind
+    // the read are not copied -- whatever the area holds there is masked out or never looked at.  A window whose used
+    // blocks stick out of [lo, hi) -- at the ends of a caller's buffer -- is read byte by byte.
+    auto stage_blocks = [&](uint64_t b, uint32_t L, uint32_t dst32) {
         const uint32_t a = (base_lo + (uint32_t)b) & (kFrNB - 1u);
         const uint32_t nb16 = (a + L + 15u) >> 4;  // 16-byte blocks the read touches
         if (L == 0u || a + L > WIN) return;
         const int64_t w0 = (int64_t)b - a;  // the window starts here
         if (w0 >= lo && w0 + (int64_t)(16u * nb16) <= hi) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.seqs + w0) + gl;
+            const uint8_t *src = p.seqs + w0 + 16 * gl;
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if ((uint32_t)(G * j + gl) < nb16) blk[j] = src[G * j];
+                if ((uint32_t)(G * j + gl) < nb16)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst32 + JS * j), "l"(src + JS * j) : "memory");
             return;
         }
 #pragma unroll 1
         for (int j = 0; j < 4; j++) {
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
-            for (int c = 0; c < 16; c++) {
-                const int64_t y = w0 + (int64_t)(JS * j + 16u * gl) + c;
-                const uint32_t v = (y >= lo && y < hi) ? (uint32_t)p.seqs[y] << (8 * (c & 3)) : 0u;
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (i == (c >> 2)) w[i] |= v;
+            for (int c4 = 0; c4 < 4; c4++) {
+                uint32_t w = 0u;
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
+                    const int64_t y = w0 + (int64_t)(JS * j + 16u * gl) + 4 * c4 + c;
+                    if (y >= lo && y < hi) w |= (uint32_t)p.seqs[y] << (8 * c);
+                }
+                sts_u32(dst32 + JS * j + 4u * c4, w);
             }
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++)
-                if (jj == j) blk[jj] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     };
 
-    unsigned long long accA = 0;  // sum of ReadCount over the reads finished here (group-uniform)
-    uint32_t accN = 0;            // their number
+    uint32_t any_done = 0;  // this warp finished a read
     const uint32_t units = (uint32_t)((p.N + RPW - 1) / RPW);
     const uint32_t gw = blockIdx.x * kFrWarps + warp, nw = gridDim.x * kFrWarps;
-    uint64_t b_cur = 0, b_nxt = 0, x0_nxt = 0, x1_nxt = 0;
-    uint32_t L_cur = 0, L_nxt = 0;
-    uint4 blk[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) blk[j] = make_uint4(0, 0, 0, 0);
+    uint64_t b_nxt = 0, x0_nxt = 0, x1_nxt = 0;
+    uint32_t L_cur = 0, L_nxt = 0, a_cur = 0;
     if (gw < units) {
         uint64_t x0, x1;
         where(gw * RPW + grp, x0, x1);
-        resolve(x0, x1, b_cur, L_cur);
-        load_blocks(b_cur, L_cur, blk);
+        resolve(x0, x1, b_nxt, L_cur);
+        stage_blocks(b_nxt, L_cur, lane32);
+        a_cur = (base_lo + (uint32_t)b_nxt) & (kFrNB - 1u);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     where((gw + nw) * RPW + grp, x0_nxt, x1_nxt);
-    const uint32_t mystage32 = stage32 + (uint32_t)grp * WIN + 16u * (uint32_t)gl;  // this lane's block j sits JS j bytes further
+    uint32_t buf = 0;  // 0 / 2048: which half of the warp's staging area holds the current reads
     for (uint32_t u = gw; u < units; u += nw) {
-        // the blocks loaded an iteration ago go to the staging area (every later step reads them from there), and the same
-        // registers take the next read's blocks: those loads are in flight for the whole iteration
-#pragma unroll
-        for (int j = 0; j < 4; j++) sts_v4(mystage32 + JS * j, blk[j]);  // (the previous iteration's readers are past their __syncwarp)
+        // the next reads' blocks start their way into the other half (its readers of two iterations ago are past their
+        // __syncwarp); the current ones have arrived when all but that newest group are complete
         resolve(x0_nxt, x1_nxt, b_nxt, L_nxt);
-        load_blocks(b_nxt, L_nxt, blk);
+        stage_blocks(b_nxt, L_nxt, lane32 + (buf ^ 2048u));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t stage32 = warp32 + buf;
+        const uint32_t mystage32 = lane32 + buf;  // this lane's block j sits JS j bytes further
+        const uint32_t a_nxt = (base_lo + (uint32_t)b_nxt) & (kFrNB - 1u);
         where((u + 2 * nw) * RPW + grp, x0_nxt, x1_nxt);
 
         const uint32_t r = u * RPW + grp;
-        const uint32_t a = (base_lo + (uint32_t)b_cur) & (kFrNB - 1u);  // the read starts at byte a of its window
+        const uint32_t a = a_cur;  // the read starts at byte a of its window
         const bool in_batch = r < N32;
         const uint32_t L = (in_batch && a + L_cur <= WIN) ? L_cur : 0u;
         const uint32_t read_count = (in_batch && q.read_count) ? q.read_count[r] : 1u;
@@ -297,57 +297,59 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         const int fo = (int)(kFrGuardF + 16u * (uint32_t)gl) - (d & ~15);
         const uint32_t fa32 = fc32 + ((uint32_t)d & 15u) * g.sf;
         const int e_hi = (int)(a + L) - 16 * gl, e_lo = (int)a - 16 * gl;  // the read covers bytes [e_lo, e_hi) counted from this lane's first block
-        FirstNz fp;
-        LastNz lf;
         // blocks past the longest read of the warp are skipped by all lanes
         const uint32_t nb_max = __reduce_max_sync(FULL_MASK, (a + L + 15u) >> 4);
+        // window offsets of the group's first difference from P and last difference from F
+        uint32_t gp;
+        int gf;
+        {
+            FirstNz fp;
+            LastNz lf;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (j >= 2 && (uint32_t)(G * j) >= nb_max) continue;
-            const uint4 wv = lds_v4(mystage32 + JS * j);
-            uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)(JS * j), 0), 16));
-            if (j == 0) {  // only the first block of a lane can start in front of the read (a < 64)
-                const uint4 kl = lds_v4(keep32 + 16u * (uint32_t)min(max(e_lo, 0), 16));
-                kp = make_uint4(kp.x & ~kl.x, kp.y & ~kl.y, kp.z & ~kl.z, kp.w & ~kl.w);
+            for (int j = 0; j < 4; j++) {
+                if (j >= 2 && (uint32_t)(G * j) >= nb_max) continue;
+                const uint4 wv = lds_v4(mystage32 + JS * j);
+                uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)(JS * j), 0), 16));
+                if (j == 0) {  // only the first block of a lane can start in front of the read (a < 64)
+                    const uint4 kl = lds_v4(keep32 + 16u * (uint32_t)min(max(e_lo, 0), 16));
+                    kp = make_uint4(kp.x & ~kl.x, kp.y & ~kl.y, kp.z & ~kl.z, kp.w & ~kl.w);
+                }
+                const uint4 pw = lds_v4(pa32 + (uint32_t)min(po + (int)(JS * j), p_top));
+                const uint4 fw = lds_v4(fa32 + (uint32_t)min(max(fo + (int)(JS * j), 0), f_top));
+                const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+                const uint32_t xp[4] = {(w[0] ^ pw.x) & kp.x, (w[1] ^ pw.y) & kp.y, (w[2] ^ pw.z) & kp.z, (w[3] ^ pw.w) & kp.w};
+                const uint32_t xf[4] = {(w[0] ^ fw.x) & kp.x, (w[1] ^ fw.y) & kp.y, (w[2] ^ fw.z) & kp.z, (w[3] ^ fw.w) & kp.w};
+                fp.block(j, xp);
+                lf.block(j, xf);
             }
-            const uint4 pw = lds_v4(pa32 + (uint32_t)min(po + (int)(JS * j), p_top));
-            const uint4 fw = lds_v4(fa32 + (uint32_t)min(max(fo + (int)(JS * j), 0), f_top));
-            const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-            const uint32_t xp[4] = {(w[0] ^ pw.x) & kp.x, (w[1] ^ pw.y) & kp.y, (w[2] ^ pw.z) & kp.z, (w[3] ^ pw.w) & kp.w};
-            const uint32_t xf[4] = {(w[0] ^ fw.x) & kp.x, (w[1] ^ fw.y) & kp.y, (w[2] ^ fw.z) & kp.z, (w[3] ^ fw.w) & kp.w};
-            fp.block(j, xp);
-            lf.block(j, xf);
-        }
-        // window offsets of the lane's first / last difference, then of the group's
-        const uint32_t wp = fp.yo ? JS * fp.jb + 16u * (uint32_t)gl + fp.byte_in_block() : 0x7fffffffu;
-        const int wf = lf.yo ? (int)(JS * lf.jb + 16u * (uint32_t)gl + lf.byte_in_block()) : -1;
-        uint32_t gp = wp;
-        int gf = wf;
+            gp = fp.yo ? JS * fp.jb + 16u * (uint32_t)gl + fp.byte_in_block() : 0x7fffffffu;
+            gf = lf.yo ? (int)(JS * lf.jb + 16u * (uint32_t)gl + lf.byte_in_block()) : -1;
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {  // (a REDUX over part of a warp runs once per group)
-            gp = min(gp, __shfl_xor_sync(FULL_MASK, gp, o));
-            gf = max(gf, __shfl_xor_sync(FULL_MASK, gf, o));
+            for (int o = G / 2; o > 0; o >>= 1) {  // (a REDUX over part of a warp runs once per group)
+                gp = min(gp, __shfl_xor_sync(FULL_MASK, gp, o));
+                gf = max(gf, __shfl_xor_sync(FULL_MASK, gf, o));
+            }
         }
         const uint32_t t = min(gp != 0x7fffffffu ? gp - a : L, min(L, Lp));             // common prefix of R and P
         const uint32_t s = min(gf >= 0 ? L - 1u - ((uint32_t)gf - a) : L, min(L, Lf));  // common suffix of R and F
+        const uint32_t rstage32 = stage32 + (uint32_t)grp * WIN + a;  // the read's first character in the staging area
         const uint32_t bp = s_pcum[t], bs = s_fsuf[s];
         const bool t0_all = s == L && L == Lf, pe_all = t == L && L == Lp;
         const bool overlap = t + s >= L;
         const uint32_t n_mid = overlap ? 0u : L - s - t;
-        // findJSS answers len - 1 for R == F, else bs (-1 is possible only with bs == 0: left to the general path); a junction
-        // start on the first site of an alternative template's region is decided by computeAltEditing (align.go:183-235);
-        // a junction longer than mid_cap may hold a saturating run
+        // findJSS answers len - 1 when every count equals FE's, else bs (-1 is possible only with bs == 0: left to the general
+        // path); a junction start on the first site of an alternative template's region is decided by computeAltEditing
+        // (align.go:183-235); a junction longer than mid_cap may hold a saturating run
         const int junc_start = t0_all ? (int)tm : (int)bs;
         const bool cand = L != 0u && (t0_all || bs >= 1u) && !(K > 2 && s_alt[junc_start] != 0) && n_mid <= g.mid_cap;
 
         // ---- the characters between prefix and suffix against Bases[bp ..): the whole warp, one read after the other ----
         bool mid_ok = true;
         uint32_t mid_bases = 0;
-        __syncwarp();
         {
             // (junction length | bases in front of it << 16) and the staged address of its first character
             const uint32_t my_nb = (cand ? n_mid : 0u) | (bp << 16);
-            const uint32_t my_at = stage32 + (uint32_t)grp * WIN + a + t;
+            const uint32_t my_at = rstage32 + t;
 #pragma unroll
             for (int k = 0; k < RPW; k++) {
                 const uint32_t nb = __shfl_sync(FULL_MASK, my_nb, k * G);
@@ -406,15 +408,18 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
                 dst[1] = make_uint4(read_count, 0u, tm, js_off);
                 dst[2] = make_uint4(js_len, tm | (tm << 16), 0u, L);
             }
-            accA += read_count;
-            accN += 1u;
-            // cmd/treat/handlers.go:203-215: three histograms, one lane each
-            if (sum_len && gl < 3 && !(edit_stop + off == q.t.tmpl_edit_stop && junc_len == 0)) {
+            any_done = 1u;
+            // cmd/treat/handlers.go:203-215: three histograms, one lane each (lanes 0..2); the sums the header counters are made
+            // of (cmd/treat/stats.go:140-187) in the CTA's unused header slots: lane 3 ReadCount, lane 4 reads
+            if (sum_len) {
+                const bool hist = gl < 3 && !(edit_stop + off == q.t.tmpl_edit_stop && junc_len == 0);
                 const uint32_t bin = gl == 0 ? (uint32_t)(edit_stop + 2) : gl == 1 ? (uint32_t)junc_len : (uint32_t)(junc_end + 2);
-                if (bin < q.bins) {
-                    const uint32_t idx = TREAT_B200_SUMMARY_HEADER + (uint32_t)gl * q.bins + bin;
-                    const uint32_t old = atomicAdd(&sum_lo[idx], read_count);
-                    if (old + read_count < old) atomicAdd(&sum_hi[idx], 1u);
+                const bool head = gl == 3 || gl == 4;
+                if ((hist && bin < q.bins) || head) {
+                    const uint32_t idx = head ? (uint32_t)gl - 3u : TREAT_B200_SUMMARY_HEADER + (uint32_t)gl * q.bins + bin;
+                    const uint32_t val = (head && (gl & 1) == 0) ? 1u : read_count;
+                    const uint32_t old = atomicAdd(&sum_lo[idx], val);
+                    if (old + val < old) atomicAdd(&sum_hi[idx], 1u);
                 }
             }
             if (q.ops && !q.ops_gapped_only) {  // m match columns: an all-zero row
@@ -432,21 +437,22 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
                 if (in_batch && !ok && gl == 0) f.rest[at + (uint32_t)__popc(todo & lt)] = r;
             }
         }
-        b_cur = b_nxt, L_cur = L_nxt;
+        L_cur = L_nxt, a_cur = a_nxt;
+        buf ^= 2048u;
     }
-    // the header counters of the reads finished above (cmd/treat/stats.go:140-187): none has a gap or a mismatch
-    if (G < 32) {
-#pragma unroll
-        for (int o = 16; o >= G; o >>= 1) {
-            accA += __shfl_xor_sync(FULL_MASK, accA, o);
-            accN += __shfl_xor_sync(FULL_MASK, accN, o);
-        }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    {
+        const bool warp_done = __any_sync(FULL_MASK, any_done != 0u);
+        if (lane == 0 && warp_done) atomicMax(&p.scalars[0], tm);
     }
-    if (lane == 0 && accN) atomicMax(&p.scalars[0], tm);
+    // the header counters of the reads finished above (cmd/treat/stats.go:140-187), from the CTA's two sums: Total and Std
+    // weighted by ReadCount, then per read, reads aligned, DP cells; none of these reads has a gap or a mismatch
     unsigned long long ctr = 0;
-    if (sum_len) {
-        const unsigned long long Nn = accN;
-        ctr = (lane == 0 || lane == 1) ? accA : (lane == 7 || lane == 8 || lane == 14) ? Nn
+    __syncthreads();
+    if (sum_len && threadIdx.x < 32) {
+        const unsigned long long A = (unsigned long long)sum_lo[0] | ((unsigned long long)sum_hi[0] << 32);
+        const unsigned long long Nn = (unsigned long long)sum_lo[1] | ((unsigned long long)sum_hi[1] << 32);
+        ctr = (lane == 0 || lane == 1) ? A : (lane == 7 || lane == 8 || lane == 14) ? Nn
               : lane == 15 ? Nn * (unsigned long long)tm * (unsigned long long)tm : 0ull;
     }
     flush_summary(q, sum_len, sum_lo, sum_hi, lane, ctr);
@@ -485,7 +491,7 @@ static int launch_frontier_kernel(Kern kern, const PackParams &p, const AlignPar
 int launch_frontier(const PackParams &p, const AlignParams &q, const FrontierParams &f, int num_sms, int max_smem_optin, void *stream)
 {
     const uint32_t sum_len = q.summary ? TREAT_B200_SUMMARY_HEADER + 3u * q.bins : 0u;
-    const size_t smem = (size_t)f.g.image_bytes + align16(8u * sum_len) + (size_t)kFrWarps * 2048u + 512u;  // + pad: the junction check reads whole rounds of 32 characters
+    const size_t smem = (size_t)f.g.image_bytes + align16(8u * sum_len) + (size_t)kFrWarps * 4096u + 512u;  // + pad: the junction check reads whole rounds of 32 characters
     const int G = frontier_group(f.g);
     if (G == 0 || smem > (size_t)max_smem_optin) return -1000;
     const bool span = p.begin != nullptr;
