@@ -43,11 +43,12 @@ namespace {
 constexpr uint32_t kFrNB = 64;      // raw characters per lane
 constexpr uint32_t kFrGuardP = 64;  // zero bytes in front of P inside a shifted copy (a block of P starts up to 48 bytes early)
 constexpr uint32_t kFrGuardF = 16;  // zero block in front of F (block offsets are clamped into the copy)
+// 16 warps x 2 CTAs: 64 registers (no spills), 32 resident warps per SM, one template image per 16 warps
 #ifndef TREAT_B200_FR_WARPS
-#define TREAT_B200_FR_WARPS 8
+#define TREAT_B200_FR_WARPS 16
 #endif
 #ifndef TREAT_B200_FR_MIN_CTAS
-#define TREAT_B200_FR_MIN_CTAS 3
+#define TREAT_B200_FR_MIN_CTAS 2
 #endif
 constexpr int kFrWarps = TREAT_B200_FR_WARPS;
 __host__ __device__ constexpr uint32_t fr_copy_bytes(uint32_t guard, uint32_t len) { return guard + ((15u + len + 15u) & ~15u) + 16u; }
