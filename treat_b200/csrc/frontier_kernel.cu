@@ -40,16 +40,18 @@
 namespace treat_b200 {
 
 namespace {
-constexpr uint32_t kFrNB = 64;      // raw characters per lane
+constexpr uint32_t kFrNB = 64;      // a read's window starts at a 64-byte boundary of memory
 constexpr uint32_t kFrGuardP = 64;  // zero bytes in front of P inside a shifted copy (a block of P starts up to 48 bytes early)
 constexpr uint32_t kFrGuardF = 16;  // zero block in front of F (block offsets are clamped into the copy)
-// 16 warps x 2 CTAs: 64 registers (no spills), 32 resident warps per SM, one template image per 16 warps
+// at most this many warps per CTA (each owns 8 KB of staging area; the launcher takes as many as fit next to the image)
+// (one CTA per SM: one copy of the template image, the rest of the shared memory stages reads -- 24 warps with RPS12)
 #ifndef TREAT_B200_FR_WARPS
-#define TREAT_B200_FR_WARPS 16
+#define TREAT_B200_FR_WARPS 24
 #endif
 #ifndef TREAT_B200_FR_MIN_CTAS
-#define TREAT_B200_FR_MIN_CTAS 2
+#define TREAT_B200_FR_MIN_CTAS 1
 #endif
+constexpr uint32_t kFrHalf = 4096;  // bytes of one half of a warp's staging area: 32 / G reads x 16 G NBL bytes, NBL = 8
 constexpr int kFrWarps = TREAT_B200_FR_WARPS;
 __host__ __device__ constexpr uint32_t fr_copy_bytes(uint32_t guard, uint32_t len) { return guard + ((15u + len + 15u) & ~15u) + 16u; }
 }  // namespace
@@ -80,7 +82,7 @@ bool build_frontier_image(const uint8_t *bases, int m, const uint32_t *fe, const
     }
     if (max_fe + max_pe > 200u) return false;  // a run in the read = a piece of a P run + the junction + a piece of an F run: stays below 255
     const uint32_t Lf = (uint32_t)F.size(), Lp = (uint32_t)P.size();
-    if (std::max(Lf, Lp) + 16u > 32u * kFrNB - (kFrNB - 1u)) return false;
+    if (std::max(Lf, Lp) + 16u > 2048u - (kFrNB - 1u)) return false;
     {
         int k = 0;
         for (int i = (int)Lf - 1; i >= 0; i--)
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
                                                                                     const __grid_constant__ FrontierParams f)
 {
     constexpr int RPW = 32 / G;
-    constexpr uint32_t WIN = kFrNB * G;   // bytes of a read's window (64 G, 64-byte aligned in memory)
+    constexpr int NBL = 8;                // 16-byte blocks per lane
+    constexpr uint32_t WIN = 16u * G * NBL;  // bytes of a read's window (64-byte aligned in memory)
     constexpr uint32_t JS = 16u * G;      // a lane's blocks are JS bytes apart
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -193,8 +196,8 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     for (uint32_t i = threadIdx.x; i < 2 * sum_len; i += blockDim.x) sum_lo[i] = 0u;
     __syncthreads();
     const uint32_t s32 = smem_u32(smem);
-    const uint32_t warp32 = s32 + g.image_bytes + sum_bytes + (uint32_t)warp * 4096u;     // two halves of 2 KB: the reads being worked on, the next ones
-    const uint32_t lane32 = warp32 + (uint32_t)grp * (kFrNB * G) + 16u * (uint32_t)gl;     // this lane's first block inside a half
+    const uint32_t warp32 = s32 + g.image_bytes + sum_bytes + (uint32_t)warp * (2u * kFrHalf);  // two halves: the reads being worked on, the next ones
+    const uint32_t lane32 = warp32 + (uint32_t)grp * WIN + 16u * (uint32_t)gl;     // this lane's first block inside a half
     const uint32_t keep32 = s32 + g.off_keep, pc32 = s32 + g.off_p, fc32 = s32 + g.off_f;
     const uint16_t *s_pcum = reinterpret_cast<const uint16_t *>(smem + g.off_pcum), *s_fsuf = reinterpret_cast<const uint16_t *>(smem + g.off_fsuf);
     const uint16_t *s_ppos = reinterpret_cast<const uint16_t *>(smem + g.off_ppos), *s_ftail = reinterpret_cast<const uint16_t *>(smem + g.off_ftail);
@@ -235,13 +238,13 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         if (w0 >= lo && w0 + (int64_t)(16u * nb16) <= hi) {
             const uint8_t *src = p.seqs + w0 + 16 * gl;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int j = 0; j < NBL; j++)
                 if ((uint32_t)(G * j + gl) < nb16)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst32 + JS * j), "l"(src + JS * j) : "memory");
             return;
         }
 #pragma unroll 1
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NBL; j++) {
 #pragma unroll 1
             for (int c4 = 0; c4 < 4; c4++) {
                 uint32_t w = 0u;
@@ -255,9 +258,10 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         }
     };
 
-    uint32_t any_done = 0;  // this warp finished a read
+    uint32_t n_done = 0;  // reads this warp finished (warp-uniform)
     const uint32_t units = (uint32_t)((p.N + RPW - 1) / RPW);
-    const uint32_t gw = blockIdx.x * kFrWarps + warp, nw = gridDim.x * kFrWarps;
+    const uint32_t wpc = blockDim.x >> 5;  // warps per CTA: as many as the shared memory holds next to the image
+    const uint32_t gw = blockIdx.x * wpc + warp, nw = gridDim.x * wpc;
     uint64_t b_nxt = 0, x0_nxt = 0, x1_nxt = 0;
     uint32_t L_cur = 0, L_nxt = 0, a_cur = 0;
     if (gw < units) {
@@ -269,12 +273,12 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     where((gw + nw) * RPW + grp, x0_nxt, x1_nxt);
-    uint32_t buf = 0;  // 0 / 2048: which half of the warp's staging area holds the current reads
+    uint32_t buf = 0;  // 0 / kFrHalf: which half of the warp's staging area holds the current reads
     for (uint32_t u = gw; u < units; u += nw) {
         // the next reads' blocks start their way into the other half (its readers of two iterations ago are past their
         // __syncwarp); the current ones have arrived when all but that newest group are complete
         resolve(x0_nxt, x1_nxt, b_nxt, L_nxt);
-        stage_blocks(b_nxt, L_nxt, lane32 + (buf ^ 2048u));
+        stage_blocks(b_nxt, L_nxt, lane32 + (buf ^ kFrHalf));
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             FirstNz fp;
             LastNz lf;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NBL; j++) {
                 if (j >= 2 && (uint32_t)(G * j) >= nb_max) continue;
                 const uint4 wv = lds_v4(mystage32 + JS * j);
                 uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)(JS * j), 0), 16));
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             // (junction length | bases in front of it << 16) and the staged address of its first character
             const uint32_t my_nb = (cand ? n_mid : 0u) | (bp << 16);
             const uint32_t my_at = rstage32 + t;
-#pragma unroll
+#pragma unroll 2
             for (int k = 0; k < RPW; k++) {
                 const uint32_t nb = __shfl_sync(FULL_MASK, my_nb, k * G);
                 int left = (int)(nb & 0xffffu);
@@ -409,16 +413,16 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
                 dst[1] = make_uint4(read_count, 0u, tm, js_off);
                 dst[2] = make_uint4(js_len, tm | (tm << 16), 0u, L);
             }
-            any_done = 1u;
             // cmd/treat/handlers.go:203-215: three histograms, one lane each (lanes 0..2); the sums the header counters are made
-            // of (cmd/treat/stats.go:140-187) in the CTA's unused header slots: lane 3 ReadCount, lane 4 reads
+            // of (cmd/treat/stats.go:140-187): lane 3 adds ReadCount to the CTA's unused header slot 0, the reads are counted
+            // per warp in a register
             if (sum_len) {
                 const bool hist = gl < 3 && !(edit_stop + off == q.t.tmpl_edit_stop && junc_len == 0);
                 const uint32_t bin = gl == 0 ? (uint32_t)(edit_stop + 2) : gl == 1 ? (uint32_t)junc_len : (uint32_t)(junc_end + 2);
-                const bool head = gl == 3 || gl == 4;
+                const bool head = gl == 3;
                 if ((hist && bin < q.bins) || head) {
-                    const uint32_t idx = head ? (uint32_t)gl - 3u : TREAT_B200_SUMMARY_HEADER + (uint32_t)gl * q.bins + bin;
-                    const uint32_t val = (head && (gl & 1) == 0) ? 1u : read_count;
+                    const uint32_t idx = head ? 0u : TREAT_B200_SUMMARY_HEADER + (uint32_t)gl * q.bins + bin;
+                    const uint32_t val = read_count;
                     const uint32_t old = atomicAdd(&sum_lo[idx], val);
                     if (old + val < old) atomicAdd(&sum_hi[idx], 1u);
                 }
@@ -428,6 +432,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
                 for (int wi = gl; wi < (int)(q.ops_stride / 4); wi += G) go[wi] = 0u;
             }
         }
+        n_done += (uint32_t)__popc(__ballot_sync(FULL_MASK, ok && gl == 0));
         // everything else goes to the general path, one list append per warp
         {
             const uint32_t todo = __ballot_sync(FULL_MASK, in_batch && !ok && gl == 0);
@@ -439,12 +444,12 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             }
         }
         L_cur = L_nxt, a_cur = a_nxt;
-        buf ^= 2048u;
+        buf ^= kFrHalf;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    {
-        const bool warp_done = __any_sync(FULL_MASK, any_done != 0u);
-        if (lane == 0 && warp_done) atomicMax(&p.scalars[0], tm);
+    if (lane == 0 && n_done) {
+        atomicMax(&p.scalars[0], tm);
+        if (sum_len) atomicAdd(&sum_lo[1], n_done);  // (a launch holds < 2^31 reads)
     }
     // the header counters of the reads finished above (cmd/treat/stats.go:140-187), from the CTA's two sums: Total and Std
     // weighted by ReadCount, then per read, reads aligned, DP cells; none of these reads has a gap or a mismatch
@@ -465,58 +470,64 @@ bool frontier_applies(const PackParams &p, const AlignParams &q, const FrontierP
            p.edit_base >= 'A' && p.edit_base <= 'Z';
 }
 
-// lanes per read: the smallest group whose pass (64 G - 63 characters at the worst alignment) holds reads a little longer
-// than the longer template string
+// lanes per read (8 blocks of 16 bytes per lane): the smallest window (64-byte aligned, so 63 bytes may be lost in front)
+// that holds reads a little longer than the longer template string
 static int frontier_group(const FrontierGeom &g)
 {
     const uint32_t need = std::max(g.Lf, g.Lp) + 16u;
-    for (int G : {8, 16, 32})
-        if (need <= (uint32_t)G * kFrNB - (kFrNB - 1u)) return G;
+    for (int G : {4, 8, 16})
+        if (need <= (uint32_t)G * 128u - (kFrNB - 1u)) return G;
     return 0;
 }
 
 template <typename Kern>
-static int launch_frontier_kernel(Kern kern, const PackParams &p, const AlignParams &q, const FrontierParams &f, int rpw, size_t smem, int num_sms,
-                                  void *stream)
+static int launch_frontier_kernel(Kern kern, const PackParams &p, const AlignParams &q, const FrontierParams &f, int rpw, size_t fixed, int max_smem,
+                                  int num_sms, void *stream)
 {
+    // as many warps per CTA as the planned number of CTAs per SM can stage next to their images (one CTA when the image is large)
+    const size_t share = ((size_t)max_smem + 1024) / TREAT_B200_FR_MIN_CTAS;  // (the driver keeps 1 KB per resident CTA)
+    int warps = (int)std::min<size_t>(kFrWarps, (share > fixed + 1024 ? (share - 1024 - fixed) / (2 * kFrHalf) : 0));
+    if (warps < 4) warps = (int)std::min<size_t>(kFrWarps, ((size_t)max_smem - fixed) / (2 * kFrHalf));
+    if (warps < 1) return -1000;
+    const size_t smem = fixed + (size_t)warps * 2 * kFrHalf;
     const uint64_t units = (p.N + rpw - 1) / rpw;
-    uint64_t blocks = (units + kFrWarps - 1) / kFrWarps;
-    const int per_sm = occupancy_cached((const void *)kern, kFrWarps * 32, smem);
+    uint64_t blocks = (units + warps - 1) / warps;
+    const int per_sm = occupancy_cached((const void *)kern, warps * 32, smem);
     const uint64_t cap = (uint64_t)num_sms * per_sm;  // persistent grid
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return 0;
-    kern<<<(unsigned)blocks, kFrWarps * 32, smem, (cudaStream_t)stream>>>(p, q, f);
+    kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p, q, f);
     return (int)cudaGetLastError();
 }
 
 int launch_frontier(const PackParams &p, const AlignParams &q, const FrontierParams &f, int num_sms, int max_smem_optin, void *stream)
 {
     const uint32_t sum_len = q.summary ? TREAT_B200_SUMMARY_HEADER + 3u * q.bins : 0u;
-    const size_t smem = (size_t)f.g.image_bytes + align16(8u * sum_len) + (size_t)kFrWarps * 4096u + 512u;  // + pad: the junction check reads whole rounds of 32 characters
+    const size_t fixed = (size_t)f.g.image_bytes + align16(8u * sum_len) + 512u;  // + pad: the junction check reads whole rounds of 32 characters
     const int G = frontier_group(f.g);
-    if (G == 0 || smem > (size_t)max_smem_optin) return -1000;
+    if (G == 0 || fixed + 2 * kFrHalf > (size_t)max_smem_optin) return -1000;
     const bool span = p.begin != nullptr;
     switch (G) {
+    case 4:
+        return span ? launch_frontier_kernel(k_frontier<4, true>, p, q, f, 8, fixed, max_smem_optin, num_sms, stream)
+                    : launch_frontier_kernel(k_frontier<4, false>, p, q, f, 8, fixed, max_smem_optin, num_sms, stream);
     case 8:
-        return span ? launch_frontier_kernel(k_frontier<8, true>, p, q, f, 4, smem, num_sms, stream)
-                    : launch_frontier_kernel(k_frontier<8, false>, p, q, f, 4, smem, num_sms, stream);
-    case 16:
-        return span ? launch_frontier_kernel(k_frontier<16, true>, p, q, f, 2, smem, num_sms, stream)
-                    : launch_frontier_kernel(k_frontier<16, false>, p, q, f, 2, smem, num_sms, stream);
+        return span ? launch_frontier_kernel(k_frontier<8, true>, p, q, f, 4, fixed, max_smem_optin, num_sms, stream)
+                    : launch_frontier_kernel(k_frontier<8, false>, p, q, f, 4, fixed, max_smem_optin, num_sms, stream);
     default:
-        return span ? launch_frontier_kernel(k_frontier<32, true>, p, q, f, 1, smem, num_sms, stream)
-                    : launch_frontier_kernel(k_frontier<32, false>, p, q, f, 1, smem, num_sms, stream);
+        return span ? launch_frontier_kernel(k_frontier<16, true>, p, q, f, 2, fixed, max_smem_optin, num_sms, stream)
+                    : launch_frontier_kernel(k_frontier<16, false>, p, q, f, 2, fixed, max_smem_optin, num_sms, stream);
     }
 }
 
 int configure_frontier_kernels(int max_smem_optin)
 {
-    cudaError_t ce = cudaFuncSetAttribute(k_frontier<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    cudaError_t ce = cudaFuncSetAttribute(k_frontier<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_frontier<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
     return (int)ce;
 }
 
