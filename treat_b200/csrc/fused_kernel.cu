@@ -423,10 +423,12 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
     // where read r lies, as loaded (no arithmetic on the loaded values here: they are used one iteration later)
     // the reads of this launch: all of them, or the ones k_frontier left (p.sel: their indices, *p.sel_count of them)
     const uint32_t total = p.sel ? min(*p.sel_count, N32) : N32;
-    auto where = [&](uint32_t i, uint64_t &x0, uint64_t &x1) {
+    // which read is item i of the launch (0xffffffff: past the end); with a list this is a load of its own, issued one pass
+    // before the read's offsets are
+    auto item = [&](uint32_t i) -> uint32_t { return i < total ? (p.sel ? p.sel[i] : i) : 0xffffffffu; };
+    auto where = [&](uint32_t r, uint64_t &x0, uint64_t &x1) {
         x0 = x1 = SPAN ? 0ull : p.off_bias;
-        if (i >= total) return;
-        const uint32_t r = p.sel ? p.sel[i] : i;
+        if (r == 0xffffffffu) return;
         if (SPAN) {
             x0 = p.begin[r];
             x1 = p.len[r];
@@ -475,22 +477,26 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
     uint64_t b_cur = 0, b_nxt = 0, x0_nxt = 0, x1_nxt = 0;
     uint32_t L_cur = 0, L_nxt = 0;
     uint4 blkA = make_uint4(0, 0, 0, 0), blkB = blkA;
+    uint32_t r_cur = 0xffffffffu, r_nxt = 0xffffffffu, r_nn = 0xffffffffu;  // the reads of this pass, the next one, the one after
     if (gw < units) {
         uint64_t x0, x1;
-        where(gw * RPW + grp, x0, x1);
+        r_cur = item(gw * RPW + grp);
+        where(r_cur, x0, x1);
         resolve(x0, x1, b_cur, L_cur);
         load_blocks(b_cur, L_cur, blkA, blkB);
     }
-    where((gw + nw) * RPW + grp, x0_nxt, x1_nxt);  // past the end: an empty read
+    r_nxt = item((gw + nw) * RPW + grp);
+    where(r_nxt, x0_nxt, x1_nxt);  // past the end: an empty read
+    r_nn = item((gw + 2 * nw) * RPW + grp);
     for (uint32_t u = gw; u < units; u += nw) {
         uint4 nA, nB;
         resolve(x0_nxt, x1_nxt, b_nxt, L_nxt);
         load_blocks(b_nxt, L_nxt, nA, nB);
-        where((u + 2 * nw) * RPW + grp, x0_nxt, x1_nxt);
+        where(r_nn, x0_nxt, x1_nxt);
+        const uint32_t r_ahead = item((u + 3 * nw) * RPW + grp);
 
-        const uint32_t ri = u * RPW + grp;
-        const bool in_batch = ri < total;
-        const uint32_t r = (p.sel && in_batch) ? p.sel[ri] : ri;
+        const bool in_batch = r_cur != 0xffffffffu;
+        const uint32_t r = in_batch ? r_cur : 0u;
         const uint32_t a = (base_lo + (uint32_t)b_cur) & 31u;  // the read starts at character a of lane 0's blocks
         const bool too_long = ((a + L_cur + 31u) >> 5) > (uint32_t)G;
         const bool valid = in_batch && !too_long;
@@ -726,6 +732,7 @@ __global__ void __launch_bounds__(kF2Warps * 32, TREAT_B200_F2_MIN_CTAS) k_pack_
         }
         __syncwarp();
         b_cur = b_nxt, L_cur = L_nxt, blkA = nA, blkB = nB;
+        r_cur = r_nxt, r_nxt = r_nn, r_nn = r_ahead;
     }
     warp_max_n = __reduce_max_sync(FULL_MASK, warp_max_n);
     warp_sat = __reduce_or_sync(FULL_MASK, warp_sat);
@@ -788,7 +795,9 @@ int launch_pack_finish(const PackParams &pack, const AlignParams &planned, int n
     if (fixed + per_warp > (size_t)max_smem_optin) return -1000;
     const int warps = (int)std::min<size_t>(kFusedWarps, ((size_t)max_smem_optin - fixed) / per_warp);  // very long reads: fewer warps
     const size_t smem = fixed + per_warp * warps;
-    const uint64_t units = p.sel ? std::min<uint64_t>(p.N, (uint64_t)num_sms * 64) : p.N;  // a list: its length is on the device
+    // a list: its length is on the device and it is short (reads longer than a pass of k_pack_finish2): one CTA per SM, so that
+    // the CTAs' set-up does not cost more than the reads
+    const uint64_t units = p.sel ? std::min<uint64_t>(p.N, (uint64_t)num_sms * warps) : p.N;
     if (p.begin) return launch_fused(k_pack_finish<true>, p, q, warps, units, warps * 32, smem, num_sms, stream);
     return launch_fused(k_pack_finish<false>, p, q, warps, units, warps * 32, smem, num_sms, stream);
 }
