@@ -183,6 +183,7 @@ struct FrontierGeom {
     uint32_t sp, sf;       // bytes per shifted copy of P / F
     uint32_t Lp, Lf, tm;   // raw lengths of the pre-edited / fully edited strings, template bases
     uint32_t mid_cap;      // longest junction (raw characters) that cannot hold a saturating edit-base run
+    uint32_t G, ws;        // lanes per read (4 / 8 / 16) and bytes between two reads' windows in a warp's staging area
 };
 struct FrontierParams {
     const uint8_t *image;

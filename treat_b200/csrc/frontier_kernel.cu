@@ -43,15 +43,14 @@ namespace {
 constexpr uint32_t kFrNB = 64;      // a read's window starts at a 64-byte boundary of memory
 constexpr uint32_t kFrGuardP = 64;  // zero bytes in front of P inside a shifted copy (a block of P starts up to 48 bytes early)
 constexpr uint32_t kFrGuardF = 16;  // zero block in front of F (block offsets are clamped into the copy)
-// at most this many warps per CTA (each owns 8 KB of staging area; the launcher takes as many as fit next to the image)
-// (one CTA per SM: one copy of the template image, the rest of the shared memory stages reads -- 24 warps with RPS12)
+// at most this many warps per CTA (each owns two staging halves of 32 / G windows; the launcher takes as many as fit next to
+// the image) (one CTA per SM: one copy of the template image, the rest of the shared memory stages reads -- 24 warps with RPS12)
 #ifndef TREAT_B200_FR_WARPS
 #define TREAT_B200_FR_WARPS 24
 #endif
 #ifndef TREAT_B200_FR_MIN_CTAS
 #define TREAT_B200_FR_MIN_CTAS 1
 #endif
-constexpr uint32_t kFrHalf = 4096;  // bytes of one half of a warp's staging area: 32 / G reads x 16 G NBL bytes, NBL = 8
 constexpr int kFrWarps = TREAT_B200_FR_WARPS;
 __host__ __device__ constexpr uint32_t fr_copy_bytes(uint32_t guard, uint32_t len) { return guard + ((15u + len + 15u) & ~15u) + 16u; }
 }  // namespace
@@ -89,6 +88,22 @@ bool build_frontier_image(const uint8_t *bases, int m, const uint32_t *fe, const
             if (F[i] != edit_base) ftail[++k] = (uint16_t)(Lf - 1 - i);  // characters of F behind base m - k
     }
     g.Lf = Lf, g.Lp = Lp, g.tm = (uint32_t)m;
+    // G lanes per read, 8 blocks of 16 bytes per lane: the smallest window (64-byte aligned, so 63 bytes may be lost in
+    // front) that holds reads a little longer than the longer template string.  Windows of one warp lie ws bytes apart in the
+    // staging area: enough for such a read, and an odd multiple of 64 when two reads share a quarter-warp (G = 4), so that
+    // their 64-byte rows fall into different halves of the 32 banks
+    {
+        const uint32_t need = std::max(Lf, Lp) + 16u + (kFrNB - 1u);
+        g.G = 0;
+        for (uint32_t G : {4u, 8u, 16u})
+            if (need <= G * 128u) {
+                g.G = G;
+                break;
+            }
+        if (g.G == 0) return false;
+        g.ws = (need + 63u) & ~63u;
+        if (g.G == 4u && ((g.ws >> 6) & 1u) == 0u) g.ws += 64u;
+    }
     g.mid_cap = 254u - max_fe - max_pe;
     g.sp = fr_copy_bytes(kFrGuardP, Lp), g.sf = fr_copy_bytes(kFrGuardF, Lf);
     uint32_t o = 0;
@@ -126,49 +141,6 @@ bool build_frontier_image(const uint8_t *bases, int m, const uint32_t *fe, const
 
 namespace {
 
-__device__ __forceinline__ uint32_t sel(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
-
-// first / last non-zero byte of sixteen words handed over four at a time (block j = words 4 j .. 4 j + 3), branch-free
-struct FirstNz {
-    uint32_t y[4] = {0u, 0u, 0u, 0u}, yo = 0u, jb = 0u;
-    __device__ __forceinline__ void block(uint32_t j, const uint32_t (&x)[4])
-    {
-        const uint32_t o = x[0] | x[1] | x[2] | x[3];
-        const bool take = yo == 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++) y[k] = sel(take, x[k], y[k]);
-        jb = sel(take, j, jb);
-        yo = sel(take, o, yo);
-    }
-    // byte index inside the kept block (valid when yo != 0)
-    __device__ __forceinline__ uint32_t byte_in_block() const
-    {
-        const bool a = y[0] != 0u, b = y[1] != 0u, c = y[2] != 0u;
-        const uint32_t k = a ? 0u : b ? 4u : c ? 8u : 12u;
-        const uint32_t w = a ? y[0] : b ? y[1] : c ? y[2] : y[3];
-        return k + ((uint32_t)(__ffs((int)w) - 1) >> 3);
-    }
-};
-struct LastNz {
-    uint32_t y[4] = {0u, 0u, 0u, 0u}, yo = 0u, jb = 0u;
-    __device__ __forceinline__ void block(uint32_t j, const uint32_t (&x)[4])
-    {
-        const uint32_t o = x[0] | x[1] | x[2] | x[3];
-        const bool take = o != 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++) y[k] = sel(take, x[k], y[k]);
-        jb = sel(take, j, jb);
-        yo = sel(take, o, yo);
-    }
-    __device__ __forceinline__ uint32_t byte_in_block() const
-    {
-        const bool a = y[3] != 0u, b = y[2] != 0u, c = y[1] != 0u;
-        const uint32_t k = a ? 12u : b ? 8u : c ? 4u : 0u;
-        const uint32_t w = a ? y[3] : b ? y[2] : c ? y[1] : y[0];
-        return k + ((uint32_t)(31 - __clz((int)w)) >> 3);
-    }
-};
-
 }  // namespace
 
 template <int G, bool SPAN>
@@ -177,7 +149,9 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
 {
     constexpr int RPW = 32 / G;
     constexpr int NBL = 8;                // 16-byte blocks per lane
-    constexpr uint32_t WIN = 16u * G * NBL;  // bytes of a read's window (64-byte aligned in memory)
+    const uint32_t ws = f.g.ws;           // bytes between two reads' windows in the staging area (a window is 64-byte aligned in memory)
+    const uint32_t half = (uint32_t)RPW * ws;  // one half of a warp's staging area: the windows of its 32 / G reads
+    const uint32_t wcap = min(ws, 16u * G * NBL);  // a read is taken when it ends inside its window (G lanes x NBL blocks)
     constexpr uint32_t JS = 16u * G;      // a lane's blocks are JS bytes apart
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -196,8 +170,8 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     for (uint32_t i = threadIdx.x; i < 2 * sum_len; i += blockDim.x) sum_lo[i] = 0u;
     __syncthreads();
     const uint32_t s32 = smem_u32(smem);
-    const uint32_t warp32 = s32 + g.image_bytes + sum_bytes + (uint32_t)warp * (2u * kFrHalf);  // two halves: the reads being worked on, the next ones
-    const uint32_t lane32 = warp32 + (uint32_t)grp * WIN + 16u * (uint32_t)gl;     // this lane's first block inside a half
+    const uint32_t warp32 = s32 + g.image_bytes + sum_bytes + (uint32_t)warp * (2u * half);  // two halves: the reads being worked on, the next ones
+    const uint32_t lane32 = warp32 + (uint32_t)grp * ws + 16u * (uint32_t)gl;     // this lane's first block inside a half
     const uint32_t keep32 = s32 + g.off_keep, pc32 = s32 + g.off_p, fc32 = s32 + g.off_f;
     const uint16_t *s_pcum = reinterpret_cast<const uint16_t *>(smem + g.off_pcum), *s_fsuf = reinterpret_cast<const uint16_t *>(smem + g.off_fsuf);
     const uint16_t *s_ppos = reinterpret_cast<const uint16_t *>(smem + g.off_ppos), *s_ftail = reinterpret_cast<const uint16_t *>(smem + g.off_ftail);
@@ -233,7 +207,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     auto stage_blocks = [&](uint64_t b, uint32_t L, uint32_t dst32) {
         const uint32_t a = (base_lo + (uint32_t)b) & (kFrNB - 1u);
         const uint32_t nb16 = (a + L + 15u) >> 4;  // 16-byte blocks the read touches
-        if (L == 0u || a + L > WIN) return;
+        if (L == 0u || a + L > wcap) return;
         const int64_t w0 = (int64_t)b - a;  // the window starts here
         if (w0 >= lo && w0 + (int64_t)(16u * nb16) <= hi) {
             const uint8_t *src = p.seqs + w0 + 16 * gl;
@@ -245,6 +219,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         }
 #pragma unroll 1
         for (int j = 0; j < NBL; j++) {
+            if ((uint32_t)(G * j + gl) >= nb16) break;
 #pragma unroll 1
             for (int c4 = 0; c4 < 4; c4++) {
                 uint32_t w = 0u;
@@ -273,12 +248,12 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     where((gw + nw) * RPW + grp, x0_nxt, x1_nxt);
-    uint32_t buf = 0;  // 0 / kFrHalf: which half of the warp's staging area holds the current reads
+    uint32_t buf = 0;  // 0 / half: which half of the warp's staging area holds the current reads
     for (uint32_t u = gw; u < units; u += nw) {
         // the next reads' blocks start their way into the other half (its readers of two iterations ago are past their
         // __syncwarp); the current ones have arrived when all but that newest group are complete
         resolve(x0_nxt, x1_nxt, b_nxt, L_nxt);
-        stage_blocks(b_nxt, L_nxt, lane32 + (buf ^ kFrHalf));
+        stage_blocks(b_nxt, L_nxt, lane32 + (buf ^ half));
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
@@ -290,7 +265,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         const uint32_t r = u * RPW + grp;
         const uint32_t a = a_cur;  // the read starts at byte a of its window
         const bool in_batch = r < N32;
-        const uint32_t L = (in_batch && a + L_cur <= WIN) ? L_cur : 0u;
+        const uint32_t L = (in_batch && a + L_cur <= wcap) ? L_cur : 0u;
         const uint32_t read_count = (in_batch && q.read_count) ? q.read_count[r] : 1u;
 
         // ---- R against P from the read's start and against F from its end ---------------------------------------
@@ -302,42 +277,80 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
         const int fo = (int)(kFrGuardF + 16u * (uint32_t)gl) - (d & ~15);
         const uint32_t fa32 = fc32 + ((uint32_t)d & 15u) * g.sf;
         const int e_hi = (int)(a + L) - 16 * gl, e_lo = (int)a - 16 * gl;  // the read covers bytes [e_lo, e_hi) counted from this lane's first block
-        // blocks past the longest read of the warp are skipped by all lanes
+        // blocks past the longest read of the warp are skipped by all lanes; rows (one block per lane) that lie inside every
+        // read of the warp need no mask but the case fold
         const uint32_t nb_max = __reduce_max_sync(FULL_MASK, (a + L + 15u) >> 4);
+        const uint32_t nb_min = __reduce_min_sync(FULL_MASK, L ? (a + L) >> 4 : 0xffffu);
         // window offsets of the group's first difference from P and last difference from F
-        uint32_t gp;
-        int gf;
+        uint32_t gp = 0x7fffffffu;
+        int gf = -1;
         {
-            FirstNz fp;
-            LastNz lf;
+            // P is walked from the lane's first block upwards, F from its last block downwards, and a lane stops loading on a
+            // side once one of its blocks differs there (only its first difference from P and its last one from F count): the
+            // registers then keep the words of exactly that block, and the two walks together touch each row about once.
+            // bit j of mp / mf: block j differs (bits set after the stop are leftovers and lie on the far side)
+            constexpr uint32_t DF = 0xdfdfdfdfu;
+            uint32_t mp = 0u, mf = 0u;
+            uint4 wp = make_uint4(0u, 0u, 0u, 0u), pw = wp, wf = wp, fw = wp;
 #pragma unroll
-            for (int j = 0; j < NBL; j++) {
-                if (j >= 2 && (uint32_t)(G * j) >= nb_max) continue;
-                const uint4 wv = lds_v4(mystage32 + JS * j);
-                uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)(JS * j), 0), 16));
-                if (j == 0) {  // only the first block of a lane can start in front of the read (a < 64)
-                    const uint4 kl = lds_v4(keep32 + 16u * (uint32_t)min(max(e_lo, 0), 16));
-                    kp = make_uint4(kp.x & ~kl.x, kp.y & ~kl.y, kp.z & ~kl.z, kp.w & ~kl.w);
+            for (int i = 0; i < NBL; i++) {
+                {
+                    const int j = i;
+                    if (!(j >= 2 && (uint32_t)(G * j) >= nb_max)) {
+                        lds_v4x2_if_zero(mp, mystage32 + JS * j, wp, pa32 + (uint32_t)min(po + (int)(JS * j), p_top), pw);
+                        uint32_t o;
+                        if (j == 0) {  // only the first block of a lane can start in front of the read (a < 64)
+                            const uint4 kl = lds_v4(keep32 + 16u * (uint32_t)min(max(e_lo, 0), 16));
+                            o = ((wp.x ^ pw.x) & ~kl.x) | ((wp.y ^ pw.y) & ~kl.y) | ((wp.z ^ pw.z) & ~kl.z) | ((wp.w ^ pw.w) & ~kl.w);
+                        } else {
+                            o = (wp.x ^ pw.x) | (wp.y ^ pw.y) | (wp.z ^ pw.z) | (wp.w ^ pw.w);
+                        }
+                        mp |= (o & DF) ? (1u << j) : 0u;
+                    }
                 }
-                const uint4 pw = lds_v4(pa32 + (uint32_t)min(po + (int)(JS * j), p_top));
-                const uint4 fw = lds_v4(fa32 + (uint32_t)min(max(fo + (int)(JS * j), 0), f_top));
-                const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-                const uint32_t xp[4] = {(w[0] ^ pw.x) & kp.x, (w[1] ^ pw.y) & kp.y, (w[2] ^ pw.z) & kp.z, (w[3] ^ pw.w) & kp.w};
-                const uint32_t xf[4] = {(w[0] ^ fw.x) & kp.x, (w[1] ^ fw.y) & kp.y, (w[2] ^ fw.z) & kp.z, (w[3] ^ fw.w) & kp.w};
-                fp.block(j, xp);
-                lf.block(j, xf);
+                {
+                    const int j = NBL - 1 - i;
+                    if (!(j >= 2 && (uint32_t)(G * j) >= nb_max)) {
+                        lds_v4x2_if_zero(mf, mystage32 + JS * j, wf, fa32 + (uint32_t)min(max(fo + (int)(JS * j), 0), f_top), fw);
+                        uint32_t o;
+                        if ((uint32_t)(G * (j + 1)) <= nb_min) {  // (warp-uniform) the row ends inside every read
+                            o = ((wf.x ^ fw.x) | (wf.y ^ fw.y) | (wf.z ^ fw.z) | (wf.w ^ fw.w)) & DF;
+                        } else {
+                            const uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)(JS * j), 0), 16));
+                            o = ((wf.x ^ fw.x) & kp.x) | ((wf.y ^ fw.y) & kp.y) | ((wf.z ^ fw.z) & kp.z) | ((wf.w ^ fw.w) & kp.w);
+                        }
+                        mf |= o ? (1u << j) : 0u;
+                    }
+                }
             }
-            gp = fp.yo ? JS * fp.jb + 16u * (uint32_t)gl + fp.byte_in_block() : 0x7fffffffu;
-            gf = lf.yo ? (int)(JS * lf.jb + 16u * (uint32_t)gl + lf.byte_in_block()) : -1;
+            if (mp) {  // (bytes behind the read's end are not masked on this side: a difference there gives t = L below)
+                const int j = __ffs((int)mp) - 1;
+                const uint4 kl = lds_v4(keep32 + 16u * (uint32_t)min(max(e_lo - (int)JS * j, 0), 16));
+                const uint32_t x0 = (wp.x ^ pw.x) & DF & ~kl.x, x1 = (wp.y ^ pw.y) & DF & ~kl.y, x2 = (wp.z ^ pw.z) & DF & ~kl.z, x3 = (wp.w ^ pw.w) & DF & ~kl.w;
+                const bool b0 = x0 != 0u, b1 = x1 != 0u, b2 = x2 != 0u;
+                const uint32_t k = b0 ? 0u : b1 ? 4u : b2 ? 8u : 12u;
+                const uint32_t w = b0 ? x0 : b1 ? x1 : b2 ? x2 : x3;
+                gp = JS * (uint32_t)j + 16u * (uint32_t)gl + k + ((uint32_t)(__ffs((int)w) - 1) >> 3);
+            }
+            if (mf) {  // (bytes in front of the read's start are not masked on this side: a difference there gives s = L below)
+                const int j = 31 - __clz((int)mf);
+                const uint4 kp = lds_v4(keep32 + 16u * (uint32_t)min(max(e_hi - (int)JS * j, 0), 16));
+                const uint32_t x0 = (wf.x ^ fw.x) & kp.x, x1 = (wf.y ^ fw.y) & kp.y, x2 = (wf.z ^ fw.z) & kp.z, x3 = (wf.w ^ fw.w) & kp.w;
+                const bool b3 = x3 != 0u, b2 = x2 != 0u, b1 = x1 != 0u;
+                const uint32_t k = b3 ? 12u : b2 ? 8u : b1 ? 4u : 0u;
+                const uint32_t w = b3 ? x3 : b2 ? x2 : b1 ? x1 : x0;
+                gf = (int)(JS * (uint32_t)j + 16u * (uint32_t)gl + k + ((uint32_t)(31 - __clz((int)w)) >> 3));
+            }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) {  // (a REDUX over part of a warp runs once per group)
                 gp = min(gp, __shfl_xor_sync(FULL_MASK, gp, o));
                 gf = max(gf, __shfl_xor_sync(FULL_MASK, gf, o));
             }
         }
-        const uint32_t t = min(gp != 0x7fffffffu ? gp - a : L, min(L, Lp));             // common prefix of R and P
-        const uint32_t s = min(gf >= 0 ? L - 1u - ((uint32_t)gf - a) : L, min(L, Lf));  // common suffix of R and F
-        const uint32_t rstage32 = stage32 + (uint32_t)grp * WIN + a;  // the read's first character in the staging area
+        const uint32_t t = min(gp != 0x7fffffffu ? gp - a : L, min(L, Lp));  // common prefix of R and P
+        // (a lane without a read -- L = 0 -- sees unmasked rows of the others' extent: its difference may lie behind a + L)
+        const uint32_t s = (uint32_t)max(min(gf >= 0 ? (int)(a + L) - 1 - gf : (int)L, (int)min(L, Lf)), 0);  // common suffix of R and F
+        const uint32_t rstage32 = stage32 + (uint32_t)grp * ws + a;  // the read's first character in the staging area
         const uint32_t bp = s_pcum[t], bs = s_fsuf[s];
         const bool t0_all = s == L && L == Lf, pe_all = t == L && L == Lp;
         const bool overlap = t + s >= L;
@@ -355,14 +368,43 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             // (junction length | bases in front of it << 16) and the staged address of its first character
             const uint32_t my_nb = (cand ? n_mid : 0u) | (bp << 16);
             const uint32_t my_at = rstage32 + t;
-#pragma unroll 2
-            for (int k = 0; k < RPW; k++) {
+            // the first 32 characters of KB reads at a time: their loads are in flight together (the two dependent
+            // shared-memory loads of a round are the latency of this kernel); a read without a junction runs through with
+            // an empty ballot.  bit k of more: read k's junction goes on and has matched so far
+            constexpr int KB = RPW < 4 ? RPW : 4;
+            uint32_t more = 0u;
+#pragma unroll
+            for (int k0 = 0; k0 < RPW; k0 += KB) {
+                uint32_t nb[KB], cu[KB], bal[KB], want[KB];
+#pragma unroll
+                for (int i = 0; i < KB; i++) {
+                    nb[i] = __shfl_sync(FULL_MASK, my_nb, (k0 + i) * G);
+                    const uint32_t at = __shfl_sync(FULL_MASK, my_at, (k0 + i) * G) + (uint32_t)lane;  // (inside the staging area + its pad)
+                    cu[i] = lds_u8(at) & 0xdfu;
+                }
+#pragma unroll
+                for (int i = 0; i < KB; i++) {
+                    bal[i] = __ballot_sync(FULL_MASK, (uint32_t)lane < (nb[i] & 0xffffu) && cu[i] != eb);
+                    want[i] = lds_u8(bases32 + (nb[i] >> 16) + (uint32_t)__popc(bal[i] & lt));
+                }
+#pragma unroll
+                for (int i = 0; i < KB; i++) {
+                    const bool bad = __any_sync(FULL_MASK, ((bal[i] >> lane) & 1u) != 0u && want[i] != cu[i]);
+                    if (grp == k0 + i) {
+                        mid_ok = !bad;
+                        mid_bases = (uint32_t)__popc(bal[i]);
+                    }
+                    if (!bad && (nb[i] & 0xffffu) > 32u) more |= 1u << (k0 + i);
+                }
+            }
+            while (more) {  // the rest of the long junctions, one read after the other
+                const int k = __ffs((int)more) - 1;
+                more &= more - 1u;
                 const uint32_t nb = __shfl_sync(FULL_MASK, my_nb, k * G);
-                int left = (int)(nb & 0xffffu);
-                if (left == 0) continue;
-                uint32_t at = __shfl_sync(FULL_MASK, my_at, k * G) + (uint32_t)lane;  // (reads past the junction stay inside the staging area + its pad)
+                int left = (int)(nb & 0xffffu) - 32;
+                uint32_t at = __shfl_sync(FULL_MASK, my_at, k * G) + 32u + (uint32_t)lane;
                 const uint32_t rank0 = bases32 + (nb >> 16);
-                uint32_t rank = rank0;
+                uint32_t rank = rank0 + __shfl_sync(FULL_MASK, mid_bases, k * G);
                 bool okk = true;
                 do {
                     const uint32_t cu = lds_u8(at) & 0xdfu;
@@ -444,7 +486,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             }
         }
         L_cur = L_nxt, a_cur = a_nxt;
-        buf ^= kFrHalf;
+        buf ^= half;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0 && n_done) {
@@ -470,26 +512,17 @@ bool frontier_applies(const PackParams &p, const AlignParams &q, const FrontierP
            p.edit_base >= 'A' && p.edit_base <= 'Z';
 }
 
-// lanes per read (8 blocks of 16 bytes per lane): the smallest window (64-byte aligned, so 63 bytes may be lost in front)
-// that holds reads a little longer than the longer template string
-static int frontier_group(const FrontierGeom &g)
-{
-    const uint32_t need = std::max(g.Lf, g.Lp) + 16u;
-    for (int G : {4, 8, 16})
-        if (need <= (uint32_t)G * 128u - (kFrNB - 1u)) return G;
-    return 0;
-}
-
 template <typename Kern>
 static int launch_frontier_kernel(Kern kern, const PackParams &p, const AlignParams &q, const FrontierParams &f, int rpw, size_t fixed, int max_smem,
                                   int num_sms, void *stream)
 {
     // as many warps per CTA as the planned number of CTAs per SM can stage next to their images (one CTA when the image is large)
     const size_t share = ((size_t)max_smem + 1024) / TREAT_B200_FR_MIN_CTAS;  // (the driver keeps 1 KB per resident CTA)
-    int warps = (int)std::min<size_t>(kFrWarps, (share > fixed + 1024 ? (share - 1024 - fixed) / (2 * kFrHalf) : 0));
-    if (warps < 4) warps = (int)std::min<size_t>(kFrWarps, ((size_t)max_smem - fixed) / (2 * kFrHalf));
+    const size_t per_warp = 2 * (size_t)rpw * f.g.ws;  // two staging halves
+    int warps = (int)std::min<size_t>(kFrWarps, (share > fixed + 1024 ? (share - 1024 - fixed) / per_warp : 0));
+    if (warps < 4) warps = (int)std::min<size_t>(kFrWarps, ((size_t)max_smem - fixed) / per_warp);
     if (warps < 1) return -1000;
-    const size_t smem = fixed + (size_t)warps * 2 * kFrHalf;
+    const size_t smem = fixed + (size_t)warps * per_warp;
     const uint64_t units = (p.N + rpw - 1) / rpw;
     uint64_t blocks = (units + warps - 1) / warps;
     const int per_sm = occupancy_cached((const void *)kern, warps * 32, smem);
@@ -504,8 +537,8 @@ int launch_frontier(const PackParams &p, const AlignParams &q, const FrontierPar
 {
     const uint32_t sum_len = q.summary ? TREAT_B200_SUMMARY_HEADER + 3u * q.bins : 0u;
     const size_t fixed = (size_t)f.g.image_bytes + align16(8u * sum_len) + 512u;  // + pad: the junction check reads whole rounds of 32 characters
-    const int G = frontier_group(f.g);
-    if (G == 0 || fixed + 2 * kFrHalf > (size_t)max_smem_optin) return -1000;
+    const int G = (int)f.g.G;
+    if (G == 0 || f.g.ws == 0 || fixed + 2 * (size_t)(32 / G) * f.g.ws > (size_t)max_smem_optin) return -1000;
     const bool span = p.begin != nullptr;
     switch (G) {
     case 4:

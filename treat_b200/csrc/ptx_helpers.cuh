@@ -65,6 +65,17 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+// two 16-byte loads that happen only while m == 0; otherwise a and b keep what they hold
+__device__ __forceinline__ void lds_v4x2_if_zero(uint32_t m, uint32_t addr_a, uint4 &a, uint32_t addr_b, uint4 &b)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.eq.u32 q, %8, 0;\n\t"
+        "@q ld.shared.v4.u32 {%0, %1, %2, %3}, [%9];\n\t"
+        "@q ld.shared.v4.u32 {%4, %5, %6, %7}, [%10];\n\t}"
+        : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w)
+        : "r"(m), "r"(addr_a), "r"(addr_b));
+}
 __device__ __forceinline__ uint2 lds_v2(uint32_t addr)
 {
     uint2 v;
