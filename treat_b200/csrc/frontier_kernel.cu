@@ -44,9 +44,9 @@ constexpr uint32_t kFrNB = 64;      // a read's window starts at a 64-byte bound
 constexpr uint32_t kFrGuardP = 64;  // zero bytes in front of P inside a shifted copy (a block of P starts up to 48 bytes early)
 constexpr uint32_t kFrGuardF = 16;  // zero block in front of F (block offsets are clamped into the copy)
 // at most this many warps per CTA (each owns two staging halves of 32 / G windows; the launcher takes as many as fit next to
-// the image) (one CTA per SM: one copy of the template image, the rest of the shared memory stages reads -- 24 warps with RPS12)
+// the image) (one CTA per SM: one copy of the template image, the rest of the shared memory stages reads -- 28 warps with RPS12)
 #ifndef TREAT_B200_FR_WARPS
-#define TREAT_B200_FR_WARPS 24
+#define TREAT_B200_FR_WARPS 28
 #endif
 #ifndef TREAT_B200_FR_MIN_CTAS
 #define TREAT_B200_FR_MIN_CTAS 1
@@ -522,6 +522,7 @@ static int launch_frontier_kernel(Kern kern, const PackParams &p, const AlignPar
     int warps = (int)std::min<size_t>(kFrWarps, (share > fixed + 1024 ? (share - 1024 - fixed) / per_warp : 0));
     if (warps < 4) warps = (int)std::min<size_t>(kFrWarps, ((size_t)max_smem - fixed) / per_warp);
     if (warps < 1) return -1000;
+    if (warps > 4) warps &= ~3;  // the same number of warps on each of the SM's four schedulers
     const size_t smem = fixed + (size_t)warps * per_warp;
     const uint64_t units = (p.N + rpw - 1) / rpw;
     uint64_t blocks = (units + warps - 1) / warps;
