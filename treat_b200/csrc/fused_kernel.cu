@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 4) k_pack_finish(const __gri
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cap = p.stage_cap;  // multiple of 16; one 2-byte pair per base
+    // a list shorter than the grid (the usual case: few reads are longer than a pass of k_pack_finish2): CTAs without a read
+    // leave before the set-up
+    if (p.sel && (uint64_t)blockIdx.x * (blockDim.x >> 5) >= (uint64_t)*p.sel_count) return;
     const uint32_t smem32 = smem_u32(smem);
     const uint32_t lut32 = (smem32 + 255u) & ~255u;  // 256-aligned: PRMT(word, lut32) splices a character into the address
     uint8_t *s_lut = smem + (lut32 - smem32);
