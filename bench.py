@@ -684,14 +684,14 @@ def run_ours(args):
     def ncu_traffic(kernel):
         # DRAM bytes per launch from the committed ncu capture (per read x reads of this launch)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json")))[kernel]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r04_traffic.json")))[kernel]
             return (tr["dram_read_bytes_per_read"] + tr["dram_write_bytes_per_read"]) * N if args.workload == "rps12" else None
         except Exception:
             return None
     def ncu_facts(kernel):
-        # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r03_*_ncu_full.md)
+        # issue-slot / pipe utilisation and instruction counts of the committed ncu capture (profiles/r04_*_ncu_full.md)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json")))[kernel]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r04_traffic.json")))[kernel]
             return {k: v for k, v in tr.items() if not k.startswith("dram_")}
         except Exception:
             return None
@@ -731,7 +731,7 @@ def run_ours(args):
         issued = facts["warp_instructions_per_read"] * N / (frontier_ms * 1e-3)
         roofline["issue"] = {"bound": "warp instructions issued", "achieved": issued / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s",
                              "frac": issued / issue_peak, "warp_instructions_per_read": facts["warp_instructions_per_read"],
-                             "note": "instruction count per read from profiles/r03_traffic.json (ncu), time measured here"}
+                             "note": "instruction count per read from profiles/r04_traffic.json (ncu), time measured here"}
     # the unfused NewFragment kernel (treat_b200_pack_device, used by the stage calls and for long / wide templates)
     pack_bytes = float(len(seqs) + N * 8 + ((n_arr + 3) // 4 + (n_arr + 1)).sum() + N * (2 + 1 + 4))
     roofline_pack = {"bound": "hbm", "kernel": "k_pack16 (stage call treat_b200_pack_device)", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
