@@ -33,7 +33,10 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "assembly.cuh"
 #include "device_format.h"
@@ -728,6 +731,35 @@ static uint64_t resident_ctas(Kern kern, int threads, size_t smem, int num_sms, 
     return (uint64_t)num_sms * std::max(1, std::min(occupancy_cached((const void *)kern, threads, smem), cap_per_sm));
 }
 
+// A second stream next to a caller's stream (per device), with the two events that fork from and join into it: the pure
+// deletions are finished there while k_band_fill, which keeps only a few warps per SM busy on a short list, runs on the main one.
+namespace {
+struct AuxLane {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+AuxLane *aux_lane(cudaStream_t st)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, AuxLane> lanes;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    AuxLane &l = lanes[std::make_pair(dev, st)];
+    if (!l.aux) {
+        if (cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            if (l.aux) cudaStreamDestroy(l.aux);
+            l = AuxLane{};
+            return nullptr;
+        }
+    }
+    return &l;
+}
+}  // namespace
+
 int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, uint32_t min_reads,
                 unsigned long long *stats, int num_sms, int max_smem, void *stream)
 {
@@ -760,11 +792,23 @@ int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_cou
         const uint64_t blocks = std::min<uint64_t>((uint64_t)num_sms * 16, (q.N + kClassifyThreads - 1) / kClassifyThreads);
         k_band_classify<<<(unsigned)blocks, kClassifyThreads, smem_c, st>>>(q, b);
     }
+    // large launches: the pure deletions (which need no fill) are finished on a second stream while the fill runs -- on a list
+    // of a few ten thousand reads k_band_fill is the latency of one thread's rows, not throughput, and leaves the SMs to others
+    static const bool no_overlap = getenv("TREAT_B200_NO_BAND_OVERLAP") != nullptr;
+    AuxLane *lane = (subseq && !no_overlap && q.N >= 100000) ? aux_lane(st) : nullptr;
+    if (lane) {
+        if (cudaEventRecord(lane->fork, st) != cudaSuccess || cudaStreamWaitEvent(lane->aux, lane->fork, 0) != cudaSuccess) return (int)cudaGetLastError();
+        b.first = 0u;
+        b.mode = 0u;
+        const uint64_t blocks_b = std::min<uint64_t>(res_b, (q.N + wb - 1) / wb);
+        k_band_finish<<<(unsigned)blocks_b, wb * 32, smem_b, lane->aux>>>(q, b);
+        if (cudaEventRecord(lane->join, lane->aux) != cudaSuccess) return (int)cudaGetLastError();
+    }
     // one round holds every band read in the usual case: then a single k_band_finish takes the pure deletions and the
     // band reads together; further rounds (more band reads than the scratch cap holds) only have band reads
     for (uint64_t first = 0; first < q.N; first += b.round_reads) {
         b.first = (uint32_t)first;
-        b.mode = first == 0 ? (subseq ? 2u : 1u) : 1u;
+        b.mode = first == 0 ? (subseq && !lane ? 2u : 1u) : 1u;
         const uint64_t reads = std::min<uint64_t>(b.round_reads, q.N - first);
         const uint64_t items = first == 0 ? q.N : reads;  // round 0 also finishes the pure deletions (at most N in all)
         const uint64_t blocks_a = std::min<uint64_t>(res_a, ((reads + 63) / 64 + wa - 1) / wa);
@@ -772,6 +816,7 @@ int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_cou
         k_band_fill<<<(unsigned)blocks_a, wa * 32, smem_a, st>>>(q, b);
         k_band_finish<<<(unsigned)blocks_b, wb * 32, smem_b, st>>>(q, b);
     }
+    if (lane && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return (int)cudaGetLastError();
     return (int)cudaGetLastError();
 }
 
