@@ -761,10 +761,11 @@ AuxLane *aux_lane(cudaStream_t st)
 }  // namespace
 
 int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, uint32_t min_reads,
-                unsigned long long *stats, int num_sms, int max_smem, void *stream)
+                unsigned long long *stats, int num_sms, int max_smem, void *stream, int *kernels_launched)
 {
     AlignParams q;
     BandParams b{};
+    int launched = 0;
     int wa = 0, wb = 0;
     if (!band_plan(planned, q, b, max_smem, wa, wb)) return -1000;
     cudaStream_t st = (cudaStream_t)stream;
@@ -791,6 +792,7 @@ int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_cou
     {
         const uint64_t blocks = std::min<uint64_t>((uint64_t)num_sms * 16, (q.N + kClassifyThreads - 1) / kClassifyThreads);
         k_band_classify<<<(unsigned)blocks, kClassifyThreads, smem_c, st>>>(q, b);
+        launched++;
     }
     // large launches: the pure deletions (which need no fill) are finished on a second stream while the fill runs -- on a list
     // of a few ten thousand reads k_band_fill is the latency of one thread's rows, not throughput, and leaves the SMs to others
@@ -802,6 +804,7 @@ int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_cou
         b.mode = 0u;
         const uint64_t blocks_b = std::min<uint64_t>(res_b, (q.N + wb - 1) / wb);
         k_band_finish<<<(unsigned)blocks_b, wb * 32, smem_b, lane->aux>>>(q, b);
+        launched++;
         if (cudaEventRecord(lane->join, lane->aux) != cudaSuccess) return (int)cudaGetLastError();
     }
     // one round holds every band read in the usual case: then a single k_band_finish takes the pure deletions and the
@@ -815,7 +818,9 @@ int launch_band(const AlignParams &planned, uint32_t *list2, uint32_t *list2_cou
         const uint64_t blocks_b = std::min<uint64_t>(res_b, (items + wb - 1) / wb);
         k_band_fill<<<(unsigned)blocks_a, wa * 32, smem_a, st>>>(q, b);
         k_band_finish<<<(unsigned)blocks_b, wb * 32, smem_b, st>>>(q, b);
+        launched += 2;
     }
+    if (kernels_launched) *kernels_launched = launched;
     if (lane && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return (int)cudaGetLastError();
     return (int)cudaGetLastError();
 }

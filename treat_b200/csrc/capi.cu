@@ -900,10 +900,11 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
         CK(ctx, o.list2->reserve(src->N * 4));
         if (!o.list2_zeroed) CK(ctx, cudaMemsetAsync(o.list2_count, 0, 12, st));  // + the pure-deletion and band list counters
         const bool subseq = !(flags & TREAT_B200_DP_EVERY_READ);
+        int n_band = 0;
         int eb = launch_band(ap, (uint32_t *)o.list2->p, o.list2_count, scratch.p, subseq, ctx->band_min_reads, ctx->d_dp_stats, ctx->num_sms,
-                             ctx->max_smem, st);
+                             ctx->max_smem, st, &n_band);
         if (eb) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("k_band launch: ") + cudaGetErrorString((cudaError_t)eb));
-        ctx->launches++;
+        ctx->launches += (uint64_t)n_band;  // k_band_classify, k_band_fill and k_band_finish (twice when the pure deletions fork)
         ap.list = (uint32_t *)o.list2->p;
         ap.list_count = o.list2_count;
     }

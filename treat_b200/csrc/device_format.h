@@ -204,7 +204,7 @@ uint64_t band_scratch_bytes(const AlignParams &p, int num_sms, int max_smem);
 // min_reads: with fewer reads to align than this the banded fill is not worth its fixed latency; band candidates then go
 // to list2 and only reads at least 16 bases shorter than the template are tested for the pure-deletion route.
 int launch_band(const AlignParams &p, uint32_t *list2, uint32_t *list2_count, void *scratch, bool subseq, uint32_t min_reads,
-                unsigned long long *stats, int num_sms, int max_smem, void *stream);
+                unsigned long long *stats, int num_sms, int max_smem, void *stream, int *kernels_launched = nullptr);
 int configure_band_kernels(int max_smem_optin);
 // K2s: finishes the reads marked kFlagSameBases without a DP and lists the others (p is the plan_align'ed block)
 int launch_same_bases(const AlignParams &p, int num_sms, void *stream);
