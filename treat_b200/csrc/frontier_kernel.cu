@@ -14,15 +14,17 @@
 //     are table look-ups on P and F.
 // tests/test_frontier_model.py states the same in Python and checks it against the CPU restatement of the Go path.
 //
-// One group of G lanes per read, 32 / G reads per warp; lane gl holds the 16-byte blocks gl, G + gl, 2 G + gl, 3 G + gl of
-// the read's 64 G-byte window (so every load, of the read and of the tables, is a run of consecutive 16-byte blocks across
-// the group: coalesced in HBM, conflict-free in shared memory).  Per block the four words are XORed against P (aligned to
-// the read's start) and F (aligned to its end) -- 16 shifted copies of each in shared memory make every operand an
-// aligned LDS.128 --, masked to the read's extent with case folding ((w ^ P) & 0xDF.. per byte is exact for letters), and
-// the first / last non-zero byte is kept with selects; one REDUX per side gives the prefix length t and the suffix
-// length s.  The characters in between (the junction: ~30 on RPS12) are checked by the whole warp, one read after the
-// other, 32 characters per round from a staged copy of the blocks, against the template's bases (rank = ballot prefix
-// count).
+// One group of G lanes per read, 32 / G reads per warp; lane gl holds the 16-byte blocks gl, G + gl, 2 G + gl, ... (eight of
+// them) of the read's 128 G-byte window, so every load, of the read and of the tables, is a run of consecutive 16-byte blocks
+// across the group: coalesced in HBM, and -- with the windows of a warp an odd multiple of 64 bytes apart when two reads share
+// a quarter-warp -- conflict-free in shared memory.  Per block the four words are XORed against P (aligned to the read's
+// start) or F (aligned to its end) -- 16 shifted copies of each in shared memory make every operand an aligned LDS.128 --
+// with case folding ((w ^ P) & 0xDF.. per byte is exact for letters); P is walked upwards and F downwards, and a lane stops
+// loading on a side at its first / last differing block (predicated loads: its registers keep that block, from which the byte
+// position follows); one min / max butterfly per side gives the prefix length t and the suffix length s.  The characters in
+// between (the junction: 33 on average on RPS12, with a long tail) are checked by the whole warp, 32 characters per round from
+// the staged copy of the blocks, against the template's bases (rank = ballot prefix count); the first round of four reads is
+// in flight together.
 // Everything else -- a substitution, an indel, a foreign character, a junction start on an alternative template's region
 // (align.go:186-205), a read whose last run differs from FE's (findJSS may answer -1), a read longer than a pass -- is
 // appended to f.rest and taken by k_pack_finish2 / k_pack_finish exactly as before.
