@@ -1252,6 +1252,20 @@ def test_frontier_kernel_edges(eng, tmp_path):
                  P[:120] + "TTTTT" + F[len(F) - 60:], F.replace("A", "N", 1), P[:30] + "\x00" + P[31:], P[:40] + " " + F[len(F) - 100:],
                  "T" * 300 + F, F + "T" * 700, P[:10] + "T" * 260 + F[len(F) - 30:], "t" * 5 + P.lower()] + raws[2:]
         es = t.edit_site
+        # one substituted base (k_frontier steps over it once): in the prefix, the suffix, the junction, at the very ends, lower
+        # case, two of them, one of them outside the alphabet, the edit base in place of a base
+        swap = {"A": "C", "C": "G", "G": "A"}
+
+        def sub(sq, k):
+            idx = [i for i, ch in enumerate(sq) if ch != "T"][k]
+            return sq[:idx] + swap[sq[idx]] + sq[idx + 1:]
+        mid = P[:120] + "TT" + F[len(F) - 150:]
+        for base in (F, P, mid, P[:60] + "TTTT" + F[len(F) - 220:]):
+            nb = sum(ch != "T" for ch in base)
+            cases += [sub(base, k) for k in (0, 1, 5, nb // 3, nb // 2, nb - 2, nb - 1)]
+            cases += [sub(sub(base, 5), nb // 2), sub(base, 7).lower(), sub(base, 30).replace("A", "N", 1), sub(base, 3) + "T", "TT" + sub(base, nb - 4)]
+            k = [i for i, ch in enumerate(base) if ch != "T"][20]
+            cases += [base[:k] + "T" + base[k + 1:], base[:k] + "N" + base[k + 1:], base[:k] + "n" + base[k + 1:]]
         for _ in range(1500):
             # a read of the model: FE below a frontier, a junction with arbitrary counts, PE above it ...
             ess = rng.randint(-1, t.m)
