@@ -864,14 +864,21 @@ static int do_align(treat_b200_ctx *ctx, const treat_b200_packed *src, uint32_t 
     if (frc) return frc;
     // The reads k_same_bases leaves for the DP are the hard ones (truncated reads fill into the global scratch).  With more
     // than 7 columns per lane the two-reads-per-warp kernel's scratch (8 bytes per lane and step) no longer fits L2 for
-    // them, so listed reads of long templates take the one-read kernel; the paired one serves whole batches.
+    // them, so listed reads of long templates take the one-read kernel; the paired one serves whole batches -- and the few
+    // reads k_band leaves (1 % of the long-gene set: two to a warp they are one round of the persistent grid instead of two).
     const bool use_list = list && d_list_count && !wide && !(flags & TREAT_B200_DP_EVERY_READ);
-    if ((use_list || (o.list2 && !(flags & TREAT_B200_DP_EVERY_READ))) && ctx->td.m > 7 * 32) ap.force_single = 1u;
-    if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
     static const bool no_band_env = getenv("TREAT_B200_NO_BAND") != nullptr;
     const bool want_band = !no_band_env && !wide && o.list2 && o.list2_count &&
                            !(flags & (TREAT_B200_NO_BAND | TREAT_B200_FULL_TRACEBACK_STORE | TREAT_B200_ONE_READ_PER_WARP));
-    const uint64_t band_bytes = want_band ? band_scratch_bytes(ap, ctx->num_sms, ctx->max_smem) : 0;  // 0: k_band does not apply
+    static const bool long_single = getenv("TREAT_B200_LONG_SINGLE") != nullptr;  // (measurement) the one-read kernel behind k_band too
+    const bool listed_long = (use_list || (o.list2 && !(flags & TREAT_B200_DP_EVERY_READ))) && ctx->td.m > 7 * 32;
+    if (listed_long && (!want_band || long_single)) ap.force_single = 1u;
+    if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
+    uint64_t band_bytes = want_band ? band_scratch_bytes(ap, ctx->num_sms, ctx->max_smem) : 0;  // 0: k_band does not apply
+    if (listed_long && want_band && band_bytes == 0 && !ap.force_single) {  // no k_band after all: every listed read is for k_align
+        ap.force_single = 1u;
+        if (plan_align(ap, wide) < 0) return fail(ctx, TREAT_B200_ERR_TOO_LONG, "align: template too long");
+    }
     {
         // global scratch for reads whose path may leave the band (one region per resident warp); k_band's direction words
         // use the same buffer (the two launches follow each other on this stream)
