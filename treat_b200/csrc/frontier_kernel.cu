@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     };
 
     uint32_t n_done = 0;  // reads this warp finished (warp-uniform)
+    unsigned long long rc_done = 0;  // ... and the sum of their ReadCount
     const uint32_t units = (uint32_t)((p.N + RPW - 1) / RPW);
     const uint32_t wpc = blockDim.x >> 5;  // warps per CTA: as many as the shared memory holds next to the image
     const uint32_t gw = blockIdx.x * wpc + warp, nw = gridDim.x * wpc;
@@ -458,17 +459,14 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
                 dst[2] = make_uint4(js_len, tm | (tm << 16), 0u, L);
             }
             // cmd/treat/handlers.go:203-215: three histograms, one lane each (lanes 0..2); the sums the header counters are made
-            // of (cmd/treat/stats.go:140-187): lane 3 adds ReadCount to the CTA's unused header slot 0, the reads are counted
-            // per warp in a register
+            // of (cmd/treat/stats.go:140-187) -- the reads and their ReadCount -- are kept per warp in registers (below)
             if (sum_len) {
                 const bool hist = gl < 3 && !(edit_stop + off == q.t.tmpl_edit_stop && junc_len == 0);
                 const uint32_t bin = gl == 0 ? (uint32_t)(edit_stop + 2) : gl == 1 ? (uint32_t)junc_len : (uint32_t)(junc_end + 2);
-                const bool head = gl == 3;
-                if ((hist && bin < q.bins) || head) {
-                    const uint32_t idx = head ? 0u : TREAT_B200_SUMMARY_HEADER + (uint32_t)gl * q.bins + bin;
-                    const uint32_t val = read_count;
-                    const uint32_t old = atomicAdd(&sum_lo[idx], val);
-                    if (old + val < old) atomicAdd(&sum_hi[idx], 1u);
+                if (hist && bin < q.bins) {
+                    const uint32_t idx = TREAT_B200_SUMMARY_HEADER + (uint32_t)gl * q.bins + bin;
+                    const uint32_t old = atomicAdd(&sum_lo[idx], read_count);
+                    if (old + read_count < old) atomicAdd(&sum_hi[idx], 1u);
                 }
             }
             if (q.ops && !q.ops_gapped_only) {  // m match columns: an all-zero row
@@ -477,6 +475,10 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
             }
         }
         n_done += (uint32_t)__popc(__ballot_sync(FULL_MASK, ok && gl == 0));
+        {   // (two 16-bit halves: a warp-wide add of 32-bit values must not wrap)
+            const uint32_t v = (ok && gl == 0) ? read_count : 0u;
+            rc_done += (unsigned long long)__reduce_add_sync(FULL_MASK, v & 0xffffu) + ((unsigned long long)__reduce_add_sync(FULL_MASK, v >> 16) << 16);
+        }
         // everything else goes to the general path, one list append per warp
         {
             const uint32_t todo = __ballot_sync(FULL_MASK, in_batch && !ok && gl == 0);
@@ -493,7 +495,11 @@ __global__ void __launch_bounds__(kFrWarps * 32, TREAT_B200_FR_MIN_CTAS) k_front
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0 && n_done) {
         atomicMax(&p.scalars[0], tm);
-        if (sum_len) atomicAdd(&sum_lo[1], n_done);  // (a launch holds < 2^31 reads)
+        if (sum_len) {
+            atomicAdd(&sum_lo[1], n_done);  // (a launch holds < 2^31 reads)
+            const uint32_t lo32 = (uint32_t)rc_done, old = atomicAdd(&sum_lo[0], lo32);
+            atomicAdd(&sum_hi[0], (uint32_t)(rc_done >> 32) + (old + lo32 < old ? 1u : 0u));
+        }
     }
     // the header counters of the reads finished above (cmd/treat/stats.go:140-187), from the CTA's two sums: Total and Std
     // weighted by ReadCount, then per read, reads aligned, DP cells; none of these reads has a gap or a mismatch
