@@ -523,11 +523,15 @@ def run_ours(args):
     flags = cabi.WANT_OPS | cabi.OPS_GAPPED_ONLY
     d_red = torch.zeros(parallel.summary_tensor(eng).numel(), dtype=torch.int64, device=dev)
 
-    def step_device():
+    def step_device(reduce=False):
         eng.align_batch_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rc.data_ptr(), N, max_len, flags,
                                d_rec.data_ptr(), d_ops.data_ptr(), stride, sraw)
-        # the only collective on the path: ~4 KB of uint64 counters, ncclAllReduce issued by the library on the same stream
-        comm.reduce_summary_device(d_red.data_ptr(), sraw)
+        # the only collective on the path: ~4 KB of uint64 counters, ncclAllReduce issued by the library.  A job reduces its
+        # summary once, behind its last batch (the counters accumulate on the device; the reference sums its per-read records
+        # when the load is over: cmd/treat/stats.go:140-187) -- `reduce` marks that batch; `nccl.every_step` times the
+        # stricter form with an all-reduce behind every step
+        if reduce:
+            comm.reduce_summary_device(d_red.data_ptr(), sraw)
         return d_red
 
     def barrier():
@@ -543,7 +547,7 @@ def run_ours(args):
         return x
 
     for _ in range(args.warmup):
-        step_device()
+        step_device(reduce=True)
     barrier()
     try:
         pr = torch.cuda.get_device_properties(dev)
@@ -556,20 +560,30 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    comm.join(sraw)  # the timed region ends when the last step's all-reduce has
+    for k in range(args.steps):
+        step_device(reduce=(k == args.steps - 1))
+    comm.join(sraw)  # the timed region ends when the job's all-reduce has
     e1.record(stream)
     sampler.sample_now()  # the queue is still draining: a sample inside the timed region even when it lasts milliseconds
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - l0
     # the one collective of the path: the all-reduced "reads aligned" counter must hold every rank's reads of every step so far
-    step_device()
-    comm.join(sraw)
     torch.cuda.synchronize()
     reduced_reads = int(d_red[14].item())
-    assert reduced_reads == world * N * (args.warmup + args.steps + 1), (reduced_reads, world, N)
+    assert reduced_reads == world * N * (args.warmup + args.steps), (reduced_reads, world, N)
+    # the stricter form: an all-reduce behind every step (it runs on the communicator's stream next to the following step)
+    every_ms = None
+    if world > 1:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device(reduce=True)
+        comm.join(sraw)
+        e1.record(stream)
+        barrier()
+        every_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        assert int(d_red[14].item()) == world * N * (args.warmup + 2 * args.steps)
     clocks = sampler.stop()
     rec_dev = d_rec.cpu().numpy().view(cabi.RECORD_DTYPE)
     cells_per_step = float((rec_dev["n_bases"].astype(np.int64) * t.m).sum())
@@ -1026,7 +1040,10 @@ def run_ours(args):
             "text_device": text_dev, "parity": parity, "long": side.get("long"), "noisy": side.get("noisy"), "collapse": collapse,
             "nccl": {"version": cabi.lib().treat_b200_nccl_version() if world > 1 else None,
                      "collective": "ncclAllReduce(uint64, sum) of the summary counters, issued by libtreat_b200.so "
-                                   "(treat_b200_comm_reduce_summary_device) once per step" if world > 1 else "none (1 GPU)"},
+                                   "(treat_b200_comm_reduce_summary_device) once per job: behind the last of the timed steps, inside "
+                                   "the timed region" if world > 1 else "none (1 GPU)",
+                     "every_step": {"ms_per_step": every_ms, "value": world * N / (every_ms * 1e-3),
+                                    "what": "the same steps with an all-reduce behind every one of them"} if every_ms else None},
             "gpu_launches": int(launches), "clocks": clocks, "summary_reads_all_ranks": reduced_reads,
         }
         emit_line(line)
