@@ -499,6 +499,23 @@ int64_t treat_b200_marshal_batch(const treat_b200_record *rec, const uint8_t *se
 int treat_b200_mutant_report(const treat_b200_template *t, const treat_b200_record *rec, const uint8_t *ops,
                              uint32_t ops_stride, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N, int32_t n,
                              char **out, size_t *out_len);
+/* `treat norm` (cmd/treat/norm.go:25-73, cmd/treat/storage.go:801-878).  NormalizeSample sums ReadCount over a sample's
+ * standard reads (HasMutation == 0) -- that sum is counter [1] ("Std", weighted by ReadCount) of the summary accumulated while
+ * the sample's reads were aligned (treat_b200_get_summary; same flags as the records) --, takes scale = norm / total (1.0 when
+ * the total is 0) and stores Norm = scale * float64(ReadCount) in every standard read's record (bytes 24..32 of its
+ * MarshalBinary blob, big-endian float64); reads with a mutation keep their Norm.
+ * treat_b200_norm_default: Normalize's default norm, the average of the samples' totals (norm.go:48-63: total / len(samples)
+ * in float64).  treat_b200_norm_scale: NormalizeSample's scale for one sample. */
+int treat_b200_norm_default(const uint64_t *std_reads_per_sample, int32_t n_samples, double *norm);
+int treat_b200_norm_scale(uint64_t std_reads_of_sample, double norm, double *scale);
+/* The per-record half of NormalizeSample for a batch on the host: norm_out[i] = scale * ReadCount for a standard read, 0.0 (the
+ * value `treat load` stored) for a read with a mutation; with blob != NULL the value is also written into blob i (as
+ * treat_b200_marshal_batch laid them out: blob_off[N + 1]) -- for standard reads only, like the reference. */
+int treat_b200_normalize_records(const treat_b200_record *rec, uint64_t N, double scale, double *norm_out, uint8_t *blob,
+                                 const uint64_t *blob_off);
+/* The same for records (and blobs from treat_b200_marshal_device) resident in HBM; asynchronous on `stream`. */
+int treat_b200_normalize_device(treat_b200_ctx *ctx, const treat_b200_record *d_rec, uint64_t N, double scale, double *d_norm,
+                                uint8_t *d_blob, const uint64_t *d_blob_off, void *stream);
 /* cmd/treat/stats.go:62-137 (`treat stats`): the block ShowStats prints for one gene -- rule, name, totals, template
  * facts, the per-sample table -- from summary counters (treat_b200_get_summary, or their sum over GPUs / samples).
  * samples[i] / summaries[i]: one row per sample (each summary holds at least 14 counters); the gene totals are their

@@ -397,3 +397,31 @@ def mutant_report(tm, fm, n):
         if cnt > n:
             break
     return "".join(out)
+
+
+# ---- `treat norm` (cmd/treat/norm.go:25-73, cmd/treat/storage.go:801-878) ---------------------------------------------
+def normalize_default(samples):
+    """norm.go:48-63: the default norm is the number of standard reads over all samples divided by the number of samples.
+    samples: one list of Alignment per sample."""
+    total = 0
+    for alns in samples:
+        for a in alns:
+            if a.HasMutation == 0:  # Search(... HasMutation: false ...)
+                total += int(a.ReadCount)
+    return float(total) / float(len(samples))
+
+
+def normalize_sample(alns, norm):
+    """storage.go:801-878 NormalizeSample: scale = norm / (ReadCount summed over the standard reads), 1.0 for an empty
+    total; Norm = scale * float64(ReadCount) for the standard reads, the others keep theirs.  Returns the scale."""
+    total = 0
+    for a in alns:
+        if a.HasMutation == 0:
+            total += int(a.ReadCount)
+    scale = 1.0
+    if total > 0:
+        scale = norm / float(total)
+    for a in alns:
+        if a.HasMutation == 0:
+            a.Norm = scale * float(a.ReadCount)
+    return scale

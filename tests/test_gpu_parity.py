@@ -927,6 +927,21 @@ def test_marshal_on_device(eng, tmp_path):
         assert blob[int(boff[i]):int(boff[i + 1])].tobytes() == O.NewAlignment(f, om).MarshalBinary(), i
     with pytest.raises(T.TreatError):
         eng.marshal_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rec.data_ptr(), N, d_boff.data_ptr(), d_blob.data_ptr(), total - 1, st)
+    # `treat norm` on the device (cmd/treat/storage.go:801-878): Norm of the standard reads as float64 and inside their blobs ==
+    # the host's normalize_records == scale * ReadCount in IEEE double (0.0 for reads with a mutation, whose blobs stay as loaded)
+    std_total = int(rec["read_count"][rec["has_mutation"] == 0].astype(np.uint64).sum())
+    scale = T.norm_scale(std_total, 4321.5)
+    d_norm = torch.zeros(N, dtype=torch.float64, device="cuda")
+    eng.normalize_device(d_rec.data_ptr(), N, scale, d_norm.data_ptr(), d_blob.data_ptr(), d_boff.data_ptr(), st)
+    torch.cuda.synchronize()
+    want = T.normalize_records(rec, scale, hblob, hboff)
+    assert (rec["has_mutation"] != 0).sum() > 50 and (rec["read_count"] > 1).sum() > 50
+    assert np.array_equal(d_norm.cpu().numpy().view(np.uint64), want.view(np.uint64))
+    assert np.array_equal(want, np.where(rec["has_mutation"] == 0, scale * rec["read_count"].astype(np.float64), 0.0))
+    assert np.array_equal(d_blob.cpu().numpy(), hblob)
+    i = int(np.flatnonzero(rec["has_mutation"] == 0)[7])
+    nb = T.UnmarshalBinary(hblob[int(hboff[i]):int(hboff[i + 1])].tobytes())
+    assert nb["Norm"] == want[i] and want[i] != 0.0
 
 
 def test_other_edit_base_is_isomorphic(eng, examples, tmp_path):

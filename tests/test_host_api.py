@@ -10,6 +10,7 @@ import treat_b200 as T
 from treat_b200 import cabi
 from oracle import oracle as O
 from oracle import pyref as P
+from helpers import summary_from_records
 
 
 def test_fragment(fx):
@@ -157,6 +158,41 @@ def test_marshal_batch_vs_oracle(examples):
                 assert blob[int(off[i]):int(off[i + 1])].tobytes() == oa.MarshalBinary(), fb.ids[i]
     blob, off = T.marshal_batch(rec[:0], fb.seqs, fb.offsets[:1])
     assert len(blob) == 0 and off.tolist() == [0]
+
+
+def test_normalize_vs_oracle(examples):
+    """`treat norm` (cmd/treat/norm.go:25-73, cmd/treat/storage.go:801-878): default norm, per-sample scale, Norm of the
+    standard reads as float64 and inside their MarshalBinary blobs -- against the pure-Python restatement, bit for bit."""
+    pt = P.template_from_fasta(examples["templates.fa"], P.FORWARD, "T")
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    files = ("clones.fa", "sample-1.fa", "sample-2.fa") if "sample-2.fa" in examples else ("clones.fa", "sample-1.fa")
+    for exclude in (False, True):
+        samples, batches = [], []
+        for rname in files:
+            recs = P.read_fasta(examples[rname])
+            recs = recs + [(i + "x", sq) for i, sq in recs[3:9]]  # a few read counts above one
+            fb = T.FastaBatch.from_records(recs)
+            orec, _, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, exclude_snps=exclude, want_ops=False)
+            samples.append([P.NewAlignment(P.Fragment(i, sq, P.FORWARD, "T"), pt, exclude) for i, sq in recs])
+            batches.append((fb, _oracle_record_as_product(orec)))
+        totals = [summary_from_records(rec, om.Len() - 1, 0, om.EditStop)[1] for _, rec in batches]  # "Std", weighted by ReadCount
+        for alns, tot in zip(samples, totals):
+            assert int(tot) == sum(int(a.ReadCount) for a in alns if a.HasMutation == 0)
+        for norm in (0.0, 1000.0, 12345.678):
+            gnorm = norm if norm else T.norm_default(totals)
+            if not norm:
+                assert gnorm == P.normalize_default(samples)
+            for (fb, rec), alns, tot in zip(batches, samples, totals):
+                scale = T.norm_scale(int(tot), gnorm)
+                assert scale == P.normalize_sample(alns, gnorm)
+                blob, off = T.marshal_batch(rec, fb.seqs, fb.offsets, 2)
+                got = T.normalize_records(rec, scale, blob, off)
+                for i, a in enumerate(alns):
+                    assert got[i] == (a.Norm if a.HasMutation == 0 else 0.0)
+                    assert blob[int(off[i]):int(off[i + 1])].tobytes() == a.MarshalBinary(), (i, exclude, norm)
+                for a in alns:
+                    a.Norm = 0.0
+    assert T.norm_scale(0, 500.0) == 1.0  # storage.go:840-843: an empty sample keeps scale 1
 
 
 def test_mutant_report_vs_oracle(examples):

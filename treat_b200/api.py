@@ -25,7 +25,7 @@ from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, OPS_GAPPED_ONLY, RECORD_DT
 __all__ = [
     "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
     "NewTemplate", "NewTemplateFromFasta", "parseMergeCount", "PrintAlignment", "read_fasta", "TreatError",
-    "marshal_batch", "mutant_report", "DeviceGroup", "Comm",
+    "marshal_batch", "mutant_report", "DeviceGroup", "Comm", "norm_default", "norm_scale", "normalize_records",
 ]
 
 
@@ -264,6 +264,35 @@ def marshal_batch(rec: np.ndarray, seqs: np.ndarray, seq_off: np.ndarray, thread
     if got < 0:
         raise TreatError(int(got))
     return out[: int(need)], off
+
+
+def norm_default(std_reads_per_sample) -> float:
+    """`treat norm` without --norm: the average of the samples' standard-read totals (cmd/treat/norm.go:48-63)."""
+    v = np.ascontiguousarray(std_reads_per_sample, dtype=np.uint64)
+    out = C.c_double(0.0)
+    check(lib().treat_b200_norm_default(v.ctypes.data, len(v), C.byref(out)))
+    return float(out.value)
+
+
+def norm_scale(std_reads_of_sample: int, norm: float) -> float:
+    """NormalizeSample's scaling factor (cmd/treat/storage.go:840-843)."""
+    out = C.c_double(0.0)
+    check(lib().treat_b200_norm_scale(int(std_reads_of_sample), float(norm), C.byref(out)))
+    return float(out.value)
+
+
+def normalize_records(rec: np.ndarray, scale: float, blob: np.ndarray = None, blob_off: np.ndarray = None) -> np.ndarray:
+    """Norm = scale * ReadCount of the standard reads (cmd/treat/storage.go:845-870); patches `blob` (from marshal_batch) in
+    place when given.  Returns the float64 Norm of every record (0.0 for reads with a mutation)."""
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE)
+    out = np.zeros(len(rec), dtype=np.float64)
+    bp = op = None
+    if blob is not None:
+        assert blob.dtype == np.uint8 and blob.flags["C_CONTIGUOUS"] and blob_off is not None
+        blob_off = np.ascontiguousarray(blob_off, dtype=np.uint64)
+        bp, op = blob.ctypes.data, blob_off.ctypes.data
+    check(lib().treat_b200_normalize_records(rec.ctypes.data, len(rec), float(scale), out.ctypes.data, bp, op))
+    return out
 
 
 def mutant_report(tmpl: "Template", rec: np.ndarray, ops: np.ndarray, seqs: np.ndarray, seq_off: np.ndarray, n: int = 10) -> str:
@@ -561,6 +590,11 @@ class Aligner:
         check(lib().treat_b200_text_device(self._ctx, d_seqs, d_seq_off, d_names, d_name_off, d_rec, d_ops, ops_stride, N, max_len, tw,
                                            d_text_off, d_text or None, text_cap, C.byref(total), stream or None), self._ctx)
         return total.value
+
+    def normalize_device(self, d_rec: int, N: int, scale: float, d_norm: int = 0, d_blob: int = 0, d_blob_off: int = 0, stream: int = 0):
+        """`treat norm` for records (and marshal_device's blobs) in HBM: Norm = scale * ReadCount of the standard reads."""
+        check(lib().treat_b200_normalize_device(self._ctx, d_rec, N, float(scale), d_norm or None, d_blob or None, d_blob_off or None,
+                                                stream or None), self._ctx)
 
     def marshal_device(self, d_seqs: int, d_seq_off: int, d_rec: int, N: int, d_blob_off: int, d_blob: int = 0, blob_cap: int = 0,
                        stream: int = 0) -> int:

@@ -104,6 +104,10 @@ SIGNATURES = {
     "treat_b200_fasta_text": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_int32, _P, _P, C.POINTER(C.c_uint64)]),
     "treat_b200_marshal_device": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64), _P]),
     "treat_b200_unmarshal_record": (C.c_int, [_P, _SZ, _P, C.POINTER(C.c_double), C.POINTER(_P)]),
+    "treat_b200_norm_default": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double)]),
+    "treat_b200_norm_scale": (C.c_int, [C.c_uint64, C.c_double, C.POINTER(C.c_double)]),
+    "treat_b200_normalize_records": (C.c_int, [_P, C.c_uint64, C.c_double, _P, _P, _P]),
+    "treat_b200_normalize_device": (C.c_int, [_P, _P, C.c_uint64, C.c_double, _P, _P, _P, _P]),
     "treat_b200_stats_text": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32,
                                        C.POINTER(_P), C.POINTER(_SZ)]),
     "treat_b200_packed_layout": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(Packed)]),

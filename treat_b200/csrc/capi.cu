@@ -2291,6 +2291,42 @@ int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const 
     return TREAT_B200_OK;
 }
 
+// `treat norm` for a batch in HBM (cmd/treat/storage.go:845-870): Norm = scale * float64(ReadCount) for the reads without a
+// mutation, as a float64 per record and, when the batch's MarshalBinary blobs are there, into bytes 24..32 of each (big-endian).
+// One multiplication in double precision: the device's IEEE result is the host's.
+namespace {
+__global__ void __launch_bounds__(256) k_normalize(const treat_b200_record *rec, uint64_t N, double scale, double *norm, uint8_t *blob,
+                                                   const uint64_t *blob_off)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t rc = rec[i].read_count;
+        const bool standard = rec[i].has_mutation == 0;
+        const double v = standard ? __dmul_rn(scale, (double)rc) : 0.0;
+        if (norm) norm[i] = v;
+        if (blob && standard) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+            uint8_t *dst = blob + blob_off[i] + 24;
+#pragma unroll
+            for (int k = 0; k < 8; k++) dst[k] = (uint8_t)(bits >> (56 - 8 * k));
+        }
+    }
+}
+}  // namespace
+
+int treat_b200_normalize_device(treat_b200_ctx *ctx, const treat_b200_record *d_rec, uint64_t N, double scale, double *d_norm,
+                                uint8_t *d_blob, const uint64_t *d_blob_off, void *stream)
+{
+    if (!ctx || (N && !d_rec) || (d_blob && !d_blob_off)) return TREAT_B200_ERR_INVALID;
+    if (N == 0 || (!d_norm && !d_blob)) return TREAT_B200_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint64_t blocks = std::min<uint64_t>((N + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    k_normalize<<<(unsigned)blocks, 256, 0, st>>>(d_rec, N, scale, d_norm, d_blob, d_blob_off);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    return TREAT_B200_OK;
+}
+
 // The loop of cmd/treat/align.go:114-120 for a caller that already holds the records (rec.Id, rec.Seq from gofasta):
 // NewFragment + NewAlignment + WriteTo for reads [0, N), chunk by chunk on two slots; the text of each chunk goes to the
 // sink in read order while the next chunk is being processed.

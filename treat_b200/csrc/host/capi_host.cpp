@@ -184,6 +184,41 @@ int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *s
     return (int64_t)b.size();
 }
 
+// `treat norm` (cmd/treat/norm.go:25-73, cmd/treat/storage.go:801-878)
+int treat_b200_norm_default(const uint64_t *std_reads_per_sample, int32_t n_samples, double *norm)
+{
+    if (!std_reads_per_sample || n_samples < 1 || !norm) return TREAT_B200_ERR_INVALID;
+    uint64_t total = 0;  // norm.go:52-56: total += int(a.ReadCount) over the standard reads of every sample
+    for (int32_t i = 0; i < n_samples; i++) total += std_reads_per_sample[i];
+    *norm = (double)total / (double)n_samples;  // norm.go:61
+    return TREAT_B200_OK;
+}
+
+int treat_b200_norm_scale(uint64_t std_reads_of_sample, double norm, double *scale)
+{
+    if (!scale) return TREAT_B200_ERR_INVALID;
+    *scale = std_reads_of_sample > 0 ? norm / (double)std_reads_of_sample : 1.0;  // storage.go:840-843
+    return TREAT_B200_OK;
+}
+
+int treat_b200_normalize_records(const treat_b200_record *rec, uint64_t N, double scale, double *norm_out, uint8_t *blob,
+                                 const uint64_t *blob_off)
+{
+    if ((N && !rec) || (blob && !blob_off)) return TREAT_B200_ERR_INVALID;
+    for (uint64_t i = 0; i < N; i++) {
+        const bool standard = rec[i].has_mutation == 0;
+        const double v = standard ? scale * (double)rec[i].read_count : 0.0;  // storage.go:858-860
+        if (norm_out) norm_out[i] = v;
+        if (blob && standard) {
+            uint64_t bits;
+            memcpy(&bits, &v, 8);
+            uint8_t *dst = blob + blob_off[i] + 24;  // align.go:328: binary.BigEndian.PutUint64(buf[24:32], Float64bits(a.Norm))
+            for (int k = 0; k < 8; k++) dst[k] = (uint8_t)(bits >> (56 - 8 * k));
+        }
+    }
+    return TREAT_B200_OK;
+}
+
 int64_t treat_b200_marshal_batch(const treat_b200_record *rec, const uint8_t *seqs, const uint64_t *seq_off, uint64_t N,
                                  uint8_t *out, uint64_t out_cap, uint64_t *out_off, int32_t threads)
 {
