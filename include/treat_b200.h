@@ -516,6 +516,28 @@ int treat_b200_normalize_records(const treat_b200_record *rec, uint64_t N, doubl
 /* The same for records (and blobs from treat_b200_marshal_device) resident in HBM; asynchronous on `stream`. */
 int treat_b200_normalize_device(treat_b200_ctx *ctx, const treat_b200_record *d_rec, uint64_t N, double scale, double *d_norm,
                                 uint8_t *d_blob, const uint64_t *d_blob_off, void *stream);
+/* The record filter of the web handlers and of `treat search` (cmd/treat/storage.go:48-64 SearchFields, :162-188 HasMatch,
+ * :257-286 the loop of Storage.Search over one sample's alignments): which records of a batch match, in record order, after
+ * `offset` matches were skipped and up to `limit` of them (0: no limit).  Gene / sample / knock-down / replicate are key
+ * matches (HasKeyMatch) and stay with the caller's storage.  edit_stop / junc_end / junc_len < 0: any value. */
+typedef struct treat_b200_search {
+    int32_t edit_stop;    /* SearchFields.EditStop */
+    int32_t junc_end;     /* SearchFields.JuncEnd */
+    int32_t junc_len;     /* SearchFields.JuncLen */
+    int32_t offset;       /* SearchFields.Offset */
+    int32_t limit;        /* SearchFields.Limit */
+    int32_t alt_region;   /* SearchFields.AltRegion: > 0: AltEditing must equal uint8(alt_region) */
+    uint8_t has_mutation; /* SearchFields.HasMutation */
+    uint8_t has_alt;      /* SearchFields.HasAlt: only reads with alt editing (without it they are left out) */
+    uint8_t all;          /* SearchFields.All: standard reads and mutants alike */
+    uint8_t reserved;
+} treat_b200_search;
+/* idx[0 .. min(*count, cap)) = the matching records' indices; *count = how many match behind the offset and inside the limit */
+int treat_b200_search_records(const treat_b200_search *f, const treat_b200_record *rec, uint64_t N, uint64_t *idx, uint64_t cap,
+                              uint64_t *count);
+/* The same for records resident in HBM (d_idx on the device); one stream synchronisation returns *count. */
+int treat_b200_search_device(treat_b200_ctx *ctx, const treat_b200_search *f, const treat_b200_record *d_rec, uint64_t N,
+                             uint64_t *d_idx, uint64_t cap, uint64_t *count, void *stream);
 /* cmd/treat/stats.go:62-137 (`treat stats`): the block ShowStats prints for one gene -- rule, name, totals, template
  * facts, the per-sample table -- from summary counters (treat_b200_get_summary, or their sum over GPUs / samples).
  * samples[i] / summaries[i]: one row per sample (each summary holds at least 14 counters); the gene totals are their

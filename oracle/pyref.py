@@ -425,3 +425,41 @@ def normalize_sample(alns, norm):
         if a.HasMutation == 0:
             a.Norm = scale * float(a.ReadCount)
     return scale
+
+
+# ---- Storage.Search's record filter (cmd/treat/storage.go:48-64, 162-188, 257-286) --------------------------------------
+def has_match(a, edit_stop=-1, junc_end=-1, junc_len=-1, alt_region=0, has_mutation=False, has_alt=False, all=False):  # :162-188
+    if not all:
+        if has_mutation and a.HasMutation == 0:
+            return False
+        elif not has_mutation and a.HasMutation == 1:
+            return False
+    if edit_stop >= 0 and edit_stop != a.EditStop:
+        return False
+    if junc_len >= 0 and junc_len != a.JuncLen:
+        return False
+    if junc_end >= 0 and junc_end != a.JuncEnd:
+        return False
+    if has_alt and a.AltEditing == 0:
+        return False
+    if alt_region > 0 and (alt_region & 0xFF) != a.AltEditing:
+        return False
+    return True
+
+
+def search(alns, offset=0, limit=0, **fields):  # :257-286, one sample's alignments in order; returns their indices
+    out, count, off = [], 0, 0
+    for i, a in enumerate(alns):
+        if not has_match(a, **fields):
+            continue
+        if not fields.get("has_alt", False) and a.AltEditing > 0:  # by default, don't include alt editing
+            continue
+        if offset > 0 and off < offset:
+            off += 1
+            continue
+        if limit > 0 and count >= limit:
+            break
+        out.append(i)
+        count += 1
+        off += 1
+    return out

@@ -927,6 +927,16 @@ def test_marshal_on_device(eng, tmp_path):
         assert blob[int(boff[i]):int(boff[i + 1])].tobytes() == O.NewAlignment(f, om).MarshalBinary(), i
     with pytest.raises(T.TreatError):
         eng.marshal_device(d_seqs.data_ptr(), d_off.data_ptr(), d_rec.data_ptr(), N, d_boff.data_ptr(), d_blob.data_ptr(), total - 1, st)
+    # Storage.Search's record filter on the device (cmd/treat/storage.go:162-188, 257-286) == the host's search_records
+    d_idx = torch.zeros(N, dtype=torch.int64, device="cuda")
+    es0 = int(np.bincount(rec["edit_stop"] - rec["edit_stop"].min()).argmax() + rec["edit_stop"].min())
+    for f in (dict(), dict(all=True), dict(has_mutation=True), dict(all=True, offset=17, limit=300), dict(edit_stop=es0), dict(all=True, has_alt=True),
+              dict(all=True, junc_len=0, limit=40), dict(has_mutation=True, offset=10 ** 6), dict(all=True, edit_stop=es0, junc_end=int(rec["junc_end"][0]))):
+        want_idx = T.search_records(rec, **f)
+        n_dev = eng.search_device(d_rec.data_ptr(), N, d_idx.data_ptr(), N, st, **f)
+        assert n_dev == len(want_idx), f
+        assert np.array_equal(d_idx.cpu().numpy()[:n_dev].astype(np.uint64), want_idx), f
+    assert len(T.search_records(rec, all=True)) > 1000 and eng.search_device(d_rec.data_ptr(), N, 0, 0, st, all=True) == len(T.search_records(rec, all=True))
     # `treat norm` on the device (cmd/treat/storage.go:801-878): Norm of the standard reads as float64 and inside their blobs ==
     # the host's normalize_records == scale * ReadCount in IEEE double (0.0 for reads with a mutation, whose blobs stay as loaded)
     std_total = int(rec["read_count"][rec["has_mutation"] == 0].astype(np.uint64).sum())

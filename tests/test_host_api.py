@@ -195,6 +195,35 @@ def test_normalize_vs_oracle(examples):
     assert T.norm_scale(0, 500.0) == 1.0  # storage.go:840-843: an empty sample keeps scale 1
 
 
+def test_search_records_vs_oracle(examples):
+    """The record filter of Storage.Search (cmd/treat/storage.go:162-188, 257-286) on a batch's records against the
+    pure-Python restatement walking Alignment objects: every combination of the fields the handlers set."""
+    pt = P.template_from_fasta(examples["templates.fa"], P.FORWARD, "T")
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    recs = P.read_fasta(examples["clones.fa"]) + P.read_fasta(examples["sample-1.fa"])
+    recs = recs + [(i + "y", sq) for i, sq in recs]
+    fb = T.FastaBatch.from_records(recs)
+    for exclude in (False, True):
+        orec, _, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, exclude_snps=exclude, want_ops=False)
+        rec = _oracle_record_as_product(orec)
+        alns = [P.NewAlignment(P.Fragment(i, sq, P.FORWARD, "T"), pt, exclude) for i, sq in recs]
+        es = sorted(set(int(a.EditStop) for a in alns))[:3] + [-1]
+        jl = sorted(set(int(a.JuncLen) for a in alns))[:2] + [-1]
+        alt = sorted(set(int(a.AltEditing) for a in alns))
+        n = 0
+        for kw in (dict(), dict(all=True), dict(has_mutation=True), dict(has_alt=True, all=True), dict(all=True, alt_region=max(alt)),
+                   dict(all=True, alt_region=300), dict(all=True, offset=3, limit=5), dict(offset=1000), dict(limit=1), dict(all=True, has_alt=True, limit=2, offset=1)):
+            for e in es:
+                for j in jl:
+                    for je in (-1, int(alns[0].JuncEnd)):
+                        f = dict(kw, edit_stop=e, junc_len=j, junc_end=je)
+                        assert T.search_records(rec, **f).tolist() == P.search(alns, **f), f
+                        n += 1
+        assert n > 100 and len(T.search_records(rec, all=True, has_alt=False)) > 10
+        if max(alt) > 0:
+            assert len(T.search_records(rec, all=True, has_alt=True)) > 0
+
+
 def test_mutant_report_vs_oracle(examples):
     """`treat mutant` (cmd/treat/mutant.go:55-110) from records + ops; ops here come from the oracle."""
     tm = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "T")

@@ -25,7 +25,7 @@ from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, OPS_GAPPED_ONLY, RECORD_DT
 __all__ = [
     "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
     "NewTemplate", "NewTemplateFromFasta", "parseMergeCount", "PrintAlignment", "read_fasta", "TreatError",
-    "marshal_batch", "mutant_report", "DeviceGroup", "Comm", "norm_default", "norm_scale", "normalize_records",
+    "marshal_batch", "mutant_report", "DeviceGroup", "Comm", "norm_default", "norm_scale", "normalize_records", "search_records",
 ]
 
 
@@ -264,6 +264,22 @@ def marshal_batch(rec: np.ndarray, seqs: np.ndarray, seq_off: np.ndarray, thread
     if got < 0:
         raise TreatError(int(got))
     return out[: int(need)], off
+
+
+def _search_fields(edit_stop=-1, junc_end=-1, junc_len=-1, offset=0, limit=0, alt_region=0, has_mutation=False, has_alt=False, all=False):
+    from .cabi import Search
+    return Search(int(edit_stop), int(junc_end), int(junc_len), int(offset), int(limit), int(alt_region), int(bool(has_mutation)),
+                  int(bool(has_alt)), int(bool(all)), 0)
+
+
+def search_records(rec: np.ndarray, **fields) -> np.ndarray:
+    """Indices of the records Storage.Search would hand out (cmd/treat/storage.go:162-188, 257-286), in record order."""
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE)
+    f = _search_fields(**fields)
+    n = C.c_uint64(0)
+    idx = np.zeros(max(len(rec), 1), dtype=np.uint64)
+    check(lib().treat_b200_search_records(C.byref(f), rec.ctypes.data, len(rec), idx.ctypes.data, len(idx), C.byref(n)))
+    return idx[: int(n.value)]
 
 
 def norm_default(std_reads_per_sample) -> float:
@@ -590,6 +606,13 @@ class Aligner:
         check(lib().treat_b200_text_device(self._ctx, d_seqs, d_seq_off, d_names, d_name_off, d_rec, d_ops, ops_stride, N, max_len, tw,
                                            d_text_off, d_text or None, text_cap, C.byref(total), stream or None), self._ctx)
         return total.value
+
+    def search_device(self, d_rec: int, N: int, d_idx: int, cap: int, stream: int = 0, **fields) -> int:
+        """Storage.Search's record filter for records in HBM: the matching indices go to d_idx (uint64), returns their number."""
+        f = _search_fields(**fields)
+        n = C.c_uint64(0)
+        check(lib().treat_b200_search_device(self._ctx, C.byref(f), d_rec, N, d_idx or None, cap, C.byref(n), stream or None), self._ctx)
+        return int(n.value)
 
     def normalize_device(self, d_rec: int, N: int, scale: float, d_norm: int = 0, d_blob: int = 0, d_blob_off: int = 0, stream: int = 0):
         """`treat norm` for records (and marshal_device's blobs) in HBM: Norm = scale * ReadCount of the standard reads."""

@@ -41,6 +41,12 @@ RECORD_DTYPE = np.dtype(
 assert RECORD_DTYPE.itemsize == 48
 
 
+class Search(C.Structure):
+    """treat_b200_search: the fields of SearchFields that HasMatch / Storage.Search read (cmd/treat/storage.go:48-64, 162-188, 257-286)."""
+    _fields_ = [("edit_stop", C.c_int32), ("junc_end", C.c_int32), ("junc_len", C.c_int32), ("offset", C.c_int32), ("limit", C.c_int32),
+                ("alt_region", C.c_int32), ("has_mutation", C.c_uint8), ("has_alt", C.c_uint8), ("all", C.c_uint8), ("reserved", C.c_uint8)]
+
+
 class Packed(C.Structure):
     """treat_b200_packed"""
     _fields_ = [
@@ -104,6 +110,8 @@ SIGNATURES = {
     "treat_b200_fasta_text": (C.c_int, [_P, _U8P, C.c_uint64, C.c_uint32, C.c_int32, _P, _P, C.POINTER(C.c_uint64)]),
     "treat_b200_marshal_device": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64), _P]),
     "treat_b200_unmarshal_record": (C.c_int, [_P, _SZ, _P, C.POINTER(C.c_double), C.POINTER(_P)]),
+    "treat_b200_search_records": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "treat_b200_search_device": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64), _P]),
     "treat_b200_norm_default": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double)]),
     "treat_b200_norm_scale": (C.c_int, [C.c_uint64, C.c_double, C.POINTER(C.c_double)]),
     "treat_b200_normalize_records": (C.c_int, [_P, C.c_uint64, C.c_double, _P, _P, _P]),

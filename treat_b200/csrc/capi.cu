@@ -2291,6 +2291,73 @@ int treat_b200_marshal_device(treat_b200_ctx *ctx, const uint8_t *d_seqs, const 
     return TREAT_B200_OK;
 }
 
+// The record filter of Storage.Search (cmd/treat/storage.go:162-188, 257-286) for a batch in HBM: a mark per record, an
+// exclusive scan (the match's rank, in record order), and the indices of the ranks [offset, offset + limit).
+namespace {
+__device__ __forceinline__ bool search_match_dev(const treat_b200_search &f, const treat_b200_record &a)
+{
+    if (!f.all) {
+        if (f.has_mutation && a.has_mutation == 0) return false;
+        if (!f.has_mutation && a.has_mutation == 1) return false;
+    }
+    if (f.edit_stop >= 0 && f.edit_stop != a.edit_stop) return false;
+    if (f.junc_len >= 0 && f.junc_len != a.junc_len) return false;
+    if (f.junc_end >= 0 && f.junc_end != a.junc_end) return false;
+    if (f.has_alt && a.alt_editing == 0) return false;
+    if (f.alt_region > 0 && (uint8_t)f.alt_region != a.alt_editing) return false;
+    if (!f.has_alt && a.alt_editing > 0) return false;
+    return true;
+}
+__global__ void __launch_bounds__(256) k_search_mark(const __grid_constant__ treat_b200_search f, const treat_b200_record *rec, uint64_t N,
+                                                     uint32_t *mark)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x)
+        mark[i] = search_match_dev(f, rec[i]) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_search_write(const uint32_t *mark, const uint64_t *rank, uint64_t N, uint64_t offset, uint64_t limit,
+                                                      uint64_t cap, uint64_t *idx)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!mark[i] || rank[i] < offset) continue;
+        const uint64_t k = rank[i] - offset;
+        if ((limit == 0 || k < limit) && k < cap) idx[k] = i;
+    }
+}
+}  // namespace
+
+int treat_b200_search_device(treat_b200_ctx *ctx, const treat_b200_search *f, const treat_b200_record *d_rec, uint64_t N,
+                             uint64_t *d_idx, uint64_t cap, uint64_t *count, void *stream)
+{
+    if (!ctx || !f || !count || (N && !d_rec)) return TREAT_B200_ERR_INVALID;
+    *count = 0;
+    if (N == 0) return TREAT_B200_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    Slot &s = ctx->dev_slot;
+    CK(ctx, s.tlen.reserve(N * 4));
+    CK(ctx, s.text_off.reserve((N + 1) * 8));
+    CK(ctx, s.tsums.reserve((N / 2048 + 4) * 8));
+    if (!s.h_text_total) CK(ctx, cudaMallocHost((void **)&s.h_text_total, 16));
+    const uint64_t blocks = std::min<uint64_t>((N + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    k_search_mark<<<(unsigned)blocks, 256, 0, st>>>(*f, d_rec, N, (uint32_t *)s.tlen.p);
+    CK(ctx, cudaGetLastError());
+    int e = launch_scan_u32((const uint32_t *)s.tlen.p, N, (uint64_t *)s.text_off.p, (uint64_t *)s.tsums.p, st);
+    if (e) return fail(ctx, TREAT_B200_ERR_CUDA, std::string("search scan launch: ") + cudaGetErrorString((cudaError_t)e));
+    const uint64_t off = f->offset > 0 ? (uint64_t)f->offset : 0, lim = f->limit > 0 ? (uint64_t)f->limit : 0;
+    if (d_idx && cap) {
+        k_search_write<<<(unsigned)blocks, 256, 0, st>>>((const uint32_t *)s.tlen.p, (const uint64_t *)s.text_off.p, N, off, lim, cap, d_idx);
+        CK(ctx, cudaGetLastError());
+    }
+    ctx->launches += 5;
+    PEEK(ctx, s.h_text_total, (uint64_t *)s.text_off.p + N, 8, st);
+    CK(ctx, cudaStreamSynchronize(st));
+    const uint64_t total = *s.h_text_total;
+    uint64_t n = total > off ? total - off : 0;
+    if (lim && n > lim) n = lim;
+    *count = n;
+    return TREAT_B200_OK;
+}
+
 // `treat norm` for a batch in HBM (cmd/treat/storage.go:845-870): Norm = scale * float64(ReadCount) for the reads without a
 // mutation, as a float64 per record and, when the batch's MarshalBinary blobs are there, into bytes 24..32 of each (big-endian).
 // One multiplication in double precision: the device's IEEE result is the host's.

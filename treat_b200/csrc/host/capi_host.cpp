@@ -184,6 +184,42 @@ int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *s
     return (int64_t)b.size();
 }
 
+// SearchFields.HasMatch (cmd/treat/storage.go:162-188) + the alt-editing rule of Storage.Search (:269-272)
+static bool search_match(const treat_b200_search &f, const treat_b200_record &a)
+{
+    if (!f.all) {
+        if (f.has_mutation && a.has_mutation == 0) return false;
+        if (!f.has_mutation && a.has_mutation == 1) return false;
+    }
+    if (f.edit_stop >= 0 && f.edit_stop != a.edit_stop) return false;
+    if (f.junc_len >= 0 && f.junc_len != a.junc_len) return false;
+    if (f.junc_end >= 0 && f.junc_end != a.junc_end) return false;
+    if (f.has_alt && a.alt_editing == 0) return false;
+    if (f.alt_region > 0 && (uint8_t)f.alt_region != a.alt_editing) return false;
+    if (!f.has_alt && a.alt_editing > 0) return false;  // by default, don't include alt editing
+    return true;
+}
+
+int treat_b200_search_records(const treat_b200_search *f, const treat_b200_record *rec, uint64_t N, uint64_t *idx, uint64_t cap,
+                              uint64_t *count)
+{
+    if (!f || (N && !rec) || !count) return TREAT_B200_ERR_INVALID;
+    uint64_t n = 0, offset = 0;  // storage.go:241-242
+    for (uint64_t i = 0; i < N; i++) {
+        if (!search_match(*f, rec[i])) continue;
+        if (f->offset > 0 && offset < (uint64_t)f->offset) {  // :274-277
+            offset++;
+            continue;
+        }
+        if (f->limit > 0 && n >= (uint64_t)f->limit) break;  // :279-281
+        if (idx && n < cap) idx[n] = i;
+        n++;
+        offset++;
+    }
+    *count = n;
+    return TREAT_B200_OK;
+}
+
 // `treat norm` (cmd/treat/norm.go:25-73, cmd/treat/storage.go:801-878)
 int treat_b200_norm_default(const uint64_t *std_reads_per_sample, int32_t n_samples, double *norm)
 {
