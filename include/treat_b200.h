@@ -538,6 +538,16 @@ int treat_b200_search_records(const treat_b200_search *f, const treat_b200_recor
 /* The same for records resident in HBM (d_idx on the device); one stream synchronisation returns *count. */
 int treat_b200_search_device(treat_b200_ctx *ctx, const treat_b200_search *f, const treat_b200_record *d_rec, uint64_t N,
                              uint64_t *d_idx, uint64_t cap, uint64_t *count, void *stream);
+/* `treat search` output (cmd/treat/search.go:30-89) for the records idx[0 .. n) of one gene / sample (e.g. from
+ * treat_b200_search_records): the header line unless header == 0, then per record gene, sample, norm ("%.4f" of
+ * RoundPlus(Norm, 4); norm == NULL: 0), read_count, alt_editing ("0" or "A<k>"), has_mutation, edit_stop, junc_end,
+ * junc_len, junc_seq (the upper-cased window of the raw read), written by Go's encoding/csv rules (a field is quoted when
+ * it holds the separator, a quote, CR / LF or starts with a blank; quotes are doubled) with ',' (csv != 0) or a tab between
+ * the fields.  The --fasta form needs the stored fragments and stays with the caller's storage.  *out is malloc'ed
+ * (treat_b200_free). */
+int treat_b200_search_text(const char *gene, const char *sample, const treat_b200_record *rec, const double *norm, const uint8_t *seqs,
+                           const uint64_t *seq_off, const uint64_t *idx, uint64_t n, int32_t csv, int32_t header, char **out,
+                           size_t *out_len);
 /* cmd/treat/stats.go:62-137 (`treat stats`): the block ShowStats prints for one gene -- rule, name, totals, template
  * facts, the per-sample table -- from summary counters (treat_b200_get_summary, or their sum over GPUs / samples).
  * samples[i] / summaries[i]: one row per sample (each summary holds at least 14 counters); the gene totals are their

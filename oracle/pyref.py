@@ -463,3 +463,39 @@ def search(alns, offset=0, limit=0, **fields):  # :257-286, one sample's alignme
         count += 1
         off += 1
     return out
+
+
+# ---- `treat search` output (cmd/treat/search.go:30-89) through Go's encoding/csv writer ---------------------------------
+def _csv_field(f, comma):  # encoding/csv: Writer.fieldNeedsQuotes + the quoted form (UseCRLF false)
+    need = False
+    if f != "":
+        if f == "\\.":
+            need = True
+        elif any(c in f for c in ("\n", "\r", '"', comma)):
+            need = True
+        else:
+            need = f[0].isspace()  # unicode.IsSpace
+    if not need:
+        return f
+    return '"' + f.replace('"', '""') + '"'
+
+
+def round_plus(f, places):  # storage.go:190-198
+    import math
+    shift = math.pow(10, float(places))
+    return math.floor(f * shift + .5) / shift
+
+
+def search_text(gene, sample, alns, idxs, csv=False, header=True):
+    comma = "," if csv else "\t"
+    rows = []
+    if header:
+        rows.append(["gene", "sample", "norm", "read_count", "alt_editing", "has_mutation", "edit_stop", "junc_end", "junc_len", "junc_seq"])
+    for i in idxs:
+        a = alns[i]
+        alt = "%d" % a.AltEditing
+        if a.AltEditing != 0:
+            alt = "A%d" % a.AltEditing
+        rows.append([gene, sample, "%.4f" % round_plus(a.Norm, 4), "%d" % a.ReadCount, alt, "%d" % a.HasMutation, "%d" % a.EditStop,
+                     "%d" % a.JuncEnd, "%d" % a.JuncLen, a.JuncSeq])
+    return "".join(comma.join(_csv_field(f, comma) for f in r) + "\n" for r in rows)

@@ -224,6 +224,41 @@ def test_search_records_vs_oracle(examples):
             assert len(T.search_records(rec, all=True, has_alt=True)) > 0
 
 
+def test_search_text_vs_oracle_and_readme(examples):
+    """`treat search` rows (cmd/treat/search.go:30-89): the README's CSV block (README.rst:175-178) byte for byte, and tab /
+    comma output with norms, alt editing, mutants and names that need Go's csv quoting against the pure-Python restatement."""
+    pt = P.template_from_fasta(examples["templates.fa"], P.FORWARD, "T")
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    recs = P.read_fasta(examples["sample-1.fa"])
+    fb = T.FastaBatch.from_records(recs)
+    orec, _, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, want_ops=False)
+    rec = _oracle_record_as_product(orec)
+    idx = T.search_records(rec, limit=2)  # (the README's sample held other reads behind these two; examples/sample-1.fa has one more)
+    norm = T.normalize_records(rec, 1.0)
+    readme = ("gene,sample,norm,read_count,alt_editing,has_mutation,edit_stop,junc_end,junc_len,junc_seq\n"
+              "RPS12,sample-1,10.0000,10,0,0,137,143,6,ATATAATATTTTTG\n"
+              "RPS12,sample-1,9.0000,9,0,0,95,123,28,TTCGGTATTTGTTTTATGTTATTATATGAGTCCGCGATTGCCCAGCTCTG\n")
+    assert T.search_text("RPS12", "sample-1", rec, fb.seqs, fb.offsets, idx, norm, csv=True) == readme
+    recs = P.read_fasta(examples["clones.fa"]) + recs
+    fb = T.FastaBatch.from_records(recs)
+    for exclude in (False, True):
+        orec, _, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, exclude_snps=exclude, want_ops=False)
+        rec = _oracle_record_as_product(orec)
+        alns = [P.NewAlignment(P.Fragment(i, sq, P.FORWARD, "T"), pt, exclude) for i, sq in recs]
+        P.normalize_sample(alns, 100000.0 if not exclude else 4321.0987)
+        scale = T.norm_scale(sum(int(a.ReadCount) for a in alns if a.HasMutation == 0), 100000.0 if not exclude else 4321.0987)
+        norm = T.normalize_records(rec, scale)
+        for gene, sample in (("RPS12", "sample-1"), ("gene,with comma", " leading blank"), ('a"quote', "tab\there"), ("", "\\.")):
+            for kw in (dict(all=True), dict(all=True, has_alt=True), dict(has_mutation=True, limit=3)):
+                idx = T.search_records(rec, **kw)
+                assert idx.tolist() == P.search(alns, **kw)
+                for csv in (False, True):
+                    for header in (True, False):
+                        assert T.search_text(gene, sample, rec, fb.seqs, fb.offsets, idx, norm, csv=csv, header=header) == \
+                            P.search_text(gene, sample, alns, idx.tolist(), csv=csv, header=header), (gene, sample, kw, csv)
+    assert T.search_text("g", "s", rec, fb.seqs, fb.offsets, [], None, csv=True, header=False) == ""
+
+
 def test_mutant_report_vs_oracle(examples):
     """`treat mutant` (cmd/treat/mutant.go:55-110) from records + ops; ops here come from the oracle."""
     tm = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "T")

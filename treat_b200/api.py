@@ -25,7 +25,7 @@ from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, OPS_GAPPED_ONLY, RECORD_DT
 __all__ = [
     "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
     "NewTemplate", "NewTemplateFromFasta", "parseMergeCount", "PrintAlignment", "read_fasta", "TreatError",
-    "marshal_batch", "mutant_report", "DeviceGroup", "Comm", "norm_default", "norm_scale", "normalize_records", "search_records",
+    "marshal_batch", "mutant_report", "DeviceGroup", "Comm", "norm_default", "norm_scale", "normalize_records", "search_records", "search_text",
 ]
 
 
@@ -280,6 +280,25 @@ def search_records(rec: np.ndarray, **fields) -> np.ndarray:
     idx = np.zeros(max(len(rec), 1), dtype=np.uint64)
     check(lib().treat_b200_search_records(C.byref(f), rec.ctypes.data, len(rec), idx.ctypes.data, len(idx), C.byref(n)))
     return idx[: int(n.value)]
+
+
+def search_text(gene: str, sample: str, rec: np.ndarray, seqs: np.ndarray, seq_off: np.ndarray, idx, norm: np.ndarray = None,
+                csv: bool = False, header: bool = True) -> str:
+    """`treat search` output (cmd/treat/search.go:30-89) for the records idx of one gene / sample."""
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    nv = None if norm is None else np.ascontiguousarray(norm, dtype=np.float64)
+    dummy = np.zeros(1, np.uint8)
+    out, ln = C.c_void_p(), C.c_size_t()
+    check(lib().treat_b200_search_text(_b(gene), _b(sample), rec.ctypes.data, None if nv is None else nv.ctypes.data,
+                                       (seqs if seqs.size else dummy).ctypes.data_as(C.POINTER(C.c_uint8)), seq_off.ctypes.data,
+                                       idx.ctypes.data if idx.size else None, len(idx), int(csv), int(header), C.byref(out), C.byref(ln)))
+    try:
+        return C.string_at(out.value, ln.value).decode("latin-1")
+    finally:
+        lib().treat_b200_free(out)
 
 
 def norm_default(std_reads_per_sample) -> float:

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+#include <cmath>
 #include <string>
 
 #include "treat_host.hpp"
@@ -182,6 +184,76 @@ int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *s
     std::vector<uint8_t> b = a.MarshalBinary();
     if (out && cap) memcpy(out, b.data(), std::min(cap, b.size()));
     return (int64_t)b.size();
+}
+
+// `treat search` rows (cmd/treat/search.go:30-89) through Go's encoding/csv writer
+static void csv_field(std::string &out, const std::string &f, char comma)
+{
+    // encoding/csv Writer.fieldNeedsQuotes
+    bool quote = false;
+    if (!f.empty()) {
+        if (f == "\\.") quote = true;
+        for (char c : f)
+            if (c == '\n' || c == '\r' || c == '"' || c == comma) quote = true;
+        const unsigned char c0 = (unsigned char)f[0];
+        if (c0 == ' ' || (c0 >= '\t' && c0 <= '\r')) quote = true;                                                  // unicode.IsSpace, ASCII
+        if (c0 == 0xC2 && f.size() > 1 && ((unsigned char)f[1] == 0x85 || (unsigned char)f[1] == 0xA0)) quote = true;  // U+0085, U+00A0
+    }
+    if (!quote) {
+        out += f;
+        return;
+    }
+    out += '"';
+    for (char c : f) {
+        if (c == '"') out += "\"\"";
+        else out += c;
+    }
+    out += '"';
+}
+
+int treat_b200_search_text(const char *gene, const char *sample, const treat_b200_record *rec, const double *norm, const uint8_t *seqs,
+                           const uint64_t *seq_off, const uint64_t *idx, uint64_t n, int32_t csv, int32_t header, char **out,
+                           size_t *out_len)
+{
+    if (!gene || !sample || !out || !out_len || (n && (!rec || !idx || !seqs || !seq_off))) return TREAT_B200_ERR_INVALID;
+    const char comma = csv ? ',' : '\t';  // search.go:38-40
+    std::string text;
+    auto row = [&](const std::vector<std::string> &fields) {
+        for (size_t k = 0; k < fields.size(); k++) {
+            if (k) text += comma;
+            csv_field(text, fields[k], comma);
+        }
+        text += '\n';
+    };
+    if (header) row({"gene", "sample", "norm", "read_count", "alt_editing", "has_mutation", "edit_stop", "junc_end", "junc_len", "junc_seq"});
+    char buf[64];
+    for (uint64_t k = 0; k < n; k++) {
+        const uint64_t i = idx[k];
+        const treat_b200_record &a = rec[i];
+        std::vector<std::string> f;
+        f.emplace_back(gene);
+        f.emplace_back(sample);
+        const double v = norm ? norm[i] : 0.0;
+        snprintf(buf, sizeof buf, "%.4f", floor(v * 10000.0 + .5) / 10000.0);  // RoundPlus(a.Norm, 4), storage.go:190-198
+        f.emplace_back(buf);
+        f.emplace_back(std::to_string(a.read_count));
+        f.emplace_back(a.alt_editing ? "A" + std::to_string((int)a.alt_editing) : std::string("0"));  // search.go:58-61
+        f.emplace_back(std::to_string((int)a.has_mutation));
+        f.emplace_back(std::to_string(a.edit_stop));
+        f.emplace_back(std::to_string(a.junc_end));
+        f.emplace_back(std::to_string(a.junc_len));
+        std::string js((const char *)seqs + seq_off[i] + a.junc_seq_off, a.junc_seq_len);
+        for (char &c : js)
+            if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+        f.emplace_back(js);
+        row(f);
+    }
+    *out = (char *)malloc(text.size() + 1);
+    if (!*out) return TREAT_B200_ERR_NOMEM;
+    memcpy(*out, text.data(), text.size());
+    (*out)[text.size()] = 0;
+    *out_len = text.size();
+    return TREAT_B200_OK;
 }
 
 // SearchFields.HasMatch (cmd/treat/storage.go:162-188) + the alt-editing rule of Storage.Search (:269-272)
