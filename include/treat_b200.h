@@ -538,6 +538,15 @@ int treat_b200_search_records(const treat_b200_search *f, const treat_b200_recor
 /* The same for records resident in HBM (d_idx on the device); one stream synchronisation returns *count. */
 int treat_b200_search_device(treat_b200_ctx *ctx, const treat_b200_search *f, const treat_b200_record *d_rec, uint64_t N,
                              uint64_t *d_idx, uint64_t cap, uint64_t *count, void *stream);
+/* highChartHist (cmd/treat/handlers.go:162-299; the /data/es-hist, /data/jl-hist and /data/je-hist series of one sample): the
+ * Norm-weighted histogram of EditStop (which = 0), JuncLen (1) or JuncEnd (2) over the records the search fields match
+ * (limit and offset are ignored, :178-179), without the reads that sit at the template's edit stop with no junction
+ * (EditStop == tmpl_edit_stop && JuncLen == 0, :203-205).  out[v - lo] += Norm for v in [lo, hi], added in record order in
+ * float64 -- the reference's summation order within a sample, so the sums are its sums bit for bit.  (The device summary's
+ * histograms are the ReadCount-weighted, unfiltered form of the same three series: exact integers that can be reduced
+ * across GPUs; with Norm = scale * ReadCount they differ from these only in the rounding of the float sum.) */
+int treat_b200_hist_norm(const treat_b200_search *f, const treat_b200_record *rec, const double *norm, uint64_t N,
+                         int32_t tmpl_edit_stop, int32_t which, int32_t lo, int32_t hi, double *out);
 /* `treat search` output (cmd/treat/search.go:30-89) for the records idx[0 .. n) of one gene / sample (e.g. from
  * treat_b200_search_records): the header line unless header == 0, then per record gene, sample, norm ("%.4f" of
  * RoundPlus(Norm, 4); norm == NULL: 0), read_count, alt_editing ("0" or "A<k>"), has_mutation, edit_stop, junc_end,

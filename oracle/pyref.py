@@ -499,3 +499,18 @@ def search_text(gene, sample, alns, idxs, csv=False, header=True):
         rows.append([gene, sample, "%.4f" % round_plus(a.Norm, 4), "%d" % a.ReadCount, alt, "%d" % a.HasMutation, "%d" % a.EditStop,
                      "%d" % a.JuncEnd, "%d" % a.JuncLen, a.JuncSeq])
     return "".join(comma.join(_csv_field(f, comma) for f in r) + "\n" for r in rows)
+
+
+# ---- highChartHist (cmd/treat/handlers.go:162-299): one sample's series --------------------------------------------------
+def hist_norm(alns, which, tmpl_edit_stop, **fields):
+    """samples[key.Sample][f(a)] += a.Norm over Storage.Search's matches (Limit = Offset = 0), without the reads at the
+    template's edit stop that have no junction; which: 0 EditStop, 1 JuncLen, 2 JuncEnd.  Returns {value: sum}."""
+    fields = dict(fields, offset=0, limit=0)
+    out = {}
+    for i in search(alns, **fields):
+        a = alns[i]
+        if a.EditStop == tmpl_edit_stop and a.JuncLen == 0:
+            continue
+        v = (a.EditStop, a.JuncLen, a.JuncEnd)[which]
+        out[v] = out.get(v, 0.0) + a.Norm
+    return out

@@ -259,6 +259,44 @@ def test_search_text_vs_oracle_and_readme(examples):
     assert T.search_text("g", "s", rec, fb.seqs, fb.offsets, [], None, csv=True, header=False) == ""
 
 
+def test_hist_norm_vs_oracle(examples):
+    """The three histogram series of the web UI (highChartHist, cmd/treat/handlers.go:162-299) for one sample: Norm-weighted,
+    filtered like a search, summed in record order -- bit for bit against the pure-Python restatement; and the device
+    summary's ReadCount-weighted histograms are the unfiltered form of the same series."""
+    pt = P.template_from_fasta(examples["templates.fa"], P.FORWARD, "T")
+    om = O.NewTemplateFromFasta(examples["templates.fa"], O.FORWARD, "T")
+    recs = P.read_fasta(examples["clones.fa"]) + P.read_fasta(examples["sample-1.fa"])
+    recs = recs + [(i + "z", sq) for i, sq in recs[::2]]
+    fb = T.FastaBatch.from_records(recs)
+    orec, _, _ = O.align_batch(om, fb.seqs, fb.offsets, fb.read_counts, want_ops=False)
+    rec = _oracle_record_as_product(orec)
+    alns = [P.NewAlignment(P.Fragment(i, sq, P.FORWARD, "T"), pt, False) for i, sq in recs]
+    scale = P.normalize_sample(alns, 98765.4321)
+    norm = T.normalize_records(rec, scale)
+    for a, v in zip(alns, norm):  # mutants keep Norm 0 on both sides
+        assert (a.Norm if a.HasMutation == 0 else 0.0) == v
+    lo, hi = -1, om.Len() + 1
+    for kw in (dict(), dict(all=True), dict(has_mutation=True), dict(all=True, has_alt=True), dict(edit_stop=int(alns[0].EditStop))):
+        for which in (0, 1, 2):
+            got = T.hist_norm(rec, norm, om.EditStop, which, lo, hi, **kw)
+            want = P.hist_norm(alns, which, om.EditStop, **kw)
+            assert {v: got[v - lo] for v in range(lo, hi + 1) if got[v - lo] != 0.0} == {v: x for v, x in want.items() if x != 0.0}, (kw, which)
+    # every read, weighted by ReadCount: what the kernels accumulate (helpers.summary_from_records states it)
+    rc_norm = rec["read_count"].astype(np.float64)
+    summ = summary_from_records(rec, om.Len() - 1, 0, om.EditStop)
+    B = om.Len() + 2
+    for which in (0, 1, 2):
+        # reads without and with alt editing together = every read; values -2 .. B - 3 <-> the summary's B bins
+        tot = T.hist_norm(rec, rc_norm, om.EditStop, which, -2, B - 3, all=True, has_alt=False) + \
+            T.hist_norm(rec, rc_norm, om.EditStop, which, -2, B - 3, all=True, has_alt=True)
+        dev = summ[16 + which * B:16 + (which + 1) * B].astype(np.float64)
+        assert tot.sum() > 0
+        if which == 1:  # bin = JuncLen
+            assert np.array_equal(tot[2:], dev[:B - 2]) and dev[B - 2:].sum() == 0
+        else:           # bin = EditStop / JuncEnd - EditOffset + 2
+            assert np.array_equal(tot, dev)
+
+
 def test_mutant_report_vs_oracle(examples):
     """`treat mutant` (cmd/treat/mutant.go:55-110) from records + ops; ops here come from the oracle."""
     tm = T.NewTemplateFromFasta(examples["templates.fa"], T.FORWARD, "T")

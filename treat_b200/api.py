@@ -25,7 +25,7 @@ from .cabi import (EXCLUDE_SNPS, FORWARD, NO_SUMMARY, OPS_GAPPED_ONLY, RECORD_DT
 __all__ = [
     "FORWARD", "REVERSE", "Fragment", "Template", "Alignment", "Aligner", "FastaBatch", "NewFragment",
     "NewTemplate", "NewTemplateFromFasta", "parseMergeCount", "PrintAlignment", "read_fasta", "TreatError",
-    "marshal_batch", "mutant_report", "DeviceGroup", "Comm", "norm_default", "norm_scale", "normalize_records", "search_records", "search_text",
+    "marshal_batch", "mutant_report", "DeviceGroup", "Comm", "norm_default", "norm_scale", "normalize_records", "search_records", "search_text", "hist_norm",
 ]
 
 
@@ -299,6 +299,18 @@ def search_text(gene: str, sample: str, rec: np.ndarray, seqs: np.ndarray, seq_o
         return C.string_at(out.value, ln.value).decode("latin-1")
     finally:
         lib().treat_b200_free(out)
+
+
+def hist_norm(rec: np.ndarray, norm: np.ndarray, tmpl_edit_stop: int, which: int, lo: int, hi: int, **fields) -> np.ndarray:
+    """highChartHist (cmd/treat/handlers.go:162-299): Norm-weighted histogram of EditStop (0) / JuncLen (1) / JuncEnd (2) over the
+    matching records of one sample; out[v - lo] for v in [lo, hi]."""
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE)
+    norm = np.ascontiguousarray(norm, dtype=np.float64)
+    f = _search_fields(**fields)
+    out = np.zeros(hi - lo + 1, dtype=np.float64)
+    check(lib().treat_b200_hist_norm(C.byref(f), rec.ctypes.data, norm.ctypes.data, len(rec), int(tmpl_edit_stop), int(which), int(lo), int(hi),
+                                     out.ctypes.data))
+    return out
 
 
 def norm_default(std_reads_per_sample) -> float:

@@ -111,6 +111,7 @@ SIGNATURES = {
     "treat_b200_marshal_device": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64), _P]),
     "treat_b200_unmarshal_record": (C.c_int, [_P, _SZ, _P, C.POINTER(C.c_double), C.POINTER(_P)]),
     "treat_b200_search_records": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "treat_b200_hist_norm": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "treat_b200_search_text": (C.c_int, [C.c_char_p, C.c_char_p, _P, _P, _U8P, _P, _P, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_SZ)]),
     "treat_b200_search_device": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64), _P]),
     "treat_b200_norm_default": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double)]),

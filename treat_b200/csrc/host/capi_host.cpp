@@ -186,6 +186,24 @@ int64_t treat_b200_marshal_record(const treat_b200_record *rec, const uint8_t *s
     return (int64_t)b.size();
 }
 
+static bool search_match(const treat_b200_search &f, const treat_b200_record &a);
+
+// highChartHist (cmd/treat/handlers.go:162-299): samples[key.Sample][f(a)] += a.Norm over the matching alignments
+int treat_b200_hist_norm(const treat_b200_search *f, const treat_b200_record *rec, const double *norm, uint64_t N,
+                         int32_t tmpl_edit_stop, int32_t which, int32_t lo, int32_t hi, double *out)
+{
+    if (!f || (N && (!rec || !norm)) || !out || hi < lo || which < 0 || which > 2) return TREAT_B200_ERR_INVALID;
+    for (int64_t v = lo; v <= hi; v++) out[v - lo] = 0.0;
+    for (uint64_t i = 0; i < N; i++) {
+        const treat_b200_record &a = rec[i];
+        if (!search_match(*f, a)) continue;                                  // Storage.Search with Limit = Offset = 0
+        if (a.edit_stop == tmpl_edit_stop && a.junc_len == 0) continue;       // handlers.go:203-205
+        const int32_t v = which == 0 ? a.edit_stop : which == 1 ? a.junc_len : a.junc_end;
+        if (v >= lo && v <= hi) out[v - lo] += norm[i];
+    }
+    return TREAT_B200_OK;
+}
+
 // `treat search` rows (cmd/treat/search.go:30-89) through Go's encoding/csv writer
 static void csv_field(std::string &out, const std::string &f, char comma)
 {
