@@ -7,7 +7,8 @@
 A "step" is one pass of the hot path (NewFragment + NewAlignment for every read: 48-byte records
 + 2-bit traceback ops) over one batch of synthetic RPS12-shaped reads per GPU (SURVEY.md 8d,
 BASELINE.json configs[2]; weak scaling: every rank aligns its own --reads reads, no data-path
-collective, one all-reduce of the summary counters per step).
+collective: one all-reduce of the summary counters per job, issued behind the last timed step inside the timed region;
+`nccl.every_step` times the stricter form with an all-reduce behind every step).
 
 One JSON line on rank 0:
   value      whole-job reads/s with the raw reads already resident in HBM (device-timed, max over ranks)
